@@ -1,0 +1,57 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement (oracle) of paragraph's read->graph
+ * alignment path.  Not part of the product: only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library.
+ *
+ * Parity status: PINNED.  pg_oracle.c is checked (tests/test_oracle.py) against
+ *   - the reference's own golden vectors (src/c++/test/test_paragraph_parts.cpp:113-144),
+ *   - oracle/_ref/libpgref.so = the unmodified reference sources compiled here
+ *     (cell-by-cell mH/mE/mF, best cell, CIGAR, uniqueness, strand) on seeded fuzz inputs,
+ *   - the committed fixtures under tests/golden/ generated from that library.
+ */
+#ifndef PG_ORACLE_H
+#define PG_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGO_AF_CIGAR 1u
+#define PGO_AF_BOTH_STRANDS 2u
+#define PGO_AF_REVERSE_GRAPH 4u
+#define PGO_AF_ALL 0xFFFFFFFFu
+
+#define PGO_OK 0
+#define PGO_E_BYTE_OVERFLOW (-2) /* reference would fall back to 16-bit mode (gssw.c:4001-4013) */
+#define PGO_E_ARG (-1)
+
+typedef struct pgo_graph pgo_graph;
+
+/* Nodes must be in topological order (edge from < to), as graphtools::Graph enforces
+ * (graph-tools src/graphcore/Graph.cpp:113-116).  Sequences are upper-cased on load
+ * (src/c++/lib/grm/GraphAligner.cpp:126,138); predecessor lists are ascending ids (:147-157). */
+pgo_graph* pgo_graph_create(int n_nodes, const char* seq_blob, const int32_t* seq_off, int n_edges,
+                            const int32_t* efrom, const int32_t* eto);
+void pgo_graph_destroy(pgo_graph* g);
+
+/* GraphAligner::alignRead (GraphAligner.cpp:308-404).
+ * out6 = {graph_pos, score, unique, mapq, is_graph_reverse_strand, cigar_strlen};
+ * out_bases (len bytes, may be NULL) receives the possibly reverse-complemented bases. */
+int pgo_align_read(const pgo_graph* g, const char* bases, int len, int is_reverse_strand, unsigned flags,
+                   int32_t* out6, char* out_bases, char* cigar, int cigar_cap);
+
+int pgo_align_batch(const pgo_graph* g, int n_reads, const char* bases_blob, const int32_t* read_off,
+                    const uint8_t* is_rev, unsigned flags, int32_t* out6, char* out_bases_blob, char* cigars,
+                    int cigar_stride);
+
+/* One gssw_graph_fill + gssw_graph_trace_back on the forward (reversed_graph=0) or reversed
+ * graph.  `read` must already be upper-case.  node_stats[4*n] = {score1, ref_end1, read_end1, 1};
+ * mats (may be NULL) = per node mH,mE,mF (len*L bytes each); res3 = {max_node, position, score};
+ * multi (may be NULL) receives alignsEndAtMultNodes (GraphAligner.cpp:170-212). */
+int pgo_fill_trace(const pgo_graph* g, int reversed_graph, const char* read, int L, int32_t* node_stats,
+                   uint8_t* mats, int32_t* res3, int32_t* multi, char* cigar, int cigar_cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,231 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes bindings for oracle/_ref/libpgref.so (the unmodified
+reference sources compiled by oracle/Makefile) and oracle/liboracle.so (the plain-C
+restatement, oracle/pg_oracle.c).  Only tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs may import this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(HERE, "_ref", "libpgref.so")
+ORACLE_SO = os.path.join(HERE, "liboracle.so")
+
+AF_CIGAR, AF_BOTH_STRANDS, AF_REVERSE_GRAPH, AF_ALL = 1, 2, 4, 0xFFFFFFFF
+CIGAR_STRIDE = 1024
+
+
+def build(ref=True):
+    """make liboracle.so (+ _ref/libpgref.so when /root/reference is present)."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "all" if ref else os.path.join(HERE, "liboracle.so")])
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def pack_graph(node_seqs, edges):
+    """-> (seq_blob bytes, seq_off int32[n+1], efrom int32[], eto int32[])"""
+    blob = "".join(node_seqs).encode("latin-1")
+    off = np.zeros(len(node_seqs) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(s) for s in node_seqs])
+    ef = np.array([e[0] for e in edges], dtype=np.int32)
+    et = np.array([e[1] for e in edges], dtype=np.int32)
+    return blob, off, ef, et
+
+
+def pack_reads(reads):
+    blob = "".join(reads).encode("latin-1")
+    off = np.zeros(len(reads) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(s) for s in reads])
+    return blob, off
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        lib = C.CDLL(REF_SO)
+        lib.pgref_aligner_create.restype = C.c_void_p
+        lib.pgref_aligner_create.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int,
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pgref_aligner_destroy.argtypes = [C.c_void_p]
+        lib.pgref_aligner_align.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_uint,
+                                            C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int]
+        lib.pgref_align_batch.restype = C.c_int
+        lib.pgref_align_batch.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int,
+                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                          C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8),
+                                          C.c_uint, C.c_int, C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int]
+        lib.pgref_gssw_create.restype = C.c_void_p
+        lib.pgref_gssw_create.argtypes = lib.pgref_aligner_create.argtypes
+        lib.pgref_gssw_destroy.argtypes = [C.c_void_p]
+        lib.pgref_gssw_fill_trace.restype = C.c_int
+        lib.pgref_gssw_fill_trace.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8),
+                                              C.POINTER(C.c_int32), C.c_char_p, C.c_int]
+        _ref = lib
+    return _ref
+
+
+def _result_dict(o, bases, cigar):
+    return dict(pos=int(o[0]), score=int(o[1]), unique=bool(o[2]), mapq=int(o[3]),
+                graph_reverse=bool(o[4]), bases=bases, cigar=cigar)
+
+
+def ref_align_batch(node_seqs, edges, reads, is_rev=None, flags=AF_ALL, threads=1):
+    """Run the reference GraphAligner::alignRead over a batch. Returns list of dicts."""
+    lib = ref_lib()
+    blob, off, ef, et = pack_graph(node_seqs, edges)
+    rblob, roff = pack_reads(reads)
+    n = len(reads)
+    out = np.zeros((n, 6), dtype=np.int32)
+    ob = C.create_string_buffer(max(1, len(rblob)))
+    cg = C.create_string_buffer(max(1, n * CIGAR_STRIDE))
+    rv = None if is_rev is None else np.asarray(is_rev, dtype=np.uint8)
+    lib.pgref_align_batch(len(node_seqs), blob, _p(off, C.c_int32), len(edges), _p(ef, C.c_int32), _p(et, C.c_int32),
+                          n, rblob, _p(roff, C.c_int32), None if rv is None else _p(rv, C.c_uint8),
+                          flags & 0xFFFFFFFF, threads, _p(out, C.c_int32), ob, cg, CIGAR_STRIDE)
+    res = []
+    raw = ob.raw
+    for i in range(n):
+        c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
+        res.append(_result_dict(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
+    return res
+
+
+class RefGssw:
+    """Raw gssw fill + traceback with matrices (reference external/gssw/gssw.c)."""
+
+    def __init__(self, node_seqs, edges):
+        self.lib = ref_lib()
+        self.node_seqs = list(node_seqs)
+        blob, off, ef, et = pack_graph(node_seqs, edges)
+        self.h = self.lib.pgref_gssw_create(len(node_seqs), blob, _p(off, C.c_int32), len(edges),
+                                            _p(ef, C.c_int32), _p(et, C.c_int32))
+
+    def fill_trace(self, read, want_mats=True):
+        L = len(read)
+        n = len(self.node_seqs)
+        stats = np.zeros((n, 4), dtype=np.int32)
+        tot = sum(len(s) for s in self.node_seqs) * L * 3
+        mats = np.zeros(max(1, tot), dtype=np.uint8) if want_mats else None
+        res = np.zeros(3, dtype=np.int32)
+        cg = C.create_string_buffer(4096)
+        self.lib.pgref_gssw_fill_trace(self.h, read.encode("latin-1"), _p(stats, C.c_int32),
+                                       _p(mats, C.c_uint8) if want_mats else None, _p(res, C.c_int32), cg, 4096)
+        out = dict(stats=stats, max_node=int(res[0]), pos=int(res[1]), score=int(res[2]), cigar=cg.value.decode())
+        if want_mats:
+            ms, o = [], 0
+            for s in self.node_seqs:
+                sz = len(s) * L
+                ms.append(tuple(mats[o + k * sz:o + (k + 1) * sz].reshape(len(s), L) for k in range(3)))
+                o += 3 * sz
+            out["mats"] = ms
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.pgref_gssw_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+# ---------------------------------------------------------------- plain-C restatement (oracle/pg_oracle.c)
+_orc = None
+
+
+def oracle_lib():
+    global _orc
+    if _orc is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        lib = C.CDLL(ORACLE_SO)
+        lib.pgo_graph_create.restype = C.c_void_p
+        lib.pgo_graph_create.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.pgo_graph_destroy.argtypes = [C.c_void_p]
+        lib.pgo_align_read.restype = C.c_int
+        lib.pgo_align_read.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_uint,
+                                       C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int]
+        lib.pgo_align_batch.restype = C.c_int
+        lib.pgo_align_batch.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8),
+                                        C.c_uint, C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int]
+        lib.pgo_fill_trace.restype = C.c_int
+        lib.pgo_fill_trace.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.c_char_p, C.c_int]
+        _orc = lib
+    return _orc
+
+
+class OracleGraph:
+    def __init__(self, node_seqs, edges):
+        self.lib = oracle_lib()
+        self.node_seqs = list(node_seqs)
+        blob, off, ef, et = pack_graph(node_seqs, edges)
+        self.h = self.lib.pgo_graph_create(len(node_seqs), blob, _p(off, C.c_int32), len(edges),
+                                           _p(ef, C.c_int32), _p(et, C.c_int32))
+        if not self.h:
+            raise ValueError("oracle: bad graph")
+
+    def align_batch(self, reads, is_rev=None, flags=AF_ALL):
+        rblob, roff = pack_reads(reads)
+        n = len(reads)
+        out = np.zeros((n, 6), dtype=np.int32)
+        ob = C.create_string_buffer(max(1, len(rblob)))
+        cg = C.create_string_buffer(max(1, n * CIGAR_STRIDE))
+        rv = None if is_rev is None else np.asarray(is_rev, dtype=np.uint8)
+        rc = self.lib.pgo_align_batch(self.h, n, rblob, _p(roff, C.c_int32),
+                                      None if rv is None else _p(rv, C.c_uint8), flags & 0xFFFFFFFF,
+                                      _p(out, C.c_int32), ob, cg, CIGAR_STRIDE)
+        if rc != 0:
+            raise RuntimeError("oracle: pgo_align_batch rc=%d" % rc)
+        res, raw = [], ob.raw
+        for i in range(n):
+            c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
+            res.append(_result_dict(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
+        return res
+
+    def fill_trace(self, read, reversed_graph=False, want_mats=True):
+        L = len(read)
+        seqs = self.node_seqs[::-1] if reversed_graph else self.node_seqs
+        n = len(seqs)
+        stats = np.zeros((n, 4), dtype=np.int32)
+        tot = sum(len(s) for s in seqs) * L * 3
+        mats = np.zeros(max(1, tot), dtype=np.uint8) if want_mats else None
+        res = np.zeros(3, dtype=np.int32)
+        multi = np.zeros(1, dtype=np.int32)
+        cg = C.create_string_buffer(4096)
+        rc = self.lib.pgo_fill_trace(self.h, 1 if reversed_graph else 0, read.encode("latin-1"), L,
+                                     _p(stats, C.c_int32), _p(mats, C.c_uint8) if want_mats else None,
+                                     _p(res, C.c_int32), _p(multi, C.c_int32), cg, 4096)
+        if rc < 0:
+            raise RuntimeError("oracle: pgo_fill_trace rc=%d" % rc)
+        out = dict(stats=stats, max_node=int(res[0]), pos=int(res[1]), score=int(res[2]), multi=bool(multi[0]),
+                   cigar=cg.value.decode())
+        if want_mats:
+            ms, o = [], 0
+            for s in seqs:
+                sz = len(s) * L
+                ms.append(tuple(mats[o + k * sz:o + (k + 1) * sz].reshape(len(s), L) for k in range(3)))
+                o += 3 * sz
+            out["mats"] = ms
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.pgo_graph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
