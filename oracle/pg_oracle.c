@@ -344,6 +344,75 @@ static int fill_node_byte(const int8_t* ref, int refLen, int L, const uint8_t* p
     return out->score1;
 }
 
+/* ------------------------------------------------------------------ model variants (not the reference)
+ * The CUDA path does not restate Farrar striping.  It computes the plain affine-gap recurrence
+ *     t = max(Hdiag + s, E, 0);  H = max(t, F);  F' = max(F - ge, t - go);
+ *     variant 1 (textbook):  E' = max(E - ge, H - go)
+ *     variant 2 (kernel):    E' = max(E - ge, t - go)      -- never opens a deletion out of an insertion
+ * and claims that H is cell-identical to the reference's mH and that the reference's traceback
+ * takes the same decisions on these E/F as on its own striped mE/mF ("equivalence").
+ * pgo_set_fill_variant() lets tests/ run the restated traceback over those matrices and compare
+ * with oracle/_ref; variant 0 (default) is the faithful restatement. */
+static int g_fill_variant = 0;
+void pgo_set_fill_variant(int v) { g_fill_variant = v; }
+
+static int fill_node_model(const int8_t* ref, int refLen, const char* read, int L, const uint8_t* seedH,
+                           const uint8_t* seedE, naln* out)
+{
+    const int segLen = (L + 15) / 16;
+    const size_t vb = (size_t)segLen * NL; /* >= L: seeds are kept linear (row p at index p) */
+    int* Hp = (int*)calloc((size_t)L + 1, sizeof(int));
+    int* Hc = (int*)calloc((size_t)L + 1, sizeof(int));
+    int* E = (int*)calloc((size_t)L + 1, sizeof(int));
+    out->mH = (uint8_t*)calloc((size_t)refLen * L + 1, 1);
+    out->mE = (uint8_t*)calloc((size_t)refLen * L + 1, 1);
+    out->mF = (uint8_t*)calloc((size_t)refLen * L + 1, 1);
+    out->seedH = (uint8_t*)calloc(vb, 1);
+    out->seedE = (uint8_t*)calloc(vb, 1);
+    for (int p = 0; p < L; ++p)
+    {
+        Hp[p] = seedH ? seedH[p] : 0;
+        E[p] = seedE ? seedE[p] : 0;
+    }
+    int max = 0, end_ref = -1, end_read = L - 1;
+    for (int i = 0; i < refLen; ++i)
+    {
+        int F = 0, colmax = 0;
+        for (int p = 0; p < L; ++p)
+        {
+            int s = sub_score(ref[i], nt_code((unsigned char)read[p]));
+            int t = (p > 0 ? Hp[p - 1] : 0) + s;
+            if (E[p] > t) t = E[p];
+            if (t < 0) t = 0;
+            int h = t > F ? t : F;
+            Hc[p] = h;
+            out->mH[(size_t)i * L + p] = (uint8_t)h;
+            out->mE[(size_t)i * L + p] = (uint8_t)(E[p] > 0 ? E[p] : 0);
+            out->mF[(size_t)i * L + p] = (uint8_t)(F > 0 ? F : 0);
+            if (h > colmax) colmax = h;
+            int open = (g_fill_variant == 1 ? h : t) - GAP_OPEN;
+            E[p] = E[p] - GAP_EXT > open ? E[p] - GAP_EXT : open;
+            F = F - GAP_EXT > t - GAP_OPEN ? F - GAP_EXT : t - GAP_OPEN;
+        }
+        if (colmax > max) /* first column reaching a new maximum; smallest row in it */
+        {
+            max = colmax;
+            end_ref = i;
+            for (int p = L - 1; p >= 0; --p)
+                if (Hc[p] == max) end_read = p;
+        }
+        int* sw = Hp; Hp = Hc; Hc = sw;
+    }
+    for (int p = 0; p < L; ++p)
+    {
+        out->seedH[p] = (uint8_t)Hp[p];
+        out->seedE[p] = (uint8_t)(E[p] > 0 ? E[p] : 0);
+    }
+    free(Hp); free(Hc); free(E);
+    out->score1 = max; out->ref_end1 = end_ref; out->read_end1 = end_read;
+    return max >= 251 ? 255 : max;
+}
+
 static void naln_free(naln* a, int n)
 {
     for (int i = 0; i < n; ++i)
@@ -385,7 +454,8 @@ static int graph_fill(const g1* g, const char* read, int L, naln** out, int* max
                 sE[x] = max8(sE[x], p->seedE[x]);
             }
         }
-        int sc = fill_node_byte(g->num[i], g->len[i], L, prof, sH, sE, &a[i]);
+        int sc = g_fill_variant ? fill_node_model(g->num[i], g->len[i], read, L, sH, sE, &a[i])
+                                : fill_node_byte(g->num[i], g->len[i], L, prof, sH, sE, &a[i]);
         if (sc == 255)
         {
             rc = PGO_E_BYTE_OVERFLOW; /* gssw.c:4001-4013 would redo the graph in 16-bit mode */

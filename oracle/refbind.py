@@ -164,8 +164,14 @@ def oracle_lib():
         lib.pgo_fill_trace.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                        C.c_char_p, C.c_int]
+        lib.pgo_set_fill_variant.argtypes = [C.c_int]
         _orc = lib
     return _orc
+
+
+def set_fill_variant(v):
+    """0 = faithful restatement; 1 = textbook E; 2 = kernel recurrence (see pg_oracle.c)."""
+    oracle_lib().pgo_set_fill_variant(int(v))
 
 
 class OracleGraph:
