@@ -1,0 +1,893 @@
+// paragraph_b200 -- core of the read->graph alignment path, shared verbatim between the sm_100a kernels
+// (pg_kernels.cu) and the host-side lane emulator used by the CPU test-suite (tests/emu/pg_emu.cpp).
+//
+// What is computed (reference: external/gssw/gssw.c gssw_graph_fill / gssw_graph_trace_back driven by
+// src/c++/lib/grm/GraphAligner.cpp:214-404):
+//   * affine-gap local Smith-Waterman of a read against the topologically ordered nodes of a variant
+//     graph; column -1 of a node = element-wise max over the last columns of its predecessors
+//     (gssw.c:3897-3931), gaps in the reference do not cross nodes (gssw.h:61-65);
+//   * best cell = first cell in (node, column, row) order holding the global maximum (gssw.c:378-386,
+//     446-454, 4015-4018); uniqueness = the maximum occurs in exactly one node (GraphAligner.cpp:170-212);
+//   * traceback with the reference's positional decision order (gssw.c:1112-1818, 2621-3537).
+//
+// How it is laid out on a warp ("wavefront"): lane t owns read rows [R*t, R*t+R); at step k it processes
+// graph column q = k - t, so the vertical dependency (F, and the diagonal into the lane's first row)
+// comes from lane t-1's previous step through one warp shuffle.  Two alignment problems that share the
+// column sequence are packed in the two int16 halves of every register (forward read / reverse-
+// complemented read), so the recurrence runs on the packed-int16 DPX instructions (VIADDMNMX.S16x2,
+// VIMNMX3.S16x2).  Recurrence per cell (d = H of the previous column one row up, s = substitution score):
+//     t  = max(d + s, E, 0)         E' = max(E - ge, t - go)
+//     H  = max(t, F)                F' = max(F - ge, t - go)      (F runs down the rows of one column)
+// H is cell-identical to gssw's mH; E/F differ from gssw's striped mE/mF only in cells where the
+// traceback cannot look (DESIGN.md "equivalence", proven by tests/test_model_equivalence.py).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PG_HD __host__ __device__ __forceinline__
+#define PG_UNROLL _Pragma("unroll")
+#else
+#define PG_HD inline
+#define PG_UNROLL
+#endif
+
+namespace pg
+{
+
+constexpr int GAP_OPEN = 6; // GraphAligner.cpp:231
+constexpr int GAP_EXT = 1;  // GraphAligner.cpp:232
+constexpr int NEG = -16384; // substitution score of sentinel columns / padded rows
+constexpr int CK = 16;      // checkpoint interval = traceback tile size, in wavefront steps
+constexpr int SENT = 32;    // sentinel columns (code 5) before and after every column sequence
+constexpr int NCODE = 6;    // A C G T other sentinel
+constexpr int MAX_READ_LEN = 250; // longer reads leave gssw's 8-bit mode (gssw.c:380) -> rejected, see DESIGN.md
+
+// ---------------------------------------------------------------------------------------------
+// packed int16x2 arithmetic: DPX on the device, plain C on the host (emulator)
+// ---------------------------------------------------------------------------------------------
+PG_HD uint32_t pk(int lo, int hi) { return (uint32_t)(uint16_t)(int16_t)lo | ((uint32_t)(uint16_t)(int16_t)hi << 16); }
+PG_HD int lo16(uint32_t x) { return (int)(int16_t)(uint16_t)(x & 0xffffu); }
+PG_HD int hi16(uint32_t x) { return (int)(int16_t)(uint16_t)(x >> 16); }
+PG_HD int half16(uint32_t x, int h) { return h ? hi16(x) : lo16(x); }
+PG_HD int imax0(int a) { return a > 0 ? a : 0; }
+
+#if defined(__CUDA_ARCH__)
+PG_HD uint32_t addmax_relu2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }
+PG_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+PG_HD uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+PG_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+PG_HD uint32_t add2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+#else
+PG_HD int imax_(int a, int b) { return a > b ? a : b; }
+PG_HD uint32_t addmax_relu2(uint32_t a, uint32_t b, uint32_t c)
+{
+    return pk(imax_(imax_(lo16(a) + lo16(b), lo16(c)), 0), imax_(imax_(hi16(a) + hi16(b), hi16(c)), 0));
+}
+PG_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c)
+{
+    return pk(imax_(lo16(a) + lo16(b), lo16(c)), imax_(hi16(a) + hi16(b), hi16(c)));
+}
+PG_HD uint32_t max2(uint32_t a, uint32_t b) { return pk(imax_(lo16(a), lo16(b)), imax_(hi16(a), hi16(b))); }
+PG_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return max2(max2(a, b), c); }
+PG_HD uint32_t add2(uint32_t a, uint32_t b) { return pk(lo16(a) + lo16(b), hi16(a) + hi16(b)); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// sequence coding
+// ---------------------------------------------------------------------------------------------
+// gssw_create_nt_table (gssw.c:4206-4220): A0 C1 G2 T3, 'U' -> 0 (sic), everything else 4.
+PG_HD int nt_code(uint8_t c)
+{
+    switch (c)
+    {
+    case 'A': case 'a': case 'U': case 'u': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 4;
+    }
+}
+// std::toupper in the "C" locale (common/StringUtil.hh:178 via GraphAligner.cpp:218)
+PG_HD uint8_t to_upper(uint8_t c) { return (c >= 'a' && c <= 'z') ? (uint8_t)(c - 32) : c; }
+// graphtools complementBase: case-sensitive, anything but ACGT -> 'N' (SequenceOperations.cpp:66-81)
+PG_HD uint8_t complement_base(uint8_t c)
+{
+    switch (c)
+    {
+    case 'A': return 'T';
+    case 'C': return 'G';
+    case 'G': return 'C';
+    case 'T': return 'A';
+    default: return 'N';
+    }
+}
+// gssw_create_score_matrix(1, 4) (gssw.c:4188-4204)
+PG_HD int sub_score(int a, int b) { return (a == 4 || b == 4) ? 0 : (a == b ? 1 : -4); }
+
+// The four strings GraphAligner::alignRead aligns (GraphAligner.cpp:315-337), by (graph orientation o,
+// packed half h), as the character the reference would see at row j after its toUpper():
+//   o=0,h=0: bases                      o=0,h=1: reverseComplement(bases)
+//   o=1,h=0: reverse(bases)             o=1,h=1: reverseComplement(reverse(bases)) = complement(bases)
+PG_HD uint8_t read_char(const uint8_t* bases, int L, int o, int h, int j)
+{
+    const bool rev = (o == 0) ? (h == 1) : (h == 0);
+    const uint8_t c = bases[rev ? (L - 1 - j) : j];
+    return to_upper(h ? complement_base(c) : c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// graph view (one orientation of one site); all arrays live in device (or emulator) memory
+// ---------------------------------------------------------------------------------------------
+struct GraphView
+{
+    const uint8_t* codes;      // codes[-SENT .. G+SENT): column code 0..4, 5 outside [0,G)
+    const int32_t* node_start; // [n_nodes] first column of each node (nodes concatenated in id order)
+    const int32_t* node_len;   // [n_nodes]
+    const int32_t* pred_ptr;   // [n_nodes+1] CSR of predecessor ids, ascending (std::set order, GraphAligner.cpp:147)
+    const int32_t* pred_idx;
+    int32_t n_nodes;
+    int32_t G; // total number of columns
+};
+
+// Device-resident description of one site (graph), both orientations (built by pg_host.hpp):
+//   bytes blob: per orientation [SENT sentinels][G column codes][SENT sentinels]; forward orientation also the
+//               G upper-cased graph characters (for the M/X/N decision, gssw.c:1601-1622);
+//   ints blob : per orientation node_start[n], node_len[n], pred_ptr[n+1], pred_idx[n_edges].
+// Orientation 1 is graphtools::reverseGraph (GraphOperations.cpp:38-60): node i -> n-1-i, sequences reversed,
+// edges flipped -- its column sequence is the forward one read backwards.
+struct SiteDev
+{
+    int32_t n_nodes, G, n_edges;
+    int32_t codes_off[2]; // byte offset of column 0 (sentinels precede it)
+    int32_t chars_off;    // byte offset of the forward graph characters
+    int32_t tab_off[2];   // int offset of the orientation's tables
+};
+
+PG_HD GraphView make_view(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, int o)
+{
+    GraphView g;
+    g.codes = bytes + sd.codes_off[o];
+    const int32_t* t = ints + sd.tab_off[o];
+    g.node_start = t;
+    g.node_len = t + sd.n_nodes;
+    g.pred_ptr = t + 2 * sd.n_nodes;
+    g.pred_idx = t + 3 * sd.n_nodes + 1;
+    g.n_nodes = sd.n_nodes;
+    g.G = sd.G;
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-lane wavefront state
+// ---------------------------------------------------------------------------------------------
+template <int R> struct Lane
+{
+    uint32_t Hp[R];    // H of the previous column, this lane's rows
+    uint32_t E[R];     // E entering the next column
+    uint32_t hupPrev;  // H (bottom row of lane t-1) received at the previous step = this step's diagonal
+    uint32_t hbotLast; // H of this lane's bottom row at the column just processed (to send down)
+    uint32_t foutLast; // F leaving this lane's bottom row at the column just processed (to send down)
+};
+
+// words per lane in a checkpoint / in a saved node last column
+template <int R> struct Sizes
+{
+    static constexpr int CKW = 2 * R + 2;  // Hp[R], E[R], hupPrev, foutLast   (hbotLast == Hp[R-1])
+    static constexpr int LASTW = 3 * R;    // node last column: H[R], E leaving it [R] (the seed), E entering it [R]
+    static constexpr int ROWS = 32 * R;
+};
+
+template <int R> PG_HD void lane_zero(Lane<R>& s)
+{
+    for (int r = 0; r < R; ++r)
+    {
+        s.Hp[r] = 0;
+        s.E[r] = 0;
+    }
+    s.hupPrev = 0;
+    s.hbotLast = 0;
+    s.foutLast = 0;
+}
+
+// One wavefront step of one lane.  recvH/recvF = hbotLast/foutLast of lane t-1 after ITS previous step
+// (zeros for lane 0).  prof = this warp's profile, word (c*R + r)*32 + lane = packed score of column code c
+// against this lane's row r.  If KEEP, the values the traceback needs are returned per row:
+// Hc = H(i,j), Ec = E(i,j) as used for H (gssw mE), Fc = F(i,j) as used for H (gssw mF).
+// Returns max over this lane's rows of t (== max of H: an F-derived H never sets a maximum).
+template <int R, bool KEEP>
+PG_HD uint32_t lane_step(Lane<R>& s, uint32_t recvH, uint32_t recvF, const uint32_t* prof, int code, int lane,
+                         uint32_t* Hc, uint32_t* Ec, uint32_t* Fc)
+{
+    const uint32_t mGO = pk(-GAP_OPEN, -GAP_OPEN), mGE = pk(-GAP_EXT, -GAP_EXT);
+    const uint32_t* p = prof + (code * R) * 32 + lane;
+    uint32_t d = s.hupPrev; // diagonal for row 0
+    s.hupPrev = recvH;
+    uint32_t F = recvF;
+    uint32_t m = 0;
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+    {
+        const uint32_t sc = p[r * 32];
+        const uint32_t e = s.E[r];
+        const uint32_t t = addmax_relu2(d, sc, e);
+        const uint32_t tg = add2(t, mGO);
+        const uint32_t h = max2(t, F);
+        if (KEEP)
+        {
+            Hc[r] = h;
+            Ec[r] = e;
+            Fc[r] = F;
+        }
+        s.E[r] = addmax2(e, mGE, tg);
+        F = addmax2(F, mGE, tg);
+        d = s.Hp[r];
+        s.Hp[r] = h;
+        m = max2(m, t);
+    }
+    s.hbotLast = s.Hp[R - 1];
+    s.foutLast = F;
+    return m;
+}
+
+// Build this lane's part of the warp profile: rows [R*lane, R*lane+R) x 6 column codes, both halves.
+// Rows >= L and the sentinel code get NEG so that they can never reach a maximum (DESIGN.md "padding").
+template <int R> PG_HD void build_profile(uint32_t* prof, const uint8_t* bases, int L, int orient, int lane)
+{
+    for (int r = 0; r < R; ++r)
+    {
+        const int j = R * lane + r;
+        int c0 = -1, c1 = -1;
+        if (j < L)
+        {
+            c0 = nt_code(read_char(bases, L, orient, 0, j));
+            c1 = nt_code(read_char(bases, L, orient, 1, j));
+        }
+        for (int c = 0; c < NCODE; ++c)
+        {
+            const int s0 = (c0 < 0 || c == 5) ? NEG : sub_score(c, c0);
+            const int s1 = (c1 < 0 || c == 5) ? NEG : sub_score(c, c1);
+            prof[(c * R + r) * 32 + lane] = pk(s0, s1);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-lane bookkeeping around the step: which node the lane is in, node maxima, node boundaries
+// ---------------------------------------------------------------------------------------------
+constexpr int COLS_INF = 0x3fffffff;
+
+struct LaneCtl
+{
+    int node;      // node the lane is currently in (n_nodes once past the end)
+    int colsLeft;  // columns of that node still to process, counted at the top of a step (0 -> node just ended)
+    uint32_t Mnode; // packed maximum of t over this lane's rows within the current node
+    int first[2];  // wavefront step at which Mnode's half first reached its current value
+};
+
+// Control state of `lane` at the top of step k0, before the node event of that step has run.
+PG_HD void ctl_at_step(LaneCtl& c, const GraphView& g, int k0, int lane)
+{
+    const int q = k0 - lane; // column about to be processed
+    c.Mnode = 0;
+    c.first[0] = c.first[1] = 0;
+    if (q <= 0)
+    {
+        c.node = 0;
+        c.colsLeft = g.node_len[0] - q;
+        return;
+    }
+    if (q >= g.G)
+    {
+        c.node = (q == g.G) ? g.n_nodes - 1 : g.n_nodes;
+        c.colsLeft = (q == g.G) ? 0 : COLS_INF;
+        return;
+    }
+    int n = 0;
+    while (q >= g.node_start[n] + g.node_len[n])
+        ++n;
+    if (q == g.node_start[n]) // first column of node n > 0: node n-1 has just ended, its event is pending
+    {
+        c.node = n - 1;
+        c.colsLeft = 0;
+    }
+    else
+    {
+        c.node = n;
+        c.colsLeft = g.node_start[n] + g.node_len[n] - q;
+    }
+}
+
+PG_HD void track_max(LaneCtl& c, uint32_t m, int k)
+{
+    const uint32_t nm = max2(c.Mnode, m);
+    if (nm != c.Mnode)
+    {
+        if (lo16(nm) != lo16(c.Mnode))
+            c.first[0] = k;
+        if (hi16(nm) != hi16(c.Mnode))
+            c.first[1] = k;
+        c.Mnode = nm;
+    }
+}
+
+// Node boundary handling at the top of a step (rare, per lane: lanes reach a boundary at different steps).
+//   FILL = true  (fill kernel): save the finished node's last column as seed (seedS, warp-private shared
+//                memory [node][2R][32]) and, for forward-graph tasks (save_trace), to lastG for the
+//                traceback; save the node maximum (infoG); then load the next node's seed.
+//   FILL = false (tile recomputation in the traceback kernel): only load the next node's seed, from lastG.
+// Seed of a node = element-wise max over its predecessors' last columns (gssw_create_seed_byte,
+// gssw.c:3897-3931), zeros for a source; if the only predecessor is the node just finished the state
+// simply carries over.  The diagonal into this lane's first row comes from the seed row just above it,
+// i.e. lane-1's last word of each predecessor (written by lane-1 at least one step earlier).
+template <int R, bool FILL>
+PG_HD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* seedS, uint32_t* lastG,
+                      uint32_t* infoG, bool save_trace)
+{
+    if (c.colsLeft == 0)
+    {
+        const int n = c.node;
+        if (FILL)
+        {
+            for (int r = 0; r < R; ++r)
+            {
+                seedS[(n * 2 * R + r) * 32 + lane] = s.Hp[r];
+                seedS[(n * 2 * R + R + r) * 32 + lane] = s.E[r];
+            }
+            if (save_trace)
+                for (int r = 0; r < R; ++r)
+                {
+                    lastG[(n * 3 * R + r) * 32 + lane] = s.Hp[r];
+                    lastG[(n * 3 * R + R + r) * 32 + lane] = s.E[r];
+                }
+            infoG[(n * 3 + 0) * 32 + lane] = c.Mnode;
+            infoG[(n * 3 + 1) * 32 + lane] = (uint32_t)c.first[0];
+            infoG[(n * 3 + 2) * 32 + lane] = (uint32_t)c.first[1];
+            c.Mnode = 0;
+        }
+        c.node = n + 1;
+        if (n + 1 < g.n_nodes)
+        {
+            c.colsLeft = g.node_len[n + 1];
+            const int p0 = g.pred_ptr[n + 1], p1 = g.pred_ptr[n + 2];
+            if (!(p1 - p0 == 1 && g.pred_idx[p0] == n))
+            {
+                uint32_t H[R], E[R], hup = 0;
+                for (int r = 0; r < R; ++r)
+                    H[r] = E[r] = 0;
+                for (int e = p0; e < p1; ++e)
+                {
+                    const int p = g.pred_idx[e];
+                    const uint32_t* src = FILL ? seedS + (size_t)p * 2 * R * 32 : lastG + (size_t)p * 3 * R * 32;
+                    for (int r = 0; r < R; ++r)
+                    {
+                        H[r] = max2(H[r], src[r * 32 + lane]);
+                        E[r] = max2(E[r], src[(R + r) * 32 + lane]);
+                    }
+                    if (lane > 0)
+                        hup = max2(hup, src[(R - 1) * 32 + lane - 1]);
+                }
+                for (int r = 0; r < R; ++r)
+                {
+                    s.Hp[r] = H[r];
+                    s.E[r] = E[r];
+                }
+                s.hupPrev = hup;
+            }
+        }
+        else
+            c.colsLeft = COLS_INF;
+    }
+    if (FILL && save_trace && c.colsLeft == 1) // about to process the node's last column: keep E entering it
+        for (int r = 0; r < R; ++r)
+            lastG[(c.node * 3 * R + 2 * R + r) * 32 + lane] = s.E[r];
+    --c.colsLeft;
+}
+
+template <int R> PG_HD void ckpt_store(const Lane<R>& s, uint32_t* ck, int lane)
+{
+    for (int r = 0; r < R; ++r)
+    {
+        ck[r * 32 + lane] = s.Hp[r];
+        ck[(R + r) * 32 + lane] = s.E[r];
+    }
+    ck[(2 * R) * 32 + lane] = s.hupPrev;
+    ck[(2 * R + 1) * 32 + lane] = s.foutLast;
+}
+template <int R> PG_HD void ckpt_load(Lane<R>& s, const uint32_t* ck, int lane)
+{
+    for (int r = 0; r < R; ++r)
+    {
+        s.Hp[r] = ck[r * 32 + lane];
+        s.E[r] = ck[(R + r) * 32 + lane];
+    }
+    s.hupPrev = ck[(2 * R) * 32 + lane];
+    s.foutLast = ck[(2 * R + 1) * 32 + lane];
+    s.hbotLast = s.Hp[R - 1];
+}
+
+PG_HD uint8_t clamp_byte(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+// one step of a traceback tile: H/E/F of this lane's rows, chosen half, as bytes ([3][ROWS])
+template <int R>
+PG_HD void tile_store(uint8_t* tstep, int lane, const uint32_t* Hc, const uint32_t* Ec, const uint32_t* Fc, int half)
+{
+    constexpr int ROWS = 32 * R;
+    for (int r = 0; r < R; ++r)
+    {
+        tstep[R * lane + r] = clamp_byte(half16(Hc[r], half));
+        tstep[ROWS + R * lane + r] = clamp_byte(half16(Ec[r], half));
+        tstep[2 * ROWS + R * lane + r] = clamp_byte(half16(Fc[r], half));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-task scratch layout (32-bit words, [..][32 lanes] innermost so that a warp store is one 128 B line)
+// ---------------------------------------------------------------------------------------------
+//   info  [n_nodes][3][32]      : per node and lane: packed node maximum, first step reaching it (half 0, half 1)
+//   last  [n_nodes][3R][32]     : node last column: H, E leaving (seed), E entering  (forward-graph tasks only)
+//   ckpt  [n_ck][2R+2][32]      : lane state before step c*CK                      (forward-graph tasks only)
+PG_HD int num_steps(int G) { return G + 32; } // lane 31 ends column G-1 at step G+30; its node event runs at step G+31
+PG_HD int num_ckpt(int G) { return (num_steps(G) + CK - 1) / CK; }
+
+struct TaskOut // result of one fill (two packed problems)
+{
+    int32_t score[2];    // global maximum S
+    int32_t n_top[2];    // number of nodes whose real cells contain S (capped at 2)
+    int32_t max_node[2]; // first node containing S, -1 when S == 0
+    int32_t end_step[2]; // wavefront step at which (end_lane) first held S in max_node
+    int32_t end_lane[2];
+};
+
+// Serial reduction of the per-(node, lane) maxima written by the fill (run by one lane at the end of a task).
+// Best cell per gssw: first node in array order whose maximum is the global one, first column in it, smallest
+// row in that column (gssw.c:378-386, 446-454, 4015-4018) -> min column = min(step - lane), ties -> smaller lane.
+PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o)
+{
+    for (int h = 0; h < 2; ++h)
+    {
+        int S = 0;
+        for (int n = 0; n < n_nodes; ++n)
+            for (int t = 0; t < 32; ++t)
+            {
+                const int v = half16(info[(n * 3 + 0) * 32 + t], h);
+                if (v > S)
+                    S = v;
+            }
+        int ntop = 0, mnode = -1, bestq = 0x7fffffff, blane = 0, bstep = 0;
+        for (int n = 0; n < n_nodes; ++n)
+        {
+            bool has = false;
+            for (int t = 0; t < 32; ++t)
+            {
+                if (half16(info[(n * 3 + 0) * 32 + t], h) != S)
+                    continue;
+                has = true;
+                if (mnode == -1 || mnode == n)
+                {
+                    const int step = (int)info[(n * 3 + 1 + h) * 32 + t];
+                    if (step - t < bestq)
+                    {
+                        bestq = step - t;
+                        blane = t;
+                        bstep = step;
+                    }
+                }
+            }
+            if (has)
+            {
+                if (mnode == -1)
+                    mnode = n;
+                if (ntop < 2)
+                    ++ntop;
+            }
+        }
+        o.score[h] = S;
+        o.n_top[h] = ntop;
+        if (S == 0)
+        {
+            // every real cell is 0: gssw leaves ref_end = -1 -> empty CIGAR, position 0 (gssw.c:2728-2732)
+            o.max_node[h] = -1;
+            o.end_step[h] = 0;
+            o.end_lane[h] = 0;
+        }
+        else
+        {
+            o.max_node[h] = mnode;
+            o.end_step[h] = bstep;
+            o.end_lane[h] = blane;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// strand choice (GraphAligner.cpp:340-356) from the forward-graph and reversed-graph fills of one read
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned AF_CIGAR = 1u, AF_BOTH_STRANDS = 2u, AF_REVERSE_GRAPH = 4u;
+
+struct Decision
+{
+    int half;    // which packed half of the forward-graph fill is reported (1 = reverse-complemented read)
+    int unique;
+    int score;
+};
+
+PG_HD Decision decide_strand(const TaskOut& fw, const TaskOut& rv, unsigned flags)
+{
+    const bool both = (flags & AF_BOTH_STRANDS) != 0, rg = (flags & AF_REVERSE_GRAPH) != 0;
+    const bool fwd_multi = fw.n_top[0] > 1;
+    const bool rev_multi = both ? fw.n_top[1] > 1 : false;
+    const bool rfwd_multi = rg ? rv.n_top[0] > 1 : false;
+    const bool rrev_multi = (rg && both) ? rv.n_top[1] > 1 : false;
+    const bool fwd_unique = !fwd_multi && !rfwd_multi;
+    const bool rev_unique = !rev_multi && !rrev_multi;
+    bool ret_rev = false;
+    if (!fwd_unique && rev_unique && both)
+        ret_rev = true;
+    else if (fwd_unique && !rev_unique)
+        ret_rev = false;
+    else if (both)
+        ret_rev = fw.score[0] < fw.score[1];
+    Decision d;
+    d.half = ret_rev ? 1 : 0;
+    d.unique = ret_rev ? rev_unique : fwd_unique;
+    d.score = fw.score[d.half];
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// output records (these two structs ARE the C-ABI result layout, see include/pg_align.h)
+// ---------------------------------------------------------------------------------------------
+struct Record
+{
+    int32_t graph_pos;
+    int32_t score;
+    uint8_t unique;
+    uint8_t chose_reverse;
+    uint8_t status; // 0 ok, 1 traceback dead end (never seen; the reference would spin/assert), 2 cigar overflow
+    uint8_t pad;
+    uint32_t cigar_off; // index of the first op in the cigar arena
+    uint32_t cigar_len; // number of ops
+};
+// cigar op word: node id << 16 | length << 3 | op code
+// OP_NONE (length 0) marks a node the path touches without emitting an op: gssw's "alignment start" step pushes
+// nothing when the characters differ although their codes match ('U' is coded as A, gssw.c:4214, 1662-1676), and
+// extractCigar still prints the node as "id[]".
+enum Op { OP_M = 0, OP_X = 1, OP_N = 2, OP_I = 3, OP_D = 4, OP_S = 5, OP_NONE = 7 };
+PG_HD uint32_t cigar_word(int node, int op, int len) { return ((uint32_t)node << 16) | ((uint32_t)len << 3) | (uint32_t)op; }
+
+// Replay an op log (traceback order, one word per move) front to back of the path, merging runs of equal
+// (node, op) like gssw_cigar_push_back/_front do within a node cigar (gssw.c:3679-3700).  An OP_NONE marker
+// survives only if its node has no other op.  Returns the number of ops (writes at most cap of them).
+PG_HD int emit_cigar(const uint32_t* oplog, int n, uint32_t* out, int cap)
+{
+    int m = 0;
+    uint32_t prev = 0;
+    bool have = false;
+    for (int x = n - 1; x >= 0; --x)
+    {
+        const uint32_t e = oplog[x];
+        if (have && (prev >> 16) == (e >> 16))
+        {
+            if ((e & 7u) == OP_NONE)
+                continue;
+            if ((prev & 7u) == OP_NONE)
+            {
+                prev = e;
+                continue;
+            }
+            if ((prev & 7u) == (e & 7u))
+            {
+                prev += e & 0xFFF8u;
+                continue;
+            }
+        }
+        if (have)
+        {
+            if (m < cap)
+                out[m] = prev;
+            ++m;
+        }
+        prev = e;
+        have = true;
+    }
+    if (have)
+    {
+        if (m < cap)
+            out[m] = prev;
+        ++m;
+    }
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// traceback over recomputed tiles
+// ---------------------------------------------------------------------------------------------
+// A tile holds H/E/F (bytes, the chosen half, clamped at 0 like gssw's unsigned saturation) of all rows for
+// CK consecutive wavefront steps; cell (node n, column i in node, row j) lives at step node_start[n]+i+j/R.
+template <int R> struct TileBuf
+{
+    uint8_t* mem;  // [2 slots][CK][3][ROWS]
+    int tile[2];   // tile index resident in each slot, -1 = empty
+    int lru;       // slot to evict next
+    PG_HD const uint8_t* find(int step) const
+    {
+        const int T = step / CK;
+        const int sl = tile[0] == T ? 0 : (tile[1] == T ? 1 : -1);
+        if (sl < 0 || step < 0)
+            return nullptr;
+        return mem + ((size_t)(sl * CK + (step - T * CK)) * 3) * Sizes<R>::ROWS;
+    }
+};
+
+struct Walker // traceback state of one read (lane 0 only)
+{
+    int n, i, j;   // current node, column in node, read row
+    int st;        // 0 = H, 1 = E (gap in read, 'D'), 2 = F (gap in reference, 'I')
+    int v;         // running score == M[st][i][j]
+    int phase;     // 0 locate end row, 1 walking, 2 done
+    int end_clip;  // trailing soft clip still to emit
+    int nops;      // raw ops pushed so far
+    int status;
+    int need_step; // on a miss: wavefront step whose tile must be made resident
+    int position;
+};
+
+// op log: one cigar_word per traceback move (length 1) or soft clip, in traceback order (back to front)
+PG_HD void push_op(Walker& w, uint32_t* oplog, int cap, int node, int op, int len)
+{
+    if (w.nops < cap)
+        oplog[w.nops] = cigar_word(node, op, len);
+    else
+        w.status = 2;
+    ++w.nops;
+}
+PG_HD int match_op(uint8_t refc, uint8_t readc) { return (refc == 'N' || readc == 'N') ? OP_N : (refc == readc ? OP_M : OP_X); }
+
+// Walk as far as the resident tiles allow.  Returns true when finished (w.phase == 2), false on a tile miss
+// (w.need_step set).  Mirrors gssw_alignment_trace_back_byte (gssw.c:1112-1818, final_traceback = 1, no
+// deflections) and the cross-node part of gssw_graph_trace_back_internal (gssw.c:2836-3148, 3486-3528).
+//   g      forward graph view;  chars = upper-cased graph characters (column-indexed like codes)
+//   last   this read's saved node last columns [n_nodes][3R][32] (packed words)
+template <int R>
+PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars, const uint32_t* last,
+                const uint8_t* bases, int L, int half, const TaskOut& fo, uint32_t* oplog, int oplog_cap)
+{
+    constexpr int ROWS = Sizes<R>::ROWS;
+    if (w.phase == 0)
+    {
+        // end cell: smallest row of end_lane holding S at end_step (gssw.c:446-454)
+        const int S = fo.score[half];
+        if (S <= 0)
+        {
+            w.position = 0;
+            w.phase = 2;
+            return true;
+        }
+        const uint8_t* t0 = tb.find(fo.end_step[half]);
+        if (!t0)
+        {
+            w.need_step = fo.end_step[half];
+            return false;
+        }
+        int row = -1;
+        for (int r = 0; r < R; ++r)
+            if (t0[R * fo.end_lane[half] + r] == S)
+            {
+                row = R * fo.end_lane[half] + r;
+                break;
+            }
+        if (row < 0)
+        {
+            w.status = 1;
+            w.phase = 2;
+            return true;
+        }
+        w.n = fo.max_node[half];
+        w.i = fo.end_step[half] - fo.end_lane[half] - g.node_start[w.n];
+        w.j = row;
+        w.st = 0;
+        w.v = S;
+        w.end_clip = L - 1 - row; // gssw.c:2766-2773
+        if (w.end_clip > 0)
+            push_op(w, oplog, oplog_cap, w.n, OP_S, w.end_clip);
+        w.phase = 1;
+    }
+    while (true)
+    {
+        // ---------------- inside node w.n (gssw_alignment_trace_back_byte) ----------------
+        bool leave = false; // left the node through its first column
+        while (w.v > 0 && w.i >= 0 && w.j >= 0)
+        {
+            const int k = g.node_start[w.n] + w.i + w.j / R; // step of the current cell
+            // neighbours: (i-1,j-1) -> step k-1 or k-2; (i-1,j) -> k-1; (i,j-1) -> k or k-1
+            const uint8_t* c0 = tb.find(k);
+            if (!c0)
+            {
+                w.need_step = k;
+                return false;
+            }
+            const int kd = k - 1 - ((w.j % R) == 0 ? 1 : 0); // step of (i-1, j-1)
+            const int kl = k - ((w.j % R) == 0 ? 1 : 0);     // step of (i, j-1)
+            if (w.st == 1)
+            {
+                if (w.i == 0)
+                {
+                    leave = true;
+                    break;
+                }
+                const uint8_t* c1 = tb.find(k - 1);
+                if (!c1)
+                {
+                    w.need_step = k - 1;
+                    return false;
+                }
+                if (w.v == (int)c1[w.j] - GAP_OPEN) // gssw.c:1347-1383
+                {
+                    push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
+                    w.v += GAP_OPEN;
+                    --w.i;
+                    w.st = 0;
+                    continue;
+                }
+                if (w.v == (int)c1[ROWS + w.j] - GAP_EXT) // gssw.c:1400-1423
+                {
+                    push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
+                    w.v += GAP_EXT;
+                    --w.i;
+                    continue;
+                }
+                w.status = 1; // "Stuck in read gap" (gssw.c:1449-1454)
+                w.phase = 2;
+                return true;
+            }
+            if (w.st == 2)
+            {
+                if (w.j > 0)
+                {
+                    const uint8_t* cl = tb.find(kl);
+                    if (!cl)
+                    {
+                        w.need_step = kl;
+                        return false;
+                    }
+                    if (w.v == (int)cl[w.j - 1] - GAP_OPEN) // gssw.c:1458-1493
+                    {
+                        push_op(w, oplog, oplog_cap, w.n, OP_I, 1);
+                        w.v += GAP_OPEN;
+                        --w.j;
+                        w.st = 0;
+                        continue;
+                    }
+                    if (w.v == (int)cl[2 * ROWS + w.j - 1] - GAP_EXT) // gssw.c:1510-1532
+                    {
+                        push_op(w, oplog, oplog_cap, w.n, OP_I, 1);
+                        w.v += GAP_EXT;
+                        --w.j;
+                        continue;
+                    }
+                }
+                w.status = 1; // "Ref gap stuck"
+                w.phase = 2;
+                return true;
+            }
+            // H state (gssw.c:1562-1801)
+            const uint8_t refc = chars[g.node_start[w.n] + w.i];
+            const uint8_t readc = read_char(bases, L, 0, half, w.j);
+            const int s = sub_score(nt_code(refc), nt_code(readc));
+            if (w.i > 0 && w.j > 0)
+            {
+                const uint8_t* cd = tb.find(kd);
+                if (!cd)
+                {
+                    w.need_step = kd;
+                    return false;
+                }
+                if (w.v == (int)cd[w.j - 1] + s) // diagonal, gssw.c:1591-1637
+                {
+                    push_op(w, oplog, oplog_cap, w.n, match_op(refc, readc), 1);
+                    w.v -= s;
+                    --w.i;
+                    --w.j;
+                    continue;
+                }
+            }
+            else if (w.v == s) // alignment starts here, gssw.c:1655-1690
+            {
+                if (refc == 'N' || readc == 'N' || refc == readc)
+                    push_op(w, oplog, oplog_cap, w.n, (refc == 'N' || readc == 'N') ? OP_N : OP_M, 1);
+                else
+                    push_op(w, oplog, oplog_cap, w.n, OP_NONE, 0);
+                --w.i;
+                --w.j;
+                w.v -= s;
+                continue;
+            }
+            if (w.j > 0 && w.v == (int)c0[2 * ROWS + w.j]) // H == F, gssw.c:1709-1729
+            {
+                w.st = 2;
+                continue;
+            }
+            if (w.v == (int)c0[ROWS + w.j]) // H == E, gssw.c:1747-1768
+            {
+                w.st = 1;
+                continue;
+            }
+            if (w.i == 0) // gssw.c:1787-1794
+            {
+                leave = true;
+                break;
+            }
+            w.status = 1; // "Stuck in main matrix"
+            w.phase = 2;
+            return true;
+        }
+        // ---------------- between nodes (gssw_graph_trace_back_internal) ----------------
+        if (!leave || w.v == 0)
+        {
+            // score exhausted (gssw.c:2836-2844): leading soft clip of readEnd+1, position = refEnd+1
+            if (w.v != 0) // ran off the read/reference with score left: reference flags gm->score = -1 (:2824-2828)
+                w.status = 1;
+            if (w.j > -1)
+                push_op(w, oplog, oplog_cap, w.n, OP_S, w.j + 1);
+            w.position = w.i + 1 < 0 ? 0 : w.i + 1;
+            w.phase = 2;
+            return true;
+        }
+        // first predecessor (ascending id) that explains the score wins (gssw.c:2966-3148)
+        int best = -1;
+        const uint8_t refc = chars[g.node_start[w.n]];
+        const uint8_t readc = read_char(bases, L, 0, half, w.j);
+        const int s = sub_score(nt_code(refc), nt_code(readc));
+        for (int e = g.pred_ptr[w.n]; e < g.pred_ptr[w.n + 1]; ++e)
+        {
+            const int c = g.pred_idx[e];
+            const uint32_t* lc = last + (size_t)c * (3 * R) * 32;
+            if (w.st == 0)
+            {
+                // diagonal source = pred's last column at row j-1 (row -1 never matches: H(0,0) is start or E)
+                const int dsrc = w.j > 0 ? half16(lc[((w.j - 1) % R) * 32 + (w.j - 1) / R], half) : -1000;
+                if (w.v == dsrc + s) // gssw.c:2999-3040
+                {
+                    best = c;
+                    push_op(w, oplog, oplog_cap, w.n, match_op(refc, readc), 1);
+                    w.v -= s;
+                    --w.j;
+                    break;
+                }
+            }
+            else
+            {
+                const int hsrc = half16(lc[(w.j % R) * 32 + w.j / R], half);
+                if (w.v == hsrc - GAP_OPEN) // open, gssw.c:3089-3110
+                {
+                    best = c;
+                    push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
+                    w.v += GAP_OPEN;
+                    w.st = 0;
+                    break;
+                }
+                const int esrc = imax0(half16(lc[(2 * R + w.j % R) * 32 + w.j / R], half)); // E entering pred's last column
+                if (w.v == esrc - GAP_EXT) // extend, gssw.c:3122-3136
+                {
+                    best = c;
+                    push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
+                    w.v += GAP_EXT;
+                    break;
+                }
+            }
+        }
+        if (best < 0)
+        {
+            // no predecessor explains the score (reference: assert compiled out, soft-clips the rest, gssw.c:3500-3517)
+            w.status = 1;
+            if (w.j > -1)
+                push_op(w, oplog, oplog_cap, w.n, OP_S, w.j + 1);
+            w.position = w.i + 1 < 0 ? 0 : w.i + 1;
+            w.phase = 2;
+            return true;
+        }
+        w.n = best;
+        w.i = g.node_len[best] - 1; // gssw.c:3486-3499
+    }
+}
+
+} // namespace pg

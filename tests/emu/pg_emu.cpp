@@ -1,0 +1,203 @@
+// TEST INFRASTRUCTURE ONLY -- CPU lane emulator of the CUDA path.
+// Compiles paragraph_b200/csrc/pg_core.cuh (the exact device source: recurrence, node events,
+// checkpoints, finalisation, strand choice, tile traceback) for the host and drives 32 emulated lanes in
+// lock step, with the warp shuffles replaced by array reads.  It exists so that the kernel logic can be
+// fuzzed against the oracle on machines without a GPU; nothing in the product loads it.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../paragraph_b200/csrc/pg_core.cuh"
+#include "../../paragraph_b200/csrc/pg_host.hpp"
+
+using namespace pg;
+
+namespace
+{
+
+template <int R>
+void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool save_trace, std::vector<uint32_t>& info,
+              std::vector<uint32_t>& last, std::vector<uint32_t>& ckpt, TaskOut& out)
+{
+    std::vector<uint32_t> prof((size_t)NCODE * R * 32);
+    std::vector<uint32_t> seedS((size_t)g.n_nodes * 2 * R * 32, 0);
+    for (int t = 0; t < 32; ++t)
+        build_profile<R>(prof.data(), bases, L, orient, t);
+    Lane<R> s[32];
+    LaneCtl c[32];
+    for (int t = 0; t < 32; ++t)
+    {
+        lane_zero(s[t]);
+        ctl_at_step(c[t], g, 0, t);
+    }
+    info.assign(host::info_words(g.n_nodes), 0);
+    if (save_trace)
+    {
+        last.assign(host::last_words(g.n_nodes, R), 0);
+        ckpt.assign(host::ckpt_words(g.G, R), 0);
+    }
+    const int nck = num_ckpt(g.G);
+    for (int k = 0; k < nck * CK; ++k)
+    {
+        if (save_trace && k % CK == 0)
+            for (int t = 0; t < 32; ++t)
+                ckpt_store<R>(s[t], ckpt.data() + (size_t)(k / CK) * (2 * R + 2) * 32, t);
+        for (int t = 0; t < 32; ++t) // events read what lane t-1 wrote at an EARLIER step only
+            node_event<R, true>(s[t], c[t], g, t, seedS.data(), save_trace ? last.data() : nullptr, info.data(),
+                                save_trace);
+        uint32_t rh[32], rf[32];
+        for (int t = 0; t < 32; ++t)
+        {
+            rh[t] = t ? s[t - 1].hbotLast : 0;
+            rf[t] = t ? s[t - 1].foutLast : 0;
+        }
+        for (int t = 0; t < 32; ++t)
+        {
+            const int code = g.codes[k - t];
+            const uint32_t m = lane_step<R, false>(s[t], rh[t], rf[t], prof.data(), code, t, nullptr, nullptr, nullptr);
+            track_max(c[t], m, k);
+        }
+    }
+    finalize_task(info.data(), g.n_nodes, out);
+}
+
+template <int R>
+void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::vector<uint32_t>& ckpt,
+              std::vector<uint32_t>& last, int T, uint8_t* dst, int half)
+{
+    Lane<R> s[32];
+    LaneCtl c[32];
+    for (int t = 0; t < 32; ++t)
+    {
+        ckpt_load<R>(s[t], ckpt.data() + (size_t)T * (2 * R + 2) * 32, t);
+        ctl_at_step(c[t], g, T * CK, t);
+    }
+    for (int kk = 0; kk < CK; ++kk)
+    {
+        const int k = T * CK + kk;
+        for (int t = 0; t < 32; ++t)
+            node_event<R, false>(s[t], c[t], g, t, nullptr, last.data(), nullptr, false);
+        uint32_t rh[32], rf[32];
+        for (int t = 0; t < 32; ++t)
+        {
+            rh[t] = t ? s[t - 1].hbotLast : 0;
+            rf[t] = t ? s[t - 1].foutLast : 0;
+        }
+        for (int t = 0; t < 32; ++t)
+        {
+            uint32_t Hc[R], Ec[R], Fc[R];
+            lane_step<R, true>(s[t], rh[t], rf[t], prof.data(), g.codes[k - t], t, Hc, Ec, Fc);
+            tile_store<R>(dst + (size_t)kk * 3 * Sizes<R>::ROWS, t, Hc, Ec, Fc, half);
+        }
+    }
+}
+
+template <int R>
+int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, const uint8_t* bases, int L,
+                  unsigned flags, Record& rec, std::vector<uint32_t>& ops_out, int* n_tiles)
+{
+    const GraphView g0 = make_view(sd, bytes, ints, 0), g1 = make_view(sd, bytes, ints, 1);
+    std::vector<uint32_t> info0, info1, last, ckpt, dummy1, dummy2;
+    TaskOut fw, rv;
+    memset(&rv, 0, sizeof rv);
+    emu_fill<R>(g0, bases, L, 0, true, info0, last, ckpt, fw);
+    if (flags & AF_REVERSE_GRAPH)
+        emu_fill<R>(g1, bases, L, 1, false, info1, dummy1, dummy2, rv);
+    const Decision d = decide_strand(fw, rv, flags);
+    std::vector<uint32_t> prof((size_t)NCODE * R * 32);
+    for (int t = 0; t < 32; ++t)
+        build_profile<R>(prof.data(), bases, L, 0, t);
+    std::vector<uint8_t> tiles((size_t)2 * CK * 3 * Sizes<R>::ROWS, 0);
+    TileBuf<R> tb;
+    tb.mem = tiles.data();
+    tb.tile[0] = tb.tile[1] = -1;
+    tb.lru = 0;
+    Walker w;
+    memset(&w, 0, sizeof w);
+    std::vector<uint32_t> oplog((size_t)2 * L + 64);
+    const uint8_t* chars = bytes + sd.chars_off;
+    int guard = 0;
+    while (!walk<R>(w, tb, g0, chars, last.data(), bases, L, d.half, fw, oplog.data(), (int)oplog.size()))
+    {
+        const int T = w.need_step / CK;
+        const int slot = tb.lru;
+        tb.lru ^= 1;
+        tb.tile[slot] = T;
+        emu_tile<R>(g0, prof, ckpt, last, T, tiles.data() + (size_t)slot * CK * 3 * Sizes<R>::ROWS, d.half);
+        if (n_tiles)
+            ++*n_tiles;
+        if (++guard > 100000)
+            return -1;
+    }
+    rec.graph_pos = w.position;
+    rec.score = d.score;
+    rec.unique = (uint8_t)d.unique;
+    rec.chose_reverse = (uint8_t)d.half;
+    rec.status = (uint8_t)w.status;
+    rec.pad = 0;
+    // replay the op log back to front, merging runs of equal (node, op)  (gssw_cigar_push_back/_front merging)
+    const int n = w.nops < (int)oplog.size() ? w.nops : (int)oplog.size();
+    ops_out.assign((size_t)n + 1, 0);
+    ops_out.resize((size_t)emit_cigar(oplog.data(), n, ops_out.data(), n + 1));
+    rec.cigar_off = 0;
+    rec.cigar_len = (flags & AF_CIGAR) ? (uint32_t)ops_out.size() : 0;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+// Same calling convention as pgo_align_batch (oracle/pg_oracle.h), plus graph arguments.
+// out6 = {graph_pos, score, unique, mapq, is_graph_reverse_strand, status}; returns 0 or negative.
+int pgemu_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off, int n_edges, const int32_t* efrom,
+                      const int32_t* eto, int n_reads, const char* bases_blob, const int32_t* read_off,
+                      const uint8_t* is_rev, unsigned flags, int32_t* out6, char* out_bases_blob, char* cigars,
+                      int cigar_stride, int64_t* tiles_total)
+{
+    host::GraphStore gs;
+    std::string err;
+    if (gs.add(n_nodes, seq_blob, seq_off, n_edges, efrom, eto, err) < 0)
+    {
+        fprintf(stderr, "pgemu: %s\n", err.c_str());
+        return -4;
+    }
+    int worst = 0;
+    for (int i = 0; i < n_reads; ++i)
+    {
+        const uint8_t* b = (const uint8_t*)bases_blob + read_off[i];
+        const int L = read_off[i + 1] - read_off[i];
+        if (L <= 0 || L > MAX_READ_LEN)
+            return -3;
+        Record rec;
+        std::vector<uint32_t> ops;
+        int nt = 0;
+        int rc = L <= 160 ? emu_align_one<5>(gs.sites[0], gs.bytes.data(), gs.ints.data(), b, L, flags, rec, ops, &nt)
+                          : emu_align_one<8>(gs.sites[0], gs.bytes.data(), gs.ints.data(), b, L, flags, rec, ops, &nt);
+        if (rc)
+            worst = rc;
+        if (tiles_total)
+            *tiles_total += nt;
+        int32_t* o = out6 + 6 * i;
+        o[0] = rec.graph_pos;
+        o[1] = rec.score;
+        o[2] = rec.unique;
+        o[3] = rec.unique ? 60 : 0;
+        o[4] = ((is_rev ? is_rev[i] : 0) != 0) != (rec.chose_reverse != 0);
+        o[5] = rec.status;
+        if (out_bases_blob)
+            for (int j = 0; j < L; ++j)
+                out_bases_blob[read_off[i] + j] = rec.chose_reverse ? (char)complement_base(b[L - 1 - j]) : (char)b[j];
+        if (cigars)
+        {
+            std::string s = (flags & AF_CIGAR) ? host::format_cigar(rec, ops.data()) : std::string();
+            size_t n = s.size() < (size_t)cigar_stride - 1 ? s.size() : (size_t)cigar_stride - 1;
+            memcpy(cigars + (size_t)i * cigar_stride, s.data(), n);
+            cigars[(size_t)i * cigar_stride + n] = 0;
+        }
+    }
+    return worst;
+}
+}
