@@ -1,0 +1,213 @@
+"""ctypes binding of the C-ABI (include/pg_align.h) exported by paragraph_b200/libpgalign.so.
+
+The shared library is built in-tree by ``__graft_entry__.build()`` (nvcc, sm_100a).  There is no CPU
+fallback anywhere in this package: importing works without a GPU (so that symbols can be checked), but
+creating a context raises ``PgError`` unless a B200-class device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpgalign.so")
+
+PG_OK = 0
+AF_CIGAR, AF_BOTH_STRANDS, AF_REVERSE_GRAPH, AF_ALL = 1, 2, 4, 0xFFFFFFFF
+MAX_READ_LEN = 250
+OPS = "MXNIDS??"
+
+RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i4"), ("unique", "u1"), ("chose_reverse", "u1"),
+                         ("status", "u1"), ("pad", "u1"), ("cigar_off", "<u4"), ("cigar_len", "<u4")])
+
+# every symbol include/pg_align.h declares
+SYMBOLS = ["pg_create", "pg_destroy", "pg_last_error", "pg_set_stream", "pg_set_scratch_limit", "pg_add_graph",
+           "pg_clear_graphs", "pg_align_batch", "pg_batch_upload", "pg_batch_run", "pg_batch_download",
+           "pg_format_cigar", "pg_stats", "pg_version"]
+
+
+class PgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """dlopen libpgalign.so and declare prototypes.  Fails loudly when the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PgError("paragraph_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p, u32p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
+    lib.pg_create.restype = C.c_int
+    lib.pg_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.pg_destroy.restype = None
+    lib.pg_destroy.argtypes = [vp]
+    lib.pg_last_error.restype = C.c_char_p
+    lib.pg_last_error.argtypes = [vp]
+    lib.pg_set_stream.restype = C.c_int
+    lib.pg_set_stream.argtypes = [vp, vp]
+    lib.pg_set_scratch_limit.restype = C.c_int
+    lib.pg_set_scratch_limit.argtypes = [vp, C.c_uint64]
+    lib.pg_add_graph.restype = C.c_int
+    lib.pg_add_graph.argtypes = [vp, C.c_int32, C.c_char_p, i32p, C.c_int32, i32p, i32p, i32p]
+    lib.pg_clear_graphs.restype = C.c_int
+    lib.pg_clear_graphs.argtypes = [vp]
+    lib.pg_align_batch.restype = C.c_int
+    lib.pg_align_batch.argtypes = [vp, C.c_int32, vp, i32p, i32p, C.c_uint32, vp, u32p, C.c_uint64,
+                                   C.POINTER(C.c_uint64)]
+    lib.pg_batch_upload.restype = C.c_int
+    lib.pg_batch_upload.argtypes = [vp, C.c_int32, vp, i32p, i32p]
+    lib.pg_batch_run.restype = C.c_int
+    lib.pg_batch_run.argtypes = [vp, C.c_uint32]
+    lib.pg_batch_download.restype = C.c_int
+    lib.pg_batch_download.argtypes = [vp, vp, u32p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.pg_format_cigar.restype = C.c_int
+    lib.pg_format_cigar.argtypes = [vp, u32p, C.c_char_p, C.c_int]
+    lib.pg_stats.restype = C.c_int
+    lib.pg_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.pg_version.restype = C.c_char_p
+    lib.pg_version.argtypes = []
+    _lib = lib
+    return lib
+
+
+def _i32(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def format_cigar(rec, ops):
+    """'<node>[<len><op>...]...' exactly as GraphAlignerImpl::extractCigar (GraphAligner.cpp:88-108)."""
+    out, cur = [], -1
+    o0, n = int(rec["cigar_off"]), int(rec["cigar_len"])
+    for w in ops[o0:o0 + n]:
+        w = int(w)
+        node = w >> 16
+        if node != cur:
+            if cur >= 0:
+                out.append("]")
+            out.append("%d[" % node)
+            cur = node
+        if (w & 7) == 7:
+            continue
+        out.append("%d%s" % ((w >> 3) & 0x1FFF, OPS[w & 7]))
+    if cur >= 0:
+        out.append("]")
+    return "".join(out)
+
+
+class Context:
+    """One engine context (one CUDA stream).  Mirrors a grm::GraphAligner that can hold many graphs."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.pg_create(int(device), C.byref(h))
+        if rc != PG_OK:
+            raise PgError("pg_create(device=%d) failed with %d: no usable sm_100 CUDA device; "
+                          "paragraph_b200 has no CPU fallback" % (device, rc))
+        self.h = h
+        self._keep = None
+        if stream is not None:
+            self.set_stream(stream)
+
+    def _check(self, rc):
+        if rc != PG_OK:
+            raise PgError("paragraph_b200 error %d: %s" % (rc, self.lib.pg_last_error(self.h).decode()))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.pg_set_stream(self.h, C.c_void_p(int(cuda_stream_ptr) if cuda_stream_ptr else None)))
+
+    def set_scratch_limit(self, nbytes):
+        self._check(self.lib.pg_set_scratch_limit(self.h, int(nbytes)))
+
+    def add_graph(self, node_seqs, edges):
+        blob = "".join(node_seqs).encode("latin-1")
+        off = np.zeros(len(node_seqs) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(s) for s in node_seqs])
+        ef = np.ascontiguousarray([e[0] for e in edges], dtype=np.int32)
+        et = np.ascontiguousarray([e[1] for e in edges], dtype=np.int32)
+        sid = C.c_int32(-1)
+        self._check(self.lib.pg_add_graph(self.h, len(node_seqs), blob, _i32(off), len(edges), _i32(ef), _i32(et),
+                                          C.byref(sid)))
+        return sid.value
+
+    def clear_graphs(self):
+        self._check(self.lib.pg_clear_graphs(self.h))
+
+    @staticmethod
+    def pack_reads(reads):
+        blob = np.frombuffer("".join(reads).encode("latin-1"), dtype=np.uint8).copy()
+        off = np.zeros(len(reads) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(r) for r in reads])
+        return blob, off
+
+    # ---- staged API (bench) -------------------------------------------------------------------
+    def upload(self, blob, off, sites=None):
+        self._keep = (blob, off, sites)
+        self._n = len(off) - 1
+        self._check(self.lib.pg_batch_upload(self.h, self._n, C.c_void_p(blob.ctypes.data), _i32(off),
+                                             _i32(sites) if sites is not None else None))
+
+    def run(self, flags=AF_ALL):
+        self._check(self.lib.pg_batch_run(self.h, flags & 0xFFFFFFFF))
+
+    def download(self, cigar_cap=None):
+        n = self._n
+        rec = np.zeros(n, dtype=RECORD_DTYPE)
+        cap = int(cigar_cap or n * 320)
+        ops = np.zeros(cap, dtype=np.uint32)
+        used = C.c_uint64(0)
+        self._check(self.lib.pg_batch_download(self.h, C.c_void_p(rec.ctypes.data),
+                                               ops.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(used)))
+        return rec, ops[:used.value]
+
+    # ---- one-call API (host buffers in, host buffers out) -----------------------------------------
+    def align_packed(self, blob, off, sites=None, flags=AF_ALL, cigar_cap=None):
+        n = len(off) - 1
+        rec = np.zeros(n, dtype=RECORD_DTYPE)
+        cap = int(cigar_cap or n * 320)
+        ops = np.zeros(cap, dtype=np.uint32)
+        used = C.c_uint64(0)
+        self._check(self.lib.pg_align_batch(self.h, n, C.c_void_p(blob.ctypes.data), _i32(off),
+                                            _i32(sites) if sites is not None else None, flags & 0xFFFFFFFF,
+                                            C.c_void_p(rec.ctypes.data), ops.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                            cap, C.byref(used)))
+        return rec, ops[:used.value]
+
+    def align(self, reads, sites=None, is_rev=None, flags=AF_ALL):
+        """Align python strings; returns dicts with the fields GraphAligner::alignRead sets on common::Read."""
+        from .synth import revcomp_exact
+        blob, off = self.pack_reads(reads)
+        st = None if sites is None else np.ascontiguousarray(sites, dtype=np.int32)
+        rec, ops = self.align_packed(blob, off, st, flags)
+        out = []
+        for i, r in enumerate(reads):
+            x = rec[i]
+            rv = bool(x["chose_reverse"])
+            out.append(dict(pos=int(x["graph_pos"]), score=int(x["score"]), unique=bool(x["unique"]),
+                            mapq=60 if x["unique"] else 0,
+                            graph_reverse=bool(is_rev[i] if is_rev is not None else 0) != rv,
+                            bases=revcomp_exact(r) if rv else r,
+                            cigar=format_cigar(x, ops) if flags & AF_CIGAR else "", status=int(x["status"])))
+        return out
+
+    def stats(self):
+        n, a, b = C.c_uint64(0), C.c_float(0), C.c_float(0)
+        self.lib.pg_stats(self.h, C.byref(n), C.byref(a), C.byref(b))
+        return dict(kernel_launches=n.value, fill_ms=a.value, trace_ms=b.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -440,6 +440,12 @@ struct TaskOut // result of one fill (two packed problems)
 // Serial reduction of the per-(node, lane) maxima written by the fill (run by one lane at the end of a task).
 // Best cell per gssw: first node in array order whose maximum is the global one, first column in it, smallest
 // row in that column (gssw.c:378-386, 446-454, 4015-4018) -> min column = min(step - lane), ties -> smaller lane.
+#if defined(__CUDA_ARCH__)
+PG_HD uint32_t ld_scratch(const uint32_t* p) { return __ldcg(p); } // written by other lanes of this warp: read at L2
+#else
+PG_HD uint32_t ld_scratch(const uint32_t* p) { return *p; }
+#endif
+
 PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o)
 {
     for (int h = 0; h < 2; ++h)
@@ -448,7 +454,7 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o)
         for (int n = 0; n < n_nodes; ++n)
             for (int t = 0; t < 32; ++t)
             {
-                const int v = half16(info[(n * 3 + 0) * 32 + t], h);
+                const int v = half16(ld_scratch(info + (n * 3 + 0) * 32 + t), h);
                 if (v > S)
                     S = v;
             }
@@ -458,12 +464,12 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o)
             bool has = false;
             for (int t = 0; t < 32; ++t)
             {
-                if (half16(info[(n * 3 + 0) * 32 + t], h) != S)
+                if (half16(ld_scratch(info + (n * 3 + 0) * 32 + t), h) != S)
                     continue;
                 has = true;
                 if (mnode == -1 || mnode == n)
                 {
-                    const int step = (int)info[(n * 3 + 1 + h) * 32 + t];
+                    const int step = (int)ld_scratch(info + (n * 3 + 1 + h) * 32 + t);
                     if (step - t < bestq)
                     {
                         bestq = step - t;
@@ -605,16 +611,29 @@ PG_HD int emit_cigar(const uint32_t* oplog, int n, uint32_t* out, int cap)
 // CK consecutive wavefront steps; cell (node n, column i in node, row j) lives at step node_start[n]+i+j/R.
 template <int R> struct TileBuf
 {
-    uint8_t* mem;  // [2 slots][CK][3][ROWS]
-    int tile[2];   // tile index resident in each slot, -1 = empty
-    int lru;       // slot to evict next
+    uint8_t* mem;     // [2 slots][CK][3][ROWS]
+    int tile0, tile1; // tile index resident in each slot, -1 = empty
+    int lru;          // slot to evict next
     PG_HD const uint8_t* find(int step) const
     {
+        if (step < 0)
+            return nullptr;
         const int T = step / CK;
-        const int sl = tile[0] == T ? 0 : (tile[1] == T ? 1 : -1);
-        if (sl < 0 || step < 0)
+        const int sl = tile0 == T ? 0 : (tile1 == T ? 1 : -1);
+        if (sl < 0)
             return nullptr;
         return mem + ((size_t)(sl * CK + (step - T * CK)) * 3) * Sizes<R>::ROWS;
+    }
+    // slot that will receive tile T (round-robin eviction: the walk moves monotonically between node jumps)
+    PG_HD int admit(int T)
+    {
+        const int sl = lru;
+        lru ^= 1;
+        if (sl == 0)
+            tile0 = T;
+        else
+            tile1 = T;
+        return sl;
     }
 };
 

@@ -1,0 +1,737 @@
+// paragraph_b200 -- sm_100a kernels and the C-ABI (include/pg_align.h) on top of them.
+//
+//   pg_fill_kernel<R>  : one warp per (read, graph orientation) task; packed-int16 wavefront over all graph
+//                        columns (pg_core.cuh); writes node maxima, and for forward-graph tasks the node last
+//                        columns and a lane-state checkpoint every CK steps.  Replaces gssw_graph_fill +
+//                        alignsEndAtMultNodes (gssw.c:3964-4028, GraphAligner.cpp:170-212).
+//   pg_trace_kernel<R> : one warp per read; strand choice (GraphAligner.cpp:340-356), then the reference's
+//                        traceback (gssw.c:1112-1818, 2621-3537) over tiles recomputed from the checkpoints.
+//
+// There is deliberately no CPU path in this file: without a CUDA device every entry point returns PG_E_CUDA.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pg_align.h"
+#include "pg_core.cuh"
+#include "pg_host.hpp"
+
+using namespace pg;
+
+static_assert(sizeof(pg_record) == sizeof(Record), "pg_record layout");
+
+namespace
+{
+
+constexpr int FILL_WARPS = 4;  // warps per CTA, fill kernel
+constexpr int TRACE_WARPS = 4; // warps per CTA, traceback kernel
+constexpr unsigned FULL = 0xffffffffu;
+
+struct FillArgs
+{
+    const SiteDev* sites;
+    const uint8_t* gbytes;
+    const int32_t* gints;
+    const uint8_t* bases;
+    const int32_t* read_off;
+    const int32_t* read_site; // may be null
+    int read0;                // first read of this chunk
+    int n_tasks;              // 2 * reads in chunk
+    unsigned flags;
+    uint32_t* info; // [task in chunk][stride_info]
+    uint32_t* last; // [read in chunk][stride_last]
+    uint32_t* ckpt; // [read in chunk][stride_ckpt]
+    size_t stride_info, stride_last, stride_ckpt;
+    TaskOut* tout; // [2 * n_reads] (global task index)
+    int smem_words_per_warp;
+};
+
+template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs a)
+{
+    extern __shared__ uint32_t smem[];
+    const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ltask = blockIdx.x * FILL_WARPS + wic;
+    if (ltask >= a.n_tasks)
+        return;
+    const int rd = a.read0 + (ltask >> 1), o = ltask & 1;
+    TaskOut* to = a.tout + (size_t)rd * 2 + o;
+    if (o == 1 && !(a.flags & AF_REVERSE_GRAPH))
+    {
+        if (lane == 0)
+        {
+            TaskOut z;
+            memset(&z, 0, sizeof z);
+            *to = z;
+        }
+        return;
+    }
+    uint32_t* prof = smem + (size_t)wic * a.smem_words_per_warp;
+    uint32_t* seedS = prof + NCODE * R * 32;
+    const SiteDev sd = a.sites[a.read_site ? a.read_site[rd] : 0];
+    const GraphView g = make_view(sd, a.gbytes, a.gints, o);
+    const uint8_t* bases = a.bases + a.read_off[rd];
+    const int L = a.read_off[rd + 1] - a.read_off[rd];
+    build_profile<R>(prof, bases, L, o, lane);
+    __syncwarp();
+
+    Lane<R> s;
+    lane_zero(s);
+    LaneCtl c;
+    ctl_at_step(c, g, 0, lane);
+    const bool save = (o == 0);
+    uint32_t* info = a.info + (size_t)ltask * a.stride_info;
+    uint32_t* last = a.last + (size_t)(ltask >> 1) * a.stride_last;
+    uint32_t* ckpt = a.ckpt + (size_t)(ltask >> 1) * a.stride_ckpt;
+    const uint8_t* codes = g.codes - lane;
+    const int nck = num_ckpt(g.G);
+    for (int cki = 0; cki < nck; ++cki)
+    {
+        if (save)
+            ckpt_store<R>(s, ckpt + (size_t)cki * (2 * R + 2) * 32, lane);
+        const int kbase = cki * CK;
+#pragma unroll 4
+        for (int kk = 0; kk < CK; ++kk)
+        {
+            const int k = kbase + kk;
+            __syncwarp();
+            if (c.colsLeft <= 1)
+                node_event<R, true>(s, c, g, lane, seedS, last, info, save);
+            else
+                --c.colsLeft;
+            uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1);
+            uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1);
+            if (lane == 0)
+            {
+                rh = 0;
+                rf = 0;
+            }
+            const int code = codes[k];
+            const uint32_t m = lane_step<R, false>(s, rh, rf, prof, code, lane, nullptr, nullptr, nullptr);
+            track_max(c, m, k);
+        }
+    }
+    __syncwarp();
+    if (lane == 0)
+    {
+        TaskOut t;
+        finalize_task(info, g.n_nodes, t);
+        *to = t;
+    }
+}
+
+struct TraceArgs
+{
+    const SiteDev* sites;
+    const uint8_t* gbytes;
+    const int32_t* gints;
+    const uint8_t* bases;
+    const int32_t* read_off;
+    const int32_t* read_site;
+    int read0, n_reads; // chunk
+    unsigned flags;
+    const uint32_t* last;
+    const uint32_t* ckpt;
+    size_t stride_last, stride_ckpt;
+    const TaskOut* tout;
+    Record* records;
+    uint32_t* arena;
+    unsigned long long* cursor;
+    unsigned long long arena_cap;
+    int smem_bytes_per_warp;
+    int oplog_cap;
+};
+
+template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_kernel(const TraceArgs a)
+{
+    extern __shared__ uint32_t smem[];
+    constexpr int ROWS = Sizes<R>::ROWS;
+    const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lrd = blockIdx.x * TRACE_WARPS + wic;
+    if (lrd >= a.n_reads)
+        return;
+    const int rd = a.read0 + lrd;
+    uint8_t* wmem = reinterpret_cast<uint8_t*>(smem) + (size_t)wic * a.smem_bytes_per_warp;
+    uint32_t* prof = reinterpret_cast<uint32_t*>(wmem);
+    uint32_t* oplog = prof + NCODE * R * 32;
+    uint8_t* tiles = reinterpret_cast<uint8_t*>(oplog + a.oplog_cap);
+
+    const SiteDev sd = a.sites[a.read_site ? a.read_site[rd] : 0];
+    const GraphView g = make_view(sd, a.gbytes, a.gints, 0);
+    const uint8_t* chars = a.gbytes + sd.chars_off;
+    const uint8_t* bases = a.bases + a.read_off[rd];
+    const int L = a.read_off[rd + 1] - a.read_off[rd];
+    const uint32_t* last = a.last + (size_t)lrd * a.stride_last;
+    const uint32_t* ckpt = a.ckpt + (size_t)lrd * a.stride_ckpt;
+    build_profile<R>(prof, bases, L, 0, lane);
+
+    const TaskOut fw = a.tout[(size_t)rd * 2], rv = a.tout[(size_t)rd * 2 + 1];
+    const Decision d = decide_strand(fw, rv, a.flags);
+    const int half = d.half;
+
+    TileBuf<R> tb;
+    tb.mem = tiles;
+    tb.tile0 = tb.tile1 = -1;
+    tb.lru = 0;
+    Walker w;
+    memset(&w, 0, sizeof w);
+    __syncwarp();
+    const uint8_t* codes = g.codes - lane;
+    for (int guard = 0; guard < (1 << 20); ++guard)
+    {
+        int done = 0, need = 0, slot = 0;
+        if (lane == 0)
+        {
+            done = walk<R>(w, tb, g, chars, last, bases, L, half, fw, oplog, a.oplog_cap) ? 1 : 0;
+            if (!done)
+            {
+                need = w.need_step / CK;
+                slot = tb.admit(need);
+            }
+        }
+        done = __shfl_sync(FULL, done, 0);
+        if (done)
+            break;
+        const int T = __shfl_sync(FULL, need, 0);
+        slot = __shfl_sync(FULL, slot, 0);
+        // recompute tile T from its checkpoint
+        Lane<R> s;
+        LaneCtl c;
+        ckpt_load<R>(s, ckpt + (size_t)T * (2 * R + 2) * 32, lane);
+        ctl_at_step(c, g, T * CK, lane);
+        uint8_t* dst = tiles + (size_t)slot * CK * 3 * ROWS;
+#pragma unroll 2
+        for (int kk = 0; kk < CK; ++kk)
+        {
+            const int k = T * CK + kk;
+            if (c.colsLeft <= 1)
+                node_event<R, false>(s, c, g, lane, nullptr, const_cast<uint32_t*>(last), nullptr, false);
+            else
+                --c.colsLeft;
+            uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1);
+            uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1);
+            if (lane == 0)
+            {
+                rh = 0;
+                rf = 0;
+            }
+            uint32_t Hc[R], Ec[R], Fc[R];
+            lane_step<R, true>(s, rh, rf, prof, codes[k], lane, Hc, Ec, Fc);
+            tile_store<R>(dst + (size_t)kk * 3 * ROWS, lane, Hc, Ec, Fc, half);
+        }
+        __syncwarp();
+    }
+    if (lane == 0)
+    {
+        Record rec;
+        rec.graph_pos = w.position;
+        rec.score = d.score;
+        rec.unique = (uint8_t)d.unique;
+        rec.chose_reverse = (uint8_t)half;
+        rec.status = (uint8_t)(w.phase == 2 ? w.status : 1);
+        rec.pad = 0;
+        rec.cigar_off = 0;
+        rec.cigar_len = 0;
+        if (a.flags & AF_CIGAR)
+        {
+            const int n = w.nops < a.oplog_cap ? w.nops : a.oplog_cap;
+            const int m = emit_cigar(oplog, n, nullptr, 0);
+            const unsigned long long off = atomicAdd(a.cursor, (unsigned long long)m);
+            if (off + (unsigned long long)m <= a.arena_cap)
+            {
+                emit_cigar(oplog, n, a.arena + off, m);
+                rec.cigar_off = (uint32_t)off;
+                rec.cigar_len = (uint32_t)m;
+            }
+            else
+                rec.status = 2;
+        }
+        a.records[rd] = rec;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+
+template <typename T> struct DevBuf
+{
+    T* p = nullptr;
+    size_t cap = 0; // elements
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess)
+            cap = n;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+template <typename T> struct PinBuf
+{
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap)
+            return cudaSuccess;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost(&p, n * sizeof(T));
+        if (e == cudaSuccess)
+            cap = n;
+        return e;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+} // namespace
+
+struct pg_ctx
+{
+    int device = 0;
+    std::string err;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    uint64_t launches = 0;
+    float fill_ms = 0, trace_ms = 0;
+    uint64_t scratch_limit = 24ull << 30;
+
+    host::GraphStore graphs;
+    bool graphs_dirty = true;
+    DevBuf<SiteDev> d_sites;
+    DevBuf<uint8_t> d_gbytes;
+    DevBuf<int32_t> d_gints;
+
+    // batch
+    int n_reads = 0, max_len = 0;
+    bool have_sites = false, uploaded = false, ran = false;
+    size_t bases_bytes = 0;
+    PinBuf<uint8_t> h_bases;
+    PinBuf<int32_t> h_off, h_site;
+    DevBuf<uint8_t> d_bases;
+    DevBuf<int32_t> d_off, d_site;
+    DevBuf<uint32_t> d_info, d_last, d_ckpt, d_arena;
+    DevBuf<TaskOut> d_tout;
+    DevBuf<Record> d_records;
+    DevBuf<unsigned long long> d_cursor;
+    PinBuf<Record> h_records;
+    PinBuf<uint32_t> h_arena;
+    PinBuf<unsigned long long> h_cursor;
+    unsigned long long arena_cap = 0;
+};
+
+namespace
+{
+
+int fail(pg_ctx* c, int code, const std::string& msg)
+{
+    if (c)
+        c->err = msg;
+    return code;
+}
+#define PG_CUDA(c, call)                                                                                               \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+            return fail(c, PG_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                             \
+    } while (0)
+
+int upload_graphs(pg_ctx* c)
+{
+    if (!c->graphs_dirty)
+        return PG_OK;
+    if (c->graphs.sites.empty())
+        return fail(c, PG_E_STATE, "no graph registered (pg_add_graph)");
+    PG_CUDA(c, c->d_sites.reserve(c->graphs.sites.size()));
+    PG_CUDA(c, c->d_gbytes.reserve(c->graphs.bytes.size()));
+    PG_CUDA(c, c->d_gints.reserve(c->graphs.ints.size()));
+    PG_CUDA(c, cudaMemcpyAsync(c->d_sites.p, c->graphs.sites.data(), c->graphs.sites.size() * sizeof(SiteDev),
+                               cudaMemcpyHostToDevice, c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(c->d_gbytes.p, c->graphs.bytes.data(), c->graphs.bytes.size(), cudaMemcpyHostToDevice,
+                               c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(c->d_gints.p, c->graphs.ints.data(), c->graphs.ints.size() * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, c->stream));
+    // the source vectors are pageable: the copies above are synchronous with respect to the host buffers
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->graphs_dirty = false;
+    return PG_OK;
+}
+
+template <int R> int run_chunks(pg_ctx* c, unsigned flags)
+{
+    const int max_nodes = c->graphs.max_nodes, max_G = c->graphs.max_G;
+    const size_t s_info = host::info_words(max_nodes), s_last = host::last_words(max_nodes, R),
+                 s_ckpt = host::ckpt_words(max_G, R);
+    const size_t per_read_bytes = (2 * s_info + s_last + s_ckpt) * sizeof(uint32_t);
+    size_t chunk = (size_t)(c->scratch_limit / (per_read_bytes ? per_read_bytes : 1));
+    if (chunk < 1)
+        chunk = 1;
+    if (chunk > (size_t)c->n_reads)
+        chunk = (size_t)c->n_reads;
+    PG_CUDA(c, c->d_info.reserve(chunk * 2 * s_info));
+    PG_CUDA(c, c->d_last.reserve(chunk * s_last));
+    PG_CUDA(c, c->d_ckpt.reserve(chunk * s_ckpt));
+    PG_CUDA(c, c->d_tout.reserve((size_t)c->n_reads * 2));
+    PG_CUDA(c, c->d_records.reserve((size_t)c->n_reads));
+    PG_CUDA(c, c->d_cursor.reserve(1));
+    const int oplog_cap = 2 * c->max_len + 16;
+    c->arena_cap = (unsigned long long)c->n_reads * (unsigned long long)(c->max_len + 2 * max_nodes + 8);
+    PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
+    PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
+
+    const int fill_words = NCODE * R * 32 + max_nodes * 2 * R * 32;
+    const size_t fill_smem = (size_t)FILL_WARPS * fill_words * sizeof(uint32_t);
+    const int trace_bytes = (NCODE * R * 32 + oplog_cap) * 4 + 2 * CK * 3 * Sizes<R>::ROWS;
+    const int trace_bytes_al = (trace_bytes + 15) & ~15;
+    const size_t trace_smem = (size_t)TRACE_WARPS * trace_bytes_al;
+    if (fill_smem > 227 * 1024 || trace_smem > 227 * 1024)
+        return fail(c, PG_E_GRAPH, "graph has too many nodes for the shared-memory seed table ("
+                        + std::to_string(max_nodes) + " nodes)");
+    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+    PG_CUDA(c, cudaFuncSetAttribute(pg_trace_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
+
+    PG_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
+    float fill_ms = 0, trace_ms = 0;
+    bool first = true;
+    for (size_t r0 = 0; r0 < (size_t)c->n_reads; r0 += chunk)
+    {
+        const int nr = (int)std::min(chunk, (size_t)c->n_reads - r0);
+        FillArgs fa;
+        fa.sites = c->d_sites.p;
+        fa.gbytes = c->d_gbytes.p;
+        fa.gints = c->d_gints.p;
+        fa.bases = c->d_bases.p;
+        fa.read_off = c->d_off.p;
+        fa.read_site = c->have_sites ? c->d_site.p : nullptr;
+        fa.read0 = (int)r0;
+        fa.n_tasks = 2 * nr;
+        fa.flags = flags;
+        fa.info = c->d_info.p;
+        fa.last = c->d_last.p;
+        fa.ckpt = c->d_ckpt.p;
+        fa.stride_info = s_info;
+        fa.stride_last = s_last;
+        fa.stride_ckpt = s_ckpt;
+        fa.tout = c->d_tout.p;
+        fa.smem_words_per_warp = fill_words;
+        const int fgrid = (fa.n_tasks + FILL_WARPS - 1) / FILL_WARPS;
+        pg_fill_kernel<R><<<fgrid, FILL_WARPS * 32, fill_smem, c->stream>>>(fa);
+        PG_CUDA(c, cudaGetLastError());
+        ++c->launches;
+        if (first)
+            PG_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+
+        TraceArgs ta;
+        ta.sites = c->d_sites.p;
+        ta.gbytes = c->d_gbytes.p;
+        ta.gints = c->d_gints.p;
+        ta.bases = c->d_bases.p;
+        ta.read_off = c->d_off.p;
+        ta.read_site = fa.read_site;
+        ta.read0 = (int)r0;
+        ta.n_reads = nr;
+        ta.flags = flags;
+        ta.last = c->d_last.p;
+        ta.ckpt = c->d_ckpt.p;
+        ta.stride_last = s_last;
+        ta.stride_ckpt = s_ckpt;
+        ta.tout = c->d_tout.p;
+        ta.records = c->d_records.p;
+        ta.arena = c->d_arena.p;
+        ta.cursor = c->d_cursor.p;
+        ta.arena_cap = c->arena_cap;
+        ta.smem_bytes_per_warp = trace_bytes_al;
+        ta.oplog_cap = oplog_cap;
+        const int tgrid = (nr + TRACE_WARPS - 1) / TRACE_WARPS;
+        pg_trace_kernel<R><<<tgrid, TRACE_WARPS * 32, trace_smem, c->stream>>>(ta);
+        PG_CUDA(c, cudaGetLastError());
+        ++c->launches;
+        if (first)
+            PG_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+        first = false;
+    }
+    PG_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    (void)fill_ms;
+    (void)trace_ms;
+    return PG_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* pg_version(void) { return "paragraph_b200 0.1 sm_100a CK=16 int16x2-wavefront"; }
+
+int pg_create(int device, pg_ctx** out)
+{
+    if (!out)
+        return PG_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0 || device < 0 || device >= n)
+    {
+        fprintf(stderr, "paragraph_b200: no usable CUDA device %d (%s) -- there is no CPU fallback\n", device,
+                e != cudaSuccess ? cudaGetErrorString(e) : "bad ordinal");
+        return PG_E_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+    {
+        fprintf(stderr, "paragraph_b200: device %d is not sm_100+ -- kernels are built for sm_100a only\n", device);
+        return PG_E_CUDA;
+    }
+    pg_ctx* c = new pg_ctx;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        delete c;
+        return PG_E_CUDA;
+    }
+    c->stream = c->own_stream;
+    for (auto& ev : c->ev)
+        cudaEventCreate(&ev);
+    *out = c;
+    return PG_OK;
+}
+
+void pg_destroy(pg_ctx* c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_sites.release();
+    c->d_gbytes.release();
+    c->d_gints.release();
+    c->d_bases.release();
+    c->d_off.release();
+    c->d_site.release();
+    c->d_info.release();
+    c->d_last.release();
+    c->d_ckpt.release();
+    c->d_arena.release();
+    c->d_tout.release();
+    c->d_records.release();
+    c->d_cursor.release();
+    c->h_bases.release();
+    c->h_off.release();
+    c->h_site.release();
+    c->h_records.release();
+    c->h_arena.release();
+    c->h_cursor.release();
+    for (auto& ev : c->ev)
+        if (ev)
+            cudaEventDestroy(ev);
+    if (c->own_stream)
+        cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* pg_last_error(const pg_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int pg_set_stream(pg_ctx* c, void* s)
+{
+    if (!c)
+        return PG_E_ARG;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return PG_OK;
+}
+
+int pg_set_scratch_limit(pg_ctx* c, uint64_t bytes)
+{
+    if (!c || bytes < (1u << 20))
+        return PG_E_ARG;
+    c->scratch_limit = bytes;
+    return PG_OK;
+}
+
+int pg_add_graph(pg_ctx* c, int32_t n_nodes, const char* blob, const int32_t* off, int32_t n_edges, const int32_t* ef,
+                 const int32_t* et, int32_t* site_id)
+{
+    if (!c)
+        return PG_E_ARG;
+    std::string err;
+    int id = c->graphs.add(n_nodes, blob, off, n_edges, ef, et, err);
+    if (id < 0)
+        return fail(c, PG_E_GRAPH, err);
+    c->graphs_dirty = true;
+    if (site_id)
+        *site_id = id;
+    return PG_OK;
+}
+
+int pg_clear_graphs(pg_ctx* c)
+{
+    if (!c)
+        return PG_E_ARG;
+    c->graphs.clear();
+    c->graphs_dirty = true;
+    return PG_OK;
+}
+
+int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t* off, const int32_t* site)
+{
+    if (!c || n_reads <= 0 || !bases || !off)
+        return fail(c, PG_E_ARG, "pg_batch_upload: bad arguments");
+    PG_CUDA(c, cudaSetDevice(c->device));
+    const int nsites = (int)c->graphs.sites.size();
+    if (nsites == 0)
+        return fail(c, PG_E_STATE, "no graph registered (pg_add_graph)");
+    int maxl = 0;
+    for (int i = 0; i < n_reads; ++i)
+    {
+        const int l = off[i + 1] - off[i];
+        if (l <= 0 || l > PG_MAX_READ_LEN)
+            return fail(c, PG_E_READ_LEN, "read " + std::to_string(i) + " has length " + std::to_string(l)
+                            + " (supported: 1.." + std::to_string(PG_MAX_READ_LEN) + ")");
+        if (l > maxl)
+            maxl = l;
+        if (site && (site[i] < 0 || site[i] >= nsites))
+            return fail(c, PG_E_ARG, "read " + std::to_string(i) + " names unknown site " + std::to_string(site[i]));
+    }
+    const size_t nb = (size_t)(off[n_reads] - off[0]);
+    PG_CUDA(c, c->h_bases.reserve(nb + 16));
+    PG_CUDA(c, c->h_off.reserve((size_t)n_reads + 1));
+    PG_CUDA(c, c->d_bases.reserve(nb + 16));
+    PG_CUDA(c, c->d_off.reserve((size_t)n_reads + 1));
+    memcpy(c->h_bases.p, bases + off[0], nb);
+    for (int i = 0; i <= n_reads; ++i)
+        c->h_off.p[i] = off[i] - off[0];
+    PG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, c->h_bases.p, nb, cudaMemcpyHostToDevice, c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(c->d_off.p, c->h_off.p, ((size_t)n_reads + 1) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                               c->stream));
+    c->have_sites = site != nullptr;
+    if (site)
+    {
+        PG_CUDA(c, c->h_site.reserve((size_t)n_reads));
+        PG_CUDA(c, c->d_site.reserve((size_t)n_reads));
+        memcpy(c->h_site.p, site, (size_t)n_reads * sizeof(int32_t));
+        PG_CUDA(c, cudaMemcpyAsync(c->d_site.p, c->h_site.p, (size_t)n_reads * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                   c->stream));
+    }
+    c->n_reads = n_reads;
+    c->max_len = maxl;
+    c->bases_bytes = nb;
+    c->uploaded = true;
+    c->ran = false;
+    return PG_OK;
+}
+
+int pg_batch_run(pg_ctx* c, uint32_t flags)
+{
+    if (!c)
+        return PG_E_ARG;
+    if (!c->uploaded)
+        return fail(c, PG_E_STATE, "pg_batch_run before pg_batch_upload");
+    PG_CUDA(c, cudaSetDevice(c->device));
+    int rc = upload_graphs(c);
+    if (rc != PG_OK)
+        return rc;
+    rc = c->max_len <= 160 ? run_chunks<5>(c, flags) : run_chunks<8>(c, flags);
+    if (rc == PG_OK)
+        c->ran = true;
+    return rc;
+}
+
+int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap, uint64_t* used)
+{
+    if (!c || !records)
+        return fail(c, PG_E_ARG, "pg_batch_download: bad arguments");
+    if (!c->ran)
+        return fail(c, PG_E_STATE, "pg_batch_download before pg_batch_run");
+    PG_CUDA(c, cudaSetDevice(c->device));
+    PG_CUDA(c, c->h_records.reserve((size_t)c->n_reads));
+    PG_CUDA(c, c->h_cursor.reserve(1));
+    PG_CUDA(c, cudaMemcpyAsync(c->h_records.p, c->d_records.p, (size_t)c->n_reads * sizeof(Record),
+                               cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->fill_ms, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->trace_ms, c->ev[1], c->ev[2]);
+    unsigned long long n = *c->h_cursor.p;
+    if (n > c->arena_cap)
+        n = c->arena_cap;
+    if (used)
+        *used = n;
+    memcpy(records, c->h_records.p, (size_t)c->n_reads * sizeof(Record));
+    for (int i = 0; i < c->n_reads; ++i)
+        if (c->h_records.p[i].status == 2)
+            return fail(c, PG_E_CAPACITY, "device cigar arena overflow at read " + std::to_string(i));
+    if (n)
+    {
+        if (!ops || cap < n)
+            return fail(c, PG_E_CAPACITY, "cigar arena too small: need " + std::to_string(n) + " ops");
+        PG_CUDA(c, c->h_arena.reserve((size_t)n));
+        PG_CUDA(c, cudaMemcpyAsync(c->h_arena.p, c->d_arena.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                   c->stream));
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+        memcpy(ops, c->h_arena.p, (size_t)n * sizeof(uint32_t));
+    }
+    return PG_OK;
+}
+
+int pg_align_batch(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t* off, const int32_t* site,
+                   uint32_t flags, pg_record* records, uint32_t* ops, uint64_t cap, uint64_t* used)
+{
+    int rc = pg_batch_upload(c, n_reads, bases, off, site);
+    if (rc != PG_OK)
+        return rc;
+    rc = pg_batch_run(c, flags);
+    if (rc != PG_OK)
+        return rc;
+    return pg_batch_download(c, records, ops, cap, used);
+}
+
+int pg_format_cigar(const pg_record* rec, const uint32_t* ops, char* out, int cap)
+{
+    if (!rec || (!ops && rec->cigar_len))
+        return PG_E_ARG;
+    Record r;
+    memcpy(&r, rec, sizeof r);
+    const std::string s = host::format_cigar(r, ops);
+    if (out && cap > 0)
+    {
+        const size_t n = s.size() < (size_t)cap - 1 ? s.size() : (size_t)cap - 1;
+        memcpy(out, s.data(), n);
+        out[n] = 0;
+    }
+    return (int)s.size();
+}
+
+int pg_stats(const pg_ctx* c, uint64_t* launches, float* fill_ms, float* trace_ms)
+{
+    if (!c)
+        return PG_E_ARG;
+    if (launches)
+        *launches = c->launches;
+    if (fill_ms)
+        *fill_ms = c->fill_ms;
+    if (trace_ms)
+        *trace_ms = c->trace_ms;
+    return PG_OK;
+}
+}

@@ -215,3 +215,8 @@ def fuzz_reads(rng, nodes, edges, n_reads, min_len=8, max_len=160, lower=0.02, i
                 b[i] = "RYKMSWBDHVNU="[int(rng.integers(0, 13))]
         reads.append("".join(b))
     return reads
+
+
+def revcomp_exact(s):
+    """graphtools::reverseComplement (SequenceOperations.cpp:66-89): case-sensitive, non-ACGT -> 'N'."""
+    return revcomp(s)

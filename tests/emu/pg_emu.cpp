@@ -112,7 +112,7 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     std::vector<uint8_t> tiles((size_t)2 * CK * 3 * Sizes<R>::ROWS, 0);
     TileBuf<R> tb;
     tb.mem = tiles.data();
-    tb.tile[0] = tb.tile[1] = -1;
+    tb.tile0 = tb.tile1 = -1;
     tb.lru = 0;
     Walker w;
     memset(&w, 0, sizeof w);
@@ -122,9 +122,7 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     while (!walk<R>(w, tb, g0, chars, last.data(), bases, L, d.half, fw, oplog.data(), (int)oplog.size()))
     {
         const int T = w.need_step / CK;
-        const int slot = tb.lru;
-        tb.lru ^= 1;
-        tb.tile[slot] = T;
+        const int slot = tb.admit(T);
         emu_tile<R>(g0, prof, ckpt, last, T, tiles.data() + (size_t)slot * CK * 3 * Sizes<R>::ROWS, d.half);
         if (n_tiles)
             ++*n_tiles;
