@@ -1,0 +1,173 @@
+"""Parity of the CUDA path, called through the C-ABI (paragraph_b200/libpgalign.so), against
+(1) the committed golden fixtures generated from the unmodified reference,
+(2) the oracle on seeded fuzz inputs (multi-site batches, all flag combinations, both row-tile sizes),
+(3) size-independent properties at BASELINE.json's full size (config 2: 10 000 x 150 bp reads).
+Bar: bit-exact (score, graph_pos, CIGAR string, uniqueness / mapq, chosen strand, rewritten bases)."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, strip_status
+from oracle import refbind as R
+from paragraph_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(built):
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_golden_fixtures(ctx, case):
+    ctx.clear_graphs()
+    ctx.add_graph(case["nodes"], [tuple(e) for e in case["edges"]])
+    got = ctx.align(case["reads"], is_rev=case["is_rev"], flags=case["flags"])
+    assert strip_status(got) == case["expected"]
+
+
+def test_fuzz_multisite_batch(ctx):
+    """300 random DAGs in ONE launch (multi-site batch), adversarial reads, vs the oracle."""
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(2024)
+    ctx.clear_graphs()
+    reads, sites, exp = [], [], []
+    for _ in range(300):
+        alpha = ["ACGT", "AC", "ACGTN", "ACGTRYN"][int(rng.integers(0, 4))]
+        nodes, edges = synth.bubble_graph(rng, max_len=int(rng.choice([5, 20, 60, 200])), alphabet=alpha)
+        rds = [r[:160] for r in synth.fuzz_reads(rng, nodes, edges, 16)]
+        sid = ctx.add_graph(nodes, edges)
+        reads += rds
+        sites += [sid] * len(rds)
+        exp += R.OracleGraph(nodes, edges).align_batch(rds)
+    got = strip_status(ctx.align(reads, sites=sites))
+    bad = [i for i, (g, e) in enumerate(zip(got, exp)) if g != e]
+    assert not bad, (len(bad), got[bad[0]], exp[bad[0]])
+
+
+@pytest.mark.parametrize("flags", [0xFFFFFFFF, 0, 1, 3, 5, 7])
+def test_flags_and_strands(ctx, flags):
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(flags & 0xFF)
+    nodes, edges = synth.inv_graph(rng, 120, 60)
+    reads = synth.simulate_reads(rng, nodes, edges, 150, read_len=90, sub=0.03, indel_frac=0.2, alternate=False)
+    isrev = [int(x) for x in rng.integers(0, 2, size=len(reads))]
+    ctx.clear_graphs()
+    ctx.add_graph(nodes, edges)
+    exp = R.OracleGraph(nodes, edges).align_batch(reads, is_rev=isrev, flags=flags)
+    assert strip_status(ctx.align(reads, is_rev=isrev, flags=flags)) == exp
+
+
+def test_long_reads_up_to_8bit_limit(ctx):
+    """161..250 bp reads run the 8-rows-per-lane instantiation."""
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(9)
+    nodes, edges = synth.del_graph(rng, 400, 200)
+    reads = synth.simulate_reads(rng, nodes, edges, 300, read_len=250, sub=0.02, indel_frac=0.3)
+    reads += synth.simulate_reads(rng, nodes, edges, 50, read_len=161)
+    ctx.clear_graphs()
+    ctx.add_graph(nodes, edges)
+    assert strip_status(ctx.align(reads)) == R.OracleGraph(nodes, edges).align_batch(reads)
+
+
+def test_long_nodes_many_checkpoints(ctx):
+    """config-5 shape (kb-sized nodes): hundreds of checkpoints / tiles per read, chunked scratch."""
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(10)
+    nodes, edges = synth.inv_graph(rng, 300, 3000)
+    reads = synth.simulate_reads(rng, nodes, edges, 96, alternate=False, indel_frac=0.1)
+    ctx.clear_graphs()
+    ctx.add_graph(nodes, edges)
+    ctx.set_scratch_limit(64 << 20)  # force several chunks
+    try:
+        got = strip_status(ctx.align(reads))
+    finally:
+        ctx.set_scratch_limit(24 << 30)
+    assert got == R.OracleGraph(nodes, edges).align_batch(reads)
+
+
+def test_many_nodes_graph(ctx):
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(12)
+    nodes, edges = synth.bubble_graph(rng, n_nodes=24, max_len=40, p_edge=0.15)
+    reads = [r[:160] for r in synth.fuzz_reads(rng, nodes, edges, 200)]
+    ctx.clear_graphs()
+    ctx.add_graph(nodes, edges)
+    assert strip_status(ctx.align(reads)) == R.OracleGraph(nodes, edges).align_batch(reads)
+
+
+def test_errors_are_loud(ctx):
+    ctx.clear_graphs()
+    with pytest.raises(capi.PgError):
+        ctx.align(["ACGT"])  # no graph
+    with pytest.raises(capi.PgError):
+        ctx.add_graph(["ACGT", "ACGT"], [(1, 0)])  # breaks topological order
+    with pytest.raises(capi.PgError):
+        ctx.add_graph(["ACGT", ""], [(0, 1)])  # empty node
+    ctx.add_graph(["ACGT" * 100], [])
+    with pytest.raises(capi.PgError):
+        ctx.align(["ACGT" * 63])  # 252 bp > PG_MAX_READ_LEN
+    with pytest.raises(capi.PgError):
+        ctx.align(["ACGT"], sites=[5])  # unknown site
+
+
+def _consumed(cigar):
+    import re
+    q = r = 0
+    for n, op in re.findall(r"(\d+)([MXNIDS])", cigar):
+        n = int(n)
+        if op in "MXNIS":
+            q += n
+        if op in "MXND":
+            r += n
+    return q, r
+
+
+def test_full_size_config2_properties(ctx):
+    """BASELINE.json configs[1] at full size: 10 000 reads x 150 bp on the 3-node DEL graph.
+    Checked against the oracle on a 500-read sample, and on all reads through size-independent properties:
+    CIGAR consumes exactly the read; score == #M - 4 #X - gaps; run twice -> identical; aligning the
+    reverse-complemented read reports the same alignment on the other strand."""
+    R.set_fill_variant(0)
+    nodes, edges, reads = synth.config2(seed=42, n_reads=10000)
+    ctx.clear_graphs()
+    ctx.add_graph(nodes, edges)
+    got = strip_status(ctx.align(reads))
+    assert got[:500] == R.OracleGraph(nodes, edges).align_batch(reads[:500])
+    import re
+    for g, r in zip(got, reads):
+        q, _ = _consumed(g["cigar"])
+        assert q == len(r), g
+        sc = 0
+        for node in re.findall(r"\[([^\]]*)\]", g["cigar"]):
+            for n, op in re.findall(r"(\d+)([MXNIDS])", node):
+                n = int(n)
+                sc += {"M": n, "X": -4 * n, "N": 0, "S": 0}.get(op, -(6 + n - 1))
+        assert sc == g["score"], (sc, g)
+        assert 0 <= g["score"] <= len(r)
+    again = strip_status(ctx.align(reads))
+    assert again == got
+    rc = strip_status(ctx.align([synth.revcomp(r) for r in reads[:2000]]))
+    for a, b in zip(got[:2000], rc):
+        if a["unique"] and b["unique"]:
+            assert (a["score"], a["pos"], a["cigar"]) == (b["score"], b["pos"], b["cigar"])
+            assert a["graph_reverse"] != b["graph_reverse"]
+
+
+def test_staged_api_matches_one_call(ctx):
+    nodes, edges, reads = synth.config2(seed=1, n_reads=512)
+    ctx.clear_graphs()
+    ctx.add_graph(nodes, edges)
+    blob, off = ctx.pack_reads(reads)
+    rec1, ops1 = ctx.align_packed(blob, off)
+    ctx.upload(blob, off)
+    ctx.run()
+    rec2, ops2 = ctx.download()
+    c1 = [capi.format_cigar(r, ops1) for r in rec1]
+    c2 = [capi.format_cigar(r, ops2) for r in rec2]
+    assert c1 == c2
+    for f in ("graph_pos", "score", "unique", "chose_reverse", "status"):
+        assert (rec1[f] == rec2[f]).all()
+    assert ctx.stats()["kernel_launches"] >= 4

@@ -1,0 +1,45 @@
+"""The kernel does not restate Farrar striping: it runs the plain affine recurrence with
+E' = max(E - ge, t - go) (no deletion opened out of an insertion).  These tests run the *reference's*
+traceback (restated in the oracle) over those matrices and demand identical results, which is the
+equivalence DESIGN.md relies on: H identical cell by cell, traceback decisions identical."""
+import numpy as np
+import pytest
+
+from conftest import golden_cases
+from oracle import refbind as R
+from paragraph_b200 import synth
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_variants_reproduce_golden(built, variant):
+    try:
+        R.set_fill_variant(variant)
+        for case in golden_cases():
+            got = R.OracleGraph(case["nodes"], case["edges"]).align_batch(case["reads"], is_rev=case["is_rev"],
+                                                                          flags=case["flags"])
+            assert got == case["expected"], case["name"]
+    finally:
+        R.set_fill_variant(0)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_variants_fuzz_H_and_results(built, variant):
+    rng = np.random.default_rng(100 + variant)
+    try:
+        for _ in range(150):
+            nodes, edges = synth.bubble_graph(rng, max_len=int(rng.choice([5, 20, 60])),
+                                              alphabet=["ACGT", "AC", "ACGTN"][int(rng.integers(0, 3))])
+            reads = synth.fuzz_reads(rng, nodes, edges, 8)
+            og = R.OracleGraph(nodes, edges)
+            R.set_fill_variant(0)
+            exp = og.align_batch(reads)
+            expH = [og.fill_trace(r.upper()) for r in reads[:3]]
+            R.set_fill_variant(variant)
+            assert og.align_batch(reads) == exp
+            for r, x in zip(reads[:3], expH):
+                y = og.fill_trace(r.upper())
+                for (h1, _, _), (h2, _, _) in zip(x["mats"], y["mats"]):
+                    assert (h1 == h2).all()
+                assert (x["cigar"], x["pos"], x["score"], x["multi"]) == (y["cigar"], y["pos"], y["score"], y["multi"])
+    finally:
+        R.set_fill_variant(0)

@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import numpy as np
 from oracle import refbind as R
 from paragraph_b200 import synth
-from tests import emubind
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
+import emubind
 
 def main():
     ng = int(sys.argv[1]) if len(sys.argv) > 1 else 100
