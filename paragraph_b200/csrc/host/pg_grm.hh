@@ -1,0 +1,334 @@
+// paragraph_b200 -- host-side C++ mirror of the reference's aligner interface for the read->graph path,
+// implemented on top of the C-ABI (include/pg_align.h).  Header only, no Boost / htslib / spdlog.
+//
+// Mirrors, with the same names, argument meaning and error behaviour (exceptions):
+//   grm::GraphAligner      setGraph / alignRead / align / AF_* flags   (src/c++/include/grm/GraphAligner.hh:36-88)
+//   grm::CompositeAligner  ctor flags, setGraph, alignRead(read, filter), counters
+//                                                                     (src/c++/include/grm/CompositeAligner.hh:44-91)
+//   grm::alignReads        batch entry: keeps MAPPED reads only        (src/c++/include/grm/Align.hh:49-52,
+//                                                                      src/c++/lib/grm/Align.cpp:114-156)
+// The classes are templates over the caller's Graph / Read types so that a paragraph build can instantiate
+// them with graphtools::Graph and common::Read unchanged; pgb::Graph / pgb::Read below are
+// minimal stand-ins with the same member names for stand-alone use and for this repo's tests.
+//
+// The GPU engine is batch-first: alignReads() makes ONE pg_align_batch call for the whole read vector
+// (results are written back in input order, so the outcome is deterministic for any `threads`); the per-read
+// alignRead() facades are batches of one.  Only the gssw stage (graph_sequence_matching) runs on the GPU;
+// asking for the path / kmer / klib stages throws (they are SURVEY.md 8f "next" rows, not silently skipped).
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <functional>
+#include <list>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/pg_align.h"
+
+namespace pgb
+{
+
+// ---- stand-in data types (same member names as graphtools::Graph / common::Read) ------------------------
+class Graph
+{
+public:
+    explicit Graph(size_t n = 0) : seq_(n), name_(n), pred_(n), succ_(n) {}
+    size_t numNodes() const { return seq_.size(); }
+    void setNodeSeq(uint32_t id, std::string const& s) { seq_.at(id) = s; }
+    void setNodeName(uint32_t id, std::string const& s) { name_.at(id) = s; }
+    std::string const& nodeSeq(uint32_t id) const { return seq_.at(id); }
+    std::string const& nodeName(uint32_t id) const { return name_.at(id); }
+    void addEdge(uint32_t from, uint32_t to)
+    {
+        if (from > to) // graphtools::Graph::addEdge, Graph.cpp:113-116
+            throw std::logic_error("Edge (" + std::to_string(from) + " ," + std::to_string(to) + ") breaks topological order");
+        succ_.at(from).insert(to);
+        pred_.at(to).insert(from);
+    }
+    std::set<uint32_t> const& predecessors(uint32_t id) const { return pred_.at(id); }
+    std::set<uint32_t> const& successors(uint32_t id) const { return succ_.at(id); }
+
+private:
+    std::vector<std::string> seq_, name_;
+    std::vector<std::set<uint32_t>> pred_, succ_;
+};
+
+struct Path
+{
+}; // placeholder for graphtools::Path (only used by the path-matching stage, which is not on the GPU path)
+
+class Read // the fields of common::Read the alignment path touches (src/c++/include/common/Read.hh:97-131)
+{
+public:
+    enum MappingStatus { UNMAPPED = 0, MAPPED = 1, BAD_ALIGN = 2 };
+    Read() = default;
+    Read(std::string const& id, std::string const& bases, std::string const& quals) { setCoreInfo(id, bases, quals); }
+    void setCoreInfo(std::string const& id, std::string const& bases, std::string const& quals)
+    {
+        fragment_id_ = id;
+        bases_ = bases;
+        quals_ = quals;
+    }
+    std::string const& fragment_id() const { return fragment_id_; }
+    std::string const& bases() const { return bases_; }
+    void set_bases(std::string const& v) { bases_ = v; }
+    std::string const& quals() const { return quals_; }
+    void set_quals(std::string const& v) { quals_ = v; }
+    bool is_reverse_strand() const { return is_reverse_strand_; }
+    void set_is_reverse_strand(bool v) { is_reverse_strand_ = v; }
+    int32_t graph_pos() const { return graph_pos_; }
+    void set_graph_pos(int32_t v) { graph_pos_ = v; }
+    std::string const& graph_cigar() const { return graph_cigar_; }
+    void set_graph_cigar(std::string v) { graph_cigar_ = std::move(v); }
+    int32_t graph_mapq() const { return graph_mapq_; }
+    void set_graph_mapq(int32_t v) { graph_mapq_ = v; }
+    int32_t graph_alignment_score() const { return graph_alignment_score_; }
+    void set_graph_alignment_score(int32_t v) { graph_alignment_score_ = v; }
+    bool is_graph_alignment_unique() const { return is_graph_alignment_unique_; }
+    void set_is_graph_alignment_unique(bool v) { is_graph_alignment_unique_ = v; }
+    bool is_graph_reverse_strand() const { return is_graph_reverse_strand_; }
+    void set_is_graph_reverse_strand(bool v) { is_graph_reverse_strand_ = v; }
+    MappingStatus graph_mapping_status() const { return graph_mapping_status_; }
+    void set_graph_mapping_status(MappingStatus s) { graph_mapping_status_ = s; }
+
+private:
+    std::string fragment_id_, bases_, quals_, graph_cigar_;
+    bool is_reverse_strand_ = false;
+    int32_t graph_pos_ = 0, graph_mapq_ = 0, graph_alignment_score_ = 0;
+    bool is_graph_alignment_unique_ = false, is_graph_reverse_strand_ = false;
+    MappingStatus graph_mapping_status_ = UNMAPPED;
+};
+
+namespace grm
+{
+
+// RAII around pg_ctx; errors become std::runtime_error like the reference's error() (common/Error.hh:55-167)
+class Engine
+{
+public:
+    explicit Engine(int device = 0)
+    {
+        if (pg_create(device, &ctx_) != PG_OK || !ctx_)
+            throw std::runtime_error("paragraph_b200: no usable sm_100 CUDA device (there is no CPU fallback)");
+    }
+    ~Engine() { pg_destroy(ctx_); }
+    Engine(Engine const&) = delete;
+    Engine& operator=(Engine const&) = delete;
+    pg_ctx* get() const { return ctx_; }
+    void check(int rc) const
+    {
+        if (rc != PG_OK)
+            throw std::runtime_error(std::string("paragraph_b200: ") + pg_last_error(ctx_));
+    }
+
+private:
+    pg_ctx* ctx_ = nullptr;
+};
+
+// graphtools::reverseComplement (SequenceOperations.cpp:66-89): case-sensitive, non-ACGT -> 'N'
+inline std::string reverseComplement(std::string s)
+{
+    for (char& c : s)
+        c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+    std::reverse(s.begin(), s.end());
+    return s;
+}
+
+class GraphAligner
+{
+public:
+    static const unsigned int AF_CIGAR = 0x01;
+    static const unsigned int AF_BOTH_STRANDS = 0x02;
+    static const unsigned int AF_REVERSE_GRAPH = 0x04;
+    static const unsigned int AF_ALL = (unsigned int)-1;
+
+    explicit GraphAligner(int device = 0) : engine_(new Engine(device)) {}
+
+    // GraphAligner::setGraph (GraphAligner.cpp:277-285); the reversed graph is derived by the engine
+    template <typename GraphT> void setGraph(GraphT const* g)
+    {
+        std::string blob;
+        std::vector<int32_t> off{ 0 }, ef, et;
+        const int32_t n = (int32_t)g->numNodes();
+        for (int32_t i = 0; i < n; ++i)
+        {
+            blob += g->nodeSeq((uint32_t)i);
+            off.push_back((int32_t)blob.size());
+            for (auto p : g->predecessors((uint32_t)i))
+            {
+                ef.push_back((int32_t)p);
+                et.push_back(i);
+            }
+        }
+        engine_->check(pg_clear_graphs(engine_->get()));
+        int32_t sid = -1;
+        engine_->check(pg_add_graph(engine_->get(), n, blob.data(), off.data(), (int32_t)ef.size(), ef.data(), et.data(), &sid));
+    }
+
+    // the loop `for read: alignRead(read, flags)` as one batch; writes the fields GraphAligner::alignRead writes
+    // (GraphAligner.cpp:358-401).  ReadIt iterates over (smart) pointers to reads; empty reads are skipped.
+    template <typename ReadIt> void alignBatch(ReadIt begin, ReadIt end, unsigned flags = AF_ALL) const
+    {
+        std::string blob;
+        std::vector<int32_t> off{ 0 };
+        std::vector<ReadIt> which;
+        for (ReadIt it = begin; it != end; ++it)
+        {
+            if ((*it)->bases().empty())
+                continue;
+            blob += (*it)->bases();
+            off.push_back((int32_t)blob.size());
+            which.push_back(it);
+        }
+        if (which.empty())
+            return;
+        std::vector<pg_record> rec(which.size());
+        std::vector<uint32_t> ops(blob.size() + 16 * which.size() + 64);
+        uint64_t used = 0;
+        engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), blob.data(), off.data(), nullptr, flags,
+                                      rec.data(), ops.data(), ops.size(), &used));
+        std::string buf;
+        for (size_t i = 0; i < which.size(); ++i)
+        {
+            auto& read = **which[i];
+            const pg_record& r = rec[i];
+            if (r.status != 0)
+                throw std::runtime_error("paragraph_b200: traceback failed for read " + std::to_string(i));
+            read.set_is_graph_reverse_strand(read.is_reverse_strand() != (r.chose_reverse != 0)); // :358-359
+            if (r.chose_reverse) // :375-378
+            {
+                read.set_bases(reverseComplement(read.bases()));
+                std::string q = read.quals();
+                std::reverse(q.begin(), q.end());
+                read.set_quals(q);
+            }
+            read.set_graph_pos(r.graph_pos);
+            read.set_graph_alignment_score(r.score);
+            read.set_is_graph_alignment_unique(r.unique != 0);
+            read.set_graph_mapq(r.unique ? 60 : 0);
+            if (flags & AF_CIGAR)
+            {
+                buf.resize((size_t)12 * (r.cigar_len + 2));
+                const int n = pg_format_cigar(&r, ops.data(), &buf[0], (int)buf.size());
+                read.set_graph_cigar(std::string(buf.data(), (size_t)std::min<int>(n, (int)buf.size() - 1)));
+            }
+        }
+    }
+
+    template <typename ReadT> void alignRead(ReadT& read, unsigned flags = AF_ALL) const
+    {
+        ReadT* p = &read;
+        alignBatch(&p, &p + 1, flags);
+    }
+
+    // GraphAligner::align (GraphAligner.cpp:287-296)
+    std::string align(const std::string& read, int& mapq, int& position, int& score) const
+    {
+        Read tmp;
+        tmp.set_bases(read);
+        alignRead(tmp, AF_CIGAR);
+        mapq = tmp.graph_mapq();
+        position = tmp.graph_pos();
+        score = tmp.graph_alignment_score();
+        return tmp.graph_cigar();
+    }
+
+private:
+    std::unique_ptr<Engine> engine_;
+};
+
+template <typename ReadT> using ReadFilterT = std::function<bool(ReadT&)>; // include/grm/Filter.hh:36
+
+class CompositeAligner
+{
+public:
+    CompositeAligner(bool pathMatching, bool graphMatching, bool klibMatching, bool kmerMatching,
+                     unsigned graphAlignmentFlags = GraphAligner::AF_ALL, int device = 0)
+        : graphMatching_(graphMatching), flags_(graphAlignmentFlags), graphAligner_(device)
+    {
+        if (pathMatching || klibMatching || kmerMatching)
+            throw std::runtime_error("paragraph_b200: only the gssw stage (graph_sequence_matching) runs on the GPU; "
+                                     "path / klib / kmer matching must stay on the reference's CPU aligners");
+    }
+    template <typename GraphT, typename PathListT> void setGraph(GraphT const* graph, PathListT const&)
+    {
+        graphAligner_.setGraph(graph);
+    }
+
+    // CompositeAligner::alignRead for a whole range (CompositeAligner.cpp:78-176, gssw branch :152-175):
+    // every read becomes MAPPED, then the filter may turn it into BAD_ALIGN; counters as in the reference.
+    template <typename ReadIt, typename FilterT> void alignReads(ReadIt begin, ReadIt end, FilterT filter)
+    {
+        if (!graphMatching_)
+        {
+            for (ReadIt it = begin; it != end; ++it)
+                attempted_ += !(*it)->bases().empty();
+            return;
+        }
+        graphAligner_.alignBatch(begin, end, flags_);
+        for (ReadIt it = begin; it != end; ++it)
+        {
+            auto& read = **it;
+            if (read.bases().empty())
+                continue;
+            ++attempted_;
+            read.set_graph_mapping_status(std::remove_reference<decltype(read)>::type::MAPPED);
+            if (filter && filter(read))
+            {
+                read.set_graph_mapping_status(std::remove_reference<decltype(read)>::type::BAD_ALIGN);
+                ++filtered_;
+            }
+            else
+                ++mappedSw_;
+        }
+    }
+    template <typename ReadT, typename FilterT> void alignRead(ReadT& read, FilterT filter)
+    {
+        ReadT* p = &read;
+        alignReads(&p, &p + 1, filter);
+    }
+
+    unsigned attempted() const { return attempted_; }
+    unsigned filtered() const { return filtered_; }
+    unsigned mappedKlib() const { return 0; }
+    unsigned mappedPath() const { return 0; }
+    unsigned anchoredPath() const { return 0; }
+    unsigned mappedKmers() const { return 0; }
+    unsigned mappedSw() const { return mappedSw_; }
+
+private:
+    const bool graphMatching_;
+    const unsigned flags_;
+    GraphAligner graphAligner_;
+    unsigned attempted_ = 0, filtered_ = 0, mappedSw_ = 0;
+};
+
+// grm::alignReads (Align.hh:49-52; Align.cpp:114-156): aligns, then keeps only MAPPED reads (input order).
+// `threads` is accepted for signature compatibility: the batch is one GPU launch sequence.
+template <typename GraphT, typename PathListT, typename ReadPtrT, typename FilterT>
+void alignReads(GraphT const* graph, PathListT const& paths, std::vector<ReadPtrT>& reads, FilterT const& filter,
+                bool path_sequence_matching, bool graph_sequence_matching, bool klib_sequence_matching,
+                bool kmer_sequence_matching, bool validate_alignments, uint32_t threads = 1, int device = 0)
+{
+    (void)threads;
+    if (validate_alignments)
+        throw std::runtime_error("paragraph_b200: ValidationAligner is diagnostics-only and not provided");
+    CompositeAligner aligner(path_sequence_matching, graph_sequence_matching, klib_sequence_matching,
+                             kmer_sequence_matching, GraphAligner::AF_ALL, device);
+    aligner.setGraph(graph, paths);
+    for (auto& r : reads) // Align.cpp:72-78
+        if (!r->bases().empty())
+            r->set_graph_mapping_status(std::remove_reference<decltype(*r)>::type::UNMAPPED);
+    aligner.alignReads(reads.begin(), reads.end(), filter);
+    std::vector<ReadPtrT> kept;
+    for (auto& r : reads)
+        if (!r->bases().empty() && r->graph_mapping_status() == std::remove_reference<decltype(*r)>::type::MAPPED)
+            kept.emplace_back(std::move(r));
+    reads.swap(kept); // Align.cpp:155
+}
+
+} // namespace grm
+} // namespace pgb

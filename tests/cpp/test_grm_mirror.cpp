@@ -1,0 +1,62 @@
+// Drives the host-side mirror (paragraph_b200/csrc/host/pg_grm.hh) the way the reference's own unit test drives
+// grm::alignReads (src/c++/test/test_paragraph_parts.cpp:52-104): same graph, same reads, gssw stage only.
+// Prints one line per surviving read: id pos cigar score mapq reverse bases status
+#include <cstdio>
+#include <list>
+#include <memory>
+#include <vector>
+
+#include "../../paragraph_b200/csrc/host/pg_grm.hh"
+
+int main()
+{
+    using namespace pgb;
+    std::vector<Read> reads(7);
+    reads[0].setCoreInfo("f1", "AAAAAAAATTTTCTTTAAAAAAAA", "########################");
+    reads[1].setCoreInfo("f2", "TTTTTTAAAGAAAATTTTTTT", "#####################");
+    reads[2].setCoreInfo("f3", "AAAAAGCGGGGGGAAAAAA", "###################");
+    reads[3].setCoreInfo("f4", "AAAAGCGGGGGGAAAAAA", "##################");
+    reads[4].setCoreInfo("f5", "TTTTTTCCCCCCGCTTTTT", "###################");
+    reads[5].setCoreInfo("f6", "AAAAAAAAAAAAAAAAAAA", "###################");
+    reads[6].setCoreInfo("f7", "CCCCCCCCCCCC", "############"); // scores 0 everywhere -> not unique -> filtered below
+    Graph graph(4);
+    graph.setNodeSeq(0, "AAAAAAAAAAA");
+    graph.setNodeSeq(1, "TTTTTTTT");
+    graph.setNodeSeq(2, "GGGGGGGG");
+    graph.setNodeSeq(3, "AAAAAAAAAAA");
+    graph.addEdge(0, 1);
+    graph.addEdge(0, 2);
+    graph.addEdge(0, 3);
+    graph.addEdge(1, 3);
+    graph.addEdge(2, 3);
+    std::vector<std::unique_ptr<Read>> rb;
+    for (auto const& r : reads)
+        rb.emplace_back(new Read(r));
+    std::list<Path> paths;
+    // NonUniq read filter (src/c++/lib/paragraph/readfilters/NonUniq.hh:48-52)
+    grm::ReadFilterT<Read> filter = [](Read& r) { return !r.is_graph_alignment_unique(); };
+    try
+    {
+        grm::alignReads(&graph, paths, rb, filter, false, true, false, false, false, 4);
+        for (auto const& r : rb)
+            printf("%s %d %s %d %d %d %s %d\n", r->fragment_id().c_str(), r->graph_pos(), r->graph_cigar().c_str(),
+                   r->graph_alignment_score(), r->graph_mapq(), (int)r->is_graph_reverse_strand(), r->bases().c_str(),
+                   (int)r->graph_mapping_status());
+        bool threw = false;
+        try
+        {
+            grm::CompositeAligner bad(true, true, false, false);
+        }
+        catch (std::runtime_error const&)
+        {
+            threw = true;
+        }
+        printf("path-stage-throws %d\n", (int)threw);
+    }
+    catch (std::exception const& e)
+    {
+        fprintf(stderr, "ERROR %s\n", e.what());
+        return 2;
+    }
+    return 0;
+}

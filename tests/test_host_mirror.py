@@ -1,0 +1,40 @@
+"""The C++ host mirror of grm::alignReads / CompositeAligner / GraphAligner (paragraph_b200/csrc/host/pg_grm.hh)
+compiles against the C-ABI, and on the GPU reproduces the reference's own unit-test expectations
+(src/c++/test/test_paragraph_parts.cpp:113-144) through grm::alignReads semantics (MAPPED-only, filter)."""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+EXE = os.path.join(ROOT, "tests", "cpp", "test_grm_mirror")
+
+
+def _compile():
+    src = os.path.join(ROOT, "tests", "cpp", "test_grm_mirror.cpp")
+    lib = os.path.join(ROOT, "paragraph_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", EXE, src, "-L" + lib, "-lpgalign",
+                           "-Wl,-rpath," + lib])
+
+
+def test_mirror_compiles_and_links(built):
+    _compile()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_mirror_reproduces_reference_unit_test(built):
+    _compile()
+    out = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().split("\n")
+    assert lines == [
+        "f1 3 0[8M]1[4M1X3M]3[8M] 19 60 0 AAAAAAAATTTTCTTTAAAAAAAA 1",
+        "f2 4 0[7M]1[4M1X3M]3[6M] 16 60 1 AAAAAAATTTTCTTTAAAAAA 1",
+        "f3 6 0[5M]2[1M1X6M]3[6M] 14 60 0 AAAAAGCGGGGGGAAAAAA 1",
+        "f4 7 0[4M]2[1M1X6M]3[6M] 13 60 0 AAAAGCGGGGGGAAAAAA 1",
+        "f5 6 0[5M]2[1M1X6M]3[6M] 14 60 1 AAAAAGCGGGGGGAAAAAA 1",
+        "f6 0 0[11M]3[8M] 19 60 0 AAAAAAAAAAAAAAAAAAA 1",
+        "path-stage-throws 1",
+    ]
