@@ -57,6 +57,8 @@ PG_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s
 PG_HD uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
 PG_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 PG_HD uint32_t add2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+// max(a, b) per half plus "a >= b" per half (one VIMNMX.S16x2 with two predicate outputs)
+PG_HD uint32_t max2_ge(uint32_t a, uint32_t b, bool& hi_ge, bool& lo_ge) { return __vibmax_s16x2(a, b, &hi_ge, &lo_ge); }
 #else
 PG_HD int imax_(int a, int b) { return a > b ? a : b; }
 PG_HD uint32_t addmax_relu2(uint32_t a, uint32_t b, uint32_t c)
@@ -70,6 +72,12 @@ PG_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c)
 PG_HD uint32_t max2(uint32_t a, uint32_t b) { return pk(imax_(lo16(a), lo16(b)), imax_(hi16(a), hi16(b))); }
 PG_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return max2(max2(a, b), c); }
 PG_HD uint32_t add2(uint32_t a, uint32_t b) { return pk(lo16(a) + lo16(b), hi16(a) + hi16(b)); }
+PG_HD uint32_t max2_ge(uint32_t a, uint32_t b, bool& hi_ge, bool& lo_ge)
+{
+    hi_ge = hi16(a) >= hi16(b);
+    lo_ge = lo16(a) >= lo16(b);
+    return max2(a, b);
+}
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -299,15 +307,12 @@ PG_HD void ctl_at_step(LaneCtl& c, const GraphView& g, int k0, int lane)
 
 PG_HD void track_max(LaneCtl& c, uint32_t m, int k)
 {
-    const uint32_t nm = max2(c.Mnode, m);
-    if (nm != c.Mnode)
-    {
-        if (lo16(nm) != lo16(c.Mnode))
-            c.first[0] = k;
-        if (hi16(nm) != hi16(c.Mnode))
-            c.first[1] = k;
-        c.Mnode = nm;
-    }
+    bool hi_ge, lo_ge; // old maximum >= this step's value: nothing new
+    c.Mnode = max2_ge(c.Mnode, m, hi_ge, lo_ge);
+    if (!lo_ge)
+        c.first[0] = k;
+    if (!hi_ge)
+        c.first[1] = k;
 }
 
 // Node boundary handling at the top of a step (rare, per lane: lanes reach a boundary at different steps).
@@ -661,6 +666,87 @@ PG_HD void push_op(Walker& w, uint32_t* oplog, int cap, int node, int op, int le
 }
 PG_HD int match_op(uint8_t refc, uint8_t readc) { return (refc == 'N' || readc == 'N') ? OP_N : (refc == readc ? OP_M : OP_X); }
 
+// Diagonal runs, 32 cells at a time.  Most traceback moves are diagonal (M/X/N); instead of one serial move per
+// iteration every lane ell probes the cell (i-ell, j-ell): is it an interior cell with positive score whose H equals
+// the diagonal neighbour plus the substitution score (gssw.c:1591-1637)?  The run is the number of leading lanes
+// that say yes; their ops are logged in parallel.  flag: 0 = no, 1 = yes, 2 = a tile the probe needs is not resident.
+template <int R>
+PG_HD void diag_probe(int ell, const Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars,
+                      const uint8_t* bases, int L, int half, int& flag, int& dval, int& op, int& need)
+{
+    const int ii = w.i - ell, jj = w.j - ell;
+    flag = 0;
+    dval = 0;
+    op = OP_M;
+    need = -1;
+    if (ii <= 0 || jj <= 0)
+        return;
+    const int k = g.node_start[w.n] + ii + jj / R;
+    const int kd = k - 1 - ((jj % R) == 0 ? 1 : 0);
+    const uint8_t* c0 = tb.find(k);
+    const uint8_t* cd = c0 ? tb.find(kd) : nullptr;
+    if (!c0 || !cd)
+    {
+        flag = 2;
+        need = c0 ? kd : k;
+        return;
+    }
+    const int hv = ell == 0 ? w.v : (int)c0[jj];
+    if (hv <= 0)
+        return;
+    const uint8_t refc = chars[g.node_start[w.n] + ii];
+    const uint8_t readc = read_char(bases, L, 0, half, jj);
+    dval = (int)cd[jj - 1];
+    op = match_op(refc, readc);
+    flag = (hv == dval + sub_score(nt_code(refc), nt_code(readc))) ? 1 : 0;
+}
+
+// Returns the run length (0..32); on 0, need >= 0 means the current cell's own probe missed a tile.
+// Warp-uniform on the device (every lane calls it with identical walker state and its own lane id).
+template <int R>
+PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars, const uint8_t* bases,
+                   int L, int half, int lane, uint32_t* oplog, int oplog_cap, int& vnew, int& need)
+{
+    int run = 0;
+#if defined(__CUDA_ARCH__)
+    int flag, dval, op, nd;
+    diag_probe<R>(lane, w, tb, g, chars, bases, L, half, flag, dval, op, nd);
+    const unsigned yes = __ballot_sync(0xffffffffu, flag == 1);
+    run = (yes == 0xffffffffu) ? 32 : (__ffs((int)~yes) - 1);
+    if (lane < run)
+    {
+        if (w.nops + lane < oplog_cap)
+            oplog[w.nops + lane] = cigar_word(w.n, op, 1);
+    }
+    vnew = __shfl_sync(0xffffffffu, dval, run > 0 ? run - 1 : 0);
+    need = __shfl_sync(0xffffffffu, flag == 2 ? nd : -1, 0);
+#else
+    (void)lane;
+    need = -1;
+    vnew = 0;
+    for (int ell = 0; ell < 32; ++ell)
+    {
+        int flag, dval, op, nd;
+        diag_probe<R>(ell, w, tb, g, chars, bases, L, half, flag, dval, op, nd);
+        if (ell == 0 && flag == 2)
+            need = nd;
+        if (flag != 1)
+            break;
+        if (w.nops + ell < oplog_cap)
+            oplog[w.nops + ell] = cigar_word(w.n, op, 1);
+        vnew = dval;
+        ++run;
+    }
+#endif
+    if (run > 0)
+    {
+        if (w.nops + run > oplog_cap)
+            w.status = 2;
+        w.nops += run;
+    }
+    return run;
+}
+
 // Walk as far as the resident tiles allow.  Returns true when finished (w.phase == 2), false on a tile miss
 // (w.need_step set).  Mirrors gssw_alignment_trace_back_byte (gssw.c:1112-1818, final_traceback = 1, no
 // deflections) and the cross-node part of gssw_graph_trace_back_internal (gssw.c:2836-3148, 3486-3528).
@@ -668,7 +754,7 @@ PG_HD int match_op(uint8_t refc, uint8_t readc) { return (refc == 'N' || readc =
 //   last   this read's saved node last columns [n_nodes][3R][32] (packed words)
 template <int R>
 PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars, const uint32_t* last,
-                const uint8_t* bases, int L, int half, const TaskOut& fo, uint32_t* oplog, int oplog_cap)
+                const uint8_t* bases, int L, int half, const TaskOut& fo, uint32_t* oplog, int oplog_cap, int lane)
 {
     constexpr int ROWS = Sizes<R>::ROWS;
     if (w.phase == 0)
@@ -724,7 +810,6 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                 w.need_step = k;
                 return false;
             }
-            const int kd = k - 1 - ((w.j % R) == 0 ? 1 : 0); // step of (i-1, j-1)
             const int kl = k - ((w.j % R) == 0 ? 1 : 0);     // step of (i, j-1)
             if (w.st == 1)
             {
@@ -794,19 +879,19 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
             const int s = sub_score(nt_code(refc), nt_code(readc));
             if (w.i > 0 && w.j > 0)
             {
-                const uint8_t* cd = tb.find(kd);
-                if (!cd)
+                int vnew, need;
+                const int run = diag_run<R>(w, tb, g, chars, bases, L, half, lane, oplog, oplog_cap, vnew, need);
+                if (run > 0) // diagonal moves, gssw.c:1591-1637
                 {
-                    w.need_step = kd;
-                    return false;
-                }
-                if (w.v == (int)cd[w.j - 1] + s) // diagonal, gssw.c:1591-1637
-                {
-                    push_op(w, oplog, oplog_cap, w.n, match_op(refc, readc), 1);
-                    w.v -= s;
-                    --w.i;
-                    --w.j;
+                    w.v = vnew;
+                    w.i -= run;
+                    w.j -= run;
                     continue;
+                }
+                if (need >= 0)
+                {
+                    w.need_step = need;
+                    return false;
                 }
             }
             else if (w.v == s) // alignment starts here, gssw.c:1655-1690

@@ -181,21 +181,13 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
     const uint8_t* codes = g.codes - lane;
     for (int guard = 0; guard < (1 << 20); ++guard)
     {
-        int done = 0, need = 0, slot = 0;
-        if (lane == 0)
-        {
-            done = walk<R>(w, tb, g, chars, last, bases, L, half, fw, oplog, a.oplog_cap) ? 1 : 0;
-            if (!done)
-            {
-                need = w.need_step / CK;
-                slot = tb.admit(need);
-            }
-        }
-        done = __shfl_sync(FULL, done, 0);
-        if (done)
+        // the walk is warp-uniform: every lane carries the same walker state; diagonal runs are probed 32 cells
+        // at a time with a ballot (diag_run), the other moves are executed redundantly by all lanes
+        if (walk<R>(w, tb, g, chars, last, bases, L, half, fw, oplog, a.oplog_cap, lane))
             break;
-        const int T = __shfl_sync(FULL, need, 0);
-        slot = __shfl_sync(FULL, slot, 0);
+        const int T = w.need_step / CK;
+        const int slot = tb.admit(T);
+        __syncwarp();
         // recompute tile T from its checkpoint
         Lane<R> s;
         LaneCtl c;
@@ -223,6 +215,7 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
         }
         __syncwarp();
     }
+    __syncwarp();
     if (lane == 0)
     {
         Record rec;

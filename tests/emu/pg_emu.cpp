@@ -119,7 +119,7 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     std::vector<uint32_t> oplog((size_t)2 * L + 64);
     const uint8_t* chars = bytes + sd.chars_off;
     int guard = 0;
-    while (!walk<R>(w, tb, g0, chars, last.data(), bases, L, d.half, fw, oplog.data(), (int)oplog.size()))
+    while (!walk<R>(w, tb, g0, chars, last.data(), bases, L, d.half, fw, oplog.data(), (int)oplog.size(), 0))
     {
         const int T = w.need_step / CK;
         const int slot = tb.admit(T);
