@@ -410,18 +410,45 @@ template <int R> PG_HD void ckpt_load(Lane<R>& s, const uint32_t* ck, int lane)
     s.hbotLast = s.Hp[R - 1];
 }
 
-PG_HD uint8_t clamp_byte(int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
-// one step of a traceback tile: H/E/F of this lane's rows, chosen half, as bytes ([3][ROWS])
-template <int R>
-PG_HD void tile_store(uint8_t* tstep, int lane, const uint32_t* Hc, const uint32_t* Ec, const uint32_t* Fc, int half)
+// Traceback tiles keep, per cell, one word H | E << 8 | F << 16 (chosen half; E/F clamped at 0 like gssw's unsigned
+// saturation; all three fit a byte because scores are <= MAX_READ_LEN) and only for a band of BAND_LANES lanes
+// (BAND_LANES * R read rows): within the CK steps of a tile the walk moves through ~CK rows, so rows outside
+// the band are never read.  A cell outside the resident bands is simply a miss (tile recomputed around it).
+constexpr int BAND_LANES = 8;
+template <int R> struct TileGeom
 {
-    constexpr int ROWS = 32 * R;
+    static constexpr int BAND_ROWS = BAND_LANES * R;
+    static constexpr int SLOT_WORDS = CK * BAND_ROWS;
+};
+
+PG_HD uint32_t pack_cell(uint32_t h, uint32_t e, uint32_t f, int half)
+{
+    e = max2(e, 0u);
+    f = max2(f, 0u);
+#if defined(__CUDA_ARCH__)
+    // bytes: b0 = h.byte(2*half), b1 = e.byte(2*half), b2 = f.byte(2*half), b3 = f.byte(2*half+1) == 0
+    const uint32_t s1 = half ? 0x0062u : 0x0040u;
+    const uint32_t s2 = half ? 0x7610u : 0x5410u;
+    return __byte_perm(__byte_perm(h, e, s1), f, s2);
+#else
+    return (uint32_t)(half16(h, half) & 0xff) | ((uint32_t)(half16(e, half) & 0xff) << 8)
+        | ((uint32_t)(half16(f, half) & 0xff) << 16);
+#endif
+}
+PG_HD int cellH(uint32_t w) { return (int)(w & 0xffu); }
+PG_HD int cellE(uint32_t w) { return (int)((w >> 8) & 0xffu); }
+PG_HD int cellF(uint32_t w) { return (int)((w >> 16) & 0xffu); }
+
+// one step of a traceback tile: lanes [blo, blo + BAND_LANES) store their R cells
+template <int R>
+PG_HD void tile_store(uint32_t* tstep, int lane, int blo, const uint32_t* Hc, const uint32_t* Ec, const uint32_t* Fc,
+                      int half)
+{
+    const int bl = lane - blo;
+    if (bl < 0 || bl >= BAND_LANES)
+        return;
     for (int r = 0; r < R; ++r)
-    {
-        tstep[R * lane + r] = clamp_byte(half16(Hc[r], half));
-        tstep[ROWS + R * lane + r] = clamp_byte(half16(Ec[r], half));
-        tstep[2 * ROWS + R * lane + r] = clamp_byte(half16(Fc[r], half));
-    }
+        tstep[R * bl + r] = pack_cell(Hc[r], Ec[r], Fc[r], half);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -616,28 +643,48 @@ PG_HD int emit_cigar(const uint32_t* oplog, int n, uint32_t* out, int cap)
 // CK consecutive wavefront steps; cell (node n, column i in node, row j) lives at step node_start[n]+i+j/R.
 template <int R> struct TileBuf
 {
-    uint8_t* mem;     // [2 slots][CK][3][ROWS]
+    uint32_t* mem;    // [2 slots][CK][BAND_ROWS] cell words
     int tile0, tile1; // tile index resident in each slot, -1 = empty
+    int blo0, blo1;   // first lane of each slot's row band
     int lru;          // slot to evict next
-    PG_HD const uint8_t* find(int step) const
+    PG_HD const uint32_t* find(int step, int row) const
     {
         if (step < 0)
             return nullptr;
-        const int T = step / CK;
-        const int sl = tile0 == T ? 0 : (tile1 == T ? 1 : -1);
+        const int T = step / CK, ln = row / R;
+        int sl = -1, blo = 0;
+        if (tile0 == T && ln >= blo0 && ln < blo0 + BAND_LANES)
+        {
+            sl = 0;
+            blo = blo0;
+        }
+        else if (tile1 == T && ln >= blo1 && ln < blo1 + BAND_LANES)
+        {
+            sl = 1;
+            blo = blo1;
+        }
         if (sl < 0)
             return nullptr;
-        return mem + ((size_t)(sl * CK + (step - T * CK)) * 3) * Sizes<R>::ROWS;
+        return mem + (size_t)(sl * CK + (step - T * CK)) * TileGeom<R>::BAND_ROWS + (row - R * blo);
     }
-    // slot that will receive tile T (round-robin eviction: the walk moves monotonically between node jumps)
-    PG_HD int admit(int T)
+    // slot that will receive tile T with a band ending at `row`'s lane (round-robin eviction)
+    PG_HD int admit(int T, int row, int& blo)
     {
+        blo = row / R - (BAND_LANES - 1);
+        if (blo < 0)
+            blo = 0;
         const int sl = lru;
         lru ^= 1;
         if (sl == 0)
+        {
             tile0 = T;
+            blo0 = blo;
+        }
         else
+        {
             tile1 = T;
+            blo1 = blo;
+        }
         return sl;
     }
 };
@@ -651,7 +698,8 @@ struct Walker // traceback state of one read (lane 0 only)
     int end_clip;  // trailing soft clip still to emit
     int nops;      // raw ops pushed so far
     int status;
-    int need_step; // on a miss: wavefront step whose tile must be made resident
+    int need_step; // on a miss: wavefront step whose tile must be made resident ...
+    int need_row;  // ... with a row band ending at this row's lane
     int position;
 };
 
@@ -672,77 +720,95 @@ PG_HD int match_op(uint8_t refc, uint8_t readc) { return (refc == 'N' || readc =
 // that say yes; their ops are logged in parallel.  flag: 0 = no, 1 = yes, 2 = a tile the probe needs is not resident.
 template <int R>
 PG_HD void diag_probe(int ell, const Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars,
-                      const uint8_t* bases, int L, int half, int& flag, int& dval, int& op, int& need)
+                      const uint8_t* bases, int L, int half, int& flag, int& dval, int& op)
 {
     const int ii = w.i - ell, jj = w.j - ell;
     flag = 0;
     dval = 0;
     op = OP_M;
-    need = -1;
     if (ii <= 0 || jj <= 0)
         return;
     const int k = g.node_start[w.n] + ii + jj / R;
     const int kd = k - 1 - ((jj % R) == 0 ? 1 : 0);
-    const uint8_t* c0 = tb.find(k);
-    const uint8_t* cd = c0 ? tb.find(kd) : nullptr;
+    const uint32_t* c0 = tb.find(k, jj);
+    const uint32_t* cd = c0 ? tb.find(kd, jj - 1) : nullptr;
     if (!c0 || !cd)
     {
         flag = 2;
-        need = c0 ? kd : k;
         return;
     }
-    const int hv = ell == 0 ? w.v : (int)c0[jj];
+    const int hv = ell == 0 ? w.v : cellH(*c0);
     if (hv <= 0)
         return;
     const uint8_t refc = chars[g.node_start[w.n] + ii];
     const uint8_t readc = read_char(bases, L, 0, half, jj);
-    dval = (int)cd[jj - 1];
+    dval = cellH(*cd);
     op = match_op(refc, readc);
     flag = (hv == dval + sub_score(nt_code(refc), nt_code(readc))) ? 1 : 0;
 }
 
-// Returns the run length (0..32); on 0, need >= 0 means the current cell's own probe missed a tile.
-// Warp-uniform on the device (every lane calls it with identical walker state and its own lane id).
+// Returns the run length (0..32) and logs the run's ops run-length encoded; on 0, miss0 tells that the current
+// cell's own probe missed a tile.  Warp-uniform on the device (every lane calls it with identical walker state
+// and its own lane id); the host version loops over the 32 probes.
 template <int R>
 PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars, const uint8_t* bases,
-                   int L, int half, int lane, uint32_t* oplog, int oplog_cap, int& vnew, int& need)
+                   int L, int half, int lane, uint32_t* oplog, int oplog_cap, int& vnew, bool& miss0)
 {
-    int run = 0;
+    int run = 0, nent = 0;
 #if defined(__CUDA_ARCH__)
-    int flag, dval, op, nd;
-    diag_probe<R>(lane, w, tb, g, chars, bases, L, half, flag, dval, op, nd);
+    int flag, dval, op;
+    diag_probe<R>(lane, w, tb, g, chars, bases, L, half, flag, dval, op);
     const unsigned yes = __ballot_sync(0xffffffffu, flag == 1);
     run = (yes == 0xffffffffu) ? 32 : (__ffs((int)~yes) - 1);
-    if (lane < run)
-    {
-        if (w.nops + lane < oplog_cap)
-            oplog[w.nops + lane] = cigar_word(w.n, op, 1);
-    }
+    miss0 = (__shfl_sync(0xffffffffu, flag, 0) == 2);
     vnew = __shfl_sync(0xffffffffu, dval, run > 0 ? run - 1 : 0);
-    need = __shfl_sync(0xffffffffu, flag == 2 ? nd : -1, 0);
+    // run-length encode: a lane starts an entry when its op differs from the previous lane's
+    const int prev = __shfl_up_sync(0xffffffffu, op, 1);
+    const bool in = lane < run;
+    const unsigned starts = __ballot_sync(0xffffffffu, in && (lane == 0 || op != prev));
+    if (in && ((starts >> lane) & 1u))
+    {
+        const unsigned above = starts & ~((2u << lane) - 1u); // entry starts after this lane
+        const int nxt = above ? (__ffs((int)above) - 1) : run;
+        const int idx = w.nops + __popc(starts & ((1u << lane) - 1u));
+        if (idx < oplog_cap)
+            oplog[idx] = cigar_word(w.n, op, nxt - lane);
+    }
+    nent = __popc(starts);
 #else
     (void)lane;
-    need = -1;
+    miss0 = false;
     vnew = 0;
+    int last_op = -1;
     for (int ell = 0; ell < 32; ++ell)
     {
-        int flag, dval, op, nd;
-        diag_probe<R>(ell, w, tb, g, chars, bases, L, half, flag, dval, op, nd);
+        int flag, dval, op;
+        diag_probe<R>(ell, w, tb, g, chars, bases, L, half, flag, dval, op);
         if (ell == 0 && flag == 2)
-            need = nd;
+            miss0 = true;
         if (flag != 1)
             break;
-        if (w.nops + ell < oplog_cap)
-            oplog[w.nops + ell] = cigar_word(w.n, op, 1);
+        if (op == last_op)
+        {
+            if (w.nops + nent - 1 < oplog_cap)
+                oplog[w.nops + nent - 1] += 1u << 3;
+        }
+        else
+        {
+            if (w.nops + nent < oplog_cap)
+                oplog[w.nops + nent] = cigar_word(w.n, op, 1);
+            ++nent;
+            last_op = op;
+        }
         vnew = dval;
         ++run;
     }
 #endif
     if (run > 0)
     {
-        if (w.nops + run > oplog_cap)
+        if (w.nops + nent > oplog_cap)
             w.status = 2;
-        w.nops += run;
+        w.nops += nent;
     }
     return run;
 }
@@ -756,7 +822,6 @@ template <int R>
 PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars, const uint32_t* last,
                 const uint8_t* bases, int L, int half, const TaskOut& fo, uint32_t* oplog, int oplog_cap, int lane)
 {
-    constexpr int ROWS = Sizes<R>::ROWS;
     if (w.phase == 0)
     {
         // end cell: smallest row of end_lane holding S at end_step (gssw.c:446-454)
@@ -767,19 +832,22 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
             w.phase = 2;
             return true;
         }
-        const uint8_t* t0 = tb.find(fo.end_step[half]);
-        if (!t0)
-        {
-            w.need_step = fo.end_step[half];
-            return false;
-        }
         int row = -1;
         for (int r = 0; r < R; ++r)
-            if (t0[R * fo.end_lane[half] + r] == S)
+        {
+            const uint32_t* t0 = tb.find(fo.end_step[half], R * fo.end_lane[half] + r);
+            if (!t0)
+            {
+                w.need_step = fo.end_step[half];
+                w.need_row = R * fo.end_lane[half] + R - 1;
+                return false;
+            }
+            if (cellH(*t0) == S)
             {
                 row = R * fo.end_lane[half] + r;
                 break;
             }
+        }
         if (row < 0)
         {
             w.status = 1;
@@ -804,10 +872,11 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
         {
             const int k = g.node_start[w.n] + w.i + w.j / R; // step of the current cell
             // neighbours: (i-1,j-1) -> step k-1 or k-2; (i-1,j) -> k-1; (i,j-1) -> k or k-1
-            const uint8_t* c0 = tb.find(k);
+            const uint32_t* c0 = tb.find(k, w.j);
             if (!c0)
             {
                 w.need_step = k;
+                w.need_row = w.j;
                 return false;
             }
             const int kl = k - ((w.j % R) == 0 ? 1 : 0);     // step of (i, j-1)
@@ -818,13 +887,14 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                     leave = true;
                     break;
                 }
-                const uint8_t* c1 = tb.find(k - 1);
+                const uint32_t* c1 = tb.find(k - 1, w.j);
                 if (!c1)
                 {
                     w.need_step = k - 1;
+                    w.need_row = w.j;
                     return false;
                 }
-                if (w.v == (int)c1[w.j] - GAP_OPEN) // gssw.c:1347-1383
+                if (w.v == cellH(*c1) - GAP_OPEN) // gssw.c:1347-1383
                 {
                     push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
                     w.v += GAP_OPEN;
@@ -832,7 +902,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                     w.st = 0;
                     continue;
                 }
-                if (w.v == (int)c1[ROWS + w.j] - GAP_EXT) // gssw.c:1400-1423
+                if (w.v == cellE(*c1) - GAP_EXT) // gssw.c:1400-1423
                 {
                     push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
                     w.v += GAP_EXT;
@@ -847,13 +917,14 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
             {
                 if (w.j > 0)
                 {
-                    const uint8_t* cl = tb.find(kl);
+                    const uint32_t* cl = tb.find(kl, w.j - 1);
                     if (!cl)
                     {
                         w.need_step = kl;
+                        w.need_row = w.j;
                         return false;
                     }
-                    if (w.v == (int)cl[w.j - 1] - GAP_OPEN) // gssw.c:1458-1493
+                    if (w.v == cellH(*cl) - GAP_OPEN) // gssw.c:1458-1493
                     {
                         push_op(w, oplog, oplog_cap, w.n, OP_I, 1);
                         w.v += GAP_OPEN;
@@ -861,7 +932,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                         w.st = 0;
                         continue;
                     }
-                    if (w.v == (int)cl[2 * ROWS + w.j - 1] - GAP_EXT) // gssw.c:1510-1532
+                    if (w.v == cellF(*cl) - GAP_EXT) // gssw.c:1510-1532
                     {
                         push_op(w, oplog, oplog_cap, w.n, OP_I, 1);
                         w.v += GAP_EXT;
@@ -879,8 +950,9 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
             const int s = sub_score(nt_code(refc), nt_code(readc));
             if (w.i > 0 && w.j > 0)
             {
-                int vnew, need;
-                const int run = diag_run<R>(w, tb, g, chars, bases, L, half, lane, oplog, oplog_cap, vnew, need);
+                int vnew;
+                bool miss0;
+                const int run = diag_run<R>(w, tb, g, chars, bases, L, half, lane, oplog, oplog_cap, vnew, miss0);
                 if (run > 0) // diagonal moves, gssw.c:1591-1637
                 {
                     w.v = vnew;
@@ -888,9 +960,10 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                     w.j -= run;
                     continue;
                 }
-                if (need >= 0)
+                if (miss0) // the diagonal neighbour (i-1, j-1) is not resident
                 {
-                    w.need_step = need;
+                    w.need_step = k - 1 - ((w.j % R) == 0 ? 1 : 0);
+                    w.need_row = w.j;
                     return false;
                 }
             }
@@ -905,12 +978,12 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                 w.v -= s;
                 continue;
             }
-            if (w.j > 0 && w.v == (int)c0[2 * ROWS + w.j]) // H == F, gssw.c:1709-1729
+            if (w.j > 0 && w.v == cellF(*c0)) // H == F, gssw.c:1709-1729
             {
                 w.st = 2;
                 continue;
             }
-            if (w.v == (int)c0[ROWS + w.j]) // H == E, gssw.c:1747-1768
+            if (w.v == cellE(*c0)) // H == E, gssw.c:1747-1768
             {
                 w.st = 1;
                 continue;

@@ -147,7 +147,6 @@ struct TraceArgs
 template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_kernel(const TraceArgs a)
 {
     extern __shared__ uint32_t smem[];
-    constexpr int ROWS = Sizes<R>::ROWS;
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lrd = blockIdx.x * TRACE_WARPS + wic;
     if (lrd >= a.n_reads)
@@ -156,7 +155,7 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
     uint8_t* wmem = reinterpret_cast<uint8_t*>(smem) + (size_t)wic * a.smem_bytes_per_warp;
     uint32_t* prof = reinterpret_cast<uint32_t*>(wmem);
     uint32_t* oplog = prof + NCODE * R * 32;
-    uint8_t* tiles = reinterpret_cast<uint8_t*>(oplog + a.oplog_cap);
+    uint32_t* tiles = oplog + a.oplog_cap;
 
     const SiteDev sd = a.sites[a.read_site ? a.read_site[rd] : 0];
     const GraphView g = make_view(sd, a.gbytes, a.gints, 0);
@@ -174,6 +173,7 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
     TileBuf<R> tb;
     tb.mem = tiles;
     tb.tile0 = tb.tile1 = -1;
+    tb.blo0 = tb.blo1 = 0;
     tb.lru = 0;
     Walker w;
     memset(&w, 0, sizeof w);
@@ -186,14 +186,15 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
         if (walk<R>(w, tb, g, chars, last, bases, L, half, fw, oplog, a.oplog_cap, lane))
             break;
         const int T = w.need_step / CK;
-        const int slot = tb.admit(T);
+        int blo;
+        const int slot = tb.admit(T, w.need_row, blo);
         __syncwarp();
         // recompute tile T from its checkpoint
         Lane<R> s;
         LaneCtl c;
         ckpt_load<R>(s, ckpt + (size_t)T * (2 * R + 2) * 32, lane);
         ctl_at_step(c, g, T * CK, lane);
-        uint8_t* dst = tiles + (size_t)slot * CK * 3 * ROWS;
+        uint32_t* dst = tiles + (size_t)slot * TileGeom<R>::SLOT_WORDS;
 #pragma unroll 2
         for (int kk = 0; kk < CK; ++kk)
         {
@@ -211,7 +212,7 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
             }
             uint32_t Hc[R], Ec[R], Fc[R];
             lane_step<R, true>(s, rh, rf, prof, codes[k], lane, Hc, Ec, Fc);
-            tile_store<R>(dst + (size_t)kk * 3 * ROWS, lane, Hc, Ec, Fc, half);
+            tile_store<R>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, lane, blo, Hc, Ec, Fc, half);
         }
         __syncwarp();
     }
@@ -396,7 +397,7 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
 
     const int fill_words = NCODE * R * 32 + max_nodes * 2 * R * 32;
     const size_t fill_smem = (size_t)FILL_WARPS * fill_words * sizeof(uint32_t);
-    const int trace_bytes = (NCODE * R * 32 + oplog_cap) * 4 + 2 * CK * 3 * Sizes<R>::ROWS;
+    const int trace_bytes = (NCODE * R * 32 + oplog_cap + 2 * TileGeom<R>::SLOT_WORDS) * 4;
     const int trace_bytes_al = (trace_bytes + 15) & ~15;
     const size_t trace_smem = (size_t)TRACE_WARPS * trace_bytes_al;
     if (fill_smem > 227 * 1024 || trace_smem > 227 * 1024)

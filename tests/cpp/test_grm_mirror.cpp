@@ -18,7 +18,7 @@ int main()
     reads[3].setCoreInfo("f4", "AAAAGCGGGGGGAAAAAA", "##################");
     reads[4].setCoreInfo("f5", "TTTTTTCCCCCCGCTTTTT", "###################");
     reads[5].setCoreInfo("f6", "AAAAAAAAAAAAAAAAAAA", "###################");
-    reads[6].setCoreInfo("f7", "CCCCCCCCCCCC", "############"); // scores 0 everywhere -> not unique -> filtered below
+    reads[6].setCoreInfo("f7", "ATATATAT", "########"); // best score ends in several nodes on both strands -> not unique -> filtered
     Graph graph(4);
     graph.setNodeSeq(0, "AAAAAAAAAAA");
     graph.setNodeSeq(1, "TTTTTTTT");

@@ -65,7 +65,7 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
 
 template <int R>
 void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::vector<uint32_t>& ckpt,
-              std::vector<uint32_t>& last, int T, uint8_t* dst, int half)
+              std::vector<uint32_t>& last, int T, int blo, uint32_t* dst, int half)
 {
     Lane<R> s[32];
     LaneCtl c[32];
@@ -89,7 +89,7 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
         {
             uint32_t Hc[R], Ec[R], Fc[R];
             lane_step<R, true>(s[t], rh[t], rf[t], prof.data(), g.codes[k - t], t, Hc, Ec, Fc);
-            tile_store<R>(dst + (size_t)kk * 3 * Sizes<R>::ROWS, t, Hc, Ec, Fc, half);
+            tile_store<R>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, t, blo, Hc, Ec, Fc, half);
         }
     }
 }
@@ -109,10 +109,11 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     std::vector<uint32_t> prof((size_t)NCODE * R * 32);
     for (int t = 0; t < 32; ++t)
         build_profile<R>(prof.data(), bases, L, 0, t);
-    std::vector<uint8_t> tiles((size_t)2 * CK * 3 * Sizes<R>::ROWS, 0);
+    std::vector<uint32_t> tiles((size_t)2 * TileGeom<R>::SLOT_WORDS, 0);
     TileBuf<R> tb;
     tb.mem = tiles.data();
     tb.tile0 = tb.tile1 = -1;
+    tb.blo0 = tb.blo1 = 0;
     tb.lru = 0;
     Walker w;
     memset(&w, 0, sizeof w);
@@ -122,8 +123,9 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     while (!walk<R>(w, tb, g0, chars, last.data(), bases, L, d.half, fw, oplog.data(), (int)oplog.size(), 0))
     {
         const int T = w.need_step / CK;
-        const int slot = tb.admit(T);
-        emu_tile<R>(g0, prof, ckpt, last, T, tiles.data() + (size_t)slot * CK * 3 * Sizes<R>::ROWS, d.half);
+        int blo;
+        const int slot = tb.admit(T, w.need_row, blo);
+        emu_tile<R>(g0, prof, ckpt, last, T, blo, tiles.data() + (size_t)slot * TileGeom<R>::SLOT_WORDS, d.half);
         if (n_tiles)
             ++*n_tiles;
         if (++guard > 100000)
