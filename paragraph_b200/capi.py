@@ -112,6 +112,8 @@ class Context:
                           "paragraph_b200 has no CPU fallback" % (device, rc))
         self.h = h
         self._keep = None
+        self._rec = None   # output buffers are reused between calls of the same size (no per-call allocation)
+        self._ops = None
         if stream is not None:
             self.set_stream(stream)
 
@@ -156,28 +158,45 @@ class Context:
     def run(self, flags=AF_ALL):
         self._check(self.lib.pg_batch_run(self.h, flags & 0xFFFFFFFF))
 
+    def _out_buffers(self, n, cigar_cap):
+        cap = int(cigar_cap or n * 64 + 4096)
+        if self._rec is None or len(self._rec) != n:
+            self._rec = np.empty(n, dtype=RECORD_DTYPE)
+        if self._ops is None or len(self._ops) < cap:
+            self._ops = np.empty(cap, dtype=np.uint32)
+        return self._rec, self._ops, len(self._ops)
+
     def download(self, cigar_cap=None):
+        """Returns (records, ops) as views of buffers owned by the context: valid until the next call."""
         n = self._n
-        rec = np.zeros(n, dtype=RECORD_DTYPE)
-        cap = int(cigar_cap or n * 320)
-        ops = np.zeros(cap, dtype=np.uint32)
-        used = C.c_uint64(0)
-        self._check(self.lib.pg_batch_download(self.h, C.c_void_p(rec.ctypes.data),
-                                               ops.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(used)))
-        return rec, ops[:used.value]
+        for attempt in range(2):
+            rec, ops, cap = self._out_buffers(n, cigar_cap)
+            used = C.c_uint64(0)
+            rc = self.lib.pg_batch_download(self.h, C.c_void_p(rec.ctypes.data),
+                                            ops.ctypes.data_as(C.POINTER(C.c_uint32)), cap, C.byref(used))
+            if rc == -5 and attempt == 0 and cigar_cap is None:  # PG_E_CAPACITY: retry with the worst-case arena
+                cigar_cap = n * 520 + 4096
+                continue
+            self._check(rc)
+            return rec, ops[:used.value]
 
     # ---- one-call API (host buffers in, host buffers out) -----------------------------------------
     def align_packed(self, blob, off, sites=None, flags=AF_ALL, cigar_cap=None):
+        """One pg_align_batch call.  Returns (records, ops) as views of buffers owned by the context (valid until
+        the next call).  If the default CIGAR arena is too small the call is repeated once with a full-size one."""
         n = len(off) - 1
-        rec = np.zeros(n, dtype=RECORD_DTYPE)
-        cap = int(cigar_cap or n * 320)
-        ops = np.zeros(cap, dtype=np.uint32)
-        used = C.c_uint64(0)
-        self._check(self.lib.pg_align_batch(self.h, n, C.c_void_p(blob.ctypes.data), _i32(off),
-                                            _i32(sites) if sites is not None else None, flags & 0xFFFFFFFF,
-                                            C.c_void_p(rec.ctypes.data), ops.ctypes.data_as(C.POINTER(C.c_uint32)),
-                                            cap, C.byref(used)))
-        return rec, ops[:used.value]
+        for attempt in range(2):
+            rec, ops, cap = self._out_buffers(n, cigar_cap)
+            used = C.c_uint64(0)
+            rc = self.lib.pg_align_batch(self.h, n, C.c_void_p(blob.ctypes.data), _i32(off),
+                                         _i32(sites) if sites is not None else None, flags & 0xFFFFFFFF,
+                                         C.c_void_p(rec.ctypes.data), ops.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                         cap, C.byref(used))
+            if rc == -5 and attempt == 0 and cigar_cap is None:  # PG_E_CAPACITY: adversarial CIGARs, take the worst case
+                cigar_cap = n * 520 + 4096
+                continue
+            self._check(rc)
+            return rec, ops[:used.value]
 
     def align(self, reads, sites=None, is_rev=None, flags=AF_ALL):
         """Align python strings; returns dicts with the fields GraphAligner::alignRead sets on common::Read."""

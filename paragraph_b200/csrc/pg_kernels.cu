@@ -92,6 +92,7 @@ template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kern
         if (save)
             ckpt_store<R>(s, ckpt + (size_t)cki * (2 * R + 2) * 32, lane);
         const int kbase = cki * CK;
+        const uint8_t* cp = codes + kbase; // per-lane pointer, immediate offsets inside the unrolled body
 #pragma unroll 4
         for (int kk = 0; kk < CK; ++kk)
         {
@@ -108,7 +109,7 @@ template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kern
                 rh = 0;
                 rf = 0;
             }
-            const int code = codes[k];
+            const int code = cp[kk];
             const uint32_t m = lane_step<R, false>(s, rh, rf, prof, code, lane, nullptr, nullptr, nullptr);
             track_max(c, m, k);
         }
