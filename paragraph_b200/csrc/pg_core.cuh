@@ -25,9 +25,11 @@
 
 #if defined(__CUDACC__)
 #define PG_HD __host__ __device__ __forceinline__
+#define PG_HD_COLD __host__ __device__ __noinline__ // rare paths: keep them out of the hot loop's I-cache footprint
 #define PG_UNROLL _Pragma("unroll")
 #else
 #define PG_HD inline
+#define PG_HD_COLD inline
 #define PG_UNROLL
 #endif
 
@@ -325,7 +327,7 @@ PG_HD void track_max(LaneCtl& c, uint32_t m, int k)
 // simply carries over.  The diagonal into this lane's first row comes from the seed row just above it,
 // i.e. lane-1's last word of each predecessor (written by lane-1 at least one step earlier).
 template <int R, bool FILL>
-PG_HD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* seedS, uint32_t* lastG,
+PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* seedS, uint32_t* lastG,
                       uint32_t* infoG, bool save_trace)
 {
     if (c.colsLeft == 0)

@@ -99,7 +99,14 @@ template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kern
             const int k = kbase + kk;
             __syncwarp();
             if (c.colsLeft <= 1)
-                node_event<R, true>(s, c, g, lane, seedS, last, info, save);
+            {
+                // rare, per lane: the out-of-line handler works on copies so that the hot loop's state stays in registers
+                Lane<R> ts = s;
+                LaneCtl tc = c;
+                node_event<R, true>(ts, tc, g, lane, seedS, last, info, save);
+                s = ts;
+                c = tc;
+            }
             else
                 --c.colsLeft;
             uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1);
@@ -201,7 +208,13 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
         {
             const int k = T * CK + kk;
             if (c.colsLeft <= 1)
-                node_event<R, false>(s, c, g, lane, nullptr, const_cast<uint32_t*>(last), nullptr, false);
+            {
+                Lane<R> ts = s;
+                LaneCtl tc = c;
+                node_event<R, false>(ts, tc, g, lane, nullptr, const_cast<uint32_t*>(last), nullptr, false);
+                s = ts;
+                c = tc;
+            }
             else
                 --c.colsLeft;
             uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1);
