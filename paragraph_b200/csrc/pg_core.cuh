@@ -25,7 +25,7 @@
 
 #if defined(__CUDACC__)
 #define PG_HD __host__ __device__ __forceinline__
-#define PG_HD_COLD __host__ __device__ __noinline__ // rare paths: keep them out of the hot loop's I-cache footprint
+#define PG_HD_COLD __host__ __device__ __forceinline__
 #define PG_UNROLL _Pragma("unroll")
 #else
 #define PG_HD inline
@@ -183,7 +183,7 @@ template <int R> struct Lane
 template <int R> struct Sizes
 {
     static constexpr int CKW = 2 * R + 2;  // Hp[R], E[R], hupPrev, foutLast   (hbotLast == Hp[R-1])
-    static constexpr int LASTW = 3 * R;    // node last column: H[R], E leaving it [R] (the seed), E entering it [R]
+    static constexpr int LASTW = 2 * R;    // node last column: H[R], E leaving it [R] (= the seed of its successors)
     static constexpr int ROWS = 32 * R;
 };
 
@@ -318,17 +318,17 @@ PG_HD void track_max(LaneCtl& c, uint32_t m, int k)
 }
 
 // Node boundary handling at the top of a step (rare, per lane: lanes reach a boundary at different steps).
-//   FILL = true  (fill kernel): save the finished node's last column as seed (seedS, warp-private shared
-//                memory [node][2R][32]) and, for forward-graph tasks (save_trace), to lastG for the
-//                traceback; save the node maximum (infoG); then load the next node's seed.
-//   FILL = false (tile recomputation in the traceback kernel): only load the next node's seed, from lastG.
+//   FILL = true  (fill kernel): save the finished node's last column (H, E leaving it) into the warp-private
+//                shared-memory seed table and the lane's node maximum / first step into infoS; then load the next
+//                node's seed from the seed table.  (The fill kernel copies the seed table to HBM once, at the end
+//                of a forward-graph task, for the traceback.)
+//   FILL = false (tile recomputation in the traceback kernel): only load the next node's seed, from that copy.
 // Seed of a node = element-wise max over its predecessors' last columns (gssw_create_seed_byte,
 // gssw.c:3897-3931), zeros for a source; if the only predecessor is the node just finished the state
 // simply carries over.  The diagonal into this lane's first row comes from the seed row just above it,
 // i.e. lane-1's last word of each predecessor (written by lane-1 at least one step earlier).
 template <int R, bool FILL>
-PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* seedS, uint32_t* lastG,
-                      uint32_t* infoG, bool save_trace)
+PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* seeds, uint32_t* infoS)
 {
     if (c.colsLeft == 0)
     {
@@ -337,18 +337,12 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
         {
             for (int r = 0; r < R; ++r)
             {
-                seedS[(n * 2 * R + r) * 32 + lane] = s.Hp[r];
-                seedS[(n * 2 * R + R + r) * 32 + lane] = s.E[r];
+                seeds[(n * 2 * R + r) * 32 + lane] = s.Hp[r];
+                seeds[(n * 2 * R + R + r) * 32 + lane] = s.E[r];
             }
-            if (save_trace)
-                for (int r = 0; r < R; ++r)
-                {
-                    lastG[(n * 3 * R + r) * 32 + lane] = s.Hp[r];
-                    lastG[(n * 3 * R + R + r) * 32 + lane] = s.E[r];
-                }
-            infoG[(n * 3 + 0) * 32 + lane] = c.Mnode;
-            infoG[(n * 3 + 1) * 32 + lane] = (uint32_t)c.first[0];
-            infoG[(n * 3 + 2) * 32 + lane] = (uint32_t)c.first[1];
+            infoS[(n * 3 + 0) * 32 + lane] = c.Mnode;
+            infoS[(n * 3 + 1) * 32 + lane] = (uint32_t)c.first[0];
+            infoS[(n * 3 + 2) * 32 + lane] = (uint32_t)c.first[1];
             c.Mnode = 0;
         }
         c.node = n + 1;
@@ -363,8 +357,7 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
                     H[r] = E[r] = 0;
                 for (int e = p0; e < p1; ++e)
                 {
-                    const int p = g.pred_idx[e];
-                    const uint32_t* src = FILL ? seedS + (size_t)p * 2 * R * 32 : lastG + (size_t)p * 3 * R * 32;
+                    const uint32_t* src = seeds + (size_t)g.pred_idx[e] * 2 * R * 32;
                     for (int r = 0; r < R; ++r)
                     {
                         H[r] = max2(H[r], src[r * 32 + lane]);
@@ -384,9 +377,6 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
         else
             c.colsLeft = COLS_INF;
     }
-    if (FILL && save_trace && c.colsLeft == 1) // about to process the node's last column: keep E entering it
-        for (int r = 0; r < R; ++r)
-            lastG[(c.node * 3 * R + 2 * R + r) * 32 + lane] = s.E[r];
     --c.colsLeft;
 }
 
@@ -457,7 +447,7 @@ PG_HD void tile_store(uint32_t* tstep, int lane, int blo, const uint32_t* Hc, co
 // per-task scratch layout (32-bit words, [..][32 lanes] innermost so that a warp store is one 128 B line)
 // ---------------------------------------------------------------------------------------------
 //   info  [n_nodes][3][32]      : per node and lane: packed node maximum, first step reaching it (half 0, half 1)
-//   last  [n_nodes][3R][32]     : node last column: H, E leaving (seed), E entering  (forward-graph tasks only)
+//   last  [n_nodes][2R][32]     : node last column: H, E leaving it (seed)            (forward-graph tasks only)
 //   ckpt  [n_ck][2R+2][32]      : lane state before step c*CK                      (forward-graph tasks only)
 PG_HD int num_steps(int G) { return G + 32; } // lane 31 ends column G-1 at step G+30; its node event runs at step G+31
 PG_HD int num_ckpt(int G) { return (num_steps(G) + CK - 1) / CK; }
@@ -474,11 +464,7 @@ struct TaskOut // result of one fill (two packed problems)
 // Serial reduction of the per-(node, lane) maxima written by the fill (run by one lane at the end of a task).
 // Best cell per gssw: first node in array order whose maximum is the global one, first column in it, smallest
 // row in that column (gssw.c:378-386, 446-454, 4015-4018) -> min column = min(step - lane), ties -> smaller lane.
-#if defined(__CUDA_ARCH__)
-PG_HD uint32_t ld_scratch(const uint32_t* p) { return __ldcg(p); } // written by other lanes of this warp: read at L2
-#else
-PG_HD uint32_t ld_scratch(const uint32_t* p) { return *p; }
-#endif
+PG_HD uint32_t ld_scratch(const uint32_t* p) { return *p; } // warp-private shared memory (after a __syncwarp)
 
 PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o)
 {
@@ -819,7 +805,7 @@ PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const ui
 // (w.need_step set).  Mirrors gssw_alignment_trace_back_byte (gssw.c:1112-1818, final_traceback = 1, no
 // deflections) and the cross-node part of gssw_graph_trace_back_internal (gssw.c:2836-3148, 3486-3528).
 //   g      forward graph view;  chars = upper-cased graph characters (column-indexed like codes)
-//   last   this read's saved node last columns [n_nodes][3R][32] (packed words)
+//   last   this read's saved node last columns [n_nodes][2R][32] (packed words)
 template <int R>
 PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars, const uint32_t* last,
                 const uint8_t* bases, int L, int half, const TaskOut& fo, uint32_t* oplog, int oplog_cap, int lane)
@@ -1019,7 +1005,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
         for (int e = g.pred_ptr[w.n]; e < g.pred_ptr[w.n + 1]; ++e)
         {
             const int c = g.pred_idx[e];
-            const uint32_t* lc = last + (size_t)c * (3 * R) * 32;
+            const uint32_t* lc = last + (size_t)c * (2 * R) * 32;
             if (w.st == 0)
             {
                 // diagonal source = pred's last column at row j-1 (row -1 never matches: H(0,0) is start or E)
@@ -1044,13 +1030,27 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                     w.st = 0;
                     break;
                 }
-                const int esrc = imax0(half16(lc[(2 * R + w.j % R) * 32 + w.j / R], half)); // E entering pred's last column
-                if (w.v == esrc - GAP_EXT) // extend, gssw.c:3122-3136
+                // extend: the reference tests v == E_c(last, j) - ge with E *entering* pred's last column
+                // (gssw.c:3122-3136).  Saved is the seed E' = max(E - ge, t - go) >= E - ge, and v >= E' (v is the max
+                // of the seeds), so v == E' is necessary; only then is the exact E read from pred's last-column tile.
+                const int eseed = imax0(half16(lc[(R + w.j % R) * 32 + w.j / R], half));
+                if (w.v == eseed)
                 {
-                    best = c;
-                    push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
-                    w.v += GAP_EXT;
-                    break;
+                    const int kc = g.node_start[c] + g.node_len[c] - 1 + w.j / R;
+                    const uint32_t* cc = tb.find(kc, w.j);
+                    if (!cc)
+                    {
+                        w.need_step = kc;
+                        w.need_row = w.j;
+                        return false; // nothing has been changed yet: the predecessor scan restarts after the reload
+                    }
+                    if (w.v == cellE(*cc) - GAP_EXT)
+                    {
+                        best = c;
+                        push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
+                        w.v += GAP_EXT;
+                        break;
+                    }
                 }
             }
         }

@@ -41,10 +41,10 @@ struct FillArgs
     int read0;                // first read of this chunk
     int n_tasks;              // 2 * reads in chunk
     unsigned flags;
-    uint32_t* info; // [task in chunk][stride_info]
     uint32_t* last; // [read in chunk][stride_last]
     uint32_t* ckpt; // [read in chunk][stride_ckpt]
-    size_t stride_info, stride_last, stride_ckpt;
+    size_t stride_last, stride_ckpt;
+    int n_nodes_cap; // seed / info table capacity per warp (nodes)
     TaskOut* tout; // [2 * n_reads] (global task index)
     int smem_words_per_warp;
 };
@@ -69,7 +69,8 @@ template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kern
         return;
     }
     uint32_t* prof = smem + (size_t)wic * a.smem_words_per_warp;
-    uint32_t* seedS = prof + NCODE * R * 32;
+    uint32_t* seedS = prof + NCODE * R * 32;               // [n_nodes_cap][2R][32]
+    uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * 32;  // [n_nodes_cap][3][32]
     const SiteDev sd = a.sites[a.read_site ? a.read_site[rd] : 0];
     const GraphView g = make_view(sd, a.gbytes, a.gints, o);
     const uint8_t* bases = a.bases + a.read_off[rd];
@@ -82,7 +83,6 @@ template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kern
     LaneCtl c;
     ctl_at_step(c, g, 0, lane);
     const bool save = (o == 0);
-    uint32_t* info = a.info + (size_t)ltask * a.stride_info;
     uint32_t* last = a.last + (size_t)(ltask >> 1) * a.stride_last;
     uint32_t* ckpt = a.ckpt + (size_t)(ltask >> 1) * a.stride_ckpt;
     const uint8_t* codes = g.codes - lane;
@@ -98,15 +98,8 @@ template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kern
         {
             const int k = kbase + kk;
             __syncwarp();
-            if (c.colsLeft <= 1)
-            {
-                // rare, per lane: the out-of-line handler works on copies so that the hot loop's state stays in registers
-                Lane<R> ts = s;
-                LaneCtl tc = c;
-                node_event<R, true>(ts, tc, g, lane, seedS, last, info, save);
-                s = ts;
-                c = tc;
-            }
+            if (c.colsLeft == 0) // rare, per lane: node boundary
+                node_event<R, true>(s, c, g, lane, seedS, infoS);
             else
                 --c.colsLeft;
             uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1);
@@ -122,10 +115,13 @@ template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kern
         }
     }
     __syncwarp();
+    if (save) // node last columns for the traceback kernel: one coalesced copy of the seed table
+        for (int x = lane; x < g.n_nodes * 2 * R * 32; x += 32)
+            last[x] = seedS[x];
     if (lane == 0)
     {
         TaskOut t;
-        finalize_task(info, g.n_nodes, t);
+        finalize_task(infoS, g.n_nodes, t);
         *to = t;
     }
 }
@@ -207,14 +203,8 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
         for (int kk = 0; kk < CK; ++kk)
         {
             const int k = T * CK + kk;
-            if (c.colsLeft <= 1)
-            {
-                Lane<R> ts = s;
-                LaneCtl tc = c;
-                node_event<R, false>(ts, tc, g, lane, nullptr, const_cast<uint32_t*>(last), nullptr, false);
-                s = ts;
-                c = tc;
-            }
+            if (c.colsLeft == 0)
+                node_event<R, false>(s, c, g, lane, const_cast<uint32_t*>(last), nullptr);
             else
                 --c.colsLeft;
             uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1);
@@ -339,7 +329,7 @@ struct pg_ctx
     PinBuf<int32_t> h_off, h_site;
     DevBuf<uint8_t> d_bases;
     DevBuf<int32_t> d_off, d_site;
-    DevBuf<uint32_t> d_info, d_last, d_ckpt, d_arena;
+    DevBuf<uint32_t> d_last, d_ckpt, d_arena;
     DevBuf<TaskOut> d_tout;
     DevBuf<Record> d_records;
     DevBuf<unsigned long long> d_cursor;
@@ -390,15 +380,13 @@ int upload_graphs(pg_ctx* c)
 template <int R> int run_chunks(pg_ctx* c, unsigned flags)
 {
     const int max_nodes = c->graphs.max_nodes, max_G = c->graphs.max_G;
-    const size_t s_info = host::info_words(max_nodes), s_last = host::last_words(max_nodes, R),
-                 s_ckpt = host::ckpt_words(max_G, R);
-    const size_t per_read_bytes = (2 * s_info + s_last + s_ckpt) * sizeof(uint32_t);
+    const size_t s_last = host::last_words(max_nodes, R), s_ckpt = host::ckpt_words(max_G, R);
+    const size_t per_read_bytes = (s_last + s_ckpt) * sizeof(uint32_t);
     size_t chunk = (size_t)(c->scratch_limit / (per_read_bytes ? per_read_bytes : 1));
     if (chunk < 1)
         chunk = 1;
     if (chunk > (size_t)c->n_reads)
         chunk = (size_t)c->n_reads;
-    PG_CUDA(c, c->d_info.reserve(chunk * 2 * s_info));
     PG_CUDA(c, c->d_last.reserve(chunk * s_last));
     PG_CUDA(c, c->d_ckpt.reserve(chunk * s_ckpt));
     PG_CUDA(c, c->d_tout.reserve((size_t)c->n_reads * 2));
@@ -409,7 +397,7 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
     PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
     PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
 
-    const int fill_words = NCODE * R * 32 + max_nodes * 2 * R * 32;
+    const int fill_words = NCODE * R * 32 + max_nodes * (2 * R + 3) * 32;
     const size_t fill_smem = (size_t)FILL_WARPS * fill_words * sizeof(uint32_t);
     const int trace_bytes = (NCODE * R * 32 + oplog_cap + 2 * TileGeom<R>::SLOT_WORDS) * 4;
     const int trace_bytes_al = (trace_bytes + 15) & ~15;
@@ -436,10 +424,9 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
         fa.read0 = (int)r0;
         fa.n_tasks = 2 * nr;
         fa.flags = flags;
-        fa.info = c->d_info.p;
         fa.last = c->d_last.p;
         fa.ckpt = c->d_ckpt.p;
-        fa.stride_info = s_info;
+        fa.n_nodes_cap = max_nodes;
         fa.stride_last = s_last;
         fa.stride_ckpt = s_ckpt;
         fa.tout = c->d_tout.p;
@@ -537,7 +524,6 @@ void pg_destroy(pg_ctx* c)
     c->d_bases.release();
     c->d_off.release();
     c->d_site.release();
-    c->d_info.release();
     c->d_last.release();
     c->d_ckpt.release();
     c->d_arena.release();

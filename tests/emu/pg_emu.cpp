@@ -34,10 +34,7 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
     }
     info.assign(host::info_words(g.n_nodes), 0);
     if (save_trace)
-    {
-        last.assign(host::last_words(g.n_nodes, R), 0);
         ckpt.assign(host::ckpt_words(g.G, R), 0);
-    }
     const int nck = num_ckpt(g.G);
     for (int k = 0; k < nck * CK; ++k)
     {
@@ -45,8 +42,10 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
             for (int t = 0; t < 32; ++t)
                 ckpt_store<R>(s[t], ckpt.data() + (size_t)(k / CK) * (2 * R + 2) * 32, t);
         for (int t = 0; t < 32; ++t) // events read what lane t-1 wrote at an EARLIER step only
-            node_event<R, true>(s[t], c[t], g, t, seedS.data(), save_trace ? last.data() : nullptr, info.data(),
-                                save_trace);
+            if (c[t].colsLeft == 0)
+                node_event<R, true>(s[t], c[t], g, t, seedS.data(), info.data());
+            else
+                --c[t].colsLeft;
         uint32_t rh[32], rf[32];
         for (int t = 0; t < 32; ++t)
         {
@@ -60,6 +59,8 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
             track_max(c[t], m, k);
         }
     }
+    if (save_trace)
+        last = seedS; // the kernel copies its shared-memory seed table to HBM at the end of a forward-graph task
     finalize_task(info.data(), g.n_nodes, out);
 }
 
@@ -78,7 +79,10 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
     {
         const int k = T * CK + kk;
         for (int t = 0; t < 32; ++t)
-            node_event<R, false>(s[t], c[t], g, t, nullptr, last.data(), nullptr, false);
+            if (c[t].colsLeft == 0)
+                node_event<R, false>(s[t], c[t], g, t, last.data(), nullptr);
+            else
+                --c[t].colsLeft;
         uint32_t rh[32], rf[32];
         for (int t = 0; t < 32; ++t)
         {
