@@ -310,7 +310,8 @@ struct pg_ctx
     int device = 0;
     std::string err;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    std::vector<cudaEvent_t> evpool; // 3 events per chunk: start, after fill, after trace
+    int n_chunks_timed = 0;
     uint64_t launches = 0;
     float fill_ms = 0, trace_ms = 0;
     uint64_t scratch_limit = 24ull << 30;
@@ -408,11 +409,18 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
     PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
     PG_CUDA(c, cudaFuncSetAttribute(pg_trace_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
 
-    PG_CUDA(c, cudaEventRecord(c->ev[0], c->stream));
-    float fill_ms = 0, trace_ms = 0;
-    bool first = true;
-    for (size_t r0 = 0; r0 < (size_t)c->n_reads; r0 += chunk)
+    const size_t n_chunks = ((size_t)c->n_reads + chunk - 1) / chunk;
+    while (c->evpool.size() < 3 * n_chunks)
     {
+        cudaEvent_t e;
+        PG_CUDA(c, cudaEventCreate(&e));
+        c->evpool.push_back(e);
+    }
+    c->n_chunks_timed = (int)n_chunks;
+    size_t ci = 0;
+    for (size_t r0 = 0; r0 < (size_t)c->n_reads; r0 += chunk, ++ci)
+    {
+        PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci], c->stream));
         const int nr = (int)std::min(chunk, (size_t)c->n_reads - r0);
         FillArgs fa;
         fa.sites = c->d_sites.p;
@@ -435,8 +443,7 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
         pg_fill_kernel<R><<<fgrid, FILL_WARPS * 32, fill_smem, c->stream>>>(fa);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
-        if (first)
-            PG_CUDA(c, cudaEventRecord(c->ev[1], c->stream));
+        PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci + 1], c->stream));
 
         TraceArgs ta;
         ta.sites = c->d_sites.p;
@@ -463,13 +470,8 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
         pg_trace_kernel<R><<<tgrid, TRACE_WARPS * 32, trace_smem, c->stream>>>(ta);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
-        if (first)
-            PG_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-        first = false;
+        PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci + 2], c->stream));
     }
-    PG_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
-    (void)fill_ms;
-    (void)trace_ms;
     return PG_OK;
 }
 
@@ -506,8 +508,6 @@ int pg_create(int device, pg_ctx** out)
         return PG_E_CUDA;
     }
     c->stream = c->own_stream;
-    for (auto& ev : c->ev)
-        cudaEventCreate(&ev);
     *out = c;
     return PG_OK;
 }
@@ -536,9 +536,8 @@ void pg_destroy(pg_ctx* c)
     c->h_records.release();
     c->h_arena.release();
     c->h_cursor.release();
-    for (auto& ev : c->ev)
-        if (ev)
-            cudaEventDestroy(ev);
+    for (auto& ev : c->evpool)
+        cudaEventDestroy(ev);
     if (c->own_stream)
         cudaStreamDestroy(c->own_stream);
     delete c;
@@ -664,8 +663,15 @@ int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap
     PG_CUDA(c, cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                c->stream));
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
-    cudaEventElapsedTime(&c->fill_ms, c->ev[0], c->ev[1]);
-    cudaEventElapsedTime(&c->trace_ms, c->ev[1], c->ev[2]);
+    c->fill_ms = c->trace_ms = 0;
+    for (int ci = 0; ci < c->n_chunks_timed; ++ci) // summed over the chunks of the batch
+    {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, c->evpool[3 * ci], c->evpool[3 * ci + 1]);
+        cudaEventElapsedTime(&b, c->evpool[3 * ci + 1], c->evpool[3 * ci + 2]);
+        c->fill_ms += a;
+        c->trace_ms += b;
+    }
     unsigned long long n = *c->h_cursor.p;
     if (n > c->arena_cap)
         n = c->arena_cap;
