@@ -180,11 +180,14 @@ template <int R> struct Lane
 };
 
 // words per lane in a checkpoint / in a saved node last column
-template <int R> struct Sizes
+// Geometry: a task (one column sequence, two packed problems) is processed by a group of W consecutive lanes
+// (W = 32, 16 or 8: 1, 2 or 4 tasks per warp), each owning R read rows; W * R >= read length.
+template <int R, int W = 32> struct Sizes
 {
     static constexpr int CKW = 2 * R + 2;  // Hp[R], E[R], hupPrev, foutLast   (hbotLast == Hp[R-1])
     static constexpr int LASTW = 2 * R;    // node last column: H[R], E leaving it [R] (= the seed of its successors)
-    static constexpr int ROWS = 32 * R;
+    static constexpr int ROWS = W * R;
+    static constexpr int NT = 32 / W;      // tasks per warp
 };
 
 template <int R> PG_HD void lane_zero(Lane<R>& s)
@@ -204,12 +207,12 @@ template <int R> PG_HD void lane_zero(Lane<R>& s)
 // against this lane's row r.  If KEEP, the values the traceback needs are returned per row:
 // Hc = H(i,j), Ec = E(i,j) as used for H (gssw mE), Fc = F(i,j) as used for H (gssw mF).
 // Returns max over this lane's rows of t (== max of H: an F-derived H never sets a maximum).
-template <int R, bool KEEP>
+template <int R, bool KEEP, int W = 32>
 PG_HD uint32_t lane_step(Lane<R>& s, uint32_t recvH, uint32_t recvF, const uint32_t* prof, int code, int lane,
                          uint32_t* Hc, uint32_t* Ec, uint32_t* Fc)
 {
     const uint32_t mGO = pk(-GAP_OPEN, -GAP_OPEN), mGE = pk(-GAP_EXT, -GAP_EXT);
-    const uint32_t* p = prof + (code * R) * 32 + lane;
+    const uint32_t* p = prof + (code * R) * W + lane;
     uint32_t d = s.hupPrev; // diagonal for row 0
     s.hupPrev = recvH;
     uint32_t F = recvF;
@@ -217,7 +220,7 @@ PG_HD uint32_t lane_step(Lane<R>& s, uint32_t recvH, uint32_t recvF, const uint3
 PG_UNROLL
     for (int r = 0; r < R; ++r)
     {
-        const uint32_t sc = p[r * 32];
+        const uint32_t sc = p[r * W];
         const uint32_t e = s.E[r];
         const uint32_t t = addmax_relu2(d, sc, e);
         const uint32_t tg = add2(t, mGO);
@@ -241,7 +244,7 @@ PG_UNROLL
 
 // Build this lane's part of the warp profile: rows [R*lane, R*lane+R) x 6 column codes, both halves.
 // Rows >= L and the sentinel code get NEG so that they can never reach a maximum (DESIGN.md "padding").
-template <int R> PG_HD void build_profile(uint32_t* prof, const uint8_t* bases, int L, int orient, int lane)
+template <int R, int W = 32> PG_HD void build_profile(uint32_t* prof, const uint8_t* bases, int L, int orient, int lane)
 {
     for (int r = 0; r < R; ++r)
     {
@@ -256,7 +259,7 @@ template <int R> PG_HD void build_profile(uint32_t* prof, const uint8_t* bases, 
         {
             const int s0 = (c0 < 0 || c == 5) ? NEG : sub_score(c, c0);
             const int s1 = (c1 < 0 || c == 5) ? NEG : sub_score(c, c1);
-            prof[(c * R + r) * 32 + lane] = pk(s0, s1);
+            prof[(c * R + r) * W + lane] = pk(s0, s1);
         }
     }
 }
@@ -327,7 +330,7 @@ PG_HD void track_max(LaneCtl& c, uint32_t m, int k)
 // gssw.c:3897-3931), zeros for a source; if the only predecessor is the node just finished the state
 // simply carries over.  The diagonal into this lane's first row comes from the seed row just above it,
 // i.e. lane-1's last word of each predecessor (written by lane-1 at least one step earlier).
-template <int R, bool FILL>
+template <int R, bool FILL, int W = 32>
 PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* seeds, uint32_t* infoS)
 {
     if (c.colsLeft == 0)
@@ -337,12 +340,12 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
         {
             for (int r = 0; r < R; ++r)
             {
-                seeds[(n * 2 * R + r) * 32 + lane] = s.Hp[r];
-                seeds[(n * 2 * R + R + r) * 32 + lane] = s.E[r];
+                seeds[(n * 2 * R + r) * W + lane] = s.Hp[r];
+                seeds[(n * 2 * R + R + r) * W + lane] = s.E[r];
             }
-            infoS[(n * 3 + 0) * 32 + lane] = c.Mnode;
-            infoS[(n * 3 + 1) * 32 + lane] = (uint32_t)c.first[0];
-            infoS[(n * 3 + 2) * 32 + lane] = (uint32_t)c.first[1];
+            infoS[(n * 3 + 0) * W + lane] = c.Mnode;
+            infoS[(n * 3 + 1) * W + lane] = (uint32_t)c.first[0];
+            infoS[(n * 3 + 2) * W + lane] = (uint32_t)c.first[1];
             c.Mnode = 0;
         }
         c.node = n + 1;
@@ -357,14 +360,14 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
                     H[r] = E[r] = 0;
                 for (int e = p0; e < p1; ++e)
                 {
-                    const uint32_t* src = seeds + (size_t)g.pred_idx[e] * 2 * R * 32;
+                    const uint32_t* src = seeds + (size_t)g.pred_idx[e] * 2 * R * W;
                     for (int r = 0; r < R; ++r)
                     {
-                        H[r] = max2(H[r], src[r * 32 + lane]);
-                        E[r] = max2(E[r], src[(R + r) * 32 + lane]);
+                        H[r] = max2(H[r], src[r * W + lane]);
+                        E[r] = max2(E[r], src[(R + r) * W + lane]);
                     }
                     if (lane > 0)
-                        hup = max2(hup, src[(R - 1) * 32 + lane - 1]);
+                        hup = max2(hup, src[(R - 1) * W + lane - 1]);
                 }
                 for (int r = 0; r < R; ++r)
                 {
@@ -380,25 +383,25 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
     --c.colsLeft;
 }
 
-template <int R> PG_HD void ckpt_store(const Lane<R>& s, uint32_t* ck, int lane)
+template <int R, int W = 32> PG_HD void ckpt_store(const Lane<R>& s, uint32_t* ck, int lane)
 {
     for (int r = 0; r < R; ++r)
     {
-        ck[r * 32 + lane] = s.Hp[r];
-        ck[(R + r) * 32 + lane] = s.E[r];
+        ck[r * W + lane] = s.Hp[r];
+        ck[(R + r) * W + lane] = s.E[r];
     }
-    ck[(2 * R) * 32 + lane] = s.hupPrev;
-    ck[(2 * R + 1) * 32 + lane] = s.foutLast;
+    ck[(2 * R) * W + lane] = s.hupPrev;
+    ck[(2 * R + 1) * W + lane] = s.foutLast;
 }
-template <int R> PG_HD void ckpt_load(Lane<R>& s, const uint32_t* ck, int lane)
+template <int R, int W = 32> PG_HD void ckpt_load(Lane<R>& s, const uint32_t* ck, int lane)
 {
     for (int r = 0; r < R; ++r)
     {
-        s.Hp[r] = ck[r * 32 + lane];
-        s.E[r] = ck[(R + r) * 32 + lane];
+        s.Hp[r] = ck[r * W + lane];
+        s.E[r] = ck[(R + r) * W + lane];
     }
-    s.hupPrev = ck[(2 * R) * 32 + lane];
-    s.foutLast = ck[(2 * R + 1) * 32 + lane];
+    s.hupPrev = ck[(2 * R) * W + lane];
+    s.foutLast = ck[(2 * R + 1) * W + lane];
     s.hbotLast = s.Hp[R - 1];
 }
 
@@ -406,9 +409,9 @@ template <int R> PG_HD void ckpt_load(Lane<R>& s, const uint32_t* ck, int lane)
 // saturation; all three fit a byte because scores are <= MAX_READ_LEN) and only for a band of BAND_LANES lanes
 // (BAND_LANES * R read rows): within the CK steps of a tile the walk moves through ~CK rows, so rows outside
 // the band are never read.  A cell outside the resident bands is simply a miss (tile recomputed around it).
-constexpr int BAND_LANES = 8;
 template <int R> struct TileGeom
 {
+    static constexpr int BAND_LANES = (35 + R - 1) / R + 1; // >= 36 rows above the entry row whatever its position in its lane
     static constexpr int BAND_ROWS = BAND_LANES * R;
     static constexpr int SLOT_WORDS = CK * BAND_ROWS;
 };
@@ -437,7 +440,7 @@ PG_HD void tile_store(uint32_t* tstep, int lane, int blo, const uint32_t* Hc, co
                       int half)
 {
     const int bl = lane - blo;
-    if (bl < 0 || bl >= BAND_LANES)
+    if (bl < 0 || bl >= TileGeom<R>::BAND_LANES)
         return;
     for (int r = 0; r < R; ++r)
         tstep[R * bl + r] = pack_cell(Hc[r], Ec[r], Fc[r], half);
@@ -449,8 +452,8 @@ PG_HD void tile_store(uint32_t* tstep, int lane, int blo, const uint32_t* Hc, co
 //   info  [n_nodes][3][32]      : per node and lane: packed node maximum, first step reaching it (half 0, half 1)
 //   last  [n_nodes][2R][32]     : node last column: H, E leaving it (seed)            (forward-graph tasks only)
 //   ckpt  [n_ck][2R+2][32]      : lane state before step c*CK                      (forward-graph tasks only)
-PG_HD int num_steps(int G) { return G + 32; } // lane 31 ends column G-1 at step G+30; its node event runs at step G+31
-PG_HD int num_ckpt(int G) { return (num_steps(G) + CK - 1) / CK; }
+PG_HD int num_steps(int G, int W) { return G + W; } // lane W-1 ends column G-1 at step G+W-2; its node event runs at step G+W-1
+PG_HD int num_ckpt(int G, int W) { return (num_steps(G, W) + CK - 1) / CK; }
 
 struct TaskOut // result of one fill (two packed problems)
 {
@@ -466,15 +469,15 @@ struct TaskOut // result of one fill (two packed problems)
 // row in that column (gssw.c:378-386, 446-454, 4015-4018) -> min column = min(step - lane), ties -> smaller lane.
 PG_HD uint32_t ld_scratch(const uint32_t* p) { return *p; } // warp-private shared memory (after a __syncwarp)
 
-PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o)
+PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W)
 {
     for (int h = 0; h < 2; ++h)
     {
         int S = 0;
         for (int n = 0; n < n_nodes; ++n)
-            for (int t = 0; t < 32; ++t)
+            for (int t = 0; t < W; ++t)
             {
-                const int v = half16(ld_scratch(info + (n * 3 + 0) * 32 + t), h);
+                const int v = half16(ld_scratch(info + (n * 3 + 0) * W + t), h);
                 if (v > S)
                     S = v;
             }
@@ -482,14 +485,14 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o)
         for (int n = 0; n < n_nodes; ++n)
         {
             bool has = false;
-            for (int t = 0; t < 32; ++t)
+            for (int t = 0; t < W; ++t)
             {
-                if (half16(ld_scratch(info + (n * 3 + 0) * 32 + t), h) != S)
+                if (half16(ld_scratch(info + (n * 3 + 0) * W + t), h) != S)
                     continue;
                 has = true;
                 if (mnode == -1 || mnode == n)
                 {
-                    const int step = (int)ld_scratch(info + (n * 3 + 1 + h) * 32 + t);
+                    const int step = (int)ld_scratch(info + (n * 3 + 1 + h) * W + t);
                     if (step - t < bestq)
                     {
                         bestq = step - t;
@@ -641,6 +644,7 @@ template <int R> struct TileBuf
             return nullptr;
         const int T = step / CK, ln = row / R;
         int sl = -1, blo = 0;
+        constexpr int BAND_LANES = TileGeom<R>::BAND_LANES;
         if (tile0 == T && ln >= blo0 && ln < blo0 + BAND_LANES)
         {
             sl = 0;
@@ -658,7 +662,7 @@ template <int R> struct TileBuf
     // slot that will receive tile T with a band ending at `row`'s lane (round-robin eviction)
     PG_HD int admit(int T, int row, int& blo)
     {
-        blo = row / R - (BAND_LANES - 1);
+        blo = row / R - (TileGeom<R>::BAND_LANES - 1);
         if (blo < 0)
             blo = 0;
         const int sl = lru;
@@ -702,7 +706,7 @@ PG_HD void push_op(Walker& w, uint32_t* oplog, int cap, int node, int op, int le
 }
 PG_HD int match_op(uint8_t refc, uint8_t readc) { return (refc == 'N' || readc == 'N') ? OP_N : (refc == readc ? OP_M : OP_X); }
 
-// Diagonal runs, 32 cells at a time.  Most traceback moves are diagonal (M/X/N); instead of one serial move per
+// Diagonal runs, W cells at a time.  Most traceback moves are diagonal (M/X/N); instead of one serial move per
 // iteration every lane ell probes the cell (i-ell, j-ell): is it an interior cell with positive score whose H equals
 // the diagonal neighbour plus the substitution score (gssw.c:1591-1637)?  The run is the number of leading lanes
 // that say yes; their ops are logged in parallel.  flag: 0 = no, 1 = yes, 2 = a tile the probe needs is not resident.
@@ -735,25 +739,28 @@ PG_HD void diag_probe(int ell, const Walker& w, const TileBuf<R>& tb, const Grap
     flag = (hv == dval + sub_score(nt_code(refc), nt_code(readc))) ? 1 : 0;
 }
 
-// Returns the run length (0..32) and logs the run's ops run-length encoded; on 0, miss0 tells that the current
-// cell's own probe missed a tile.  Warp-uniform on the device (every lane calls it with identical walker state
-// and its own lane id); the host version loops over the 32 probes.
-template <int R>
+// Returns the run length (0..W) and logs the run's ops run-length encoded; on 0, miss0 tells that the current
+// cell's own probe missed a tile.  Group-uniform on the device: every lane of the W-lane group calls it with
+// identical walker state and its own group-lane id; gmask = the group's lanes (other groups of the warp may be
+// executing something else).  The host version loops over the W probes.
+template <int R, int W>
 PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars, const uint8_t* bases,
-                   int L, int half, int lane, uint32_t* oplog, int oplog_cap, int& vnew, bool& miss0)
+                   int L, int half, int lane, unsigned gmask, uint32_t* oplog, int oplog_cap, int& vnew, bool& miss0)
 {
     int run = 0, nent = 0;
 #if defined(__CUDA_ARCH__)
+    constexpr unsigned WM = (W == 32) ? 0xffffffffu : ((1u << (W & 31)) - 1u);
+    const int gshift = __ffs((int)gmask) - 1; // first lane of this group
     int flag, dval, op;
     diag_probe<R>(lane, w, tb, g, chars, bases, L, half, flag, dval, op);
-    const unsigned yes = __ballot_sync(0xffffffffu, flag == 1);
-    run = (yes == 0xffffffffu) ? 32 : (__ffs((int)~yes) - 1);
-    miss0 = (__shfl_sync(0xffffffffu, flag, 0) == 2);
-    vnew = __shfl_sync(0xffffffffu, dval, run > 0 ? run - 1 : 0);
+    const unsigned yes = (__ballot_sync(gmask, flag == 1) >> gshift) & WM;
+    run = (yes == WM) ? W : (__ffs((int)~yes) - 1);
+    miss0 = (__shfl_sync(gmask, flag, 0, W) == 2);
+    vnew = __shfl_sync(gmask, dval, run > 0 ? run - 1 : 0, W);
     // run-length encode: a lane starts an entry when its op differs from the previous lane's
-    const int prev = __shfl_up_sync(0xffffffffu, op, 1);
+    const int prev = __shfl_up_sync(gmask, op, 1, W);
     const bool in = lane < run;
-    const unsigned starts = __ballot_sync(0xffffffffu, in && (lane == 0 || op != prev));
+    const unsigned starts = (__ballot_sync(gmask, in && (lane == 0 || op != prev)) >> gshift) & WM;
     if (in && ((starts >> lane) & 1u))
     {
         const unsigned above = starts & ~((2u << lane) - 1u); // entry starts after this lane
@@ -765,10 +772,11 @@ PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const ui
     nent = __popc(starts);
 #else
     (void)lane;
+    (void)gmask;
     miss0 = false;
     vnew = 0;
     int last_op = -1;
-    for (int ell = 0; ell < 32; ++ell)
+    for (int ell = 0; ell < W; ++ell)
     {
         int flag, dval, op;
         diag_probe<R>(ell, w, tb, g, chars, bases, L, half, flag, dval, op);
@@ -806,9 +814,10 @@ PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const ui
 // deflections) and the cross-node part of gssw_graph_trace_back_internal (gssw.c:2836-3148, 3486-3528).
 //   g      forward graph view;  chars = upper-cased graph characters (column-indexed like codes)
 //   last   this read's saved node last columns [n_nodes][2R][32] (packed words)
-template <int R>
+template <int R, int W>
 PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars, const uint32_t* last,
-                const uint8_t* bases, int L, int half, const TaskOut& fo, uint32_t* oplog, int oplog_cap, int lane)
+                const uint8_t* bases, int L, int half, const TaskOut& fo, uint32_t* oplog, int oplog_cap, int lane,
+                unsigned gmask)
 {
     if (w.phase == 0)
     {
@@ -940,7 +949,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
             {
                 int vnew;
                 bool miss0;
-                const int run = diag_run<R>(w, tb, g, chars, bases, L, half, lane, oplog, oplog_cap, vnew, miss0);
+                const int run = diag_run<R, W>(w, tb, g, chars, bases, L, half, lane, gmask, oplog, oplog_cap, vnew, miss0);
                 if (run > 0) // diagonal moves, gssw.c:1591-1637
                 {
                     w.v = vnew;
@@ -1005,11 +1014,11 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
         for (int e = g.pred_ptr[w.n]; e < g.pred_ptr[w.n + 1]; ++e)
         {
             const int c = g.pred_idx[e];
-            const uint32_t* lc = last + (size_t)c * (2 * R) * 32;
+            const uint32_t* lc = last + (size_t)c * (2 * R) * W;
             if (w.st == 0)
             {
                 // diagonal source = pred's last column at row j-1 (row -1 never matches: H(0,0) is start or E)
-                const int dsrc = w.j > 0 ? half16(lc[((w.j - 1) % R) * 32 + (w.j - 1) / R], half) : -1000;
+                const int dsrc = w.j > 0 ? half16(lc[((w.j - 1) % R) * W + (w.j - 1) / R], half) : -1000;
                 if (w.v == dsrc + s) // gssw.c:2999-3040
                 {
                     best = c;
@@ -1021,7 +1030,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
             }
             else
             {
-                const int hsrc = half16(lc[(w.j % R) * 32 + w.j / R], half);
+                const int hsrc = half16(lc[(w.j % R) * W + w.j / R], half);
                 if (w.v == hsrc - GAP_OPEN) // open, gssw.c:3089-3110
                 {
                     best = c;
@@ -1033,7 +1042,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                 // extend: the reference tests v == E_c(last, j) - ge with E *entering* pred's last column
                 // (gssw.c:3122-3136).  Saved is the seed E' = max(E - ge, t - go) >= E - ge, and v >= E' (v is the max
                 // of the seeds), so v == E' is necessary; only then is the exact E read from pred's last-column tile.
-                const int eseed = imax0(half16(lc[(R + w.j % R) * 32 + w.j / R], half));
+                const int eseed = imax0(half16(lc[(R + w.j % R) * W + w.j / R], half));
                 if (w.v == eseed)
                 {
                     const int kc = g.node_start[c] + g.node_len[c] - 1 + w.j / R;

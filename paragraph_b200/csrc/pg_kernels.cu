@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -46,51 +47,62 @@ struct FillArgs
     size_t stride_last, stride_ckpt;
     int n_nodes_cap; // seed / info table capacity per warp (nodes)
     TaskOut* tout; // [2 * n_reads] (global task index)
-    int smem_words_per_warp;
+    int smem_words_per_task;
 };
 
-template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs a)
+template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs a)
 {
     extern __shared__ uint32_t smem[];
+    constexpr int NT = 32 / W; // tasks per warp: a group of W lanes per task
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ltask = blockIdx.x * FILL_WARPS + wic;
-    if (ltask >= a.n_tasks)
-        return;
+    const int grp = lane / W, gl = lane % W;
+    const int ltask = (blockIdx.x * FILL_WARPS + wic) * NT + grp;
+    if ((blockIdx.x * FILL_WARPS + wic) * NT >= a.n_tasks)
+        return; // whole warp beyond the work list
     const int rd = a.read0 + (ltask >> 1), o = ltask & 1;
+    const bool active = ltask < a.n_tasks && !(o == 1 && !(a.flags & AF_REVERSE_GRAPH));
+    uint32_t* prof = smem + ((size_t)wic * NT + grp) * a.smem_words_per_task;
+    uint32_t* seedS = prof + NCODE * R * W;               // [n_nodes_cap][2R][W]
+    uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * W;  // [n_nodes_cap][3][W]
     TaskOut* to = a.tout + (size_t)rd * 2 + o;
-    if (o == 1 && !(a.flags & AF_REVERSE_GRAPH))
+    if (!active && ltask < a.n_tasks && gl == 0)
     {
-        if (lane == 0)
-        {
-            TaskOut z;
-            memset(&z, 0, sizeof z);
-            *to = z;
-        }
-        return;
+        TaskOut z;
+        memset(&z, 0, sizeof z);
+        *to = z;
     }
-    uint32_t* prof = smem + (size_t)wic * a.smem_words_per_warp;
-    uint32_t* seedS = prof + NCODE * R * 32;               // [n_nodes_cap][2R][32]
-    uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * 32;  // [n_nodes_cap][3][32]
-    const SiteDev sd = a.sites[a.read_site ? a.read_site[rd] : 0];
+    const int rdc = ltask < a.n_tasks ? rd : a.read0; // clamp for inactive tail groups (they only idle along)
+    const SiteDev sd = a.sites[a.read_site ? a.read_site[rdc] : 0];
     const GraphView g = make_view(sd, a.gbytes, a.gints, o);
-    const uint8_t* bases = a.bases + a.read_off[rd];
-    const int L = a.read_off[rd + 1] - a.read_off[rd];
-    build_profile<R>(prof, bases, L, o, lane);
+    const uint8_t* bases = a.bases + a.read_off[rdc];
+    const int L = a.read_off[rdc + 1] - a.read_off[rdc];
+    if (active)
+        build_profile<R, W>(prof, bases, L, o, gl);
+    else
+        for (int x = gl; x < NCODE * R * W; x += W)
+            prof[x] = pk(NEG, NEG);
     __syncwarp();
 
     Lane<R> s;
     lane_zero(s);
     LaneCtl c;
-    ctl_at_step(c, g, 0, lane);
-    const bool save = (o == 0);
+    ctl_at_step(c, g, 0, gl);
+    if (!active)
+        c.colsLeft = COLS_INF;
+    const bool save = active && (o == 0);
     uint32_t* last = a.last + (size_t)(ltask >> 1) * a.stride_last;
     uint32_t* ckpt = a.ckpt + (size_t)(ltask >> 1) * a.stride_ckpt;
-    const uint8_t* codes = g.codes - lane;
-    const int nck = num_ckpt(g.G);
+    const uint8_t* codes = g.codes - gl;
+    const int my_nck = active ? num_ckpt(g.G, W) : 0;
+    int nck = my_nck;
+    if (NT > 1) // groups of one warp may belong to different sites: run to the longest, the others idle on sentinels
+        for (int d = W; d < 32; d <<= 1)
+            nck = max(nck, __shfl_xor_sync(FULL, nck, d));
     for (int cki = 0; cki < nck; ++cki)
     {
-        if (save)
-            ckpt_store<R>(s, ckpt + (size_t)cki * (2 * R + 2) * 32, lane);
+        const bool live = cki < my_nck;
+        if (save && live)
+            ckpt_store<R, W>(s, ckpt + (size_t)cki * (2 * R + 2) * W, gl);
         const int kbase = cki * CK;
         const uint8_t* cp = codes + kbase; // per-lane pointer, immediate offsets inside the unrolled body
 #pragma unroll 4
@@ -99,29 +111,29 @@ template <int R> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kern
             const int k = kbase + kk;
             __syncwarp();
             if (c.colsLeft == 0) // rare, per lane: node boundary
-                node_event<R, true>(s, c, g, lane, seedS, infoS);
+                node_event<R, true, W>(s, c, g, gl, seedS, infoS);
             else
                 --c.colsLeft;
-            uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1);
-            uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1);
-            if (lane == 0)
+            uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
+            uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
+            if (gl == 0)
             {
                 rh = 0;
                 rf = 0;
             }
-            const int code = cp[kk];
-            const uint32_t m = lane_step<R, false>(s, rh, rf, prof, code, lane, nullptr, nullptr, nullptr);
+            const int code = live ? cp[kk] : 5;
+            const uint32_t m = lane_step<R, false, W>(s, rh, rf, prof, code, gl, nullptr, nullptr, nullptr);
             track_max(c, m, k);
         }
     }
     __syncwarp();
     if (save) // node last columns for the traceback kernel: one coalesced copy of the seed table
-        for (int x = lane; x < g.n_nodes * 2 * R * 32; x += 32)
+        for (int x = gl; x < g.n_nodes * 2 * R * W; x += W)
             last[x] = seedS[x];
-    if (lane == 0)
+    if (active && gl == 0)
     {
         TaskOut t;
-        finalize_task(infoS, g.n_nodes, t);
+        finalize_task(infoS, g.n_nodes, t, W);
         *to = t;
     }
 }
@@ -144,21 +156,26 @@ struct TraceArgs
     uint32_t* arena;
     unsigned long long* cursor;
     unsigned long long arena_cap;
-    int smem_bytes_per_warp;
+    int smem_bytes_per_task;
     int oplog_cap;
 };
 
-template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_kernel(const TraceArgs a)
+template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_kernel(const TraceArgs a)
 {
     extern __shared__ uint32_t smem[];
+    constexpr int NT = 32 / W; // reads per warp: a group of W lanes per read
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int lrd = blockIdx.x * TRACE_WARPS + wic;
-    if (lrd >= a.n_reads)
+    const int grp = lane / W, gl = lane % W;
+    const unsigned gmask = (W == 32) ? FULL : (((1u << (W & 31)) - 1u) << (grp * W));
+    const int lrd0 = (blockIdx.x * TRACE_WARPS + wic) * NT;
+    if (lrd0 >= a.n_reads)
         return;
+    const bool active = lrd0 + grp < a.n_reads;
+    const int lrd = active ? lrd0 + grp : lrd0; // idle tail groups shadow the warp's first read (no stores)
     const int rd = a.read0 + lrd;
-    uint8_t* wmem = reinterpret_cast<uint8_t*>(smem) + (size_t)wic * a.smem_bytes_per_warp;
+    uint8_t* wmem = reinterpret_cast<uint8_t*>(smem) + ((size_t)wic * NT + grp) * a.smem_bytes_per_task;
     uint32_t* prof = reinterpret_cast<uint32_t*>(wmem);
-    uint32_t* oplog = prof + NCODE * R * 32;
+    uint32_t* oplog = prof + NCODE * R * W;
     uint32_t* tiles = oplog + a.oplog_cap;
 
     const SiteDev sd = a.sites[a.read_site ? a.read_site[rd] : 0];
@@ -168,7 +185,7 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
     const int L = a.read_off[rd + 1] - a.read_off[rd];
     const uint32_t* last = a.last + (size_t)lrd * a.stride_last;
     const uint32_t* ckpt = a.ckpt + (size_t)lrd * a.stride_ckpt;
-    build_profile<R>(prof, bases, L, 0, lane);
+    build_profile<R, W>(prof, bases, L, 0, gl);
 
     const TaskOut fw = a.tout[(size_t)rd * 2], rv = a.tout[(size_t)rd * 2 + 1];
     const Decision d = decide_strand(fw, rv, a.flags);
@@ -182,46 +199,65 @@ template <int R> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_ke
     Walker w;
     memset(&w, 0, sizeof w);
     __syncwarp();
-    const uint8_t* codes = g.codes - lane;
+    const uint8_t* codes = g.codes - gl;
+    bool done = !active;
     for (int guard = 0; guard < (1 << 20); ++guard)
     {
-        // the walk is warp-uniform: every lane carries the same walker state; diagonal runs are probed 32 cells
-        // at a time with a ballot (diag_run), the other moves are executed redundantly by all lanes
-        if (walk<R>(w, tb, g, chars, last, bases, L, half, fw, oplog, a.oplog_cap, lane))
+        // Walk phase: group-uniform (every lane of a group carries the same walker state; diagonal runs are probed
+        // W cells at a time with a ballot, the other moves are executed redundantly by the group's lanes).  Groups
+        // of one warp diverge here and reconverge for the recomputation below.
+        if (!done)
+            done = walk<R, W>(w, tb, g, chars, last, bases, L, half, fw, oplog, a.oplog_cap, gl, gmask);
+        if (__all_sync(FULL, done))
             break;
-        const int T = w.need_step / CK;
-        int blo;
-        const int slot = tb.admit(T, w.need_row, blo);
+        // Recompute phase (warp-uniform): every unfinished group rebuilds the tile it missed from its checkpoint
+        int T = 0, slot = 0, blo = 0;
+        if (!done)
+        {
+            T = w.need_step / CK;
+            slot = tb.admit(T, w.need_row, blo);
+        }
         __syncwarp();
-        // recompute tile T from its checkpoint
         Lane<R> s;
         LaneCtl c;
-        ckpt_load<R>(s, ckpt + (size_t)T * (2 * R + 2) * 32, lane);
-        ctl_at_step(c, g, T * CK, lane);
+        if (!done)
+        {
+            ckpt_load<R, W>(s, ckpt + (size_t)T * (2 * R + 2) * W, gl);
+            ctl_at_step(c, g, T * CK, gl);
+        }
+        else
+        {
+            lane_zero(s);
+            c.node = 0;
+            c.colsLeft = COLS_INF;
+            c.Mnode = 0;
+            c.first[0] = c.first[1] = 0;
+        }
         uint32_t* dst = tiles + (size_t)slot * TileGeom<R>::SLOT_WORDS;
+        const uint8_t* cp = codes + T * CK;
 #pragma unroll 2
         for (int kk = 0; kk < CK; ++kk)
         {
-            const int k = T * CK + kk;
             if (c.colsLeft == 0)
-                node_event<R, false>(s, c, g, lane, const_cast<uint32_t*>(last), nullptr);
+                node_event<R, false, W>(s, c, g, gl, const_cast<uint32_t*>(last), nullptr);
             else
                 --c.colsLeft;
-            uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1);
-            uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1);
-            if (lane == 0)
+            uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
+            uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
+            if (gl == 0)
             {
                 rh = 0;
                 rf = 0;
             }
             uint32_t Hc[R], Ec[R], Fc[R];
-            lane_step<R, true>(s, rh, rf, prof, codes[k], lane, Hc, Ec, Fc);
-            tile_store<R>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, lane, blo, Hc, Ec, Fc, half);
+            lane_step<R, true, W>(s, rh, rf, prof, done ? 5 : cp[kk], gl, Hc, Ec, Fc);
+            if (!done)
+                tile_store<R>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, gl, blo, Hc, Ec, Fc, half);
         }
         __syncwarp();
     }
     __syncwarp();
-    if (lane == 0)
+    if (active && gl == 0)
     {
         Record rec;
         rec.graph_pos = w.position;
@@ -315,6 +351,7 @@ struct pg_ctx
     uint64_t launches = 0;
     float fill_ms = 0, trace_ms = 0;
     uint64_t scratch_limit = 24ull << 30;
+    int geom_w = 16; // lanes per task; PG_GEOM_W=32|16|8 overrides (tuning / A-B measurements only)
 
     host::GraphStore graphs;
     bool graphs_dirty = true;
@@ -378,10 +415,11 @@ int upload_graphs(pg_ctx* c)
     return PG_OK;
 }
 
-template <int R> int run_chunks(pg_ctx* c, unsigned flags)
+template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
 {
+    constexpr int NT = 32 / W;
     const int max_nodes = c->graphs.max_nodes, max_G = c->graphs.max_G;
-    const size_t s_last = host::last_words(max_nodes, R), s_ckpt = host::ckpt_words(max_G, R);
+    const size_t s_last = host::last_words(max_nodes, R, W), s_ckpt = host::ckpt_words(max_G, R, W);
     const size_t per_read_bytes = (s_last + s_ckpt) * sizeof(uint32_t);
     size_t chunk = (size_t)(c->scratch_limit / (per_read_bytes ? per_read_bytes : 1));
     if (chunk < 1)
@@ -398,16 +436,16 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
     PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
     PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
 
-    const int fill_words = NCODE * R * 32 + max_nodes * (2 * R + 3) * 32;
-    const size_t fill_smem = (size_t)FILL_WARPS * fill_words * sizeof(uint32_t);
-    const int trace_bytes = (NCODE * R * 32 + oplog_cap + 2 * TileGeom<R>::SLOT_WORDS) * 4;
+    const int fill_words = NCODE * R * W + max_nodes * (2 * R + 3) * W; // per task
+    const size_t fill_smem = (size_t)FILL_WARPS * NT * fill_words * sizeof(uint32_t);
+    const int trace_bytes = (NCODE * R * W + oplog_cap + 2 * TileGeom<R>::SLOT_WORDS) * 4; // per read
     const int trace_bytes_al = (trace_bytes + 15) & ~15;
-    const size_t trace_smem = (size_t)TRACE_WARPS * trace_bytes_al;
+    const size_t trace_smem = (size_t)TRACE_WARPS * NT * trace_bytes_al;
     if (fill_smem > 227 * 1024 || trace_smem > 227 * 1024)
         return fail(c, PG_E_GRAPH, "graph has too many nodes for the shared-memory seed table ("
                         + std::to_string(max_nodes) + " nodes)");
-    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
-    PG_CUDA(c, cudaFuncSetAttribute(pg_trace_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
+    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+    PG_CUDA(c, cudaFuncSetAttribute(pg_trace_kernel<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
 
     const size_t n_chunks = ((size_t)c->n_reads + chunk - 1) / chunk;
     while (c->evpool.size() < 3 * n_chunks)
@@ -438,9 +476,9 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
         fa.stride_last = s_last;
         fa.stride_ckpt = s_ckpt;
         fa.tout = c->d_tout.p;
-        fa.smem_words_per_warp = fill_words;
-        const int fgrid = (fa.n_tasks + FILL_WARPS - 1) / FILL_WARPS;
-        pg_fill_kernel<R><<<fgrid, FILL_WARPS * 32, fill_smem, c->stream>>>(fa);
+        fa.smem_words_per_task = fill_words;
+        const int fgrid = (fa.n_tasks + FILL_WARPS * NT - 1) / (FILL_WARPS * NT);
+        pg_fill_kernel<R, W><<<fgrid, FILL_WARPS * 32, fill_smem, c->stream>>>(fa);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
         PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci + 1], c->stream));
@@ -464,10 +502,10 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
         ta.arena = c->d_arena.p;
         ta.cursor = c->d_cursor.p;
         ta.arena_cap = c->arena_cap;
-        ta.smem_bytes_per_warp = trace_bytes_al;
+        ta.smem_bytes_per_task = trace_bytes_al;
         ta.oplog_cap = oplog_cap;
-        const int tgrid = (nr + TRACE_WARPS - 1) / TRACE_WARPS;
-        pg_trace_kernel<R><<<tgrid, TRACE_WARPS * 32, trace_smem, c->stream>>>(ta);
+        const int tgrid = (nr + TRACE_WARPS * NT - 1) / (TRACE_WARPS * NT);
+        pg_trace_kernel<R, W><<<tgrid, TRACE_WARPS * 32, trace_smem, c->stream>>>(ta);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
         PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci + 2], c->stream));
@@ -479,7 +517,7 @@ template <int R> int run_chunks(pg_ctx* c, unsigned flags)
 
 extern "C" {
 
-const char* pg_version(void) { return "paragraph_b200 0.1 sm_100a CK=16 int16x2-wavefront"; }
+const char* pg_version(void) { return "paragraph_b200 0.2 sm_100a CK=16 int16x2-wavefront W=16/32/8"; }
 
 int pg_create(int device, pg_ctx** out)
 {
@@ -508,6 +546,12 @@ int pg_create(int device, pg_ctx** out)
         return PG_E_CUDA;
     }
     c->stream = c->own_stream;
+    if (const char* e = getenv("PG_GEOM_W"))
+    {
+        const int w = atoi(e);
+        if (w == 32 || w == 16 || w == 8)
+            c->geom_w = w;
+    }
     *out = c;
     return PG_OK;
 }
@@ -643,7 +687,13 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
     int rc = upload_graphs(c);
     if (rc != PG_OK)
         return rc;
-    rc = c->max_len <= 160 ? run_chunks<5>(c, flags) : run_chunks<8>(c, flags);
+    // geometry: W lanes per task, R rows per lane (W * R >= read length); see DESIGN.md "geometry"
+    if (c->geom_w == 32)
+        rc = c->max_len <= 160 ? run_chunks<5, 32>(c, flags) : run_chunks<8, 32>(c, flags);
+    else if (c->geom_w == 8 && c->max_len <= 160)
+        rc = run_chunks<20, 8>(c, flags);
+    else
+        rc = c->max_len <= 160 ? run_chunks<10, 16>(c, flags) : run_chunks<16, 16>(c, flags);
     if (rc == PG_OK)
         c->ran = true;
     return rc;

@@ -17,88 +17,88 @@ using namespace pg;
 namespace
 {
 
-template <int R>
+template <int R, int W>
 void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool save_trace, std::vector<uint32_t>& info,
               std::vector<uint32_t>& last, std::vector<uint32_t>& ckpt, TaskOut& out)
 {
-    std::vector<uint32_t> prof((size_t)NCODE * R * 32);
-    std::vector<uint32_t> seedS((size_t)g.n_nodes * 2 * R * 32, 0);
-    for (int t = 0; t < 32; ++t)
-        build_profile<R>(prof.data(), bases, L, orient, t);
-    Lane<R> s[32];
-    LaneCtl c[32];
-    for (int t = 0; t < 32; ++t)
+    std::vector<uint32_t> prof((size_t)NCODE * R * W);
+    std::vector<uint32_t> seedS((size_t)g.n_nodes * 2 * R * W, 0);
+    for (int t = 0; t < W; ++t)
+        build_profile<R, W>(prof.data(), bases, L, orient, t);
+    Lane<R> s[W];
+    LaneCtl c[W];
+    for (int t = 0; t < W; ++t)
     {
         lane_zero(s[t]);
         ctl_at_step(c[t], g, 0, t);
     }
-    info.assign(host::info_words(g.n_nodes), 0);
+    info.assign(host::info_words(g.n_nodes, W), 0);
     if (save_trace)
-        ckpt.assign(host::ckpt_words(g.G, R), 0);
-    const int nck = num_ckpt(g.G);
+        ckpt.assign(host::ckpt_words(g.G, R, W), 0);
+    const int nck = num_ckpt(g.G, W);
     for (int k = 0; k < nck * CK; ++k)
     {
         if (save_trace && k % CK == 0)
-            for (int t = 0; t < 32; ++t)
-                ckpt_store<R>(s[t], ckpt.data() + (size_t)(k / CK) * (2 * R + 2) * 32, t);
-        for (int t = 0; t < 32; ++t) // events read what lane t-1 wrote at an EARLIER step only
+            for (int t = 0; t < W; ++t)
+                ckpt_store<R, W>(s[t], ckpt.data() + (size_t)(k / CK) * (2 * R + 2) * W, t);
+        for (int t = 0; t < W; ++t) // events read what lane t-1 wrote at an EARLIER step only
             if (c[t].colsLeft == 0)
-                node_event<R, true>(s[t], c[t], g, t, seedS.data(), info.data());
+                node_event<R, true, W>(s[t], c[t], g, t, seedS.data(), info.data());
             else
                 --c[t].colsLeft;
-        uint32_t rh[32], rf[32];
-        for (int t = 0; t < 32; ++t)
+        uint32_t rh[W], rf[W];
+        for (int t = 0; t < W; ++t)
         {
             rh[t] = t ? s[t - 1].hbotLast : 0;
             rf[t] = t ? s[t - 1].foutLast : 0;
         }
-        for (int t = 0; t < 32; ++t)
+        for (int t = 0; t < W; ++t)
         {
             const int code = g.codes[k - t];
-            const uint32_t m = lane_step<R, false>(s[t], rh[t], rf[t], prof.data(), code, t, nullptr, nullptr, nullptr);
+            const uint32_t m = lane_step<R, false, W>(s[t], rh[t], rf[t], prof.data(), code, t, nullptr, nullptr, nullptr);
             track_max(c[t], m, k);
         }
     }
     if (save_trace)
         last = seedS; // the kernel copies its shared-memory seed table to HBM at the end of a forward-graph task
-    finalize_task(info.data(), g.n_nodes, out);
+    finalize_task(info.data(), g.n_nodes, out, W);
 }
 
-template <int R>
+template <int R, int W>
 void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::vector<uint32_t>& ckpt,
               std::vector<uint32_t>& last, int T, int blo, uint32_t* dst, int half)
 {
-    Lane<R> s[32];
-    LaneCtl c[32];
-    for (int t = 0; t < 32; ++t)
+    Lane<R> s[W];
+    LaneCtl c[W];
+    for (int t = 0; t < W; ++t)
     {
-        ckpt_load<R>(s[t], ckpt.data() + (size_t)T * (2 * R + 2) * 32, t);
+        ckpt_load<R, W>(s[t], ckpt.data() + (size_t)T * (2 * R + 2) * W, t);
         ctl_at_step(c[t], g, T * CK, t);
     }
     for (int kk = 0; kk < CK; ++kk)
     {
         const int k = T * CK + kk;
-        for (int t = 0; t < 32; ++t)
+        for (int t = 0; t < W; ++t)
             if (c[t].colsLeft == 0)
-                node_event<R, false>(s[t], c[t], g, t, last.data(), nullptr);
+                node_event<R, false, W>(s[t], c[t], g, t, last.data(), nullptr);
             else
                 --c[t].colsLeft;
-        uint32_t rh[32], rf[32];
-        for (int t = 0; t < 32; ++t)
+        uint32_t rh[W], rf[W];
+        for (int t = 0; t < W; ++t)
         {
             rh[t] = t ? s[t - 1].hbotLast : 0;
             rf[t] = t ? s[t - 1].foutLast : 0;
         }
-        for (int t = 0; t < 32; ++t)
+        for (int t = 0; t < W; ++t)
         {
             uint32_t Hc[R], Ec[R], Fc[R];
-            lane_step<R, true>(s[t], rh[t], rf[t], prof.data(), g.codes[k - t], t, Hc, Ec, Fc);
+            lane_step<R, true, W>(s[t], rh[t], rf[t], prof.data(), g.codes[k - t], t, Hc, Ec, Fc);
             tile_store<R>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, t, blo, Hc, Ec, Fc, half);
         }
     }
 }
 
-template <int R>
+template <int R, int W>
 int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, const uint8_t* bases, int L,
                   unsigned flags, Record& rec, std::vector<uint32_t>& ops_out, int* n_tiles)
 {
@@ -106,13 +106,13 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     std::vector<uint32_t> info0, info1, last, ckpt, dummy1, dummy2;
     TaskOut fw, rv;
     memset(&rv, 0, sizeof rv);
-    emu_fill<R>(g0, bases, L, 0, true, info0, last, ckpt, fw);
+    emu_fill<R, W>(g0, bases, L, 0, true, info0, last, ckpt, fw);
     if (flags & AF_REVERSE_GRAPH)
-        emu_fill<R>(g1, bases, L, 1, false, info1, dummy1, dummy2, rv);
+        emu_fill<R, W>(g1, bases, L, 1, false, info1, dummy1, dummy2, rv);
     const Decision d = decide_strand(fw, rv, flags);
-    std::vector<uint32_t> prof((size_t)NCODE * R * 32);
-    for (int t = 0; t < 32; ++t)
-        build_profile<R>(prof.data(), bases, L, 0, t);
+    std::vector<uint32_t> prof((size_t)NCODE * R * W);
+    for (int t = 0; t < W; ++t)
+        build_profile<R, W>(prof.data(), bases, L, 0, t);
     std::vector<uint32_t> tiles((size_t)2 * TileGeom<R>::SLOT_WORDS, 0);
     TileBuf<R> tb;
     tb.mem = tiles.data();
@@ -124,12 +124,12 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     std::vector<uint32_t> oplog((size_t)2 * L + 64);
     const uint8_t* chars = bytes + sd.chars_off;
     int guard = 0;
-    while (!walk<R>(w, tb, g0, chars, last.data(), bases, L, d.half, fw, oplog.data(), (int)oplog.size(), 0))
+    while (!walk<R, W>(w, tb, g0, chars, last.data(), bases, L, d.half, fw, oplog.data(), (int)oplog.size(), 0, 0u))
     {
         const int T = w.need_step / CK;
         int blo;
         const int slot = tb.admit(T, w.need_row, blo);
-        emu_tile<R>(g0, prof, ckpt, last, T, blo, tiles.data() + (size_t)slot * TileGeom<R>::SLOT_WORDS, d.half);
+        emu_tile<R, W>(g0, prof, ckpt, last, T, blo, tiles.data() + (size_t)slot * TileGeom<R>::SLOT_WORDS, d.half);
         if (n_tiles)
             ++*n_tiles;
         if (++guard > 100000)
@@ -152,7 +152,15 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
 
 } // namespace
 
+namespace
+{
+int g_geom_w = 16; // lanes per task used by the emulator (the kernels' default), see pgemu_set_geometry
+}
+
 extern "C" {
+
+// W = 32, 16 or 8 lanes per task; rows per lane follow from the read length exactly like in the kernels' dispatch
+void pgemu_set_geometry(int w) { g_geom_w = w; }
 
 // Same calling convention as pgo_align_batch (oracle/pg_oracle.h), plus graph arguments.
 // out6 = {graph_pos, score, unique, mapq, is_graph_reverse_strand, status}; returns 0 or negative.
@@ -178,8 +186,19 @@ int pgemu_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off,
         Record rec;
         std::vector<uint32_t> ops;
         int nt = 0;
-        int rc = L <= 160 ? emu_align_one<5>(gs.sites[0], gs.bytes.data(), gs.ints.data(), b, L, flags, rec, ops, &nt)
-                          : emu_align_one<8>(gs.sites[0], gs.bytes.data(), gs.ints.data(), b, L, flags, rec, ops, &nt);
+        const SiteDev& sd0 = gs.sites[0];
+        const uint8_t* gb = gs.bytes.data();
+        const int32_t* gi = gs.ints.data();
+        int rc;
+        if (g_geom_w == 32)
+            rc = L <= 160 ? emu_align_one<5, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt)
+                          : emu_align_one<8, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt);
+        else if (g_geom_w == 16)
+            rc = L <= 160 ? emu_align_one<10, 16>(sd0, gb, gi, b, L, flags, rec, ops, &nt)
+                          : emu_align_one<16, 16>(sd0, gb, gi, b, L, flags, rec, ops, &nt);
+        else
+            rc = L <= 160 ? emu_align_one<20, 8>(sd0, gb, gi, b, L, flags, rec, ops, &nt)
+                          : emu_align_one<32, 8>(sd0, gb, gi, b, L, flags, rec, ops, &nt);
         if (rc)
             worst = rc;
         if (tiles_total)

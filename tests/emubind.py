@@ -31,8 +31,14 @@ def lib():
                                         C.POINTER(C.c_int32), C.c_int, C.c_char_p, C.POINTER(C.c_int32),
                                         C.POINTER(C.c_uint8), C.c_uint, C.POINTER(C.c_int32), C.c_char_p, C.c_char_p,
                                         C.c_int, C.POINTER(C.c_int64)]
+        l.pgemu_set_geometry.argtypes = [C.c_int]
         _lib = l
     return _lib
+
+
+def set_geometry(w):
+    """lanes per task (32, 16 or 8) used by the emulated kernels"""
+    lib().pgemu_set_geometry(int(w))
 
 
 def _p(a, t):

@@ -1,5 +1,5 @@
 """Differential fuzz: CPU lane emulator of the CUDA path (tests/emu) vs the reference (oracle/_ref) or,
-when the reference is absent, the oracle restatement.  Usage: fuzz_emu.py [n_graphs] [reads] [seed] [maxlen]"""
+when the reference is absent, the oracle restatement.  Usage: fuzz_emu.py [n_graphs] [reads] [seed] [maxlen] [W]"""
 import sys, os, time
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
 import numpy as np
@@ -13,6 +13,7 @@ def main():
     nr = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     maxlen = int(sys.argv[4]) if len(sys.argv) > 4 else 160
+    emubind.set_geometry(int(sys.argv[5]) if len(sys.argv) > 5 else 16)
     rng = np.random.default_rng(seed)
     bad = n = tiles = 0
     t0 = time.time()
