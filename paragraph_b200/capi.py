@@ -38,10 +38,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("PG_LIB", LIB_PATH)  # A/B builds of the same ABI (tools/ab_variants.py); default = in-tree library
+    if not os.path.exists(path):
         raise PgError("paragraph_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
-                      "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+                      "(nvcc, sm_100a).  There is no CPU fallback." % path)
+    lib = C.CDLL(path)
     vp, i32p, u32p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint32)
     lib.pg_create.restype = C.c_int
     lib.pg_create.argtypes = [C.c_int, C.POINTER(vp)]

@@ -27,8 +27,18 @@ static_assert(sizeof(pg_record) == sizeof(Record), "pg_record layout");
 namespace
 {
 
-constexpr int FILL_WARPS = 4;  // warps per CTA, fill kernel
-constexpr int TRACE_WARPS = 4; // warps per CTA, traceback kernel
+#ifndef PG_FILL_WARPS
+#define PG_FILL_WARPS 4
+#endif
+#ifndef PG_TRACE_WARPS
+#define PG_TRACE_WARPS 4
+#endif
+#ifndef PG_FILL_UNROLL
+#define PG_FILL_UNROLL 4
+#endif
+constexpr int FILL_UNROLL = PG_FILL_UNROLL;
+constexpr int FILL_WARPS = PG_FILL_WARPS;   // warps per CTA, fill kernel
+constexpr int TRACE_WARPS = PG_TRACE_WARPS; // warps per CTA, traceback kernel
 constexpr unsigned FULL = 0xffffffffu;
 
 struct FillArgs
@@ -105,7 +115,7 @@ template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fi
             ckpt_store<R, W>(s, ckpt + (size_t)cki * (2 * R + 2) * W, gl);
         const int kbase = cki * CK;
         const uint8_t* cp = codes + kbase; // per-lane pointer, immediate offsets inside the unrolled body
-#pragma unroll 4
+#pragma unroll FILL_UNROLL
         for (int kk = 0; kk < CK; ++kk)
         {
             const int k = kbase + kk;
@@ -351,7 +361,7 @@ struct pg_ctx
     uint64_t launches = 0;
     float fill_ms = 0, trace_ms = 0;
     uint64_t scratch_limit = 24ull << 30;
-    int geom_w = 16; // lanes per task; PG_GEOM_W=32|16|8 overrides (tuning / A-B measurements only)
+    int geom_w = 32; // lanes per task; PG_GEOM_W=32|16|8 overrides (tuning / A-B measurements only)
 
     host::GraphStore graphs;
     bool graphs_dirty = true;

@@ -154,7 +154,7 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
 
 namespace
 {
-int g_geom_w = 16; // lanes per task used by the emulator (the kernels' default), see pgemu_set_geometry
+int g_geom_w = 32; // lanes per task used by the emulator (the kernels' default), see pgemu_set_geometry
 }
 
 extern "C" {

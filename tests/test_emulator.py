@@ -11,11 +11,28 @@ from oracle import refbind as R
 from paragraph_b200 import synth
 
 
+@pytest.fixture(autouse=True)
+def _default_geometry():
+    yield
+    emubind.set_geometry(32)
+
+
 @pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
 def test_emulator_golden(built, case):
     got, _ = emubind.emu_align_batch(case["nodes"], case["edges"], case["reads"], is_rev=case["is_rev"],
                                      flags=case["flags"])
     assert strip_status(got) == case["expected"]
+
+
+@pytest.mark.parametrize("w", [16, 8])
+def test_emulator_other_geometries(built, w):
+    """The kernels are templates over (W lanes per task, R rows per lane); W = 16 and 8 instantiations
+    (PG_GEOM_W) must give the same bits as the default W = 32."""
+    emubind.set_geometry(w)
+    for case in golden_cases():
+        got, _ = emubind.emu_align_batch(case["nodes"], case["edges"], case["reads"], is_rev=case["is_rev"],
+                                         flags=case["flags"])
+        assert strip_status(got) == case["expected"], (w, case["name"])
 
 
 def test_emulator_fuzz_vs_oracle(built):

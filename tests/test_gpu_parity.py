@@ -159,6 +159,31 @@ def test_full_size_config2_properties(ctx):
             assert a["graph_reverse"] != b["graph_reverse"]
 
 
+@pytest.mark.parametrize("w", ["16", "8"])
+def test_other_lane_geometries(built, w, monkeypatch):
+    """W = 16 / 8 lanes per task (2 / 4 tasks per warp) give the same bits as the default W = 32."""
+    R.set_fill_variant(0)
+    monkeypatch.setenv("PG_GEOM_W", w)
+    c = capi.Context(0)
+    try:
+        rng = np.random.default_rng(31)
+        reads, sites, exp = [], [], []
+        for k in range(40):
+            nodes, edges = synth.bubble_graph(rng, max_len=int(rng.choice([5, 20, 60, 200])), alphabet="ACGTN")
+            rds = [r[:250] for r in synth.fuzz_reads(rng, nodes, edges, 12, max_len=160)]
+            sid = c.add_graph(nodes, edges)
+            reads += rds
+            sites += [sid] * len(rds)
+            exp += R.OracleGraph(nodes, edges).align_batch(rds)
+        assert strip_status(c.align(reads, sites=sites)) == exp
+        nodes, edges, rds = synth.config2(seed=3, n_reads=301)  # odd count: a half-empty warp at the tail
+        c.clear_graphs()
+        c.add_graph(nodes, edges)
+        assert strip_status(c.align(rds)) == R.OracleGraph(nodes, edges).align_batch(rds)
+    finally:
+        c.close()
+
+
 def test_staged_api_matches_one_call(ctx):
     nodes, edges, reads = synth.config2(seed=1, n_reads=512)
     ctx.clear_graphs()

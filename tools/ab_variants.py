@@ -1,0 +1,46 @@
+"""Build compile-time variants of libpgalign.so (tools/ab_variants.py build) and time them on config 2
+(tools/ab_variants.py run, under gpurun).  Variants live in ab_build/ (git-ignored, travels with gpurun)."""
+import os, subprocess, sys
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+OUT = os.path.join(ROOT, "ab_build")
+VARIANTS = {
+    "base": [],
+    "fw2": ["-DPG_FILL_WARPS=2"],
+    "fw8": ["-DPG_FILL_WARPS=8"],
+    "un2": ["-DPG_FILL_UNROLL=2"],
+    "un8": ["-DPG_FILL_UNROLL=8"],
+    "un16": ["-DPG_FILL_UNROLL=16"],
+    "tw2": ["-DPG_TRACE_WARPS=2"],
+    "tw8": ["-DPG_TRACE_WARPS=8"],
+    "reg96": ["-maxrregcount=96"],
+}
+def build():
+    os.makedirs(OUT, exist_ok=True)
+    src = os.path.join(ROOT, "paragraph_b200", "csrc", "pg_kernels.cu")
+    for name, flags in VARIANTS.items():
+        so = os.path.join(OUT, "libpg_%s.so" % name)
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
+               "-Xcompiler", "-fPIC"] + flags + ["-o", so, src]
+        subprocess.check_call(cmd)
+        print("built", so)
+def run():
+    code = r'''
+import os, sys
+sys.path.insert(0, %r)
+from paragraph_b200 import capi, synth
+nodes, edges, reads = synth.config2(seed=42, n_reads=10000)
+ctx = capi.Context(0); ctx.add_graph(nodes, edges)
+blob, off = ctx.pack_reads(reads)
+for _ in range(3): ctx.align_packed(blob, off)
+ts = []
+for _ in range(6):
+    ctx.align_packed(blob, off); s = ctx.stats(); ts.append((s["fill_ms"], s["trace_ms"]))
+f = min(t[0] for t in ts); t = min(t[1] for t in ts)
+print("%%-6s W=%%s fill %%.3f trace %%.3f total %%.3f ms" %% (os.environ["PG_VARIANT"], os.environ.get("PG_GEOM_W","32"), f, t, f+t), flush=True)
+''' % ROOT
+    for name in VARIANTS:
+        for w in (["32", "16"] if name in ("base", "fw2", "fw8", "un8") else ["32"]):
+            env = dict(os.environ, PG_LIB=os.path.join(OUT, "libpg_%s.so" % name), PG_VARIANT=name, PG_GEOM_W=w)
+            subprocess.run([sys.executable, "-c", code], env=env)
+if __name__ == "__main__":
+    build() if sys.argv[1] == "build" else run()

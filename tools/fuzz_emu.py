@@ -13,7 +13,7 @@ def main():
     nr = int(sys.argv[2]) if len(sys.argv) > 2 else 20
     seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     maxlen = int(sys.argv[4]) if len(sys.argv) > 4 else 160
-    emubind.set_geometry(int(sys.argv[5]) if len(sys.argv) > 5 else 16)
+    emubind.set_geometry(int(sys.argv[5]) if len(sys.argv) > 5 else 32)
     rng = np.random.default_rng(seed)
     bad = n = tiles = 0
     t0 = time.time()
