@@ -45,54 +45,40 @@ constexpr int NCODE = 6;    // A C G T other sentinel
 constexpr int MAX_READ_LEN = 250; // longer reads leave gssw's 8-bit mode (gssw.c:380) -> rejected, see DESIGN.md
 
 // ---------------------------------------------------------------------------------------------
-// packed 2 x 16-bit arithmetic: DPX on the device, plain C on the host (emulator)
+// packed int16x2 arithmetic: DPX on the device, plain C on the host (emulator)
 // ---------------------------------------------------------------------------------------------
-// Every score register holds two problems (halves).  Each half is stored BIASED and UNSIGNED: value + BIAS.
-// Why: with both halves far from 0 and 65535, a per-half add of a small signed constant is exactly one 32-bit
-// integer add of a carry-compensated constant (addend2) -- which runs on the FMA pipe (IMAD), leaving the ALU
-// pipe to the DPX max operations that bound this kernel.  The floor of a local alignment (0)
-// becomes the constant FLOOR2; saturation never happens (scores <= MAX_READ_LEN, sentinel NEG = -16384).
-constexpr int BIAS = 0x5000;
-constexpr uint32_t FLOOR2 = 0x50005000u; // packed biased zero
-
-PG_HD uint32_t pkb(int lo, int hi) { return (uint32_t)((lo + BIAS) & 0xffff) | ((uint32_t)((hi + BIAS) & 0xffff) << 16); }
-PG_HD int val16(uint32_t x, int h) { return (int)((x >> (h ? 16 : 0)) & 0xffffu) - BIAS; } // unbiased value of half h
+PG_HD uint32_t pk(int lo, int hi) { return (uint32_t)(uint16_t)(int16_t)lo | ((uint32_t)(uint16_t)(int16_t)hi << 16); }
+PG_HD int lo16(uint32_t x) { return (int)(int16_t)(uint16_t)(x & 0xffffu); }
+PG_HD int hi16(uint32_t x) { return (int)(int16_t)(uint16_t)(x >> 16); }
+PG_HD int half16(uint32_t x, int h) { return h ? hi16(x) : lo16(x); }
 PG_HD int imax0(int a) { return a > 0 ? a : 0; }
-// addend for addw(): per-half add of (lo, hi); a negative low addend always carries into the high half
-// (biased halves are > |lo|), which the high addend pre-compensates
-PG_HD uint32_t addend2(int lo, int hi) { return (uint32_t)(lo & 0xffff) | ((uint32_t)((hi - (lo < 0 ? 1 : 0)) & 0xffff) << 16); }
 
 #if defined(__CUDA_ARCH__)
-PG_HD uint32_t addw(uint32_t a, uint32_t c)
-{
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(r) : "r"(a), "r"(c)); // IMAD: FMA pipe
-    return r;
-}
-// biased halves lie in [4096, 20480 + MAX_READ_LEN]: positive as int16 as well, so the signed DPX forms apply
-PG_HD uint32_t addmaxu2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); } // max(a+b, c) per half
-PG_HD uint32_t maxu2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
-PG_HD uint32_t maxu3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+PG_HD uint32_t addmax_relu2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); }
+PG_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2(a, b, c); }
+PG_HD uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+PG_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+PG_HD uint32_t add2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
 // max(a, b) per half plus "a >= b" per half (one VIMNMX.S16x2 with two predicate outputs)
-PG_HD uint32_t maxu2_ge(uint32_t a, uint32_t b, bool& hi_ge, bool& lo_ge) { return __vibmax_s16x2(a, b, &hi_ge, &lo_ge); }
+PG_HD uint32_t max2_ge(uint32_t a, uint32_t b, bool& hi_ge, bool& lo_ge) { return __vibmax_s16x2(a, b, &hi_ge, &lo_ge); }
 #else
-PG_HD uint32_t addw(uint32_t a, uint32_t c) { return a + c; }
-PG_HD uint32_t umax_(uint32_t a, uint32_t b) { return a > b ? a : b; }
-PG_HD uint32_t maxu2(uint32_t a, uint32_t b)
+PG_HD int imax_(int a, int b) { return a > b ? a : b; }
+PG_HD uint32_t addmax_relu2(uint32_t a, uint32_t b, uint32_t c)
 {
-    return umax_(a & 0xffffu, b & 0xffffu) | (umax_(a >> 16, b >> 16) << 16);
+    return pk(imax_(imax_(lo16(a) + lo16(b), lo16(c)), 0), imax_(imax_(hi16(a) + hi16(b), hi16(c)), 0));
 }
-PG_HD uint32_t maxu3(uint32_t a, uint32_t b, uint32_t c) { return maxu2(maxu2(a, b), c); }
-PG_HD uint32_t addmaxu2(uint32_t a, uint32_t b, uint32_t c)
+PG_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c)
 {
-    const uint32_t sum = ((a + b) & 0xffffu) | ((((a >> 16) + (b >> 16)) & 0xffffu) << 16);
-    return maxu2(sum, c);
+    return pk(imax_(lo16(a) + lo16(b), lo16(c)), imax_(hi16(a) + hi16(b), hi16(c)));
 }
-PG_HD uint32_t maxu2_ge(uint32_t a, uint32_t b, bool& hi_ge, bool& lo_ge)
+PG_HD uint32_t max2(uint32_t a, uint32_t b) { return pk(imax_(lo16(a), lo16(b)), imax_(hi16(a), hi16(b))); }
+PG_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return max2(max2(a, b), c); }
+PG_HD uint32_t add2(uint32_t a, uint32_t b) { return pk(lo16(a) + lo16(b), hi16(a) + hi16(b)); }
+PG_HD uint32_t max2_ge(uint32_t a, uint32_t b, bool& hi_ge, bool& lo_ge)
 {
-    hi_ge = (a >> 16) >= (b >> 16);
-    lo_ge = (a & 0xffffu) >= (b & 0xffffu);
-    return maxu2(a, b);
+    hi_ge = hi16(a) >= hi16(b);
+    lo_ge = lo16(a) >= lo16(b);
+    return max2(a, b);
 }
 #endif
 
@@ -208,12 +194,12 @@ template <int R> PG_HD void lane_zero(Lane<R>& s)
 {
     for (int r = 0; r < R; ++r)
     {
-        s.Hp[r] = FLOOR2;
-        s.E[r] = FLOOR2;
+        s.Hp[r] = 0;
+        s.E[r] = 0;
     }
-    s.hupPrev = FLOOR2;
-    s.hbotLast = FLOOR2;
-    s.foutLast = FLOOR2;
+    s.hupPrev = 0;
+    s.hbotLast = 0;
+    s.foutLast = 0;
 }
 
 // One wavefront step of one lane.  recvH/recvF = hbotLast/foutLast of lane t-1 after ITS previous step
@@ -225,33 +211,31 @@ template <int R, bool KEEP, int W = 32>
 PG_HD uint32_t lane_step(Lane<R>& s, uint32_t recvH, uint32_t recvF, const uint32_t* prof, int code, int lane,
                          uint32_t* Hc, uint32_t* Ec, uint32_t* Fc)
 {
-    const uint32_t cGO = addend2(-GAP_OPEN, -GAP_OPEN); // t - go as one 32-bit add
-    const uint32_t mGE = 0xffffffffu;                    // per-half -ge inside the DPX add (modular per half)
+    const uint32_t mGO = pk(-GAP_OPEN, -GAP_OPEN), mGE = pk(-GAP_EXT, -GAP_EXT);
     const uint32_t* p = prof + (code * R) * W + lane;
     uint32_t d = s.hupPrev; // diagonal for row 0
     s.hupPrev = recvH;
     uint32_t F = recvF;
     uint32_t m = 0;
-    PG_UNROLL
+PG_UNROLL
     for (int r = 0; r < R; ++r)
     {
-        const uint32_t sc = p[r * W]; // carry-compensated addend (build_profile)
+        const uint32_t sc = p[r * W];
         const uint32_t e = s.E[r];
-        const uint32_t u = addw(d, sc);          // d + s                 (FMA pipe)
-        const uint32_t t = maxu3(u, e, FLOOR2);  // max(d + s, E, 0)
-        const uint32_t tg = addw(t, cGO);        // t - go                (FMA pipe)
-        const uint32_t h = maxu2(t, F);
+        const uint32_t t = addmax_relu2(d, sc, e);
+        const uint32_t tg = add2(t, mGO);
+        const uint32_t h = max2(t, F);
         if (KEEP)
         {
             Hc[r] = h;
             Ec[r] = e;
             Fc[r] = F;
         }
-        s.E[r] = addmaxu2(e, mGE, tg); // max(E - ge, t - go)
-        F = addmaxu2(F, mGE, tg);      // max(F - ge, t - go)
+        s.E[r] = addmax2(e, mGE, tg);
+        F = addmax2(F, mGE, tg);
         d = s.Hp[r];
         s.Hp[r] = h;
-        m = maxu2(m, t);
+        m = max2(m, t);
     }
     s.hbotLast = s.Hp[R - 1];
     s.foutLast = F;
@@ -275,7 +259,7 @@ template <int R, int W = 32> PG_HD void build_profile(uint32_t* prof, const uint
         {
             const int s0 = (c0 < 0 || c == 5) ? NEG : sub_score(c, c0);
             const int s1 = (c1 < 0 || c == 5) ? NEG : sub_score(c, c1);
-            prof[(c * R + r) * W + lane] = addend2(s0, s1);
+            prof[(c * R + r) * W + lane] = pk(s0, s1);
         }
     }
 }
@@ -297,7 +281,7 @@ struct LaneCtl
 PG_HD void ctl_at_step(LaneCtl& c, const GraphView& g, int k0, int lane)
 {
     const int q = k0 - lane; // column about to be processed
-    c.Mnode = FLOOR2;
+    c.Mnode = 0;
     c.first[0] = c.first[1] = 0;
     if (q <= 0)
     {
@@ -329,7 +313,7 @@ PG_HD void ctl_at_step(LaneCtl& c, const GraphView& g, int k0, int lane)
 PG_HD void track_max(LaneCtl& c, uint32_t m, int k)
 {
     bool hi_ge, lo_ge; // old maximum >= this step's value: nothing new
-    c.Mnode = maxu2_ge(c.Mnode, m, hi_ge, lo_ge);
+    c.Mnode = max2_ge(c.Mnode, m, hi_ge, lo_ge);
     if (!lo_ge)
         c.first[0] = k;
     if (!hi_ge)
@@ -362,7 +346,7 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
             infoS[(n * 3 + 0) * W + lane] = c.Mnode;
             infoS[(n * 3 + 1) * W + lane] = (uint32_t)c.first[0];
             infoS[(n * 3 + 2) * W + lane] = (uint32_t)c.first[1];
-            c.Mnode = FLOOR2;
+            c.Mnode = 0;
         }
         c.node = n + 1;
         if (n + 1 < g.n_nodes)
@@ -371,19 +355,19 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
             const int p0 = g.pred_ptr[n + 1], p1 = g.pred_ptr[n + 2];
             if (!(p1 - p0 == 1 && g.pred_idx[p0] == n))
             {
-                uint32_t H[R], E[R], hup = FLOOR2;
+                uint32_t H[R], E[R], hup = 0;
                 for (int r = 0; r < R; ++r)
-                    H[r] = E[r] = FLOOR2;
+                    H[r] = E[r] = 0;
                 for (int e = p0; e < p1; ++e)
                 {
                     const uint32_t* src = seeds + (size_t)g.pred_idx[e] * 2 * R * W;
                     for (int r = 0; r < R; ++r)
                     {
-                        H[r] = maxu2(H[r], src[r * W + lane]);
-                        E[r] = maxu2(E[r], src[(R + r) * W + lane]);
+                        H[r] = max2(H[r], src[r * W + lane]);
+                        E[r] = max2(E[r], src[(R + r) * W + lane]);
                     }
                     if (lane > 0)
-                        hup = maxu2(hup, src[(R - 1) * W + lane - 1]);
+                        hup = max2(hup, src[(R - 1) * W + lane - 1]);
                 }
                 for (int r = 0; r < R; ++r)
                 {
@@ -434,18 +418,16 @@ template <int R> struct TileGeom
 
 PG_HD uint32_t pack_cell(uint32_t h, uint32_t e, uint32_t f, int half)
 {
-    // un-bias (each half >= BIAS after the clamp, so one 32-bit subtraction is exact per half)
-    h = h - FLOOR2;
-    e = maxu2(e, FLOOR2) - FLOOR2;
-    f = maxu2(f, FLOOR2) - FLOOR2;
+    e = max2(e, 0u);
+    f = max2(f, 0u);
 #if defined(__CUDA_ARCH__)
     // bytes: b0 = h.byte(2*half), b1 = e.byte(2*half), b2 = f.byte(2*half), b3 = f.byte(2*half+1) == 0
     const uint32_t s1 = half ? 0x0062u : 0x0040u;
     const uint32_t s2 = half ? 0x7610u : 0x5410u;
     return __byte_perm(__byte_perm(h, e, s1), f, s2);
 #else
-    const int sh = half ? 16 : 0;
-    return ((h >> sh) & 0xffu) | (((e >> sh) & 0xffu) << 8) | (((f >> sh) & 0xffu) << 16);
+    return (uint32_t)(half16(h, half) & 0xff) | ((uint32_t)(half16(e, half) & 0xff) << 8)
+        | ((uint32_t)(half16(f, half) & 0xff) << 16);
 #endif
 }
 PG_HD int cellH(uint32_t w) { return (int)(w & 0xffu); }
@@ -495,7 +477,7 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W)
         for (int n = 0; n < n_nodes; ++n)
             for (int t = 0; t < W; ++t)
             {
-                const int v = val16(ld_scratch(info + (n * 3 + 0) * W + t), h);
+                const int v = half16(ld_scratch(info + (n * 3 + 0) * W + t), h);
                 if (v > S)
                     S = v;
             }
@@ -505,7 +487,7 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W)
             bool has = false;
             for (int t = 0; t < W; ++t)
             {
-                if (val16(ld_scratch(info + (n * 3 + 0) * W + t), h) != S)
+                if (half16(ld_scratch(info + (n * 3 + 0) * W + t), h) != S)
                     continue;
                 has = true;
                 if (mnode == -1 || mnode == n)
@@ -1036,7 +1018,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
             if (w.st == 0)
             {
                 // diagonal source = pred's last column at row j-1 (row -1 never matches: H(0,0) is start or E)
-                const int dsrc = w.j > 0 ? val16(lc[((w.j - 1) % R) * W + (w.j - 1) / R], half) : -1000;
+                const int dsrc = w.j > 0 ? half16(lc[((w.j - 1) % R) * W + (w.j - 1) / R], half) : -1000;
                 if (w.v == dsrc + s) // gssw.c:2999-3040
                 {
                     best = c;
@@ -1048,7 +1030,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
             }
             else
             {
-                const int hsrc = val16(lc[(w.j % R) * W + w.j / R], half);
+                const int hsrc = half16(lc[(w.j % R) * W + w.j / R], half);
                 if (w.v == hsrc - GAP_OPEN) // open, gssw.c:3089-3110
                 {
                     best = c;
@@ -1060,7 +1042,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                 // extend: the reference tests v == E_c(last, j) - ge with E *entering* pred's last column
                 // (gssw.c:3122-3136).  Saved is the seed E' = max(E - ge, t - go) >= E - ge, and v >= E' (v is the max
                 // of the seeds), so v == E' is necessary; only then is the exact E read from pred's last-column tile.
-                const int eseed = imax0(val16(lc[(R + w.j % R) * W + w.j / R], half));
+                const int eseed = imax0(half16(lc[(R + w.j % R) * W + w.j / R], half));
                 if (w.v == eseed)
                 {
                     const int kc = g.node_start[c] + g.node_len[c] - 1 + w.j / R;

@@ -31,7 +31,7 @@ namespace
 #define PG_FILL_WARPS 4
 #endif
 #ifndef PG_TRACE_WARPS
-#define PG_TRACE_WARPS 2
+#define PG_TRACE_WARPS 4
 #endif
 #ifndef PG_FILL_UNROLL
 #define PG_FILL_UNROLL 4
@@ -90,7 +90,7 @@ template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fi
         build_profile<R, W>(prof, bases, L, o, gl);
     else
         for (int x = gl; x < NCODE * R * W; x += W)
-            prof[x] = addend2(NEG, NEG);
+            prof[x] = pk(NEG, NEG);
     __syncwarp();
 
     Lane<R> s;
@@ -128,8 +128,8 @@ template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fi
             uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
             if (gl == 0)
             {
-                rh = FLOOR2; // row -1 and the F entering row 0 are 0
-                rf = FLOOR2;
+                rh = 0;
+                rf = 0;
             }
             const int code = live ? cp[kk] : 5;
             const uint32_t m = lane_step<R, false, W>(s, rh, rf, prof, code, gl, nullptr, nullptr, nullptr);
@@ -240,7 +240,7 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
             lane_zero(s);
             c.node = 0;
             c.colsLeft = COLS_INF;
-            c.Mnode = FLOOR2;
+            c.Mnode = 0;
             c.first[0] = c.first[1] = 0;
         }
         uint32_t* dst = tiles + (size_t)slot * TileGeom<R>::SLOT_WORDS;
@@ -256,8 +256,8 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
             uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
             if (gl == 0)
             {
-                rh = FLOOR2; // row -1 and the F entering row 0 are 0
-                rf = FLOOR2;
+                rh = 0;
+                rf = 0;
             }
             uint32_t Hc[R], Ec[R], Fc[R];
             lane_step<R, true, W>(s, rh, rf, prof, done ? 5 : cp[kk], gl, Hc, Ec, Fc);

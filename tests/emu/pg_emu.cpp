@@ -49,8 +49,8 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
         uint32_t rh[W], rf[W];
         for (int t = 0; t < W; ++t)
         {
-            rh[t] = t ? s[t - 1].hbotLast : FLOOR2;
-            rf[t] = t ? s[t - 1].foutLast : FLOOR2;
+            rh[t] = t ? s[t - 1].hbotLast : 0;
+            rf[t] = t ? s[t - 1].foutLast : 0;
         }
         for (int t = 0; t < W; ++t)
         {
@@ -86,8 +86,8 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
         uint32_t rh[W], rf[W];
         for (int t = 0; t < W; ++t)
         {
-            rh[t] = t ? s[t - 1].hbotLast : FLOOR2;
-            rf[t] = t ? s[t - 1].foutLast : FLOOR2;
+            rh[t] = t ? s[t - 1].hbotLast : 0;
+            rf[t] = t ? s[t - 1].foutLast : 0;
         }
         for (int t = 0; t < W; ++t)
         {
