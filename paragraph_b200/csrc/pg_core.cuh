@@ -153,6 +153,10 @@ struct SiteDev
     int32_t tab_off[2];   // int offset of the orientation's tables
 };
 
+// bytes of one orientation's column codes as staged into shared memory: leading sentinels + G + trailing sentinels,
+// rounded up to the 16-byte granularity of cp.async.bulk (pg_host.hpp lays the blob out accordingly)
+PG_HD uint32_t code_span_bytes(int G) { return ((uint32_t)SENT + (uint32_t)G + SENT + CK + 4 + 15u) & ~15u; }
+
 PG_HD GraphView make_view(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, int o)
 {
     GraphView g;

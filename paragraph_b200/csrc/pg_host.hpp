@@ -84,13 +84,13 @@ struct GraphStore
             chars[(size_t)x] = to_upper((uint8_t)blob[base0 + x]);
         for (int o = 0; o < 2; ++o)
         {
-            while (bytes.size() % 4)
+            while (bytes.size() % 16) // the staged span [codes - SENT, ...) must be 16-byte aligned for the bulk copy (TMA)
                 bytes.push_back(0);
             bytes.insert(bytes.end(), SENT, (uint8_t)5);
             sd.codes_off[o] = (int32_t)bytes.size();
             for (int64_t x = 0; x < G; ++x)
                 bytes.push_back((uint8_t)nt_code(chars[(size_t)(o == 0 ? x : G - 1 - x)]));
-            bytes.insert(bytes.end(), SENT + CK + 4, (uint8_t)5);
+            bytes.insert(bytes.end(), SENT + CK + 4 + 16, (uint8_t)5); // + slack so the span can be rounded up to 16 bytes
         }
         sd.chars_off = (int32_t)bytes.size();
         bytes.insert(bytes.end(), chars.begin(), chars.end());

@@ -31,7 +31,7 @@ namespace
 #define PG_FILL_WARPS 4
 #endif
 #ifndef PG_TRACE_WARPS
-#define PG_TRACE_WARPS 4
+#define PG_TRACE_WARPS 2
 #endif
 #ifndef PG_FILL_UNROLL
 #define PG_FILL_UNROLL 4
@@ -55,10 +55,42 @@ struct FillArgs
     uint32_t* last; // [read in chunk][stride_last]
     uint32_t* ckpt; // [read in chunk][stride_ckpt]
     size_t stride_last, stride_ckpt;
-    int n_nodes_cap; // seed / info table capacity per warp (nodes)
+    int n_nodes_cap; // seed / info table capacity per task (nodes)
+    int code_smem_bytes; // per-task shared-memory room for the staged column codes (0 = read them from global/L1)
+    uint32_t* tabG;  // seed + info tables in HBM when they do not fit shared memory (graphs with very many nodes), else null
+    size_t stride_tab;
     TaskOut* tout; // [2 * n_reads] (global task index)
     int smem_words_per_task;
 };
+
+// ---- TMA (bulk async copy) staging of a task's column codes into shared memory ---------------------------------
+// One elected lane arms an mbarrier with the byte count and issues cp.async.bulk (SASS: UBLKCP); the group's
+// lanes then wait on the barrier's phase 0.  Source and size are 16-byte aligned by construction (pg_host.hpp).
+__device__ __forceinline__ void tma_stage_codes(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
+                                                bool elected)
+{
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
+    const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(dst_smem);
+    if (elected)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
+                     "l"(src_gmem), "r"(bytes), "r"(bar_s)
+                     : "memory");
+    }
+}
+__device__ __forceinline__ void tma_wait(uint64_t* bar)
+{
+    const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar_s)
+                     : "memory");
+}
 
 template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs a)
 {
@@ -66,14 +98,16 @@ template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fi
     constexpr int NT = 32 / W; // tasks per warp: a group of W lanes per task
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / W, gl = lane % W;
-    const int ltask = (blockIdx.x * FILL_WARPS + wic) * NT + grp;
-    if ((blockIdx.x * FILL_WARPS + wic) * NT >= a.n_tasks)
+    const int wpc = blockDim.x >> 5; // warps per CTA: 4, fewer when the seed tables of a many-node graph need the room
+    const int ltask = (blockIdx.x * wpc + wic) * NT + grp;
+    if ((blockIdx.x * wpc + wic) * NT >= a.n_tasks)
         return; // whole warp beyond the work list
     const int rd = a.read0 + (ltask >> 1), o = ltask & 1;
     const bool active = ltask < a.n_tasks && !(o == 1 && !(a.flags & AF_REVERSE_GRAPH));
     uint32_t* prof = smem + ((size_t)wic * NT + grp) * a.smem_words_per_task;
-    uint32_t* seedS = prof + NCODE * R * W;               // [n_nodes_cap][2R][W]
-    uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * W;  // [n_nodes_cap][3][W]
+    // [n_nodes_cap][2R][W] seeds, [n_nodes_cap][3][W] node maxima: warp-private shared memory, or (fallback) HBM
+    uint32_t* seedS = a.tabG ? a.tabG + (size_t)(ltask < a.n_tasks ? ltask : 0) * a.stride_tab : prof + NCODE * R * W;
+    uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * W;
     TaskOut* to = a.tout + (size_t)rd * 2 + o;
     if (!active && ltask < a.n_tasks && gl == 0)
     {
@@ -86,12 +120,21 @@ template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fi
     const GraphView g = make_view(sd, a.gbytes, a.gints, o);
     const uint8_t* bases = a.bases + a.read_off[rdc];
     const int L = a.read_off[rdc + 1] - a.read_off[rdc];
+    // node sequences (column codes) of this task's orientation: TMA-staged into shared memory when they fit
+    uint8_t* code_s = reinterpret_cast<uint8_t*>(prof + a.smem_words_per_task) - a.code_smem_bytes;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(code_s) - 1;
+    const uint32_t span = (uint32_t)code_span_bytes(g.G);
+    const bool staged = active && a.code_smem_bytes >= (int)span;
+    if (staged)
+        tma_stage_codes(code_s, g.codes - SENT, span, bar, gl == 0);
     if (active)
         build_profile<R, W>(prof, bases, L, o, gl);
     else
         for (int x = gl; x < NCODE * R * W; x += W)
             prof[x] = pk(NEG, NEG);
     __syncwarp();
+    if (staged)
+        tma_wait(bar);
 
     Lane<R> s;
     lane_zero(s);
@@ -102,7 +145,7 @@ template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fi
     const bool save = active && (o == 0);
     uint32_t* last = a.last + (size_t)(ltask >> 1) * a.stride_last;
     uint32_t* ckpt = a.ckpt + (size_t)(ltask >> 1) * a.stride_ckpt;
-    const uint8_t* codes = g.codes - gl;
+    const uint8_t* codes = (staged ? code_s + SENT : g.codes) - gl;
     const int my_nck = active ? num_ckpt(g.G, W) : 0;
     int nck = my_nck;
     if (NT > 1) // groups of one warp may belong to different sites: run to the longest, the others idle on sentinels
@@ -377,7 +420,7 @@ struct pg_ctx
     PinBuf<int32_t> h_off, h_site;
     DevBuf<uint8_t> d_bases;
     DevBuf<int32_t> d_off, d_site;
-    DevBuf<uint32_t> d_last, d_ckpt, d_arena;
+    DevBuf<uint32_t> d_last, d_ckpt, d_arena, d_tab;
     DevBuf<TaskOut> d_tout;
     DevBuf<Record> d_records;
     DevBuf<unsigned long long> d_cursor;
@@ -430,13 +473,33 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     constexpr int NT = 32 / W;
     const int max_nodes = c->graphs.max_nodes, max_G = c->graphs.max_G;
     const size_t s_last = host::last_words(max_nodes, R, W), s_ckpt = host::ckpt_words(max_G, R, W);
-    const size_t per_read_bytes = (s_last + s_ckpt) * sizeof(uint32_t);
+    // fill kernel shared memory per task: profile + seed/info tables; fewer warps per CTA for many-node graphs, and
+    // beyond that the tables move to HBM
+    const int tab_words = max_nodes * (2 * R + 3) * W;
+    // staged column codes (+ 8 bytes for the mbarrier in front, kept 16-byte aligned); graphs over 16 KB are read from L1/L2
+    int code_bytes = (int)code_span_bytes(max_G) + 16;
+    if (code_bytes > 16 * 1024 + 16)
+        code_bytes = 0;
+    int fill_words = NCODE * R * W + tab_words + code_bytes / 4;
+    int fill_warps = FILL_WARPS;
+    while (fill_warps > 1 && (size_t)fill_warps * NT * fill_words * 4 > 200 * 1024)
+        fill_warps >>= 1;
+    bool tab_global = false;
+    if ((size_t)fill_warps * NT * fill_words * 4 > 200 * 1024)
+    {
+        tab_global = true;
+        fill_words = NCODE * R * W + code_bytes / 4;
+        fill_warps = FILL_WARPS;
+    }
+    const size_t per_read_bytes = (s_last + s_ckpt + (tab_global ? 2 * (size_t)tab_words : 0)) * sizeof(uint32_t);
     size_t chunk = (size_t)(c->scratch_limit / (per_read_bytes ? per_read_bytes : 1));
     if (chunk < 1)
         chunk = 1;
     if (chunk > (size_t)c->n_reads)
         chunk = (size_t)c->n_reads;
     PG_CUDA(c, c->d_last.reserve(chunk * s_last));
+    if (tab_global)
+        PG_CUDA(c, c->d_tab.reserve(chunk * 2 * (size_t)tab_words));
     PG_CUDA(c, c->d_ckpt.reserve(chunk * s_ckpt));
     PG_CUDA(c, c->d_tout.reserve((size_t)c->n_reads * 2));
     PG_CUDA(c, c->d_records.reserve((size_t)c->n_reads));
@@ -446,8 +509,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
     PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
 
-    const int fill_words = NCODE * R * W + max_nodes * (2 * R + 3) * W; // per task
-    const size_t fill_smem = (size_t)FILL_WARPS * NT * fill_words * sizeof(uint32_t);
+    const size_t fill_smem = (size_t)fill_warps * NT * fill_words * sizeof(uint32_t);
     const int trace_bytes = (NCODE * R * W + oplog_cap + 2 * TileGeom<R>::SLOT_WORDS) * 4; // per read
     const int trace_bytes_al = (trace_bytes + 15) & ~15;
     const size_t trace_smem = (size_t)TRACE_WARPS * NT * trace_bytes_al;
@@ -483,12 +545,15 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.last = c->d_last.p;
         fa.ckpt = c->d_ckpt.p;
         fa.n_nodes_cap = max_nodes;
+        fa.code_smem_bytes = code_bytes ? code_bytes - 16 : 0;
+        fa.tabG = tab_global ? c->d_tab.p : nullptr;
+        fa.stride_tab = (size_t)tab_words;
         fa.stride_last = s_last;
         fa.stride_ckpt = s_ckpt;
         fa.tout = c->d_tout.p;
         fa.smem_words_per_task = fill_words;
-        const int fgrid = (fa.n_tasks + FILL_WARPS * NT - 1) / (FILL_WARPS * NT);
-        pg_fill_kernel<R, W><<<fgrid, FILL_WARPS * 32, fill_smem, c->stream>>>(fa);
+        const int fgrid = (fa.n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
+        pg_fill_kernel<R, W><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
         PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci + 1], c->stream));
@@ -579,6 +644,7 @@ void pg_destroy(pg_ctx* c)
     c->d_off.release();
     c->d_site.release();
     c->d_last.release();
+    c->d_tab.release();
     c->d_ckpt.release();
     c->d_arena.release();
     c->d_tout.release();

@@ -88,10 +88,13 @@ def test_long_nodes_many_checkpoints(ctx):
     assert got == R.OracleGraph(nodes, edges).align_batch(reads)
 
 
-def test_many_nodes_graph(ctx):
+@pytest.mark.parametrize("n_nodes", [24, 60, 300])
+def test_many_nodes_graph(ctx, n_nodes):
+    """24 nodes: 4 warps per CTA; 60: the seed tables force 1 warp per CTA; 300: they move to HBM."""
     R.set_fill_variant(0)
-    rng = np.random.default_rng(12)
-    nodes, edges = synth.bubble_graph(rng, n_nodes=24, max_len=40, p_edge=0.15)
+    rng = np.random.default_rng(12 + n_nodes)
+    nodes, edges = synth.bubble_graph(rng, n_nodes=n_nodes, max_len=40 if n_nodes < 100 else 12,
+                                      p_edge=0.15 if n_nodes < 100 else 0.02)
     reads = [r[:160] for r in synth.fuzz_reads(rng, nodes, edges, 200)]
     ctx.clear_graphs()
     ctx.add_graph(nodes, edges)
