@@ -92,7 +92,9 @@ __device__ __forceinline__ void tma_wait(uint64_t* bar)
                      : "memory");
 }
 
-template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs a)
+// STAGED: the task's column codes are TMA-staged into shared memory (graphs up to 16 KB); otherwise they are read
+// through L1 from global memory.  A template parameter so that the hot loop's loads have a static address space.
+template <int R, int W, bool STAGED> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs a)
 {
     extern __shared__ uint32_t smem[];
     constexpr int NT = 32 / W; // tasks per warp: a group of W lanes per task
@@ -124,7 +126,7 @@ template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fi
     uint8_t* code_s = reinterpret_cast<uint8_t*>(prof + a.smem_words_per_task) - a.code_smem_bytes;
     uint64_t* bar = reinterpret_cast<uint64_t*>(code_s) - 1;
     const uint32_t span = (uint32_t)code_span_bytes(g.G);
-    const bool staged = active && a.code_smem_bytes >= (int)span;
+    const bool staged = STAGED && active; // the host only picks STAGED when every graph of the batch fits
     if (staged)
         tma_stage_codes(code_s, g.codes - SENT, span, bar, gl == 0);
     if (active)
@@ -145,7 +147,7 @@ template <int R, int W> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fi
     const bool save = active && (o == 0);
     uint32_t* last = a.last + (size_t)(ltask >> 1) * a.stride_last;
     uint32_t* ckpt = a.ckpt + (size_t)(ltask >> 1) * a.stride_ckpt;
-    const uint8_t* codes = (staged ? code_s + SENT : g.codes) - gl;
+    const uint8_t* codes = (STAGED ? code_s + SENT : g.codes) - gl;
     const int my_nck = active ? num_ckpt(g.G, W) : 0;
     int nck = my_nck;
     if (NT > 1) // groups of one warp may belong to different sites: run to the longest, the others idle on sentinels
@@ -404,6 +406,7 @@ struct pg_ctx
     uint64_t launches = 0;
     float fill_ms = 0, trace_ms = 0;
     uint64_t scratch_limit = 24ull << 30;
+    bool use_tma = true; // PG_NO_TMA=1 disables the shared-memory staging of column codes (A/B only)
     int geom_w = 32; // lanes per task; PG_GEOM_W=32|16|8 overrides (tuning / A-B measurements only)
 
     host::GraphStore graphs;
@@ -478,7 +481,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     const int tab_words = max_nodes * (2 * R + 3) * W;
     // staged column codes (+ 8 bytes for the mbarrier in front, kept 16-byte aligned); graphs over 16 KB are read from L1/L2
     int code_bytes = (int)code_span_bytes(max_G) + 16;
-    if (code_bytes > 16 * 1024 + 16)
+    if (code_bytes > 16 * 1024 + 16 || !c->use_tma)
         code_bytes = 0;
     int fill_words = NCODE * R * W + tab_words + code_bytes / 4;
     int fill_warps = FILL_WARPS;
@@ -516,7 +519,8 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     if (fill_smem > 227 * 1024 || trace_smem > 227 * 1024)
         return fail(c, PG_E_GRAPH, "graph has too many nodes for the shared-memory seed table ("
                         + std::to_string(max_nodes) + " nodes)");
-    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
     PG_CUDA(c, cudaFuncSetAttribute(pg_trace_kernel<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
 
     const size_t n_chunks = ((size_t)c->n_reads + chunk - 1) / chunk;
@@ -553,7 +557,10 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.tout = c->d_tout.p;
         fa.smem_words_per_task = fill_words;
         const int fgrid = (fa.n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
-        pg_fill_kernel<R, W><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+        if (code_bytes)
+            pg_fill_kernel<R, W, true><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+        else
+            pg_fill_kernel<R, W, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
         PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci + 1], c->stream));
@@ -621,6 +628,8 @@ int pg_create(int device, pg_ctx** out)
         return PG_E_CUDA;
     }
     c->stream = c->own_stream;
+    if (const char* e = getenv("PG_NO_TMA"))
+        c->use_tma = atoi(e) == 0;
     if (const char* e = getenv("PG_GEOM_W"))
     {
         const int w = atoi(e);
