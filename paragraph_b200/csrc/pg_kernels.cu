@@ -94,7 +94,9 @@ __device__ __forceinline__ void tma_wait(uint64_t* bar)
 
 // STAGED: the task's column codes are TMA-staged into shared memory (graphs up to 16 KB); otherwise they are read
 // through L1 from global memory.  A template parameter so that the hot loop's loads have a static address space.
-template <int R, int W, bool STAGED> __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs a)
+// TABG: the seed / node-maximum tables live in HBM (graphs with so many nodes that they do not fit shared memory).
+template <int R, int W, bool STAGED, bool TABG>
+__global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs a)
 {
     extern __shared__ uint32_t smem[];
     constexpr int NT = 32 / W; // tasks per warp: a group of W lanes per task
@@ -108,7 +110,7 @@ template <int R, int W, bool STAGED> __global__ void __launch_bounds__(FILL_WARP
     const bool active = ltask < a.n_tasks && !(o == 1 && !(a.flags & AF_REVERSE_GRAPH));
     uint32_t* prof = smem + ((size_t)wic * NT + grp) * a.smem_words_per_task;
     // [n_nodes_cap][2R][W] seeds, [n_nodes_cap][3][W] node maxima: warp-private shared memory, or (fallback) HBM
-    uint32_t* seedS = a.tabG ? a.tabG + (size_t)(ltask < a.n_tasks ? ltask : 0) * a.stride_tab : prof + NCODE * R * W;
+    uint32_t* seedS = TABG ? a.tabG + (size_t)(ltask < a.n_tasks ? ltask : 0) * a.stride_tab : prof + NCODE * R * W;
     uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * W;
     TaskOut* to = a.tout + (size_t)rd * 2 + o;
     if (!active && ltask < a.n_tasks && gl == 0)
@@ -491,7 +493,8 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     if ((size_t)fill_warps * NT * fill_words * 4 > 200 * 1024)
     {
         tab_global = true;
-        fill_words = NCODE * R * W + code_bytes / 4;
+        code_bytes = 0; // the HBM-table variant reads the codes through L1
+        fill_words = NCODE * R * W;
         fill_warps = FILL_WARPS;
     }
     const size_t per_read_bytes = (s_last + s_ckpt + (tab_global ? 2 * (size_t)tab_words : 0)) * sizeof(uint32_t);
@@ -519,8 +522,9 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     if (fill_smem > 227 * 1024 || trace_smem > 227 * 1024)
         return fail(c, PG_E_GRAPH, "graph has too many nodes for the shared-memory seed table ("
                         + std::to_string(max_nodes) + " nodes)");
-    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
-    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+    PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
     PG_CUDA(c, cudaFuncSetAttribute(pg_trace_kernel<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
 
     const size_t n_chunks = ((size_t)c->n_reads + chunk - 1) / chunk;
@@ -557,10 +561,12 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.tout = c->d_tout.p;
         fa.smem_words_per_task = fill_words;
         const int fgrid = (fa.n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
-        if (code_bytes)
-            pg_fill_kernel<R, W, true><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+        if (tab_global)
+            pg_fill_kernel<R, W, false, true><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+        else if (code_bytes)
+            pg_fill_kernel<R, W, true, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
         else
-            pg_fill_kernel<R, W, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+            pg_fill_kernel<R, W, false, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
         PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci + 1], c->stream));
