@@ -50,7 +50,9 @@ typedef struct pg_record
     uint8_t unique;
     uint8_t chose_reverse;
     uint8_t status; /* 0 ok; 1 traceback dead end (the reference would assert/spin); 2 op log overflow */
-    uint8_t pad;
+    uint8_t query_clipped; /* soft-clipped query bases = sum of the S ops; readfilters::BadAlign
+                              (src/c++/lib/paragraph/readfilters/BadAlign.hh:62-73) filters a read when
+                              read_len - query_clipped < round(bad_align_frac * read_len) -- no CIGAR decode needed */
     uint32_t cigar_off;
     uint32_t cigar_len;
 } pg_record;

@@ -970,3 +970,33 @@ int pgo_align_batch(const pgo_graph* G, int n_reads, const char* blob, const int
     }
     return worst;
 }
+
+/* readfilters::BadAlign (src/c++/lib/paragraph/readfilters/BadAlign.hh:62-73): decode the graph CIGAR, sum the
+ * clipped query bases, filter when aligned < round(frac * queryLength).  queryLength counts M X N I S ops.
+ * Returns 1 if filtered; *clipped_out receives the number of soft-clipped query bases. */
+int pgo_bad_align(const char* cigar, double bad_align_frac, int* clipped_out)
+{
+    long qlen = 0, clipped = 0, num = 0;
+    for (const char* p = cigar; *p; ++p)
+    {
+        if (*p >= '0' && *p <= '9')
+            num = num * 10 + (*p - '0');
+        else if (*p == '[') /* the number before '[' is the node id */
+            num = 0;
+        else if (*p == ']')
+            num = 0;
+        else
+        {
+            if (*p == 'M' || *p == 'X' || *p == 'N' || *p == 'I' || *p == 'S')
+                qlen += num;
+            if (*p == 'S')
+                clipped += num;
+            num = 0;
+        }
+    }
+    if (clipped_out)
+        *clipped_out = (int)clipped;
+    double thr = bad_align_frac * (double)qlen;
+    double r = (double)(long)(thr + 0.5); /* round(): half away from zero, thr >= 0 */
+    return (double)(qlen - clipped) < r;
+}

@@ -51,6 +51,9 @@ int pgo_align_batch(const pgo_graph* g, int n_reads, const char* bases_blob, con
 int pgo_fill_trace(const pgo_graph* g, int reversed_graph, const char* read, int L, int32_t* node_stats,
                    uint8_t* mats, int32_t* res3, int32_t* multi, char* cigar, int cigar_cap);
 
+/* readfilters::BadAlign on a graph CIGAR string (BadAlign.hh:62-73); NonUniq is simply !unique (NonUniq.hh:48-52) */
+int pgo_bad_align(const char* cigar, double bad_align_frac, int* clipped_out);
+
 /* 0 = faithful restatement (default); 1/2 = plain-recurrence model variants used by tests/ to
  * prove the CUDA path's simplifications decision-equivalent (see pg_oracle.c). Not thread-safe. */
 void pgo_set_fill_variant(int v);

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <math.h> // ::round for the reference BadAlign.hh (it relies on a transitive include)
 #include <memory>
 #include <string>
 #include <thread>
@@ -19,6 +20,10 @@
 
 #include "grm/GraphAligner.hh"
 #include "graphcore/Graph.hh"
+#include "graphalign/GraphAlignmentOperations.hh"
+// the reference's read filters applied after alignment (src/c++/lib/paragraph/ReadFilter.cpp:73-90); header-only classes
+#include "../lib/paragraph/readfilters/BadAlign.hh"
+#include "../lib/paragraph/readfilters/NonUniq.hh"
 
 extern "C" {
 #include "gssw.h"
@@ -139,6 +144,49 @@ int pgref_align_batch(
     for (auto& th : pool)
         th.join();
     return 0;
+}
+
+// ---------------------------------------------------------------- read filters (first piece)
+// For each read: decode its graph CIGAR with the reference's decodeGraphAlignment (which also validates it against
+// the graph and throws on any inconsistency) and run readfilters::NonUniq and readfilters::BadAlign.
+// out4[i] = {decode_ok, query_clipped, nonuniq_filtered, badalign_filtered}
+int pgref_filter_batch(
+    int n_nodes, const char* seq_blob, const int32_t* seq_off, int n_edges, const int32_t* efrom, const int32_t* eto,
+    int n_reads, const int32_t* read_len, const int32_t* graph_pos, const uint8_t* unique, const char* cigars,
+    int cigar_stride, double bad_align_frac, int32_t* out4)
+{
+    Graph graph = makeGraph(n_nodes, seq_blob, seq_off, n_edges, efrom, eto);
+    paragraph::readfilters::BadAlign bad(&graph, bad_align_frac);
+    paragraph::readfilters::NonUniq nonuniq;
+    int failures = 0;
+    for (int i = 0; i < n_reads; ++i)
+    {
+        common::Read r;
+        r.set_bases(std::string(static_cast<size_t>(read_len[i]), 'A'));
+        r.set_graph_pos(graph_pos[i]);
+        r.set_graph_cigar(std::string(cigars + static_cast<size_t>(i) * cigar_stride));
+        r.set_is_graph_alignment_unique(unique[i] != 0);
+        int32_t* o = out4 + 4 * i;
+        o[0] = o[1] = o[2] = o[3] = 0;
+        o[2] = nonuniq.filterRead(r).first ? 1 : 0;
+        if (r.graph_cigar().empty()) // score-0 read / AF_CIGAR off: nothing to decode (the reference's NonUniq removes it first)
+            continue;
+        try
+        {
+            const graphtools::GraphAlignment m = graphtools::decodeGraphAlignment(r.graph_pos(), r.graph_cigar(), &graph);
+            size_t clipped = 0;
+            for (auto const& aln : m)
+                clipped += aln.numClipped();
+            o[0] = (m.queryLength() == static_cast<uint32_t>(read_len[i])) ? 1 : 0;
+            o[1] = static_cast<int32_t>(clipped);
+            o[3] = bad.filterRead(r).first ? 1 : 0;
+        }
+        catch (std::exception const&)
+        {
+            ++failures;
+        }
+    }
+    return failures;
 }
 
 // ---------------------------------------------------------------- raw gssw

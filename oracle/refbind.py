@@ -169,6 +169,16 @@ def oracle_lib():
     return _orc
 
 
+def oracle_bad_align(cigar, frac=0.8):
+    """-> (filtered, clipped) per the oracle's restatement of readfilters::BadAlign"""
+    lib = oracle_lib()
+    lib.pgo_bad_align.restype = C.c_int
+    lib.pgo_bad_align.argtypes = [C.c_char_p, C.c_double, C.POINTER(C.c_int)]
+    cl = C.c_int(0)
+    bad = lib.pgo_bad_align(cigar.encode(), float(frac), C.byref(cl))
+    return bool(bad), cl.value
+
+
 def set_fill_variant(v):
     """0 = faithful restatement; 1 = textbook E; 2 = kernel recurrence (see pg_oracle.c)."""
     oracle_lib().pgo_set_fill_variant(int(v))
@@ -235,3 +245,27 @@ class OracleGraph:
 
     def __del__(self):
         self.close()
+
+
+def ref_filter_batch(node_seqs, edges, read_lens, graph_pos, unique, cigars, bad_align_frac=0.8):
+    """Reference decodeGraphAlignment + readfilters::NonUniq / BadAlign on given alignments.
+    Returns int32 array [n][4] = {decode_ok, query_clipped, nonuniq_filtered, badalign_filtered}."""
+    lib = ref_lib()
+    lib.pgref_filter_batch.restype = C.c_int
+    lib.pgref_filter_batch.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_uint8), C.c_char_p, C.c_int, C.c_double, C.POINTER(C.c_int32)]
+    blob, off, ef, et = pack_graph(node_seqs, edges)
+    n = len(read_lens)
+    rl = np.ascontiguousarray(read_lens, dtype=np.int32)
+    gp = np.ascontiguousarray(graph_pos, dtype=np.int32)
+    un = np.ascontiguousarray(unique, dtype=np.uint8)
+    buf = C.create_string_buffer(max(1, n * CIGAR_STRIDE))
+    for i, c in enumerate(cigars):
+        b = c.encode()
+        buf[i * CIGAR_STRIDE:i * CIGAR_STRIDE + len(b) + 1] = b + b"\0"
+    out = np.zeros((n, 4), dtype=np.int32)
+    lib.pgref_filter_batch(len(node_seqs), blob, _p(off, C.c_int32), len(edges), _p(ef, C.c_int32), _p(et, C.c_int32),
+                           n, _p(rl, C.c_int32), _p(gp, C.c_int32), _p(un, C.c_uint8), buf, CIGAR_STRIDE,
+                           float(bad_align_frac), _p(out, C.c_int32))
+    return out

@@ -18,7 +18,7 @@ MAX_READ_LEN = 250
 OPS = "MXNIDS??"
 
 RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i4"), ("unique", "u1"), ("chose_reverse", "u1"),
-                         ("status", "u1"), ("pad", "u1"), ("cigar_off", "<u4"), ("cigar_len", "<u4")])
+                         ("status", "u1"), ("query_clipped", "u1"), ("cigar_off", "<u4"), ("cigar_len", "<u4")])
 
 # every symbol include/pg_align.h declares
 SYMBOLS = ["pg_create", "pg_destroy", "pg_last_error", "pg_set_stream", "pg_set_scratch_limit", "pg_add_graph",
@@ -213,8 +213,20 @@ class Context:
                             mapq=60 if x["unique"] else 0,
                             graph_reverse=bool(is_rev[i] if is_rev is not None else 0) != rv,
                             bases=revcomp_exact(r) if rv else r,
-                            cigar=format_cigar(x, ops) if flags & AF_CIGAR else "", status=int(x["status"])))
+                            cigar=format_cigar(x, ops) if flags & AF_CIGAR else "", status=int(x["status"]),
+                            clipped=int(x["query_clipped"])))
         return out
+
+    @staticmethod
+    def read_filter(rec, read_lens, remove_nonuniq=True, bad_align_frac=0.8):
+        """The reference's default read filter chain (createReadFilter, src/c++/lib/paragraph/ReadFilter.cpp:73-90:
+        NonUniq then BadAlign) evaluated on the records, vectorised.  Returns (nonuniq, bad_align) boolean arrays;
+        a read is filtered when either is set (NonUniq is tested first, like the chain does)."""
+        L = np.asarray(read_lens, dtype=np.int64)
+        nonuniq = (rec["unique"] == 0) if remove_nonuniq else np.zeros(len(rec), dtype=bool)
+        aligned = L - rec["query_clipped"].astype(np.int64)
+        thr = np.floor(bad_align_frac * L + 0.5)  # C round(): half away from zero, arguments are non-negative
+        return nonuniq, aligned < thr
 
     def stats(self):
         n, a, b = C.c_uint64(0), C.c_float(0), C.c_float(0)

@@ -102,6 +102,29 @@ private:
     MappingStatus graph_mapping_status_ = UNMAPPED;
 };
 
+namespace paragraph
+{
+// The reference's default read-filter chain (createReadFilter, src/c++/lib/paragraph/ReadFilter.cpp:73-90: NonUniq,
+// then BadAlign) evaluated from the engine's record instead of decoding the CIGAR string:
+//   NonUniq  : !is_graph_alignment_unique                                   (readfilters/NonUniq.hh:48-52)
+//   BadAlign : read_len - query_clipped < round(bad_align_frac * read_len)  (readfilters/BadAlign.hh:62-73)
+// Returns the reason like ReadFilter::filterRead does ("" = keep).  (KmerFilter is not on the GPU path.)
+struct DefaultReadFilter
+{
+    bool remove_nonuniq = true;
+    double bad_align_frac = 0.8;
+    const char* operator()(pg_record const& r, int read_len) const
+    {
+        if (remove_nonuniq && !r.unique)
+            return "nonuniq";
+        const double thr = (double)(long)(bad_align_frac * read_len + 0.5); // round(), non-negative argument
+        if ((double)(read_len - (int)r.query_clipped) < thr)
+            return "bad_align";
+        return "";
+    }
+};
+} // namespace paragraph
+
 namespace grm
 {
 
@@ -170,7 +193,8 @@ public:
 
     // the loop `for read: alignRead(read, flags)` as one batch; writes the fields GraphAligner::alignRead writes
     // (GraphAligner.cpp:358-401).  ReadIt iterates over (smart) pointers to reads; empty reads are skipped.
-    template <typename ReadIt> void alignBatch(ReadIt begin, ReadIt end, unsigned flags = AF_ALL) const
+    template <typename ReadIt>
+    void alignBatch(ReadIt begin, ReadIt end, unsigned flags = AF_ALL, std::vector<pg_record>* records_out = nullptr) const
     {
         std::string blob;
         std::vector<int32_t> off{ 0 };
@@ -190,6 +214,8 @@ public:
         uint64_t used = 0;
         engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), blob.data(), off.data(), nullptr, flags,
                                       rec.data(), ops.data(), ops.size(), &used));
+        if (records_out) // e.g. for paragraph::DefaultReadFilter, which needs query_clipped
+            *records_out = rec;
         std::string buf;
         for (size_t i = 0; i < which.size(); ++i)
         {

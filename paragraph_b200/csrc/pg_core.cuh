@@ -576,7 +576,7 @@ struct Record
     uint8_t unique;
     uint8_t chose_reverse;
     uint8_t status; // 0 ok, 1 traceback dead end (never seen; the reference would spin/assert), 2 cigar overflow
-    uint8_t pad;
+    uint8_t query_clipped; // soft-clipped query bases: what readfilters::BadAlign sums with numClipped() (BadAlign.hh:62-73)
     uint32_t cigar_off; // index of the first op in the cigar arena
     uint32_t cigar_len; // number of ops
 };
@@ -696,12 +696,15 @@ struct Walker // traceback state of one read (lane 0 only)
     int status;
     int need_step; // on a miss: wavefront step whose tile must be made resident ...
     int need_row;  // ... with a row band ending at this row's lane
+    int clipped;   // soft-clipped query bases (leading + trailing 'S'), for the BadAlign read filter
     int position;
 };
 
 // op log: one cigar_word per traceback move (length 1) or soft clip, in traceback order (back to front)
 PG_HD void push_op(Walker& w, uint32_t* oplog, int cap, int node, int op, int len)
 {
+    if (op == OP_S)
+        w.clipped += len;
     if (w.nops < cap)
         oplog[w.nops] = cigar_word(node, op, len);
     else

@@ -322,7 +322,7 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         rec.unique = (uint8_t)d.unique;
         rec.chose_reverse = (uint8_t)half;
         rec.status = (uint8_t)(w.phase == 2 ? w.status : 1);
-        rec.pad = 0;
+        rec.query_clipped = (uint8_t)w.clipped;
         rec.cigar_off = 0;
         rec.cigar_len = 0;
         if (a.flags & AF_CIGAR)

@@ -140,7 +140,7 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     rec.unique = (uint8_t)d.unique;
     rec.chose_reverse = (uint8_t)d.half;
     rec.status = (uint8_t)w.status;
-    rec.pad = 0;
+    rec.query_clipped = (uint8_t)w.clipped;
     // replay the op log back to front, merging runs of equal (node, op)  (gssw_cigar_push_back/_front merging)
     const int n = w.nops < (int)oplog.size() ? w.nops : (int)oplog.size();
     ops_out.assign((size_t)n + 1, 0);
@@ -209,7 +209,7 @@ int pgemu_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off,
         o[2] = rec.unique;
         o[3] = rec.unique ? 60 : 0;
         o[4] = ((is_rev ? is_rev[i] : 0) != 0) != (rec.chose_reverse != 0);
-        o[5] = rec.status;
+        o[5] = rec.status | (rec.query_clipped << 8);
         if (out_bases_blob)
             for (int j = 0; j < L; ++j)
                 out_bases_blob[read_off[i] + j] = rec.chose_reverse ? (char)complement_base(b[L - 1 - j]) : (char)b[j];

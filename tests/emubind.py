@@ -71,5 +71,5 @@ def emu_align_batch(node_seqs, edges, reads, is_rev=None, flags=0xFFFFFFFF):
         c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
         res.append(dict(pos=int(out[i, 0]), score=int(out[i, 1]), unique=bool(out[i, 2]), mapq=int(out[i, 3]),
                         graph_reverse=bool(out[i, 4]), bases=raw[roff[i]:roff[i + 1]].decode("latin-1"), cigar=c,
-                        status=int(out[i, 5])))
+                        status=int(out[i, 5]) & 0xFF, clipped=int(out[i, 5]) >> 8))
     return res, int(tiles[0])

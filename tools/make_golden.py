@@ -12,8 +12,12 @@ OUT = os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
 
 def case(name, nodes, edges, reads, is_rev=None, flags=R.AF_ALL, note=""):
     res = R.ref_align_batch(nodes, edges, reads, is_rev=is_rev, flags=flags, threads=8)
+    # the reference's decodeGraphAlignment + read filters (NonUniq, BadAlign at 0.8) on its own alignments
+    filt = R.ref_filter_batch(nodes, edges, [len(r) for r in reads], [x["pos"] for x in res],
+                              [x["unique"] for x in res], [x["cigar"] for x in res], 0.8).tolist()
     d = dict(name=name, note=note, nodes=nodes, edges=[list(e) for e in edges], reads=reads,
-             is_rev=list(map(int, is_rev)) if is_rev is not None else None, flags=flags, expected=res)
+             is_rev=list(map(int, is_rev)) if is_rev is not None else None, flags=flags, expected=res,
+             filters=filt, filters_note="per read: [decode_ok, query_clipped, nonuniq_filtered, badalign_filtered(0.8)]")
     with open(os.path.join(OUT, name + ".json"), "w") as f:
         json.dump(d, f, indent=0, separators=(",", ":"))
     print(name, len(reads), "reads")
