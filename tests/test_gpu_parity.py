@@ -202,3 +202,53 @@ def test_staged_api_matches_one_call(ctx):
     for f in ("graph_pos", "score", "unique", "chose_reverse", "status"):
         assert (rec1[f] == rec2[f]).all()
     assert ctx.stats()["kernel_launches"] >= 4
+
+
+def test_two_contexts_in_two_host_threads(built):
+    """A context is single-owner, the library is re-entrant across contexts (one aligner per chunk/thread in the
+    reference, src/c++/lib/grm/Align.cpp:107-110): two host threads, two contexts, same device, same answers."""
+    import threading
+    R.set_fill_variant(0)
+    nodes, edges, reads = synth.config2(seed=11, n_reads=600)
+    exp = R.OracleGraph(nodes, edges).align_batch(reads)
+    out = {}
+
+    def work(k):
+        c = capi.Context(0)
+        try:
+            c.add_graph(nodes, edges)
+            for _ in range(3):
+                out[k] = strip_status(c.align(reads[k::2]))
+        finally:
+            c.close()
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert out[0] == exp[0::2] and out[1] == exp[1::2]
+
+
+def test_runs_on_a_caller_stream(ctx):
+    """pg_set_stream: kernels are launched on the caller's (torch) stream and ordered with its events."""
+    import torch
+    nodes, edges, reads = synth.config2(seed=12, n_reads=256)
+    ctx.clear_graphs()
+    ctx.add_graph(nodes, edges)
+    base = strip_status(ctx.align(reads))
+    s = torch.cuda.Stream()
+    ctx.set_stream(s.cuda_stream)
+    try:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        blob, off = ctx.pack_reads(reads)
+        ctx.upload(blob, off)
+        e0.record(s)
+        ctx.run()
+        e1.record(s)
+        rec, ops = ctx.download()
+        assert e0.elapsed_time(e1) > 0.0
+        got = [capi.format_cigar(r, ops) for r in rec]
+        assert got == [b["cigar"] for b in base]
+    finally:
+        ctx.set_stream(None)
