@@ -39,7 +39,10 @@ namespace pg
 constexpr int GAP_OPEN = 6; // GraphAligner.cpp:231
 constexpr int GAP_EXT = 1;  // GraphAligner.cpp:232
 constexpr int NEG = -16384; // substitution score of sentinel columns / padded rows
-constexpr int CK = 16;      // checkpoint interval = traceback tile size, in wavefront steps
+#ifndef PG_CK
+#define PG_CK 16
+#endif
+constexpr int CK = PG_CK;   // checkpoint interval = traceback tile size, in wavefront steps
 constexpr int SENT = 32;    // sentinel columns (code 5) before and after every column sequence
 constexpr int NCODE = 6;    // A C G T other sentinel
 constexpr int MAX_READ_LEN = 250; // longer reads leave gssw's 8-bit mode (gssw.c:380) -> rejected, see DESIGN.md
@@ -415,7 +418,8 @@ template <int R, int W = 32> PG_HD void ckpt_load(Lane<R>& s, const uint32_t* ck
 // the band are never read.  A cell outside the resident bands is simply a miss (tile recomputed around it).
 template <int R> struct TileGeom
 {
-    static constexpr int BAND_LANES = (35 + R - 1) / R + 1; // >= 36 rows above the entry row whatever its position in its lane
+    // rows the walk can climb within one tile (<= 1 per step on a diagonal, + insertions) + lane alignment slack
+    static constexpr int BAND_LANES = (CK + 19 + R - 1) / R + 1;
     static constexpr int BAND_ROWS = BAND_LANES * R;
     static constexpr int SLOT_WORDS = CK * BAND_ROWS;
 };

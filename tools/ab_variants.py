@@ -5,14 +5,10 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 OUT = os.path.join(ROOT, "ab_build")
 VARIANTS = {
     "base": [],
-    "fw2": ["-DPG_FILL_WARPS=2"],
-    "fw8": ["-DPG_FILL_WARPS=8"],
-    "un2": ["-DPG_FILL_UNROLL=2"],
-    "un8": ["-DPG_FILL_UNROLL=8"],
-    "un16": ["-DPG_FILL_UNROLL=16"],
-    "tw2": ["-DPG_TRACE_WARPS=2"],
-    "tw8": ["-DPG_TRACE_WARPS=8"],
-    "reg96": ["-maxrregcount=96"],
+    "ck32": ["-DPG_CK=32"],
+    "ck8": ["-DPG_CK=8"],
+    "ck32tw4": ["-DPG_CK=32", "-DPG_TRACE_WARPS=4"],
+    "tw1": ["-DPG_TRACE_WARPS=1"],
 }
 def build():
     os.makedirs(OUT, exist_ok=True)
@@ -39,7 +35,7 @@ f = min(t[0] for t in ts); t = min(t[1] for t in ts)
 print("%%-6s W=%%s fill %%.3f trace %%.3f total %%.3f ms" %% (os.environ["PG_VARIANT"], os.environ.get("PG_GEOM_W","32"), f, t, f+t), flush=True)
 ''' % ROOT
     for name in VARIANTS:
-        for w in (["32", "16"] if name in ("base", "fw2", "fw8", "un8") else ["32"]):
+        for w in ["32"]:
             env = dict(os.environ, PG_LIB=os.path.join(OUT, "libpg_%s.so" % name), PG_VARIANT=name, PG_GEOM_W=w)
             subprocess.run([sys.executable, "-c", code], env=env)
 if __name__ == "__main__":
