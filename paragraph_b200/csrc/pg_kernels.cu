@@ -31,7 +31,7 @@ namespace
 #define PG_FILL_WARPS 4
 #endif
 #ifndef PG_TRACE_WARPS
-#define PG_TRACE_WARPS 2
+#define PG_TRACE_WARPS 1
 #endif
 #ifndef PG_FILL_UNROLL
 #define PG_FILL_UNROLL 4

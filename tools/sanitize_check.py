@@ -1,0 +1,24 @@
+"""Small run for compute-sanitizer (memcheck / racecheck / synccheck): golden cases + a multi-site fuzz batch."""
+import json, glob, os, sys
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+import numpy as np
+from paragraph_b200 import capi, synth
+ctx = capi.Context(0)
+n = 0
+for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "*.json")))[:6]:
+    c = json.load(open(p))
+    ctx.clear_graphs(); ctx.add_graph(c["nodes"], [tuple(e) for e in c["edges"]])
+    got = ctx.align(c["reads"][:40], is_rev=(c["is_rev"] or [0] * len(c["reads"]))[:40], flags=c["flags"])
+    for g, e in zip(got, c["expected"][:40]):
+        g.pop("status"); g.pop("clipped")
+        assert g == e
+    n += len(got)
+rng = np.random.default_rng(1)
+ctx.clear_graphs()
+reads, sites = [], []
+for k in range(12):
+    nodes, edges = synth.bubble_graph(rng, n_nodes=[3, 9, 40][k % 3], max_len=40)
+    rd = [r[:160] for r in synth.fuzz_reads(rng, nodes, edges, 6)]
+    sid = ctx.add_graph(nodes, edges); reads += rd; sites += [sid] * len(rd)
+ctx.align(reads, sites=sites)
+print("sanitize run ok:", n + len(reads), "reads")
