@@ -64,22 +64,34 @@ struct FillArgs
 };
 
 // ---- TMA (bulk async copy) staging of a task's column codes into shared memory ---------------------------------
-// One elected lane arms an mbarrier with the byte count and issues cp.async.bulk (SASS: UBLKCP); the group's
-// lanes then wait on the barrier's phase 0.  Source and size are 16-byte aligned by construction (pg_host.hpp).
+// Canonical mbarrier protocol (CUDA programming guide, "Using TMA to transfer one-dimensional arrays"), at group
+// scope: the elected lane initialises the barrier for `nlanes` arrivals and fences the init towards the async
+// proxy; after a __syncwarp it posts the expected byte count (its own arrival) and issues cp.async.bulk
+// (SASS: UBLKCP.S.G); the other lanes arrive; everybody waits for phase 0.  Source and size are 16-byte aligned by
+// construction (pg_host.hpp).
+__device__ __forceinline__ void tma_barrier_init(uint64_t* bar, int nlanes, bool elected)
+{
+    if (elected)
+    {
+        const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(nlanes) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+}
 __device__ __forceinline__ void tma_stage_codes(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar,
                                                 bool elected)
 {
     const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
-    const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(dst_smem);
     if (elected)
     {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t dst_s = (uint32_t)__cvta_generic_to_shared(dst_smem);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s),
                      "l"(src_gmem), "r"(bytes), "r"(bar_s)
                      : "memory");
     }
+    else
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
 }
 __device__ __forceinline__ void tma_wait(uint64_t* bar)
 {
@@ -130,7 +142,10 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     const uint32_t span = (uint32_t)code_span_bytes(g.G);
     const bool staged = STAGED && active; // the host only picks STAGED when every graph of the batch fits
     if (staged)
-        tma_stage_codes(code_s, g.codes - SENT, span, bar, gl == 0);
+        tma_barrier_init(bar, W, gl == 0);
+    __syncwarp();
+    if (staged)
+        tma_stage_codes(code_s, g.codes - SENT, span, bar, gl == 0); // in flight while the profile is built
     if (active)
         build_profile<R, W>(prof, bases, L, o, gl);
     else
