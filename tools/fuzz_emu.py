@@ -31,7 +31,7 @@ def main():
         tiles += nt
         for i, (a, b) in enumerate(zip(exp, got)):
             n += 1
-            st = b.pop("status")
+            st = b.pop("status"); b.pop("clipped", None)
             if a != b or st != 0:
                 bad += 1
                 if bad <= 8:
