@@ -40,6 +40,20 @@ DPX_SLOTS_PER_CELL_PAIR = 5.0           # 4 half-rate DPX ops + 2 full-rate VIMN
 WORKLOAD = "config2: 3-node DEL graph (500 bp flanks, D=300), 10k synthetic 150 bp reads per GPU"
 
 
+def ncu_traffic():
+    """dram bytes read + written per launch of the dominant kernel, from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "r01_fill_kernel_ncu.txt")
+    try:
+        tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        for line in open(path):
+            f = line.split()
+            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * scale[f[2]]
+        return dict(dram_bytes_per_launch=int(tot), source="profiles/r01_fill_kernel_ncu.txt (ncu --set full, same command)")
+    except Exception:
+        return None
+
+
 def workload(rank):
     return synth.config2(seed=42 + rank, n_reads=READS_PER_SITE, read_len=READ_LEN, flank=FLANK, d=DEL_LEN)
 
@@ -264,7 +278,7 @@ def main():
             roofline=dict(bound="alu (packed-int16 DPX issue; neither hbm nor tensor applies, see DESIGN.md)",
                           kernel="pg_fill_kernel<5>", achieved=round(ach_cells / 1e9, 1), peak=round(peak_cells / 1e9, 1),
                           unit="Gcell/s", frac=round(ach_cells / peak_cells, 4) if peak_cells else None,
-                          traffic=None,
+                          traffic=ncu_traffic(),
                           peak_source="tools/ubench/dpx_ubench.cu on this pool: 63.2 DPX lane-ops/clk/SM x 148 SM x "
                                       "clocks.max.sm, 2 cells per lane-op, 5 issue slots per cell pair"),
             roofline_hbm=dict(bound="hbm", achieved=None, peak=peaks.get("hbm_gbs"), unit="GB/s",
