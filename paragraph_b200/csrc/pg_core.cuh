@@ -191,7 +191,7 @@ template <int R> struct Lane
 // (W = 32, 16 or 8: 1, 2 or 4 tasks per warp), each owning R read rows; W * R >= read length.
 template <int R, int W = 32> struct Sizes
 {
-    static constexpr int CKW = 2 * R + 2;  // Hp[R], E[R], hupPrev, foutLast   (hbotLast == Hp[R-1])
+    static constexpr int CKW = R + 1;      // checkpoint words per lane: Hp[R], E[R], hupPrev, foutLast as 4 bytes per word
     static constexpr int LASTW = 2 * R;    // node last column: H[R], E leaving it [R] (= the seed of its successors)
     static constexpr int ROWS = W * R;
     static constexpr int NT = 32 / W;      // tasks per warp
@@ -390,25 +390,54 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
     --c.colsLeft;
 }
 
+// Checkpoint = lane state at the top of a step, byte-packed: every value is two halves in [0, 255] once clamped at
+// 0 (scores <= MAX_READ_LEN; negative E / F are equivalent to 0), so two packed registers fit
+// one 32-bit word: (lo0, hi0, lo1, hi1).  R + 1 words per lane instead of 2R + 2.
+PG_HD uint32_t ck_pack(uint32_t v0, uint32_t v1)
+{
+    v0 = max2(v0, 0u);
+    v1 = max2(v1, 0u);
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v0, v1, 0x6420);
+#else
+    return (v0 & 0xffu) | (((v0 >> 16) & 0xffu) << 8) | ((v1 & 0xffu) << 16) | (((v1 >> 16) & 0xffu) << 24);
+#endif
+}
+PG_HD void ck_unpack(uint32_t w, uint32_t& v0, uint32_t& v1)
+{
+#if defined(__CUDA_ARCH__)
+    v0 = __byte_perm(w, 0u, 0x4140);
+    v1 = __byte_perm(w, 0u, 0x4342);
+#else
+    v0 = (w & 0xffu) | (((w >> 8) & 0xffu) << 16);
+    v1 = ((w >> 16) & 0xffu) | (((w >> 24) & 0xffu) << 16);
+#endif
+}
 template <int R, int W = 32> PG_HD void ckpt_store(const Lane<R>& s, uint32_t* ck, int lane)
 {
+    uint32_t v[2 * R + 2];
     for (int r = 0; r < R; ++r)
     {
-        ck[r * W + lane] = s.Hp[r];
-        ck[(R + r) * W + lane] = s.E[r];
+        v[r] = s.Hp[r];
+        v[R + r] = s.E[r];
     }
-    ck[(2 * R) * W + lane] = s.hupPrev;
-    ck[(2 * R + 1) * W + lane] = s.foutLast;
+    v[2 * R] = s.hupPrev;
+    v[2 * R + 1] = s.foutLast;
+    for (int x = 0; x < R + 1; ++x)
+        ck[x * W + lane] = ck_pack(v[2 * x], v[2 * x + 1]);
 }
 template <int R, int W = 32> PG_HD void ckpt_load(Lane<R>& s, const uint32_t* ck, int lane)
 {
+    uint32_t v[2 * R + 2];
+    for (int x = 0; x < R + 1; ++x)
+        ck_unpack(ck[x * W + lane], v[2 * x], v[2 * x + 1]);
     for (int r = 0; r < R; ++r)
     {
-        s.Hp[r] = ck[r * W + lane];
-        s.E[r] = ck[(R + r) * W + lane];
+        s.Hp[r] = v[r];
+        s.E[r] = v[R + r];
     }
-    s.hupPrev = ck[(2 * R) * W + lane];
-    s.foutLast = ck[(2 * R + 1) * W + lane];
+    s.hupPrev = v[2 * R];
+    s.foutLast = v[2 * R + 1];
     s.hbotLast = s.Hp[R - 1];
 }
 
@@ -459,7 +488,7 @@ PG_HD void tile_store(uint32_t* tstep, int lane, int blo, const uint32_t* Hc, co
 // ---------------------------------------------------------------------------------------------
 //   info  [n_nodes][3][32]      : per node and lane: packed node maximum, first step reaching it (half 0, half 1)
 //   last  [n_nodes][2R][32]     : node last column: H, E leaving it (seed)            (forward-graph tasks only)
-//   ckpt  [n_ck][2R+2][32]      : lane state before step c*CK                      (forward-graph tasks only)
+//   ckpt  [n_ck][R+1][32]       : byte-packed lane state before step c*CK           (forward-graph tasks only)
 PG_HD int num_steps(int G, int W) { return G + W; } // lane W-1 ends column G-1 at step G+W-2; its node event runs at step G+W-1
 PG_HD int num_ckpt(int G, int W) { return (num_steps(G, W) + CK - 1) / CK; }
 

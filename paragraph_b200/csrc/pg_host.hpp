@@ -144,7 +144,7 @@ struct GraphStore
 // per-read scratch sizes in 32-bit words (see pg_core.cuh "per-task scratch layout")
 inline size_t info_words(int max_nodes, int W) { return (size_t)max_nodes * 3 * W; }
 inline size_t last_words(int max_nodes, int R, int W) { return (size_t)max_nodes * 2 * R * W; }
-inline size_t ckpt_words(int max_G, int R, int W) { return (size_t)num_ckpt(max_G, W) * (2 * R + 2) * W; }
+inline size_t ckpt_words(int max_G, int R, int W) { return (size_t)num_ckpt(max_G, W) * (R + 1) * W; }
 
 // "<node>[<len><op>...]..." -- GraphAlignerImpl::extractCigar (GraphAligner.cpp:88-108)
 inline std::string format_cigar(const Record& rec, const uint32_t* ops)

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     {
         const bool live = cki < my_nck;
         if (save && live)
-            ckpt_store<R, W>(s, ckpt + (size_t)cki * (2 * R + 2) * W, gl);
+            ckpt_store<R, W>(s, ckpt + (size_t)cki * (R + 1) * W, gl);
         const int kbase = cki * CK;
         const uint8_t* cp = codes + kbase; // per-lane pointer, immediate offsets inside the unrolled body
 #pragma unroll FILL_UNROLL
@@ -294,7 +294,7 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         LaneCtl c;
         if (!done)
         {
-            ckpt_load<R, W>(s, ckpt + (size_t)T * (2 * R + 2) * W, gl);
+            ckpt_load<R, W>(s, ckpt + (size_t)T * (R + 1) * W, gl);
             ctl_at_step(c, g, T * CK, gl);
         }
         else

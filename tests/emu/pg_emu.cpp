@@ -40,7 +40,7 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
     {
         if (save_trace && k % CK == 0)
             for (int t = 0; t < W; ++t)
-                ckpt_store<R, W>(s[t], ckpt.data() + (size_t)(k / CK) * (2 * R + 2) * W, t);
+                ckpt_store<R, W>(s[t], ckpt.data() + (size_t)(k / CK) * (R + 1) * W, t);
         for (int t = 0; t < W; ++t) // events read what lane t-1 wrote at an EARLIER step only
             if (c[t].colsLeft == 0)
                 node_event<R, true, W>(s[t], c[t], g, t, seedS.data(), info.data());
@@ -72,7 +72,7 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
     LaneCtl c[W];
     for (int t = 0; t < W; ++t)
     {
-        ckpt_load<R, W>(s[t], ckpt.data() + (size_t)T * (2 * R + 2) * W, t);
+        ckpt_load<R, W>(s[t], ckpt.data() + (size_t)T * (R + 1) * W, t);
         ctl_at_step(c[t], g, T * CK, t);
     }
     for (int kk = 0; kk < CK; ++kk)
