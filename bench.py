@@ -201,7 +201,7 @@ def main():
     assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
     ctx.add_graph(nodes, edges)
-    blob, off = ctx.pack_reads(reads)
+    blob, off = ctx.pack_reads(reads, pinned=True)  # the step's inputs live in page-locked host memory
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():

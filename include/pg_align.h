@@ -105,6 +105,12 @@ int pg_batch_upload(pg_ctx* ctx, int32_t n_reads, const char* bases_blob, const 
 int pg_batch_run(pg_ctx* ctx, uint32_t flags);
 int pg_batch_download(pg_ctx* ctx, pg_record* records, uint32_t* cigar_ops, uint64_t cigar_cap, uint64_t* cigar_used);
 
+/* ---- page-locked host buffers (optional) -------------------------------------------------------- */
+/* Reads / records / CIGAR buffers allocated here (or otherwise page-locked and known to CUDA) are copied to and from
+ * the device directly; pageable buffers are staged through the context's own pinned buffers (one extra memcpy). */
+int pg_host_alloc(uint64_t bytes, void** out);
+void pg_host_free(void* p);
+
 /* ---- helpers ----------------------------------------------------------------------------------- */
 /* "<node>[<len><op>...]..." into out (NUL terminated); returns the string length (may exceed cap). */
 int pg_format_cigar(const pg_record* rec, const uint32_t* cigar_ops, char* out, int cap);

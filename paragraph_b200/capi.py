@@ -23,7 +23,7 @@ RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i4"), ("unique", "u1"
 # every symbol include/pg_align.h declares
 SYMBOLS = ["pg_create", "pg_destroy", "pg_last_error", "pg_set_stream", "pg_set_scratch_limit", "pg_add_graph",
            "pg_clear_graphs", "pg_align_batch", "pg_batch_upload", "pg_batch_run", "pg_batch_download",
-           "pg_format_cigar", "pg_stats", "pg_version"]
+           "pg_format_cigar", "pg_stats", "pg_version", "pg_host_alloc", "pg_host_free"]
 
 
 class PgError(RuntimeError):
@@ -73,6 +73,10 @@ def load():
     lib.pg_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.pg_version.restype = C.c_char_p
     lib.pg_version.argtypes = []
+    lib.pg_host_alloc.restype = C.c_int
+    lib.pg_host_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
+    lib.pg_host_free.restype = None
+    lib.pg_host_free.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -99,6 +103,27 @@ def format_cigar(rec, ops):
     if cur >= 0:
         out.append("]")
     return "".join(out)
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory from pg_host_alloc (copied to / from the device without staging)."""
+
+    def __init__(self, shape, dtype):
+        lib = load()
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        if lib.pg_host_alloc(max(n, 16), C.byref(p)) != PG_OK:
+            raise PgError("pg_host_alloc(%d) failed" % n)
+        self._lib, self._p = lib, p
+        buf = (C.c_uint8 * max(n, 16)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            self._lib.pg_host_free(self._p)
+        except Exception:
+            pass
 
 
 class Context:
@@ -143,11 +168,22 @@ class Context:
         self._check(self.lib.pg_clear_graphs(self.h))
 
     @staticmethod
-    def pack_reads(reads):
-        blob = np.frombuffer("".join(reads).encode("latin-1"), dtype=np.uint8).copy()
-        off = np.zeros(len(reads) + 1, dtype=np.int32)
-        off[1:] = np.cumsum([len(r) for r in reads])
+    def pack_reads(reads, pinned=False):
+        raw = np.frombuffer("".join(reads).encode("latin-1"), dtype=np.uint8)
+        offs = np.zeros(len(reads) + 1, dtype=np.int32)
+        offs[1:] = np.cumsum([len(r) for r in reads])
+        if not pinned:
+            return raw.copy(), offs
+        b, o = PinnedArray(raw.shape, np.uint8), PinnedArray(offs.shape, np.int32)
+        b.array[:] = raw
+        o.array[:] = offs
+        b.array.flags.writeable = True
+        keep = (b, o)
+        blob, off = b.array, o.array
+        Context._pinned_keep.append(keep)  # keep the page-locked buffers alive as long as the process
         return blob, off
+
+    _pinned_keep = []
 
     # ---- staged API (bench) -------------------------------------------------------------------
     def upload(self, blob, off, sites=None):
@@ -162,9 +198,11 @@ class Context:
     def _out_buffers(self, n, cigar_cap):
         cap = int(cigar_cap or n * 64 + 4096)
         if self._rec is None or len(self._rec) != n:
-            self._rec = np.empty(n, dtype=RECORD_DTYPE)
+            self._rec_pin = PinnedArray((n,), RECORD_DTYPE)  # page-locked: D2H lands here without staging
+            self._rec = self._rec_pin.array
         if self._ops is None or len(self._ops) < cap:
-            self._ops = np.empty(cap, dtype=np.uint32)
+            self._ops_pin = PinnedArray((cap,), np.uint32)
+            self._ops = self._ops_pin.array
         return self._rec, self._ops, len(self._ops)
 
     def download(self, cigar_cap=None):

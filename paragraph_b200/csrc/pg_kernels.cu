@@ -434,7 +434,7 @@ struct pg_ctx
 
     // batch
     int n_reads = 0, max_len = 0;
-    bool have_sites = false, uploaded = false, ran = false;
+    bool have_sites = false, uploaded = false, ran = false, staging_busy = false;
     size_t bases_bytes = 0;
     PinBuf<uint8_t> h_bases;
     PinBuf<int32_t> h_off, h_site;
@@ -466,6 +466,18 @@ int fail(pg_ctx* c, int code, const std::string& msg)
         if (e_ != cudaSuccess)                                                                                         \
             return fail(c, PG_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));                             \
     } while (0)
+
+// true when p is page-locked host memory known to CUDA (cudaMallocHost / pg_host_alloc / cudaHostRegister)
+bool is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
 
 int upload_graphs(pg_ctx* c)
 {
@@ -756,16 +768,32 @@ int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t
             return fail(c, PG_E_ARG, "read " + std::to_string(i) + " names unknown site " + std::to_string(site[i]));
     }
     const size_t nb = (size_t)(off[n_reads] - off[0]);
-    PG_CUDA(c, c->h_bases.reserve(nb + 16));
-    PG_CUDA(c, c->h_off.reserve((size_t)n_reads + 1));
     PG_CUDA(c, c->d_bases.reserve(nb + 16));
     PG_CUDA(c, c->d_off.reserve((size_t)n_reads + 1));
-    memcpy(c->h_bases.p, bases + off[0], nb);
-    for (int i = 0; i <= n_reads; ++i)
-        c->h_off.p[i] = off[i] - off[0];
-    PG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, c->h_bases.p, nb, cudaMemcpyHostToDevice, c->stream));
-    PG_CUDA(c, cudaMemcpyAsync(c->d_off.p, c->h_off.p, ((size_t)n_reads + 1) * sizeof(int32_t), cudaMemcpyHostToDevice,
-                               c->stream));
+    if (c->staging_busy) // a previous upload's copies may still read the staging buffers
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->staging_busy = false;
+    // Caller buffers that are already page-locked (pg_host_alloc) are copied from directly; pageable ones go
+    // through the context's pinned staging buffers.
+    const bool direct = off[0] == 0 && is_pinned(bases) && is_pinned(off);
+    if (direct)
+    {
+        PG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, bases, nb, cudaMemcpyHostToDevice, c->stream));
+        PG_CUDA(c, cudaMemcpyAsync(c->d_off.p, off, ((size_t)n_reads + 1) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                   c->stream));
+    }
+    else
+    {
+        PG_CUDA(c, c->h_bases.reserve(nb + 16));
+        PG_CUDA(c, c->h_off.reserve((size_t)n_reads + 1));
+        memcpy(c->h_bases.p, bases + off[0], nb);
+        for (int i = 0; i <= n_reads; ++i)
+            c->h_off.p[i] = off[i] - off[0];
+        PG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, c->h_bases.p, nb, cudaMemcpyHostToDevice, c->stream));
+        PG_CUDA(c, cudaMemcpyAsync(c->d_off.p, c->h_off.p, ((size_t)n_reads + 1) * sizeof(int32_t),
+                                   cudaMemcpyHostToDevice, c->stream));
+        c->staging_busy = true;
+    }
     c->have_sites = site != nullptr;
     if (site)
     {
@@ -774,6 +802,7 @@ int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t
         memcpy(c->h_site.p, site, (size_t)n_reads * sizeof(int32_t));
         PG_CUDA(c, cudaMemcpyAsync(c->d_site.p, c->h_site.p, (size_t)n_reads * sizeof(int32_t), cudaMemcpyHostToDevice,
                                    c->stream));
+        c->staging_busy = true;
     }
     c->n_reads = n_reads;
     c->max_len = maxl;
@@ -812,13 +841,20 @@ int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap
     if (!c->ran)
         return fail(c, PG_E_STATE, "pg_batch_download before pg_batch_run");
     PG_CUDA(c, cudaSetDevice(c->device));
-    PG_CUDA(c, c->h_records.reserve((size_t)c->n_reads));
+    const bool rec_direct = is_pinned(records);
+    Record* hrec = reinterpret_cast<Record*>(records);
+    if (!rec_direct)
+    {
+        PG_CUDA(c, c->h_records.reserve((size_t)c->n_reads));
+        hrec = c->h_records.p;
+    }
     PG_CUDA(c, c->h_cursor.reserve(1));
-    PG_CUDA(c, cudaMemcpyAsync(c->h_records.p, c->d_records.p, (size_t)c->n_reads * sizeof(Record),
-                               cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(hrec, c->d_records.p, (size_t)c->n_reads * sizeof(Record), cudaMemcpyDeviceToHost,
+                               c->stream));
     PG_CUDA(c, cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                c->stream));
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->staging_busy = false;
     c->fill_ms = c->trace_ms = 0;
     for (int ci = 0; ci < c->n_chunks_timed; ++ci) // summed over the chunks of the batch
     {
@@ -833,19 +869,28 @@ int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap
         n = c->arena_cap;
     if (used)
         *used = n;
-    memcpy(records, c->h_records.p, (size_t)c->n_reads * sizeof(Record));
+    if (!rec_direct)
+        memcpy(records, hrec, (size_t)c->n_reads * sizeof(Record));
     for (int i = 0; i < c->n_reads; ++i)
-        if (c->h_records.p[i].status == 2)
+        if (hrec[i].status == 2)
             return fail(c, PG_E_CAPACITY, "device cigar arena overflow at read " + std::to_string(i));
     if (n)
     {
         if (!ops || cap < n)
             return fail(c, PG_E_CAPACITY, "cigar arena too small: need " + std::to_string(n) + " ops");
-        PG_CUDA(c, c->h_arena.reserve((size_t)n));
-        PG_CUDA(c, cudaMemcpyAsync(c->h_arena.p, c->d_arena.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                   c->stream));
-        PG_CUDA(c, cudaStreamSynchronize(c->stream));
-        memcpy(ops, c->h_arena.p, (size_t)n * sizeof(uint32_t));
+        if (is_pinned(ops))
+        {
+            PG_CUDA(c, cudaMemcpyAsync(ops, c->d_arena.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            PG_CUDA(c, cudaStreamSynchronize(c->stream));
+        }
+        else
+        {
+            PG_CUDA(c, c->h_arena.reserve((size_t)n));
+            PG_CUDA(c, cudaMemcpyAsync(c->h_arena.p, c->d_arena.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                       c->stream));
+            PG_CUDA(c, cudaStreamSynchronize(c->stream));
+            memcpy(ops, c->h_arena.p, (size_t)n * sizeof(uint32_t));
+        }
     }
     return PG_OK;
 }
@@ -876,6 +921,20 @@ int pg_format_cigar(const pg_record* rec, const uint32_t* ops, char* out, int ca
         out[n] = 0;
     }
     return (int)s.size();
+}
+
+int pg_host_alloc(uint64_t bytes, void** out)
+{
+    if (!out || !bytes)
+        return PG_E_ARG;
+    *out = nullptr;
+    return cudaMallocHost(out, (size_t)bytes) == cudaSuccess ? PG_OK : PG_E_CUDA;
+}
+
+void pg_host_free(void* p)
+{
+    if (p)
+        cudaFreeHost(p);
 }
 
 int pg_stats(const pg_ctx* c, uint64_t* launches, float* fill_ms, float* trace_ms)
