@@ -240,6 +240,8 @@ class Context:
     def align(self, reads, sites=None, is_rev=None, flags=AF_ALL):
         """Align python strings; returns dicts with the fields GraphAligner::alignRead sets on common::Read."""
         from .synth import revcomp_exact
+        if not reads:
+            return []
         blob, off = self.pack_reads(reads)
         st = None if sites is None else np.ascontiguousarray(sites, dtype=np.int32)
         rec, ops = self.align_packed(blob, off, st, flags)

@@ -749,8 +749,15 @@ int pg_clear_graphs(pg_ctx* c)
 
 int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t* off, const int32_t* site)
 {
-    if (!c || n_reads <= 0 || !bases || !off)
+    if (!c || n_reads < 0 || (n_reads > 0 && (!bases || !off)))
         return fail(c, PG_E_ARG, "pg_batch_upload: bad arguments");
+    if (n_reads == 0) // an empty batch is legal (grm::alignReads on an empty read vector does nothing)
+    {
+        c->n_reads = 0;
+        c->uploaded = true;
+        c->ran = false;
+        return PG_OK;
+    }
     PG_CUDA(c, cudaSetDevice(c->device));
     const int nsites = (int)c->graphs.sites.size();
     if (nsites == 0)
@@ -818,6 +825,12 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
         return PG_E_ARG;
     if (!c->uploaded)
         return fail(c, PG_E_STATE, "pg_batch_run before pg_batch_upload");
+    if (c->n_reads == 0)
+    {
+        c->ran = true;
+        c->n_chunks_timed = 0;
+        return PG_OK;
+    }
     PG_CUDA(c, cudaSetDevice(c->device));
     int rc = upload_graphs(c);
     if (rc != PG_OK)
@@ -836,10 +849,16 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
 
 int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap, uint64_t* used)
 {
-    if (!c || !records)
+    if (!c || (!records && c->n_reads > 0))
         return fail(c, PG_E_ARG, "pg_batch_download: bad arguments");
     if (!c->ran)
         return fail(c, PG_E_STATE, "pg_batch_download before pg_batch_run");
+    if (c->n_reads == 0)
+    {
+        if (used)
+            *used = 0;
+        return PG_OK;
+    }
     PG_CUDA(c, cudaSetDevice(c->device));
     const bool rec_direct = is_pinned(records);
     Record* hrec = reinterpret_cast<Record*>(records);

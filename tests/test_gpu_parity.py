@@ -101,6 +101,15 @@ def test_many_nodes_graph(ctx, n_nodes):
     assert strip_status(ctx.align(reads)) == R.OracleGraph(nodes, edges).align_batch(reads)
 
 
+def test_empty_batch_is_legal(ctx):
+    ctx.clear_graphs()
+    ctx.add_graph(["ACGT"], [])
+    assert ctx.align([]) == []
+    blob, off = np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.int32)
+    rec, ops = ctx.align_packed(blob, off)
+    assert len(rec) == 0 and len(ops) == 0
+
+
 def test_errors_are_loud(ctx):
     ctx.clear_graphs()
     with pytest.raises(capi.PgError):
