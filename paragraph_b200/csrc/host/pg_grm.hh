@@ -216,33 +216,39 @@ public:
                                       rec.data(), ops.data(), ops.size(), &used));
         if (records_out) // e.g. for paragraph::DefaultReadFilter, which needs query_clipped
             *records_out = rec;
-        std::string buf;
         for (size_t i = 0; i < which.size(); ++i)
+            applyRecord(**which[i], rec[i], ops.data(), flags, i);
+    }
+
+    // write one record back into a read: the fields GraphAligner::alignRead sets (GraphAligner.cpp:358-401)
+    template <typename ReadT>
+    static void applyRecord(ReadT& read, pg_record const& r, const uint32_t* ops, unsigned flags, size_t index)
+    {
+        if (r.status != 0)
+            throw std::runtime_error("paragraph_b200: traceback failed for read " + std::to_string(index));
+        read.set_is_graph_reverse_strand(read.is_reverse_strand() != (r.chose_reverse != 0)); // :358-359
+        if (r.chose_reverse) // :375-378
         {
-            auto& read = **which[i];
-            const pg_record& r = rec[i];
-            if (r.status != 0)
-                throw std::runtime_error("paragraph_b200: traceback failed for read " + std::to_string(i));
-            read.set_is_graph_reverse_strand(read.is_reverse_strand() != (r.chose_reverse != 0)); // :358-359
-            if (r.chose_reverse) // :375-378
-            {
-                read.set_bases(reverseComplement(read.bases()));
-                std::string q = read.quals();
-                std::reverse(q.begin(), q.end());
-                read.set_quals(q);
-            }
-            read.set_graph_pos(r.graph_pos);
-            read.set_graph_alignment_score(r.score);
-            read.set_is_graph_alignment_unique(r.unique != 0);
-            read.set_graph_mapq(r.unique ? 60 : 0);
-            if (flags & AF_CIGAR)
-            {
-                buf.resize((size_t)12 * (r.cigar_len + 2));
-                const int n = pg_format_cigar(&r, ops.data(), &buf[0], (int)buf.size());
-                read.set_graph_cigar(std::string(buf.data(), (size_t)std::min<int>(n, (int)buf.size() - 1)));
-            }
+            read.set_bases(reverseComplement(read.bases()));
+            std::string q = read.quals();
+            std::reverse(q.begin(), q.end());
+            read.set_quals(q);
+        }
+        read.set_graph_pos(r.graph_pos);
+        read.set_graph_alignment_score(r.score);
+        read.set_is_graph_alignment_unique(r.unique != 0);
+        read.set_graph_mapq(r.unique ? 60 : 0);
+        if (flags & AF_CIGAR)
+        {
+            std::string buf((size_t)12 * (r.cigar_len + 2), '\0');
+            const int n = pg_format_cigar(&r, ops, &buf[0], (int)buf.size());
+            buf.resize((size_t)std::min<int>(n, (int)buf.size() - 1));
+            read.set_graph_cigar(buf);
         }
     }
+
+    pg_ctx* context() const { return engine_->get(); }
+    void check(int rc) const { engine_->check(rc); }
 
     template <typename ReadT> void alignRead(ReadT& read, unsigned flags = AF_ALL) const
     {
@@ -264,6 +270,94 @@ public:
 
 private:
     std::unique_ptr<Engine> engine_;
+};
+
+// Many sites in ONE launch sequence.  grmpy hands (sample, graph) pairs to threads one at a time
+// (src/c++/lib/grmpy/Workflow.cpp:108-146) and a 30x site has only ~200 reads -- far too few to fill a B200 -- so the
+// GPU caller collects sites and flushes them together; results are the same as calling alignReads per site.
+template <typename ReadPtrT> class MultiSiteAligner
+{
+public:
+    explicit MultiSiteAligner(int device = 0, unsigned flags = GraphAligner::AF_ALL) : engine_(new Engine(device)), flags_(flags) {}
+
+    // register a site: its graph and its reads (the vector is updated in place by run(), like grm::alignReads does)
+    template <typename GraphT> void addSite(GraphT const* g, std::vector<ReadPtrT>* reads)
+    {
+        std::string blob;
+        std::vector<int32_t> off{ 0 }, ef, et;
+        const int32_t n = (int32_t)g->numNodes();
+        for (int32_t i = 0; i < n; ++i)
+        {
+            blob += g->nodeSeq((uint32_t)i);
+            off.push_back((int32_t)blob.size());
+            for (auto p : g->predecessors((uint32_t)i))
+            {
+                ef.push_back((int32_t)p);
+                et.push_back(i);
+            }
+        }
+        int32_t sid = -1;
+        engine_->check(pg_add_graph(engine_->get(), n, blob.data(), off.data(), (int32_t)ef.size(), ef.data(), et.data(), &sid));
+        sites_.push_back({ sid, reads });
+    }
+
+    // align every registered site in one batch, apply the filter, keep MAPPED reads per site (Align.cpp:72-84,155)
+    template <typename FilterT> void run(FilterT filter)
+    {
+        std::string blob;
+        std::vector<int32_t> off{ 0 }, site;
+        std::vector<ReadPtrT*> which;
+        for (auto& s : sites_)
+            for (auto& r : *s.reads)
+            {
+                if (r->bases().empty())
+                    continue;
+                blob += r->bases();
+                off.push_back((int32_t)blob.size());
+                site.push_back(s.id);
+                which.push_back(&r);
+            }
+        if (!which.empty())
+        {
+            std::vector<pg_record> rec(which.size());
+            std::vector<uint32_t> ops(blob.size() + 16 * which.size() + 64);
+            uint64_t used = 0;
+            engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), blob.data(), off.data(), site.data(), flags_,
+                                          rec.data(), ops.data(), ops.size(), &used));
+            for (size_t i = 0; i < which.size(); ++i)
+            {
+                auto& read = **which[i];
+                typedef typename std::remove_reference<decltype(read)>::type ReadT;
+                GraphAligner::applyRecord(read, rec[i], ops.data(), flags_, i);
+                read.set_graph_mapping_status(ReadT::MAPPED); // CompositeAligner.cpp:156
+                if (filter && filter(read))
+                    read.set_graph_mapping_status(ReadT::BAD_ALIGN);
+            }
+        }
+        for (auto& s : sites_)
+        {
+            std::vector<ReadPtrT> kept;
+            for (auto& r : *s.reads)
+            {
+                typedef typename std::remove_reference<decltype(*r)>::type ReadT;
+                if (!r->bases().empty() && r->graph_mapping_status() == ReadT::MAPPED)
+                    kept.emplace_back(std::move(r));
+            }
+            s.reads->swap(kept);
+        }
+        sites_.clear();
+        engine_->check(pg_clear_graphs(engine_->get()));
+    }
+
+private:
+    struct Site
+    {
+        int32_t id;
+        std::vector<ReadPtrT>* reads;
+    };
+    std::unique_ptr<Engine> engine_;
+    unsigned flags_;
+    std::vector<Site> sites_;
 };
 
 template <typename ReadT> using ReadFilterT = std::function<bool(ReadT&)>; // include/grm/Filter.hh:36

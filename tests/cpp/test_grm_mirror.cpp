@@ -52,6 +52,32 @@ int main()
             threw = true;
         }
         printf("path-stage-throws %d\n", (int)threw);
+
+        // the same site twice plus a second graph, all in ONE launch through MultiSiteAligner
+        Graph g2(2);
+        g2.setNodeSeq(0, "ACGTACGTAC");
+        g2.setNodeSeq(1, "GGGTTTGGGA");
+        g2.addEdge(0, 1);
+        std::vector<std::unique_ptr<Read>> a, b, c;
+        for (auto const& r : reads)
+        {
+            a.emplace_back(new Read(r));
+            b.emplace_back(new Read(r));
+        }
+        c.emplace_back(new Read("g1", "GTACGGGTTT", "##########"));
+        c.emplace_back(new Read("g2", "AAACCCGTAC", "##########")); // reverse complement of GTACGGGTTT
+        grm::MultiSiteAligner<std::unique_ptr<Read>> multi;
+        multi.addSite(&graph, &a);
+        multi.addSite(&g2, &c);
+        multi.addSite(&graph, &b);
+        multi.run(filter);
+        printf("multi %zu %zu %zu\n", a.size(), c.size(), b.size());
+        for (auto const& r : b)
+            printf("m %s %d %s %d\n", r->fragment_id().c_str(), r->graph_pos(), r->graph_cigar().c_str(),
+                   r->graph_alignment_score());
+        for (auto const& r : c)
+            printf("m %s %d %s %d %d\n", r->fragment_id().c_str(), r->graph_pos(), r->graph_cigar().c_str(),
+                   r->graph_alignment_score(), (int)r->is_graph_reverse_strand());
     }
     catch (std::exception const& e)
     {
