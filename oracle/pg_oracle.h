@@ -58,6 +58,39 @@ int pgo_bad_align(const char* cigar, double bad_align_frac, int* clipped_out);
  * prove the CUDA path's simplifications decision-equivalent (see pg_oracle.c). Not thread-safe. */
 void pgo_set_fill_variant(int v);
 
+/* ---- read filtering + disambiguation + read counting of one site (oracle/pg_oracle_counts.c) ---- */
+enum { PGO_V_MAPPED = 0, PGO_V_NONUNIQ = 1, PGO_V_BAD_ALIGN = 2, PGO_V_INVALID = 3 };
+#define PGO_SUP_NODE_MASK 0xFFFFu
+#define PGO_SUP_NODE 0x40000000u /* path word: the read supports this node */
+#define PGO_SUP_EDGE 0x80000000u /* path word: the read supports the edge (previous path node -> this node) */
+typedef struct pgo_read_support
+{
+    uint64_t sequences; /* bit k: path family (edge label) k is in graph_sequences_supported */
+    uint32_t path_off;  /* first path word of this read */
+    uint16_t path_len;  /* path nodes (0 unless MAPPED) */
+    uint8_t verdict;    /* PGO_V_* */
+    uint8_t graph_reverse;
+} pgo_read_support;
+typedef struct pgo_count4
+{
+    uint32_t fragments, reads, fwd, rev; /* "<name>", ":READS", ":FWD", ":REV" of ReadCounting.cpp:52-69 */
+} pgo_count4;
+
+/* Filter chain (NonUniq if remove_nonuniq, then BadAlign), disambiguateReads with the node/edge support filters of
+ * alignAndDisambiguate (use_support_filters=1) or with null filters (0, as the reference's unit tests call it),
+ * fragments by `fragment` id (>= 0; NULL = every read its own fragment) and the three count tables.
+ * node_len[n_nodes]; edge_labels[n_edges] (bit k = label k) or NULL; cigars = n_reads strings, cigar_stride apart.
+ * node_counts[n_nodes], edge_counts[n_edges]; family_words receives one entry per distinct non-empty label set,
+ * in order of first appearance: {mask_lo, mask_hi, (1 + n_nodes + n_edges) x pgo_count4 = total, nodes, edges}.
+ * Returns 0, -1 path_words too small, -2 negative fragment id, -3 family_words too small. */
+int pgo_count_site(
+    int n_nodes, const int32_t* node_len, int n_edges, const int32_t* efrom, const int32_t* eto,
+    const uint64_t* edge_labels, int n_reads, const int32_t* read_len, const int32_t* graph_pos, const uint8_t* unique,
+    const char* cigars, int cigar_stride, const uint8_t* is_graph_reverse, const int32_t* fragment, int remove_nonuniq,
+    double bad_align_frac, int use_support_filters, pgo_read_support* support, uint32_t* path_words, int path_cap,
+    int* path_used, pgo_count4* node_counts, pgo_count4* edge_counts, uint32_t* family_words, int family_cap,
+    int* family_used);
+
 #ifdef __cplusplus
 }
 #endif

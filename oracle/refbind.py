@@ -269,3 +269,126 @@ def ref_filter_batch(node_seqs, edges, read_lens, graph_pos, unique, cigars, bad
                            n, _p(rl, C.c_int32), _p(gp, C.c_int32), _p(un, C.c_uint8), buf, CIGAR_STRIDE,
                            float(bad_align_frac), _p(out, C.c_int32))
     return out
+
+
+def _cigar_buffer(cigars, stride=None):
+    stride = stride or max([CIGAR_STRIDE] + [len(c) + 1 for c in cigars])
+    buf = C.create_string_buffer(max(1, len(cigars) * stride))
+    for i, c in enumerate(cigars):
+        b = c.encode()
+        buf[i * stride:i * stride + len(b) + 1] = b + b"\0"
+    return buf, stride
+
+
+def ref_count_site(node_seqs, edges, edge_labels, read_lens, graph_pos, cigars, is_graph_reverse=None, fragment=None,
+                   use_filters=True, detailed=True):
+    """Disambiguation + counting of ONE site's MAPPED reads through the reference (oracle/ref_counts.cpp: the
+    unmodified ReadCounting.cpp / Fragment.cpp / graph-tools, plus the restated filter lambdas).
+    edge_labels: one uint64 bit mask per edge (bit k = label "L<k>") or None.  Returns the parsed JSON document
+    (node i is "n<i>", edges "n<i>_n<j>"), or raises RuntimeError with the reference's exception text."""
+    import json
+    lib = ref_lib()
+    lib.pgref_count_site.restype = C.c_int
+    lib.pgref_count_site.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_int, C.POINTER(C.c_int32),
+                                     C.POINTER(C.c_int32), C.c_char_p, C.c_int, C.POINTER(C.c_uint8),
+                                     C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_char_p, C.c_int]
+    blob, off, ef, et = pack_graph(node_seqs, edges)
+    n = len(read_lens)
+    rl = np.ascontiguousarray(read_lens, dtype=np.int32)
+    gp = np.ascontiguousarray(graph_pos, dtype=np.int32)
+    lab = np.ascontiguousarray(edge_labels if edge_labels is not None else np.zeros(len(edges)), dtype=np.uint64)
+    rv = np.ascontiguousarray(is_graph_reverse if is_graph_reverse is not None else np.zeros(n), dtype=np.uint8)
+    fr = np.ascontiguousarray(fragment if fragment is not None else np.arange(n), dtype=np.int32)
+    buf, stride = _cigar_buffer(cigars)
+    cap = 1 << 16
+    while True:
+        out = C.create_string_buffer(cap)
+        rc = lib.pgref_count_site(len(node_seqs), blob, _p(off, C.c_int32), len(edges), _p(ef, C.c_int32),
+                                  _p(et, C.c_int32), _p(lab, C.c_uint64), n, _p(rl, C.c_int32), _p(gp, C.c_int32),
+                                  buf, stride, _p(rv, C.c_uint8), _p(fr, C.c_int32), int(use_filters), int(detailed),
+                                  out, cap)
+        if rc == -1:
+            cap *= 4
+            continue
+        if rc == -2:
+            raise RuntimeError(out.value.decode(errors="replace"))
+        return json.loads(out.value.decode())
+
+
+V_MAPPED, V_NONUNIQ, V_BAD_ALIGN, V_INVALID = 0, 1, 2, 3
+SUP_NODE_MASK, SUP_NODE, SUP_EDGE = 0xFFFF, 0x40000000, 0x80000000
+SUPPORT_DTYPE = np.dtype([("sequences", np.uint64), ("path_off", np.uint32), ("path_len", np.uint16),
+                          ("verdict", np.uint8), ("graph_reverse", np.uint8)])
+
+
+def unpack_families(words, n_nodes, n_edges):
+    """family words -> {mask: int array [(1+n_nodes+n_edges), 4]}"""
+    stride = 2 + 4 * (1 + n_nodes + n_edges)
+    out = {}
+    for q in range(len(words) // stride):
+        h = words[q * stride:(q + 1) * stride]
+        out[int(h[0]) | (int(h[1]) << 32)] = np.array(h[2:], dtype=np.int64).reshape(-1, 4)
+    return out
+
+
+def oracle_count_site(node_lens, edges, edge_labels, read_lens, graph_pos, unique, cigars, is_graph_reverse=None,
+                      fragment=None, remove_nonuniq=True, bad_align_frac=0.8, use_filters=True):
+    """oracle/pg_oracle_counts.c::pgo_count_site.  Returns dict(support, path_words, node_counts [n,4],
+    edge_counts [m,4], families {mask: [(1+n+m),4]})."""
+    lib = oracle_lib()
+    lib.pgo_count_site.restype = C.c_int
+    i32p, u8p, u32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    lib.pgo_count_site.argtypes = [C.c_int, i32p, C.c_int, i32p, i32p, u64p, C.c_int, i32p, i32p, u8p, C.c_char_p,
+                                   C.c_int, u8p, i32p, C.c_int, C.c_double, C.c_int, C.c_void_p, u32p, C.c_int,
+                                   i32p, C.c_void_p, C.c_void_p, u32p, C.c_int, i32p]
+    n, nn, ne = len(read_lens), len(node_lens), len(edges)
+    nl = np.ascontiguousarray(node_lens, dtype=np.int32)
+    ef = np.ascontiguousarray([e[0] for e in edges], dtype=np.int32)
+    et = np.ascontiguousarray([e[1] for e in edges], dtype=np.int32)
+    lab = np.ascontiguousarray(edge_labels if edge_labels is not None else np.zeros(ne), dtype=np.uint64)
+    rl = np.ascontiguousarray(read_lens, dtype=np.int32)
+    gp = np.ascontiguousarray(graph_pos, dtype=np.int32)
+    un = np.ascontiguousarray(unique, dtype=np.uint8)
+    rv = np.ascontiguousarray(is_graph_reverse if is_graph_reverse is not None else np.zeros(n), dtype=np.uint8)
+    fr = np.ascontiguousarray(fragment if fragment is not None else np.arange(n), dtype=np.int32)
+    buf, stride = _cigar_buffer(cigars)
+    sup = np.zeros(n, dtype=SUPPORT_DTYPE)
+    path_cap = max(1, sum(c.count("[") for c in cigars))
+    pw = np.zeros(path_cap, dtype=np.uint32)
+    nc = np.zeros((max(nn, 1), 4), dtype=np.uint32)
+    ec = np.zeros((max(ne, 1), 4), dtype=np.uint32)
+    fam_cap = (2 + 4 * (1 + nn + ne)) * 256
+    fw = np.zeros(fam_cap, dtype=np.uint32)
+    used = np.zeros(2, dtype=np.int32)
+    rc = lib.pgo_count_site(nn, _p(nl, C.c_int32), ne, _p(ef, C.c_int32), _p(et, C.c_int32), _p(lab, C.c_uint64), n,
+                            _p(rl, C.c_int32), _p(gp, C.c_int32), _p(un, C.c_uint8), buf, stride, _p(rv, C.c_uint8),
+                            _p(fr, C.c_int32), int(remove_nonuniq), float(bad_align_frac), int(use_filters),
+                            sup.ctypes.data, _p(pw, C.c_uint32), path_cap, _p(used[0:], C.c_int32), nc.ctypes.data,
+                            ec.ctypes.data, _p(fw, C.c_uint32), fam_cap, _p(used[1:], C.c_int32))
+    if rc != 0:
+        raise RuntimeError("pgo_count_site rc=%d" % rc)
+    return dict(support=sup, path_words=pw[:used[0]], node_counts=nc[:nn].astype(np.int64),
+                edge_counts=ec[:ne].astype(np.int64), families=unpack_families(fw[:used[1]], nn, ne))
+
+
+def counts_from_ref_doc(doc, n_nodes, edges):
+    """Convert ref_count_site()'s JSON (names n<i>, L<k>) into the oracle's array layout."""
+    def four(d, key):
+        return [d.get(key, 0), d.get(key + ":READS", 0), d.get(key + ":FWD", 0), d.get(key + ":REV", 0)]
+    nc = np.array([four(doc["read_counts_by_node"], "n%d" % i) for i in range(n_nodes)], dtype=np.int64).reshape(-1, 4)
+    ec = np.array([four(doc["read_counts_by_edge"], "n%d_n%d" % e) for e in edges], dtype=np.int64).reshape(-1, 4)
+    fams = {}
+    for key, d in doc["read_counts_by_sequence"].items():
+        mask = sum(1 << int(x[1:]) for x in key.split(","))
+        rows = [four(d, "total")] + [four(d, "n%d" % i) for i in range(n_nodes)] + [four(d, "n%d_n%d" % e) for e in edges]
+        fams[mask] = np.array(rows, dtype=np.int64)
+    return nc, ec, fams
+
+
+def support_sets(sup, path_words, i, edges=None):
+    """(nodes set, edges set of (a,b), sequences mask) of read i from the oracle/GPU arrays."""
+    w = path_words[int(sup["path_off"][i]):int(sup["path_off"][i]) + int(sup["path_len"][i])]
+    nodes = {int(x & SUP_NODE_MASK) for x in w if x & SUP_NODE}
+    es = {(int(w[k - 1] & SUP_NODE_MASK), int(w[k] & SUP_NODE_MASK)) for k in range(1, len(w)) if w[k] & SUP_EDGE}
+    return nodes, es, int(sup["sequences"][i])

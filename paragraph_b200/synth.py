@@ -117,6 +117,43 @@ def haplotypes(nodes, edges, limit=64):
     return out
 
 
+def haplotype_paths(nodes, edges, limit=64):
+    """Node-id lists of the source->sink paths, in the order haplotypes() enumerates them."""
+    n = len(nodes)
+    succ = _successors(n, edges)
+    has_pred = {t for _, t in edges}
+    out = []
+
+    def walk(v, acc):
+        if len(out) >= limit:
+            return
+        acc = acc + [v]
+        if not succ[v]:
+            out.append(acc)
+            return
+        for w in succ[v]:
+            walk(w, acc)
+
+    for s in range(n):
+        if s not in has_pred:
+            walk(s, [])
+    return out
+
+
+def haplotype_labels(nodes, edges, limit=8):
+    """One uint64 label mask per edge, bit k = the edge lies on haplotype k (what vcf2paragraph writes as the
+    edge's "sequences", e.g. REF / ALT)."""
+    paths = haplotype_paths(nodes, edges, limit=limit)
+    masks = []
+    for f, t in edges:
+        m = 0
+        for k, p in enumerate(paths):
+            if any(p[i] == f and p[i + 1] == t for i in range(len(p) - 1)):
+                m |= 1 << k
+        masks.append(m)
+    return masks
+
+
 def mutate(rng, s, sub=0.01, indel=0.0, max_indel=6, n_rate=0.0, alphabet="ACGT"):
     b = list(s)
     for i in range(len(b)):
