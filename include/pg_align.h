@@ -114,6 +114,84 @@ void pg_host_free(void* p);
 /* ---- helpers ----------------------------------------------------------------------------------- */
 /* "<node>[<len><op>...]..." into out (NUL terminated); returns the string length (may exceed cap). */
 int pg_format_cigar(const pg_record* rec, const uint32_t* cigar_ops, char* out, int cap);
+/* ------------------------------------------------------------------------------------------------------------
+ * Counting stage: what paragraph::alignAndDisambiguate does with the aligned reads of a site
+ * after grm::alignReads -- the read filter chain, disambiguateReads and countReads -- computed on the device from
+ * the op words of the last pg_batch_run, so that a caller that only needs counts (grmpy: AlignSamples.cpp:124-127)
+ * never downloads or parses a CIGAR.  Replaces
+ *   createReadFilter: NonUniq, BadAlign                src/c++/lib/paragraph/ReadFilter.cpp:73-90
+ *   disambiguateReads + node/edge support filters      src/c++/lib/paragraph/Disambiguation.cpp:82-142, 212-296
+ *   readsToFragments / Fragment::addRead counters      src/c++/lib/common/Fragment.cpp:33-67, 141-182
+ *   countNodes / countEdges / countPathFamilies        src/c++/lib/paragraph/ReadCounting.cpp:52-127
+ * ------------------------------------------------------------------------------------------------------------ */
+
+/* Path-family labels of a site's edges (the "sequences" of the graph JSON's edges; Graph::addLabelToEdge,
+ * GraphInput.cpp:137-147): one 64-bit mask per edge in the order the edges were given to pg_add_graph, bit k =
+ * label k (the caller keeps the k -> name table; at most 64 labels per site).  NULL clears the site's labels. */
+int pg_set_edge_labels(pg_ctx* ctx, int32_t site, const uint64_t* edge_label_mask);
+
+#define PG_V_MAPPED 0    /* passed the filters: takes part in the counts (Read::MAPPED) */
+#define PG_V_NONUNIQ 1   /* removed by readfilters::NonUniq ("nonuniq") */
+#define PG_V_BAD_ALIGN 2 /* removed by readfilters::BadAlign ("bad_align") */
+#define PG_V_INVALID 3   /* decodeGraphAlignment would throw on this CIGAR (empty alignment of a score-0 read that
+                            NonUniq did not remove, or gssw's 'U' quirk): the reference aborts the site; here the read
+                            is reported and left out of the counts */
+
+#define PG_SUP_NODE_MASK 0xFFFFu
+#define PG_SUP_NODE 0x40000000u /* path word: the read supports this node (graph_nodes_supported) */
+#define PG_SUP_EDGE 0x80000000u /* path word: the read supports the edge previous path node -> this node */
+
+typedef struct pg_read_support
+{
+    uint64_t sequences;    /* bit k set: label k is in graph_sequences_supported */
+    uint32_t path_off;     /* first path word of the read ( = its record's cigar_off) */
+    uint16_t path_len;     /* number of path nodes; 0 unless verdict == PG_V_MAPPED */
+    uint8_t verdict;       /* PG_V_* */
+    uint8_t graph_reverse; /* is_graph_reverse_strand = is_reverse_strand != chose_reverse (GraphAligner.cpp:358-359) */
+} pg_read_support;
+
+typedef struct pg_count4
+{
+    uint32_t fragments, reads, fwd, rev; /* JSON "<name>", "<name>:READS", ":FWD", ":REV" (ReadCounting.cpp:52-69) */
+} pg_count4;
+
+typedef struct pg_count_params
+{
+    int32_t remove_nonuniq;      /* Parameters::remove_nonuniq_reads (default 1) */
+    int32_t use_support_filters; /* 1: the node/edge filters alignAndDisambiguate passes to disambiguateReads;
+                                    0: null filters, as the reference's unit tests call disambiguateReads */
+    double bad_align_frac;       /* Parameters::bad_align_frac (default 0.8) */
+    int32_t family_slots;        /* distinct label sets per site the device table can hold; 0 = 16 */
+    int32_t reserved;
+} pg_count_params;
+
+/* Instead of pg_batch_upload + pg_batch_run: load alignments made elsewhere (the other stages of the reference's
+ * CompositeAligner cascade -- PathAligner / KmerAligner / KlibAligner -- or a previous run) as the context's current
+ * batch, so that pg_batch_count can filter, disambiguate and count them.  records[i].cigar_off / cigar_len index
+ * cigar_ops (n_ops words, encoding above); read_len[i] is the read's length (common::Read::bases().size());
+ * read_site as in pg_batch_upload. */
+int pg_batch_import(pg_ctx* ctx, int32_t n_reads, const int32_t* read_len, const int32_t* read_site,
+                    const pg_record* records, const uint32_t* cigar_ops, uint64_t n_ops);
+
+/* Run the counting stage on the batch last executed by pg_batch_run / pg_align_batch on this context.
+ *   fragment          [n_reads] fragment of each read: reads of one fragment (mates) share a value >= 0; a fragment
+ *                     must not span sites.  NULL = every read is its own fragment.
+ *   is_reverse_strand [n_reads] the read's BAM strand (common::Read::is_reverse_strand) or NULL (all forward)
+ *   support           [n_reads] or NULL
+ *   path_words        [path_cap] or NULL: path words of read i at path_words[support[i].path_off ..]; path_cap must
+ *                     be >= the op count pg_batch_download reports; *path_used receives it
+ *   node_counts       [sum of n_nodes over all registered sites], site-major in pg_add_graph order, node order
+ *   edge_counts       [sum of n_edges ...], edges in the order given to pg_add_graph
+ *   family_words      read_counts_by_sequence: one entry per (site, distinct non-empty label set) in no particular
+ *                     order: {site, n, mask_lo, mask_hi, n x pg_count4} with n = 1 + n_nodes + n_edges and the rows
+ *                     "total", nodes, edges (DETAILED_READ_COUNTS); *family_used = words written
+ * PG_E_CAPACITY: an output buffer is too small (sizes in pg_last_error) or a site has more than family_slots label
+ * sets. */
+int pg_batch_count(pg_ctx* ctx, const int32_t* fragment, const uint8_t* is_reverse_strand,
+                   const pg_count_params* params, pg_read_support* support, uint32_t* path_words, uint64_t path_cap,
+                   uint64_t* path_used, pg_count4* node_counts, uint64_t node_cap, pg_count4* edge_counts,
+                   uint64_t edge_cap, uint32_t* family_words, uint64_t family_cap, uint64_t* family_used);
+
 /* Kernels launched by this context so far, and the last batch's per-kernel device time in ms
  * (fill, traceback) measured with CUDA events on the launching stream. */
 int pg_stats(const pg_ctx* ctx, uint64_t* kernel_launches, float* last_fill_ms, float* last_trace_ms);

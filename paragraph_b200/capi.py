@@ -23,7 +23,19 @@ RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i4"), ("unique", "u1"
 # every symbol include/pg_align.h declares
 SYMBOLS = ["pg_create", "pg_destroy", "pg_last_error", "pg_set_stream", "pg_set_scratch_limit", "pg_add_graph",
            "pg_clear_graphs", "pg_align_batch", "pg_batch_upload", "pg_batch_run", "pg_batch_download",
-           "pg_format_cigar", "pg_stats", "pg_version", "pg_host_alloc", "pg_host_free"]
+           "pg_format_cigar", "pg_stats", "pg_version", "pg_host_alloc", "pg_host_free", "pg_set_edge_labels",
+           "pg_batch_import", "pg_batch_count"]
+
+# counting stage (include/pg_align.h, "Counting stage")
+V_MAPPED, V_NONUNIQ, V_BAD_ALIGN, V_INVALID = 0, 1, 2, 3
+SUP_NODE_MASK, SUP_NODE, SUP_EDGE = 0xFFFF, 0x40000000, 0x80000000
+SUPPORT_DTYPE = np.dtype([("sequences", "<u8"), ("path_off", "<u4"), ("path_len", "<u2"), ("verdict", "u1"),
+                          ("graph_reverse", "u1")])
+
+
+class CountParams(C.Structure):
+    _fields_ = [("remove_nonuniq", C.c_int32), ("use_support_filters", C.c_int32), ("bad_align_frac", C.c_double),
+                ("family_slots", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PgError(RuntimeError):
@@ -77,6 +89,14 @@ def load():
     lib.pg_host_alloc.argtypes = [C.c_uint64, C.POINTER(vp)]
     lib.pg_host_free.restype = None
     lib.pg_host_free.argtypes = [vp]
+    u64p = C.POINTER(C.c_uint64)
+    lib.pg_set_edge_labels.restype = C.c_int
+    lib.pg_set_edge_labels.argtypes = [vp, C.c_int32, u64p]
+    lib.pg_batch_import.restype = C.c_int
+    lib.pg_batch_import.argtypes = [vp, C.c_int32, i32p, i32p, vp, u32p, C.c_uint64]
+    lib.pg_batch_count.restype = C.c_int
+    lib.pg_batch_count.argtypes = [vp, i32p, C.POINTER(C.c_uint8), C.POINTER(CountParams), vp, u32p, C.c_uint64, u64p,
+                                   vp, C.c_uint64, vp, C.c_uint64, u32p, C.c_uint64, u64p]
     _lib = lib
     return lib
 
@@ -103,6 +123,20 @@ def format_cigar(rec, ops):
     if cur >= 0:
         out.append("]")
     return "".join(out)
+
+
+def parse_cigar(cigar):
+    """'<node>[<len><op>...]...' -> op words (node << 16 | len << 3 | op), the inverse of format_cigar; an empty
+    node group "id[]" becomes the OP_NONE marker."""
+    import re
+    words = []
+    for node, body in re.findall(r"(\d+)\[([^\]]*)\]", cigar):
+        ops = re.findall(r"(\d+)([MXNIDS])", body)
+        if not ops:
+            words.append((int(node) << 16) | 7)
+        for ln, op in ops:
+            words.append((int(node) << 16) | (int(ln) << 3) | OPS.index(op))
+    return words
 
 
 class PinnedArray:
@@ -138,6 +172,8 @@ class Context:
                           "paragraph_b200 has no CPU fallback" % (device, rc))
         self.h = h
         self._keep = None
+        self._shape = []   # (n_nodes, n_edges) of every registered site, for sizing the count tables
+        self._n = 0
         self._rec = None   # output buffers are reused between calls of the same size (no per-call allocation)
         self._ops = None
         if stream is not None:
@@ -162,10 +198,71 @@ class Context:
         sid = C.c_int32(-1)
         self._check(self.lib.pg_add_graph(self.h, len(node_seqs), blob, _i32(off), len(edges), _i32(ef), _i32(et),
                                           C.byref(sid)))
+        self._shape.append((len(node_seqs), len(edges)))
         return sid.value
 
     def clear_graphs(self):
         self._check(self.lib.pg_clear_graphs(self.h))
+        self._shape = []
+
+    # ---- counting stage ------------------------------------------------------------------------
+    def set_edge_labels(self, site, masks):
+        """Path-family labels ("sequences") of a site's edges: one uint64 bit mask per edge, in add_graph's edge order."""
+        m = None if masks is None else np.ascontiguousarray(masks, dtype=np.uint64)
+        self._check(self.lib.pg_set_edge_labels(self.h, int(site),
+                                                None if m is None else m.ctypes.data_as(C.POINTER(C.c_uint64))))
+
+    def import_alignments(self, read_lens, records, ops, sites=None):
+        """Make alignments produced elsewhere (records + op words) the context's current batch (pg_batch_import)."""
+        rl = np.ascontiguousarray(read_lens, dtype=np.int32)
+        rec = np.ascontiguousarray(records, dtype=RECORD_DTYPE)
+        op = np.ascontiguousarray(ops, dtype=np.uint32)
+        st = None if sites is None else np.ascontiguousarray(sites, dtype=np.int32)
+        self._n = len(rl)
+        self._check(self.lib.pg_batch_import(self.h, len(rl), _i32(rl), _i32(st) if st is not None else None,
+                                             C.c_void_p(rec.ctypes.data), op.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                             len(op)))
+
+    def count(self, fragment=None, is_rev=None, remove_nonuniq=True, bad_align_frac=0.8, use_filters=True,
+              family_slots=0, want_support=True):
+        """Read filters + disambiguation + fragment counts of the batch last run (pg_batch_count).
+        Returns dict(support, path_words, node_counts [sum n_nodes, 4], edge_counts [sum n_edges, 4],
+        families {(site, mask): int array [1 + n_nodes + n_edges, 4]}); rows are site-major in add_graph order."""
+        n = self._n
+        prm = CountParams(int(remove_nonuniq), int(use_filters), float(bad_align_frac), int(family_slots), 0)
+        fr = None if fragment is None else np.ascontiguousarray(fragment, dtype=np.int32)
+        rv = None if is_rev is None else np.ascontiguousarray(is_rev, dtype=np.uint8)
+        tn, te = sum(s[0] for s in self._shape), sum(s[1] for s in self._shape)
+        nc = np.zeros((max(tn, 1), 4), dtype=np.uint32)
+        ec = np.zeros((max(te, 1), 4), dtype=np.uint32)
+        sup = np.zeros(max(n, 1), dtype=SUPPORT_DTYPE)
+        path_cap = int(n * 64 + 4096)
+        fam_cap = 1 << 16
+        for attempt in range(3):
+            pw = np.zeros(path_cap, dtype=np.uint32)
+            fw = np.zeros(fam_cap, dtype=np.uint32)
+            pu, fu = C.c_uint64(0), C.c_uint64(0)
+            rc = self.lib.pg_batch_count(
+                self.h, _i32(fr) if fr is not None else None,
+                rv.ctypes.data_as(C.POINTER(C.c_uint8)) if rv is not None else None, C.byref(prm),
+                C.c_void_p(sup.ctypes.data) if want_support else None,
+                pw.ctypes.data_as(C.POINTER(C.c_uint32)) if want_support else None, path_cap, C.byref(pu),
+                C.c_void_p(nc.ctypes.data), len(nc), C.c_void_p(ec.ctypes.data), len(ec),
+                fw.ctypes.data_as(C.POINTER(C.c_uint32)), fam_cap, C.byref(fu))
+            if rc == -5 and attempt < 2 and b"needs" in self.lib.pg_last_error(self.h):
+                path_cap = max(path_cap, int(n) * 520 + 4096)
+                fam_cap = max(fam_cap * 16, int(fu.value) + 16)
+                continue
+            self._check(rc)
+            break
+        fams, w, words = {}, 0, fw[:fu.value]
+        while w < len(words):
+            k = int(words[w + 1])
+            fams[(int(words[w]), int(words[w + 2]) | (int(words[w + 3]) << 32))] = \
+                words[w + 4:w + 4 + 4 * k].astype(np.int64).reshape(k, 4)
+            w += 4 + 4 * k
+        return dict(support=sup[:n], path_words=pw[:pu.value], node_counts=nc[:tn].astype(np.int64),
+                    edge_counts=ec[:te].astype(np.int64), families=fams)
 
     @staticmethod
     def pack_reads(reads, pinned=False):
@@ -223,7 +320,7 @@ class Context:
     def align_packed(self, blob, off, sites=None, flags=AF_ALL, cigar_cap=None):
         """One pg_align_batch call.  Returns (records, ops) as views of buffers owned by the context (valid until
         the next call).  If the default CIGAR arena is too small the call is repeated once with a full-size one."""
-        n = len(off) - 1
+        n = self._n = len(off) - 1
         for attempt in range(2):
             rec, ops, cap = self._out_buffers(n, cigar_cap)
             used = C.c_uint64(0)

@@ -8,9 +8,11 @@
 #include <algorithm>
 #include <cstdint>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "pg_core.cuh"
+#include "pg_count.cuh"
 
 namespace pg
 {
@@ -24,6 +26,11 @@ struct GraphStore
     std::vector<int32_t> ints;
     int max_nodes = 0;
     int max_G = 0;
+    // for the counting stage (pg_count.cuh): the edges as given (input order is the order of the edge count rows),
+    // their path-family label masks (pg_set_edge_labels; 0 = unlabelled) and each site's first row
+    std::vector<int32_t> in_from, in_to;
+    std::vector<uint64_t> in_label;
+    std::vector<int64_t> edge_base, node_base; // [n_sites + 1]
 
     void clear()
     {
@@ -31,6 +38,11 @@ struct GraphStore
         bytes.clear();
         ints.clear();
         max_nodes = max_G = 0;
+        in_from.clear();
+        in_to.clear();
+        in_label.clear();
+        edge_base.clear();
+        node_base.clear();
     }
 
     // returns site id >= 0, or -1 with err set
@@ -135,11 +147,99 @@ struct GraphStore
                 ints.push_back(0);
         }
         sites.push_back(sd);
+        if (edge_base.empty())
+        {
+            edge_base.push_back(0);
+            node_base.push_back(0);
+        }
+        in_from.insert(in_from.end(), ef, ef + n_edges);
+        in_to.insert(in_to.end(), et, et + n_edges);
+        in_label.insert(in_label.end(), (size_t)n_edges, 0ull);
+        edge_base.push_back(edge_base.back() + n_edges);
+        node_base.push_back(node_base.back() + n_nodes);
         max_nodes = std::max(max_nodes, n_nodes);
         max_G = std::max(max_G, (int)G);
         return (int)sites.size() - 1;
     }
 };
+
+// ---------------------------------------------------------------------------------------------
+// counting stage, host side (tables for pg_count.cuh)
+// ---------------------------------------------------------------------------------------------
+struct CountHostTables
+{
+    std::vector<CountSite> csite;
+    std::vector<int32_t> csr_input;
+    std::vector<uint64_t> lab_edge, lab_out, lab_in;
+    int64_t fam_rows = 0;
+};
+
+// per site: CSR edge -> input edge index, label masks per CSR edge and per node, bases of the count rows
+inline void build_count_tables(const GraphStore& gs, int slots, CountHostTables& t)
+{
+    const size_t ns = gs.sites.size();
+    t.csr_input.assign((size_t)gs.edge_base[ns], 0);
+    t.lab_edge.assign((size_t)gs.edge_base[ns], 0);
+    t.lab_out.assign((size_t)gs.node_base[ns], 0);
+    t.lab_in.assign((size_t)gs.node_base[ns], 0);
+    t.csite.resize(ns);
+    int64_t fam = 0;
+    for (size_t s = 0; s < ns; ++s)
+    {
+        const SiteDev& sd = gs.sites[s];
+        const GraphView g = make_view(sd, gs.bytes.data(), gs.ints.data(), 0);
+        const int64_t eb = gs.edge_base[s], nb = gs.node_base[s];
+        t.csite[s] = CountSite{ (int32_t)nb, (int32_t)eb, fam };
+        fam += (int64_t)slots * (1 + sd.n_nodes + sd.n_edges);
+        for (int e = sd.n_edges - 1; e >= 0; --e) // descending: a duplicated input edge maps to its first occurrence
+            t.csr_input[(size_t)(eb + csr_edge(g, gs.in_from[(size_t)(eb + e)], gs.in_to[(size_t)(eb + e)]))] = e;
+        for (int e = 0; e < sd.n_edges; ++e)
+        {
+            const int a = gs.in_from[(size_t)(eb + e)], b = gs.in_to[(size_t)(eb + e)];
+            const uint64_t lab = gs.in_label[(size_t)(eb + e)];
+            t.lab_edge[(size_t)(eb + csr_edge(g, a, b))] |= lab;
+            t.lab_out[(size_t)(nb + a)] |= lab;
+            t.lab_in[(size_t)(nb + b)] |= lab;
+        }
+    }
+    t.fam_rows = fam;
+}
+
+// Chain the reads of each fragment in input order (readsToFragments keeps one Fragment per fragment_id,
+// Fragment.cpp:165-181); head[i] = 1 for the first read of a fragment.  site may be nullptr (single site).
+inline bool build_fragment_chains(const int32_t* fragment, const int32_t* site, int n, std::vector<int32_t>& next,
+                                  std::vector<uint8_t>& head, std::string& err)
+{
+    next.assign((size_t)n, -1);
+    head.assign((size_t)n, 1);
+    if (!fragment)
+        return true;
+    std::unordered_map<int32_t, int32_t> last;
+    last.reserve((size_t)n);
+    for (int i = 0; i < n; ++i)
+    {
+        if (fragment[i] < 0)
+        {
+            err = "negative fragment id at read " + std::to_string(i);
+            return false;
+        }
+        auto it = last.find(fragment[i]);
+        if (it == last.end())
+        {
+            last.emplace(fragment[i], i);
+            continue;
+        }
+        if (site && site[it->second] != site[i])
+        {
+            err = "fragment " + std::to_string(fragment[i]) + " spans two sites";
+            return false;
+        }
+        next[(size_t)it->second] = i;
+        head[(size_t)i] = 0;
+        it->second = i;
+    }
+    return true;
+}
 
 // per-read scratch sizes in 32-bit words (see pg_core.cuh "per-task scratch layout")
 inline size_t info_words(int max_nodes, int W) { return (size_t)max_nodes * 3 * W; }

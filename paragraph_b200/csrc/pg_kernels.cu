@@ -14,10 +14,12 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/pg_align.h"
 #include "pg_core.cuh"
+#include "pg_count.cuh"
 #include "pg_host.hpp"
 
 using namespace pg;
@@ -384,6 +386,7 @@ template <typename T> struct DevBuf
         p = nullptr;
         cap = 0;
     }
+    ~DevBuf() { release(); }
 };
 template <typename T> struct PinBuf
 {
@@ -412,6 +415,80 @@ template <typename T> struct PinBuf
 };
 
 } // namespace
+
+// ---------------------------------------------------------------------------------------------
+// counting stage kernels (logic in pg_count.cuh).  All three are thread-per-item passes over a few dozen bytes per
+// read: HBM-latency bound, microseconds per 10k reads next to the milliseconds of the fill.
+// ---------------------------------------------------------------------------------------------
+struct CountArgs
+{
+    CountTables t;
+    CountParams prm;
+    const Record* records;
+    const uint32_t* ops;
+    const int32_t* read_off;
+    const int32_t* read_site; // nullptr = site 0
+    const uint8_t* is_rev;    // nullptr = all forward
+    int n_reads;
+    ReadSupport* sup;
+    uint32_t* path;
+    const int32_t* next;
+    const uint8_t* head;
+    Count4 *node_counts, *edge_counts, *fam_counts;
+    unsigned long long* fam_keys;
+    unsigned long long* cursor; // [0] family words written, [1] site + 1 whose family table overflowed
+    uint32_t* fam_out;
+    unsigned long long fam_out_cap;
+    int n_sites;
+};
+
+__global__ void __launch_bounds__(128) pg_support_kernel(CountArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_reads)
+        return;
+    const Record rec = a.records[i];
+    ReadSupport sup;
+    support_read(rec, a.ops, a.read_off[i + 1] - a.read_off[i], a.read_site ? a.read_site[i] : 0,
+                 a.is_rev ? a.is_rev[i] != 0 : false, a.t, a.prm, sup, a.path);
+    a.sup[i] = sup;
+}
+
+__global__ void __launch_bounds__(128) pg_fragment_kernel(CountArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_reads || !a.head[i])
+        return;
+    const int site = a.read_site ? a.read_site[i] : 0;
+    if (!count_fragment(i, site, a.next, a.sup, a.path, a.t, a.prm, a.node_counts, a.edge_counts, a.fam_keys,
+                        a.fam_counts))
+        atomicMax(&a.cursor[1], (unsigned long long)site + 1ull);
+}
+
+// one thread per (site, slot): occupied slots are appended to the compact family list
+__global__ void __launch_bounds__(128) pg_family_compact_kernel(CountArgs a)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)a.n_sites * a.prm.family_slots)
+        return;
+    const unsigned long long key = a.fam_keys[idx];
+    if (!key)
+        return;
+    const int site = (int)(idx / a.prm.family_slots), slot = (int)(idx % a.prm.family_slots);
+    const SiteDev& sd = a.t.sites[site];
+    const int n = 1 + sd.n_nodes + sd.n_edges;
+    const unsigned long long off = atomicAdd(&a.cursor[0], 4ull + 4ull * (unsigned long long)n);
+    if (off + 4ull + 4ull * (unsigned long long)n > a.fam_out_cap)
+        return;
+    uint32_t* o = a.fam_out + off;
+    o[0] = (uint32_t)site;
+    o[1] = (uint32_t)n;
+    o[2] = (uint32_t)key;
+    o[3] = (uint32_t)(key >> 32);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.fam_counts + a.t.csite[site].fam_base + (int64_t)slot * n);
+    for (int x = 0; x < 4 * n; ++x)
+        o[4 + x] = src[x];
+}
 
 struct pg_ctx
 {
@@ -448,6 +525,22 @@ struct pg_ctx
     PinBuf<uint32_t> h_arena;
     PinBuf<unsigned long long> h_cursor;
     unsigned long long arena_cap = 0;
+
+    // counting stage (pg_count.cuh)
+    bool count_dirty = true;
+    int count_slots = 0;
+    uint64_t count_launches = 0;
+    float count_ms = 0;
+    DevBuf<CountSite> d_csite;
+    DevBuf<int32_t> d_csr_input, d_next;
+    DevBuf<uint64_t> d_lab_edge, d_lab_out, d_lab_in;
+    DevBuf<uint8_t> d_head, d_isrev;
+    DevBuf<ReadSupport> d_support;
+    DevBuf<uint32_t> d_path, d_fam_out;
+    DevBuf<Count4> d_node_counts, d_edge_counts, d_fam_counts;
+    DevBuf<unsigned long long> d_fam_keys, d_count_cursor; // cursor[0] = family words, cursor[1] = overflow site + 1
+    int64_t fam_rows = 0;
+    cudaEvent_t count_ev[2] = { nullptr, nullptr };
 };
 
 namespace
@@ -498,6 +591,46 @@ int upload_graphs(pg_ctx* c)
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
     c->graphs_dirty = false;
     return PG_OK;
+}
+
+// host -> device copy of a small pageable vector (synchronous with respect to the host buffer after the sync below)
+template <typename T> cudaError_t put(pg_ctx* c, DevBuf<T>& d, const std::vector<T>& h)
+{
+    cudaError_t e = d.reserve(h.size() ? h.size() : 1);
+    if (e != cudaSuccess || h.empty())
+        return e;
+    return cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream);
+}
+
+// per-site tables of the counting stage (built by pg_host.hpp)
+int upload_count_tables(pg_ctx* c, int slots)
+{
+    if (!c->count_dirty && c->count_slots == slots)
+        return PG_OK;
+    const host::GraphStore& gs = c->graphs;
+    const size_t ns = gs.sites.size();
+    if (gs.edge_base[ns] > 0x7FFFFFFF || gs.node_base[ns] > 0x7FFFFFFF)
+        return fail(c, PG_E_GRAPH, "counting stage: more than 2^31 nodes or edges registered");
+    host::CountHostTables t;
+    host::build_count_tables(gs, slots, t);
+    c->fam_rows = t.fam_rows;
+    PG_CUDA(c, put(c, c->d_csite, t.csite));
+    PG_CUDA(c, put(c, c->d_csr_input, t.csr_input));
+    PG_CUDA(c, put(c, c->d_lab_edge, t.lab_edge));
+    PG_CUDA(c, put(c, c->d_lab_out, t.lab_out));
+    PG_CUDA(c, put(c, c->d_lab_in, t.lab_in));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->count_dirty = false;
+    c->count_slots = slots;
+    return PG_OK;
+}
+
+// device -> caller buffer (pinned: direct; pageable: synchronous copy)
+cudaError_t get(pg_ctx* c, void* dst, const void* src, size_t bytes)
+{
+    if (!bytes)
+        return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
 }
 
 template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
@@ -700,6 +833,9 @@ void pg_destroy(pg_ctx* c)
     c->h_cursor.release();
     for (auto& ev : c->evpool)
         cudaEventDestroy(ev);
+    for (auto& ev : c->count_ev)
+        if (ev)
+            cudaEventDestroy(ev);
     if (c->own_stream)
         cudaStreamDestroy(c->own_stream);
     delete c;
@@ -733,6 +869,7 @@ int pg_add_graph(pg_ctx* c, int32_t n_nodes, const char* blob, const int32_t* of
     if (id < 0)
         return fail(c, PG_E_GRAPH, err);
     c->graphs_dirty = true;
+    c->count_dirty = true;
     if (site_id)
         *site_id = id;
     return PG_OK;
@@ -744,6 +881,7 @@ int pg_clear_graphs(pg_ctx* c)
         return PG_E_ARG;
     c->graphs.clear();
     c->graphs_dirty = true;
+    c->count_dirty = true;
     return PG_OK;
 }
 
@@ -954,6 +1092,242 @@ void pg_host_free(void* p)
 {
     if (p)
         cudaFreeHost(p);
+}
+
+int pg_batch_import(pg_ctx* c, int32_t n_reads, const int32_t* read_len, const int32_t* site, const pg_record* records,
+                    const uint32_t* ops, uint64_t n_ops)
+{
+    if (!c || n_reads < 0 || (n_reads > 0 && (!read_len || !records)) || (n_ops > 0 && !ops))
+        return fail(c, PG_E_ARG, "pg_batch_import: bad arguments");
+    c->uploaded = false;
+    c->ran = false;
+    c->n_reads = 0;
+    if (n_reads == 0)
+    {
+        c->uploaded = c->ran = true;
+        c->n_chunks_timed = 0;
+        return PG_OK;
+    }
+    const int nsites = (int)c->graphs.sites.size();
+    if (nsites == 0)
+        return fail(c, PG_E_STATE, "no graph registered (pg_add_graph)");
+    PG_CUDA(c, cudaSetDevice(c->device));
+    if (c->staging_busy)
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->staging_busy = false;
+    PG_CUDA(c, c->h_off.reserve((size_t)n_reads + 1));
+    int maxl = 0;
+    c->h_off.p[0] = 0;
+    for (int i = 0; i < n_reads; ++i)
+    {
+        if (read_len[i] <= 0 || (int64_t)c->h_off.p[i] + read_len[i] > 0x7FFFFFFF)
+            return fail(c, PG_E_READ_LEN, "pg_batch_import: bad length of read " + std::to_string(i));
+        if (site && (site[i] < 0 || site[i] >= nsites))
+            return fail(c, PG_E_ARG, "read " + std::to_string(i) + " names unknown site " + std::to_string(site[i]));
+        if ((uint64_t)records[i].cigar_off + records[i].cigar_len > n_ops)
+            return fail(c, PG_E_ARG, "pg_batch_import: record " + std::to_string(i) + " points outside cigar_ops");
+        c->h_off.p[i + 1] = c->h_off.p[i] + read_len[i];
+        maxl = std::max(maxl, (int)read_len[i]);
+    }
+    PG_CUDA(c, c->d_off.reserve((size_t)n_reads + 1));
+    PG_CUDA(c, c->d_records.reserve((size_t)n_reads));
+    PG_CUDA(c, c->d_arena.reserve((size_t)n_ops + 1));
+    PG_CUDA(c, c->d_cursor.reserve(1));
+    PG_CUDA(c, c->h_cursor.reserve(1));
+    PG_CUDA(c, cudaMemcpyAsync(c->d_off.p, c->h_off.p, ((size_t)n_reads + 1) * sizeof(int32_t), cudaMemcpyHostToDevice,
+                               c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(c->d_records.p, records, (size_t)n_reads * sizeof(Record), cudaMemcpyHostToDevice, c->stream));
+    if (n_ops)
+        PG_CUDA(c, cudaMemcpyAsync(c->d_arena.p, ops, (size_t)n_ops * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    *c->h_cursor.p = n_ops;
+    PG_CUDA(c, cudaMemcpyAsync(c->d_cursor.p, c->h_cursor.p, sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    c->have_sites = site != nullptr;
+    if (site)
+    {
+        PG_CUDA(c, c->h_site.reserve((size_t)n_reads));
+        PG_CUDA(c, c->d_site.reserve((size_t)n_reads));
+        memcpy(c->h_site.p, site, (size_t)n_reads * sizeof(int32_t));
+        PG_CUDA(c, cudaMemcpyAsync(c->d_site.p, c->h_site.p, (size_t)n_reads * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                   c->stream));
+    }
+    PG_CUDA(c, cudaStreamSynchronize(c->stream)); // caller buffers may be pageable and reused right away
+    c->arena_cap = n_ops;
+    c->n_reads = n_reads;
+    c->max_len = maxl;
+    c->uploaded = true;
+    c->ran = true;
+    c->n_chunks_timed = 0;
+    return PG_OK;
+}
+
+int pg_set_edge_labels(pg_ctx* c, int32_t site, const uint64_t* masks)
+{
+    if (!c)
+        return PG_E_ARG;
+    if (site < 0 || (size_t)site >= c->graphs.sites.size())
+        return fail(c, PG_E_ARG, "pg_set_edge_labels: unknown site " + std::to_string(site));
+    const int64_t eb = c->graphs.edge_base[(size_t)site];
+    const int n = c->graphs.sites[(size_t)site].n_edges;
+    for (int e = 0; e < n; ++e)
+        c->graphs.in_label[(size_t)(eb + e)] = masks ? masks[e] : 0ull;
+    c->count_dirty = true;
+    return PG_OK;
+}
+
+int pg_batch_count(pg_ctx* c, const int32_t* fragment, const uint8_t* is_reverse_strand, const pg_count_params* params,
+                   pg_read_support* support, uint32_t* path_words, uint64_t path_cap, uint64_t* path_used,
+                   pg_count4* node_counts, uint64_t node_cap, pg_count4* edge_counts, uint64_t edge_cap,
+                   uint32_t* family_words, uint64_t family_cap, uint64_t* family_used)
+{
+    static_assert(sizeof(pg_read_support) == sizeof(ReadSupport) && sizeof(pg_count4) == sizeof(Count4), "ABI structs");
+    if (!c || !params)
+        return fail(c, PG_E_ARG, "pg_batch_count: bad arguments");
+    if (!c->ran)
+        return fail(c, PG_E_STATE, "pg_batch_count before pg_batch_run");
+    const host::GraphStore& gs = c->graphs;
+    const size_t ns = gs.sites.size();
+    if (ns == 0)
+        return fail(c, PG_E_STATE, "no graph registered (pg_add_graph)");
+    const uint64_t total_nodes = (uint64_t)gs.node_base[ns], total_edges = (uint64_t)gs.edge_base[ns];
+    if ((node_counts && node_cap < total_nodes) || (edge_counts && edge_cap < total_edges))
+        return fail(c, PG_E_CAPACITY, "pg_batch_count: need " + std::to_string(total_nodes) + " node rows and "
+                        + std::to_string(total_edges) + " edge rows");
+    CountParams prm;
+    prm.remove_nonuniq = params->remove_nonuniq;
+    prm.use_support_filters = params->use_support_filters;
+    prm.bad_align_frac = params->bad_align_frac;
+    prm.family_slots = params->family_slots > 0 ? params->family_slots : 16;
+    if (path_used)
+        *path_used = 0;
+    if (family_used)
+        *family_used = 0;
+    if (node_counts)
+        memset(node_counts, 0, (size_t)total_nodes * sizeof(pg_count4));
+    if (edge_counts)
+        memset(edge_counts, 0, (size_t)total_edges * sizeof(pg_count4));
+    if (c->n_reads == 0)
+        return PG_OK;
+    PG_CUDA(c, cudaSetDevice(c->device));
+    const int n = c->n_reads;
+
+    // fragments: chain the reads of a fragment in input order; the first one accumulates
+    std::vector<int32_t> next;
+    std::vector<uint8_t> head;
+    {
+        std::string err;
+        if (!host::build_fragment_chains(fragment, c->have_sites ? c->h_site.p : nullptr, n, next, head, err))
+            return fail(c, PG_E_ARG, "pg_batch_count: " + err);
+    }
+    int rc = upload_graphs(c);
+    if (rc == PG_OK)
+        rc = upload_count_tables(c, prm.family_slots);
+    if (rc != PG_OK)
+        return rc;
+
+    // the op count of the batch bounds the path words
+    PG_CUDA(c, c->h_cursor.reserve(1));
+    PG_CUDA(c, cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    const unsigned long long n_ops = *c->h_cursor.p;
+    if (n_ops > c->arena_cap)
+        return fail(c, PG_E_CAPACITY, "device cigar arena overflowed in the last run");
+    if (path_words && path_cap < n_ops)
+        return fail(c, PG_E_CAPACITY, "pg_batch_count: path_words needs " + std::to_string(n_ops) + " words");
+
+    PG_CUDA(c, put(c, c->d_next, next));
+    PG_CUDA(c, put(c, c->d_head, head));
+    if (is_reverse_strand)
+    {
+        PG_CUDA(c, c->d_isrev.reserve((size_t)n));
+        PG_CUDA(c, cudaMemcpyAsync(c->d_isrev.p, is_reverse_strand, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    }
+    PG_CUDA(c, c->d_support.reserve((size_t)n));
+    PG_CUDA(c, c->d_path.reserve((size_t)n_ops + 1));
+    PG_CUDA(c, c->d_node_counts.reserve((size_t)total_nodes + 1));
+    PG_CUDA(c, c->d_edge_counts.reserve((size_t)total_edges + 1));
+    PG_CUDA(c, c->d_fam_counts.reserve((size_t)c->fam_rows + 1));
+    PG_CUDA(c, c->d_fam_keys.reserve(ns * (size_t)prm.family_slots));
+    PG_CUDA(c, c->d_count_cursor.reserve(2));
+    const unsigned long long fam_out_cap = 4ull * (unsigned long long)c->fam_rows + 4ull * ns * (unsigned long long)prm.family_slots;
+    PG_CUDA(c, c->d_fam_out.reserve((size_t)fam_out_cap + 1));
+    if (!c->count_ev[0])
+    {
+        PG_CUDA(c, cudaEventCreate(&c->count_ev[0]));
+        PG_CUDA(c, cudaEventCreate(&c->count_ev[1]));
+    }
+    PG_CUDA(c, cudaEventRecord(c->count_ev[0], c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_node_counts.p, 0, ((size_t)total_nodes + 1) * sizeof(Count4), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_edge_counts.p, 0, ((size_t)total_edges + 1) * sizeof(Count4), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_fam_counts.p, 0, ((size_t)c->fam_rows + 1) * sizeof(Count4), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_fam_keys.p, 0, ns * (size_t)prm.family_slots * sizeof(unsigned long long), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_count_cursor.p, 0, 2 * sizeof(unsigned long long), c->stream));
+
+    CountArgs a;
+    a.t.sites = c->d_sites.p;
+    a.t.gints = c->d_gints.p;
+    a.t.csite = c->d_csite.p;
+    a.t.csr_input = c->d_csr_input.p;
+    a.t.lab_edge = c->d_lab_edge.p;
+    a.t.lab_out = c->d_lab_out.p;
+    a.t.lab_in = c->d_lab_in.p;
+    a.prm = prm;
+    a.records = c->d_records.p;
+    a.ops = c->d_arena.p;
+    a.read_off = c->d_off.p;
+    a.read_site = c->have_sites ? c->d_site.p : nullptr;
+    a.is_rev = is_reverse_strand ? c->d_isrev.p : nullptr;
+    a.n_reads = n;
+    a.sup = c->d_support.p;
+    a.path = c->d_path.p;
+    a.next = c->d_next.p;
+    a.head = c->d_head.p;
+    a.node_counts = c->d_node_counts.p;
+    a.edge_counts = c->d_edge_counts.p;
+    a.fam_counts = c->d_fam_counts.p;
+    a.fam_keys = c->d_fam_keys.p;
+    a.cursor = c->d_count_cursor.p;
+    a.fam_out = c->d_fam_out.p;
+    a.fam_out_cap = fam_out_cap;
+    a.n_sites = (int)ns;
+    const int grid = (n + 127) / 128;
+    pg_support_kernel<<<grid, 128, 0, c->stream>>>(a);
+    PG_CUDA(c, cudaGetLastError());
+    pg_fragment_kernel<<<grid, 128, 0, c->stream>>>(a);
+    PG_CUDA(c, cudaGetLastError());
+    const long long slots_total = (long long)ns * prm.family_slots;
+    pg_family_compact_kernel<<<(unsigned)((slots_total + 127) / 128), 128, 0, c->stream>>>(a);
+    PG_CUDA(c, cudaGetLastError());
+    c->launches += 3;
+    c->count_launches += 3;
+    PG_CUDA(c, cudaEventRecord(c->count_ev[1], c->stream));
+
+    unsigned long long cur[2] = { 0, 0 };
+    PG_CUDA(c, cudaMemcpyAsync(cur, c->d_count_cursor.p, sizeof cur, cudaMemcpyDeviceToHost, c->stream));
+    if (support)
+        PG_CUDA(c, get(c, support, c->d_support.p, (size_t)n * sizeof(ReadSupport)));
+    if (path_words)
+        PG_CUDA(c, get(c, path_words, c->d_path.p, (size_t)n_ops * sizeof(uint32_t)));
+    if (node_counts)
+        PG_CUDA(c, get(c, node_counts, c->d_node_counts.p, (size_t)total_nodes * sizeof(Count4)));
+    if (edge_counts)
+        PG_CUDA(c, get(c, edge_counts, c->d_edge_counts.p, (size_t)total_edges * sizeof(Count4)));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->count_ms, c->count_ev[0], c->count_ev[1]);
+    if (path_used)
+        *path_used = n_ops;
+    if (cur[1])
+        return fail(c, PG_E_CAPACITY, "pg_batch_count: site " + std::to_string(cur[1] - 1) + " has more than "
+                        + std::to_string(prm.family_slots) + " distinct path-family sets (raise family_slots)");
+    if (family_used)
+        *family_used = cur[0];
+    if (cur[0])
+    {
+        if (!family_words || family_cap < cur[0])
+            return fail(c, PG_E_CAPACITY, "pg_batch_count: family_words needs " + std::to_string(cur[0]) + " words");
+        PG_CUDA(c, get(c, family_words, c->d_fam_out.p, (size_t)cur[0] * sizeof(uint32_t)));
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return PG_OK;
 }
 
 int pg_stats(const pg_ctx* c, uint64_t* launches, float* fill_ms, float* trace_ms)

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../paragraph_b200/csrc/pg_core.cuh"
+#include "../../paragraph_b200/csrc/pg_count.cuh"
 #include "../../paragraph_b200/csrc/pg_host.hpp"
 
 using namespace pg;
@@ -222,5 +223,97 @@ int pgemu_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off,
         }
     }
     return worst;
+}
+// Align + count ONE site on the host with the device code of pg_core.cuh / pg_count.cuh.
+// support: n_reads x 16 bytes (pg_read_support); path_words / ops_out: capacity `cap` words each (the op arena is
+// returned too so that a test can look at the CIGARs); node_counts[n_nodes], edge_counts[n_edges] (4 x u32 each);
+// family_words: entries {site, n, mask_lo, mask_hi, n x 4 counts}.  Returns 0, -5 on a capacity problem.
+int pgemu_count_site(int n_nodes, const char* seq_blob, const int32_t* seq_off, int n_edges, const int32_t* efrom,
+                     const int32_t* eto, const uint64_t* edge_labels, int n_reads, const char* bases_blob,
+                     const int32_t* read_off, const uint8_t* is_rev, const int32_t* fragment, int remove_nonuniq,
+                     double bad_align_frac, int use_support_filters, int family_slots, void* support,
+                     uint32_t* path_words, uint32_t* ops_out, int cap, int32_t* used, uint32_t* node_counts,
+                     uint32_t* edge_counts, uint32_t* family_words, int family_cap, int32_t* family_used)
+{
+    host::GraphStore gs;
+    std::string err;
+    if (gs.add(n_nodes, seq_blob, seq_off, n_edges, efrom, eto, err) < 0)
+        return -4;
+    for (int e = 0; e < n_edges; ++e)
+        gs.in_label[(size_t)e] = edge_labels ? edge_labels[e] : 0ull;
+    const SiteDev& sd0 = gs.sites[0];
+    const uint8_t* gb = gs.bytes.data();
+    const int32_t* gi = gs.ints.data();
+    std::vector<Record> recs((size_t)n_reads);
+    std::vector<uint32_t> arena;
+    for (int i = 0; i < n_reads; ++i)
+    {
+        const uint8_t* b = (const uint8_t*)bases_blob + read_off[i];
+        const int L = read_off[i + 1] - read_off[i];
+        std::vector<uint32_t> ops;
+        int nt = 0;
+        const int rc = L <= 160 ? emu_align_one<5, 32>(sd0, gb, gi, b, L, 0xFFFFFFFFu, recs[(size_t)i], ops, &nt)
+                                : emu_align_one<8, 32>(sd0, gb, gi, b, L, 0xFFFFFFFFu, recs[(size_t)i], ops, &nt);
+        if (rc)
+            return rc;
+        recs[(size_t)i].cigar_off = (uint32_t)arena.size();
+        arena.insert(arena.end(), ops.begin(), ops.begin() + recs[(size_t)i].cigar_len);
+    }
+    if ((int)arena.size() > cap)
+        return -5;
+    *used = (int32_t)arena.size();
+    memcpy(ops_out, arena.data(), arena.size() * sizeof(uint32_t));
+
+    CountParams prm;
+    prm.remove_nonuniq = remove_nonuniq;
+    prm.use_support_filters = use_support_filters;
+    prm.bad_align_frac = bad_align_frac;
+    prm.family_slots = family_slots > 0 ? family_slots : 16;
+    host::CountHostTables ht;
+    host::build_count_tables(gs, prm.family_slots, ht);
+    CountTables t;
+    t.sites = gs.sites.data();
+    t.gints = gi;
+    t.csite = ht.csite.data();
+    t.csr_input = ht.csr_input.data();
+    t.lab_edge = ht.lab_edge.data();
+    t.lab_out = ht.lab_out.data();
+    t.lab_in = ht.lab_in.data();
+    ReadSupport* sup = static_cast<ReadSupport*>(support);
+    for (int i = 0; i < n_reads; ++i)
+        support_read(recs[(size_t)i], arena.data(), read_off[i + 1] - read_off[i], 0, is_rev && is_rev[i], t, prm, sup[i],
+                     path_words);
+    std::vector<int32_t> next;
+    std::vector<uint8_t> head;
+    if (!host::build_fragment_chains(fragment, nullptr, n_reads, next, head, err))
+        return -1;
+    std::vector<Count4> nc((size_t)n_nodes), ec((size_t)n_edges + 1), fam((size_t)ht.fam_rows);
+    std::vector<unsigned long long> keys((size_t)prm.family_slots, 0ull);
+    memset(nc.data(), 0, nc.size() * sizeof(Count4));
+    memset(ec.data(), 0, ec.size() * sizeof(Count4));
+    memset(fam.data(), 0, fam.size() * sizeof(Count4));
+    for (int i = 0; i < n_reads; ++i)
+        if (head[(size_t)i]
+            && !count_fragment(i, 0, next.data(), sup, path_words, t, prm, nc.data(), ec.data(), keys.data(), fam.data()))
+            return -5;
+    memcpy(node_counts, nc.data(), (size_t)n_nodes * sizeof(Count4));
+    memcpy(edge_counts, ec.data(), (size_t)n_edges * sizeof(Count4));
+    const int n = 1 + n_nodes + n_edges;
+    int w = 0;
+    for (int slot = 0; slot < prm.family_slots; ++slot)
+    {
+        if (!keys[(size_t)slot])
+            continue;
+        if (w + 4 + 4 * n > family_cap)
+            return -5;
+        family_words[w] = 0;
+        family_words[w + 1] = (uint32_t)n;
+        family_words[w + 2] = (uint32_t)keys[(size_t)slot];
+        family_words[w + 3] = (uint32_t)(keys[(size_t)slot] >> 32);
+        memcpy(family_words + w + 4, fam.data() + (size_t)slot * n, (size_t)n * sizeof(Count4));
+        w += 4 + 4 * n;
+    }
+    *family_used = w;
+    return 0;
 }
 }

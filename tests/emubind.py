@@ -10,7 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "emu", "libpgemu.so")
 SRC = [os.path.join(HERE, "emu", "pg_emu.cpp"), os.path.join(ROOT, "paragraph_b200", "csrc", "pg_core.cuh"),
-       os.path.join(ROOT, "paragraph_b200", "csrc", "pg_host.hpp")]
+       os.path.join(ROOT, "paragraph_b200", "csrc", "pg_host.hpp"),
+       os.path.join(ROOT, "paragraph_b200", "csrc", "pg_count.cuh")]
 CIGAR_STRIDE = 1024
 _lib = None
 
@@ -73,3 +74,56 @@ def emu_align_batch(node_seqs, edges, reads, is_rev=None, flags=0xFFFFFFFF):
                         graph_reverse=bool(out[i, 4]), bases=raw[roff[i]:roff[i + 1]].decode("latin-1"), cigar=c,
                         status=int(out[i, 5]) & 0xFF, clipped=int(out[i, 5]) >> 8))
     return res, int(tiles[0])
+
+
+def emu_count_site(node_seqs, edges, edge_labels, reads, is_rev=None, fragment=None, remove_nonuniq=True,
+                   bad_align_frac=0.8, use_filters=True, family_slots=16):
+    """Emulated alignment + counting stage (pg_count.cuh on the host) of one site.  Returns a dict shaped like
+    oracle.refbind.oracle_count_site's plus the records' CIGAR strings ("cigars")."""
+    from oracle import refbind as R
+    l = lib()
+    i32p, u8p, u32p, u64p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    l.pgemu_count_site.restype = C.c_int
+    l.pgemu_count_site.argtypes = [C.c_int, C.c_char_p, i32p, C.c_int, i32p, i32p, u64p, C.c_int, C.c_char_p, i32p, u8p,
+                                   i32p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p, u32p, u32p, C.c_int, i32p,
+                                   u32p, u32p, u32p, C.c_int, i32p]
+    blob = "".join(node_seqs).encode("latin-1")
+    off = np.zeros(len(node_seqs) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(s) for s in node_seqs])
+    ef = np.array([e[0] for e in edges], dtype=np.int32)
+    et = np.array([e[1] for e in edges], dtype=np.int32)
+    lab = np.ascontiguousarray(edge_labels if edge_labels is not None else np.zeros(len(edges)), dtype=np.uint64)
+    rblob = "".join(reads).encode("latin-1")
+    roff = np.zeros(len(reads) + 1, dtype=np.int32)
+    roff[1:] = np.cumsum([len(s) for s in reads])
+    n, nn, ne = len(reads), len(node_seqs), len(edges)
+    rv = np.ascontiguousarray(is_rev if is_rev is not None else np.zeros(n), dtype=np.uint8)
+    fr = np.ascontiguousarray(fragment if fragment is not None else np.arange(n), dtype=np.int32)
+    sup = np.zeros(n, dtype=R.SUPPORT_DTYPE)
+    cap = int(roff[-1]) + (2 * nn + 8) * n + 16
+    pw = np.zeros(cap, dtype=np.uint32)
+    ops = np.zeros(cap, dtype=np.uint32)
+    nc = np.zeros((max(nn, 1), 4), dtype=np.uint32)
+    ec = np.zeros((max(ne, 1), 4), dtype=np.uint32)
+    fcap = (4 + 4 * (1 + nn + ne)) * family_slots
+    fw = np.zeros(fcap, dtype=np.uint32)
+    used = np.zeros(2, dtype=np.int32)
+    rc = l.pgemu_count_site(nn, blob, _p(off, C.c_int32), ne, _p(ef, C.c_int32), _p(et, C.c_int32), _p(lab, C.c_uint64),
+                            n, rblob, _p(roff, C.c_int32), _p(rv, C.c_uint8), _p(fr, C.c_int32), int(remove_nonuniq),
+                            float(bad_align_frac), int(use_filters), family_slots, sup.ctypes.data, _p(pw, C.c_uint32),
+                            _p(ops, C.c_uint32), cap, _p(used[0:], C.c_int32), _p(nc, C.c_uint32), _p(ec, C.c_uint32),
+                            _p(fw, C.c_uint32), fcap, _p(used[1:], C.c_int32))
+    if rc != 0:
+        raise RuntimeError("pgemu_count_site rc=%d" % rc)
+    return dict(support=sup, path_words=pw[:used[0]], ops=ops[:used[0]], node_counts=nc[:nn].astype(np.int64),
+                edge_counts=ec[:ne].astype(np.int64), families=unpack_family_entries(fw[:used[1]]))
+
+
+def unpack_family_entries(words):
+    """C-ABI family words {site, n, mask_lo, mask_hi, n x 4} -> {mask: [n, 4]} (single-site use) """
+    out, w = {}, 0
+    while w < len(words):
+        n = int(words[w + 1])
+        out[int(words[w + 2]) | (int(words[w + 3]) << 32)] = np.array(words[w + 4:w + 4 + 4 * n], dtype=np.int64).reshape(n, 4)
+        w += 4 + 4 * n
+    return out

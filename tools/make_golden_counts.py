@@ -69,17 +69,17 @@ def unit():
             "edges": [["LF", "P1", ["P"]], ["LF", "Q1", ["Q"]], ["LF", "RF", ["D"]], ["P1", "RF", ["P"]],
                       ["Q1", "RF", ["Q"]]],
             "reads": [
-                {"pos": 3, "cigar": "0[8M]1[4M1X3M]3[8M]", "len": 24, "rev": False,
+                {"bases": "AAAAAAAATTTTCTTTAAAAAAAA", "pos": 3, "cigar": "0[8M]1[4M1X3M]3[8M]", "len": 24, "rev": False,
                  "nodes": ["LF", "P1", "RF"], "edges": ["LF_P1", "P1_RF"], "seqs": ["P"]},
-                {"pos": 4, "cigar": "0[7M]1[4M1X3M]3[6M]", "len": 21, "rev": True,
+                {"bases": "TTTTTTAAAGAAAATTTTTTT", "pos": 4, "cigar": "0[7M]1[4M1X3M]3[6M]", "len": 21, "rev": True,
                  "nodes": ["LF", "P1", "RF"], "edges": ["LF_P1", "P1_RF"], "seqs": ["P"]},
-                {"pos": 6, "cigar": "0[5M]2[1M1X6M]3[6M]", "len": 19, "rev": False,
+                {"bases": "AAAAAGCGGGGGGAAAAAA", "pos": 6, "cigar": "0[5M]2[1M1X6M]3[6M]", "len": 19, "rev": False,
                  "nodes": ["LF", "Q1", "RF"], "edges": ["LF_Q1", "Q1_RF"], "seqs": ["Q"]},
-                {"pos": 7, "cigar": "0[4M]2[1M1X6M]3[6M]", "len": 18, "rev": False,
+                {"bases": "AAAAGCGGGGGGAAAAAA", "pos": 7, "cigar": "0[4M]2[1M1X6M]3[6M]", "len": 18, "rev": False,
                  "nodes": ["LF", "Q1", "RF"], "edges": ["LF_Q1", "Q1_RF"], "seqs": ["Q"]},
-                {"pos": 6, "cigar": "0[5M]2[1M1X6M]3[6M]", "len": 19, "rev": True,
+                {"bases": "TTTTTTCCCCCCGCTTTTT", "pos": 6, "cigar": "0[5M]2[1M1X6M]3[6M]", "len": 19, "rev": True,
                  "nodes": ["LF", "Q1", "RF"], "edges": ["LF_Q1", "Q1_RF"], "seqs": ["Q"]},
-                {"pos": 0, "cigar": "0[11M]3[8M]", "len": 19, "rev": False,
+                {"bases": "AAAAAAAAAAAAAAAAAAA", "pos": 0, "cigar": "0[11M]3[8M]", "len": 19, "rev": False,
                  "nodes": ["LF", "RF"], "edges": ["LF_RF"], "seqs": ["D"]},
             ],
         },

@@ -5,7 +5,7 @@ import numpy as np
 from paragraph_b200 import capi, synth
 ctx = capi.Context(0)
 n = 0
-for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "*.json")))[:6]:
+for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "site_*.json")))[:6]:
     c = json.load(open(p))
     ctx.clear_graphs(); ctx.add_graph(c["nodes"], [tuple(e) for e in c["edges"]])
     got = ctx.align(c["reads"][:40], is_rev=(c["is_rev"] or [0] * len(c["reads"]))[:40], flags=c["flags"])
