@@ -161,7 +161,8 @@ typedef struct pg_count_params
     int32_t use_support_filters; /* 1: the node/edge filters alignAndDisambiguate passes to disambiguateReads;
                                     0: null filters, as the reference's unit tests call disambiguateReads */
     double bad_align_frac;       /* Parameters::bad_align_frac (default 0.8) */
-    int32_t family_slots;        /* distinct label sets per site the device table can hold; 0 = 16 */
+    int32_t family_slots;        /* most distinct label sets per site the device table holds (a site with L labels
+                                    gets min(family_slots, 2^L) slots); 0 = 256 */
     int32_t reserved;
 } pg_count_params;
 

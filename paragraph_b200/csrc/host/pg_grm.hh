@@ -20,10 +20,12 @@
 #include <cstdint>
 #include <functional>
 #include <list>
+#include <map>
 #include <memory>
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../../include/pg_align.h"
@@ -50,10 +52,23 @@ public:
     }
     std::set<uint32_t> const& predecessors(uint32_t id) const { return pred_.at(id); }
     std::set<uint32_t> const& successors(uint32_t id) const { return succ_.at(id); }
+    bool hasEdge(uint32_t from, uint32_t to) const { return succ_.at(from).count(to) != 0; }
+    void addLabelToEdge(uint32_t from, uint32_t to, std::string const& label) // graphtools Graph.cpp:151-158
+    {
+        if (!hasEdge(from, to))
+            throw std::logic_error("There is no edge between " + std::to_string(from) + " and " + std::to_string(to));
+        labels_[std::make_pair(from, to)].insert(label);
+    }
+    std::set<std::string> edgeLabels(uint32_t from, uint32_t to) const
+    {
+        auto it = labels_.find(std::make_pair(from, to));
+        return it == labels_.end() ? std::set<std::string>() : it->second;
+    }
 
 private:
     std::vector<std::string> seq_, name_;
     std::vector<std::set<uint32_t>> pred_, succ_;
+    std::map<std::pair<uint32_t, uint32_t>, std::set<std::string>> labels_;
 };
 
 struct Path
@@ -93,8 +108,19 @@ public:
     void set_is_graph_reverse_strand(bool v) { is_graph_reverse_strand_ = v; }
     MappingStatus graph_mapping_status() const { return graph_mapping_status_; }
     void set_graph_mapping_status(MappingStatus s) { graph_mapping_status_ = s; }
+    // what disambiguateReads fills in (Read.hh:115-131)
+    std::vector<std::string> const& graph_nodes_supported() const { return nodes_supported_; }
+    void add_graph_nodes_supported(std::string const& v) { nodes_supported_.push_back(v); }
+    void clear_graph_nodes_supported() { nodes_supported_.clear(); }
+    std::vector<std::string> const& graph_edges_supported() const { return edges_supported_; }
+    void add_graph_edges_supported(std::string const& v) { edges_supported_.push_back(v); }
+    void clear_graph_edges_supported() { edges_supported_.clear(); }
+    std::vector<std::string> const& graph_sequences_supported() const { return sequences_supported_; }
+    void add_graph_sequences_supported(std::string const& v) { sequences_supported_.push_back(v); }
+    void clear_graph_sequences_supported() { sequences_supported_.clear(); }
 
 private:
+    std::vector<std::string> nodes_supported_, edges_supported_, sequences_supported_;
     std::string fragment_id_, bases_, quals_, graph_cigar_;
     bool is_reverse_strand_ = false;
     int32_t graph_pos_ = 0, graph_mapq_ = 0, graph_alignment_score_ = 0;
@@ -122,6 +148,28 @@ struct DefaultReadFilter
             return "bad_align";
         return "";
     }
+};
+
+// Result of the counting stage for one site: the three tables paragraph::countReads writes
+// (src/c++/lib/paragraph/ReadCounting.cpp:215-233) with the same keys -- node name, "<from>_<to>", and for
+// read_counts_by_sequence the sorted label names joined by "," holding "total" plus node and edge rows.
+struct Count4
+{
+    uint64_t fragments = 0, reads = 0, fwd = 0, rev = 0; // JSON "<key>", "<key>:READS", "<key>:FWD", "<key>:REV"
+    bool operator==(Count4 const& o) const { return fragments == o.fragments && reads == o.reads && fwd == o.fwd && rev == o.rev; }
+};
+struct SiteCounts
+{
+    std::map<std::string, Count4> read_counts_by_node, read_counts_by_edge;
+    std::map<std::string, std::map<std::string, Count4>> read_counts_by_sequence;
+    size_t invalid_alignments = 0; // reads whose CIGAR the reference's decodeGraphAlignment would reject (it throws there)
+};
+struct CountOptions // paragraph::Parameters defaults (include/paragraph/Parameters.hh:47-141)
+{
+    bool remove_nonuniq_reads = true;
+    double bad_align_frac = 0.8;
+    bool use_support_filters = true; // false = disambiguateReads(graph, reads) with null filters (the unit tests)
+    int family_slots = 0;
 };
 } // namespace paragraph
 
@@ -298,7 +346,176 @@ public:
         }
         int32_t sid = -1;
         engine_->check(pg_add_graph(engine_->get(), n, blob.data(), off.data(), (int32_t)ef.size(), ef.data(), et.data(), &sid));
-        sites_.push_back({ sid, reads });
+        Site site{ sid, reads, {}, {}, {} };
+        // names and path-family labels for the counting stage (Graph::edgeLabels; at most 64 labels per site)
+        std::vector<uint64_t> masks(ef.size(), 0);
+        std::map<std::string, int> label_id;
+        for (int32_t i = 0; i < n; ++i)
+            site.node_names.push_back(g->nodeName((uint32_t)i));
+        for (size_t e = 0; e < ef.size(); ++e)
+        {
+            site.edges.emplace_back(ef[e], et[e]);
+            for (auto const& label : g->edgeLabels((uint32_t)ef[e], (uint32_t)et[e]))
+            {
+                auto it = label_id.find(label);
+                if (it == label_id.end())
+                {
+                    if (site.labels.size() == 64)
+                        throw std::runtime_error("paragraph_b200: more than 64 sequence labels on one graph");
+                    it = label_id.emplace(label, (int)site.labels.size()).first;
+                    site.labels.push_back(label);
+                }
+                masks[e] |= 1ull << it->second;
+            }
+        }
+        engine_->check(pg_set_edge_labels(engine_->get(), sid, masks.data()));
+        sites_.push_back(std::move(site));
+    }
+
+    // alignAndDisambiguate's core for every registered site in one go (Disambiguation.cpp:152-299 without the JSON
+    // plumbing): align, apply the default filter chain, disambiguate and count -- filters, supports and counts are
+    // computed on the device from the op arena (pg_batch_count).  Each site's read vector keeps its MAPPED reads, with
+    // graph_{nodes,edges,sequences}_supported filled in like disambiguateReads does; returns one SiteCounts per site
+    // in addSite order.
+    std::vector<paragraph::SiteCounts> alignAndCount(paragraph::CountOptions const& opt = paragraph::CountOptions())
+    {
+        std::string blob;
+        std::vector<int32_t> off{ 0 }, site, fragment;
+        std::vector<uint8_t> is_rev;
+        std::vector<ReadPtrT*> which;
+        int32_t next_fragment = 0;
+        size_t total_nodes = 0, total_edges = 0;
+        for (auto& s : sites_)
+        {
+            std::unordered_map<std::string, int32_t> frag_id; // readsToFragments groups by fragment_id (Fragment.cpp:165-181)
+            for (auto& r : *s.reads)
+            {
+                if (r->bases().empty())
+                    continue;
+                blob += r->bases();
+                off.push_back((int32_t)blob.size());
+                site.push_back(s.id);
+                is_rev.push_back(r->is_reverse_strand() ? 1 : 0);
+                auto it = frag_id.find(r->fragment_id());
+                if (it == frag_id.end())
+                    it = frag_id.emplace(r->fragment_id(), next_fragment++).first;
+                fragment.push_back(it->second);
+                which.push_back(&r);
+            }
+            total_nodes += s.node_names.size();
+            total_edges += s.edges.size();
+        }
+        std::vector<paragraph::SiteCounts> out(sites_.size());
+        std::vector<pg_read_support> sup(which.size());
+        std::vector<pg_count4> nc(total_nodes + 1), ec(total_edges + 1);
+        std::vector<uint32_t> path, fam(1 << 16);
+        uint64_t fam_used = 0;
+        if (!which.empty())
+        {
+            std::vector<pg_record> rec(which.size());
+            std::vector<uint32_t> ops(blob.size() + 16 * which.size() + 64);
+            uint64_t used = 0, path_used = 0;
+            engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), blob.data(), off.data(), site.data(), flags_,
+                                          rec.data(), ops.data(), ops.size(), &used));
+            path.resize(used + 1);
+            pg_count_params prm{ opt.remove_nonuniq_reads ? 1 : 0, opt.use_support_filters ? 1 : 0, opt.bad_align_frac,
+                                 opt.family_slots, 0 };
+            for (int attempt = 0;; ++attempt)
+            {
+                const int rc = pg_batch_count(engine_->get(), fragment.data(), is_rev.data(), &prm, sup.data(), path.data(),
+                                              path.size(), &path_used, nc.data(), nc.size(), ec.data(), ec.size(), fam.data(),
+                                              fam.size(), &fam_used);
+                if (rc == PG_E_CAPACITY && attempt == 0 && fam_used > fam.size())
+                {
+                    fam.resize(fam_used);
+                    continue;
+                }
+                engine_->check(rc);
+                break;
+            }
+            std::unordered_map<int32_t, size_t> site_index;
+            for (size_t k = 0; k < sites_.size(); ++k)
+                site_index[sites_[k].id] = k;
+            for (size_t i = 0; i < which.size(); ++i)
+            {
+                auto& read = **which[i];
+                typedef typename std::remove_reference<decltype(read)>::type ReadT;
+                const Site& s = sites_[site_index[site[i]]];
+                GraphAligner::applyRecord(read, rec[i], ops.data(), flags_, i);
+                read.clear_graph_nodes_supported();
+                read.clear_graph_edges_supported();
+                read.clear_graph_sequences_supported();
+                if (sup[i].verdict != PG_V_MAPPED)
+                {
+                    read.set_graph_mapping_status(ReadT::BAD_ALIGN); // Disambiguation.cpp:184 / CompositeAligner.cpp:165-169
+                    out[site_index[site[i]]].invalid_alignments += sup[i].verdict == PG_V_INVALID;
+                    continue;
+                }
+                read.set_graph_mapping_status(ReadT::MAPPED);
+                // std::set order of the reference: nodes by id, edges by (from name, to name), labels by name
+                std::set<std::pair<std::string, std::string>> edges;
+                for (uint32_t k = 0; k < sup[i].path_len; ++k)
+                {
+                    const uint32_t w = path[sup[i].path_off + k];
+                    if (w & PG_SUP_NODE)
+                        read.add_graph_nodes_supported(s.node_names[w & PG_SUP_NODE_MASK]);
+                    if (k > 0 && (w & PG_SUP_EDGE))
+                        edges.emplace(s.node_names[path[sup[i].path_off + k - 1] & PG_SUP_NODE_MASK], s.node_names[w & PG_SUP_NODE_MASK]);
+                }
+                for (auto const& e : edges)
+                    read.add_graph_edges_supported(e.first + "_" + e.second);
+                std::set<std::string> seqs;
+                for (size_t k = 0; k < s.labels.size(); ++k)
+                    if ((sup[i].sequences >> k) & 1)
+                        seqs.insert(s.labels[k]);
+                for (auto const& l : seqs)
+                    read.add_graph_sequences_supported(l);
+            }
+        }
+        // tables: rows are site-major in addSite order (this object registers nothing else on the context)
+        size_t nb = 0, eb = 0;
+        std::vector<std::pair<size_t, size_t>> bases;
+        for (size_t k = 0; k < sites_.size(); ++k)
+        {
+            const Site& s = sites_[k];
+            bases.emplace_back(nb, eb);
+            for (size_t v = 0; v < s.node_names.size(); ++v)
+                if (nc[nb + v].fragments)
+                    out[k].read_counts_by_node[s.node_names[v]] = conv(nc[nb + v]);
+            for (size_t e = 0; e < s.edges.size(); ++e)
+                if (ec[eb + e].fragments)
+                    out[k].read_counts_by_edge[edgeName(s, e)] = conv(ec[eb + e]);
+            nb += s.node_names.size();
+            eb += s.edges.size();
+        }
+        for (uint64_t w = 0; w < fam_used;)
+        {
+            const uint32_t sid = fam[w], n = fam[w + 1];
+            const uint64_t mask = (uint64_t)fam[w + 2] | ((uint64_t)fam[w + 3] << 32);
+            size_t k = 0;
+            while (k < sites_.size() && sites_[k].id != (int32_t)sid)
+                ++k;
+            const Site& s = sites_.at(k);
+            std::set<std::string> names;
+            for (size_t b = 0; b < s.labels.size(); ++b)
+                if ((mask >> b) & 1)
+                    names.insert(s.labels[b]);
+            std::string key;
+            for (auto const& nme : names)
+                key += (key.empty() ? "" : ",") + nme;
+            auto& dst = out[k].read_counts_by_sequence[key];
+            const pg_count4* rows = reinterpret_cast<const pg_count4*>(&fam[w + 4]);
+            dst["total"] = conv(rows[0]);
+            for (size_t v = 0; v < s.node_names.size(); ++v)
+                if (rows[1 + v].fragments)
+                    dst[s.node_names[v]] = conv(rows[1 + v]);
+            for (size_t e = 0; e < s.edges.size(); ++e)
+                if (rows[1 + s.node_names.size() + e].fragments)
+                    dst[edgeName(s, e)] = conv(rows[1 + s.node_names.size() + e]);
+            w += 4 + 4ull * n;
+        }
+        keepMapped();
+        return out;
     }
 
     // align every registered site in one batch, apply the filter, keep MAPPED reads per site (Align.cpp:72-84,155)
@@ -334,6 +551,32 @@ public:
                     read.set_graph_mapping_status(ReadT::BAD_ALIGN);
             }
         }
+        keepMapped();
+    }
+
+private:
+    struct Site
+    {
+        int32_t id;
+        std::vector<ReadPtrT>* reads;
+        std::vector<std::string> node_names, labels;
+        std::vector<std::pair<int32_t, int32_t>> edges; // in the order given to pg_add_graph
+    };
+    static paragraph::Count4 conv(pg_count4 const& c)
+    {
+        paragraph::Count4 r;
+        r.fragments = c.fragments;
+        r.reads = c.reads;
+        r.fwd = c.fwd;
+        r.rev = c.rev;
+        return r;
+    }
+    static std::string edgeName(Site const& s, size_t e)
+    {
+        return s.node_names[(size_t)s.edges[e].first] + "_" + s.node_names[(size_t)s.edges[e].second];
+    }
+    void keepMapped()
+    {
         for (auto& s : sites_)
         {
             std::vector<ReadPtrT> kept;
@@ -348,13 +591,6 @@ public:
         sites_.clear();
         engine_->check(pg_clear_graphs(engine_->get()));
     }
-
-private:
-    struct Site
-    {
-        int32_t id;
-        std::vector<ReadPtrT>* reads;
-    };
     std::unique_ptr<Engine> engine_;
     unsigned flags_;
     std::vector<Site> sites_;

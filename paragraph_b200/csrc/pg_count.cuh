@@ -54,11 +54,15 @@ struct CountParams
 // Per-site tables for counting, all indexed from the site's bases:
 //   node_base / edge_base : first row of the site in node_counts / edge_counts (and in lab_out/lab_in / lab_edge,
 //                           csr_input, which are laid out the same way);
-//   fam_base              : first Count4 of the site's family table, family_slots x (1 + n_nodes + n_edges) rows.
+//   fam_base / key_base   : the site's family table: `slots` keys at fam_keys[key_base ...] and
+//                           slots x (1 + n_nodes + n_edges) Count4 rows at fam_counts[fam_base ...].
+//                           slots = min(family_slots, 2^(labels used by the site)): a DEL/INS graph with the two
+//                           labels REF and ALT gets 4, only graphs with many haplotype labels get the full table.
 struct CountSite
 {
     int32_t node_base, edge_base;
     int64_t fam_base;
+    int32_t slots, key_base;
 };
 
 struct CountTables
@@ -318,7 +322,7 @@ PG_HD bool count_fragment(int head, int site, const int32_t* next, const ReadSup
     Count4* fam = nullptr;
     if (seqs)
     {
-        const int slot = family_slot(fam_keys + (size_t)site * prm.family_slots, prm.family_slots, seqs);
+        const int slot = family_slot(fam_keys + cs.key_base, cs.slots, seqs);
         if (slot < 0)
             return false;
         fam = fam_counts + cs.fam_base + (int64_t)slot * (1 + sd.n_nodes + sd.n_edges);

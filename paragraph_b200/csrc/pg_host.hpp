@@ -171,7 +171,7 @@ struct CountHostTables
     std::vector<CountSite> csite;
     std::vector<int32_t> csr_input;
     std::vector<uint64_t> lab_edge, lab_out, lab_in;
-    int64_t fam_rows = 0;
+    int64_t fam_rows = 0, fam_keys = 0;
 };
 
 // per site: CSR edge -> input edge index, label masks per CSR edge and per node, bases of the count rows
@@ -183,14 +183,22 @@ inline void build_count_tables(const GraphStore& gs, int slots, CountHostTables&
     t.lab_out.assign((size_t)gs.node_base[ns], 0);
     t.lab_in.assign((size_t)gs.node_base[ns], 0);
     t.csite.resize(ns);
-    int64_t fam = 0;
+    int64_t fam = 0, keys = 0;
     for (size_t s = 0; s < ns; ++s)
     {
         const SiteDev& sd = gs.sites[s];
         const GraphView g = make_view(sd, gs.bytes.data(), gs.ints.data(), 0);
         const int64_t eb = gs.edge_base[s], nb = gs.node_base[s];
-        t.csite[s] = CountSite{ (int32_t)nb, (int32_t)eb, fam };
-        fam += (int64_t)slots * (1 + sd.n_nodes + sd.n_edges);
+        uint64_t used = 0;
+        for (int e = 0; e < sd.n_edges; ++e)
+            used |= gs.in_label[(size_t)(eb + e)];
+        int n_labels = 0;
+        for (; used; used &= used - 1)
+            ++n_labels;
+        const int site_slots = n_labels >= 30 ? slots : (int)std::min<int64_t>(slots, (int64_t)1 << n_labels);
+        t.csite[s] = CountSite{ (int32_t)nb, (int32_t)eb, fam, site_slots, (int32_t)keys };
+        fam += (int64_t)site_slots * (1 + sd.n_nodes + sd.n_edges);
+        keys += site_slots;
         for (int e = sd.n_edges - 1; e >= 0; --e) // descending: a duplicated input edge maps to its first occurrence
             t.csr_input[(size_t)(eb + csr_edge(g, gs.in_from[(size_t)(eb + e)], gs.in_to[(size_t)(eb + e)]))] = e;
         for (int e = 0; e < sd.n_edges; ++e)
@@ -203,6 +211,7 @@ inline void build_count_tables(const GraphStore& gs, int slots, CountHostTables&
         }
     }
     t.fam_rows = fam;
+    t.fam_keys = keys;
 }
 
 // Chain the reads of each fragment in input order (readsToFragments keeps one Fragment per fragment_id,

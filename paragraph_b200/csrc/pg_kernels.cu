@@ -465,29 +465,32 @@ __global__ void __launch_bounds__(128) pg_fragment_kernel(CountArgs a)
         atomicMax(&a.cursor[1], (unsigned long long)site + 1ull);
 }
 
-// one thread per (site, slot): occupied slots are appended to the compact family list
+// one warp per site: its lanes walk the site's slots; occupied slots are appended to the compact family list
 __global__ void __launch_bounds__(128) pg_family_compact_kernel(CountArgs a)
 {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)a.n_sites * a.prm.family_slots)
+    const int site = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (site >= a.n_sites)
         return;
-    const unsigned long long key = a.fam_keys[idx];
-    if (!key)
-        return;
-    const int site = (int)(idx / a.prm.family_slots), slot = (int)(idx % a.prm.family_slots);
+    const CountSite cs = a.t.csite[site];
     const SiteDev& sd = a.t.sites[site];
     const int n = 1 + sd.n_nodes + sd.n_edges;
-    const unsigned long long off = atomicAdd(&a.cursor[0], 4ull + 4ull * (unsigned long long)n);
-    if (off + 4ull + 4ull * (unsigned long long)n > a.fam_out_cap)
-        return;
-    uint32_t* o = a.fam_out + off;
-    o[0] = (uint32_t)site;
-    o[1] = (uint32_t)n;
-    o[2] = (uint32_t)key;
-    o[3] = (uint32_t)(key >> 32);
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.fam_counts + a.t.csite[site].fam_base + (int64_t)slot * n);
-    for (int x = 0; x < 4 * n; ++x)
-        o[4 + x] = src[x];
+    for (int slot = lane; slot < cs.slots; slot += 32)
+    {
+        const unsigned long long key = a.fam_keys[cs.key_base + slot];
+        if (!key)
+            continue;
+        const unsigned long long off = atomicAdd(&a.cursor[0], 4ull + 4ull * (unsigned long long)n);
+        if (off + 4ull + 4ull * (unsigned long long)n > a.fam_out_cap)
+            continue;
+        uint32_t* o = a.fam_out + off;
+        o[0] = (uint32_t)site;
+        o[1] = (uint32_t)n;
+        o[2] = (uint32_t)key;
+        o[3] = (uint32_t)(key >> 32);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.fam_counts + cs.fam_base + (int64_t)slot * n);
+        for (int x = 0; x < 4 * n; ++x)
+            o[4 + x] = src[x];
+    }
 }
 
 struct pg_ctx
@@ -539,7 +542,7 @@ struct pg_ctx
     DevBuf<uint32_t> d_path, d_fam_out;
     DevBuf<Count4> d_node_counts, d_edge_counts, d_fam_counts;
     DevBuf<unsigned long long> d_fam_keys, d_count_cursor; // cursor[0] = family words, cursor[1] = overflow site + 1
-    int64_t fam_rows = 0;
+    int64_t fam_rows = 0, fam_nkeys = 0;
     cudaEvent_t count_ev[2] = { nullptr, nullptr };
 };
 
@@ -614,6 +617,7 @@ int upload_count_tables(pg_ctx* c, int slots)
     host::CountHostTables t;
     host::build_count_tables(gs, slots, t);
     c->fam_rows = t.fam_rows;
+    c->fam_nkeys = t.fam_keys;
     PG_CUDA(c, put(c, c->d_csite, t.csite));
     PG_CUDA(c, put(c, c->d_csr_input, t.csr_input));
     PG_CUDA(c, put(c, c->d_lab_edge, t.lab_edge));
@@ -1196,7 +1200,7 @@ int pg_batch_count(pg_ctx* c, const int32_t* fragment, const uint8_t* is_reverse
     prm.remove_nonuniq = params->remove_nonuniq;
     prm.use_support_filters = params->use_support_filters;
     prm.bad_align_frac = params->bad_align_frac;
-    prm.family_slots = params->family_slots > 0 ? params->family_slots : 16;
+    prm.family_slots = params->family_slots > 0 ? params->family_slots : 256;
     if (path_used)
         *path_used = 0;
     if (family_used)
@@ -1246,9 +1250,9 @@ int pg_batch_count(pg_ctx* c, const int32_t* fragment, const uint8_t* is_reverse
     PG_CUDA(c, c->d_node_counts.reserve((size_t)total_nodes + 1));
     PG_CUDA(c, c->d_edge_counts.reserve((size_t)total_edges + 1));
     PG_CUDA(c, c->d_fam_counts.reserve((size_t)c->fam_rows + 1));
-    PG_CUDA(c, c->d_fam_keys.reserve(ns * (size_t)prm.family_slots));
+    PG_CUDA(c, c->d_fam_keys.reserve((size_t)c->fam_nkeys + 1));
     PG_CUDA(c, c->d_count_cursor.reserve(2));
-    const unsigned long long fam_out_cap = 4ull * (unsigned long long)c->fam_rows + 4ull * ns * (unsigned long long)prm.family_slots;
+    const unsigned long long fam_out_cap = 4ull * (unsigned long long)c->fam_rows + 4ull * (unsigned long long)c->fam_nkeys;
     PG_CUDA(c, c->d_fam_out.reserve((size_t)fam_out_cap + 1));
     if (!c->count_ev[0])
     {
@@ -1259,7 +1263,7 @@ int pg_batch_count(pg_ctx* c, const int32_t* fragment, const uint8_t* is_reverse
     PG_CUDA(c, cudaMemsetAsync(c->d_node_counts.p, 0, ((size_t)total_nodes + 1) * sizeof(Count4), c->stream));
     PG_CUDA(c, cudaMemsetAsync(c->d_edge_counts.p, 0, ((size_t)total_edges + 1) * sizeof(Count4), c->stream));
     PG_CUDA(c, cudaMemsetAsync(c->d_fam_counts.p, 0, ((size_t)c->fam_rows + 1) * sizeof(Count4), c->stream));
-    PG_CUDA(c, cudaMemsetAsync(c->d_fam_keys.p, 0, ns * (size_t)prm.family_slots * sizeof(unsigned long long), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_fam_keys.p, 0, ((size_t)c->fam_nkeys + 1) * sizeof(unsigned long long), c->stream));
     PG_CUDA(c, cudaMemsetAsync(c->d_count_cursor.p, 0, 2 * sizeof(unsigned long long), c->stream));
 
     CountArgs a;
@@ -1294,8 +1298,7 @@ int pg_batch_count(pg_ctx* c, const int32_t* fragment, const uint8_t* is_reverse
     PG_CUDA(c, cudaGetLastError());
     pg_fragment_kernel<<<grid, 128, 0, c->stream>>>(a);
     PG_CUDA(c, cudaGetLastError());
-    const long long slots_total = (long long)ns * prm.family_slots;
-    pg_family_compact_kernel<<<(unsigned)((slots_total + 127) / 128), 128, 0, c->stream>>>(a);
+    pg_family_compact_kernel<<<(unsigned)((ns * 32 + 127) / 128), 128, 0, c->stream>>>(a);
     PG_CUDA(c, cudaGetLastError());
     c->launches += 3;
     c->count_launches += 3;

@@ -53,6 +53,50 @@ int main()
         }
         printf("path-stage-throws %d\n", (int)threw);
 
+        // alignAndDisambiguate's core on the device: ParagraphTest.Aligns expects these supports
+        // (test_paragraph_parts.cpp:113-144; the test calls disambiguateReads with null filters)
+        {
+            Graph lg = graph;
+            lg.addLabelToEdge(0, 1, "P");
+            lg.addLabelToEdge(1, 3, "P");
+            lg.addLabelToEdge(0, 2, "Q");
+            lg.addLabelToEdge(2, 3, "Q");
+            lg.addLabelToEdge(0, 3, "D");
+            std::vector<std::unique_ptr<Read>> rd;
+            for (auto const& r : reads)
+                rd.emplace_back(new Read(r));
+            const char* names[] = { "LF", "P1", "Q1", "RF" };
+            for (uint32_t v = 0; v < 4; ++v)
+                lg.setNodeName(v, names[v]);
+            grm::MultiSiteAligner<std::unique_ptr<Read>> counter;
+            counter.addSite(&lg, &rd);
+            pgb::paragraph::CountOptions opt;
+            opt.use_support_filters = false;
+            auto counts = counter.alignAndCount(opt);
+            printf("count-sites %zu reads %zu\n", counts.size(), rd.size());
+            for (auto const& r : rd)
+            {
+                printf("s %s n", r->fragment_id().c_str());
+                for (auto const& x : r->graph_nodes_supported())
+                    printf(" %s", x.c_str());
+                printf(" e");
+                for (auto const& x : r->graph_edges_supported())
+                    printf(" %s", x.c_str());
+                printf(" q");
+                for (auto const& x : r->graph_sequences_supported())
+                    printf(" %s", x.c_str());
+                printf("\n");
+            }
+            for (auto const& kv : counts[0].read_counts_by_node)
+                printf("cn %s %llu %llu %llu %llu\n", kv.first.c_str(), (unsigned long long)kv.second.fragments,
+                       (unsigned long long)kv.second.reads, (unsigned long long)kv.second.fwd, (unsigned long long)kv.second.rev);
+            for (auto const& kv : counts[0].read_counts_by_edge)
+                printf("ce %s %llu\n", kv.first.c_str(), (unsigned long long)kv.second.fragments);
+            for (auto const& kv : counts[0].read_counts_by_sequence)
+                printf("cs %s total %llu keys %zu\n", kv.first.c_str(), (unsigned long long)kv.second.at("total").fragments,
+                       kv.second.size());
+        }
+
         // the same site twice plus a second graph, all in ONE launch through MultiSiteAligner
         Graph g2(2);
         g2.setNodeSeq(0, "ACGTACGTAC");

@@ -268,7 +268,7 @@ int pgemu_count_site(int n_nodes, const char* seq_blob, const int32_t* seq_off, 
     prm.remove_nonuniq = remove_nonuniq;
     prm.use_support_filters = use_support_filters;
     prm.bad_align_frac = bad_align_frac;
-    prm.family_slots = family_slots > 0 ? family_slots : 16;
+    prm.family_slots = family_slots > 0 ? family_slots : 256;
     host::CountHostTables ht;
     host::build_count_tables(gs, prm.family_slots, ht);
     CountTables t;
@@ -288,7 +288,7 @@ int pgemu_count_site(int n_nodes, const char* seq_blob, const int32_t* seq_off, 
     if (!host::build_fragment_chains(fragment, nullptr, n_reads, next, head, err))
         return -1;
     std::vector<Count4> nc((size_t)n_nodes), ec((size_t)n_edges + 1), fam((size_t)ht.fam_rows);
-    std::vector<unsigned long long> keys((size_t)prm.family_slots, 0ull);
+    std::vector<unsigned long long> keys((size_t)ht.fam_keys + 1, 0ull);
     memset(nc.data(), 0, nc.size() * sizeof(Count4));
     memset(ec.data(), 0, ec.size() * sizeof(Count4));
     memset(fam.data(), 0, fam.size() * sizeof(Count4));
@@ -300,7 +300,7 @@ int pgemu_count_site(int n_nodes, const char* seq_blob, const int32_t* seq_off, 
     memcpy(edge_counts, ec.data(), (size_t)n_edges * sizeof(Count4));
     const int n = 1 + n_nodes + n_edges;
     int w = 0;
-    for (int slot = 0; slot < prm.family_slots; ++slot)
+    for (int slot = 0; slot < ht.csite[0].slots; ++slot)
     {
         if (!keys[(size_t)slot])
             continue;

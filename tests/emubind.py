@@ -77,7 +77,7 @@ def emu_align_batch(node_seqs, edges, reads, is_rev=None, flags=0xFFFFFFFF):
 
 
 def emu_count_site(node_seqs, edges, edge_labels, reads, is_rev=None, fragment=None, remove_nonuniq=True,
-                   bad_align_frac=0.8, use_filters=True, family_slots=16):
+                   bad_align_frac=0.8, use_filters=True, family_slots=256):
     """Emulated alignment + counting stage (pg_count.cuh on the host) of one site.  Returns a dict shaped like
     oracle.refbind.oracle_count_site's plus the records' CIGAR strings ("cigars")."""
     from oracle import refbind as R

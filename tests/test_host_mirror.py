@@ -38,6 +38,17 @@ def test_mirror_reproduces_reference_unit_test(built):
         "f6 0 0[11M]3[8M] 19 60 0 AAAAAAAAAAAAAAAAAAA 1",
         "path-stage-throws 1",
     ]
+    # alignAndCount: supports as ParagraphTest.Aligns expects them (test_paragraph_parts.cpp:113-144), f7 filtered
+    # (nonuniq); counts as the reference build gives them for these six single-read fragments
+    cl = [l for l in lines if l[:2] in ("co", "s ", "cn", "ce", "cs")]
+    assert cl == [
+        "count-sites 1 reads 6",
+        "s f1 n LF P1 RF e LF_P1 P1_RF q P", "s f2 n LF P1 RF e LF_P1 P1_RF q P", "s f3 n LF Q1 RF e LF_Q1 Q1_RF q Q",
+        "s f4 n LF Q1 RF e LF_Q1 Q1_RF q Q", "s f5 n LF Q1 RF e LF_Q1 Q1_RF q Q", "s f6 n LF RF e LF_RF q D",
+        "cn LF 6 6 4 2", "cn P1 2 2 1 1", "cn Q1 3 3 2 1", "cn RF 6 6 4 2",
+        "ce LF_P1 2", "ce LF_Q1 3", "ce LF_RF 1", "ce P1_RF 2", "ce Q1_RF 3",
+        "cs D total 1 keys 4", "cs P total 2 keys 6", "cs Q total 3 keys 6"]
+    lines = [l for l in lines if l not in cl]
     # MultiSiteAligner: three sites in one launch give the per-site results of separate alignReads calls
     assert lines[7] == "multi 6 2 6"
     assert lines[8:14] == [
