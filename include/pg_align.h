@@ -193,6 +193,10 @@ int pg_batch_count(pg_ctx* ctx, const int32_t* fragment, const uint8_t* is_rever
                    uint64_t* path_used, pg_count4* node_counts, uint64_t node_cap, pg_count4* edge_counts,
                    uint64_t edge_cap, uint32_t* family_words, uint64_t family_cap, uint64_t* family_used);
 
+/* Counting-stage kernels launched by this context so far and the device time in ms of the last pg_batch_count
+ * (memsets + the three kernels, CUDA events on the launching stream). */
+int pg_count_stats(const pg_ctx* ctx, uint64_t* kernel_launches, float* last_count_ms);
+
 /* Kernels launched by this context so far, and the last batch's per-kernel device time in ms
  * (fill, traceback) measured with CUDA events on the launching stream. */
 int pg_stats(const pg_ctx* ctx, uint64_t* kernel_launches, float* last_fill_ms, float* last_trace_ms);

@@ -24,7 +24,7 @@ RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i4"), ("unique", "u1"
 SYMBOLS = ["pg_create", "pg_destroy", "pg_last_error", "pg_set_stream", "pg_set_scratch_limit", "pg_add_graph",
            "pg_clear_graphs", "pg_align_batch", "pg_batch_upload", "pg_batch_run", "pg_batch_download",
            "pg_format_cigar", "pg_stats", "pg_version", "pg_host_alloc", "pg_host_free", "pg_set_edge_labels",
-           "pg_batch_import", "pg_batch_count"]
+           "pg_batch_import", "pg_batch_count", "pg_count_stats"]
 
 # counting stage (include/pg_align.h, "Counting stage")
 V_MAPPED, V_NONUNIQ, V_BAD_ALIGN, V_INVALID = 0, 1, 2, 3
@@ -94,6 +94,8 @@ def load():
     lib.pg_set_edge_labels.argtypes = [vp, C.c_int32, u64p]
     lib.pg_batch_import.restype = C.c_int
     lib.pg_batch_import.argtypes = [vp, C.c_int32, i32p, i32p, vp, u32p, C.c_uint64]
+    lib.pg_count_stats.restype = C.c_int
+    lib.pg_count_stats.argtypes = [vp, u64p, C.POINTER(C.c_float)]
     lib.pg_batch_count.restype = C.c_int
     lib.pg_batch_count.argtypes = [vp, i32p, C.POINTER(C.c_uint8), C.POINTER(CountParams), vp, u32p, C.c_uint64, u64p,
                                    vp, C.c_uint64, vp, C.c_uint64, u32p, C.c_uint64, u64p]
@@ -368,7 +370,10 @@ class Context:
     def stats(self):
         n, a, b = C.c_uint64(0), C.c_float(0), C.c_float(0)
         self.lib.pg_stats(self.h, C.byref(n), C.byref(a), C.byref(b))
-        return dict(kernel_launches=n.value, fill_ms=a.value, trace_ms=b.value)
+        cn, cm = C.c_uint64(0), C.c_float(0)
+        self.lib.pg_count_stats(self.h, C.byref(cn), C.byref(cm))
+        return dict(kernel_launches=n.value, fill_ms=a.value, trace_ms=b.value, count_launches=cn.value,
+                    count_ms=cm.value)
 
     def close(self):
         if getattr(self, "h", None):

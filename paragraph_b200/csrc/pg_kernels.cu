@@ -1333,6 +1333,17 @@ int pg_batch_count(pg_ctx* c, const int32_t* fragment, const uint8_t* is_reverse
     return PG_OK;
 }
 
+int pg_count_stats(const pg_ctx* c, uint64_t* launches, float* ms)
+{
+    if (!c)
+        return PG_E_ARG;
+    if (launches)
+        *launches = c->count_launches;
+    if (ms)
+        *ms = c->count_ms;
+    return PG_OK;
+}
+
 int pg_stats(const pg_ctx* c, uint64_t* launches, float* fill_ms, float* trace_ms)
 {
     if (!c)
