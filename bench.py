@@ -240,14 +240,33 @@ def main():
         rec, ops = ctx.align_packed(blob, off)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
     h2d = int(blob.nbytes + off.nbytes)
     d2h = int(rec.nbytes + ops.nbytes + 8)
+    # ---------------- reads -> count tables: host reads in, node/edge/path-family fragment counts
+    # out; the CIGARs never leave the device.  Reads 2k, 2k+1 form a fragment; labels = the two haplotypes (REF/ALT).
+    ctx.set_edge_labels(0, synth.haplotype_labels(nodes, edges))
+    pairs = np.arange(READS_PER_SITE, dtype=np.int32) // 2
+    for _ in range(2):
+        ctx.upload(blob, off)
+        ctx.run()
+        cnt = ctx.count(fragment=pairs, want_support=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.upload(blob, off)
+        ctx.run()
+        cnt = ctx.count(fragment=pairs, want_support=False)
+    torch.cuda.synchronize()
+    cnt_s = time.perf_counter() - t0
+    cst = ctx.stats()
+    clocks = sampler.stop()
+    cnt_d2h = int(cnt["node_counts"].shape[0] * 16 + cnt["edge_counts"].shape[0] * 16
+                  + sum(16 + 16 * v.shape[0] for v in cnt["families"].values()))
 
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_s * 1e3, cnt_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms, cnt_ms = float(t[0]), float(t[1]), float(t[2])
     n_reads_all = READS_PER_SITE * world
     value = n_reads_all * args.steps / (total_ms * 1e-3)
     e2e_value = n_reads_all * args.steps / (e2e_ms * 1e-3)
@@ -274,7 +293,13 @@ def main():
                         l2="256 MiB flush write between timed steps; per-step scratch (checkpoints) exceeds L2"),
             e2e=dict(value=round(e2e_value, 1), unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
             gpu_launches=int(launches),
-            kernels=dict(fill_ms=round(st["fill_ms"], 4), trace_ms=round(st["trace_ms"], 4)),
+            kernels=dict(fill_ms=round(st["fill_ms"], 4), trace_ms=round(st["trace_ms"], 4),
+                         count_ms=round(cst["count_ms"], 4)),
+            e2e_counts=dict(value=round(n_reads_all * args.steps / (cnt_ms * 1e-3), 1), unit="reads/s",
+                            what="host reads -> filters + disambiguation + node/edge/path-family fragment counts on "
+                                 "the device (pg_batch_count); only the count tables are copied back",
+                            h2d_bytes_per_step=h2d + int(pairs.nbytes), d2h_bytes_per_step=cnt_d2h,
+                            fragments=int(cnt["node_counts"][:, 0].max())),
             roofline=dict(bound="alu (packed-int16 DPX issue; neither hbm nor tensor applies, see DESIGN.md)",
                           kernel="pg_fill_kernel<5>", achieved=round(ach_cells / 1e9, 1), peak=round(peak_cells / 1e9, 1),
                           unit="Gcell/s", frac=round(ach_cells / peak_cells, 4) if peak_cells else None,

@@ -241,7 +241,7 @@ class Context:
         path_cap = int(n * 64 + 4096)
         fam_cap = 1 << 16
         for attempt in range(3):
-            pw = np.zeros(path_cap, dtype=np.uint32)
+            pw = np.zeros(path_cap if want_support else 1, dtype=np.uint32)
             fw = np.zeros(fam_cap, dtype=np.uint32)
             pu, fu = C.c_uint64(0), C.c_uint64(0)
             rc = self.lib.pg_batch_count(
