@@ -174,9 +174,13 @@ void pgo_graph_destroy(pgo_graph* G)
 
 typedef struct
 {
-    uint8_t *mH, *mE, *mF; /* len x L, row = reference position (gssw.c:395-430) */
-    uint8_t *seedH, *seedE; /* striped [segLen][16]  (alignment->seed, gssw.c:442-443) */
+    /* len x L, row = reference position (gssw.c:395-430 byte mode, :706-740 word mode).  Held as 16-bit cells in
+     * both modes; in byte mode every value is <= 255 (the reference's arrays are uint8_t there). */
+    uint16_t *mH, *mE, *mF;
+    uint8_t *seedH, *seedE;      /* byte mode: striped [segLen][16]  (alignment->seed, gssw.c:442-443) */
+    uint16_t *seedH16, *seedE16; /* word mode: striped [segLen8][8]  (gssw.c:745-746) */
     int score1, ref_end1, read_end1;
+    int is_byte; /* alignment->is_byte (gssw.c:226, 598) */
 } naln;
 
 /* gssw_qP_byte, gssw.c:72-98: prof[nt][i][lane] = j>=L ? bias : mat[nt][read[j]]+bias, j = i + lane*segLen */
@@ -222,11 +226,12 @@ static int fill_node_byte(const int8_t* ref, int refLen, int L, const uint8_t* p
     uint8_t* E = (uint8_t*)calloc(vb, 1);
     uint8_t* ES = (uint8_t*)calloc(vb, 1);
     uint8_t* FS = (uint8_t*)calloc(vb, 1);
-    out->mH = (uint8_t*)calloc((size_t)refLen * L + 1, 1);
-    out->mE = (uint8_t*)calloc((size_t)refLen * L + 1, 1);
-    out->mF = (uint8_t*)calloc((size_t)refLen * L + 1, 1);
+    out->mH = (uint16_t*)calloc((size_t)refLen * L + 1, sizeof(uint16_t));
+    out->mE = (uint16_t*)calloc((size_t)refLen * L + 1, sizeof(uint16_t));
+    out->mF = (uint16_t*)calloc((size_t)refLen * L + 1, sizeof(uint16_t));
     out->seedH = (uint8_t*)calloc(vb, 1);
     out->seedE = (uint8_t*)calloc(vb, 1);
+    out->is_byte = 1;
     if (seedH) /* gssw.c:215-218 */
     {
         memcpy(E, seedE, vb);
@@ -344,6 +349,173 @@ static int fill_node_byte(const int8_t* ref, int refLen, int L, const uint8_t* p
     return out->score1;
 }
 
+/* ------------------------------------------------------------------ 16-bit ("word") mode
+ * gssw_graph_fill_internal redoes the whole graph with 8 x int16 lanes as soon as a byte-mode node fill reports
+ * overflow (score + bias >= 255, i.e. a score >= 251: gssw.c:380, 467, 4001-4013, 4098-4102). */
+enum { NLW = 8 };
+static inline int16_t adds16(int16_t a, int16_t b)
+{
+    int v = (int)a + (int)b;
+    return (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
+}
+static inline int16_t subsu16(int16_t a, int16_t b) /* _mm_subs_epu16 on the bit patterns */
+{
+    uint16_t x = (uint16_t)a, y = (uint16_t)b;
+    return (int16_t)(x > y ? x - y : 0);
+}
+static inline int16_t max16(int16_t a, int16_t b) { return a > b ? a : b; }
+
+/* gssw_qP_word, gssw.c:475-498: prof[nt][i][lane] = j >= L ? 0 : mat[nt][read[j]], j = i + lane*segLen */
+static int16_t* make_profile_word(const char* read, int L, int segLen)
+{
+    int16_t* p = (int16_t*)malloc((size_t)5 * segLen * NLW * sizeof(int16_t));
+    int16_t* t = p;
+    for (int nt = 0; nt < 5; ++nt)
+        for (int i = 0; i < segLen; ++i)
+        {
+            int j = i;
+            for (int s = 0; s < NLW; ++s, j += segLen)
+                *t++ = (int16_t)(j >= L ? 0 : sub_score(nt, nt_code((unsigned char)read[j])));
+        }
+    return p;
+}
+
+static void shl1w(int16_t* v) /* _mm_slli_si128(v, 2) */
+{
+    for (int k = NLW - 1; k > 0; --k)
+        v[k] = v[k - 1];
+    v[0] = 0;
+}
+
+/* gssw_sw_sse2_word, gssw.c:527-786 (ref_dir = 0) */
+static int fill_node_word(const int8_t* ref, int refLen, int L, const int16_t* prof, const uint16_t* seedH,
+                          const uint16_t* seedE, naln* out)
+{
+    const int segLen = (L + 7) / 8;
+    const size_t vn = (size_t)segLen * NLW;
+    int16_t* HS = (int16_t*)calloc(vn, sizeof(int16_t));
+    int16_t* HL = (int16_t*)calloc(vn, sizeof(int16_t));
+    int16_t* Hmax = (int16_t*)calloc(vn, sizeof(int16_t));
+    int16_t* E = (int16_t*)calloc(vn, sizeof(int16_t));
+    int16_t* ES = (int16_t*)calloc(vn, sizeof(int16_t));
+    int16_t* FS = (int16_t*)calloc(vn, sizeof(int16_t));
+    out->mH = (uint16_t*)calloc((size_t)refLen * L + 1, sizeof(uint16_t));
+    out->mE = (uint16_t*)calloc((size_t)refLen * L + 1, sizeof(uint16_t));
+    out->mF = (uint16_t*)calloc((size_t)refLen * L + 1, sizeof(uint16_t));
+    out->seedH16 = (uint16_t*)calloc(vn, sizeof(uint16_t));
+    out->seedE16 = (uint16_t*)calloc(vn, sizeof(uint16_t));
+    out->is_byte = 0;
+    if (seedH) /* gssw.c:588-591 */
+    {
+        memcpy(E, seedE, vn * sizeof(int16_t));
+        memcpy(HS, seedH, vn * sizeof(int16_t));
+    }
+    uint16_t max = 0;
+    int end_read = L - 1, end_ref = 0; /* NB: 0, not -1 as in byte mode (gssw.c:543) */
+    int16_t vMaxScore[NLW] = { 0 }, vMaxMark[NLW] = { 0 };
+
+    for (int i = 0; i < refLen; ++i)
+    {
+        int16_t e[NLW], vF[NLW] = { 0 }, vMaxColumn[NLW] = { 0 }, vH[NLW];
+        memcpy(vH, HS + (size_t)(segLen - 1) * NLW, sizeof vH); /* gssw.c:625-626 */
+        shl1w(vH);
+        const int16_t* vP = prof + (size_t)ref[i] * segLen * NLW;
+        int16_t* pv = HL; /* swap, gssw.c:629-635 */
+        HL = HS;
+        HS = pv;
+        for (int j = 0; j < segLen; ++j) /* gssw.c:638-668 */
+        {
+            for (int k = 0; k < NLW; ++k)
+            {
+                int16_t h = adds16(vH[k], vP[j * NLW + k]);
+                e[k] = E[j * NLW + k];
+                h = max16(h, e[k]);
+                h = max16(h, vF[k]);
+                vMaxColumn[k] = max16(vMaxColumn[k], h);
+                HS[j * NLW + k] = h;
+                ES[j * NLW + k] = e[k];
+                FS[j * NLW + k] = vF[k];
+                h = subsu16(h, GAP_OPEN);
+                e[k] = max16(subsu16(e[k], GAP_EXT), h);
+                E[j * NLW + k] = e[k];
+                vF[k] = max16(subsu16(vF[k], GAP_EXT), h);
+                vH[k] = HL[j * NLW + k];
+            }
+        }
+        /* lazy-F, gssw.c:671-693: up to 8 passes; stops as soon as no lane has vF > H - gapO */
+        {
+            int done = 0;
+            for (int k8 = 0; k8 < NLW && !done; ++k8)
+            {
+                shl1w(vF);
+                for (int j = 0; j < segLen && !done; ++j)
+                {
+                    int any = 0;
+                    for (int k = 0; k < NLW; ++k)
+                    {
+                        int16_t h = max16(HS[j * NLW + k], vF[k]);
+                        HS[j * NLW + k] = h;
+                        FS[j * NLW + k] = max16(FS[j * NLW + k], vF[k]);
+                        h = subsu16(h, GAP_OPEN);
+                        vF[k] = subsu16(vF[k], GAP_EXT);
+                        if (vF[k] > h)
+                            any = 1;
+                    }
+                    if (!any)
+                        done = 1;
+                }
+            }
+        }
+        /* running maximum and end column snapshot, gssw.c:696-710 (vMaxColumn is NOT updated by the lazy-F loop here) */
+        for (int k = 0; k < NLW; ++k)
+            vMaxScore[k] = max16(vMaxScore[k], vMaxColumn[k]);
+        if (memcmp(vMaxMark, vMaxScore, sizeof vMaxMark) != 0)
+        {
+            int16_t temp = vMaxScore[0];
+            memcpy(vMaxMark, vMaxScore, sizeof vMaxMark);
+            for (int k = 1; k < NLW; ++k)
+                temp = max16(temp, vMaxScore[k]);
+            if ((uint16_t)temp > max)
+            {
+                max = (uint16_t)temp;
+                end_ref = i;
+                memcpy(Hmax, HS, vn * sizeof(int16_t));
+            }
+        }
+        /* de-stripe, gssw.c:713-748; padded positions p >= L land in the next row and are overwritten by it */
+        for (int j = 0; j < segLen; ++j)
+            for (int ti = 0; ti < NLW; ++ti)
+            {
+                int p = ti * segLen + j;
+                if (p < L)
+                {
+                    out->mH[(size_t)i * L + p] = (uint16_t)HS[j * NLW + ti];
+                    out->mE[(size_t)i * L + p] = (uint16_t)ES[j * NLW + ti];
+                    out->mF[(size_t)i * L + p] = (uint16_t)FS[j * NLW + ti];
+                }
+            }
+    }
+    memcpy(out->seedE16, E, vn * sizeof(int16_t)); /* gssw.c:756-757 */
+    memcpy(out->seedH16, HS, vn * sizeof(int16_t));
+    for (int idx = 0; idx < segLen * NLW; ++idx) /* gssw.c:761-769 */
+        if ((uint16_t)Hmax[idx] == max)
+        {
+            int temp = idx / NLW + idx % NLW * segLen;
+            if (temp < end_read)
+                end_read = temp;
+        }
+    free(HS);
+    free(HL);
+    free(Hmax);
+    free(E);
+    free(ES);
+    free(FS);
+    out->score1 = max;
+    out->ref_end1 = end_ref;
+    out->read_end1 = end_read;
+    return max;
+}
+
 /* ------------------------------------------------------------------ model variants (not the reference)
  * The CUDA path does not restate Farrar striping.  It computes the plain affine-gap recurrence
  *     t = max(Hdiag + s, E, 0);  H = max(t, F);  F' = max(F - ge, t - go);
@@ -356,25 +528,26 @@ static int fill_node_byte(const int8_t* ref, int refLen, int L, const uint8_t* p
 static int g_fill_variant = 0;
 void pgo_set_fill_variant(int v) { g_fill_variant = v; }
 
-static int fill_node_model(const int8_t* ref, int refLen, const char* read, int L, const uint8_t* seedH,
-                           const uint8_t* seedE, naln* out)
+/* seeds of the model variants are linear (row p at index p), 16-bit; word != 0 = "the reference is in 16-bit mode":
+ * no overflow report, and is_byte = 0 for the uniqueness scan (aligns_end_at_mult_nodes). */
+static int fill_node_model(const int8_t* ref, int refLen, const char* read, int L, const uint16_t* seedH,
+                           const uint16_t* seedE, int word, naln* out)
 {
-    const int segLen = (L + 15) / 16;
-    const size_t vb = (size_t)segLen * NL; /* >= L: seeds are kept linear (row p at index p) */
     int* Hp = (int*)calloc((size_t)L + 1, sizeof(int));
     int* Hc = (int*)calloc((size_t)L + 1, sizeof(int));
     int* E = (int*)calloc((size_t)L + 1, sizeof(int));
-    out->mH = (uint8_t*)calloc((size_t)refLen * L + 1, 1);
-    out->mE = (uint8_t*)calloc((size_t)refLen * L + 1, 1);
-    out->mF = (uint8_t*)calloc((size_t)refLen * L + 1, 1);
-    out->seedH = (uint8_t*)calloc(vb, 1);
-    out->seedE = (uint8_t*)calloc(vb, 1);
+    out->mH = (uint16_t*)calloc((size_t)refLen * L + 1, sizeof(uint16_t));
+    out->mE = (uint16_t*)calloc((size_t)refLen * L + 1, sizeof(uint16_t));
+    out->mF = (uint16_t*)calloc((size_t)refLen * L + 1, sizeof(uint16_t));
+    out->seedH16 = (uint16_t*)calloc((size_t)L + 1, sizeof(uint16_t));
+    out->seedE16 = (uint16_t*)calloc((size_t)L + 1, sizeof(uint16_t));
+    out->is_byte = !word;
     for (int p = 0; p < L; ++p)
     {
         Hp[p] = seedH ? seedH[p] : 0;
         E[p] = seedE ? seedE[p] : 0;
     }
-    int max = 0, end_ref = -1, end_read = L - 1;
+    int max = 0, end_ref = word ? 0 : -1, end_read = L - 1;
     for (int i = 0; i < refLen; ++i)
     {
         int F = 0, colmax = 0;
@@ -386,9 +559,9 @@ static int fill_node_model(const int8_t* ref, int refLen, const char* read, int 
             if (t < 0) t = 0;
             int h = t > F ? t : F;
             Hc[p] = h;
-            out->mH[(size_t)i * L + p] = (uint8_t)h;
-            out->mE[(size_t)i * L + p] = (uint8_t)(E[p] > 0 ? E[p] : 0);
-            out->mF[(size_t)i * L + p] = (uint8_t)(F > 0 ? F : 0);
+            out->mH[(size_t)i * L + p] = (uint16_t)h;
+            out->mE[(size_t)i * L + p] = (uint16_t)(E[p] > 0 ? E[p] : 0);
+            out->mF[(size_t)i * L + p] = (uint16_t)(F > 0 ? F : 0);
             if (h > colmax) colmax = h;
             int open = (g_fill_variant == 1 ? h : t) - GAP_OPEN;
             E[p] = E[p] - GAP_EXT > open ? E[p] - GAP_EXT : open;
@@ -405,75 +578,116 @@ static int fill_node_model(const int8_t* ref, int refLen, const char* read, int 
     }
     for (int p = 0; p < L; ++p)
     {
-        out->seedH[p] = (uint8_t)Hp[p];
-        out->seedE[p] = (uint8_t)(E[p] > 0 ? E[p] : 0);
+        out->seedH16[p] = (uint16_t)Hp[p];
+        out->seedE16[p] = (uint16_t)(E[p] > 0 ? E[p] : 0);
     }
     free(Hp); free(Hc); free(E);
     out->score1 = max; out->ref_end1 = end_ref; out->read_end1 = end_read;
-    return max >= 251 ? 255 : max;
+    return (!word && max >= 251) ? 255 : max;
+}
+
+static void naln_clear(naln* a)
+{
+    free(a->mH);
+    free(a->mE);
+    free(a->mF);
+    free(a->seedH);
+    free(a->seedE);
+    free(a->seedH16);
+    free(a->seedE16);
+    memset(a, 0, sizeof(*a));
 }
 
 static void naln_free(naln* a, int n)
 {
+    if (!a)
+        return;
     for (int i = 0; i < n; ++i)
-    {
-        free(a[i].mH);
-        free(a[i].mE);
-        free(a[i].mF);
-        free(a[i].seedH);
-        free(a[i].seedE);
-    }
+        naln_clear(&a[i]);
     free(a);
 }
 
-/* gssw_graph_fill_internal, gssw.c:3964-4028.  *max_node = first node (array order) whose score1
- * strictly exceeds every earlier one, starting from 0 (:4015-4018); -1 when no node scores > 0
- * (the reference then keeps a stale/first max_node whose fresh score1 is 0 -- same observable
- * result: score 0, ref_end -1, empty CIGAR). */
-static int graph_fill(const g1* g, const char* read, int L, naln** out, int* max_node)
+/* One pass of gssw_graph_fill_internal over all nodes in one mode.  Returns 255 when a byte-mode node fill
+ * overflowed (the caller redoes everything in word mode), else 0. */
+static int graph_fill_mode(const g1* g, const char* read, int L, int word, naln* a, int* max_node)
 {
-    const int segLen = (L + 15) / 16;
-    const size_t vb = (size_t)segLen * NL;
-    uint8_t* prof = make_profile(read, L, segLen);
-    naln* a = (naln*)calloc((size_t)g->n, sizeof(naln));
-    uint8_t* sH = (uint8_t*)malloc(vb);
-    uint8_t* sE = (uint8_t*)malloc(vb);
-    int max_score = 0, rc = PGO_OK;
+    const int segLen = word ? (L + 7) / 8 : (L + 15) / 16;
+    const size_t vn = g_fill_variant ? (size_t)L + 1 : (size_t)segLen * (word ? NLW : NL);
+    uint8_t* prof8 = (!word && !g_fill_variant) ? make_profile(read, L, segLen) : NULL;
+    int16_t* prof16 = (word && !g_fill_variant) ? make_profile_word(read, L, segLen) : NULL;
+    uint8_t* sH = (uint8_t*)malloc(vn);
+    uint8_t* sE = (uint8_t*)malloc(vn);
+    uint16_t* sH16 = (uint16_t*)malloc(vn * sizeof(uint16_t));
+    uint16_t* sE16 = (uint16_t*)malloc(vn * sizeof(uint16_t));
+    int max_score = 0, rc = 0;
     *max_node = -1;
     for (int i = 0; i < g->n; ++i)
     {
-        /* gssw_create_seed_byte, gssw.c:3897-3931: lane-wise max over predecessors, zeros if none */
-        memset(sH, 0, vb);
-        memset(sE, 0, vb);
+        /* gssw_create_seed_byte / _word, gssw.c:3897-3962: lane-wise max over predecessors, zeros if none */
+        memset(sH, 0, vn);
+        memset(sE, 0, vn);
+        memset(sH16, 0, vn * sizeof(uint16_t));
+        memset(sE16, 0, vn * sizeof(uint16_t));
         for (int k = 0; k < g->npred[i]; ++k)
         {
             const naln* p = &a[g->pred[i][k]];
-            for (size_t x = 0; x < vb; ++x)
+            for (size_t x = 0; x < vn; ++x)
             {
-                sH[x] = max8(sH[x], p->seedH[x]);
-                sE[x] = max8(sE[x], p->seedE[x]);
+                if (p->seedH)
+                {
+                    sH[x] = max8(sH[x], p->seedH[x]);
+                    sE[x] = max8(sE[x], p->seedE[x]);
+                }
+                else
+                {
+                    sH16[x] = sH16[x] > p->seedH16[x] ? sH16[x] : p->seedH16[x];
+                    sE16[x] = sE16[x] > p->seedE16[x] ? sE16[x] : p->seedE16[x];
+                }
             }
         }
-        int sc = g_fill_variant ? fill_node_model(g->num[i], g->len[i], read, L, sH, sE, &a[i])
-                                : fill_node_byte(g->num[i], g->len[i], L, prof, sH, sE, &a[i]);
-        if (sc == 255)
+        int sc;
+        if (g_fill_variant)
+            sc = fill_node_model(g->num[i], g->len[i], read, L, sH16, sE16, word, &a[i]);
+        else if (word)
+            sc = fill_node_word(g->num[i], g->len[i], L, prof16, sH16, sE16, &a[i]);
+        else
+            sc = fill_node_byte(g->num[i], g->len[i], L, prof8, sH, sE, &a[i]);
+        if (!word && sc == 255)
         {
-            rc = PGO_E_BYTE_OVERFLOW; /* gssw.c:4001-4013 would redo the graph in 16-bit mode */
-            for (int r = i + 1; r < g->n; ++r)
-                memset(&a[r], 0, sizeof(naln));
+            rc = 255; /* gssw.c:4001-4013 */
             break;
         }
-        if (sc > max_score)
+        if (sc > max_score) /* gssw.c:4015-4018 (max_score restarts at 0 in the word-mode re-run) */
         {
             *max_node = i;
             max_score = sc;
         }
     }
-    free(prof);
+    free(prof8);
+    free(prof16);
     free(sH);
     free(sE);
-    *out = a;
+    free(sH16);
+    free(sE16);
     return rc;
+}
+
+/* gssw_graph_fill_internal, gssw.c:3964-4028.  *max_node = first node (array order) whose score1
+ * strictly exceeds every earlier one, starting from 0 (:4015-4018); -1 when no node scores > 0
+ * (the reference then keeps a stale/first max_node whose fresh score1 is 0 -- same observable
+ * result: score 0, ref_end -1, empty CIGAR).  Byte mode first (score_size 2, GraphAligner.cpp:220); when a node
+ * overflows, every node is refilled in word mode (:4001-4013). */
+static int graph_fill(const g1* g, const char* read, int L, naln** out, int* max_node)
+{
+    naln* a = (naln*)calloc((size_t)g->n, sizeof(naln));
+    if (graph_fill_mode(g, read, L, 0, a, max_node) == 255)
+    {
+        for (int i = 0; i < g->n; ++i)
+            naln_clear(&a[i]);
+        graph_fill_mode(g, read, L, 1, a, max_node);
+    }
+    *out = a;
+    return PGO_OK;
 }
 
 /* ------------------------------------------------------------------ CIGAR containers */
@@ -534,7 +748,7 @@ static char match_op(char refc, char readc) /* gssw.c:1601-1622 */
 static void node_trace_back(const g1* g, const naln* a, int n, const char* read, int L, int* score, int* refEnd,
                             int* readEnd, int* gRef, int* gRead, cig* result)
 {
-    const uint8_t *mH = a[n].mH, *mE = a[n].mE, *mF = a[n].mF;
+    const uint16_t *mH = a[n].mH, *mE = a[n].mE, *mF = a[n].mF;
     const char* ref = g->seq[n];
     int i = *refEnd, j = *readEnd;
     int inE = *gRead, inF = *gRef;
@@ -759,7 +973,11 @@ static void graph_trace_back(const g1* g, const naln* a, int max_node, const cha
     gm->position = refEnd + 1 < 0 ? 0 : refEnd + 1; /* :3528 */
 }
 
-/* alignsEndAtMultNodes, GraphAligner.cpp:170-212 (gssw node id == graph node id: Graph{n,false}) */
+/* alignsEndAtMultNodes, GraphAligner.cpp:170-212 (gssw node id == graph node id: Graph{n,false}).
+ * The reference scans `(uint8_t*)alignment->mH` over len*L BYTES whatever the mode (:177-186).  In byte mode that is
+ * the matrix.  In word mode it is the first half of the int16 matrix seen as bytes (little-endian: low byte, high
+ * byte, ...), each compared with the uint16 top score: nothing matches a top score >= 256, and for 251..255 only
+ * the low bytes of cells with linear index < ceil(len*L/2) can.  Restated literally. */
 static int aligns_end_at_mult_nodes(const g1* g, const naln* a, int max_node, int L)
 {
     int top = max_node >= 0 ? a[max_node].score1 : 0;
@@ -768,8 +986,20 @@ static int aligns_end_at_mult_nodes(const g1* g, const naln* a, int max_node, in
     {
         int found = 0;
         size_t tot = (size_t)g->len[n] * L;
-        for (size_t x = 0; x < tot && !found; ++x)
-            found = a[n].mH[x] == top;
+        if (a[n].is_byte)
+        {
+            for (size_t x = 0; x < tot && !found; ++x)
+                found = a[n].mH[x] == top;
+        }
+        else
+        {
+            for (size_t x = 0; x < tot && !found; ++x)
+            {
+                uint16_t cell = a[n].mH[x >> 1];
+                uint8_t byte = (uint8_t)((x & 1) ? (cell >> 8) : (cell & 0xff));
+                found = byte == top;
+            }
+        }
         cnt += found;
         if (cnt > 1)
             return 1;
@@ -824,8 +1054,8 @@ static int align_string(const g1* g, const char* str, int L, gmap* gm, int* mult
     return PGO_OK;
 }
 
-int pgo_fill_trace(const pgo_graph* G, int reversed_graph, const char* read, int L, int32_t* node_stats, uint8_t* mats,
-                   int32_t* res3, int32_t* multi, char* cigar, int cigar_cap)
+static int fill_trace_impl(const pgo_graph* G, int reversed_graph, const char* read, int L, int32_t* node_stats,
+                           uint8_t* mats8, uint16_t* mats16, int32_t* res3, int32_t* multi, char* cigar, int cigar_cap)
 {
     const g1* g = reversed_graph ? &G->rev : &G->fwd;
     naln* a = NULL;
@@ -842,15 +1072,18 @@ int pgo_fill_trace(const pgo_graph* G, int reversed_graph, const char* read, int
         node_stats[4 * i + 0] = a[i].score1;
         node_stats[4 * i + 1] = a[i].ref_end1;
         node_stats[4 * i + 2] = a[i].read_end1;
-        node_stats[4 * i + 3] = 1;
-        if (mats)
-        {
-            size_t sz = (size_t)g->len[i] * L;
-            memcpy(mats + off, a[i].mH, sz);
-            memcpy(mats + off + sz, a[i].mE, sz);
-            memcpy(mats + off + 2 * sz, a[i].mF, sz);
-            off += 3 * sz;
-        }
+        node_stats[4 * i + 3] = a[i].is_byte;
+        size_t sz = (size_t)g->len[i] * L;
+        const uint16_t* m3[3] = { a[i].mH, a[i].mE, a[i].mF };
+        for (int k = 0; k < 3; ++k)
+            for (size_t x = 0; x < sz; ++x)
+            {
+                if (mats8 && a[i].is_byte)
+                    mats8[off + k * sz + x] = (uint8_t)m3[k][x];
+                if (mats16)
+                    mats16[off + k * sz + x] = m3[k][x];
+            }
+        off += 3 * sz;
     }
     gmap gm;
     graph_trace_back(g, a, max_node, read, L, &gm);
@@ -863,6 +1096,18 @@ int pgo_fill_trace(const pgo_graph* G, int reversed_graph, const char* read, int
     gmap_free(&gm);
     naln_free(a, g->n);
     return rc;
+}
+
+int pgo_fill_trace(const pgo_graph* G, int reversed_graph, const char* read, int L, int32_t* node_stats, uint8_t* mats,
+                   int32_t* res3, int32_t* multi, char* cigar, int cigar_cap)
+{
+    return fill_trace_impl(G, reversed_graph, read, L, node_stats, mats, NULL, res3, multi, cigar, cigar_cap);
+}
+
+int pgo_fill_trace16(const pgo_graph* G, int reversed_graph, const char* read, int L, int32_t* node_stats,
+                     uint16_t* mats, int32_t* res3, int32_t* multi, char* cigar, int cigar_cap)
+{
+    return fill_trace_impl(G, reversed_graph, read, L, node_stats, NULL, mats, res3, multi, cigar, cigar_cap);
 }
 
 static char complement_base(char b) /* graph-tools src/graphutils/SequenceOperations.cpp:66-81 (case-sensitive) */

@@ -22,7 +22,7 @@ extern "C" {
 #define PGO_AF_ALL 0xFFFFFFFFu
 
 #define PGO_OK 0
-#define PGO_E_BYTE_OVERFLOW (-2) /* reference would fall back to 16-bit mode (gssw.c:4001-4013) */
+#define PGO_E_BYTE_OVERFLOW (-2) /* no longer returned: the 16-bit fallback (gssw.c:4001-4013) is restated */
 #define PGO_E_ARG (-1)
 
 typedef struct pgo_graph pgo_graph;
@@ -45,11 +45,16 @@ int pgo_align_batch(const pgo_graph* g, int n_reads, const char* bases_blob, con
                     int cigar_stride);
 
 /* One gssw_graph_fill + gssw_graph_trace_back on the forward (reversed_graph=0) or reversed
- * graph.  `read` must already be upper-case.  node_stats[4*n] = {score1, ref_end1, read_end1, 1};
- * mats (may be NULL) = per node mH,mE,mF (len*L bytes each); res3 = {max_node, position, score};
+ * graph.  `read` must already be upper-case.  node_stats[4*n] = {score1, ref_end1, read_end1, is_byte};
+ * mats (may be NULL) = per node mH,mE,mF (len*L bytes each; filled in byte mode only); res3 = {max_node, position, score};
  * multi (may be NULL) receives alignsEndAtMultNodes (GraphAligner.cpp:170-212). */
 int pgo_fill_trace(const pgo_graph* g, int reversed_graph, const char* read, int L, int32_t* node_stats,
                    uint8_t* mats, int32_t* res3, int32_t* multi, char* cigar, int cigar_cap);
+
+/* Same with 16-bit matrices: valid in both modes.  node_stats[4*n+3] = is_byte (0 after the reference's fallback to
+ * 16-bit mode, which happens when a score reaches 251: gssw.c:380, 467, 4001-4013). */
+int pgo_fill_trace16(const pgo_graph* g, int reversed_graph, const char* read, int L, int32_t* node_stats,
+                     uint16_t* mats, int32_t* res3, int32_t* multi, char* cigar, int cigar_cap);
 
 /* readfilters::BadAlign on a graph CIGAR string (BadAlign.hh:62-73); NonUniq is simply !unique (NonUniq.hh:48-52) */
 int pgo_bad_align(const char* cigar, double bad_align_frac, int* clipped_out);

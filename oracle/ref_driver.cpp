@@ -237,10 +237,12 @@ void pgref_gssw_destroy(void* hv)
 
 // Fill + traceback one (already upper-cased) read.  Outputs:
 //   node_stats[4*n] = {score1, ref_end1, read_end1, is_byte} per node
-//   mats: if non-NULL, concatenated per node: mH[len*L], mE[len*L], mF[len*L]  (bytes; byte mode only)
+//   mats8 : if non-NULL, concatenated per node: mH[len*L], mE[len*L], mF[len*L]  (bytes; byte mode only)
+//   mats16: if non-NULL, the same cells widened to 16 bits (byte mode) or copied (word mode, after gssw's fallback)
 //   res3 = {max_node_id, position, score}; cigar string "id[..]id[..]"
-int pgref_gssw_fill_trace(
-    void* hv, const char* read, int32_t* node_stats, uint8_t* mats, int32_t* res3, char* cigar, int cigar_cap)
+static int fillTrace(
+    void* hv, const char* read, int32_t* node_stats, uint8_t* mats8, uint16_t* mats16, int32_t* res3, char* cigar,
+    int cigar_cap)
 {
     auto* h = static_cast<RefGssw*>(hv);
     int L = static_cast<int>(strlen(read));
@@ -253,14 +255,21 @@ int pgref_gssw_fill_trace(
         node_stats[4 * i + 1] = a->ref_end1;
         node_stats[4 * i + 2] = a->read_end1;
         node_stats[4 * i + 3] = a->is_byte;
-        if (mats && a->is_byte)
+        size_t sz = static_cast<size_t>(h->nodes[i]->len) * L;
+        const void* m3[3] = { a->mH, a->mE, a->mF };
+        if (mats8 && a->is_byte)
         {
-            size_t sz = static_cast<size_t>(h->nodes[i]->len) * L;
-            memcpy(mats + off, a->mH, sz);
-            memcpy(mats + off + sz, a->mE, sz);
-            memcpy(mats + off + 2 * sz, a->mF, sz);
-            off += 3 * sz;
+            for (int k = 0; k < 3; ++k)
+                memcpy(mats8 + off + k * sz, m3[k], sz);
         }
+        if (mats16)
+        {
+            for (int k = 0; k < 3; ++k)
+                for (size_t x = 0; x < sz; ++x)
+                    mats16[off + k * sz + x] = a->is_byte ? static_cast<const uint8_t*>(m3[k])[x]
+                                                          : static_cast<const uint16_t*>(m3[k])[x];
+        }
+        off += 3 * sz;
     }
     gssw_graph_mapping* gm = gssw_graph_trace_back(h->g, read, L, h->nt, h->mat, 6, 1);
     res3[0] = static_cast<int32_t>(h->g->max_node->id);
@@ -283,5 +292,17 @@ int pgref_gssw_fill_trace(
         cigar[n] = 0;
     }
     return static_cast<int>(s.size());
+}
+
+int pgref_gssw_fill_trace(
+    void* hv, const char* read, int32_t* node_stats, uint8_t* mats, int32_t* res3, char* cigar, int cigar_cap)
+{
+    return fillTrace(hv, read, node_stats, mats, nullptr, res3, cigar, cigar_cap);
+}
+
+int pgref_gssw_fill_trace16(
+    void* hv, const char* read, int32_t* node_stats, uint16_t* mats, int32_t* res3, char* cigar, int cigar_cap)
+{
+    return fillTrace(hv, read, node_stats, nullptr, mats, res3, cigar, cigar_cap);
 }
 }

@@ -14,7 +14,7 @@ REF_SO = os.path.join(HERE, "_ref", "libpgref.so")
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 
 AF_CIGAR, AF_BOTH_STRANDS, AF_REVERSE_GRAPH, AF_ALL = 1, 2, 4, 0xFFFFFFFF
-CIGAR_STRIDE = 1024
+CIGAR_STRIDE = 4096
 
 
 def build(ref=True):
@@ -71,6 +71,9 @@ def ref_lib():
         lib.pgref_gssw_fill_trace.restype = C.c_int
         lib.pgref_gssw_fill_trace.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8),
                                               C.POINTER(C.c_int32), C.c_char_p, C.c_int]
+        lib.pgref_gssw_fill_trace16.restype = C.c_int
+        lib.pgref_gssw_fill_trace16.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint16),
+                                                C.POINTER(C.c_int32), C.c_char_p, C.c_int]
         _ref = lib
     return _ref
 
@@ -111,16 +114,21 @@ class RefGssw:
         self.h = self.lib.pgref_gssw_create(len(node_seqs), blob, _p(off, C.c_int32), len(edges),
                                             _p(ef, C.c_int32), _p(et, C.c_int32))
 
-    def fill_trace(self, read, want_mats=True):
+    def fill_trace(self, read, want_mats=True, wide=False):
+        """wide: 16-bit matrices, valid in gssw's byte and word mode alike (stats[:, 3] = is_byte)."""
         L = len(read)
         n = len(self.node_seqs)
         stats = np.zeros((n, 4), dtype=np.int32)
         tot = sum(len(s) for s in self.node_seqs) * L * 3
-        mats = np.zeros(max(1, tot), dtype=np.uint8) if want_mats else None
+        mats = np.zeros(max(1, tot), dtype=np.uint16 if wide else np.uint8) if want_mats else None
         res = np.zeros(3, dtype=np.int32)
-        cg = C.create_string_buffer(4096)
-        self.lib.pgref_gssw_fill_trace(self.h, read.encode("latin-1"), _p(stats, C.c_int32),
-                                       _p(mats, C.c_uint8) if want_mats else None, _p(res, C.c_int32), cg, 4096)
+        cg = C.create_string_buffer(8192)
+        if wide:
+            self.lib.pgref_gssw_fill_trace16(self.h, read.encode("latin-1"), _p(stats, C.c_int32),
+                                             _p(mats, C.c_uint16) if want_mats else None, _p(res, C.c_int32), cg, 8192)
+        else:
+            self.lib.pgref_gssw_fill_trace(self.h, read.encode("latin-1"), _p(stats, C.c_int32),
+                                           _p(mats, C.c_uint8) if want_mats else None, _p(res, C.c_int32), cg, 8192)
         out = dict(stats=stats, max_node=int(res[0]), pos=int(res[1]), score=int(res[2]), cigar=cg.value.decode())
         if want_mats:
             ms, o = [], 0
@@ -164,6 +172,10 @@ def oracle_lib():
         lib.pgo_fill_trace.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                        C.c_char_p, C.c_int]
+        lib.pgo_fill_trace16.restype = C.c_int
+        lib.pgo_fill_trace16.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_uint16), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                         C.c_char_p, C.c_int]
         lib.pgo_set_fill_variant.argtypes = [C.c_int]
         _orc = lib
     return _orc
@@ -212,19 +224,20 @@ class OracleGraph:
             res.append(_result_dict(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
         return res
 
-    def fill_trace(self, read, reversed_graph=False, want_mats=True):
+    def fill_trace(self, read, reversed_graph=False, want_mats=True, wide=False):
         L = len(read)
         seqs = self.node_seqs[::-1] if reversed_graph else self.node_seqs
         n = len(seqs)
         stats = np.zeros((n, 4), dtype=np.int32)
         tot = sum(len(s) for s in seqs) * L * 3
-        mats = np.zeros(max(1, tot), dtype=np.uint8) if want_mats else None
+        mats = np.zeros(max(1, tot), dtype=np.uint16 if wide else np.uint8) if want_mats else None
         res = np.zeros(3, dtype=np.int32)
         multi = np.zeros(1, dtype=np.int32)
-        cg = C.create_string_buffer(4096)
-        rc = self.lib.pgo_fill_trace(self.h, 1 if reversed_graph else 0, read.encode("latin-1"), L,
-                                     _p(stats, C.c_int32), _p(mats, C.c_uint8) if want_mats else None,
-                                     _p(res, C.c_int32), _p(multi, C.c_int32), cg, 4096)
+        cg = C.create_string_buffer(8192)
+        fn, ct = (self.lib.pgo_fill_trace16, C.c_uint16) if wide else (self.lib.pgo_fill_trace, C.c_uint8)
+        rc = fn(self.h, 1 if reversed_graph else 0, read.encode("latin-1"), L,
+                _p(stats, C.c_int32), _p(mats, ct) if want_mats else None,
+                _p(res, C.c_int32), _p(multi, C.c_int32), cg, 8192)
         if rc < 0:
             raise RuntimeError("oracle: pgo_fill_trace rc=%d" % rc)
         out = dict(stats=stats, max_node=int(res[0]), pos=int(res[1]), score=int(res[2]), multi=bool(multi[0]),

@@ -206,47 +206,96 @@ template <int R> PG_HD void lane_zero(Lane<R>& s)
     }
     s.hupPrev = 0;
     s.hbotLast = 0;
-    s.foutLast = 0;
+    s.foutLast = pk(-1, -1); // no insertion running (any F <= 0 is equivalent; negative lets lazy-F skip)
 }
 
 // One wavefront step of one lane.  recvH/recvF = hbotLast/foutLast of lane t-1 after ITS previous step
-// (zeros for lane 0).  prof = this warp's profile, word (c*R + r)*32 + lane = packed score of column code c
-// against this lane's row r.  If KEEP, the values the traceback needs are returned per row:
-// Hc = H(i,j), Ec = E(i,j) as used for H (gssw mE), Fc = F(i,j) as used for H (gssw mF).
-// Returns max over this lane's rows of t (== max of H: an F-derived H never sets a maximum).
+// (zero / any value <= 0 for lane 0).  pf(r) = packed substitution score of the step's column code against this
+// lane's row r.  If KEEP, the values the traceback needs are returned per row:
+// Hc = H(i,j), Ec = E(i,j) as used for H (gssw mE), Fc = F(i,j) as used for H (gssw mF; <= 0 when not live).
+// Returns max over this lane's rows of t - GAP_OPEN (MBIAS below: the node maxima are tracked with that offset; max t
+// == max H since an F-derived H never sets a maximum).
+//
+// Two passes.  Pass 1: t, E' and the lane maximum for the R rows.  Pass 2: the F chain down the rows, H = max(t, F),
+// F' = max(F - ge, t - go).  With LAZY, pass 2 is skipped when it cannot change anything: every t - go of the step
+// is negative and the incoming F is negative -- then H = t in every row and the outgoing F is negative too (any
+// negative F is as good as another: H >= 0 always wins and F only decays or is replaced by a t - go).  Away from a
+// real alignment, i.e. in most columns of the graph, that is the common case.  On the device the decision is taken
+// per warp (vote) so that the skip is a uniform branch.
+#ifndef PG_LAZY_F
+#define PG_LAZY_F 0
+#endif
+constexpr int MBIAS = GAP_OPEN; // offset of the tracked maxima: Mnode = max(t) - MBIAS, "no score yet" = -MBIAS
+template <int W> struct ProfPtr // profile row accessor: plain pointer (host emulator, traceback kernel)
+{
+    const uint32_t* p;
+    PG_HD uint32_t operator()(int r) const { return p[r * W]; }
+};
+PG_HD bool warp_any(bool x)
+{
+#if defined(__CUDA_ARCH__)
+    return __any_sync(0xffffffffu, x);
+#else
+    return x; // the emulator steps lane by lane: a per-lane decision is exact as well
+#endif
+}
+
+template <int R, bool KEEP, bool LAZY, class PF>
+PG_HD uint32_t lane_step_pf(Lane<R>& s, uint32_t recvH, uint32_t recvF, const PF& pf, uint32_t* Hc, uint32_t* Ec,
+                            uint32_t* Fc)
+{
+    const uint32_t mGO = pk(-GAP_OPEN, -GAP_OPEN), mGE = pk(-GAP_EXT, -GAP_EXT);
+    uint32_t d = s.hupPrev; // diagonal for row 0
+    s.hupPrev = recvH;
+    uint32_t tg[R];
+    uint32_t mg = mGO;
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+    {
+        const uint32_t sc = pf(r);
+        const uint32_t e = s.E[r];
+        const uint32_t t = addmax_relu2(d, sc, e);
+        tg[r] = add2(t, mGO);
+        if (KEEP)
+            Ec[r] = e;
+        s.E[r] = addmax2(e, mGE, tg[r]);
+        d = s.Hp[r];
+        s.Hp[r] = t;
+        mg = max2(mg, tg[r]);
+    }
+    bool need = true;
+    if (LAZY) // both halves of max(t - go, F in) negative in every lane: nothing for the F chain to do
+        need = warp_any((~max2(mg, recvF) & 0x80008000u) != 0u);
+    if (need)
+    {
+        uint32_t F = recvF;
+PG_UNROLL
+        for (int r = 0; r < R; ++r)
+        {
+            const uint32_t h = max2(s.Hp[r], F);
+            if (KEEP)
+            {
+                Hc[r] = h;
+                Fc[r] = F;
+            }
+            s.Hp[r] = h;
+            F = addmax2(F, mGE, tg[r]);
+        }
+        s.foutLast = F;
+    }
+    else
+        s.foutLast = mGE;
+    s.hbotLast = s.Hp[R - 1];
+    return mg;
+}
+
+// prof = this group's profile, word (c*R + r)*W + lane = packed score of column code c against this lane's row r.
 template <int R, bool KEEP, int W = 32>
 PG_HD uint32_t lane_step(Lane<R>& s, uint32_t recvH, uint32_t recvF, const uint32_t* prof, int code, int lane,
                          uint32_t* Hc, uint32_t* Ec, uint32_t* Fc)
 {
-    const uint32_t mGO = pk(-GAP_OPEN, -GAP_OPEN), mGE = pk(-GAP_EXT, -GAP_EXT);
-    const uint32_t* p = prof + (code * R) * W + lane;
-    uint32_t d = s.hupPrev; // diagonal for row 0
-    s.hupPrev = recvH;
-    uint32_t F = recvF;
-    uint32_t m = 0;
-PG_UNROLL
-    for (int r = 0; r < R; ++r)
-    {
-        const uint32_t sc = p[r * W];
-        const uint32_t e = s.E[r];
-        const uint32_t t = addmax_relu2(d, sc, e);
-        const uint32_t tg = add2(t, mGO);
-        const uint32_t h = max2(t, F);
-        if (KEEP)
-        {
-            Hc[r] = h;
-            Ec[r] = e;
-            Fc[r] = F;
-        }
-        s.E[r] = addmax2(e, mGE, tg);
-        F = addmax2(F, mGE, tg);
-        d = s.Hp[r];
-        s.Hp[r] = h;
-        m = max2(m, t);
-    }
-    s.hbotLast = s.Hp[R - 1];
-    s.foutLast = F;
-    return m;
+    const ProfPtr<W> pf = { prof + (code * R) * W + lane };
+    return lane_step_pf<R, KEEP, (PG_LAZY_F != 0) && !KEEP>(s, recvH, recvF, pf, Hc, Ec, Fc);
 }
 
 // Build this lane's part of the warp profile: rows [R*lane, R*lane+R) x 6 column codes, both halves.
@@ -280,7 +329,7 @@ struct LaneCtl
 {
     int node;      // node the lane is currently in (n_nodes once past the end)
     int colsLeft;  // columns of that node still to process, counted at the top of a step (0 -> node just ended)
-    uint32_t Mnode; // packed maximum of t over this lane's rows within the current node
+    uint32_t Mnode; // packed maximum of t - MBIAS over this lane's rows within the current node
     int first[2];  // wavefront step at which Mnode's half first reached its current value
 };
 
@@ -288,7 +337,7 @@ struct LaneCtl
 PG_HD void ctl_at_step(LaneCtl& c, const GraphView& g, int k0, int lane)
 {
     const int q = k0 - lane; // column about to be processed
-    c.Mnode = 0;
+    c.Mnode = pk(-MBIAS, -MBIAS);
     c.first[0] = c.first[1] = 0;
     if (q <= 0)
     {
@@ -353,7 +402,7 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
             infoS[(n * 3 + 0) * W + lane] = c.Mnode;
             infoS[(n * 3 + 1) * W + lane] = (uint32_t)c.first[0];
             infoS[(n * 3 + 2) * W + lane] = (uint32_t)c.first[1];
-            c.Mnode = 0;
+            c.Mnode = pk(-MBIAS, -MBIAS);
         }
         c.node = n + 1;
         if (n + 1 < g.n_nodes)
@@ -514,7 +563,7 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W)
         for (int n = 0; n < n_nodes; ++n)
             for (int t = 0; t < W; ++t)
             {
-                const int v = half16(ld_scratch(info + (n * 3 + 0) * W + t), h);
+                const int v = half16(ld_scratch(info + (n * 3 + 0) * W + t), h) + MBIAS;
                 if (v > S)
                     S = v;
             }
@@ -524,7 +573,7 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W)
             bool has = false;
             for (int t = 0; t < W; ++t)
             {
-                if (half16(ld_scratch(info + (n * 3 + 0) * W + t), h) != S)
+                if (half16(ld_scratch(info + (n * 3 + 0) * W + t), h) + MBIAS != S)
                     continue;
                 has = true;
                 if (mnode == -1 || mnode == n)

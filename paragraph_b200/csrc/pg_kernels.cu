@@ -38,7 +38,16 @@ namespace
 #ifndef PG_FILL_UNROLL
 #define PG_FILL_UNROLL 4
 #endif
+#ifndef PG_FAST_UNROLL
+#define PG_FAST_UNROLL 4
+#endif
+#ifndef PG_FAST_BLOCKS
+#define PG_FAST_BLOCKS 1
+#endif
 constexpr int FILL_UNROLL = PG_FILL_UNROLL;
+constexpr int FAST_UNROLL = PG_FAST_UNROLL;   // unroll of the boundary-free block of the fill kernel
+constexpr bool FAST_BLOCKS = PG_FAST_BLOCKS != 0;
+constexpr bool FILL_LAZY_F = PG_LAZY_F != 0;
 constexpr int FILL_WARPS = PG_FILL_WARPS;   // warps per CTA, fill kernel
 constexpr int TRACE_WARPS = PG_TRACE_WARPS; // warps per CTA, traceback kernel
 constexpr unsigned FULL = 0xffffffffu;
@@ -104,6 +113,74 @@ __device__ __forceinline__ void tma_wait(uint64_t* bar)
                      : "=r"(done)
                      : "r"(bar_s)
                      : "memory");
+}
+
+// Profile row accessor of the fill kernel: 32-bit shared-window address of (code row block, this lane); the R loads
+// of a step are LDS with immediate offsets.
+template <int W> struct ProfSmem
+{
+    uint32_t a;
+    __device__ __forceinline__ uint32_t operator()(int r) const
+    {
+        uint32_t v;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a + (uint32_t)(r * W * 4)));
+        return v;
+    }
+};
+
+// finalize_task (pg_core.cuh, the serial statement used by the emulator) as W-lane group reductions: every lane scans
+// its own column of the [node][3][W] table, four min / max reductions per packed half give the global maximum, the
+// first node holding it, whether a second node holds it, and the earliest cell (column, then lane) in the first.
+template <int W> __device__ __forceinline__ int group_min(int v)
+{
+#pragma unroll
+    for (int d = W / 2; d > 0; d >>= 1)
+        v = min(v, __shfl_xor_sync(FULL, v, d, W));
+    return v;
+}
+template <int W> __device__ __forceinline__ void finalize_task_group(const uint32_t* info, int n_nodes, int gl, TaskOut& o)
+{
+    constexpr int INF = 0x7fffffff;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+        int S = 0;
+        for (int n = 0; n < n_nodes; ++n)
+            S = max(S, half16(info[(n * 3 + 0) * W + gl], h) + MBIAS);
+        S = -group_min<W>(-S);
+        int first = INF;
+        for (int n = n_nodes - 1; n >= 0; --n)
+            if (half16(info[(n * 3 + 0) * W + gl], h) + MBIAS == S)
+                first = n;
+        const int mnode = group_min<W>(first);
+        int second = INF, key = INF;
+        if (mnode != INF)
+        {
+            for (int n = n_nodes - 1; n > mnode; --n)
+                if (half16(info[(n * 3 + 0) * W + gl], h) + MBIAS == S)
+                    second = n;
+            if (half16(info[(mnode * 3 + 0) * W + gl], h) + MBIAS == S)
+                key = (((int)info[(mnode * 3 + 1 + h) * W + gl] - gl) << 5) | gl; // (column, lane): W <= 32
+        }
+        second = group_min<W>(second);
+        key = group_min<W>(key);
+        o.score[h] = S;
+        o.n_top[h] = (mnode == INF) ? 0 : (second == INF ? 1 : 2);
+        if (S == 0 || mnode == INF)
+        {
+            // every real cell is 0: gssw leaves ref_end = -1 -> empty CIGAR, position 0 (gssw.c:2728-2732)
+            o.n_top[h] = min(n_nodes, 2);
+            o.max_node[h] = -1;
+            o.end_step[h] = 0;
+            o.end_lane[h] = 0;
+        }
+        else
+        {
+            o.max_node[h] = mnode;
+            o.end_lane[h] = key & 31;
+            o.end_step[h] = (key >> 5) + (key & 31);
+        }
+    }
 }
 
 // STAGED: the task's column codes are TMA-staged into shared memory (graphs up to 16 KB); otherwise they are read
@@ -172,13 +249,40 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     if (NT > 1) // groups of one warp may belong to different sites: run to the longest, the others idle on sentinels
         for (int d = W; d < 32; d <<= 1)
             nck = max(nck, __shfl_xor_sync(FULL, nck, d));
+    // this lane's column of the profile as a shared-window address: one IMAD per step selects the code's rows
+    const uint32_t NO_F = pk(-1, -1); // "no insertion running into lane 0": any F <= 0 will do, negative lets lazy-F skip
+    const ProfSmem<W> pf0 = { (uint32_t)__cvta_generic_to_shared(prof + gl) };
     for (int cki = 0; cki < nck; ++cki)
     {
-        const bool live = cki < my_nck;
+        const bool live = (NT == 1) || cki < my_nck;
         if (save && live)
             ckpt_store<R, W>(s, ckpt + (size_t)cki * (R + 1) * W, gl);
         const int kbase = cki * CK;
         const uint8_t* cp = codes + kbase; // per-lane pointer, immediate offsets inside the unrolled body
+        // Node boundaries are rare (a few per lane and task) but testing for them costs every step a counter, a
+        // branch with its reconvergence point, a warp barrier and the register shuffling of the merge.  So: when no
+        // lane of the warp meets a boundary within this block of CK steps (warp-uniform test), run the block
+        // straight-line.
+        if (FAST_BLOCKS && __all_sync(FULL, c.colsLeft >= CK))
+        {
+#pragma unroll FAST_UNROLL
+            for (int kk = 0; kk < CK; ++kk)
+            {
+                uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
+                uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
+                if (gl == 0)
+                {
+                    rh = 0;
+                    rf = NO_F;
+                }
+                const int code = live ? cp[kk] : 5;
+                const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
+                const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr);
+                track_max(c, m, kbase + kk);
+            }
+            c.colsLeft -= CK;
+            continue;
+        }
 #pragma unroll FILL_UNROLL
         for (int kk = 0; kk < CK; ++kk)
         {
@@ -193,10 +297,11 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
             if (gl == 0)
             {
                 rh = 0;
-                rf = 0;
+                rf = NO_F;
             }
             const int code = live ? cp[kk] : 5;
-            const uint32_t m = lane_step<R, false, W>(s, rh, rf, prof, code, gl, nullptr, nullptr, nullptr);
+            const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
+            const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr);
             track_max(c, m, k);
         }
     }
@@ -204,12 +309,10 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     if (save) // node last columns for the traceback kernel: one coalesced copy of the seed table
         for (int x = gl; x < g.n_nodes * 2 * R * W; x += W)
             last[x] = seedS[x];
+    TaskOut t;
+    finalize_task_group<W>(infoS, g.n_nodes, gl, t); // every lane of the warp takes part (group-wide reductions)
     if (active && gl == 0)
-    {
-        TaskOut t;
-        finalize_task(infoS, g.n_nodes, t, W);
         *to = t;
-    }
 }
 
 struct TraceArgs

@@ -51,7 +51,7 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
         for (int t = 0; t < W; ++t)
         {
             rh[t] = t ? s[t - 1].hbotLast : 0;
-            rf[t] = t ? s[t - 1].foutLast : 0;
+            rf[t] = t ? s[t - 1].foutLast : pk(-1, -1);
         }
         for (int t = 0; t < W; ++t)
         {
@@ -88,7 +88,7 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
         for (int t = 0; t < W; ++t)
         {
             rh[t] = t ? s[t - 1].hbotLast : 0;
-            rf[t] = t ? s[t - 1].foutLast : 0;
+            rf[t] = t ? s[t - 1].foutLast : pk(-1, -1);
         }
         for (int t = 0; t < W; ++t)
         {

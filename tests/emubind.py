@@ -12,7 +12,7 @@ SO = os.path.join(HERE, "emu", "libpgemu.so")
 SRC = [os.path.join(HERE, "emu", "pg_emu.cpp"), os.path.join(ROOT, "paragraph_b200", "csrc", "pg_core.cuh"),
        os.path.join(ROOT, "paragraph_b200", "csrc", "pg_host.hpp"),
        os.path.join(ROOT, "paragraph_b200", "csrc", "pg_count.cuh")]
-CIGAR_STRIDE = 1024
+CIGAR_STRIDE = 4096
 _lib = None
 
 

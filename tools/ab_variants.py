@@ -4,11 +4,12 @@ import os, subprocess, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 OUT = os.path.join(ROOT, "ab_build")
 VARIANTS = {
-    "base": [],
-    "ck32": ["-DPG_CK=32"],
-    "ck8": ["-DPG_CK=8"],
-    "ck32tw4": ["-DPG_CK=32", "-DPG_TRACE_WARPS=4"],
-    "tw1": ["-DPG_TRACE_WARPS=1"],
+    "noopt": ["-DPG_FAST_BLOCKS=0", "-DPG_LAZY_F=0"],
+    "fast": ["-DPG_FAST_BLOCKS=1", "-DPG_LAZY_F=0"],
+    "fast_lazy": ["-DPG_FAST_BLOCKS=1", "-DPG_LAZY_F=1"],
+    "fast_lazy_u8": ["-DPG_FAST_BLOCKS=1", "-DPG_LAZY_F=1", "-DPG_FAST_UNROLL=8"],
+    "fast_u8": ["-DPG_FAST_BLOCKS=1", "-DPG_LAZY_F=0", "-DPG_FAST_UNROLL=8"],
+    "lazy": ["-DPG_FAST_BLOCKS=0", "-DPG_LAZY_F=1"],
 }
 def build():
     os.makedirs(OUT, exist_ok=True)
@@ -32,7 +33,13 @@ ts = []
 for _ in range(6):
     ctx.align_packed(blob, off); s = ctx.stats(); ts.append((s["fill_ms"], s["trace_ms"]))
 f = min(t[0] for t in ts); t = min(t[1] for t in ts)
-print("%%-6s W=%%s fill %%.3f trace %%.3f total %%.3f ms" %% (os.environ["PG_VARIANT"], os.environ.get("PG_GEOM_W","32"), f, t, f+t), flush=True)
+import hashlib
+rec, ops = ctx.align_packed(blob, off)
+h = hashlib.sha1()
+for x in rec:
+    h.update(repr(tuple(int(x[f]) for f in ("graph_pos", "score", "unique", "chose_reverse", "status", "query_clipped"))).encode())
+    h.update(ops[int(x["cigar_off"]):int(x["cigar_off"]) + int(x["cigar_len"])].tobytes())
+print("%%-9s W=%%s fill %%.3f trace %%.3f total %%.3f ms  digest %%s" %% (os.environ["PG_VARIANT"], os.environ.get("PG_GEOM_W","32"), f, t, f+t, h.hexdigest()[:12]), flush=True)
 ''' % ROOT
     for name in VARIANTS:
         for w in ["32"]:
