@@ -26,9 +26,10 @@ extern "C" {
 #define PG_E_CAPACITY (-5) /* caller's cigar arena too small */
 #define PG_E_STATE (-6)    /* call order (e.g. run before upload) */
 
-/* Reads longer than this leave gssw's 8-bit mode (external/gssw/gssw.c:380, :4001-4013) whose 16-bit
- * fallback has different tie behaviour; they are rejected rather than answered differently. */
-#define PG_MAX_READ_LEN 250
+/* Longest read (16 rows per lane x 32 lanes).  Reads whose score reaches 251 take gssw's 16-bit mode in the
+ * reference (external/gssw/gssw.c:380, 527-786, 4001-4013); results stay bit-identical, including what
+ * GraphAligner's uniqueness scan makes of a 16-bit matrix (src/c++/lib/grm/GraphAligner.cpp:177-186). */
+#define PG_MAX_READ_LEN 512
 
 /* GraphAligner alignment flags (src/c++/include/grm/GraphAligner.hh:64-67) */
 #define PG_AF_CIGAR 0x01u
@@ -46,13 +47,14 @@ typedef struct pg_ctx pg_ctx;
 typedef struct pg_record
 {
     int32_t graph_pos;
-    int32_t score;
+    int16_t score;          /* gssw_graph_mapping::score is an int16_t as well */
+    uint16_t query_clipped; /* soft-clipped query bases = sum of the S ops; readfilters::BadAlign
+                               (src/c++/lib/paragraph/readfilters/BadAlign.hh:62-73) filters a read when
+                               read_len - query_clipped < round(bad_align_frac * read_len) -- no CIGAR decode needed */
     uint8_t unique;
     uint8_t chose_reverse;
     uint8_t status; /* 0 ok; 1 traceback dead end (the reference would assert/spin); 2 op log overflow */
-    uint8_t query_clipped; /* soft-clipped query bases = sum of the S ops; readfilters::BadAlign
-                              (src/c++/lib/paragraph/readfilters/BadAlign.hh:62-73) filters a read when
-                              read_len - query_clipped < round(bad_align_frac * read_len) -- no CIGAR decode needed */
+    uint8_t reserved;
     uint32_t cigar_off;
     uint32_t cigar_len;
 } pg_record;

@@ -14,11 +14,12 @@ LIB_PATH = os.path.join(HERE, "libpgalign.so")
 
 PG_OK = 0
 AF_CIGAR, AF_BOTH_STRANDS, AF_REVERSE_GRAPH, AF_ALL = 1, 2, 4, 0xFFFFFFFF
-MAX_READ_LEN = 250
+MAX_READ_LEN = 512
 OPS = "MXNIDS??"
 
-RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i4"), ("unique", "u1"), ("chose_reverse", "u1"),
-                         ("status", "u1"), ("query_clipped", "u1"), ("cigar_off", "<u4"), ("cigar_len", "<u4")])
+RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i2"), ("query_clipped", "<u2"), ("unique", "u1"),
+                         ("chose_reverse", "u1"), ("status", "u1"), ("reserved", "u1"), ("cigar_off", "<u4"),
+                         ("cigar_len", "<u4")])
 
 # every symbol include/pg_align.h declares
 SYMBOLS = ["pg_create", "pg_destroy", "pg_last_error", "pg_set_stream", "pg_set_scratch_limit", "pg_add_graph",

@@ -27,10 +27,12 @@
 #define PG_HD __host__ __device__ __forceinline__
 #define PG_HD_COLD __host__ __device__ __forceinline__
 #define PG_UNROLL _Pragma("unroll")
+#define PG_NOUNROLL _Pragma("unroll 1")
 #else
 #define PG_HD inline
 #define PG_HD_COLD inline
 #define PG_UNROLL
+#define PG_NOUNROLL
 #endif
 
 namespace pg
@@ -45,7 +47,14 @@ constexpr int NEG = -16384; // substitution score of sentinel columns / padded r
 constexpr int CK = PG_CK;   // checkpoint interval = traceback tile size, in wavefront steps
 constexpr int SENT = 32;    // sentinel columns (code 5) before and after every column sequence
 constexpr int NCODE = 6;    // A C G T other sentinel
-constexpr int MAX_READ_LEN = 250; // longer reads leave gssw's 8-bit mode (gssw.c:380) -> rejected, see DESIGN.md
+constexpr int MAX_READ_LEN = 512;  // R = 16 rows per lane x 32 lanes
+// gssw fills in 8-bit mode until a score reaches 251 (score + bias(4) >= 255, gssw.c:380, 467) and then redoes the
+// whole graph in 16-bit mode (gssw.c:4001-4013).  Scores are the same in both modes (this path computes in int16
+// throughout); what changes is GraphAligner's uniqueness scan (finalize_task) and what fits a byte in the scratch
+// layouts: geometries whose reads can exceed BYTE_MAX_SCORE use the WIDE checkpoint / tile-cell packing.
+constexpr int BYTE_MAX_SCORE = 250;
+constexpr int BYTE_MAX_READ_LEN = 250; // longest read a non-WIDE geometry takes
+PG_HD constexpr bool is_wide(int R, int W) { return R * W > 256; }
 
 // ---------------------------------------------------------------------------------------------
 // packed int16x2 arithmetic: DPX on the device, plain C on the host (emulator)
@@ -154,11 +163,26 @@ struct SiteDev
     int32_t codes_off[2]; // byte offset of column 0 (sentinels precede it)
     int32_t chars_off;    // byte offset of the forward graph characters
     int32_t tab_off[2];   // int offset of the orientation's tables
+    int32_t tab_ints;     // ints in one orientation's tables: 3 n_nodes + 1 + distinct edges
 };
 
 // bytes of one orientation's column codes as staged into shared memory: leading sentinels + G + trailing sentinels,
 // rounded up to the 16-byte granularity of cp.async.bulk (pg_host.hpp lays the blob out accordingly)
 PG_HD uint32_t code_span_bytes(int G) { return ((uint32_t)SENT + (uint32_t)G + SENT + CK + 4 + 15u) & ~15u; }
+
+// view over one orientation's int tables t (in HBM, or a copy staged in shared memory)
+PG_HD GraphView make_view_at(const SiteDev& sd, const uint8_t* codes, const int32_t* t)
+{
+    GraphView g;
+    g.codes = codes;
+    g.node_start = t;
+    g.node_len = t + sd.n_nodes;
+    g.pred_ptr = t + 2 * sd.n_nodes;
+    g.pred_idx = t + 3 * sd.n_nodes + 1;
+    g.n_nodes = sd.n_nodes;
+    g.G = sd.G;
+    return g;
+}
 
 PG_HD GraphView make_view(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, int o)
 {
@@ -191,7 +215,10 @@ template <int R> struct Lane
 // (W = 32, 16 or 8: 1, 2 or 4 tasks per warp), each owning R read rows; W * R >= read length.
 template <int R, int W = 32> struct Sizes
 {
-    static constexpr int CKW = R + 1;      // checkpoint words per lane: Hp[R], E[R], hupPrev, foutLast as 4 bytes per word
+    static constexpr bool WIDE = is_wide(R, W);
+    // checkpoint words per lane: Hp[R], E[R], hupPrev, foutLast -- 4 byte values per word, or (WIDE) the 2R+2 packed registers as they are
+    static constexpr int CKW = WIDE ? 2 * R + 2 : R + 1;
+    static constexpr int INFOW = WIDE ? 4 : 3; // words per (node, lane) of the node-maximum table
     static constexpr int LASTW = 2 * R;    // node last column: H[R], E leaving it [R] (= the seed of its successors)
     static constexpr int ROWS = W * R;
     static constexpr int NT = 32 / W;      // tasks per warp
@@ -242,12 +269,13 @@ PG_HD bool warp_any(bool x)
 
 template <int R, bool KEEP, bool LAZY, class PF>
 PG_HD uint32_t lane_step_pf(Lane<R>& s, uint32_t recvH, uint32_t recvF, const PF& pf, uint32_t* Hc, uint32_t* Ec,
-                            uint32_t* Fc)
+                            uint32_t* Fc, uint32_t* TgOut = nullptr)
 {
     const uint32_t mGO = pk(-GAP_OPEN, -GAP_OPEN), mGE = pk(-GAP_EXT, -GAP_EXT);
     uint32_t d = s.hupPrev; // diagonal for row 0
     s.hupPrev = recvH;
-    uint32_t tg[R];
+    uint32_t tgLocal[R];
+    uint32_t* tg = TgOut ? TgOut : tgLocal; // per-row t - go (the WIDE fill looks at them, track_region)
     uint32_t mg = mGO;
 PG_UNROLL
     for (int r = 0; r < R; ++r)
@@ -331,7 +359,20 @@ struct LaneCtl
     int colsLeft;  // columns of that node still to process, counted at the top of a step (0 -> node just ended)
     uint32_t Mnode; // packed maximum of t - MBIAS over this lane's rows within the current node
     int first[2];  // wavefront step at which Mnode's half first reached its current value
+    // WIDE geometries only: the same maximum restricted to the cells GraphAligner's uniqueness scan sees once gssw
+    // is in 16-bit mode (finalize_task): the node's first ceil(len * L / 2) cells in (column, row) order.
+    uint32_t Mreg;
+    int regLeft;   // columns still fully inside that region (0: the next column is the partial one, < 0: past it)
 };
+
+// number of leading columns of a node of length len that lie fully inside the scanned region, and the number of
+// rows of the following column that do (GraphAligner.cpp:177-186 reads len * L BYTES of the int16 matrix)
+PG_HD void scan_region(int len, int L, int& full_cols, int& part_rows)
+{
+    const int cells = (len * L + 1) >> 1;
+    full_cols = cells / L;
+    part_rows = cells - full_cols * L;
+}
 
 // Control state of `lane` at the top of step k0, before the node event of that step has run.
 PG_HD void ctl_at_step(LaneCtl& c, const GraphView& g, int k0, int lane)
@@ -339,6 +380,8 @@ PG_HD void ctl_at_step(LaneCtl& c, const GraphView& g, int k0, int lane)
     const int q = k0 - lane; // column about to be processed
     c.Mnode = pk(-MBIAS, -MBIAS);
     c.first[0] = c.first[1] = 0;
+    c.Mreg = pk(-MBIAS, -MBIAS);
+    c.regLeft = -1; // set by region_begin() in the fill of a WIDE geometry
     if (q <= 0)
     {
         c.node = 0;
@@ -376,6 +419,34 @@ PG_HD void track_max(LaneCtl& c, uint32_t m, int k)
         c.first[1] = k;
 }
 
+// WIDE fill, once per step after lane_step: fold the step into the region-restricted maximum.  tg = the step's
+// per-row t - go (lane_step's optional output), mg their maximum.
+template <int R> PG_HD void track_region(LaneCtl& c, uint32_t mg, const uint32_t* tg, const GraphView& g, int L, int lane)
+{
+    if (c.regLeft > 0)
+    {
+        c.Mreg = max2(c.Mreg, mg);
+        --c.regLeft;
+    }
+    else if (c.regLeft == 0) // the column the region ends in: only its first part_rows rows count
+    {
+        int full, part;
+        scan_region(g.node_len[c.node], L, full, part);
+        for (int r = 0; r < R; ++r)
+            if (R * lane + r < part)
+                c.Mreg = max2(c.Mreg, tg[r]);
+        c.regLeft = -1;
+    }
+}
+// start of the fill (step 0): lane t first runs through t sentinel columns, which count for nothing
+PG_HD void region_begin(LaneCtl& c, const GraphView& g, int L, int lane)
+{
+    int full, part;
+    scan_region(g.node_len[0], L, full, part);
+    c.regLeft = full + lane;
+    c.Mreg = pk(-MBIAS, -MBIAS);
+}
+
 // Node boundary handling at the top of a step (rare, per lane: lanes reach a boundary at different steps).
 //   FILL = true  (fill kernel): save the finished node's last column (H, E leaving it) into the warp-private
 //                shared-memory seed table and the lane's node maximum / first step into infoS; then load the next
@@ -387,8 +458,10 @@ PG_HD void track_max(LaneCtl& c, uint32_t m, int k)
 // simply carries over.  The diagonal into this lane's first row comes from the seed row just above it,
 // i.e. lane-1's last word of each predecessor (written by lane-1 at least one step earlier).
 template <int R, bool FILL, int W = 32>
-PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* seeds, uint32_t* infoS)
+PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* seeds, uint32_t* infoS,
+                           int L = 0)
 {
+    constexpr int IW = Sizes<R, W>::INFOW;
     if (c.colsLeft == 0)
     {
         const int n = c.node;
@@ -399,10 +472,21 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
                 seeds[(n * 2 * R + r) * W + lane] = s.Hp[r];
                 seeds[(n * 2 * R + R + r) * W + lane] = s.E[r];
             }
-            infoS[(n * 3 + 0) * W + lane] = c.Mnode;
-            infoS[(n * 3 + 1) * W + lane] = (uint32_t)c.first[0];
-            infoS[(n * 3 + 2) * W + lane] = (uint32_t)c.first[1];
+            infoS[(n * IW + 0) * W + lane] = c.Mnode;
+            infoS[(n * IW + 1) * W + lane] = (uint32_t)c.first[0];
+            infoS[(n * IW + 2) * W + lane] = (uint32_t)c.first[1];
             c.Mnode = pk(-MBIAS, -MBIAS);
+            if (Sizes<R, W>::WIDE)
+            {
+                infoS[(n * IW + 3) * W + lane] = c.Mreg;
+                c.Mreg = pk(-MBIAS, -MBIAS);
+                c.regLeft = -1;
+                if (n + 1 < g.n_nodes)
+                {
+                    int part;
+                    scan_region(g.node_len[n + 1], L, c.regLeft, part);
+                }
+            }
         }
         c.node = n + 1;
         if (n + 1 < g.n_nodes)
@@ -414,9 +498,10 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
                 uint32_t H[R], E[R], hup = 0;
                 for (int r = 0; r < R; ++r)
                     H[r] = E[r] = 0;
+PG_NOUNROLL
                 for (int e = p0; e < p1; ++e)
                 {
-                    const uint32_t* src = seeds + (size_t)g.pred_idx[e] * 2 * R * W;
+                    const uint32_t* src = seeds + g.pred_idx[e] * (2 * R * W);
                     for (int r = 0; r < R; ++r)
                     {
                         H[r] = max2(H[r], src[r * W + lane]);
@@ -472,14 +557,22 @@ template <int R, int W = 32> PG_HD void ckpt_store(const Lane<R>& s, uint32_t* c
     }
     v[2 * R] = s.hupPrev;
     v[2 * R + 1] = s.foutLast;
-    for (int x = 0; x < R + 1; ++x)
-        ck[x * W + lane] = ck_pack(v[2 * x], v[2 * x + 1]);
+    if (Sizes<R, W>::WIDE) // scores may exceed a byte: keep the packed int16 pairs
+        for (int x = 0; x < 2 * R + 2; ++x)
+            ck[x * W + lane] = v[x];
+    else
+        for (int x = 0; x < R + 1; ++x)
+            ck[x * W + lane] = ck_pack(v[2 * x], v[2 * x + 1]);
 }
 template <int R, int W = 32> PG_HD void ckpt_load(Lane<R>& s, const uint32_t* ck, int lane)
 {
     uint32_t v[2 * R + 2];
-    for (int x = 0; x < R + 1; ++x)
-        ck_unpack(ck[x * W + lane], v[2 * x], v[2 * x + 1]);
+    if (Sizes<R, W>::WIDE)
+        for (int x = 0; x < 2 * R + 2; ++x)
+            v[x] = ck[x * W + lane];
+    else
+        for (int x = 0; x < R + 1; ++x)
+            ck_unpack(ck[x * W + lane], v[2 * x], v[2 * x + 1]);
     for (int r = 0; r < R; ++r)
     {
         s.Hp[r] = v[r];
@@ -502,10 +595,12 @@ template <int R> struct TileGeom
     static constexpr int SLOT_WORDS = CK * BAND_ROWS;
 };
 
-PG_HD uint32_t pack_cell(uint32_t h, uint32_t e, uint32_t f, int half)
+template <bool WIDE> PG_HD uint32_t pack_cell(uint32_t h, uint32_t e, uint32_t f, int half)
 {
     e = max2(e, 0u);
     f = max2(f, 0u);
+    if (WIDE) // 10-bit fields: scores <= MAX_READ_LEN = 512
+        return (uint32_t)half16(h, half) | ((uint32_t)half16(e, half) << 10) | ((uint32_t)half16(f, half) << 20);
 #if defined(__CUDA_ARCH__)
     // bytes: b0 = h.byte(2*half), b1 = e.byte(2*half), b2 = f.byte(2*half), b3 = f.byte(2*half+1) == 0
     const uint32_t s1 = half ? 0x0062u : 0x0040u;
@@ -516,12 +611,12 @@ PG_HD uint32_t pack_cell(uint32_t h, uint32_t e, uint32_t f, int half)
         | ((uint32_t)(half16(f, half) & 0xff) << 16);
 #endif
 }
-PG_HD int cellH(uint32_t w) { return (int)(w & 0xffu); }
-PG_HD int cellE(uint32_t w) { return (int)((w >> 8) & 0xffu); }
-PG_HD int cellF(uint32_t w) { return (int)((w >> 16) & 0xffu); }
+template <bool WIDE> PG_HD int cellH(uint32_t w) { return (int)(WIDE ? (w & 0x3ffu) : (w & 0xffu)); }
+template <bool WIDE> PG_HD int cellE(uint32_t w) { return (int)(WIDE ? ((w >> 10) & 0x3ffu) : ((w >> 8) & 0xffu)); }
+template <bool WIDE> PG_HD int cellF(uint32_t w) { return (int)(WIDE ? ((w >> 20) & 0x3ffu) : ((w >> 16) & 0xffu)); }
 
 // one step of a traceback tile: lanes [blo, blo + BAND_LANES) store their R cells
-template <int R>
+template <int R, bool WIDE = false>
 PG_HD void tile_store(uint32_t* tstep, int lane, int blo, const uint32_t* Hc, const uint32_t* Ec, const uint32_t* Fc,
                       int half)
 {
@@ -529,7 +624,7 @@ PG_HD void tile_store(uint32_t* tstep, int lane, int blo, const uint32_t* Hc, co
     if (bl < 0 || bl >= TileGeom<R>::BAND_LANES)
         return;
     for (int r = 0; r < R; ++r)
-        tstep[R * bl + r] = pack_cell(Hc[r], Ec[r], Fc[r], half);
+        tstep[R * bl + r] = pack_cell<WIDE>(Hc[r], Ec[r], Fc[r], half);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -555,7 +650,14 @@ struct TaskOut // result of one fill (two packed problems)
 // row in that column (gssw.c:378-386, 446-454, 4015-4018) -> min column = min(step - lane), ties -> smaller lane.
 PG_HD uint32_t ld_scratch(const uint32_t* p) { return *p; } // warp-private shared memory (after a __syncwarp)
 
-PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W)
+// Uniqueness (GraphAligner.cpp:170-212): n_top = number of nodes "containing the top score" as the reference's scan
+// sees them.  In 8-bit mode (S <= BYTE_MAX_SCORE) that is the plain count.  Once S >= 251 gssw has redone the graph
+// in 16-bit mode and the scan, which walks len*L BYTES of each node's matrix through a uint8_t*, (a) can never match
+// a top score >= 256 -> no node, "unique"; (b) for 251..255 matches the low byte of the cells in the first half of
+// the node's matrix only -> the count over the region-restricted maxima (LaneCtl::Mreg, info word 3).
+PG_HD int n_top_rule(int S, int plain, int region) { return S <= BYTE_MAX_SCORE ? plain : (S >= 256 ? 1 : region); }
+
+PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W, int IW = 3)
 {
     for (int h = 0; h < 2; ++h)
     {
@@ -563,22 +665,24 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W)
         for (int n = 0; n < n_nodes; ++n)
             for (int t = 0; t < W; ++t)
             {
-                const int v = half16(ld_scratch(info + (n * 3 + 0) * W + t), h) + MBIAS;
+                const int v = half16(ld_scratch(info + (n * IW + 0) * W + t), h) + MBIAS;
                 if (v > S)
                     S = v;
             }
-        int ntop = 0, mnode = -1, bestq = 0x7fffffff, blane = 0, bstep = 0;
+        int ntop = 0, nreg = 0, mnode = -1, bestq = 0x7fffffff, blane = 0, bstep = 0;
         for (int n = 0; n < n_nodes; ++n)
         {
-            bool has = false;
+            bool has = false, hasreg = false;
             for (int t = 0; t < W; ++t)
             {
-                if (half16(ld_scratch(info + (n * 3 + 0) * W + t), h) + MBIAS != S)
+                if (IW > 3 && half16(ld_scratch(info + (n * IW + 3) * W + t), h) + MBIAS == S)
+                    hasreg = true;
+                if (half16(ld_scratch(info + (n * IW + 0) * W + t), h) + MBIAS != S)
                     continue;
                 has = true;
                 if (mnode == -1 || mnode == n)
                 {
-                    const int step = (int)ld_scratch(info + (n * 3 + 1 + h) * W + t);
+                    const int step = (int)ld_scratch(info + (n * IW + 1 + h) * W + t);
                     if (step - t < bestq)
                     {
                         bestq = step - t;
@@ -594,9 +698,11 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W)
                 if (ntop < 2)
                     ++ntop;
             }
+            if (hasreg && nreg < 2)
+                ++nreg;
         }
         o.score[h] = S;
-        o.n_top[h] = ntop;
+        o.n_top[h] = n_top_rule(S, ntop, nreg);
         if (S == 0)
         {
             // every real cell is 0: gssw leaves ref_end = -1 -> empty CIGAR, position 0 (gssw.c:2728-2732)
@@ -654,11 +760,12 @@ PG_HD Decision decide_strand(const TaskOut& fw, const TaskOut& rv, unsigned flag
 struct Record
 {
     int32_t graph_pos;
-    int32_t score;
+    int16_t score;          // gssw_graph_mapping::score is an int16_t too (gssw.h)
+    uint16_t query_clipped; // soft-clipped query bases: what readfilters::BadAlign sums with numClipped() (BadAlign.hh:62-73)
     uint8_t unique;
     uint8_t chose_reverse;
     uint8_t status; // 0 ok, 1 traceback dead end (never seen; the reference would spin/assert), 2 cigar overflow
-    uint8_t query_clipped; // soft-clipped query bases: what readfilters::BadAlign sums with numClipped() (BadAlign.hh:62-73)
+    uint8_t reserved;
     uint32_t cigar_off; // index of the first op in the cigar arena
     uint32_t cigar_len; // number of ops
 };
@@ -799,10 +906,11 @@ PG_HD int match_op(uint8_t refc, uint8_t readc) { return (refc == 'N' || readc =
 // iteration every lane ell probes the cell (i-ell, j-ell): is it an interior cell with positive score whose H equals
 // the diagonal neighbour plus the substitution score (gssw.c:1591-1637)?  The run is the number of leading lanes
 // that say yes; their ops are logged in parallel.  flag: 0 = no, 1 = yes, 2 = a tile the probe needs is not resident.
-template <int R>
+template <int R, int W>
 PG_HD void diag_probe(int ell, const Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars,
                       const uint8_t* bases, int L, int half, int& flag, int& dval, int& op)
 {
+    constexpr bool WD = is_wide(R, W);
     const int ii = w.i - ell, jj = w.j - ell;
     flag = 0;
     dval = 0;
@@ -818,12 +926,12 @@ PG_HD void diag_probe(int ell, const Walker& w, const TileBuf<R>& tb, const Grap
         flag = 2;
         return;
     }
-    const int hv = ell == 0 ? w.v : cellH(*c0);
+    const int hv = ell == 0 ? w.v : cellH<WD>(*c0);
     if (hv <= 0)
         return;
     const uint8_t refc = chars[g.node_start[w.n] + ii];
     const uint8_t readc = read_char(bases, L, 0, half, jj);
-    dval = cellH(*cd);
+    dval = cellH<WD>(*cd);
     op = match_op(refc, readc);
     flag = (hv == dval + sub_score(nt_code(refc), nt_code(readc))) ? 1 : 0;
 }
@@ -841,7 +949,7 @@ PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const ui
     constexpr unsigned WM = (W == 32) ? 0xffffffffu : ((1u << (W & 31)) - 1u);
     const int gshift = __ffs((int)gmask) - 1; // first lane of this group
     int flag, dval, op;
-    diag_probe<R>(lane, w, tb, g, chars, bases, L, half, flag, dval, op);
+    diag_probe<R, W>(lane, w, tb, g, chars, bases, L, half, flag, dval, op);
     const unsigned yes = (__ballot_sync(gmask, flag == 1) >> gshift) & WM;
     run = (yes == WM) ? W : (__ffs((int)~yes) - 1);
     miss0 = (__shfl_sync(gmask, flag, 0, W) == 2);
@@ -868,7 +976,7 @@ PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const ui
     for (int ell = 0; ell < W; ++ell)
     {
         int flag, dval, op;
-        diag_probe<R>(ell, w, tb, g, chars, bases, L, half, flag, dval, op);
+        diag_probe<R, W>(ell, w, tb, g, chars, bases, L, half, flag, dval, op);
         if (ell == 0 && flag == 2)
             miss0 = true;
         if (flag != 1)
@@ -908,6 +1016,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                 const uint8_t* bases, int L, int half, const TaskOut& fo, uint32_t* oplog, int oplog_cap, int lane,
                 unsigned gmask)
 {
+    constexpr bool WD = is_wide(R, W);
     if (w.phase == 0)
     {
         // end cell: smallest row of end_lane holding S at end_step (gssw.c:446-454)
@@ -928,7 +1037,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                 w.need_row = R * fo.end_lane[half] + R - 1;
                 return false;
             }
-            if (cellH(*t0) == S)
+            if (cellH<WD>(*t0) == S)
             {
                 row = R * fo.end_lane[half] + r;
                 break;
@@ -980,7 +1089,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                     w.need_row = w.j;
                     return false;
                 }
-                if (w.v == cellH(*c1) - GAP_OPEN) // gssw.c:1347-1383
+                if (w.v == cellH<WD>(*c1) - GAP_OPEN) // gssw.c:1347-1383
                 {
                     push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
                     w.v += GAP_OPEN;
@@ -988,7 +1097,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                     w.st = 0;
                     continue;
                 }
-                if (w.v == cellE(*c1) - GAP_EXT) // gssw.c:1400-1423
+                if (w.v == cellE<WD>(*c1) - GAP_EXT) // gssw.c:1400-1423
                 {
                     push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
                     w.v += GAP_EXT;
@@ -1010,7 +1119,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                         w.need_row = w.j;
                         return false;
                     }
-                    if (w.v == cellH(*cl) - GAP_OPEN) // gssw.c:1458-1493
+                    if (w.v == cellH<WD>(*cl) - GAP_OPEN) // gssw.c:1458-1493
                     {
                         push_op(w, oplog, oplog_cap, w.n, OP_I, 1);
                         w.v += GAP_OPEN;
@@ -1018,7 +1127,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                         w.st = 0;
                         continue;
                     }
-                    if (w.v == cellF(*cl) - GAP_EXT) // gssw.c:1510-1532
+                    if (w.v == cellF<WD>(*cl) - GAP_EXT) // gssw.c:1510-1532
                     {
                         push_op(w, oplog, oplog_cap, w.n, OP_I, 1);
                         w.v += GAP_EXT;
@@ -1064,12 +1173,12 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                 w.v -= s;
                 continue;
             }
-            if (w.j > 0 && w.v == cellF(*c0)) // H == F, gssw.c:1709-1729
+            if (w.j > 0 && w.v == cellF<WD>(*c0)) // H == F, gssw.c:1709-1729
             {
                 w.st = 2;
                 continue;
             }
-            if (w.v == cellE(*c0)) // H == E, gssw.c:1747-1768
+            if (w.v == cellE<WD>(*c0)) // H == E, gssw.c:1747-1768
             {
                 w.st = 1;
                 continue;
@@ -1142,7 +1251,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                         w.need_row = w.j;
                         return false; // nothing has been changed yet: the predecessor scan restarts after the reload
                     }
-                    if (w.v == cellE(*cc) - GAP_EXT)
+                    if (w.v == cellE<WD>(*cc) - GAP_EXT)
                     {
                         best = c;
                         push_op(w, oplog, oplog_cap, w.n, OP_D, 1);

@@ -26,6 +26,7 @@ struct GraphStore
     std::vector<int32_t> ints;
     int max_nodes = 0;
     int max_G = 0;
+    int max_tab_ints = 0; // largest per-orientation int table (SiteDev::tab_ints)
     // for the counting stage (pg_count.cuh): the edges as given (input order is the order of the edge count rows),
     // their path-family label masks (pg_set_edge_labels; 0 = unlabelled) and each site's first row
     std::vector<int32_t> in_from, in_to;
@@ -37,7 +38,7 @@ struct GraphStore
         sites.clear();
         bytes.clear();
         ints.clear();
-        max_nodes = max_G = 0;
+        max_nodes = max_G = max_tab_ints = 0;
         in_from.clear();
         in_to.clear();
         in_label.clear();
@@ -251,9 +252,11 @@ inline bool build_fragment_chains(const int32_t* fragment, const int32_t* site, 
 }
 
 // per-read scratch sizes in 32-bit words (see pg_core.cuh "per-task scratch layout")
-inline size_t info_words(int max_nodes, int W) { return (size_t)max_nodes * 3 * W; }
 inline size_t last_words(int max_nodes, int R, int W) { return (size_t)max_nodes * 2 * R * W; }
-inline size_t ckpt_words(int max_G, int R, int W) { return (size_t)num_ckpt(max_G, W) * (R + 1) * W; }
+inline size_t ckpt_words(int max_G, int R, int W)
+{
+    return (size_t)num_ckpt(max_G, W) * (is_wide(R, W) ? 2 * R + 2 : R + 1) * W;
+}
 
 // "<node>[<len><op>...]..." -- GraphAlignerImpl::extractCigar (GraphAligner.cpp:88-108)
 inline std::string format_cigar(const Record& rec, const uint32_t* ops)

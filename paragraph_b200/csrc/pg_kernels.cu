@@ -191,6 +191,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
 {
     extern __shared__ uint32_t smem[];
     constexpr int NT = 32 / W; // tasks per warp: a group of W lanes per task
+    constexpr bool WIDE = Sizes<R, W>::WIDE; // reads that can score past a byte: wider checkpoints, region maxima
+    constexpr int CKW = Sizes<R, W>::CKW, IW = Sizes<R, W>::INFOW;
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / W, gl = lane % W;
     const int wpc = blockDim.x >> 5; // warps per CTA: 4, fewer when the seed tables of a many-node graph need the room
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     const int rd = a.read0 + (ltask >> 1), o = ltask & 1;
     const bool active = ltask < a.n_tasks && !(o == 1 && !(a.flags & AF_REVERSE_GRAPH));
     uint32_t* prof = smem + ((size_t)wic * NT + grp) * a.smem_words_per_task;
-    // [n_nodes_cap][2R][W] seeds, [n_nodes_cap][3][W] node maxima: warp-private shared memory, or (fallback) HBM
+    // [n_nodes_cap][2R][W] seeds, [n_nodes_cap][IW][W] node maxima: warp-private shared memory, or (fallback) HBM
     uint32_t* seedS = TABG ? a.tabG + (size_t)(ltask < a.n_tasks ? ltask : 0) * a.stride_tab : prof + NCODE * R * W;
     uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * W;
     TaskOut* to = a.tout + (size_t)rd * 2 + o;
@@ -238,6 +240,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     lane_zero(s);
     LaneCtl c;
     ctl_at_step(c, g, 0, gl);
+    if (WIDE)
+        region_begin(c, g, L, gl);
     if (!active)
         c.colsLeft = COLS_INF;
     const bool save = active && (o == 0);
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     {
         const bool live = (NT == 1) || cki < my_nck;
         if (save && live)
-            ckpt_store<R, W>(s, ckpt + (size_t)cki * (R + 1) * W, gl);
+            ckpt_store<R, W>(s, ckpt + (size_t)cki * CKW * W, gl);
         const int kbase = cki * CK;
         const uint8_t* cp = codes + kbase; // per-lane pointer, immediate offsets inside the unrolled body
         // Node boundaries are rare (a few per lane and task) but testing for them costs every step a counter, a
@@ -277,8 +281,11 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                 }
                 const int code = live ? cp[kk] : 5;
                 const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
-                const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr);
+                uint32_t tg[R];
+                const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr, tg);
                 track_max(c, m, kbase + kk);
+                if (WIDE)
+                    track_region<R>(c, m, tg, g, L, gl);
             }
             c.colsLeft -= CK;
             continue;
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
             const int k = kbase + kk;
             __syncwarp();
             if (c.colsLeft == 0) // rare, per lane: node boundary
-                node_event<R, true, W>(s, c, g, gl, seedS, infoS);
+                node_event<R, true, W>(s, c, g, gl, seedS, infoS, L);
             else
                 --c.colsLeft;
             uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
@@ -301,8 +308,11 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
             }
             const int code = live ? cp[kk] : 5;
             const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
-            const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr);
+            uint32_t tg[R];
+            const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr, tg);
             track_max(c, m, k);
+            if (WIDE)
+                track_region<R>(c, m, tg, g, L, gl);
         }
     }
     __syncwarp();
@@ -310,9 +320,14 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         for (int x = gl; x < g.n_nodes * 2 * R * W; x += W)
             last[x] = seedS[x];
     TaskOut t;
-    finalize_task_group<W>(infoS, g.n_nodes, gl, t); // every lane of the warp takes part (group-wide reductions)
+    if (!WIDE)
+        finalize_task_group<W>(infoS, g.n_nodes, gl, t); // every lane of the warp takes part (group-wide reductions)
     if (active && gl == 0)
+    {
+        if (WIDE) // long reads: the serial statement, with the 16-bit-mode uniqueness rule (n_top_rule)
+            finalize_task(infoS, g.n_nodes, t, W, IW);
         *to = t;
+    }
 }
 
 struct TraceArgs
@@ -399,7 +414,7 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         LaneCtl c;
         if (!done)
         {
-            ckpt_load<R, W>(s, ckpt + (size_t)T * (R + 1) * W, gl);
+            ckpt_load<R, W>(s, ckpt + (size_t)T * Sizes<R, W>::CKW * W, gl);
             ctl_at_step(c, g, T * CK, gl);
         }
         else
@@ -429,7 +444,7 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
             uint32_t Hc[R], Ec[R], Fc[R];
             lane_step<R, true, W>(s, rh, rf, prof, done ? 5 : cp[kk], gl, Hc, Ec, Fc);
             if (!done)
-                tile_store<R>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, gl, blo, Hc, Ec, Fc, half);
+                tile_store<R, Sizes<R, W>::WIDE>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, gl, blo, Hc, Ec, Fc, half);
         }
         __syncwarp();
     }
@@ -438,11 +453,12 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
     {
         Record rec;
         rec.graph_pos = w.position;
-        rec.score = d.score;
+        rec.score = (int16_t)d.score;
         rec.unique = (uint8_t)d.unique;
         rec.chose_reverse = (uint8_t)half;
         rec.status = (uint8_t)(w.phase == 2 ? w.status : 1);
-        rec.query_clipped = (uint8_t)w.clipped;
+        rec.reserved = 0;
+        rec.query_clipped = (uint16_t)w.clipped;
         rec.cigar_off = 0;
         rec.cigar_len = 0;
         if (a.flags & AF_CIGAR)
@@ -747,7 +763,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     const size_t s_last = host::last_words(max_nodes, R, W), s_ckpt = host::ckpt_words(max_G, R, W);
     // fill kernel shared memory per task: profile + seed/info tables; fewer warps per CTA for many-node graphs, and
     // beyond that the tables move to HBM
-    const int tab_words = max_nodes * (2 * R + 3) * W;
+    const int tab_words = max_nodes * (2 * R + Sizes<R, W>::INFOW) * W;
     // staged column codes (+ 8 bytes for the mbarrier in front, kept 16-byte aligned); graphs over 16 KB are read from L1/L2
     int code_bytes = (int)code_span_bytes(max_G) + 16;
     if (code_bytes > 16 * 1024 + 16 || !c->use_tma)
@@ -872,7 +888,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
 
 extern "C" {
 
-const char* pg_version(void) { return "paragraph_b200 0.2 sm_100a CK=16 int16x2-wavefront W=16/32/8"; }
+const char* pg_version(void) { return "paragraph_b200 0.3 sm_100a CK=16 int16x2-wavefront W=16/32/8 reads<=512"; }
 
 int pg_create(int device, pg_ctx** out)
 {
@@ -1081,7 +1097,10 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
     if (rc != PG_OK)
         return rc;
     // geometry: W lanes per task, R rows per lane (W * R >= read length); see DESIGN.md "geometry"
-    if (c->geom_w == 32)
+    // reads over BYTE_MAX_READ_LEN can score past a byte (gssw's 16-bit mode): WIDE geometries, W = 32 only
+    if (c->max_len > BYTE_MAX_READ_LEN)
+        rc = c->max_len <= 320 ? run_chunks<10, 32>(c, flags) : run_chunks<16, 32>(c, flags);
+    else if (c->geom_w == 32)
         rc = c->max_len <= 160 ? run_chunks<5, 32>(c, flags) : run_chunks<8, 32>(c, flags);
     else if (c->geom_w == 8 && c->max_len <= 160)
         rc = run_chunks<20, 8>(c, flags);

@@ -26,25 +26,29 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
     std::vector<uint32_t> seedS((size_t)g.n_nodes * 2 * R * W, 0);
     for (int t = 0; t < W; ++t)
         build_profile<R, W>(prof.data(), bases, L, orient, t);
+    constexpr bool WIDE = Sizes<R, W>::WIDE;
+    constexpr int CKW = Sizes<R, W>::CKW, IW = Sizes<R, W>::INFOW;
     Lane<R> s[W];
     LaneCtl c[W];
     for (int t = 0; t < W; ++t)
     {
         lane_zero(s[t]);
         ctl_at_step(c[t], g, 0, t);
+        if (WIDE)
+            region_begin(c[t], g, L, t);
     }
-    info.assign(host::info_words(g.n_nodes, W), 0);
+    info.assign((size_t)g.n_nodes * IW * W, 0);
     if (save_trace)
-        ckpt.assign(host::ckpt_words(g.G, R, W), 0);
+        ckpt.assign((size_t)num_ckpt(g.G, W) * CKW * W, 0);
     const int nck = num_ckpt(g.G, W);
     for (int k = 0; k < nck * CK; ++k)
     {
         if (save_trace && k % CK == 0)
             for (int t = 0; t < W; ++t)
-                ckpt_store<R, W>(s[t], ckpt.data() + (size_t)(k / CK) * (R + 1) * W, t);
+                ckpt_store<R, W>(s[t], ckpt.data() + (size_t)(k / CK) * CKW * W, t);
         for (int t = 0; t < W; ++t) // events read what lane t-1 wrote at an EARLIER step only
             if (c[t].colsLeft == 0)
-                node_event<R, true, W>(s[t], c[t], g, t, seedS.data(), info.data());
+                node_event<R, true, W>(s[t], c[t], g, t, seedS.data(), info.data(), L);
             else
                 --c[t].colsLeft;
         uint32_t rh[W], rf[W];
@@ -56,13 +60,17 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
         for (int t = 0; t < W; ++t)
         {
             const int code = g.codes[k - t];
-            const uint32_t m = lane_step<R, false, W>(s[t], rh[t], rf[t], prof.data(), code, t, nullptr, nullptr, nullptr);
+            const ProfPtr<W> pf = { prof.data() + (code * R) * W + t };
+            uint32_t tg[R];
+            const uint32_t m = lane_step_pf<R, false, PG_LAZY_F != 0>(s[t], rh[t], rf[t], pf, nullptr, nullptr, nullptr, tg);
             track_max(c[t], m, k);
+            if (WIDE)
+                track_region<R>(c[t], m, tg, g, L, t);
         }
     }
     if (save_trace)
         last = seedS; // the kernel copies its shared-memory seed table to HBM at the end of a forward-graph task
-    finalize_task(info.data(), g.n_nodes, out, W);
+    finalize_task(info.data(), g.n_nodes, out, W, IW);
 }
 
 template <int R, int W>
@@ -73,7 +81,7 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
     LaneCtl c[W];
     for (int t = 0; t < W; ++t)
     {
-        ckpt_load<R, W>(s[t], ckpt.data() + (size_t)T * (R + 1) * W, t);
+        ckpt_load<R, W>(s[t], ckpt.data() + (size_t)T * Sizes<R, W>::CKW * W, t);
         ctl_at_step(c[t], g, T * CK, t);
     }
     for (int kk = 0; kk < CK; ++kk)
@@ -94,7 +102,7 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
         {
             uint32_t Hc[R], Ec[R], Fc[R];
             lane_step<R, true, W>(s[t], rh[t], rf[t], prof.data(), g.codes[k - t], t, Hc, Ec, Fc);
-            tile_store<R>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, t, blo, Hc, Ec, Fc, half);
+            tile_store<R, Sizes<R, W>::WIDE>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, t, blo, Hc, Ec, Fc, half);
         }
     }
 }
@@ -141,7 +149,7 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     rec.unique = (uint8_t)d.unique;
     rec.chose_reverse = (uint8_t)d.half;
     rec.status = (uint8_t)w.status;
-    rec.query_clipped = (uint8_t)w.clipped;
+    rec.query_clipped = (uint16_t)w.clipped;
     // replay the op log back to front, merging runs of equal (node, op)  (gssw_cigar_push_back/_front merging)
     const int n = w.nops < (int)oplog.size() ? w.nops : (int)oplog.size();
     ops_out.assign((size_t)n + 1, 0);
@@ -191,7 +199,11 @@ int pgemu_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off,
         const uint8_t* gb = gs.bytes.data();
         const int32_t* gi = gs.ints.data();
         int rc;
-        if (g_geom_w == 32)
+        // reads that can leave gssw's 8-bit mode take a WIDE geometry (W = 32 only), like the kernels' dispatch
+        if (L > BYTE_MAX_READ_LEN)
+            rc = L <= 320 ? emu_align_one<10, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt)
+                          : emu_align_one<16, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt);
+        else if (g_geom_w == 32)
             rc = L <= 160 ? emu_align_one<5, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt)
                           : emu_align_one<8, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt);
         else if (g_geom_w == 16)
@@ -210,7 +222,7 @@ int pgemu_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off,
         o[2] = rec.unique;
         o[3] = rec.unique ? 60 : 0;
         o[4] = ((is_rev ? is_rev[i] : 0) != 0) != (rec.chose_reverse != 0);
-        o[5] = rec.status | (rec.query_clipped << 8);
+        o[5] = rec.status | ((int32_t)rec.query_clipped << 8);
         if (out_bases_blob)
             for (int j = 0; j < L; ++j)
                 out_bases_blob[read_off[i] + j] = rec.chose_reverse ? (char)complement_base(b[L - 1 - j]) : (char)b[j];

@@ -54,4 +54,47 @@ def test_emulator_fuzz_vs_oracle(built):
 
 def test_emulator_rejects_long_reads(built):
     with pytest.raises(RuntimeError):
-        emubind.emu_align_batch(["ACGT" * 100], [], ["ACGT" * 63])  # 252 > 250
+        emubind.emu_align_batch(["ACGT" * 200], [], ["ACGT" * 129])  # 516 > 512
+
+
+def test_emulator_long_reads_16bit_mode(built):
+    """251..512 bp reads (WIDE geometries: 16-bit checkpoints, 10-bit tile cells, region maxima).  Scores from 251 on
+    put the reference into gssw's 16-bit mode (other lazy-F loop, byte-wise uniqueness scan of a 16-bit matrix)."""
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(31)
+    n = hi = 0
+    for _ in range(25):
+        alpha = ["ACGT", "ACGT", "AC", "ACGTN"][int(rng.integers(0, 4))]
+        nodes, edges = synth.bubble_graph(rng, n_nodes=int(rng.integers(1, 6)), max_len=int(rng.choice([300, 500, 700])),
+                                          alphabet=alpha)
+        reads = synth.fuzz_reads(rng, nodes, edges, 6, min_len=200, max_len=512)
+        isrev = [i & 1 for i in range(len(reads))]
+        exp = R.OracleGraph(nodes, edges).align_batch(reads, is_rev=isrev)
+        got, _ = emubind.emu_align_batch(nodes, edges, reads, is_rev=isrev)
+        assert strip_status(got) == exp
+        n += len(reads)
+        hi += sum(e["score"] >= 251 for e in exp)
+    assert hi > 30
+
+
+def long_read_uniqueness_cases(rng):
+    """Two parallel copies of one sequence: every read has two equally good placements.  Top scores around the 8-bit
+    limit (250 | 251..255 | >= 256) exercise the three branches of the uniqueness rule (pg_core.cuh n_top_rule)."""
+    for L in (250, 251, 252, 253, 254, 255, 256, 257, 300, 400):
+        rep = synth.random_seq(rng, L)
+        nodes = [synth.random_seq(rng, 20), rep, rep, synth.random_seq(rng, 20)]
+        edges = [(0, 1), (0, 2), (1, 3), (2, 3)]
+        reads = [rep, rep[: L - 3] + "A", nodes[0][-5:] + rep[: L - 5], synth.revcomp_exact(rep), rep[: L // 2 + 3],
+                 rep[L // 2 - 3:]]
+        yield nodes, edges, reads
+
+
+def test_emulator_16bit_uniqueness_rule(built):
+    R.set_fill_variant(0)
+    seen = set()
+    for nodes, edges, reads in long_read_uniqueness_cases(np.random.default_rng(5)):
+        exp = R.OracleGraph(nodes, edges).align_batch(reads)
+        got, _ = emubind.emu_align_batch(nodes, edges, reads)
+        assert strip_status(got) == exp
+        seen |= {(min(max(e["score"], 250), 256), e["unique"]) for e in exp}
+    assert (256, True) in seen and (250, False) in seen and any(250 < s < 256 for s, _ in seen)

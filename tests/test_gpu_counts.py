@@ -80,8 +80,8 @@ def import_phasing(ctx, g, site, keep):
     ops = []
     for i, a in enumerate(rd):
         w = capi.parse_cigar(a["cigar"])
-        rec[i] = (a["pos"], a["score"], int(a["unique"]), 0, 0,
-                  min(255, sum((x >> 3) & 0x1FFF for x in w if x & 7 == 5)), len(ops), len(w))
+        rec[i] = (a["pos"], a["score"], sum((x >> 3) & 0x1FFF for x in w if x & 7 == 5), int(a["unique"]), 0, 0, 0,
+                  len(ops), len(w))
         ops += w
     ctx.import_alignments([a["len"] for a in rd], rec, np.array(ops, dtype=np.uint32))
     return rd, frag

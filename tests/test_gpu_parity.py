@@ -72,6 +72,48 @@ def test_long_reads_up_to_8bit_limit(ctx):
     assert strip_status(ctx.align(reads)) == R.OracleGraph(nodes, edges).align_batch(reads)
 
 
+def test_reads_past_the_8bit_limit(ctx):
+    """251..512 bp reads: WIDE geometries (R = 10 / 16), scores >= 251 = gssw's 16-bit mode in the reference."""
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(19)
+    nodes, edges = synth.del_graph(rng, 600, 300)
+    for rl in (251, 300, 320, 321, 450, 512):
+        reads = synth.simulate_reads(rng, nodes, edges, 60, read_len=rl, sub=0.02, indel_frac=0.3)
+        ctx.clear_graphs()
+        ctx.add_graph(nodes, edges)
+        exp = R.OracleGraph(nodes, edges).align_batch(reads)
+        assert strip_status(ctx.align(reads)) == exp
+        assert rl < 300 or max(e["score"] for e in exp) >= 251
+    n = hi = 0
+    for _ in range(40):  # adversarial long reads on bubble graphs, mixed lengths in one batch
+        alpha = ["ACGT", "ACGT", "AC", "ACGTN"][int(rng.integers(0, 4))]
+        nodes, edges = synth.bubble_graph(rng, n_nodes=int(rng.integers(1, 6)), max_len=int(rng.choice([300, 500, 700])),
+                                          alphabet=alpha)
+        reads = synth.fuzz_reads(rng, nodes, edges, 8, min_len=100, max_len=512)
+        isrev = [i & 1 for i in range(len(reads))]
+        ctx.clear_graphs()
+        ctx.add_graph(nodes, edges)
+        exp = R.OracleGraph(nodes, edges).align_batch(reads, is_rev=isrev)
+        assert strip_status(ctx.align(reads, is_rev=isrev)) == exp
+        n += len(reads)
+        hi += sum(e["score"] >= 251 for e in exp)
+    assert hi > 40
+
+
+def test_16bit_mode_uniqueness_rule(ctx):
+    """GraphAligner scans the 16-bit matrix byte-wise (GraphAligner.cpp:177-186): top scores 251..255 and >= 256."""
+    from test_emulator import long_read_uniqueness_cases
+    R.set_fill_variant(0)
+    seen = set()
+    for nodes, edges, reads in long_read_uniqueness_cases(np.random.default_rng(5)):
+        ctx.clear_graphs()
+        ctx.add_graph(nodes, edges)
+        exp = R.OracleGraph(nodes, edges).align_batch(reads)
+        assert strip_status(ctx.align(reads)) == exp
+        seen |= {(min(max(e["score"], 250), 256), e["unique"]) for e in exp}
+    assert (256, True) in seen and (250, False) in seen and any(250 < s < 256 for s, _ in seen)
+
+
 def test_long_nodes_many_checkpoints(ctx):
     """config-5 shape (kb-sized nodes): hundreds of checkpoints / tiles per read, chunked scratch."""
     R.set_fill_variant(0)
@@ -120,7 +162,7 @@ def test_errors_are_loud(ctx):
         ctx.add_graph(["ACGT", ""], [(0, 1)])  # empty node
     ctx.add_graph(["ACGT" * 100], [])
     with pytest.raises(capi.PgError):
-        ctx.align(["ACGT" * 63])  # 252 bp > PG_MAX_READ_LEN
+        ctx.align(["ACGT" * 129])  # 516 bp > PG_MAX_READ_LEN
     with pytest.raises(capi.PgError):
         ctx.align(["ACGT"], sites=[5])  # unknown site
 

@@ -43,3 +43,32 @@ def test_variants_fuzz_H_and_results(built, variant):
                 assert (x["cigar"], x["pos"], x["score"], x["multi"]) == (y["cigar"], y["pos"], y["score"], y["multi"])
     finally:
         R.set_fill_variant(0)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_variants_in_16bit_mode(built, variant):
+    """The same equivalence once scores pass 250 and the reference is in gssw's 16-bit mode (gssw_sw_sse2_word has its
+    own lazy-F loop, so its mE / mF differ from the 8-bit ones): H cell by cell, results, uniqueness."""
+    rng = np.random.default_rng(200 + variant)
+    hi = 0
+    try:
+        for _ in range(20):
+            nodes, edges = synth.bubble_graph(rng, n_nodes=int(rng.integers(1, 5)), max_len=int(rng.choice([300, 600])),
+                                              alphabet=["ACGT", "AC", "ACGTN"][int(rng.integers(0, 3))])
+            reads = synth.fuzz_reads(rng, nodes, edges, 5, min_len=240, max_len=500)
+            og = R.OracleGraph(nodes, edges)
+            R.set_fill_variant(0)
+            exp = og.align_batch(reads)
+            expH = [og.fill_trace(r.upper(), wide=True) for r in reads[:2]]
+            R.set_fill_variant(variant)
+            assert og.align_batch(reads) == exp
+            for r, x in zip(reads[:2], expH):
+                y = og.fill_trace(r.upper(), wide=True)
+                assert (x["stats"][:, 3] == y["stats"][:, 3]).all()  # same mode decision
+                for (h1, _, _), (h2, _, _) in zip(x["mats"], y["mats"]):
+                    assert (h1 == h2).all()
+                assert (x["cigar"], x["pos"], x["score"], x["multi"]) == (y["cigar"], y["pos"], y["score"], y["multi"])
+            hi += sum(e["score"] >= 251 for e in exp)
+        assert hi > 20
+    finally:
+        R.set_fill_variant(0)

@@ -18,11 +18,12 @@ def main():
         ctx.clear_graphs()
         reads, sites, exp, isrev = [], [], [], []
         flags = int(rng.choice([0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 1, 3, 5, 7]))
-        maxlen = int(rng.choice([160, 160, 250]))
+        maxlen = int(rng.choice([160, 160, 250, 320, 512]))
         for gi in range(min(200, ng - batch)):
             alpha = ["ACGT", "ACGT", "AC", "ACGTN", "ACGTRYN"][int(rng.integers(0, 5))]
             nodes, edges = synth.bubble_graph(rng, n_nodes=int(rng.integers(1, 10)), max_len=int(rng.choice([5, 20, 60, 200, 600])), alphabet=alpha)
-            rd = [r[:maxlen] for r in synth.fuzz_reads(rng, nodes, edges, nr, max_len=maxlen)]
+            minlen = 8 if maxlen <= 250 else int(rng.choice([8, 200]))
+            rd = [r[:maxlen] for r in synth.fuzz_reads(rng, nodes, edges, nr, min_len=minlen, max_len=maxlen)]
             rv = [int(x) for x in rng.integers(0, 2, size=len(rd))]
             sid = ctx.add_graph(nodes, edges)
             reads += rd; sites += [sid] * len(rd); isrev += rv
