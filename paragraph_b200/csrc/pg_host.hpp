@@ -147,6 +147,8 @@ struct GraphStore
             for (int32_t x = ptr; x < n_edges; ++x)
                 ints.push_back(0);
         }
+        sd.tab_ints = 3 * n_nodes + 1 + n_edges;
+        max_tab_ints = std::max(max_tab_ints, sd.tab_ints);
         sites.push_back(sd);
         if (edge_base.empty())
         {

@@ -68,6 +68,7 @@ struct FillArgs
     size_t stride_last, stride_ckpt;
     int n_nodes_cap; // seed / info table capacity per task (nodes)
     int code_smem_bytes; // per-task shared-memory room for the staged column codes (0 = read them from global/L1)
+    int tab_ints_cap;    // per-task shared-memory room (words) for the staged node tables (STAGED only)
     uint32_t* tabG;  // seed + info tables in HBM when they do not fit shared memory (graphs with very many nodes), else null
     size_t stride_tab;
     TaskOut* tout; // [2 * n_reads] (global task index)
@@ -214,7 +215,13 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     }
     const int rdc = ltask < a.n_tasks ? rd : a.read0; // clamp for inactive tail groups (they only idle along)
     const SiteDev sd = a.sites[a.read_site ? a.read_site[rdc] : 0];
-    const GraphView g = make_view(sd, a.gbytes, a.gints, o);
+    // STAGED: the orientation's node tables (lengths, predecessor lists) are copied next to the seed tables, so that
+    // the node-boundary code of the hot loop reads shared memory with 32-bit addresses instead of chasing HBM pointers
+    int32_t* tabS = reinterpret_cast<int32_t*>(infoS + a.n_nodes_cap * IW * W);
+    if (STAGED)
+        for (int x = gl; x < sd.tab_ints; x += W)
+            tabS[x] = a.gints[sd.tab_off[o] + x];
+    const GraphView g = STAGED ? make_view_at(sd, a.gbytes + sd.codes_off[o], tabS) : make_view(sd, a.gbytes, a.gints, o);
     const uint8_t* bases = a.bases + a.read_off[rdc];
     const int L = a.read_off[rdc + 1] - a.read_off[rdc];
     // node sequences (column codes) of this task's orientation: TMA-staged into shared memory when they fit
@@ -255,6 +262,9 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
             nck = max(nck, __shfl_xor_sync(FULL, nck, d));
     // this lane's column of the profile as a shared-window address: one IMAD per step selects the code's rows
     const uint32_t NO_F = pk(-1, -1); // "no insertion running into lane 0": any F <= 0 will do, negative lets lazy-F skip
+    uint32_t lmask, nof0;
+    asm("mov.u32 %0, %1;" : "=r"(lmask) : "r"(gl ? 1u : 0u));
+    asm("mov.u32 %0, %1;" : "=r"(nof0) : "r"(gl ? 0u : NO_F));
     const ProfSmem<W> pf0 = { (uint32_t)__cvta_generic_to_shared(prof + gl) };
     for (int cki = 0; cki < nck; ++cki)
     {
@@ -274,11 +284,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
             {
                 uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
                 uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
-                if (gl == 0)
-                {
-                    rh = 0;
-                    rf = NO_F;
-                }
+                rh *= lmask; // lane 0 has no lane above it: H = 0, no insertion running in.  (Multiply-add by an opaque
+                rf = rf * lmask + nof0; // 0/1 instead of a select: runs on the FMA pipe, the ALU pipe is the busy one)
                 const int code = live ? cp[kk] : 5;
                 const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
                 uint32_t tg[R];
@@ -768,7 +775,8 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     int code_bytes = (int)code_span_bytes(max_G) + 16;
     if (code_bytes > 16 * 1024 + 16 || !c->use_tma)
         code_bytes = 0;
-    int fill_words = NCODE * R * W + tab_words + code_bytes / 4;
+    const int tab_ints_cap = code_bytes ? ((c->graphs.max_tab_ints + 3) & ~3) : 0; // staged with the codes (keeps 16-byte alignment)
+    int fill_words = NCODE * R * W + tab_words + tab_ints_cap + code_bytes / 4;
     int fill_warps = FILL_WARPS;
     while (fill_warps > 1 && (size_t)fill_warps * NT * fill_words * 4 > 200 * 1024)
         fill_warps >>= 1;
@@ -837,6 +845,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.ckpt = c->d_ckpt.p;
         fa.n_nodes_cap = max_nodes;
         fa.code_smem_bytes = code_bytes ? code_bytes - 16 : 0;
+        fa.tab_ints_cap = code_bytes ? tab_ints_cap : 0;
         fa.tabG = tab_global ? c->d_tab.p : nullptr;
         fa.stride_tab = (size_t)tab_words;
         fa.stride_last = s_last;
