@@ -96,6 +96,18 @@ int pgo_count_site(
     int* path_used, pgo_count4* node_counts, pgo_count4* edge_counts, uint32_t* family_words, int family_cap,
     int* family_used);
 
+/* ---- grm::PathAligner, the exact-match stage in front of the DP (oracle/pg_oracle_path.c) ---- */
+struct pgo_path_index;
+struct pgo_path_index* pgo_path_index_create(int n_nodes, const char* seq_blob, const int32_t* seq_off, int n_edges,
+                                             const int32_t* efrom, const int32_t* eto, int kmer_len);
+void pgo_path_index_destroy(struct pgo_path_index* ix);
+/* out8 = {mapped, graph_pos, score, unique, mapq, is_graph_reverse_strand, cigar_strlen, anchored} */
+int pgo_path_align_read(const struct pgo_path_index* ix, const char* bases, int len, int32_t* out8, char* out_bases,
+                        char* cigar, int cigar_cap);
+/* counters3 = {attempted, anchored, mapped} (PathAligner.hh:66-68) */
+int pgo_path_align_batch(const struct pgo_path_index* ix, int n_reads, const char* bases_blob, const int32_t* read_off,
+                         int32_t* out8, char* out_bases_blob, char* cigars, int cigar_stride, int32_t* counters3);
+
 #ifdef __cplusplus
 }
 #endif

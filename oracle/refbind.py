@@ -405,3 +405,83 @@ def support_sets(sup, path_words, i, edges=None):
     nodes = {int(x & SUP_NODE_MASK) for x in w if x & SUP_NODE}
     es = {(int(w[k - 1] & SUP_NODE_MASK), int(w[k] & SUP_NODE_MASK)) for k in range(1, len(w)) if w[k] & SUP_EDGE}
     return nodes, es, int(sup["sequences"][i])
+
+
+# ---------------------------------------------------------------- grm::PathAligner (exact-match stage)
+def _path_result(o, bases, cigar):
+    return dict(mapped=bool(o[0]), pos=int(o[1]), score=int(o[2]), unique=bool(o[3]), mapq=int(o[4]),
+                graph_reverse=bool(o[5]), bases=bases, cigar=cigar)
+
+
+def ref_path_align_batch(node_seqs, edges, reads, kmer_len=32, is_rev=None):
+    """The UNMODIFIED reference PathAligner (oracle/ref_path.cpp).  -> (list of dicts, (attempted, anchored, mapped))"""
+    lib = ref_lib()
+    lib.pgref_path_align_batch.restype = C.c_int
+    lib.pgref_path_align_batch.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int,
+                                           C.POINTER(C.c_int32)]
+    blob, off, ef, et = pack_graph(node_seqs, edges)
+    rblob, roff = pack_reads(reads)
+    n = len(reads)
+    out = np.zeros((n, 8), dtype=np.int32)
+    ob = C.create_string_buffer(max(1, len(rblob)))
+    cg = C.create_string_buffer(max(1, n * CIGAR_STRIDE))
+    cnt = np.zeros(3, dtype=np.int32)
+    rv = None if is_rev is None else np.asarray(is_rev, dtype=np.uint8)
+    rc = lib.pgref_path_align_batch(len(node_seqs), blob, _p(off, C.c_int32), len(edges), _p(ef, C.c_int32),
+                                    _p(et, C.c_int32), int(kmer_len), n, rblob, _p(roff, C.c_int32),
+                                    None if rv is None else _p(rv, C.c_uint8), _p(out, C.c_int32), ob, cg, CIGAR_STRIDE,
+                                    _p(cnt, C.c_int32))
+    if rc != 0:
+        raise RuntimeError("reference PathAligner threw")
+    raw = ob.raw
+    res = []
+    for i in range(n):
+        c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
+        res.append(_path_result(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
+    return res, tuple(int(x) for x in cnt)
+
+
+class OraclePathIndex:
+    """oracle/pg_oracle_path.c: the C restatement of KmerIndex + PathAligner::alignRead."""
+
+    def __init__(self, node_seqs, edges, kmer_len=32):
+        self.lib = oracle_lib()
+        self.lib.pgo_path_index_create.restype = C.c_void_p
+        self.lib.pgo_path_index_create.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int,
+                                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
+        self.lib.pgo_path_index_destroy.argtypes = [C.c_void_p]
+        self.lib.pgo_path_align_batch.restype = C.c_int
+        self.lib.pgo_path_align_batch.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_int32),
+                                                  C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int,
+                                                  C.POINTER(C.c_int32)]
+        blob, off, ef, et = pack_graph(node_seqs, edges)
+        self.h = self.lib.pgo_path_index_create(len(node_seqs), blob, _p(off, C.c_int32), len(edges),
+                                                _p(ef, C.c_int32), _p(et, C.c_int32), int(kmer_len))
+        if not self.h:
+            raise ValueError("oracle: bad graph / k-mer length")
+
+    def align_batch(self, reads):
+        rblob, roff = pack_reads(reads)
+        n = len(reads)
+        out = np.zeros((n, 8), dtype=np.int32)
+        ob = C.create_string_buffer(max(1, len(rblob)))
+        cg = C.create_string_buffer(max(1, n * CIGAR_STRIDE))
+        cnt = np.zeros(3, dtype=np.int32)
+        self.lib.pgo_path_align_batch(self.h, n, rblob, _p(roff, C.c_int32), _p(out, C.c_int32), ob, cg, CIGAR_STRIDE,
+                                      _p(cnt, C.c_int32))
+        raw = ob.raw
+        res = []
+        for i in range(n):
+            c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
+            res.append(_path_result(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
+        return res, tuple(int(x) for x in cnt)
+
+    def close(self):
+        if self.h:
+            self.lib.pgo_path_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

@@ -19,7 +19,7 @@ def pytest_configure(config):
 def golden_cases():
     out = []
     for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.json"))):
-        if os.path.basename(p).startswith("counts_"):  # fixtures of the counting stage (test_counts_*.py)
+        if os.path.basename(p).startswith(("counts_", "path_")):  # counting stage / PathAligner fixtures (own tests)
             continue
         with open(p) as f:
             out.append(json.load(f))
