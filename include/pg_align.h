@@ -31,6 +31,10 @@ extern "C" {
  * GraphAligner's uniqueness scan makes of a 16-bit matrix (src/c++/lib/grm/GraphAligner.cpp:177-186). */
 #define PG_MAX_READ_LEN 512
 
+/* pg_record::mapped_by: the stage of grm::CompositeAligner that mapped the read */
+#define PG_STAGE_GSSW_ID 0
+#define PG_STAGE_PATH_ID 1
+
 /* GraphAligner alignment flags (src/c++/include/grm/GraphAligner.hh:64-67) */
 #define PG_AF_CIGAR 0x01u
 #define PG_AF_BOTH_STRANDS 0x02u
@@ -53,8 +57,12 @@ typedef struct pg_record
                                read_len - query_clipped < round(bad_align_frac * read_len) -- no CIGAR decode needed */
     uint8_t unique;
     uint8_t chose_reverse;
-    uint8_t status; /* 0 ok; 1 traceback dead end (the reference would assert/spin); 2 op log overflow */
-    uint8_t reserved;
+    uint8_t status; /* 0 ok; 1 traceback dead end (the reference would assert/spin); 2 op log overflow;
+                       3 unmapped: no enabled stage mapped the read (graph_mapping_status stays UNMAPPED) */
+    uint8_t mapped_by; /* stage of grm::CompositeAligner that mapped the read: PG_STAGE_GSSW or PG_STAGE_PATH.  The
+                          two stages set the strand differently: gssw -> is_graph_reverse_strand =
+                          is_reverse_strand != chose_reverse, quals reversed too (GraphAligner.cpp:358-378);
+                          PathAligner -> is_graph_reverse_strand = chose_reverse, quals untouched (PathAligner.cpp:124-135) */
     uint32_t cigar_off;
     uint32_t cigar_len;
 } pg_record;
@@ -198,6 +206,25 @@ int pg_batch_count(pg_ctx* ctx, const int32_t* fragment, const uint8_t* is_rever
 /* Counting-stage kernels launched by this context so far and the device time in ms of the last pg_batch_count
  * (memsets + the three kernels, CUDA events on the launching stream). */
 int pg_count_stats(const pg_ctx* ctx, uint64_t* kernel_launches, float* last_count_ms);
+
+/* ---- stages of the cascade --------------------------------------------------------------------------------
+ * grm::CompositeAligner(pathMatching, graphMatching, klib, kmer) (src/c++/include/grm/CompositeAligner.hh:44-67,
+ * lib/grm/CompositeAligner.cpp:78-176) tries its enabled stages in order; the first that maps a read wins.
+ *   path_kmer_len > 0 : exact-match stage first = grm::PathAligner(kmer_size) (include/grm/PathAligner.hh:39-78,
+ *                       lib/grm/PathAligner.cpp:75-164) with the graphtools::KmerIndex it builds in setGraph (32 in
+ *                       the reference, `paragraph` switches it on by default: src/c++/main/paragraph.cpp:60).  A read
+ *                       with a full-length exact match on either strand gets score = read length, graph_pos = offset
+ *                       in the first node, ops "<overlap>M" per node, unique = 0 iff a second full-length match
+ *                       exists, mapped_by = PG_STAGE_PATH_ID.  The index of every registered graph is (re)built at
+ *                       the next pg_batch_run.
+ *   graph_matching    : the gssw stage (the DP kernels) for the reads still unmapped; when 0 they stay unmapped
+ *                       (pg_record::status 3).
+ * Default: path_kmer_len = 0, graph_matching = 1 (what grmpy runs: src/c++/main/grmpy.cpp:69-72).  The KmerAligner
+ * and KlibAligner stages are not built. */
+int pg_set_stages(pg_ctx* ctx, int32_t path_kmer_len, int32_t graph_matching);
+/* counters3 = {attempted, anchored, mapped} of the last batch (PathAligner::attempted/anchored/mapped,
+ * PathAligner.hh:66-68) and the stage's device time in ms. */
+int pg_path_stats(pg_ctx* ctx, uint64_t* counters3, float* path_ms);
 
 /* Kernels launched by this context so far, and the last batch's per-kernel device time in ms
  * (fill, traceback) measured with CUDA events on the launching stream. */

@@ -18,14 +18,14 @@ MAX_READ_LEN = 512
 OPS = "MXNIDS??"
 
 RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i2"), ("query_clipped", "<u2"), ("unique", "u1"),
-                         ("chose_reverse", "u1"), ("status", "u1"), ("reserved", "u1"), ("cigar_off", "<u4"),
+                         ("chose_reverse", "u1"), ("status", "u1"), ("mapped_by", "u1"), ("cigar_off", "<u4"),
                          ("cigar_len", "<u4")])
 
 # every symbol include/pg_align.h declares
 SYMBOLS = ["pg_create", "pg_destroy", "pg_last_error", "pg_set_stream", "pg_set_scratch_limit", "pg_add_graph",
            "pg_clear_graphs", "pg_align_batch", "pg_batch_upload", "pg_batch_run", "pg_batch_download",
            "pg_format_cigar", "pg_stats", "pg_version", "pg_host_alloc", "pg_host_free", "pg_set_edge_labels",
-           "pg_batch_import", "pg_batch_count", "pg_count_stats"]
+           "pg_batch_import", "pg_batch_count", "pg_count_stats", "pg_set_stages", "pg_path_stats"]
 
 # counting stage (include/pg_align.h, "Counting stage")
 V_MAPPED, V_NONUNIQ, V_BAD_ALIGN, V_INVALID = 0, 1, 2, 3
@@ -97,6 +97,10 @@ def load():
     lib.pg_batch_import.argtypes = [vp, C.c_int32, i32p, i32p, vp, u32p, C.c_uint64]
     lib.pg_count_stats.restype = C.c_int
     lib.pg_count_stats.argtypes = [vp, u64p, C.POINTER(C.c_float)]
+    lib.pg_set_stages.restype = C.c_int
+    lib.pg_set_stages.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.pg_path_stats.restype = C.c_int
+    lib.pg_path_stats.argtypes = [vp, u64p, C.POINTER(C.c_float)]
     lib.pg_batch_count.restype = C.c_int
     lib.pg_batch_count.argtypes = [vp, i32p, C.POINTER(C.c_uint8), C.POINTER(CountParams), vp, u32p, C.c_uint64, u64p,
                                    vp, C.c_uint64, vp, C.c_uint64, u32p, C.c_uint64, u64p]
@@ -191,6 +195,18 @@ class Context:
 
     def set_scratch_limit(self, nbytes):
         self._check(self.lib.pg_set_scratch_limit(self.h, int(nbytes)))
+
+    def set_stages(self, path_kmer_len=0, graph_matching=True):
+        """grm::CompositeAligner's cascade: exact-match stage (PathAligner, k-mer length; 0 = off) in front of the DP."""
+        self._check(self.lib.pg_set_stages(self.h, int(path_kmer_len), 1 if graph_matching else 0))
+        self._path_k = int(path_kmer_len)
+
+    def path_stats(self):
+        """-> dict(attempted, anchored, mapped, path_ms) of the last batch (PathAligner.hh:66-68)"""
+        cnt = (C.c_uint64 * 3)()
+        ms = C.c_float(0)
+        self._check(self.lib.pg_path_stats(self.h, cnt, C.byref(ms)))
+        return dict(attempted=int(cnt[0]), anchored=int(cnt[1]), mapped=int(cnt[2]), path_ms=float(ms.value))
 
     def add_graph(self, node_seqs, edges):
         blob = "".join(node_seqs).encode("latin-1")
@@ -349,12 +365,16 @@ class Context:
         for i, r in enumerate(reads):
             x = rec[i]
             rv = bool(x["chose_reverse"])
-            out.append(dict(pos=int(x["graph_pos"]), score=int(x["score"]), unique=bool(x["unique"]),
-                            mapq=60 if x["unique"] else 0,
-                            graph_reverse=bool(is_rev[i] if is_rev is not None else 0) != rv,
-                            bases=revcomp_exact(r) if rv else r,
-                            cigar=format_cigar(x, ops) if flags & AF_CIGAR else "", status=int(x["status"]),
-                            clipped=int(x["query_clipped"])))
+            by_path = int(x["mapped_by"]) == 1  # PathAligner sets the strand itself and always writes a CIGAR
+            d = dict(pos=int(x["graph_pos"]), score=int(x["score"]), unique=bool(x["unique"]),
+                     mapq=60 if x["unique"] else 0,
+                     graph_reverse=rv if by_path else (bool(is_rev[i] if is_rev is not None else 0) != rv),
+                     bases=revcomp_exact(r) if rv else r,
+                     cigar=format_cigar(x, ops) if (flags & AF_CIGAR or by_path) else "", status=int(x["status"]),
+                     clipped=int(x["query_clipped"]))
+            if getattr(self, "_path_k", 0):
+                d["stage"] = "path" if by_path else "gssw"
+            out.append(d)
         return out
 
     @staticmethod

@@ -164,6 +164,7 @@ struct SiteDev
     int32_t chars_off;    // byte offset of the forward graph characters
     int32_t tab_off[2];   // int offset of the orientation's tables
     int32_t tab_ints;     // ints in one orientation's tables: 3 n_nodes + 1 + distinct edges
+    int32_t raw_off;      // byte offset of the RAW (as given) forward graph characters (exact-match stage, pg_path.cuh)
 };
 
 // bytes of one orientation's column codes as staged into shared memory: leading sentinels + G + trailing sentinels,
@@ -757,6 +758,8 @@ PG_HD Decision decide_strand(const TaskOut& fw, const TaskOut& rv, unsigned flag
 // ---------------------------------------------------------------------------------------------
 // output records (these two structs ARE the C-ABI result layout, see include/pg_align.h)
 // ---------------------------------------------------------------------------------------------
+constexpr int STAGE_GSSW = 0, STAGE_PATH = 1; // Record::mapped_by
+constexpr int ST_UNMAPPED = 3;                // Record::status: no enabled stage mapped the read
 struct Record
 {
     int32_t graph_pos;
@@ -764,8 +767,8 @@ struct Record
     uint16_t query_clipped; // soft-clipped query bases: what readfilters::BadAlign sums with numClipped() (BadAlign.hh:62-73)
     uint8_t unique;
     uint8_t chose_reverse;
-    uint8_t status; // 0 ok, 1 traceback dead end (never seen; the reference would spin/assert), 2 cigar overflow
-    uint8_t reserved;
+    uint8_t status; // 0 ok, 1 traceback dead end (never seen; the reference would spin/assert), 2 cigar overflow, 3 unmapped
+    uint8_t mapped_by; // stage of the CompositeAligner cascade that mapped the read: 0 gssw (DP), 1 PathAligner (pg_path.cuh)
     uint32_t cigar_off; // index of the first op in the cigar arena
     uint32_t cigar_len; // number of ops
 };

@@ -141,7 +141,10 @@ PG_HD void support_read(const Record& rec, const uint32_t* ops, int read_len, in
     sup.sequences = 0;
     sup.path_off = rec.cigar_off;
     sup.path_len = 0;
-    sup.graph_reverse = (uint8_t)((is_reverse_strand ? 1 : 0) ^ (rec.chose_reverse ? 1 : 0));
+    // gssw: is_graph_reverse_strand = read.is_reverse_strand() != chose_reverse (GraphAligner.cpp:358-359);
+    // PathAligner sets it to the matched strand itself (PathAligner.cpp:124-135)
+    sup.graph_reverse = rec.mapped_by == STAGE_PATH ? (uint8_t)(rec.chose_reverse ? 1 : 0)
+                                                    : (uint8_t)((is_reverse_strand ? 1 : 0) ^ (rec.chose_reverse ? 1 : 0));
     if (prm.remove_nonuniq && !rec.unique)
     {
         sup.verdict = V_NONUNIQ;

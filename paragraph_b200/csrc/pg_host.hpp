@@ -7,12 +7,14 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <unordered_map>
 #include <vector>
 
 #include "pg_core.cuh"
 #include "pg_count.cuh"
+#include "pg_path.cuh"
 
 namespace pg
 {
@@ -107,6 +109,8 @@ struct GraphStore
         }
         sd.chars_off = (int32_t)bytes.size();
         bytes.insert(bytes.end(), chars.begin(), chars.end());
+        sd.raw_off = (int32_t)bytes.size(); // as given: the exact-match stage compares characters case-sensitively
+        bytes.insert(bytes.end(), (const uint8_t*)blob + base0, (const uint8_t*)blob + base0 + G);
         for (int o = 0; o < 2; ++o)
         {
             sd.tab_off[o] = (int32_t)ints.size();
@@ -251,6 +255,188 @@ inline bool build_fragment_chains(const int32_t* fragment, const int32_t* site, 
         it->second = i;
     }
     return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact-match stage (pg_path.cuh): per-site index of the UNIQUE k-mer paths
+// ---------------------------------------------------------------------------------------------
+// Replaces graphtools::KmerIndex(graph, k) (graph-tools src/graphalign/KmerIndex.cpp:75-125): every path of k
+// characters through the graph (extendPathEnd, src/graphcore/PathOperations.cpp:73-103) is enumerated; PathAligner only
+// ever uses k-mers that spell exactly one path (numPaths(kmer) == 1, PathAligner.cpp:99), so only those are kept.
+struct PathIndexHost
+{
+    std::vector<PathSite> sites;   // one per GraphStore site
+    std::vector<PathEntry> table;  // open addressing, per site a power-of-two block
+    std::vector<int32_t> lists;    // node lists of the entries
+    std::vector<int32_t> succ;     // per site: succ_ptr[n+1], succ_idx[]
+    int k = 0;
+};
+
+inline void build_path_index(const GraphStore& gs, int k, PathIndexHost& out)
+{
+    out = PathIndexHost();
+    out.k = k;
+    struct KP
+    {
+        uint64_t h;
+        int32_t start_pos, end_pos, list_off, n_nodes;
+    };
+    for (size_t si = 0; si < gs.sites.size(); ++si)
+    {
+        const SiteDev& sd = gs.sites[si];
+        const int n = sd.n_nodes;
+        const int32_t* t = gs.ints.data() + sd.tab_off[0];
+        const int32_t *node_start = t, *node_len = t + n;
+        const uint8_t* raw = gs.bytes.data() + sd.raw_off;
+        // successors, ascending, without duplicates
+        std::vector<std::vector<int32_t>> succ((size_t)n);
+        for (int64_t e = gs.edge_base[si]; e < gs.edge_base[si + 1]; ++e)
+            succ[(size_t)gs.in_from[(size_t)e]].push_back(gs.in_to[(size_t)e]);
+        PathSite ps;
+        ps.k = k;
+        ps.raw_off = sd.raw_off;
+        ps.succ_ptr_off = (int32_t)out.succ.size();
+        {
+            int32_t ptr = 0;
+            for (int i = 0; i < n; ++i)
+            {
+                auto& v = succ[(size_t)i];
+                std::sort(v.begin(), v.end());
+                v.erase(std::unique(v.begin(), v.end()), v.end());
+                out.succ.push_back(ptr);
+                ptr += (int32_t)v.size();
+            }
+            out.succ.push_back(ptr);
+            for (int i = 0; i < n; ++i)
+                out.succ.insert(out.succ.end(), succ[(size_t)i].begin(), succ[(size_t)i].end());
+        }
+        // enumerate the k-mer paths (depth first over the successors, like extendPathEnd)
+        std::vector<KP> kps;
+        std::vector<int32_t> lists; // site-local node lists of ALL k-mer paths
+        std::vector<int32_t> stack_nodes((size_t)k + 2);
+        struct Frame
+        {
+            int depth, end, ext, next_succ;
+        };
+        std::vector<Frame> st;
+        for (int v0 = 0; v0 < n; ++v0)
+            for (int pos = 0; pos < node_len[v0]; ++pos)
+            {
+                stack_nodes[0] = v0;
+                st.clear();
+                st.push_back({ 1, pos, k - 1, 0 });
+                while (!st.empty())
+                {
+                    Frame& f = st.back();
+                    const int last = stack_nodes[(size_t)f.depth - 1];
+                    const int room = node_len[last] - f.end - 1;
+                    if (f.ext <= room)
+                    {
+                        KP kp;
+                        kp.start_pos = pos;
+                        kp.end_pos = f.end + f.ext;
+                        kp.list_off = (int32_t)lists.size();
+                        kp.n_nodes = f.depth;
+                        lists.insert(lists.end(), stack_nodes.begin(), stack_nodes.begin() + f.depth);
+                        uint64_t h = 0;
+                        for (int x = 0; x < f.depth; ++x)
+                        {
+                            const int nd = stack_nodes[(size_t)x];
+                            const int a = x == 0 ? pos : 0, b = x == f.depth - 1 ? kp.end_pos : node_len[nd] - 1;
+                            for (int p = a; p <= b; ++p)
+                                h = path_hash_step(h, raw[node_start[nd] + p]);
+                        }
+                        kp.h = h ? h : 1;
+                        kps.push_back(kp);
+                        st.pop_back();
+                        continue;
+                    }
+                    const auto& sv = succ[(size_t)last];
+                    if (f.next_succ >= (int)sv.size())
+                    {
+                        st.pop_back();
+                        continue;
+                    }
+                    const int c = sv[(size_t)f.next_succ++];
+                    const Frame nf = { f.depth + 1, 0, f.ext - room - 1, 0 };
+                    stack_nodes[(size_t)f.depth] = c;
+                    st.push_back(nf);
+                }
+            }
+        // group equal k-mers: sort by hash, compare the characters inside a run of equal hashes
+        auto kmer_char = [&](const KP& kp, int j) -> uint8_t {
+            for (int x = 0; x < kp.n_nodes; ++x)
+            {
+                const int nd = lists[(size_t)kp.list_off + (size_t)x];
+                const int a = x == 0 ? kp.start_pos : 0, b = x == kp.n_nodes - 1 ? kp.end_pos : node_len[nd] - 1;
+                if (j <= b - a)
+                    return raw[node_start[nd] + a + j];
+                j -= b - a + 1;
+            }
+            return 0;
+        };
+        auto same_kmer = [&](const KP& a, const KP& b) {
+            for (int j = 0; j < k; ++j)
+                if (kmer_char(a, j) != kmer_char(b, j))
+                    return false;
+            return true;
+        };
+        std::vector<uint32_t> order(kps.size());
+        for (size_t i = 0; i < order.size(); ++i)
+            order[i] = (uint32_t)i;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return kps[a].h < kps[b].h; });
+        std::vector<uint32_t> uniq;
+        for (size_t i = 0; i < order.size();)
+        {
+            size_t j = i;
+            while (j < order.size() && kps[order[j]].h == kps[order[i]].h)
+                ++j;
+            // run [i, j): usually one string; count occurrences of each distinct string
+            std::vector<char> done(j - i, 0);
+            for (size_t a = i; a < j; ++a)
+            {
+                if (done[a - i])
+                    continue;
+                int cnt = 1;
+                for (size_t b = a + 1; b < j; ++b)
+                    if (!done[b - i] && same_kmer(kps[order[a]], kps[order[b]]))
+                    {
+                        done[b - i] = 1;
+                        ++cnt;
+                    }
+                if (cnt == 1)
+                    uniq.push_back(order[a]);
+            }
+            i = j;
+        }
+        size_t cap = 8;
+        while (cap < 2 * uniq.size() + 1)
+            cap <<= 1;
+        ps.table_off = (int32_t)out.table.size();
+        ps.table_mask = (int32_t)(cap - 1);
+        ps.lists_off = (int32_t)out.lists.size();
+        PathEntry empty;
+        memset(&empty, 0, sizeof empty);
+        out.table.resize(out.table.size() + cap, empty);
+        PathEntry* tab = out.table.data() + ps.table_off;
+        for (uint32_t id : uniq)
+        {
+            const KP& kp = kps[id];
+            PathEntry e;
+            e.key_lo = (uint32_t)kp.h;
+            e.key_hi = (uint32_t)(kp.h >> 32);
+            e.start_pos = kp.start_pos;
+            e.end_pos = kp.end_pos;
+            e.n_nodes = kp.n_nodes;
+            e.nodes_off = (int32_t)(out.lists.size() - (size_t)ps.lists_off);
+            out.lists.insert(out.lists.end(), lists.begin() + kp.list_off, lists.begin() + kp.list_off + kp.n_nodes);
+            uint32_t slot = (uint32_t)(kp.h ^ (kp.h >> 29)) & (uint32_t)ps.table_mask;
+            while (tab[slot].n_nodes != 0)
+                slot = (slot + 1) & (uint32_t)ps.table_mask;
+            tab[slot] = e;
+        }
+        out.sites.push_back(ps);
+    }
 }
 
 // per-read scratch sizes in 32-bit words (see pg_core.cuh "per-task scratch layout")

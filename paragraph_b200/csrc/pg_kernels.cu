@@ -73,6 +73,9 @@ struct FillArgs
     size_t stride_tab;
     TaskOut* tout; // [2 * n_reads] (global task index)
     int smem_words_per_task;
+    // exact-match stage in front (pg_path.cuh): the reads still to align, compacted; null = all reads of the chunk
+    const int32_t* todo;
+    const int32_t* n_todo;
 };
 
 // ---- TMA (bulk async copy) staging of a task's column codes into shared memory ---------------------------------
@@ -198,22 +201,27 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     const int grp = lane / W, gl = lane % W;
     const int wpc = blockDim.x >> 5; // warps per CTA: 4, fewer when the seed tables of a many-node graph need the room
     const int ltask = (blockIdx.x * wpc + wic) * NT + grp;
-    if ((blockIdx.x * wpc + wic) * NT >= a.n_tasks)
+    int n_tasks = a.n_tasks;
+    if (a.todo) // tasks = the reads the exact-match stage left over, in the order it listed them
+        n_tasks = min(n_tasks, 2 * max(*a.n_todo - a.read0, 0));
+    if ((blockIdx.x * wpc + wic) * NT >= n_tasks)
         return; // whole warp beyond the work list
-    const int rd = a.read0 + (ltask >> 1), o = ltask & 1;
-    const bool active = ltask < a.n_tasks && !(o == 1 && !(a.flags & AF_REVERSE_GRAPH));
+    const int o = ltask & 1;
+    const int rd = (ltask < n_tasks) ? (a.todo ? a.todo[a.read0 + (ltask >> 1)] : a.read0 + (ltask >> 1)) : 0;
+    const bool active = ltask < n_tasks && !(o == 1 && !(a.flags & AF_REVERSE_GRAPH));
     uint32_t* prof = smem + ((size_t)wic * NT + grp) * a.smem_words_per_task;
     // [n_nodes_cap][2R][W] seeds, [n_nodes_cap][IW][W] node maxima: warp-private shared memory, or (fallback) HBM
-    uint32_t* seedS = TABG ? a.tabG + (size_t)(ltask < a.n_tasks ? ltask : 0) * a.stride_tab : prof + NCODE * R * W;
+    uint32_t* seedS = TABG ? a.tabG + (size_t)(ltask < n_tasks ? ltask : 0) * a.stride_tab : prof + NCODE * R * W;
     uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * W;
     TaskOut* to = a.tout + (size_t)rd * 2 + o;
-    if (!active && ltask < a.n_tasks && gl == 0)
+    if (!active && ltask < n_tasks && gl == 0)
     {
         TaskOut z;
         memset(&z, 0, sizeof z);
         *to = z;
     }
-    const int rdc = ltask < a.n_tasks ? rd : a.read0; // clamp for inactive tail groups (they only idle along)
+    // inactive tail groups shadow the warp's first read (they only idle along)
+    const int rdc = ltask < n_tasks ? rd : (a.todo ? a.todo[a.read0 + ((ltask - grp) >> 1)] : a.read0 + ((ltask - grp) >> 1));
     const SiteDev sd = a.sites[a.read_site ? a.read_site[rdc] : 0];
     // STAGED: the orientation's node tables (lengths, predecessor lists) are copied next to the seed tables, so that
     // the node-boundary code of the hot loop reads shared memory with 32-bit addresses instead of chasing HBM pointers
@@ -357,6 +365,8 @@ struct TraceArgs
     unsigned long long arena_cap;
     int smem_bytes_per_task;
     int oplog_cap;
+    const int32_t* todo; // see FillArgs
+    const int32_t* n_todo;
 };
 
 template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_kernel(const TraceArgs a)
@@ -367,11 +377,14 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
     const int grp = lane / W, gl = lane % W;
     const unsigned gmask = (W == 32) ? FULL : (((1u << (W & 31)) - 1u) << (grp * W));
     const int lrd0 = (blockIdx.x * TRACE_WARPS + wic) * NT;
-    if (lrd0 >= a.n_reads)
+    int n_reads = a.n_reads;
+    if (a.todo)
+        n_reads = min(n_reads, max(*a.n_todo - a.read0, 0));
+    if (lrd0 >= n_reads)
         return;
-    const bool active = lrd0 + grp < a.n_reads;
+    const bool active = lrd0 + grp < n_reads;
     const int lrd = active ? lrd0 + grp : lrd0; // idle tail groups shadow the warp's first read (no stores)
-    const int rd = a.read0 + lrd;
+    const int rd = a.todo ? a.todo[a.read0 + lrd] : a.read0 + lrd;
     uint8_t* wmem = reinterpret_cast<uint8_t*>(smem) + ((size_t)wic * NT + grp) * a.smem_bytes_per_task;
     uint32_t* prof = reinterpret_cast<uint32_t*>(wmem);
     uint32_t* oplog = prof + NCODE * R * W;
@@ -464,7 +477,7 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         rec.unique = (uint8_t)d.unique;
         rec.chose_reverse = (uint8_t)half;
         rec.status = (uint8_t)(w.phase == 2 ? w.status : 1);
-        rec.reserved = 0;
+        rec.mapped_by = 0;
         rec.query_clipped = (uint16_t)w.clipped;
         rec.cigar_off = 0;
         rec.cigar_len = 0;
@@ -482,6 +495,72 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
             else
                 rec.status = 2;
         }
+        a.records[rd] = rec;
+    }
+}
+
+// ---- exact-match stage (grm::PathAligner, pg_path.cuh): one thread per read ---------------------------------------
+struct PathArgs
+{
+    const SiteDev* sites;
+    const uint8_t* gbytes;
+    const int32_t* gints;
+    const PathSite* psites;
+    const PathEntry* ptable;
+    const int32_t* plists;
+    const int32_t* psucc;
+    const uint8_t* bases;
+    const int32_t* read_off;
+    const int32_t* read_site; // may be null
+    int n_reads;
+    int no_gssw; // no DP stage behind this one: unmapped reads get their (unmapped) record here
+    Record* records;
+    uint32_t* arena;
+    unsigned long long* cursor;
+    unsigned long long arena_cap;
+    int32_t* todo;   // reads the stage did not map, for the DP kernels
+    int32_t* n_todo;
+    unsigned long long* counters; // attempted, anchored, mapped (PathAligner.hh:66-68)
+};
+
+__global__ void __launch_bounds__(128) pg_path_kernel(const PathArgs a)
+{
+    const int rd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rd >= a.n_reads)
+        return;
+    const int site = a.read_site ? a.read_site[rd] : 0;
+    const PathView v = make_path_view(a.psites[site], a.sites[site], a.ptable, a.plists, a.psucc, a.gbytes, a.gints);
+    const uint8_t* bases = a.bases + a.read_off[rd];
+    const int L = a.read_off[rd + 1] - a.read_off[rd];
+    PathResult r;
+    path_scan(v, bases, L, r);
+    if (r.n_matches > 0)
+        atomicAdd(a.counters + 1, 1ull);
+    if (r.n_full > 0)
+    {
+        Record rec;
+        path_record(r, L, rec);
+        const unsigned long long off = atomicAdd(a.cursor, (unsigned long long)rec.cigar_len);
+        if (off + rec.cigar_len <= a.arena_cap)
+        {
+            path_emit(v, bases, L, r, a.arena + off);
+            rec.cigar_off = (uint32_t)off;
+        }
+        else
+        {
+            rec.status = 2;
+            rec.cigar_len = 0;
+        }
+        a.records[rd] = rec;
+        atomicAdd(a.counters + 2, 1ull);
+        return;
+    }
+    a.todo[atomicAdd(a.n_todo, 1)] = rd;
+    if (a.no_gssw) // no later stage: the read stays UNMAPPED (CompositeAligner.cpp:78-176)
+    {
+        Record rec;
+        memset(&rec, 0, sizeof rec);
+        rec.status = (uint8_t)ST_UNMAPPED;
         a.records[rd] = rec;
     }
 }
@@ -655,6 +734,19 @@ struct pg_ctx
     PinBuf<unsigned long long> h_cursor;
     unsigned long long arena_cap = 0;
 
+    // exact-match stage (pg_path.cuh)
+    int path_k = 0; // k-mer length; 0 = the stage is off
+    bool gssw_on = true; // graphMatching of the cascade
+    bool path_dirty = true;
+    DevBuf<PathSite> d_psites;
+    DevBuf<PathEntry> d_ptable;
+    DevBuf<int32_t> d_plists, d_psucc, d_todo, d_ntodo;
+    DevBuf<unsigned long long> d_pcount;
+    unsigned long long path_counters[3] = { 0, 0, 0 };
+    bool path_ran = false;
+    float path_ms = 0;
+    cudaEvent_t path_ev[2] = { nullptr, nullptr };
+
     // counting stage (pg_count.cuh)
     bool count_dirty = true;
     int count_slots = 0;
@@ -719,6 +811,74 @@ int upload_graphs(pg_ctx* c)
     // the source vectors are pageable: the copies above are synchronous with respect to the host buffers
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
     c->graphs_dirty = false;
+    return PG_OK;
+}
+
+template <typename T> cudaError_t put(pg_ctx* c, DevBuf<T>& d, const std::vector<T>& h);
+
+// index of the exact-match stage (unique k-mer paths of every site), built on the host and uploaded once per graph set
+int upload_path_index(pg_ctx* c)
+{
+    if (!c->path_dirty)
+        return PG_OK;
+    host::PathIndexHost ix;
+    host::build_path_index(c->graphs, c->path_k, ix);
+    PG_CUDA(c, put(c, c->d_psites, ix.sites));
+    PG_CUDA(c, put(c, c->d_ptable, ix.table));
+    PG_CUDA(c, put(c, c->d_plists, ix.lists));
+    PG_CUDA(c, put(c, c->d_psucc, ix.succ));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->path_dirty = false;
+    return PG_OK;
+}
+
+// The stage itself: one launch over all reads of the batch.  Mapped reads get their record and op words here; the
+// others are listed in d_todo for the DP kernels.
+int run_path_stage(pg_ctx* c)
+{
+    int rc = upload_path_index(c);
+    if (rc != PG_OK)
+        return rc;
+    const int max_nodes = c->graphs.max_nodes;
+    PG_CUDA(c, c->d_records.reserve((size_t)c->n_reads));
+    PG_CUDA(c, c->d_cursor.reserve(1));
+    PG_CUDA(c, c->d_todo.reserve((size_t)c->n_reads));
+    PG_CUDA(c, c->d_ntodo.reserve(1));
+    PG_CUDA(c, c->d_pcount.reserve(3));
+    c->arena_cap = (unsigned long long)c->n_reads * (unsigned long long)(c->max_len + 2 * max_nodes + 8);
+    PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
+    PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_ntodo.p, 0, sizeof(int32_t), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_pcount.p, 0, 3 * sizeof(unsigned long long), c->stream));
+    for (auto& ev : c->path_ev)
+        if (!ev)
+            PG_CUDA(c, cudaEventCreate(&ev));
+    PathArgs pa;
+    pa.sites = c->d_sites.p;
+    pa.gbytes = c->d_gbytes.p;
+    pa.gints = c->d_gints.p;
+    pa.psites = c->d_psites.p;
+    pa.ptable = c->d_ptable.p;
+    pa.plists = c->d_plists.p;
+    pa.psucc = c->d_psucc.p;
+    pa.bases = c->d_bases.p;
+    pa.read_off = c->d_off.p;
+    pa.read_site = c->have_sites ? c->d_site.p : nullptr;
+    pa.n_reads = c->n_reads;
+    pa.no_gssw = c->gssw_on ? 0 : 1;
+    pa.records = c->d_records.p;
+    pa.arena = c->d_arena.p;
+    pa.cursor = c->d_cursor.p;
+    pa.arena_cap = c->arena_cap;
+    pa.todo = c->d_todo.p;
+    pa.n_todo = c->d_ntodo.p;
+    pa.counters = c->d_pcount.p;
+    PG_CUDA(c, cudaEventRecord(c->path_ev[0], c->stream));
+    pg_path_kernel<<<(c->n_reads + 127) / 128, 128, 0, c->stream>>>(pa);
+    PG_CUDA(c, cudaGetLastError());
+    ++c->launches;
+    PG_CUDA(c, cudaEventRecord(c->path_ev[1], c->stream));
+    c->path_ran = true;
     return PG_OK;
 }
 
@@ -804,7 +964,9 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     const int oplog_cap = 2 * c->max_len + 16;
     c->arena_cap = (unsigned long long)c->n_reads * (unsigned long long)(c->max_len + 2 * max_nodes + 8);
     PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
-    PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
+    const bool after_path = c->path_ran; // the exact-match stage already wrote records / op words
+    if (!after_path)
+        PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
 
     const size_t fill_smem = (size_t)fill_warps * NT * fill_words * sizeof(uint32_t);
     const int trace_bytes = (NCODE * R * W + oplog_cap + 2 * TileGeom<R>::SLOT_WORDS) * 4; // per read
@@ -852,6 +1014,8 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.stride_ckpt = s_ckpt;
         fa.tout = c->d_tout.p;
         fa.smem_words_per_task = fill_words;
+        fa.todo = after_path ? c->d_todo.p : nullptr;
+        fa.n_todo = after_path ? c->d_ntodo.p : nullptr;
         const int fgrid = (fa.n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
         if (tab_global)
             pg_fill_kernel<R, W, false, true><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
@@ -884,6 +1048,8 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         ta.arena_cap = c->arena_cap;
         ta.smem_bytes_per_task = trace_bytes_al;
         ta.oplog_cap = oplog_cap;
+        ta.todo = fa.todo;
+        ta.n_todo = fa.n_todo;
         const int tgrid = (nr + TRACE_WARPS * NT - 1) / (TRACE_WARPS * NT);
         pg_trace_kernel<R, W><<<tgrid, TRACE_WARPS * 32, trace_smem, c->stream>>>(ta);
         PG_CUDA(c, cudaGetLastError());
@@ -957,6 +1123,16 @@ void pg_destroy(pg_ctx* c)
     c->d_tout.release();
     c->d_records.release();
     c->d_cursor.release();
+    c->d_psites.release();
+    c->d_ptable.release();
+    c->d_plists.release();
+    c->d_psucc.release();
+    c->d_todo.release();
+    c->d_ntodo.release();
+    c->d_pcount.release();
+    for (auto& ev : c->path_ev)
+        if (ev)
+            cudaEventDestroy(ev);
     c->h_bases.release();
     c->h_off.release();
     c->h_site.release();
@@ -1002,6 +1178,7 @@ int pg_add_graph(pg_ctx* c, int32_t n_nodes, const char* blob, const int32_t* of
         return fail(c, PG_E_GRAPH, err);
     c->graphs_dirty = true;
     c->count_dirty = true;
+    c->path_dirty = true;
     if (site_id)
         *site_id = id;
     return PG_OK;
@@ -1014,6 +1191,7 @@ int pg_clear_graphs(pg_ctx* c)
     c->graphs.clear();
     c->graphs_dirty = true;
     c->count_dirty = true;
+    c->path_dirty = true;
     return PG_OK;
 }
 
@@ -1105,6 +1283,21 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
     int rc = upload_graphs(c);
     if (rc != PG_OK)
         return rc;
+    c->path_ran = false;
+    if (c->path_k > 0) // grm::CompositeAligner with path matching on: exact matches first, the DP for the rest
+    {
+        rc = run_path_stage(c);
+        if (rc != PG_OK)
+            return rc;
+        if (!c->gssw_on)
+        {
+            c->n_chunks_timed = 0;
+            c->ran = true;
+            return PG_OK;
+        }
+    }
+    else if (!c->gssw_on)
+        return fail(c, PG_E_STATE, "pg_batch_run: no alignment stage enabled (pg_set_stages)");
     // geometry: W lanes per task, R rows per lane (W * R >= read length); see DESIGN.md "geometry"
     // reads over BYTE_MAX_READ_LEN can score past a byte (gssw's 16-bit mode): WIDE geometries, W = 32 only
     if (c->max_len > BYTE_MAX_READ_LEN)
@@ -1472,6 +1665,45 @@ int pg_count_stats(const pg_ctx* c, uint64_t* launches, float* ms)
         *launches = c->count_launches;
     if (ms)
         *ms = c->count_ms;
+    return PG_OK;
+}
+
+int pg_set_stages(pg_ctx* c, int32_t path_kmer_len, int32_t graph_matching)
+{
+    if (!c || path_kmer_len < 0 || path_kmer_len > 4096)
+        return fail(c, PG_E_ARG, "pg_set_stages: bad k-mer length");
+    if (path_kmer_len == 0 && !graph_matching)
+        return fail(c, PG_E_ARG, "pg_set_stages: no alignment stage enabled");
+    if (path_kmer_len != c->path_k)
+        c->path_dirty = true;
+    c->path_k = path_kmer_len;
+    c->gssw_on = graph_matching != 0;
+    return PG_OK;
+}
+
+int pg_path_stats(pg_ctx* c, uint64_t* counters3, float* path_ms)
+{
+    if (!c)
+        return PG_E_ARG;
+    if (c->path_ran)
+    {
+        PG_CUDA(c, cudaSetDevice(c->device));
+        PG_CUDA(c, cudaMemcpyAsync(c->path_counters, c->d_pcount.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                   c->stream));
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->path_counters[0] = (unsigned long long)c->n_reads; // attempted: every read of the batch
+        PG_CUDA(c, cudaEventElapsedTime(&c->path_ms, c->path_ev[0], c->path_ev[1]));
+    }
+    else
+    {
+        c->path_counters[0] = c->path_counters[1] = c->path_counters[2] = 0;
+        c->path_ms = 0;
+    }
+    if (counters3)
+        for (int i = 0; i < 3; ++i)
+            counters3[i] = c->path_counters[i];
+    if (path_ms)
+        *path_ms = c->path_ms;
     return PG_OK;
 }
 

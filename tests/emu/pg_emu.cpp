@@ -236,6 +236,66 @@ int pgemu_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off,
     }
     return worst;
 }
+// The exact-match stage (pg_path.cuh) on the host: same calling convention as pgo_path_align_batch (oracle/pg_oracle.h)
+// plus graph arguments.  out8 = {mapped, graph_pos, score, unique, mapq, is_graph_reverse_strand, cigar_strlen, anchored}
+int pgemu_path_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off, int n_edges, const int32_t* efrom,
+                           const int32_t* eto, int kmer_len, int n_reads, const char* bases_blob,
+                           const int32_t* read_off, int32_t* out8, char* out_bases_blob, char* cigars, int cigar_stride,
+                           int32_t* counters3)
+{
+    host::GraphStore gs;
+    std::string err;
+    if (gs.add(n_nodes, seq_blob, seq_off, n_edges, efrom, eto, err) < 0)
+    {
+        fprintf(stderr, "pgemu: %s\n", err.c_str());
+        return -4;
+    }
+    host::PathIndexHost ix;
+    host::build_path_index(gs, kmer_len, ix);
+    const PathView v = make_path_view(ix.sites[0], gs.sites[0], ix.table.data(), ix.lists.data(), ix.succ.data(),
+                                      gs.bytes.data(), gs.ints.data());
+    counters3[0] = counters3[1] = counters3[2] = 0;
+    for (int i = 0; i < n_reads; ++i)
+    {
+        const uint8_t* b = (const uint8_t*)bases_blob + read_off[i];
+        const int L = read_off[i + 1] - read_off[i];
+        PathResult r;
+        path_scan(v, b, L, r);
+        int32_t* o = out8 + 8 * i;
+        memset(o, 0, 8 * sizeof(int32_t));
+        ++counters3[0];
+        counters3[1] += r.n_matches > 0;
+        o[7] = r.n_matches > 0;
+        std::string cg;
+        if (r.n_full > 0)
+        {
+            Record rec;
+            path_record(r, L, rec);
+            std::vector<uint32_t> ops((size_t)r.first.n_nodes);
+            path_emit(v, b, L, r, ops.data());
+            cg = host::format_cigar(rec, ops.data());
+            o[0] = 1;
+            o[1] = rec.graph_pos;
+            o[2] = rec.score;
+            o[3] = rec.unique;
+            o[4] = rec.unique ? 60 : 0;
+            o[5] = rec.chose_reverse; // PathAligner.cpp:127-135: not combined with the read's own strand
+            o[6] = (int32_t)cg.size();
+            ++counters3[2];
+        }
+        if (out_bases_blob)
+            for (int j = 0; j < L; ++j)
+                out_bases_blob[read_off[i] + j] = (char)path_read_char(b, L, (r.n_full > 0) ? r.strand : 0, j);
+        if (cigars)
+        {
+            size_t n = cg.size() < (size_t)cigar_stride - 1 ? cg.size() : (size_t)cigar_stride - 1;
+            memcpy(cigars + (size_t)i * cigar_stride, cg.data(), n);
+            cigars[(size_t)i * cigar_stride + n] = 0;
+        }
+    }
+    return 0;
+}
+
 // Align + count ONE site on the host with the device code of pg_core.cuh / pg_count.cuh.
 // support: n_reads x 16 bytes (pg_read_support); path_words / ops_out: capacity `cap` words each (the op arena is
 // returned too so that a test can look at the CIGARs); node_counts[n_nodes], edge_counts[n_edges] (4 x u32 each);

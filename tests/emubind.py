@@ -127,3 +127,39 @@ def unpack_family_entries(words):
         out[int(words[w + 2]) | (int(words[w + 3]) << 32)] = np.array(words[w + 4:w + 4 + 4 * n], dtype=np.int64).reshape(n, 4)
         w += 4 + 4 * n
     return out
+
+
+def emu_path_align_batch(node_seqs, edges, reads, kmer_len=32):
+    """The exact-match stage (paragraph_b200/csrc/pg_path.cuh) on the host.  -> (dicts like refbind.ref_path_align_batch,
+    (attempted, anchored, mapped))"""
+    l = lib()
+    l.pgemu_path_align_batch.restype = C.c_int
+    l.pgemu_path_align_batch.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int32)]
+    blob = "".join(node_seqs).encode("latin-1")
+    off = np.zeros(len(node_seqs) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(s) for s in node_seqs])
+    ef = np.array([e[0] for e in edges], dtype=np.int32)
+    et = np.array([e[1] for e in edges], dtype=np.int32)
+    rblob = "".join(reads).encode("latin-1")
+    roff = np.zeros(len(reads) + 1, dtype=np.int32)
+    roff[1:] = np.cumsum([len(s) for s in reads])
+    n = len(reads)
+    out = np.zeros((n, 8), dtype=np.int32)
+    ob = C.create_string_buffer(max(1, len(rblob)))
+    cg = C.create_string_buffer(max(1, n * CIGAR_STRIDE))
+    cnt = np.zeros(3, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+    rc = l.pgemu_path_align_batch(len(node_seqs), blob, p(off), len(edges), p(ef), p(et), int(kmer_len), n, rblob, p(roff),
+                                  p(out), ob, cg, CIGAR_STRIDE, p(cnt))
+    if rc != 0:
+        raise RuntimeError("pgemu_path_align_batch rc=%d" % rc)
+    raw = ob.raw
+    res = []
+    for i in range(n):
+        c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
+        o = out[i]
+        res.append(dict(mapped=bool(o[0]), pos=int(o[1]), score=int(o[2]), unique=bool(o[3]), mapq=int(o[4]),
+                        graph_reverse=bool(o[5]), bases=raw[roff[i]:roff[i + 1]].decode("latin-1"), cigar=c))
+    return res, tuple(int(x) for x in cnt)

@@ -303,3 +303,94 @@ def test_runs_on_a_caller_stream(ctx):
         assert got == [b["cigar"] for b in base]
     finally:
         ctx.set_stream(None)
+
+
+# ---------------------------------------------------------------- exact-match stage in front of the DP (pg_set_stages)
+def _cascade_expected(nodes, edges, reads, k, isrev=None, graph_matching=True):
+    """grm::CompositeAligner(path=true, graph=graph_matching): PathAligner first, gssw for the reads it leaves unmapped
+    (lib/grm/CompositeAligner.cpp:90-107, 146-170), from the two oracles."""
+    pexp, cnt = R.OraclePathIndex(nodes, edges, k).align_batch(reads)
+    gexp = R.OracleGraph(nodes, edges).align_batch(reads, is_rev=isrev) if graph_matching else [None] * len(reads)
+    out = []
+    for p, g in zip(pexp, gexp):
+        if p["mapped"]:
+            d = {key: p[key] for key in ("pos", "score", "unique", "mapq", "graph_reverse", "bases", "cigar")}
+            d["stage"] = "path"
+        elif g is not None:
+            d = dict(g)
+            d["stage"] = "gssw"
+        else:
+            d = None
+        out.append(d)
+    return out, cnt
+
+
+def test_path_stage_then_dp(ctx):
+    from test_path_oracle import path_cases
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(47)
+    n = by_path = 0
+    try:
+        for nodes, edges, reads, k in path_cases(rng, 120):
+            isrev = [i & 1 for i in range(len(reads))]
+            ctx.clear_graphs()
+            ctx.add_graph(nodes, edges)
+            ctx.set_stages(k, True)
+            exp, cnt = _cascade_expected(nodes, edges, reads, k, isrev)
+            got = strip_status(ctx.align(reads, is_rev=isrev))
+            assert got == exp, (nodes, edges, k)
+            st = ctx.path_stats()
+            assert (st["attempted"], st["anchored"], st["mapped"]) == cnt
+            n += len(reads)
+            by_path += sum(e["stage"] == "path" for e in exp)
+        assert by_path > n // 4 and by_path < n
+    finally:
+        ctx.set_stages(0, True)
+
+
+def test_path_stage_alone_leaves_reads_unmapped(ctx):
+    rng = np.random.default_rng(48)
+    nodes, edges = synth.del_graph(rng, 200, 80)
+    reads = synth.simulate_reads(rng, nodes, edges, 200, read_len=100, sub=0.004, indel_frac=0.0)
+    try:
+        ctx.clear_graphs()
+        ctx.add_graph(nodes, edges)
+        ctx.set_stages(32, False)
+        exp, cnt = _cascade_expected(nodes, edges, reads, 32, graph_matching=False)
+        got = ctx.align(reads)
+        assert 0 < cnt[2] < len(reads)
+        for g, e in zip(got, exp):
+            if e is None:
+                assert g["status"] == 3
+            else:
+                assert g.pop("status") == 0 and g.pop("clipped") == 0
+                assert g == e
+        with pytest.raises(capi.PgError):
+            ctx.set_stages(0, False)  # no stage at all
+    finally:
+        ctx.set_stages(0, True)
+
+
+def test_path_stage_config2_mix(ctx):
+    """10k-read shape of the benchmark: most reads differ from the haplotypes by >= 1 base (1 % substitutions), the
+    rest are exact -- both populations must come out as the cascade of the two oracles says, across multiple sites."""
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(49)
+    try:
+        ctx.clear_graphs()
+        ctx.set_stages(32, True)
+        reads, sites, exp = [], [], []
+        for s in range(6):
+            nodes, edges = synth.del_graph(rng, 300, int(rng.integers(40, 200)))
+            rd = synth.simulate_reads(rng, nodes, edges, 150, read_len=150, sub=0.002, indel_frac=0.002)
+            sid = ctx.add_graph(nodes, edges)
+            e, _ = _cascade_expected(nodes, edges, rd, 32)
+            reads += rd
+            sites += [sid] * len(rd)
+            exp += e
+        got = strip_status(ctx.align(reads, sites=sites))
+        assert got == exp
+        frac = sum(e["stage"] == "path" for e in exp) / len(exp)
+        assert 0.3 < frac < 0.95
+    finally:
+        ctx.set_stages(0, True)

@@ -64,3 +64,30 @@ def test_golden_fixtures(built):
         got, cnt = R.OraclePathIndex(case["nodes"], [tuple(e) for e in case["edges"]], case["k"]).align_batch(case["reads"])
         assert got == case["expected"], case["name"]
         assert list(cnt) == case["counters"]
+
+
+def test_device_code_on_host_matches_oracle(built):
+    """paragraph_b200/csrc/pg_path.cuh (the kernel's source, compiled for the host by tests/emu) + the host-side index
+    builder (pg_host.hpp: build_path_index) against the oracle restatement: same reads mapped, same position, CIGAR,
+    strand, uniqueness, counters."""
+    import emubind
+    rng = np.random.default_rng(43)
+    n = mapped = 0
+    for nodes, edges, reads, k in path_cases(rng, 250):
+        exp, ecnt = R.OraclePathIndex(nodes, edges, k).align_batch(reads)
+        got, gcnt = emubind.emu_path_align_batch(nodes, edges, reads, kmer_len=k)
+        assert got == exp, (nodes, edges, k)
+        assert gcnt == ecnt
+        n += len(reads)
+        mapped += sum(e["mapped"] for e in exp)
+    assert mapped > n // 4
+
+
+def test_device_code_on_host_golden(built):
+    import emubind
+    with open(os.path.join(GOLDEN_DIR, "path_aligner.json")) as f:
+        doc = json.load(f)
+    for case in doc["cases"]:
+        got, cnt = emubind.emu_path_align_batch(case["nodes"], [tuple(e) for e in case["edges"]], case["reads"], case["k"])
+        assert got == case["expected"], case["name"]
+        assert list(cnt) == case["counters"]
