@@ -34,6 +34,7 @@ extern "C" {
 /* pg_record::mapped_by: the stage of grm::CompositeAligner that mapped the read */
 #define PG_STAGE_GSSW_ID 0
 #define PG_STAGE_PATH_ID 1
+#define PG_STAGE_GSSW_REV_ID 2 /* gssw, after the exact-match stage had reverse-complemented the bases (second chance) */
 
 /* GraphAligner alignment flags (src/c++/include/grm/GraphAligner.hh:64-67) */
 #define PG_AF_CIGAR 0x01u
@@ -59,10 +60,12 @@ typedef struct pg_record
     uint8_t chose_reverse;
     uint8_t status; /* 0 ok; 1 traceback dead end (the reference would assert/spin); 2 op log overflow;
                        3 unmapped: no enabled stage mapped the read (graph_mapping_status stays UNMAPPED) */
-    uint8_t mapped_by; /* stage of grm::CompositeAligner that mapped the read: PG_STAGE_GSSW or PG_STAGE_PATH.  The
-                          two stages set the strand differently: gssw -> is_graph_reverse_strand =
-                          is_reverse_strand != chose_reverse, quals reversed too (GraphAligner.cpp:358-378);
-                          PathAligner -> is_graph_reverse_strand = chose_reverse, quals untouched (PathAligner.cpp:124-135) */
+    uint8_t mapped_by; /* stage of grm::CompositeAligner that mapped the read (PG_STAGE_*_ID).  The stages set the
+                          strand differently: gssw -> is_graph_reverse_strand = is_reverse_strand != chose_reverse,
+                          bases reverse-complemented and quals reversed if chose_reverse (GraphAligner.cpp:358-378);
+                          PathAligner -> is_graph_reverse_strand = chose_reverse, bases reverse-complemented, quals
+                          untouched (PathAligner.cpp:124-135); GSSW_REV -> as gssw, applied to bases that PathAligner
+                          had already reverse-complemented once */
     uint32_t cigar_off;
     uint32_t cigar_len;
 } pg_record;
@@ -219,9 +222,17 @@ int pg_count_stats(const pg_ctx* ctx, uint64_t* kernel_launches, float* last_cou
  *                       the next pg_batch_run.
  *   graph_matching    : the gssw stage (the DP kernels) for the reads still unmapped; when 0 they stay unmapped
  *                       (pg_record::status 3).
+ *   nonuniq_second_chance : the cascade runs the caller's read filter right after the exact-match stage and hands a
+ *                       rejected read to the later stages (CompositeAligner.cpp:97-103).  With paragraph's default
+ *                       filter chain that happens exactly to NON-UNIQUE exact matches (NonUniq, ReadFilter.cpp:79-83;
+ *                       BadAlign never rejects an unclipped match).  1 = do that on the device: such a read goes to
+ *                       the DP with the bases PathAligner left behind (reverse-complemented if its first match was on
+ *                       the reverse strand; mapped_by = PG_STAGE_GSSW_REV_ID then).  0 = report the non-unique exact
+ *                       match itself (what the cascade does with a null filter); a host adapter with an arbitrary
+ *                       filter callback re-submits rejected reads itself (pg_grm.hh).
  * Default: path_kmer_len = 0, graph_matching = 1 (what grmpy runs: src/c++/main/grmpy.cpp:69-72).  The KmerAligner
  * and KlibAligner stages are not built. */
-int pg_set_stages(pg_ctx* ctx, int32_t path_kmer_len, int32_t graph_matching);
+int pg_set_stages(pg_ctx* ctx, int32_t path_kmer_len, int32_t graph_matching, int32_t nonuniq_second_chance);
 /* counters3 = {attempted, anchored, mapped} of the last batch (PathAligner::attempted/anchored/mapped,
  * PathAligner.hh:66-68) and the stage's device time in ms. */
 int pg_path_stats(pg_ctx* ctx, uint64_t* counters3, float* path_ms);

@@ -98,7 +98,7 @@ def load():
     lib.pg_count_stats.restype = C.c_int
     lib.pg_count_stats.argtypes = [vp, u64p, C.POINTER(C.c_float)]
     lib.pg_set_stages.restype = C.c_int
-    lib.pg_set_stages.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.pg_set_stages.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
     lib.pg_path_stats.restype = C.c_int
     lib.pg_path_stats.argtypes = [vp, u64p, C.POINTER(C.c_float)]
     lib.pg_batch_count.restype = C.c_int
@@ -196,9 +196,11 @@ class Context:
     def set_scratch_limit(self, nbytes):
         self._check(self.lib.pg_set_scratch_limit(self.h, int(nbytes)))
 
-    def set_stages(self, path_kmer_len=0, graph_matching=True):
-        """grm::CompositeAligner's cascade: exact-match stage (PathAligner, k-mer length; 0 = off) in front of the DP."""
-        self._check(self.lib.pg_set_stages(self.h, int(path_kmer_len), 1 if graph_matching else 0))
+    def set_stages(self, path_kmer_len=0, graph_matching=True, nonuniq_second_chance=False):
+        """grm::CompositeAligner's cascade: exact-match stage (PathAligner, k-mer length; 0 = off) in front of the DP;
+        nonuniq_second_chance: a non-unique exact match goes on to the DP (what the NonUniq read filter causes)."""
+        self._check(self.lib.pg_set_stages(self.h, int(path_kmer_len), 1 if graph_matching else 0,
+                                           1 if nonuniq_second_chance else 0))
         self._path_k = int(path_kmer_len)
 
     def path_stats(self):
@@ -366,6 +368,8 @@ class Context:
             x = rec[i]
             rv = bool(x["chose_reverse"])
             by_path = int(x["mapped_by"]) == 1  # PathAligner sets the strand itself and always writes a CIGAR
+            if int(x["mapped_by"]) == 2:  # second chance: gssw saw the bases PathAligner had reverse-complemented
+                r = revcomp_exact(r)
             d = dict(pos=int(x["graph_pos"]), score=int(x["score"]), unique=bool(x["unique"]),
                      mapq=60 if x["unique"] else 0,
                      graph_reverse=rv if by_path else (bool(is_rev[i] if is_rev is not None else 0) != rv),
@@ -373,7 +377,7 @@ class Context:
                      cigar=format_cigar(x, ops) if (flags & AF_CIGAR or by_path) else "", status=int(x["status"]),
                      clipped=int(x["query_clipped"]))
             if getattr(self, "_path_k", 0):
-                d["stage"] = "path" if by_path else "gssw"
+                d["stage"] = ("gssw", "path", "gssw2")[int(x["mapped_by"])]
             out.append(d)
         return out
 

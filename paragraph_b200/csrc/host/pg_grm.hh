@@ -14,7 +14,8 @@
 // The GPU engine is batch-first: alignReads() makes ONE pg_align_batch call for the whole read vector
 // (results are written back in input order, so the outcome is deterministic for any `threads`); the per-read
 // alignRead() facades are batches of one.  Only the gssw stage (graph_sequence_matching) runs on the GPU;
-// asking for the path / kmer / klib stages throws (they are SURVEY.md 8f "next" rows, not silently skipped).
+// the path stage (grm::PathAligner) and the gssw stage run on the GPU; asking for the kmer / klib stages throws
+// (SURVEY.md 8f "next" rows, not silently skipped).
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -242,7 +243,8 @@ public:
     // the loop `for read: alignRead(read, flags)` as one batch; writes the fields GraphAligner::alignRead writes
     // (GraphAligner.cpp:358-401).  ReadIt iterates over (smart) pointers to reads; empty reads are skipped.
     template <typename ReadIt>
-    void alignBatch(ReadIt begin, ReadIt end, unsigned flags = AF_ALL, std::vector<pg_record>* records_out = nullptr) const
+    void alignBatch(ReadIt begin, ReadIt end, unsigned flags = AF_ALL, std::vector<pg_record>* records_out = nullptr,
+                    bool tolerate_unmapped = false) const
     {
         std::string blob;
         std::vector<int32_t> off{ 0 };
@@ -265,7 +267,8 @@ public:
         if (records_out) // e.g. for paragraph::DefaultReadFilter, which needs query_clipped
             *records_out = rec;
         for (size_t i = 0; i < which.size(); ++i)
-            applyRecord(**which[i], rec[i], ops.data(), flags, i);
+            if (!(tolerate_unmapped && rec[i].status == 3)) // 3: no enabled stage mapped the read -- it stays UNMAPPED
+                applyRecord(**which[i], rec[i], ops.data(), flags, i);
     }
 
     // write one record back into a read: the fields GraphAligner::alignRead sets (GraphAligner.cpp:358-401)
@@ -274,6 +277,23 @@ public:
     {
         if (r.status != 0)
             throw std::runtime_error("paragraph_b200: traceback failed for read " + std::to_string(index));
+        if (r.mapped_by == PG_STAGE_PATH_ID) // what PathAligner::alignRead writes (PathAligner.cpp:124-161)
+        {
+            read.set_is_graph_reverse_strand(r.chose_reverse != 0);
+            if (r.chose_reverse)
+                read.set_bases(reverseComplement(read.bases())); // quals stay as they are
+            read.set_graph_alignment_score(r.score);
+            read.set_graph_pos(r.graph_pos);
+            std::string buf((size_t)12 * (r.cigar_len + 2), '\0');
+            const int n = pg_format_cigar(&r, ops, &buf[0], (int)buf.size());
+            buf.resize((size_t)std::min<int>(n, (int)buf.size() - 1));
+            read.set_graph_cigar(buf);
+            read.set_is_graph_alignment_unique(r.unique != 0);
+            read.set_graph_mapq(r.unique ? 60 : 0);
+            return;
+        }
+        if (r.mapped_by == PG_STAGE_GSSW_REV_ID) // the exact-match stage had reverse-complemented the bases first
+            read.set_bases(reverseComplement(read.bases()));
         read.set_is_graph_reverse_strand(read.is_reverse_strand() != (r.chose_reverse != 0)); // :358-359
         if (r.chose_reverse) // :375-378
         {
@@ -327,6 +347,12 @@ template <typename ReadPtrT> class MultiSiteAligner
 {
 public:
     explicit MultiSiteAligner(int device = 0, unsigned flags = GraphAligner::AF_ALL) : engine_(new Engine(device)), flags_(flags) {}
+
+    // path_sequence_matching of alignAndDisambiguate (`paragraph` switches it on by default, main/paragraph.cpp:60):
+    // the exact-match stage (grm::PathAligner, k-mer size 32 in the reference) runs in front of gssw in alignAndCount().
+    // A non-unique exact match is what the default filter chain rejects right after that stage; it then gets its second
+    // chance in gssw on the device (pg_set_stages: nonuniq_second_chance) iff remove_nonuniq_reads is set.
+    void setPathMatching(int kmer_len) { path_kmer_ = kmer_len; }
 
     // register a site: its graph and its reads (the vector is updated in place by run(), like grm::alignReads does)
     template <typename GraphT> void addSite(GraphT const* g, std::vector<ReadPtrT>* reads)
@@ -415,6 +441,7 @@ public:
             std::vector<pg_record> rec(which.size());
             std::vector<uint32_t> ops(blob.size() + 16 * which.size() + 64);
             uint64_t used = 0, path_used = 0;
+            engine_->check(pg_set_stages(engine_->get(), path_kmer_, 1, opt.remove_nonuniq_reads ? 1 : 0));
             engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), blob.data(), off.data(), site.data(), flags_,
                                           rec.data(), ops.data(), ops.size(), &used));
             path.resize(used + 1);
@@ -539,6 +566,7 @@ public:
             std::vector<pg_record> rec(which.size());
             std::vector<uint32_t> ops(blob.size() + 16 * which.size() + 64);
             uint64_t used = 0;
+            engine_->check(pg_set_stages(engine_->get(), 0, 1, 0)); // run(filter): gssw stage only
             engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), blob.data(), off.data(), site.data(), flags_,
                                           rec.data(), ops.data(), ops.size(), &used));
             for (size_t i = 0; i < which.size(); ++i)
@@ -593,6 +621,7 @@ private:
     }
     std::unique_ptr<Engine> engine_;
     unsigned flags_;
+    int path_kmer_ = 0;
     std::vector<Site> sites_;
 };
 
@@ -602,43 +631,87 @@ class CompositeAligner
 {
 public:
     CompositeAligner(bool pathMatching, bool graphMatching, bool klibMatching, bool kmerMatching,
-                     unsigned graphAlignmentFlags = GraphAligner::AF_ALL, int device = 0)
-        : graphMatching_(graphMatching), flags_(graphAlignmentFlags), graphAligner_(device)
+                     unsigned graphAlignmentFlags = GraphAligner::AF_ALL, int device = 0, int pathKmerSize = 32)
+        : pathMatching_(pathMatching), graphMatching_(graphMatching), flags_(graphAlignmentFlags),
+          pathKmerSize_(pathKmerSize), graphAligner_(device)
     {
-        if (pathMatching || klibMatching || kmerMatching)
-            throw std::runtime_error("paragraph_b200: only the gssw stage (graph_sequence_matching) runs on the GPU; "
-                                     "path / klib / kmer matching must stay on the reference's CPU aligners");
+        if (klibMatching || kmerMatching)
+            throw std::runtime_error("paragraph_b200: the path and gssw stages run on the GPU; "
+                                     "klib / kmer matching must stay on the reference's CPU aligners");
     }
     template <typename GraphT, typename PathListT> void setGraph(GraphT const* graph, PathListT const&)
     {
         graphAligner_.setGraph(graph);
     }
 
-    // CompositeAligner::alignRead for a whole range (CompositeAligner.cpp:78-176, gssw branch :152-175):
-    // every read becomes MAPPED, then the filter may turn it into BAD_ALIGN; counters as in the reference.
+    // CompositeAligner::alignRead for a whole range (CompositeAligner.cpp:78-176): exact-match stage (:82-95), the
+    // filter right after it with a second chance for rejected reads (:97-103), gssw stage (:146-175: every read it
+    // sees becomes MAPPED, then the filter may turn it into BAD_ALIGN); counters as in the reference.
     template <typename ReadIt, typename FilterT> void alignReads(ReadIt begin, ReadIt end, FilterT filter)
     {
-        if (!graphMatching_)
+        typedef typename std::remove_reference<decltype(**begin)>::type ReadT;
+        if (!pathMatching_ && !graphMatching_)
         {
             for (ReadIt it = begin; it != end; ++it)
                 attempted_ += !(*it)->bases().empty();
             return;
         }
-        graphAligner_.alignBatch(begin, end, flags_);
+        graphAligner_.check(pg_set_stages(graphAligner_.context(), pathMatching_ ? pathKmerSize_ : 0, graphMatching_ ? 1 : 0, 0));
+        std::vector<pg_record> rec;
+        graphAligner_.alignBatch(begin, end, flags_, &rec, /*tolerate_unmapped=*/true);
+        std::vector<ReadT*> again; // rejected right after the exact-match stage: second chance in the gssw stage
+        size_t i = 0;
         for (ReadIt it = begin; it != end; ++it)
         {
-            auto& read = **it;
+            ReadT& read = **it;
             if (read.bases().empty())
                 continue;
             ++attempted_;
-            read.set_graph_mapping_status(std::remove_reference<decltype(read)>::type::MAPPED);
-            if (filter && filter(read))
+            const pg_record& r = rec[i++];
+            if (r.status == 3) // no stage mapped it (graphMatching off)
+                continue;
+            read.set_graph_mapping_status(ReadT::MAPPED);
+            const bool rejected = filter && filter(read);
+            if (r.mapped_by == PG_STAGE_PATH_ID)
             {
-                read.set_graph_mapping_status(std::remove_reference<decltype(read)>::type::BAD_ALIGN);
+                ++mappedPath_;
+                if (rejected)
+                {
+                    read.set_graph_mapping_status(ReadT::BAD_ALIGN);
+                    filtered_ += !graphMatching_;
+                    if (graphMatching_)
+                        again.push_back(&read);
+                }
+            }
+            else if (rejected)
+            {
+                read.set_graph_mapping_status(ReadT::BAD_ALIGN);
                 ++filtered_;
             }
             else
                 ++mappedSw_;
+        }
+        if (pathMatching_)
+        {
+            uint64_t cnt[3] = { 0, 0, 0 };
+            graphAligner_.check(pg_path_stats(graphAligner_.context(), cnt, nullptr));
+            anchoredPath_ += (unsigned)cnt[1];
+        }
+        if (!again.empty())
+        {
+            graphAligner_.check(pg_set_stages(graphAligner_.context(), 0, 1, 0));
+            graphAligner_.alignBatch(again.begin(), again.end(), flags_);
+            for (ReadT* p : again)
+            {
+                p->set_graph_mapping_status(ReadT::MAPPED);
+                if (filter && filter(*p))
+                {
+                    p->set_graph_mapping_status(ReadT::BAD_ALIGN);
+                    ++filtered_;
+                }
+                else
+                    ++mappedSw_;
+            }
         }
     }
     template <typename ReadT, typename FilterT> void alignRead(ReadT& read, FilterT filter)
@@ -650,16 +723,17 @@ public:
     unsigned attempted() const { return attempted_; }
     unsigned filtered() const { return filtered_; }
     unsigned mappedKlib() const { return 0; }
-    unsigned mappedPath() const { return 0; }
-    unsigned anchoredPath() const { return 0; }
+    unsigned mappedPath() const { return mappedPath_; }
+    unsigned anchoredPath() const { return anchoredPath_; }
     unsigned mappedKmers() const { return 0; }
     unsigned mappedSw() const { return mappedSw_; }
 
 private:
-    const bool graphMatching_;
+    const bool pathMatching_, graphMatching_;
     const unsigned flags_;
+    const int pathKmerSize_;
     GraphAligner graphAligner_;
-    unsigned attempted_ = 0, filtered_ = 0, mappedSw_ = 0;
+    unsigned attempted_ = 0, filtered_ = 0, mappedSw_ = 0, mappedPath_ = 0, anchoredPath_ = 0;
 };
 
 // grm::alignReads (Align.hh:49-52; Align.cpp:114-156): aligns, then keeps only MAPPED reads (input order).

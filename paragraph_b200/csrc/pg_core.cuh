@@ -758,7 +758,7 @@ PG_HD Decision decide_strand(const TaskOut& fw, const TaskOut& rv, unsigned flag
 // ---------------------------------------------------------------------------------------------
 // output records (these two structs ARE the C-ABI result layout, see include/pg_align.h)
 // ---------------------------------------------------------------------------------------------
-constexpr int STAGE_GSSW = 0, STAGE_PATH = 1; // Record::mapped_by
+constexpr int STAGE_GSSW = 0, STAGE_PATH = 1, STAGE_GSSW_REV = 2; // Record::mapped_by (include/pg_align.h)
 constexpr int ST_UNMAPPED = 3;                // Record::status: no enabled stage mapped the read
 struct Record
 {

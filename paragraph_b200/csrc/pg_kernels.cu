@@ -367,6 +367,7 @@ struct TraceArgs
     int oplog_cap;
     const int32_t* todo; // see FillArgs
     const int32_t* n_todo;
+    const uint8_t* prerev; // see PathArgs; null without the exact-match stage
 };
 
 template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_kernel(const TraceArgs a)
@@ -477,7 +478,7 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         rec.unique = (uint8_t)d.unique;
         rec.chose_reverse = (uint8_t)half;
         rec.status = (uint8_t)(w.phase == 2 ? w.status : 1);
-        rec.mapped_by = 0;
+        rec.mapped_by = (uint8_t)((a.prerev && a.prerev[rd]) ? STAGE_GSSW_REV : STAGE_GSSW);
         rec.query_clipped = (uint16_t)w.clipped;
         rec.cigar_off = 0;
         rec.cigar_len = 0;
@@ -509,11 +510,13 @@ struct PathArgs
     const PathEntry* ptable;
     const int32_t* plists;
     const int32_t* psucc;
-    const uint8_t* bases;
+    uint8_t* bases; // writable: a second-chance read is reverse-complemented in place like PathAligner.cpp:124-128 does
     const int32_t* read_off;
     const int32_t* read_site; // may be null
     int n_reads;
     int no_gssw; // no DP stage behind this one: unmapped reads get their (unmapped) record here
+    int second_chance; // the caller's filter has NonUniq: a non-unique exact match goes on to the DP (see pg_set_stages)
+    uint8_t* prerev;   // [n_reads] 1 = bases were reverse-complemented here before the DP saw them
     Record* records;
     uint32_t* arena;
     unsigned long long* cursor;
@@ -530,12 +533,31 @@ __global__ void __launch_bounds__(128) pg_path_kernel(const PathArgs a)
         return;
     const int site = a.read_site ? a.read_site[rd] : 0;
     const PathView v = make_path_view(a.psites[site], a.sites[site], a.ptable, a.plists, a.psucc, a.gbytes, a.gints);
-    const uint8_t* bases = a.bases + a.read_off[rd];
+    uint8_t* bases = a.bases + a.read_off[rd];
     const int L = a.read_off[rd + 1] - a.read_off[rd];
     PathResult r;
     path_scan(v, bases, L, r);
     if (r.n_matches > 0)
         atomicAdd(a.counters + 1, 1ull);
+    a.prerev[rd] = 0;
+    if (r.n_full > 1 && a.second_chance && !a.no_gssw)
+    {
+        // MAPPED by this stage but not unique: the NonUniq filter turns it into BAD_ALIGN and the gssw stage gets the
+        // read (CompositeAligner.cpp:97-103, 146-170) -- with the bases PathAligner left behind
+        atomicAdd(a.counters + 2, 1ull);
+        if (r.strand)
+        {
+            for (int x = 0, y = L - 1; x <= y; ++x, --y)
+            {
+                const uint8_t cx = complement_base(bases[x]), cy = complement_base(bases[y]);
+                bases[x] = cy;
+                bases[y] = cx;
+            }
+            a.prerev[rd] = 1;
+        }
+        a.todo[atomicAdd(a.n_todo, 1)] = rd;
+        return;
+    }
     if (r.n_full > 0)
     {
         Record rec;
@@ -737,6 +759,8 @@ struct pg_ctx
     // exact-match stage (pg_path.cuh)
     int path_k = 0; // k-mer length; 0 = the stage is off
     bool gssw_on = true; // graphMatching of the cascade
+    bool path_second_chance = false;
+    DevBuf<uint8_t> d_prerev;
     bool path_dirty = true;
     DevBuf<PathSite> d_psites;
     DevBuf<PathEntry> d_ptable;
@@ -845,6 +869,7 @@ int run_path_stage(pg_ctx* c)
     PG_CUDA(c, c->d_todo.reserve((size_t)c->n_reads));
     PG_CUDA(c, c->d_ntodo.reserve(1));
     PG_CUDA(c, c->d_pcount.reserve(3));
+    PG_CUDA(c, c->d_prerev.reserve((size_t)c->n_reads));
     c->arena_cap = (unsigned long long)c->n_reads * (unsigned long long)(c->max_len + 2 * max_nodes + 8);
     PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
     PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
@@ -866,6 +891,8 @@ int run_path_stage(pg_ctx* c)
     pa.read_site = c->have_sites ? c->d_site.p : nullptr;
     pa.n_reads = c->n_reads;
     pa.no_gssw = c->gssw_on ? 0 : 1;
+    pa.second_chance = c->path_second_chance ? 1 : 0;
+    pa.prerev = c->d_prerev.p;
     pa.records = c->d_records.p;
     pa.arena = c->d_arena.p;
     pa.cursor = c->d_cursor.p;
@@ -1050,6 +1077,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         ta.oplog_cap = oplog_cap;
         ta.todo = fa.todo;
         ta.n_todo = fa.n_todo;
+        ta.prerev = after_path ? c->d_prerev.p : nullptr;
         const int tgrid = (nr + TRACE_WARPS * NT - 1) / (TRACE_WARPS * NT);
         pg_trace_kernel<R, W><<<tgrid, TRACE_WARPS * 32, trace_smem, c->stream>>>(ta);
         PG_CUDA(c, cudaGetLastError());
@@ -1130,6 +1158,7 @@ void pg_destroy(pg_ctx* c)
     c->d_todo.release();
     c->d_ntodo.release();
     c->d_pcount.release();
+    c->d_prerev.release();
     for (auto& ev : c->path_ev)
         if (ev)
             cudaEventDestroy(ev);
@@ -1668,7 +1697,7 @@ int pg_count_stats(const pg_ctx* c, uint64_t* launches, float* ms)
     return PG_OK;
 }
 
-int pg_set_stages(pg_ctx* c, int32_t path_kmer_len, int32_t graph_matching)
+int pg_set_stages(pg_ctx* c, int32_t path_kmer_len, int32_t graph_matching, int32_t nonuniq_second_chance)
 {
     if (!c || path_kmer_len < 0 || path_kmer_len > 4096)
         return fail(c, PG_E_ARG, "pg_set_stages: bad k-mer length");
@@ -1678,6 +1707,7 @@ int pg_set_stages(pg_ctx* c, int32_t path_kmer_len, int32_t graph_matching)
         c->path_dirty = true;
     c->path_k = path_kmer_len;
     c->gssw_on = graph_matching != 0;
+    c->path_second_chance = nonuniq_second_chance != 0;
     return PG_OK;
 }
 

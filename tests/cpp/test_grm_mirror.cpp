@@ -2,6 +2,8 @@
 // grm::alignReads (src/c++/test/test_paragraph_parts.cpp:52-104): same graph, same reads, gssw stage only.
 // Prints one line per surviving read: id pos cigar score mapq reverse bases status
 #include <cstdio>
+#include <cstring>
+#include <string>
 #include <list>
 #include <memory>
 #include <vector>
@@ -45,13 +47,13 @@ int main()
         bool threw = false;
         try
         {
-            grm::CompositeAligner bad(true, true, false, false);
+            grm::CompositeAligner bad(true, true, true, false); // klib stage: not on the GPU
         }
         catch (std::runtime_error const&)
         {
             threw = true;
         }
-        printf("path-stage-throws %d\n", (int)threw);
+        printf("klib-stage-throws %d\n", (int)threw);
 
         // alignAndDisambiguate's core on the device: ParagraphTest.Aligns expects these supports
         // (test_paragraph_parts.cpp:113-144; the test calls disambiguateReads with null filters)
@@ -122,6 +124,27 @@ int main()
         for (auto const& r : c)
             printf("m %s %d %s %d %d\n", r->fragment_id().c_str(), r->graph_pos(), r->graph_cigar().c_str(),
                    r->graph_alignment_score(), (int)r->is_graph_reverse_strand());
+        // the cascade: exact-match stage (PathAligner, k = 8 so that it bites on this tiny graph) in front of gssw, with the
+        // NonUniq filter -- c10 matches exactly on both strands (non-unique for PathAligner), is rejected by the filter
+        // and gets its second chance in the gssw stage (CompositeAligner.cpp:97-103)
+        {
+            const char* cr[] = { "AAAAAAAATTTTTTTTAAAAAAAA", "TTTTTTTTAAAAAAAATTTTTTTT", "AAAAAAAATTTTCTTTAAAAAAAA", "AAAAAAAAAAAAAAAAAAA",
+                                 "GGGGGGGG", "ATATATAT", "AAAATTTTTTTTAAAA", "AAAGGGGGGGGAAA", "TTTCCCCCCCCTTT", "AAAAAATTTTTT" };
+            std::vector<std::unique_ptr<Read>> cs;
+            for (int i = 0; i < 10; ++i)
+                cs.emplace_back(new Read("c" + std::to_string(i + 1), cr[i], std::string(strlen(cr[i]), '#')));
+            grm::CompositeAligner cascade(true, true, false, false, grm::GraphAligner::AF_ALL, 0, 8);
+            cascade.setGraph(&graph, paths);
+            for (auto& r : cs)
+                r->set_graph_mapping_status(Read::UNMAPPED);
+            cascade.alignReads(cs.begin(), cs.end(), filter);
+            for (auto const& r : cs)
+                printf("%s %d %s %d %d %d %s %d\n", r->fragment_id().c_str(), r->graph_pos(), r->graph_cigar().c_str(),
+                       r->graph_alignment_score(), r->graph_mapq(), (int)r->is_graph_reverse_strand(), r->bases().c_str(),
+                       (int)r->graph_mapping_status());
+            printf("cascade %u %u %u %u %u\n", cascade.attempted(), cascade.mappedPath(), cascade.anchoredPath(),
+                   cascade.mappedSw(), cascade.filtered());
+        }
     }
     catch (std::exception const& e)
     {

@@ -306,14 +306,19 @@ def test_runs_on_a_caller_stream(ctx):
 
 
 # ---------------------------------------------------------------- exact-match stage in front of the DP (pg_set_stages)
-def _cascade_expected(nodes, edges, reads, k, isrev=None, graph_matching=True):
+def _cascade_expected(nodes, edges, reads, k, isrev=None, graph_matching=True, second_chance=False):
     """grm::CompositeAligner(path=true, graph=graph_matching): PathAligner first, gssw for the reads it leaves unmapped
-    (lib/grm/CompositeAligner.cpp:90-107, 146-170), from the two oracles."""
+    (lib/grm/CompositeAligner.cpp:90-107, 146-170), from the two oracles.  second_chance: the read filter holds NonUniq,
+    so a non-unique exact match is rejected right after the stage (:97-103) and gssw aligns the bases PathAligner left."""
     pexp, cnt = R.OraclePathIndex(nodes, edges, k).align_batch(reads)
-    gexp = R.OracleGraph(nodes, edges).align_batch(reads, is_rev=isrev) if graph_matching else [None] * len(reads)
+    og = R.OracleGraph(nodes, edges)
+    gexp = og.align_batch(reads, is_rev=isrev) if graph_matching else [None] * len(reads)
     out = []
-    for p, g in zip(pexp, gexp):
-        if p["mapped"]:
+    for i, (p, g) in enumerate(zip(pexp, gexp)):
+        if p["mapped"] and second_chance and graph_matching and not p["unique"]:
+            d = og.align_batch([p["bases"]], is_rev=None if isrev is None else [isrev[i]])[0]
+            d["stage"] = "gssw2" if p["graph_reverse"] else "gssw"
+        elif p["mapped"]:
             d = {key: p[key] for key in ("pos", "score", "unique", "mapq", "graph_reverse", "bases", "cigar")}
             d["stage"] = "path"
         elif g is not None:
@@ -329,21 +334,23 @@ def test_path_stage_then_dp(ctx):
     from test_path_oracle import path_cases
     R.set_fill_variant(0)
     rng = np.random.default_rng(47)
-    n = by_path = 0
+    n = by_path = again = 0
     try:
         for nodes, edges, reads, k in path_cases(rng, 120):
             isrev = [i & 1 for i in range(len(reads))]
             ctx.clear_graphs()
             ctx.add_graph(nodes, edges)
-            ctx.set_stages(k, True)
-            exp, cnt = _cascade_expected(nodes, edges, reads, k, isrev)
-            got = strip_status(ctx.align(reads, is_rev=isrev))
-            assert got == exp, (nodes, edges, k)
-            st = ctx.path_stats()
-            assert (st["attempted"], st["anchored"], st["mapped"]) == cnt
+            for second in (False, True):
+                ctx.set_stages(k, True, second)
+                exp, cnt = _cascade_expected(nodes, edges, reads, k, isrev, second_chance=second)
+                got = strip_status(ctx.align(reads, is_rev=isrev))
+                assert got == exp, (nodes, edges, k, second)
+                st = ctx.path_stats()
+                assert (st["attempted"], st["anchored"], st["mapped"]) == cnt
+                again += sum(e["stage"] == "gssw2" for e in exp)
             n += len(reads)
             by_path += sum(e["stage"] == "path" for e in exp)
-        assert by_path > n // 4 and by_path < n
+        assert by_path > n // 4 and by_path < n and again > 0
     finally:
         ctx.set_stages(0, True)
 

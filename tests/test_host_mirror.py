@@ -36,7 +36,7 @@ def test_mirror_reproduces_reference_unit_test(built):
         "f4 7 0[4M]2[1M1X6M]3[6M] 13 60 0 AAAAGCGGGGGGAAAAAA 1",
         "f5 6 0[5M]2[1M1X6M]3[6M] 14 60 1 AAAAAGCGGGGGGAAAAAA 1",
         "f6 0 0[11M]3[8M] 19 60 0 AAAAAAAAAAAAAAAAAAA 1",
-        "path-stage-throws 1",
+        "klib-stage-throws 1",
     ]
     # alignAndCount: supports as ParagraphTest.Aligns expects them (test_paragraph_parts.cpp:113-144), f7 filtered
     # (nonuniq); counts as the reference build gives them for these six single-read fragments
@@ -54,4 +54,19 @@ def test_mirror_reproduces_reference_unit_test(built):
     assert lines[8:14] == [
         "m f1 3 0[8M]1[4M1X3M]3[8M] 19", "m f2 4 0[7M]1[4M1X3M]3[6M] 16", "m f3 6 0[5M]2[1M1X6M]3[6M] 14",
         "m f4 7 0[4M]2[1M1X6M]3[6M] 13", "m f5 6 0[5M]2[1M1X6M]3[6M] 14", "m f6 0 0[11M]3[8M] 19"]
-    assert lines[14:] == ["m g1 6 0[4M]1[6M] 10 0", "m g2 6 0[4M]1[6M] 10 1"]
+    assert lines[14:16] == ["m g1 6 0[4M]1[6M] 10 0", "m g2 6 0[4M]1[6M] 10 1"]
+    # the cascade (PathAligner k = 8, then gssw, NonUniq filter): expectations from the unmodified reference PathAligner
+    # + GraphAligner (oracle/_ref) combined as CompositeAligner::alignRead does (CompositeAligner.cpp:78-176);
+    # status 1 = MAPPED, 2 = BAD_ALIGN; c10 is the second-chance case
+    assert lines[16:] == [
+        "c1 3 0[8M]1[8M]3[8M] 24 60 0 AAAAAAAATTTTTTTTAAAAAAAA 1",
+        "c2 3 0[8M]1[8M]3[8M] 24 60 1 AAAAAAAATTTTTTTTAAAAAAAA 1",
+        "c3 3 0[8M]1[4M1X3M]3[8M] 19 60 0 AAAAAAAATTTTCTTTAAAAAAAA 1",
+        "c4 0 0[11M]3[8M] 19 60 0 AAAAAAAAAAAAAAAAAAA 1",
+        "c5 0 2[8M] 8 60 0 GGGGGGGG 1",
+        "c6 10 0[1M]1[1M6S] 2 0 0 ATATATAT 2",
+        "c7 7 0[4M]1[8M]3[4M] 16 60 0 AAAATTTTTTTTAAAA 1",
+        "c8 8 0[3M]2[8M]3[3M] 14 60 0 AAAGGGGGGGGAAA 1",
+        "c9 8 0[3M]2[8M]3[3M] 14 60 1 AAAGGGGGGGGAAA 1",
+        "c10 5 0[6M]1[6M] 12 60 0 AAAAAATTTTTT 1",
+        "cascade 10 7 9 3 1"]
