@@ -42,14 +42,14 @@ WORKLOAD = "config2: 3-node DEL graph (500 bp flanks, D=300), 10k synthetic 150 
 
 def ncu_traffic():
     """dram bytes read + written per launch of the dominant kernel, from the committed ncu --set full capture."""
-    path = os.path.join(ROOT, "profiles", "r01_fill_kernel_ncu.txt")
+    path = os.path.join(ROOT, "profiles", "r01d_fill_kernel_ncu.txt")
     try:
         tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for line in open(path):
             f = line.split()
             if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[1]) * scale[f[2]]
-        return dict(dram_bytes_per_launch=int(tot), source="profiles/r01_fill_kernel_ncu.txt (ncu --set full, same command)")
+        return dict(dram_bytes_per_launch=int(tot), source="profiles/r01d_fill_kernel_ncu.txt (ncu --set full, same command)")
     except Exception:
         return None
 
@@ -259,14 +259,28 @@ def main():
     torch.cuda.synchronize()
     cnt_s = time.perf_counter() - t0
     cst = ctx.stats()
+    # ---------------- the cascade of `paragraph` (path_sequence_matching on, main/paragraph.cpp:60): exact-match stage
+    # (grm::PathAligner, k = 32) in front of the DP, same host-buffer call; reads it maps skip the DP kernels
+    ctx.set_stages(32, True, True)
+    for _ in range(2):
+        ctx.align_packed(blob, off)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.align_packed(blob, off)
+    torch.cuda.synchronize()
+    casc_s = time.perf_counter() - t0
+    pst = ctx.path_stats()
+    cascade_kernels = ctx.stats()
+    ctx.set_stages(0, True, False)
     clocks = sampler.stop()
     cnt_d2h = int(cnt["node_counts"].shape[0] * 16 + cnt["edge_counts"].shape[0] * 16
                   + sum(16 + 16 * v.shape[0] for v in cnt["families"].values()))
 
-    t = torch.tensor([total_ms, e2e_s * 1e3, cnt_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, e2e_s * 1e3, cnt_s * 1e3, casc_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, cnt_ms = float(t[0]), float(t[1]), float(t[2])
+    total_ms, e2e_ms, cnt_ms, casc_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     n_reads_all = READS_PER_SITE * world
     value = n_reads_all * args.steps / (total_ms * 1e-3)
     e2e_value = n_reads_all * args.steps / (e2e_ms * 1e-3)
@@ -300,15 +314,24 @@ def main():
                                  "the device (pg_batch_count); only the count tables are copied back",
                             h2d_bytes_per_step=h2d + int(pairs.nbytes), d2h_bytes_per_step=cnt_d2h,
                             fragments=int(cnt["node_counts"][:, 0].max())),
+            e2e_cascade=dict(value=round(n_reads_all * args.steps / (casc_ms * 1e-3), 1), unit="reads/s",
+                             what="host reads -> exact-match stage (grm::PathAligner, k=32) + DP for the rest "
+                                  "(pg_set_stages), records + CIGARs back; rank 0's stage counters and kernel times",
+                             path_mapped=pst["mapped"], path_anchored=pst["anchored"], reads=READS_PER_SITE,
+                             path_ms=round(pst["path_ms"], 4), fill_ms=round(cascade_kernels["fill_ms"], 4),
+                             trace_ms=round(cascade_kernels["trace_ms"], 4)),
             roofline=dict(bound="alu (packed-int16 DPX issue; neither hbm nor tensor applies, see DESIGN.md)",
                           kernel="pg_fill_kernel<5>", achieved=round(ach_cells / 1e9, 1), peak=round(peak_cells / 1e9, 1),
                           unit="Gcell/s", frac=round(ach_cells / peak_cells, 4) if peak_cells else None,
                           traffic=ncu_traffic(),
                           peak_source="tools/ubench/dpx_ubench.cu on this pool: 63.2 DPX lane-ops/clk/SM x 148 SM x "
                                       "clocks.max.sm, 2 cells per lane-op, 5 issue slots per cell pair"),
-            roofline_hbm=dict(bound="hbm", achieved=None, peak=peaks.get("hbm_gbs"), unit="GB/s",
-                              note="algorithmic traffic ~200 B/read (reads in, records + CIGAR out): not HBM-bound; "
-                                   "checkpoint scratch traffic is in profiles/"),
+            roofline_hbm=dict(bound="hbm", achieved=round(READS_PER_SITE * 200 / (fill_ms * 1e-3) / 1e9, 3) if fill_ms > 0 else None,
+                              peak=peaks.get("hbm_gbs"), unit="GB/s",
+                              frac=round(READS_PER_SITE * 200 / (fill_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 6)
+                              if fill_ms > 0 and peaks.get("hbm_gbs") else None,
+                              note="algorithmic traffic ~200 B/read (reads in, records + CIGAR out, SURVEY.md 8d): the path "
+                                   "is not HBM-bound; the checkpoint scratch actually written is roofline.traffic"),
             clocks=clocks)
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -500,7 +500,7 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
     }
 }
 
-// ---- exact-match stage (grm::PathAligner, pg_path.cuh): one thread per read ---------------------------------------
+// ---- exact-match stage (grm::PathAligner, pg_path.cuh) ----------------------------------------------------------
 struct PathArgs
 {
     const SiteDev* sites;
@@ -517,6 +517,7 @@ struct PathArgs
     int no_gssw; // no DP stage behind this one: unmapped reads get their (unmapped) record here
     int second_chance; // the caller's filter has NonUniq: a non-unique exact match goes on to the DP (see pg_set_stages)
     uint8_t* prerev;   // [n_reads] 1 = bases were reverse-complemented here before the DP saw them
+    int row_stride;    // bytes per thread of staged strand characters
     Record* records;
     uint32_t* arena;
     unsigned long long* cursor;
@@ -526,17 +527,37 @@ struct PathArgs
     unsigned long long* counters; // attempted, anchored, mapped (PathAligner.hh:66-68)
 };
 
-__global__ void __launch_bounds__(128) pg_path_kernel(const PathArgs a)
+// Two threads per read, one per strand (the reference scans forward, then reverse: PathAligner.cpp:90-109).  Each thread
+// stages its strand's characters in shared memory (row stride = 4 x odd bytes: the threads of a warp walk their rows in
+// lock step without bank conflicts), scans, and leaves its result in shared memory; the forward thread combines the
+// two, writes the record / op words of a mapped read or appends the read to the DP's to-do list.
+constexpr int PATH_THREADS = 128;
+__global__ void __launch_bounds__(PATH_THREADS) pg_path_kernel(const PathArgs a)
 {
-    const int rd = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rd >= a.n_reads)
+    extern __shared__ uint32_t smem[];
+    PathResult* res = reinterpret_cast<PathResult*>(smem);
+    uint8_t* rows = reinterpret_cast<uint8_t*>(res + PATH_THREADS);
+    const int tid = threadIdx.x, strand = tid & 1;
+    const int rd = blockIdx.x * (PATH_THREADS / 2) + (tid >> 1);
+    const bool valid = rd < a.n_reads;
+    uint8_t* q = rows + (size_t)tid * a.row_stride;
+    int L = 0;
+    PathView v;
+    uint8_t* bases = nullptr;
+    if (valid)
+    {
+        const int site = a.read_site ? a.read_site[rd] : 0;
+        v = make_path_view(a.psites[site], a.sites[site], a.ptable, a.plists, a.psucc, a.gbytes, a.gints);
+        bases = a.bases + a.read_off[rd];
+        L = a.read_off[rd + 1] - a.read_off[rd];
+        path_strand_chars(bases, L, strand, q);
+        path_scan_strand(v, q, L, strand, res[tid]);
+    }
+    __syncthreads();
+    if (!valid || strand != 0)
         return;
-    const int site = a.read_site ? a.read_site[rd] : 0;
-    const PathView v = make_path_view(a.psites[site], a.sites[site], a.ptable, a.plists, a.psucc, a.gbytes, a.gints);
-    uint8_t* bases = a.bases + a.read_off[rd];
-    const int L = a.read_off[rd + 1] - a.read_off[rd];
     PathResult r;
-    path_scan(v, bases, L, r);
+    path_combine(res[tid], res[tid + 1], r);
     if (r.n_matches > 0)
         atomicAdd(a.counters + 1, 1ull);
     a.prerev[rd] = 0;
@@ -547,12 +568,9 @@ __global__ void __launch_bounds__(128) pg_path_kernel(const PathArgs a)
         atomicAdd(a.counters + 2, 1ull);
         if (r.strand)
         {
-            for (int x = 0, y = L - 1; x <= y; ++x, --y)
-            {
-                const uint8_t cx = complement_base(bases[x]), cy = complement_base(bases[y]);
-                bases[x] = cy;
-                bases[y] = cx;
-            }
+            const uint8_t* q1 = q + a.row_stride; // the reverse-strand thread's row = reverseComplement(bases)
+            for (int x = 0; x < L; ++x)
+                bases[x] = q1[x];
             a.prerev[rd] = 1;
         }
         a.todo[atomicAdd(a.n_todo, 1)] = rd;
@@ -565,7 +583,7 @@ __global__ void __launch_bounds__(128) pg_path_kernel(const PathArgs a)
         const unsigned long long off = atomicAdd(a.cursor, (unsigned long long)rec.cigar_len);
         if (off + rec.cigar_len <= a.arena_cap)
         {
-            path_emit(v, bases, L, r, a.arena + off);
+            path_emit(v, q + (r.strand ? a.row_stride : 0), L, r, a.arena + off);
             rec.cigar_off = (uint32_t)off;
         }
         else
@@ -900,8 +918,13 @@ int run_path_stage(pg_ctx* c)
     pa.todo = c->d_todo.p;
     pa.n_todo = c->d_ntodo.p;
     pa.counters = c->d_pcount.p;
+    int sw = (c->max_len + 3) / 4; // row stride in words, odd
+    sw |= 1;
+    pa.row_stride = 4 * sw;
+    const size_t path_smem = (size_t)PATH_THREADS * (sizeof(PathResult) + (size_t)pa.row_stride);
+    PG_CUDA(c, cudaFuncSetAttribute(pg_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
     PG_CUDA(c, cudaEventRecord(c->path_ev[0], c->stream));
-    pg_path_kernel<<<(c->n_reads + 127) / 128, 128, 0, c->stream>>>(pa);
+    pg_path_kernel<<<(c->n_reads + PATH_THREADS / 2 - 1) / (PATH_THREADS / 2), PATH_THREADS, path_smem, c->stream>>>(pa);
     PG_CUDA(c, cudaGetLastError());
     ++c->launches;
     PG_CUDA(c, cudaEventRecord(c->path_ev[1], c->stream));

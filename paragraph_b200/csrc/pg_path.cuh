@@ -259,68 +259,107 @@ struct PathResult
     PathMatch first;
 };
 
-// PathAligner::alignRead's scan (PathAligner.cpp:89-118), without writing anything
-PG_HD void path_scan(const PathView& v, const uint8_t* bases, int L, PathResult& r)
+// One strand of PathAligner::alignRead's scan (PathAligner.cpp:93-108).  q = the L characters of that strand (the
+// bases, or their reverse complement: the caller prepares them so that the scan reads plain characters), nothing is
+// written.  The k-mer hashes of PATH_BATCH consecutive positions are rolled and their table slots fetched together
+// (independent loads in flight instead of one dependent probe after the other); the slots are then examined in order,
+// because a match makes the scan jump past its end.
+constexpr int PATH_BATCH = 8;
+PG_HD void path_scan_strand(const PathView& v, const uint8_t* q, int L, int strand, PathResult& r)
 {
     r.n_matches = r.n_full = 0;
-    r.strand = r.seed_pos = 0;
+    r.strand = strand;
+    r.seed_pos = 0;
     r.seed_hash = 0;
     const int k = v.k;
     if (k <= 0 || L < k)
         return;
     const uint64_t top = path_hash_pow(k);
-    for (int strand = 0; strand < 2; ++strand)
+    uint64_t hprev = 0;
+    int have = -1; // position whose k-mer hash hprev holds
+    int pos = 0;
+    while (pos + k <= L)
     {
-        uint64_t h = 0;
-        int have = 0; // position whose k-mer hash h currently holds, -1 = recompute
-        for (int j = 0; j < k; ++j)
-            h = path_hash_step(h, path_read_char(bases, L, strand, j));
-        for (int pos = 0; pos + k <= L; ++pos)
+        const int nb = (L - k - pos + 1) < PATH_BATCH ? (L - k - pos + 1) : PATH_BATCH;
+        uint64_t h[PATH_BATCH];
+        int32_t nn[PATH_BATCH];
+        if (have == pos - 1 && pos > 0) // roll on from the previous batch
+            h[0] = path_hash_step(hprev - ((uint64_t)q[pos - 1] + 1u) * top, q[pos + k - 1]);
+        else
         {
-            if (have != pos) // after a jump: rebuild the hash of q[pos .. pos+k)
-            {
-                h = 0;
-                for (int j = 0; j < k; ++j)
-                    h = path_hash_step(h, path_read_char(bases, L, strand, pos + j));
-                have = pos;
-            }
-            const PathEntry* e = path_lookup(v, h, bases, L, strand, pos);
-            if (e)
-            {
-                PathMatch m;
-                path_extend(v, *e, bases, L, strand, pos, m, nullptr, nullptr);
-                ++r.n_matches;
-                if (m.plen == L)
-                {
-                    if (r.n_full == 0)
-                    {
-                        r.strand = strand;
-                        r.seed_pos = pos;
-                        r.seed_hash = h;
-                        r.first = m;
-                    }
-                    ++r.n_full;
-                }
-                pos = m.qpos + m.plen; // PathAligner.cpp:106; the loop's ++pos follows
-                have = -1;
+            uint64_t x = 0;
+            for (int j = 0; j < k; ++j)
+                x = path_hash_step(x, q[pos + j]);
+            h[0] = x;
+        }
+PG_UNROLL
+        for (int j = 1; j < PATH_BATCH; ++j)
+            h[j] = j < nb ? path_hash_step(h[j - 1] - ((uint64_t)q[pos + j - 1] + 1u) * top, q[pos + j + k - 1]) : 0;
+PG_UNROLL
+        for (int j = 0; j < PATH_BATCH; ++j) // first probe slot of every position of the batch
+        {
+            const uint64_t hj = h[j] ? h[j] : 1;
+            nn[j] = j < nb ? v.table[(uint32_t)(hj ^ (hj >> 29)) & (uint32_t)v.mask].n_nodes : 0;
+        }
+        bool jumped = false;
+        for (int j = 0; j < nb; ++j)
+        {
+            if (nn[j] == 0) // empty slot: this k-mer is on no unique path
                 continue;
-            }
-            if (pos + k < L) // roll: drop q[pos], append q[pos+k]
+            const uint64_t hj = h[j] ? h[j] : 1;
+            // occupied: the full lookup (key compare, collision check along the entry's nodes, further probing)
+            const PathEntry* e = path_lookup(v, hj, q, L, 0, pos + j);
+            if (!e)
+                continue;
+            PathMatch m;
+            path_extend(v, *e, q, L, 0, pos + j, m, nullptr, nullptr);
+            ++r.n_matches;
+            if (m.plen == L)
             {
-                h -= ((uint64_t)path_read_char(bases, L, strand, pos) + 1u) * top;
-                h = path_hash_step(h, path_read_char(bases, L, strand, pos + k));
-                have = pos + 1;
+                if (r.n_full == 0)
+                {
+                    r.seed_pos = pos + j;
+                    r.seed_hash = hj;
+                    r.first = m;
+                }
+                ++r.n_full;
             }
+            pos = m.qpos + m.plen + 1; // PathAligner.cpp:106 and the loop's ++pos
+            have = -1;
+            jumped = true;
+            break;
+        }
+        if (!jumped)
+        {
+            hprev = h[nb - 1];
+            have = pos + nb - 1;
+            pos += nb;
         }
     }
 }
 
-// Second walk of the first full-length match: writes its r.first.n_nodes op words to ops[0 .. n_nodes)
-PG_HD void path_emit(const PathView& v, const uint8_t* bases, int L, const PathResult& r, uint32_t* ops)
+// both strands in the reference's order: forward first, so a forward full-length match is "the first one"
+PG_HD void path_combine(const PathResult& fwd, const PathResult& rev, PathResult& r)
 {
-    const PathEntry* e = path_lookup(v, r.seed_hash, bases, L, r.strand, r.seed_pos);
+    r = fwd.n_full > 0 ? fwd : rev;
+    r.n_matches = fwd.n_matches + rev.n_matches;
+    r.n_full = fwd.n_full + rev.n_full;
+}
+
+// the characters of one strand as the stage sees them (see path_read_char)
+PG_HD void path_strand_chars(const uint8_t* bases, int L, int strand, uint8_t* q)
+{
+    for (int j = 0; j < L; ++j)
+        q[j] = path_read_char(bases, L, strand, j);
+}
+
+// Second walk of the first full-length match: writes its r.first.n_nodes op words to ops[0 .. n_nodes).
+// q = the characters of strand r.strand (path_strand_chars)
+PG_HD void path_emit(const PathView& v, const uint8_t* q, int L, const PathResult& r, uint32_t* ops)
+{
+    const PathEntry* e = path_lookup(v, r.seed_hash, q, L, 0, r.seed_pos);
     PathMatch m;
-    path_extend(v, *e, bases, L, r.strand, r.seed_pos, m, ops, &r.first);
+    path_extend(v, *e, q, L, 0, r.seed_pos, m, ops, &r.first);
 }
 
 // The record of a read the stage mapped (PathAligner.cpp:124-161)

@@ -259,8 +259,13 @@ int pgemu_path_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq
     {
         const uint8_t* b = (const uint8_t*)bases_blob + read_off[i];
         const int L = read_off[i + 1] - read_off[i];
-        PathResult r;
-        path_scan(v, b, L, r);
+        std::vector<uint8_t> q0((size_t)L + 1), q1((size_t)L + 1);
+        path_strand_chars(b, L, 0, q0.data());
+        path_strand_chars(b, L, 1, q1.data());
+        PathResult rf, rr, r;
+        path_scan_strand(v, q0.data(), L, 0, rf);
+        path_scan_strand(v, q1.data(), L, 1, rr);
+        path_combine(rf, rr, r);
         int32_t* o = out8 + 8 * i;
         memset(o, 0, 8 * sizeof(int32_t));
         ++counters3[0];
@@ -272,7 +277,7 @@ int pgemu_path_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq
             Record rec;
             path_record(r, L, rec);
             std::vector<uint32_t> ops((size_t)r.first.n_nodes);
-            path_emit(v, b, L, r, ops.data());
+            path_emit(v, r.strand ? q1.data() : q0.data(), L, r, ops.data());
             cg = host::format_cigar(rec, ops.data());
             o[0] = 1;
             o[1] = rec.graph_pos;
