@@ -605,6 +605,346 @@ __global__ void __launch_bounds__(PATH_THREADS) pg_path_kernel(const PathArgs a)
     }
 }
 
+// ---- the same stage, one WARP per read (default) -------------------------------------------------------------------
+// pg_path_kernel above gives every strand to one thread: 20 k threads for a 10 k-read batch, about one warp per SM
+// sub-partition and 7 of 32 lanes active (profiles/r01_path_kernel_ncu.txt).  Here a warp owns the read: both strands'
+// characters sit in shared memory, the k-mer hashes of all positions are computed and probed by the 32 lanes in
+// parallel (hit[p] = table slot of a verified unique k-mer, -1 otherwise), and the reference's sequential scan --
+// first anchor at or after pos, greedy extension, resume one past the match (PathAligner.cpp:93-108) -- runs
+// warp-uniformly with 32 characters per compare (ballot).  Same results as path_scan_strand / path_extend
+// (pg_path.cuh), which stay the statement of the logic that the CPU emulator checks against the oracle.
+__device__ __forceinline__ int lead_ones(unsigned m) { return m == FULL ? 32 : __ffs((int)~m) - 1; }
+
+// common prefix of q[qi ..) and s[si ..), at most n characters
+__device__ __forceinline__ int warp_prefix(const uint8_t* q, int qi, const uint8_t* s, int si, int n, int lane)
+{
+    int done = 0;
+    while (done < n)
+    {
+        const int x = done + lane;
+        const int lead = lead_ones(__ballot_sync(FULL, x < n && q[qi + x] == s[si + x]));
+        done += lead;
+        if (lead < 32)
+            break;
+    }
+    return n <= 0 ? 0 : (done < n ? done : n);
+}
+// common suffix of q[.. qi) and s[.. si) (both exclusive ends), at most n characters
+__device__ __forceinline__ int warp_suffix(const uint8_t* q, int qi, const uint8_t* s, int si, int n, int lane)
+{
+    int done = 0;
+    while (done < n)
+    {
+        const int x = done + lane;
+        const int lead = lead_ones(__ballot_sync(FULL, x < n && q[qi - 1 - x] == s[si - 1 - x]));
+        done += lead;
+        if (lead < 32)
+            break;
+    }
+    return n <= 0 ? 0 : (done < n ? done : n);
+}
+
+// path_extend (pg_path.cuh) with every character loop done by the warp; all lanes hold the same state
+__device__ void warp_path_extend(const PathView& v, const PathEntry& e, const uint8_t* q, int L, int pos, PathMatch& m,
+                                 uint32_t* ops, const PathMatch* first_pass, int lane)
+{
+    int pos_in_query = pos + v.k;
+    int node = v.lists[e.nodes_off + e.n_nodes - 1];
+    int pos_in_node = e.end_pos + 1;
+    int n_after = 0;
+    const int base = first_pass ? first_pass->n_before : 0;
+    if (ops && lane == 0)
+        for (int x = 0; x < e.n_nodes; ++x)
+            ops[base + x] = (uint32_t)v.lists[e.nodes_off + x] << 16;
+    while (true) // ---- end extension (extendPathEndMatching, PathOperations.cpp:117-189)
+    {
+        const int nl = v.node_len[node];
+        const int adv = warp_prefix(q, pos_in_query, v.raw + v.node_start[node], pos_in_node,
+                                    min(L - pos_in_query, nl - pos_in_node), lane);
+        pos_in_query += adv;
+        pos_in_node += adv;
+        if (pos_in_node < nl)
+            break;
+        int num_longest = 0, longest = 0, best = 0, min_size = 0x7fffffff;
+        for (int x = v.succ_ptr[node]; x < v.succ_ptr[node + 1]; ++x)
+            min_size = min(min_size, v.node_len[v.succ_idx[x]]);
+        for (int x = v.succ_ptr[node]; x < v.succ_ptr[node + 1]; ++x)
+        {
+            const int c = v.succ_idx[x];
+            const int p = warp_prefix(q, pos_in_query, v.raw + v.node_start[c], 0, min(min_size, L - pos_in_query), lane);
+            if (p > longest)
+            {
+                longest = p;
+                best = c;
+                num_longest = 1;
+            }
+            else if (p == longest)
+                ++num_longest;
+        }
+        if (longest == 0 || num_longest != 1)
+            break;
+        if (ops && lane == 0)
+            ops[base + e.n_nodes + n_after] = (uint32_t)best << 16;
+        ++n_after;
+        pos_in_query += longest;
+        pos_in_node = longest;
+        node = best;
+    }
+    const int end_pos = pos_in_node - 1, q_end = pos_in_query;
+    pos_in_query = pos;
+    node = v.lists[e.nodes_off];
+    pos_in_node = e.start_pos;
+    int n_before = 0;
+    while (true) // ---- start extension (extendPathStartMatching, PathOperations.cpp:191-266)
+    {
+        const int adv = warp_suffix(q, pos_in_query, v.raw + v.node_start[node], pos_in_node, min(pos_in_query, pos_in_node), lane);
+        pos_in_query -= adv;
+        pos_in_node -= adv;
+        if (pos_in_node > 0)
+            break;
+        int num_longest = 0, longest = 0, best = 0, min_size = 0x7fffffff;
+        for (int x = v.pred_ptr[node]; x < v.pred_ptr[node + 1]; ++x)
+            min_size = min(min_size, v.node_len[v.pred_idx[x]]);
+        for (int x = v.pred_ptr[node]; x < v.pred_ptr[node + 1]; ++x)
+        {
+            const int c = v.pred_idx[x];
+            const int cl = v.node_len[c];
+            const int p = warp_suffix(q, pos_in_query, v.raw + v.node_start[c], cl, min(min_size, pos_in_query), lane);
+            if (p > longest)
+            {
+                longest = p;
+                best = c;
+                num_longest = 1;
+            }
+            else if (p == longest)
+                ++num_longest;
+        }
+        if (longest == 0 || num_longest != 1)
+            break;
+        ++n_before;
+        if (ops && lane == 0)
+            ops[base - n_before] = (uint32_t)best << 16;
+        pos_in_query -= longest;
+        node = best;
+        pos_in_node = v.node_len[node] - longest;
+    }
+    m.qpos = pos_in_query;
+    m.plen = q_end - pos_in_query;
+    m.start_node = node;
+    m.start_pos = pos_in_node;
+    m.n_before = n_before;
+    m.n_nodes = n_before + e.n_nodes + n_after;
+    if (ops)
+    {
+        __syncwarp();
+        for (int x = lane; x < m.n_nodes; x += 32)
+        {
+            const int nd = (int)(ops[x] >> 16);
+            int ov = v.node_len[nd];
+            if (m.n_nodes == 1)
+                ov = end_pos - m.start_pos + 1;
+            else if (x == 0)
+                ov = v.node_len[nd] - m.start_pos;
+            else if (x == m.n_nodes - 1)
+                ov = end_pos + 1;
+            ops[x] = cigar_word(nd, OP_M, ov);
+        }
+    }
+}
+
+constexpr int PATHW_WARPS = 4;
+__global__ void __launch_bounds__(PATHW_WARPS * 32) pg_path_warp_kernel(const PathArgs a)
+{
+    extern __shared__ uint32_t smem[];
+    const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rd = blockIdx.x * PATHW_WARPS + wic;
+    if (rd >= a.n_reads)
+        return;
+    // per warp: hit[max_len] (int32), then the two strands' characters (row_stride bytes each)
+    uint8_t* wmem = reinterpret_cast<uint8_t*>(smem) + (size_t)wic * (size_t)(a.row_stride * 6);
+    int32_t* hit = reinterpret_cast<int32_t*>(wmem);
+    uint8_t* q0 = wmem + 4 * (size_t)a.row_stride;
+    uint8_t* q1 = q0 + a.row_stride;
+    const int site = a.read_site ? a.read_site[rd] : 0;
+    const PathView v = make_path_view(a.psites[site], a.sites[site], a.ptable, a.plists, a.psucc, a.gbytes, a.gints);
+    uint8_t* bases = a.bases + a.read_off[rd];
+    const int L = a.read_off[rd + 1] - a.read_off[rd];
+    const int k = v.k;
+    for (int j = lane; j < L; j += 32)
+    {
+        const uint8_t c = bases[j];
+        q0[j] = c;
+        q1[L - 1 - j] = complement_base(c);
+    }
+    __syncwarp();
+    PathResult r;
+    r.n_matches = r.n_full = 0;
+    r.strand = r.seed_pos = 0;
+    r.seed_hash = 0;
+    int seed_slot = -1;
+    if (k > 0 && L >= k)
+        for (int strand = 0; strand < 2; ++strand)
+        {
+            const uint8_t* q = strand ? q1 : q0;
+            // every lane: rolling hash over its contiguous share of the positions, first probe of each: hit[p] = slot
+            // of an entry with the k-mer's key (a CANDIDATE: its characters are compared when the scan gets there),
+            // -1 when the probe sequence ends at an empty slot
+            const int npos = L - k + 1, per = (npos + 31) / 32;
+            const uint64_t top = path_hash_pow(k);
+            {
+                const int p0 = lane * per, p1 = min(npos, p0 + per);
+                uint64_t h = 0;
+                if (p0 < p1)
+                    for (int j = 0; j < k; ++j)
+                        h = path_hash_step(h, q[p0 + j]);
+                for (int p = p0; p < p1; ++p)
+                {
+                    const uint64_t hk = h ? h : 1;
+                    const uint32_t lo = (uint32_t)hk, hi = (uint32_t)(hk >> 32);
+                    int32_t cand = -1;
+                    for (uint32_t slot = (uint32_t)(hk ^ (hk >> 29)) & (uint32_t)v.mask;; slot = (slot + 1) & (uint32_t)v.mask)
+                    {
+                        const PathEntry& e = v.table[slot];
+                        if (e.n_nodes == 0)
+                            break;
+                        if (e.key_lo == lo && e.key_hi == hi)
+                        {
+                            cand = (int32_t)slot;
+                            break;
+                        }
+                    }
+                    hit[p] = cand;
+                    if (p + 1 < p1)
+                        h = path_hash_step(h - ((uint64_t)q[p] + 1u) * top, q[p + k]);
+                }
+            }
+            __syncwarp();
+            int pos = 0;
+            while (pos + k <= L)
+            {
+                int found = -1;
+                for (int b0 = pos; b0 + k <= L && found < 0; b0 += 32)
+                {
+                    const int p = b0 + lane;
+                    const unsigned mk = __ballot_sync(FULL, p + k <= L && hit[p] >= 0);
+                    if (mk)
+                        found = b0 + __ffs((int)mk) - 1;
+                }
+                if (found < 0)
+                    break;
+                // verify the candidate's characters along its node list (32 at a time); on a hash collision go on
+                // probing like path_lookup does
+                int slot = hit[found];
+                bool ok = false;
+                while (true)
+                {
+                    const PathEntry& e = v.table[slot];
+                    if (e.n_nodes == 0)
+                        break;
+                    if (e.key_lo == v.table[hit[found]].key_lo && e.key_hi == v.table[hit[found]].key_hi)
+                    {
+                        int j = found;
+                        ok = true;
+                        for (int x = 0; x < e.n_nodes && ok; ++x)
+                        {
+                            const int nd = v.lists[e.nodes_off + x];
+                            const int a0 = x == 0 ? e.start_pos : 0, b1 = x == e.n_nodes - 1 ? e.end_pos : v.node_len[nd] - 1;
+                            const int n = b1 - a0 + 1;
+                            ok = warp_prefix(q, j, v.raw + v.node_start[nd], a0, n, lane) == n;
+                            j += n;
+                        }
+                        if (ok)
+                            break;
+                    }
+                    slot = (slot + 1) & v.mask;
+                }
+                if (!ok)
+                {
+                    pos = found + 1;
+                    continue;
+                }
+                __syncwarp();
+                if (lane == 0)
+                    hit[found] = slot;
+                __syncwarp();
+                PathMatch m;
+                warp_path_extend(v, v.table[hit[found]], q, L, found, m, nullptr, nullptr, lane);
+                ++r.n_matches;
+                if (m.plen == L)
+                {
+                    if (r.n_full == 0)
+                    {
+                        r.strand = strand;
+                        r.seed_pos = found;
+                        r.first = m;
+                        seed_slot = hit[found];
+                    }
+                    ++r.n_full;
+                }
+                pos = m.qpos + m.plen + 1; // PathAligner.cpp:106 and the loop's ++pos
+            }
+            __syncwarp();
+        }
+    if (lane == 0)
+    {
+        if (r.n_matches > 0)
+            atomicAdd(a.counters + 1, 1ull);
+        a.prerev[rd] = 0;
+    }
+    if (r.n_full > 1 && a.second_chance && !a.no_gssw)
+    {
+        // MAPPED by this stage but not unique: the NonUniq filter turns it into BAD_ALIGN and the gssw stage gets the
+        // read (CompositeAligner.cpp:97-103, 146-170) -- with the bases PathAligner left behind
+        if (r.strand)
+            for (int x = lane; x < L; x += 32)
+                bases[x] = q1[x];
+        if (lane == 0)
+        {
+            atomicAdd(a.counters + 2, 1ull);
+            a.prerev[rd] = (uint8_t)(r.strand ? 1 : 0);
+            a.todo[atomicAdd(a.n_todo, 1)] = rd;
+        }
+        return;
+    }
+    if (r.n_full > 0)
+    {
+        Record rec;
+        path_record(r, L, rec);
+        unsigned long long off = 0;
+        if (lane == 0)
+            off = atomicAdd(a.cursor, (unsigned long long)rec.cigar_len);
+        off = __shfl_sync(FULL, off, 0);
+        if (off + rec.cigar_len <= a.arena_cap)
+        {
+            PathMatch m2;
+            warp_path_extend(v, v.table[seed_slot], r.strand ? q1 : q0, L, r.seed_pos, m2, a.arena + off, &r.first, lane);
+            rec.cigar_off = (uint32_t)off;
+        }
+        else
+        {
+            rec.status = 2;
+            rec.cigar_len = 0;
+        }
+        if (lane == 0)
+        {
+            a.records[rd] = rec;
+            atomicAdd(a.counters + 2, 1ull);
+        }
+        return;
+    }
+    if (lane == 0)
+    {
+        a.todo[atomicAdd(a.n_todo, 1)] = rd;
+        if (a.no_gssw) // no later stage: the read stays UNMAPPED (CompositeAligner.cpp:78-176)
+        {
+            Record rec;
+            memset(&rec, 0, sizeof rec);
+            rec.status = (uint8_t)ST_UNMAPPED;
+            a.records[rd] = rec;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host
 
 template <typename T> struct DevBuf
@@ -778,6 +1118,7 @@ struct pg_ctx
     int path_k = 0; // k-mer length; 0 = the stage is off
     bool gssw_on = true; // graphMatching of the cascade
     bool path_second_chance = false;
+    bool path_scalar = false;
     DevBuf<uint8_t> d_prerev;
     bool path_dirty = true;
     DevBuf<PathSite> d_psites;
@@ -923,8 +1264,13 @@ int run_path_stage(pg_ctx* c)
     pa.row_stride = 4 * sw;
     const size_t path_smem = (size_t)PATH_THREADS * (sizeof(PathResult) + (size_t)pa.row_stride);
     PG_CUDA(c, cudaFuncSetAttribute(pg_path_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)path_smem));
+    const size_t pathw_smem = (size_t)PATHW_WARPS * 6 * (size_t)pa.row_stride;
+    PG_CUDA(c, cudaFuncSetAttribute(pg_path_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pathw_smem));
     PG_CUDA(c, cudaEventRecord(c->path_ev[0], c->stream));
-    pg_path_kernel<<<(c->n_reads + PATH_THREADS / 2 - 1) / (PATH_THREADS / 2), PATH_THREADS, path_smem, c->stream>>>(pa);
+    if (c->path_scalar) // PG_PATH_SCALAR=1: the one-thread-per-strand kernel (A/B only)
+        pg_path_kernel<<<(c->n_reads + PATH_THREADS / 2 - 1) / (PATH_THREADS / 2), PATH_THREADS, path_smem, c->stream>>>(pa);
+    else
+        pg_path_warp_kernel<<<(c->n_reads + PATHW_WARPS - 1) / PATHW_WARPS, PATHW_WARPS * 32, pathw_smem, c->stream>>>(pa);
     PG_CUDA(c, cudaGetLastError());
     ++c->launches;
     PG_CUDA(c, cudaEventRecord(c->path_ev[1], c->stream));
@@ -1145,6 +1491,8 @@ int pg_create(int device, pg_ctx** out)
     c->stream = c->own_stream;
     if (const char* e = getenv("PG_NO_TMA"))
         c->use_tma = atoi(e) == 0;
+    if (const char* e = getenv("PG_PATH_SCALAR"))
+        c->path_scalar = atoi(e) != 0;
     if (const char* e = getenv("PG_GEOM_W"))
     {
         const int w = atoi(e);
