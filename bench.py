@@ -42,14 +42,14 @@ WORKLOAD = "config2: 3-node DEL graph (500 bp flanks, D=300), 10k synthetic 150 
 
 def ncu_traffic():
     """dram bytes read + written per launch of the dominant kernel, from the committed ncu --set full capture."""
-    path = os.path.join(ROOT, "profiles", "r01d_fill_kernel_ncu.txt")
+    path = os.path.join(ROOT, "profiles", "r01j_fill_kernel_ncu.txt")
     try:
         tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         for line in open(path):
             f = line.split()
             if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 tot += float(f[1]) * scale[f[2]]
-        return dict(dram_bytes_per_launch=int(tot), source="profiles/r01d_fill_kernel_ncu.txt (ncu --set full, same command)")
+        return dict(dram_bytes_per_launch=int(tot), source="profiles/r01j_fill_kernel_ncu.txt (ncu --set full of the same workload, tools/profile_run.py)")
     except Exception:
         return None
 

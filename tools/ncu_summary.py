@@ -1,5 +1,5 @@
 """Summarise one kernel of an .ncu-rep (ncu --set full) into the text format kept under profiles/.
-usage: ncu_summary.py <file.ncu-rep> "<header line>" > profiles/<name>.txt"""
+usage: ncu_summary.py <file.ncu-rep> "<header line>" [kernel index in the report, default 0] > profiles/<name>.txt"""
 import csv, subprocess, sys
 
 KEYS = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -21,7 +21,7 @@ def main():
     rep, header = sys.argv[1], sys.argv[2]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr, units, vals = rows[0], rows[1], rows[2]
+    hdr, units, vals = rows[0], rows[1], rows[2 + (int(sys.argv[3]) if len(sys.argv) > 3 else 0)]
     col = {h: i for i, h in enumerate(hdr)}
     print(header)
     for k in KEYS:

@@ -22,3 +22,15 @@ for k in range(12):
     sid = ctx.add_graph(nodes, edges); reads += rd; sites += [sid] * len(rd)
 ctx.align(reads, sites=sites)
 print("sanitize run ok:", n + len(reads), "reads")
+# reads past the 8-bit limit (WIDE geometries) and the exact-match stage in front of the DP (both path kernels)
+nodes, edges = synth.del_graph(rng, 400, 120)
+ctx.clear_graphs(); ctx.add_graph(nodes, edges)
+ctx.align(synth.simulate_reads(rng, nodes, edges, 24, read_len=300, sub=0.01) + synth.simulate_reads(rng, nodes, edges, 16, read_len=500, sub=0.01))
+for second in (False, True):
+    ctx.set_stages(32, True, second)
+    got = ctx.align(synth.simulate_reads(rng, nodes, edges, 96, read_len=150, sub=0.003, indel_frac=0.0))
+    print("cascade:", ctx.path_stats(), sum(g["stage"] == "path" for g in got), "of", len(got), "by the exact-match stage")
+ctx.set_stages(32, False, False)
+ctx.align(synth.simulate_reads(rng, nodes, edges, 32, read_len=150, sub=0.003, indel_frac=0.0))
+ctx.set_stages(0, True, False)
+print("sanitize extras ok")
