@@ -1083,7 +1083,10 @@ struct pg_ctx
     int device = 0;
     std::string err;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    std::vector<cudaEvent_t> evpool; // 3 events per chunk: start, after fill, after trace
+    std::vector<cudaEvent_t> evpool; // 4 events per chunk: before / after fill (main stream), before / after trace (aux stream)
+    cudaStream_t aux_stream = nullptr; // the traceback of chunk i runs here, next to the fill of chunk i+1
+    int split = 1;                     // chunks a batch is cut into for that overlap (PG_SPLIT; 1 = off, the default:
+                                       // measured slower on the B200)
     int n_chunks_timed = 0;
     uint64_t launches = 0;
     float fill_ms = 0, trace_ms = 0;
@@ -1350,10 +1353,19 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         chunk = 1;
     if (chunk > (size_t)c->n_reads)
         chunk = (size_t)c->n_reads;
-    PG_CUDA(c, c->d_last.reserve(chunk * s_last));
+    // Overlap: the traceback kernel is latency-bound, the fill kernel ALU-bound -- cut the batch into a few chunks and
+    // run the traceback of chunk i on a second stream while chunk i+1 is being filled (scratch double-buffered).
+    const bool overlap = c->split > 1 && c->aux_stream && c->n_reads >= 1024;
+    if (overlap)
+    {
+        chunk = std::min(chunk / 2 > 0 ? chunk / 2 : 1, ((size_t)c->n_reads + c->split - 1) / c->split);
+        chunk = (chunk + 63) & ~(size_t)63; // whole CTAs
+    }
+    const size_t slots = overlap ? 2 : 1;
+    PG_CUDA(c, c->d_last.reserve(slots * chunk * s_last));
     if (tab_global)
-        PG_CUDA(c, c->d_tab.reserve(chunk * 2 * (size_t)tab_words));
-    PG_CUDA(c, c->d_ckpt.reserve(chunk * s_ckpt));
+        PG_CUDA(c, c->d_tab.reserve(slots * chunk * 2 * (size_t)tab_words));
+    PG_CUDA(c, c->d_ckpt.reserve(slots * chunk * s_ckpt));
     PG_CUDA(c, c->d_tout.reserve((size_t)c->n_reads * 2));
     PG_CUDA(c, c->d_records.reserve((size_t)c->n_reads));
     PG_CUDA(c, c->d_cursor.reserve(1));
@@ -1377,7 +1389,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     PG_CUDA(c, cudaFuncSetAttribute(pg_trace_kernel<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
 
     const size_t n_chunks = ((size_t)c->n_reads + chunk - 1) / chunk;
-    while (c->evpool.size() < 3 * n_chunks)
+    while (c->evpool.size() < 4 * n_chunks)
     {
         cudaEvent_t e;
         PG_CUDA(c, cudaEventCreate(&e));
@@ -1387,7 +1399,10 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     size_t ci = 0;
     for (size_t r0 = 0; r0 < (size_t)c->n_reads; r0 += chunk, ++ci)
     {
-        PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci], c->stream));
+        const size_t slot = overlap ? (ci & 1) : 0;
+        if (overlap && ci >= 2) // the scratch slot is free once the traceback of chunk ci-2 is through
+            PG_CUDA(c, cudaStreamWaitEvent(c->stream, c->evpool[4 * (ci - 2) + 3], 0));
+        PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci], c->stream));
         const int nr = (int)std::min(chunk, (size_t)c->n_reads - r0);
         FillArgs fa;
         fa.sites = c->d_sites.p;
@@ -1399,12 +1414,12 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.read0 = (int)r0;
         fa.n_tasks = 2 * nr;
         fa.flags = flags;
-        fa.last = c->d_last.p;
-        fa.ckpt = c->d_ckpt.p;
+        fa.last = c->d_last.p + slot * chunk * s_last;
+        fa.ckpt = c->d_ckpt.p + slot * chunk * s_ckpt;
         fa.n_nodes_cap = max_nodes;
         fa.code_smem_bytes = code_bytes ? code_bytes - 16 : 0;
         fa.tab_ints_cap = code_bytes ? tab_ints_cap : 0;
-        fa.tabG = tab_global ? c->d_tab.p : nullptr;
+        fa.tabG = tab_global ? c->d_tab.p + slot * chunk * 2 * (size_t)tab_words : nullptr;
         fa.stride_tab = (size_t)tab_words;
         fa.stride_last = s_last;
         fa.stride_ckpt = s_ckpt;
@@ -1421,7 +1436,11 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
             pg_fill_kernel<R, W, false, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
-        PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci + 1], c->stream));
+        PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 1], c->stream));
+        cudaStream_t ts = overlap ? c->aux_stream : c->stream;
+        if (overlap)
+            PG_CUDA(c, cudaStreamWaitEvent(ts, c->evpool[4 * ci + 1], 0));
+        PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 2], ts));
 
         TraceArgs ta;
         ta.sites = c->d_sites.p;
@@ -1433,8 +1452,8 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         ta.read0 = (int)r0;
         ta.n_reads = nr;
         ta.flags = flags;
-        ta.last = c->d_last.p;
-        ta.ckpt = c->d_ckpt.p;
+        ta.last = fa.last;
+        ta.ckpt = fa.ckpt;
         ta.stride_last = s_last;
         ta.stride_ckpt = s_ckpt;
         ta.tout = c->d_tout.p;
@@ -1448,11 +1467,14 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         ta.n_todo = fa.n_todo;
         ta.prerev = after_path ? c->d_prerev.p : nullptr;
         const int tgrid = (nr + TRACE_WARPS * NT - 1) / (TRACE_WARPS * NT);
-        pg_trace_kernel<R, W><<<tgrid, TRACE_WARPS * 32, trace_smem, c->stream>>>(ta);
+        pg_trace_kernel<R, W><<<tgrid, TRACE_WARPS * 32, trace_smem, ts>>>(ta);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
-        PG_CUDA(c, cudaEventRecord(c->evpool[3 * ci + 2], c->stream));
+        PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 3], ts));
     }
+    if (overlap) // everything later on the caller's stream (download, counting stage) sees the tracebacks finished
+        for (size_t k = n_chunks >= 2 ? n_chunks - 2 : 0; k < n_chunks; ++k)
+            PG_CUDA(c, cudaStreamWaitEvent(c->stream, c->evpool[4 * k + 3], 0));
     return PG_OK;
 }
 
@@ -1489,6 +1511,10 @@ int pg_create(int device, pg_ctx** out)
         return PG_E_CUDA;
     }
     c->stream = c->own_stream;
+    if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess)
+        c->aux_stream = nullptr;
+    if (const char* e = getenv("PG_SPLIT"))
+        c->split = std::max(1, atoi(e));
     if (const char* e = getenv("PG_NO_TMA"))
         c->use_tma = atoi(e) == 0;
     if (const char* e = getenv("PG_PATH_SCALAR"))
@@ -1544,6 +1570,8 @@ void pg_destroy(pg_ctx* c)
     for (auto& ev : c->count_ev)
         if (ev)
             cudaEventDestroy(ev);
+    if (c->aux_stream)
+        cudaStreamDestroy(c->aux_stream);
     if (c->own_stream)
         cudaStreamDestroy(c->own_stream);
     delete c;
@@ -1744,8 +1772,8 @@ int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap
     for (int ci = 0; ci < c->n_chunks_timed; ++ci) // summed over the chunks of the batch
     {
         float a = 0, b = 0;
-        cudaEventElapsedTime(&a, c->evpool[3 * ci], c->evpool[3 * ci + 1]);
-        cudaEventElapsedTime(&b, c->evpool[3 * ci + 1], c->evpool[3 * ci + 2]);
+        cudaEventElapsedTime(&a, c->evpool[4 * ci], c->evpool[4 * ci + 1]);
+        cudaEventElapsedTime(&b, c->evpool[4 * ci + 2], c->evpool[4 * ci + 3]);
         c->fill_ms += a;
         c->trace_ms += b;
     }

@@ -6,6 +6,33 @@ import numpy as np
 from paragraph_b200 import capi, synth
 from oracle import refbind as R
 
+estage = []
+
+
+def cascade(graphs, reads, sites, isrev, flags, gexp, k, second):
+    """CompositeAligner(path, gssw) from the two oracles (CompositeAligner.cpp:78-176), per site"""
+    global estage
+    out, estage = list(gexp), ["gssw"] * len(gexp)
+    by_site = {}
+    for i, s in enumerate(sites):
+        by_site.setdefault(s, []).append(i)
+    for s, idx in by_site.items():
+        nodes, edges = graphs[s]
+        pexp, _ = R.OraclePathIndex(nodes, edges, k).align_batch([reads[i] for i in idx])
+        og = None
+        for i, p in zip(idx, pexp):
+            if not p["mapped"]:
+                continue
+            if second and not p["unique"]:
+                og = og or R.OracleGraph(nodes, edges)
+                out[i] = og.align_batch([p["bases"]], is_rev=[isrev[i]], flags=flags)[0]
+                estage[i] = "gssw2" if p["graph_reverse"] else "gssw"
+            else:
+                out[i] = {key: p[key] for key in ("pos", "score", "unique", "mapq", "graph_reverse", "bases", "cigar")}
+                estage[i] = "path"
+    return out
+
+
 def main():
     ng = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
     nr = int(sys.argv[2]) if len(sys.argv) > 2 else 30
@@ -17,6 +44,7 @@ def main():
     for batch in range(0, ng, 200):
         ctx.clear_graphs()
         reads, sites, exp, isrev = [], [], [], []
+        ctx_graphs = {}
         flags = int(rng.choice([0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 1, 3, 5, 7]))
         maxlen = int(rng.choice([160, 160, 250, 320, 512]))
         for gi in range(min(200, ng - batch)):
@@ -26,12 +54,21 @@ def main():
             rd = [r[:maxlen] for r in synth.fuzz_reads(rng, nodes, edges, nr, min_len=minlen, max_len=maxlen)]
             rv = [int(x) for x in rng.integers(0, 2, size=len(rd))]
             sid = ctx.add_graph(nodes, edges)
+            ctx_graphs[sid] = (nodes, edges)
             reads += rd; sites += [sid] * len(rd); isrev += rv
             exp += R.OracleGraph(nodes, edges).align_batch(rd, is_rev=rv, flags=flags)
+        # every other batch: the exact-match stage (grm::PathAligner) in front, with / without the filter's second chance
+        k = int(rng.choice([0, 0, 8, 16, 32]))
+        second = bool(rng.integers(0, 2))
+        ctx.set_stages(k, True, second)
+        if k:
+            exp = cascade(ctx_graphs, reads, sites, isrev, flags, exp, k, second)
         got = ctx.align(reads, sites=sites, is_rev=isrev, flags=flags)
         for i, (g, e) in enumerate(zip(got, exp)):
-            st = g.pop("status"); cl = g.pop("clipped")
+            st = g.pop("status"); cl = g.pop("clipped"); stage = g.pop("stage", None)
             ok = (g == e and st == 0)
+            if ok and stage is not None:
+                ok = stage == estage[i]
             if ok and (flags & 1) and e["cigar"]:
                 ok = R.oracle_bad_align(e["cigar"], 0.8)[1] == cl
             if not ok:
