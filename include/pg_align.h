@@ -233,9 +233,9 @@ int pg_count_stats(const pg_ctx* ctx, uint64_t* kernel_launches, float* last_cou
  * Default: path_kmer_len = 0, graph_matching = 1 (what grmpy runs: src/c++/main/grmpy.cpp:69-72).  The KmerAligner
  * and KlibAligner stages are not built. */
 int pg_set_stages(pg_ctx* ctx, int32_t path_kmer_len, int32_t graph_matching, int32_t nonuniq_second_chance);
-/* counters3 = {attempted, anchored, mapped} of the last batch (PathAligner::attempted/anchored/mapped,
- * PathAligner.hh:66-68) and the stage's device time in ms. */
-int pg_path_stats(pg_ctx* ctx, uint64_t* counters3, float* path_ms);
+/* counters4 = {attempted, anchored, mapped} of the last batch (PathAligner::attempted/anchored/mapped,
+ * PathAligner.hh:66-68) + the host time in microseconds of the last index build; path_ms = the stage's device time. */
+int pg_path_stats(pg_ctx* ctx, uint64_t* counters4, float* path_ms);
 
 /* Kernels launched by this context so far, and the last batch's per-kernel device time in ms
  * (fill, traceback) measured with CUDA events on the launching stream. */

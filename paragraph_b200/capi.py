@@ -205,10 +205,11 @@ class Context:
 
     def path_stats(self):
         """-> dict(attempted, anchored, mapped, path_ms) of the last batch (PathAligner.hh:66-68)"""
-        cnt = (C.c_uint64 * 3)()
+        cnt = (C.c_uint64 * 4)()
         ms = C.c_float(0)
         self._check(self.lib.pg_path_stats(self.h, cnt, C.byref(ms)))
-        return dict(attempted=int(cnt[0]), anchored=int(cnt[1]), mapped=int(cnt[2]), path_ms=float(ms.value))
+        return dict(attempted=int(cnt[0]), anchored=int(cnt[1]), mapped=int(cnt[2]), path_ms=float(ms.value),
+                    index_build_ms=cnt[3] / 1e3)
 
     def add_graph(self, node_seqs, edges):
         blob = "".join(node_seqs).encode("latin-1")

@@ -693,7 +693,7 @@ public:
         }
         if (pathMatching_)
         {
-            uint64_t cnt[3] = { 0, 0, 0 };
+            uint64_t cnt[4] = { 0, 0, 0, 0 };
             graphAligner_.check(pg_path_stats(graphAligner_.context(), cnt, nullptr));
             anchoredPath_ += (unsigned)cnt[1];
         }

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -272,170 +273,270 @@ struct PathIndexHost
     int k = 0;
 };
 
-inline void build_path_index(const GraphStore& gs, int k, PathIndexHost& out)
+// one site's share of the index, with site-local offsets
+struct PathSiteBuild
 {
-    out = PathIndexHost();
-    out.k = k;
+    std::vector<int32_t> succ;      // succ_ptr[n+1], succ_idx[]
+    std::vector<PathEntry> entries; // the unique k-mers, not yet placed in the table
+    std::vector<int32_t> lists;     // node lists of the kept entries
+};
+
+inline void build_path_site(const GraphStore& gs, size_t si, int k, PathSiteBuild& out)
+{
     struct KP
     {
         uint64_t h;
-        int32_t start_pos, end_pos, list_off, n_nodes;
+        int32_t v0, start_pos, end_pos, list_off, n_nodes; // list_off < 0: the path stays inside node v0
     };
-    for (size_t si = 0; si < gs.sites.size(); ++si)
+    const SiteDev& sd = gs.sites[si];
+    const int n = sd.n_nodes;
+    const int32_t* t = gs.ints.data() + sd.tab_off[0];
+    const int32_t *node_start = t, *node_len = t + n;
+    const uint8_t* raw = gs.bytes.data() + sd.raw_off;
+    // successors, ascending, without duplicates
+    std::vector<std::vector<int32_t>> succ((size_t)n);
+    for (int64_t e = gs.edge_base[si]; e < gs.edge_base[si + 1]; ++e)
+        succ[(size_t)gs.in_from[(size_t)e]].push_back(gs.in_to[(size_t)e]);
     {
-        const SiteDev& sd = gs.sites[si];
-        const int n = sd.n_nodes;
-        const int32_t* t = gs.ints.data() + sd.tab_off[0];
-        const int32_t *node_start = t, *node_len = t + n;
-        const uint8_t* raw = gs.bytes.data() + sd.raw_off;
-        // successors, ascending, without duplicates
-        std::vector<std::vector<int32_t>> succ((size_t)n);
-        for (int64_t e = gs.edge_base[si]; e < gs.edge_base[si + 1]; ++e)
-            succ[(size_t)gs.in_from[(size_t)e]].push_back(gs.in_to[(size_t)e]);
-        PathSite ps;
-        ps.k = k;
-        ps.raw_off = sd.raw_off;
-        ps.succ_ptr_off = (int32_t)out.succ.size();
+        int32_t ptr = 0;
+        for (int i = 0; i < n; ++i)
         {
-            int32_t ptr = 0;
-            for (int i = 0; i < n; ++i)
-            {
-                auto& v = succ[(size_t)i];
-                std::sort(v.begin(), v.end());
-                v.erase(std::unique(v.begin(), v.end()), v.end());
-                out.succ.push_back(ptr);
-                ptr += (int32_t)v.size();
-            }
+            auto& v = succ[(size_t)i];
+            std::sort(v.begin(), v.end());
+            v.erase(std::unique(v.begin(), v.end()), v.end());
             out.succ.push_back(ptr);
-            for (int i = 0; i < n; ++i)
-                out.succ.insert(out.succ.end(), succ[(size_t)i].begin(), succ[(size_t)i].end());
+            ptr += (int32_t)v.size();
         }
-        // enumerate the k-mer paths (depth first over the successors, like extendPathEnd)
-        std::vector<KP> kps;
-        std::vector<int32_t> lists; // site-local node lists of ALL k-mer paths
-        std::vector<int32_t> stack_nodes((size_t)k + 2);
-        struct Frame
+        out.succ.push_back(ptr);
+        for (int i = 0; i < n; ++i)
+            out.succ.insert(out.succ.end(), succ[(size_t)i].begin(), succ[(size_t)i].end());
+    }
+    // enumerate the k-mer paths: inside a node by rolling the hash along it, across node ends depth first over the
+    // successors like extendPathEnd
+    std::vector<KP> kps;
+    kps.reserve((size_t)sd.G + 16);
+    std::vector<int32_t> lists; // node lists of the multi-node k-mer paths
+    std::vector<int32_t> stack_nodes((size_t)k + 2);
+    struct Frame
+    {
+        int depth, end, ext, next_succ;
+    };
+    std::vector<Frame> st;
+    const uint64_t top = path_hash_pow(k);
+    for (int v0 = 0; v0 < n; ++v0)
+    {
+        const uint8_t* sq = raw + node_start[v0];
+        const int len = node_len[v0];
+        uint64_t h = 0;
+        for (int pos = 0; pos + k <= len; ++pos) // k-mers inside the node
         {
-            int depth, end, ext, next_succ;
-        };
-        std::vector<Frame> st;
-        for (int v0 = 0; v0 < n; ++v0)
-            for (int pos = 0; pos < node_len[v0]; ++pos)
+            if (pos == 0)
+                for (int j = 0; j < k; ++j)
+                    h = path_hash_step(h, sq[j]);
+            else
+                h = path_hash_step(h - ((uint64_t)sq[pos - 1] + 1u) * top, sq[pos + k - 1]);
+            KP kp = { h ? h : 1, v0, pos, pos + k - 1, -1, 1 };
+            kps.push_back(kp);
+        }
+        for (int pos = std::max(0, len - k + 1); pos < len; ++pos) // k-mers that leave the node
+        {
+            stack_nodes[0] = v0;
+            st.clear();
+            st.push_back({ 1, pos, k - 1, 0 });
+            while (!st.empty())
             {
-                stack_nodes[0] = v0;
-                st.clear();
-                st.push_back({ 1, pos, k - 1, 0 });
-                while (!st.empty())
+                Frame& f = st.back();
+                const int last = stack_nodes[(size_t)f.depth - 1];
+                const int room = node_len[last] - f.end - 1;
+                if (f.ext <= room)
                 {
-                    Frame& f = st.back();
-                    const int last = stack_nodes[(size_t)f.depth - 1];
-                    const int room = node_len[last] - f.end - 1;
-                    if (f.ext <= room)
+                    KP kp;
+                    kp.v0 = v0;
+                    kp.start_pos = pos;
+                    kp.end_pos = f.end + f.ext;
+                    kp.list_off = (int32_t)lists.size();
+                    kp.n_nodes = f.depth;
+                    lists.insert(lists.end(), stack_nodes.begin(), stack_nodes.begin() + f.depth);
+                    uint64_t hh = 0;
+                    for (int x = 0; x < f.depth; ++x)
                     {
-                        KP kp;
-                        kp.start_pos = pos;
-                        kp.end_pos = f.end + f.ext;
-                        kp.list_off = (int32_t)lists.size();
-                        kp.n_nodes = f.depth;
-                        lists.insert(lists.end(), stack_nodes.begin(), stack_nodes.begin() + f.depth);
-                        uint64_t h = 0;
-                        for (int x = 0; x < f.depth; ++x)
-                        {
-                            const int nd = stack_nodes[(size_t)x];
-                            const int a = x == 0 ? pos : 0, b = x == f.depth - 1 ? kp.end_pos : node_len[nd] - 1;
-                            for (int p = a; p <= b; ++p)
-                                h = path_hash_step(h, raw[node_start[nd] + p]);
-                        }
-                        kp.h = h ? h : 1;
-                        kps.push_back(kp);
-                        st.pop_back();
-                        continue;
+                        const int nd = stack_nodes[(size_t)x];
+                        const int a = x == 0 ? pos : 0, b = x == f.depth - 1 ? kp.end_pos : node_len[nd] - 1;
+                        for (int p = a; p <= b; ++p)
+                            hh = path_hash_step(hh, raw[node_start[nd] + p]);
                     }
-                    const auto& sv = succ[(size_t)last];
-                    if (f.next_succ >= (int)sv.size())
-                    {
-                        st.pop_back();
-                        continue;
-                    }
-                    const int c = sv[(size_t)f.next_succ++];
-                    const Frame nf = { f.depth + 1, 0, f.ext - room - 1, 0 };
-                    stack_nodes[(size_t)f.depth] = c;
-                    st.push_back(nf);
+                    kp.h = hh ? hh : 1;
+                    kps.push_back(kp);
+                    st.pop_back();
+                    continue;
+                }
+                const auto& sv = succ[(size_t)last];
+                if (f.next_succ >= (int)sv.size())
+                {
+                    st.pop_back();
+                    continue;
+                }
+                const int c = sv[(size_t)f.next_succ++];
+                const Frame nf = { f.depth + 1, 0, f.ext - room - 1, 0 };
+                stack_nodes[(size_t)f.depth] = c;
+                st.push_back(nf);
+            }
+        }
+    }
+    // group equal k-mers: sort by hash, compare the characters inside a run of equal hashes
+    auto kmer_char = [&](const KP& kp, int j) -> uint8_t {
+        if (kp.list_off < 0)
+            return raw[node_start[kp.v0] + kp.start_pos + j];
+        for (int x = 0; x < kp.n_nodes; ++x)
+        {
+            const int nd = lists[(size_t)kp.list_off + (size_t)x];
+            const int a = x == 0 ? kp.start_pos : 0, b = x == kp.n_nodes - 1 ? kp.end_pos : node_len[nd] - 1;
+            if (j <= b - a)
+                return raw[node_start[nd] + a + j];
+            j -= b - a + 1;
+        }
+        return 0;
+    };
+    auto same_kmer = [&](const KP& a, const KP& b) {
+        for (int j = 0; j < k; ++j)
+            if (kmer_char(a, j) != kmer_char(b, j))
+                return false;
+        return true;
+    };
+    // count the occurrences of every distinct k-mer with a scratch open-addressing table over ALL k-mer paths (key =
+    // hash, verified by comparing the characters with the first path that took the slot); the unique ones are kept
+    std::vector<uint32_t> uniq;
+    {
+        size_t cap2 = 16;
+        while (cap2 < 2 * kps.size() + 2)
+            cap2 <<= 1;
+        std::vector<uint32_t> first(cap2, 0xFFFFFFFFu); // index of the first path with this k-mer
+        std::vector<uint32_t> count(cap2, 0);
+        for (uint32_t id = 0; id < (uint32_t)kps.size(); ++id)
+        {
+            const uint64_t h = kps[id].h;
+            for (size_t slot = (size_t)(h ^ (h >> 29)) & (cap2 - 1);; slot = (slot + 1) & (cap2 - 1))
+            {
+                if (first[slot] == 0xFFFFFFFFu)
+                {
+                    first[slot] = id;
+                    count[slot] = 1;
+                    break;
+                }
+                if (kps[first[slot]].h == h && same_kmer(kps[first[slot]], kps[id]))
+                {
+                    ++count[slot];
+                    break;
                 }
             }
-        // group equal k-mers: sort by hash, compare the characters inside a run of equal hashes
-        auto kmer_char = [&](const KP& kp, int j) -> uint8_t {
-            for (int x = 0; x < kp.n_nodes; ++x)
-            {
-                const int nd = lists[(size_t)kp.list_off + (size_t)x];
-                const int a = x == 0 ? kp.start_pos : 0, b = x == kp.n_nodes - 1 ? kp.end_pos : node_len[nd] - 1;
-                if (j <= b - a)
-                    return raw[node_start[nd] + a + j];
-                j -= b - a + 1;
-            }
-            return 0;
-        };
-        auto same_kmer = [&](const KP& a, const KP& b) {
-            for (int j = 0; j < k; ++j)
-                if (kmer_char(a, j) != kmer_char(b, j))
-                    return false;
-            return true;
-        };
-        std::vector<uint32_t> order(kps.size());
-        for (size_t i = 0; i < order.size(); ++i)
-            order[i] = (uint32_t)i;
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return kps[a].h < kps[b].h; });
-        std::vector<uint32_t> uniq;
-        for (size_t i = 0; i < order.size();)
-        {
-            size_t j = i;
-            while (j < order.size() && kps[order[j]].h == kps[order[i]].h)
-                ++j;
-            // run [i, j): usually one string; count occurrences of each distinct string
-            std::vector<char> done(j - i, 0);
-            for (size_t a = i; a < j; ++a)
-            {
-                if (done[a - i])
-                    continue;
-                int cnt = 1;
-                for (size_t b = a + 1; b < j; ++b)
-                    if (!done[b - i] && same_kmer(kps[order[a]], kps[order[b]]))
-                    {
-                        done[b - i] = 1;
-                        ++cnt;
-                    }
-                if (cnt == 1)
-                    uniq.push_back(order[a]);
-            }
-            i = j;
         }
-        size_t cap = 8;
-        while (cap < 2 * uniq.size() + 1)
-            cap <<= 1;
-        ps.table_off = (int32_t)out.table.size();
-        ps.table_mask = (int32_t)(cap - 1);
-        ps.lists_off = (int32_t)out.lists.size();
-        PathEntry empty;
-        memset(&empty, 0, sizeof empty);
-        out.table.resize(out.table.size() + cap, empty);
-        PathEntry* tab = out.table.data() + ps.table_off;
-        for (uint32_t id : uniq)
-        {
-            const KP& kp = kps[id];
-            PathEntry e;
-            e.key_lo = (uint32_t)kp.h;
-            e.key_hi = (uint32_t)(kp.h >> 32);
-            e.start_pos = kp.start_pos;
-            e.end_pos = kp.end_pos;
-            e.n_nodes = kp.n_nodes;
-            e.nodes_off = (int32_t)(out.lists.size() - (size_t)ps.lists_off);
+        uniq.reserve(kps.size());
+        for (size_t slot = 0; slot < cap2; ++slot)
+            if (count[slot] == 1)
+                uniq.push_back(first[slot]);
+        std::sort(uniq.begin(), uniq.end()); // enumeration order: deterministic tables
+    }
+    out.lists.reserve(uniq.size() + lists.size());
+    out.entries.reserve(uniq.size());
+    for (uint32_t id : uniq)
+    {
+        const KP& kp = kps[id];
+        PathEntry e;
+        e.key_lo = (uint32_t)kp.h;
+        e.key_hi = (uint32_t)(kp.h >> 32);
+        e.start_pos = kp.start_pos;
+        e.end_pos = kp.end_pos;
+        e.n_nodes = kp.n_nodes;
+        e.nodes_off = (int32_t)out.lists.size();
+        if (kp.list_off < 0)
+            out.lists.push_back(kp.v0);
+        else
             out.lists.insert(out.lists.end(), lists.begin() + kp.list_off, lists.begin() + kp.list_off + kp.n_nodes);
-            uint32_t slot = (uint32_t)(kp.h ^ (kp.h >> 29)) & (uint32_t)ps.table_mask;
-            while (tab[slot].n_nodes != 0)
-                slot = (slot + 1) & (uint32_t)ps.table_mask;
-            tab[slot] = e;
-        }
-        out.sites.push_back(ps);
+        out.entries.push_back(e);
+    }
+}
+
+// open addressing with linear probing into a zeroed power-of-two block (load factor <= 0.75)
+inline size_t path_table_cap(size_t n_entries)
+{
+    size_t cap = 8;
+    while (3 * cap < 4 * n_entries + 4)
+        cap <<= 1;
+    return cap;
+}
+inline void place_path_entries(const std::vector<PathEntry>& entries, PathEntry* tab, size_t cap)
+{
+    for (const PathEntry& e : entries)
+    {
+        const uint64_t h = ((uint64_t)e.key_hi << 32) | e.key_lo;
+        uint32_t slot = (uint32_t)(h ^ (h >> 29)) & (uint32_t)(cap - 1);
+        while (tab[slot].n_nodes != 0)
+            slot = (slot + 1) & (uint32_t)(cap - 1);
+        tab[slot] = e;
+    }
+}
+
+// all sites; the per-site builds are independent and run on a few host threads
+inline void build_path_index(const GraphStore& gs, int k, PathIndexHost& out, int threads = 0)
+{
+    out = PathIndexHost();
+    out.k = k;
+    const size_t ns = gs.sites.size();
+    std::vector<PathSiteBuild> parts(ns);
+    if (threads <= 0)
+        threads = (int)std::min<size_t>(16, std::max(1u, std::thread::hardware_concurrency()));
+    threads = (int)std::min<size_t>((size_t)threads, std::max<size_t>(1, ns / 8));
+    if (threads <= 1)
+        for (size_t si = 0; si < ns; ++si)
+            build_path_site(gs, si, k, parts[si]);
+    else
+    {
+        std::vector<std::thread> pool;
+        for (int w = 0; w < threads; ++w)
+            pool.emplace_back([&, w]() {
+                for (size_t si = (size_t)w; si < ns; si += (size_t)threads)
+                    build_path_site(gs, si, k, parts[si]);
+            });
+        for (auto& th : pool)
+            th.join();
+    }
+    size_t n_table = 0, n_lists = 0, n_succ = 0;
+    out.sites.resize(ns);
+    for (size_t si = 0; si < ns; ++si)
+    {
+        PathSite& ps = out.sites[si];
+        ps.k = k;
+        ps.raw_off = gs.sites[si].raw_off;
+        ps.succ_ptr_off = (int32_t)n_succ;
+        ps.table_off = (int32_t)n_table;
+        ps.table_mask = (int32_t)(path_table_cap(parts[si].entries.size()) - 1);
+        ps.lists_off = (int32_t)n_lists;
+        n_table += (size_t)ps.table_mask + 1;
+        n_lists += parts[si].lists.size();
+        n_succ += parts[si].succ.size();
+    }
+    out.table.resize(n_table); // value-initialised: n_nodes = 0 marks an empty slot
+    out.lists.resize(n_lists);
+    out.succ.resize(n_succ);
+    auto fill = [&](size_t si) {
+        const PathSite& ps = out.sites[si];
+        place_path_entries(parts[si].entries, out.table.data() + ps.table_off, (size_t)ps.table_mask + 1);
+        std::copy(parts[si].lists.begin(), parts[si].lists.end(), out.lists.begin() + ps.lists_off);
+        std::copy(parts[si].succ.begin(), parts[si].succ.end(), out.succ.begin() + ps.succ_ptr_off);
+    };
+    if (threads <= 1)
+        for (size_t si = 0; si < ns; ++si)
+            fill(si);
+    else
+    {
+        std::vector<std::thread> pool;
+        for (int w = 0; w < threads; ++w)
+            pool.emplace_back([&, w]() {
+                for (size_t si = (size_t)w; si < ns; si += (size_t)threads)
+                    fill(si);
+            });
+        for (auto& th : pool)
+            th.join();
     }
 }
 

@@ -10,6 +10,7 @@
 // There is deliberately no CPU path in this file: without a CUDA device every entry point returns PG_E_CUDA.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -39,7 +40,7 @@ namespace
 #define PG_FILL_UNROLL 4
 #endif
 #ifndef PG_FAST_UNROLL
-#define PG_FAST_UNROLL 4
+#define PG_FAST_UNROLL 8
 #endif
 #ifndef PG_FAST_BLOCKS
 #define PG_FAST_BLOCKS 1
@@ -1129,6 +1130,7 @@ struct pg_ctx
     DevBuf<int32_t> d_plists, d_psucc, d_todo, d_ntodo;
     DevBuf<unsigned long long> d_pcount;
     unsigned long long path_counters[3] = { 0, 0, 0 };
+    unsigned long long path_index_us = 0; // host time of the last index build
     bool path_ran = false;
     float path_ms = 0;
     cudaEvent_t path_ev[2] = { nullptr, nullptr };
@@ -1208,7 +1210,9 @@ int upload_path_index(pg_ctx* c)
     if (!c->path_dirty)
         return PG_OK;
     host::PathIndexHost ix;
+    const auto t0 = std::chrono::steady_clock::now();
     host::build_path_index(c->graphs, c->path_k, ix);
+    c->path_index_us = (unsigned long long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     PG_CUDA(c, put(c, c->d_psites, ix.sites));
     PG_CUDA(c, put(c, c->d_ptable, ix.table));
     PG_CUDA(c, put(c, c->d_plists, ix.lists));
@@ -2110,7 +2114,7 @@ int pg_set_stages(pg_ctx* c, int32_t path_kmer_len, int32_t graph_matching, int3
     return PG_OK;
 }
 
-int pg_path_stats(pg_ctx* c, uint64_t* counters3, float* path_ms)
+int pg_path_stats(pg_ctx* c, uint64_t* counters4, float* path_ms)
 {
     if (!c)
         return PG_E_ARG;
@@ -2128,9 +2132,12 @@ int pg_path_stats(pg_ctx* c, uint64_t* counters3, float* path_ms)
         c->path_counters[0] = c->path_counters[1] = c->path_counters[2] = 0;
         c->path_ms = 0;
     }
-    if (counters3)
+    if (counters4)
+    {
         for (int i = 0; i < 3; ++i)
-            counters3[i] = c->path_counters[i];
+            counters4[i] = c->path_counters[i];
+        counters4[3] = c->path_index_us;
+    }
     if (path_ms)
         *path_ms = c->path_ms;
     return PG_OK;

@@ -4,12 +4,11 @@ import os, subprocess, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 OUT = os.path.join(ROOT, "ab_build")
 VARIANTS = {
-    "noopt": ["-DPG_FAST_BLOCKS=0", "-DPG_LAZY_F=0"],
-    "fast": ["-DPG_FAST_BLOCKS=1", "-DPG_LAZY_F=0"],
-    "fast_lazy": ["-DPG_FAST_BLOCKS=1", "-DPG_LAZY_F=1"],
-    "fast_lazy_u8": ["-DPG_FAST_BLOCKS=1", "-DPG_LAZY_F=1", "-DPG_FAST_UNROLL=8"],
-    "fast_u8": ["-DPG_FAST_BLOCKS=1", "-DPG_LAZY_F=0", "-DPG_FAST_UNROLL=8"],
-    "lazy": ["-DPG_FAST_BLOCKS=0", "-DPG_LAZY_F=1"],
+    "base_u8": [],
+    "u16": ["-DPG_FAST_UNROLL=16"],
+    "u8_w2": ["-DPG_FILL_WARPS=2"],
+    "u8_w8": ["-DPG_FILL_WARPS=8"],
+    "u8_ck32": ["-DPG_CK=32"],
 }
 def build():
     os.makedirs(OUT, exist_ok=True)
