@@ -72,6 +72,62 @@ def test_multisite_counts_match_oracle(built, use_filters):
         ctx.close()
 
 
+def test_counts_behind_the_cascade(built):
+    """alignAndDisambiguate with path_sequence_matching on (the `paragraph` default): exact matches come from the
+    exact-match stage (its own strand convention: graph_reverse = matched strand), non-unique ones get their second
+    chance in gssw because the default filter chain rejects them, everything else is gssw -- then the same filter /
+    disambiguation / counting.  Expected = the oracle's counting over the cascade of the two alignment oracles."""
+    from test_gpu_parity import _cascade_expected
+    rng = np.random.default_rng(321)
+    kinds = ["DEL", "INS", "DUP", "INV", "bubble", "DEL"]
+    ctx = capi.Context(0)
+    try:
+        ctx.set_stages(16, True, True)
+        sites, all_reads, all_sites, all_rev, all_frag, fbase = [], [], [], [], [], 0
+        for k in range(12):
+            nodes, edges, masks, reads, is_rev, frag = fuzz_site(rng, kinds[k % 6])
+            # make a good share of the reads exact so that the stage has something to map
+            haps = synth.haplotypes(nodes, edges)
+            for i in range(0, len(reads), 2):
+                h = haps[int(rng.integers(0, len(haps)))]
+                L = min(len(h), len(reads[i]))
+                st = int(rng.integers(0, len(h) - L + 1))
+                reads[i] = h[st:st + L] if rng.random() < 0.5 else synth.revcomp_exact(h[st:st + L])
+            sites.append((nodes, edges, masks, reads, is_rev, frag))
+            sid = ctx.add_graph(nodes, edges)
+            ctx.set_edge_labels(sid, masks)
+            all_reads += reads
+            all_sites += [sid] * len(reads)
+            all_rev += is_rev
+            all_frag += [fbase + f for f in frag]
+            fbase += max(frag) + 1
+        blob, off = ctx.pack_reads(all_reads)
+        rec, ops = ctx.align_packed(blob, off, np.array(all_sites, dtype=np.int32))
+        assert (rec["mapped_by"] == 1).sum() > len(all_reads) // 8
+        kw = dict(remove_nonuniq=True, bad_align_frac=0.8, use_filters=True)
+        got = ctx.count(fragment=all_frag, is_rev=all_rev, **kw)
+        r0 = 0
+        for k, ((nodes, edges, masks, reads, is_rev, frag), (n0, n1, e0, e1)) in enumerate(
+                zip(sites, site_slices([(len(s[0]), len(s[1])) for s in sites]))):
+            al, _ = _cascade_expected(nodes, edges, reads, 16, is_rev, True, True)
+            o = R.oracle_count_site([len(s) for s in nodes], edges, masks, [len(r) for r in reads],
+                                    [a["pos"] for a in al], [a["unique"] for a in al], [a["cigar"] for a in al],
+                                    [a["graph_reverse"] for a in al], frag, **kw)
+            sl = slice(r0, r0 + len(reads))
+            assert (got["support"]["verdict"][sl] == o["support"]["verdict"]).all(), k
+            assert (got["support"]["graph_reverse"][sl] == o["support"]["graph_reverse"]).all(), k
+            assert (got["support"]["sequences"][sl] == o["support"]["sequences"]).all(), k
+            assert (got["node_counts"][n0:n1] == o["node_counts"]).all(), k
+            assert (got["edge_counts"][e0:e1] == o["edge_counts"]).all(), k
+            fam = {m: v for (s, m), v in got["families"].items() if s == k}
+            assert set(fam) == set(o["families"]), k
+            for m in fam:
+                assert (fam[m] == o["families"][m]).all(), (k, hex(m))
+            r0 += len(reads)
+    finally:
+        ctx.close()
+
+
 def import_phasing(ctx, g, site, keep):
     rd, frag = phasing_inputs(g, keep)
     sid = ctx.add_graph(["A" * n for n in site["lens"]], site["edges"])
