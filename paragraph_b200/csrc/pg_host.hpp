@@ -281,6 +281,28 @@ struct PathSiteBuild
     std::vector<int32_t> lists;     // node lists of the kept entries
 };
 
+// successors of every node of a site, ascending, without duplicates; csr = succ_ptr[n+1], succ_idx[]
+inline void build_successors(const GraphStore& gs, size_t si, std::vector<std::vector<int32_t>>& succ,
+                             std::vector<int32_t>& csr)
+{
+    const int n = gs.sites[si].n_nodes;
+    succ.assign((size_t)n, std::vector<int32_t>());
+    for (int64_t e = gs.edge_base[si]; e < gs.edge_base[si + 1]; ++e)
+        succ[(size_t)gs.in_from[(size_t)e]].push_back(gs.in_to[(size_t)e]);
+    int32_t ptr = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        auto& v = succ[(size_t)i];
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        csr.push_back(ptr);
+        ptr += (int32_t)v.size();
+    }
+    csr.push_back(ptr);
+    for (int i = 0; i < n; ++i)
+        csr.insert(csr.end(), succ[(size_t)i].begin(), succ[(size_t)i].end());
+}
+
 inline void build_path_site(const GraphStore& gs, size_t si, int k, PathSiteBuild& out)
 {
     struct KP
@@ -293,24 +315,8 @@ inline void build_path_site(const GraphStore& gs, size_t si, int k, PathSiteBuil
     const int32_t* t = gs.ints.data() + sd.tab_off[0];
     const int32_t *node_start = t, *node_len = t + n;
     const uint8_t* raw = gs.bytes.data() + sd.raw_off;
-    // successors, ascending, without duplicates
-    std::vector<std::vector<int32_t>> succ((size_t)n);
-    for (int64_t e = gs.edge_base[si]; e < gs.edge_base[si + 1]; ++e)
-        succ[(size_t)gs.in_from[(size_t)e]].push_back(gs.in_to[(size_t)e]);
-    {
-        int32_t ptr = 0;
-        for (int i = 0; i < n; ++i)
-        {
-            auto& v = succ[(size_t)i];
-            std::sort(v.begin(), v.end());
-            v.erase(std::unique(v.begin(), v.end()), v.end());
-            out.succ.push_back(ptr);
-            ptr += (int32_t)v.size();
-        }
-        out.succ.push_back(ptr);
-        for (int i = 0; i < n; ++i)
-            out.succ.insert(out.succ.end(), succ[(size_t)i].begin(), succ[(size_t)i].end());
-    }
+    std::vector<std::vector<int32_t>> succ;
+    build_successors(gs, si, succ, out.succ);
     // enumerate the k-mer paths: inside a node by rolling the hash along it, across node ends depth first over the
     // successors like extendPathEnd
     std::vector<KP> kps;
@@ -470,10 +476,47 @@ inline void place_path_entries(const std::vector<PathEntry>& entries, PathEntry*
     {
         const uint64_t h = ((uint64_t)e.key_hi << 32) | e.key_lo;
         uint32_t slot = (uint32_t)(h ^ (h >> 29)) & (uint32_t)(cap - 1);
-        while (tab[slot].n_nodes != 0)
+        while ((tab[slot].key_lo | tab[slot].key_hi) != 0u)
             slot = (slot + 1) & (uint32_t)(cap - 1);
         tab[slot] = e;
     }
+}
+
+// ---- sizing for the DEVICE-side build (pg_kernels.cu: pg_path_index_*): how many k-mer paths a site has, and an upper
+// bound of the node-list entries they need.  P[v][r] = number of ways to read r more characters starting at the first
+// character of node v (extendPathEnd, PathOperations.cpp:73-103): 1 if they fit the node, else the sum over successors.
+inline void count_kmer_paths(const GraphStore& gs, size_t si, int k, const int32_t* succ_ptr, const int32_t* succ_idx,
+                             int64_t& n_paths, int64_t& list_ints)
+{
+    const SiteDev& sd = gs.sites[si];
+    const int n = sd.n_nodes;
+    const int32_t* node_len = gs.ints.data() + sd.tab_off[0] + n;
+    std::vector<double> P((size_t)n * (size_t)k, 0.0); // [v][r], r = 1 .. k-1 (doubles: dense graphs can overflow int64)
+    for (int v = n - 1; v >= 0; --v) // successors have larger ids
+        for (int r = 1; r < k; ++r)
+        {
+            double c = 0;
+            if (r <= node_len[v])
+                c = 1;
+            else
+                for (int x = succ_ptr[v]; x < succ_ptr[v + 1]; ++x)
+                    c += P[(size_t)succ_idx[x] * (size_t)k + (size_t)(r - node_len[v])];
+            P[(size_t)v * (size_t)k + (size_t)r] = c;
+        }
+    double paths = 0, multi = 0;
+    for (int v = 0; v < n; ++v)
+    {
+        const int len = node_len[v];
+        paths += std::max(0, len - k + 1);
+        for (int pos = std::max(0, len - k + 1); pos < len; ++pos)
+        {
+            const int r = k - (len - pos);
+            for (int x = succ_ptr[v]; x < succ_ptr[v + 1]; ++x)
+                multi += P[(size_t)succ_idx[x] * (size_t)k + (size_t)r];
+        }
+    }
+    n_paths = (int64_t)std::min(paths + multi, 4e18);
+    list_ints = (int64_t)std::min(paths + multi * (double)std::min(k, n), 4e18);
 }
 
 // all sites; the per-site builds are independent and run on a few host threads

@@ -806,9 +806,9 @@ __global__ void __launch_bounds__(PATHW_WARPS * 32) pg_path_warp_kernel(const Pa
                     for (uint32_t slot = (uint32_t)(hk ^ (hk >> 29)) & (uint32_t)v.mask;; slot = (slot + 1) & (uint32_t)v.mask)
                     {
                         const PathEntry& e = v.table[slot];
-                        if (e.n_nodes == 0)
+                        if ((e.key_lo | e.key_hi) == 0u)
                             break;
-                        if (e.key_lo == lo && e.key_hi == hi)
+                        if (e.n_nodes > 0 && e.key_lo == lo && e.key_hi == hi)
                         {
                             cand = (int32_t)slot;
                             break;
@@ -840,9 +840,9 @@ __global__ void __launch_bounds__(PATHW_WARPS * 32) pg_path_warp_kernel(const Pa
                 while (true)
                 {
                     const PathEntry& e = v.table[slot];
-                    if (e.n_nodes == 0)
+                    if ((e.key_lo | e.key_hi) == 0u)
                         break;
-                    if (e.key_lo == v.table[hit[found]].key_lo && e.key_hi == v.table[hit[found]].key_hi)
+                    if (e.n_nodes > 0 && e.key_lo == v.table[hit[found]].key_lo && e.key_hi == v.table[hit[found]].key_hi)
                     {
                         int j = found;
                         ok = true;
@@ -943,6 +943,159 @@ __global__ void __launch_bounds__(PATHW_WARPS * 32) pg_path_warp_kernel(const Pa
             rec.status = (uint8_t)ST_UNMAPPED;
             a.records[rd] = rec;
         }
+    }
+}
+
+// ---- building the exact-match index on the device --------------------------------------------------------------
+// The host build (pg_host.hpp: build_path_index) costs ~25 us per site and thread; for a batch of 1 000 new sites that
+// is as long as aligning their reads.  Here: one thread per start position of every site enumerates its k-mer paths
+// (depth first over the successors, like extendPathEnd) and
+//   pass 1 (pg_path_index_count): claims the table slot of each path's 64-bit hash (atomicCAS on the key) and adds the
+//           path to the slot's occurrence count and to the slot's sum of a second, independent 64-bit hash;
+//   pass 2 (pg_path_index_fill): a path whose slot counts exactly one occurrence is the unique path of its k-mer and
+//           writes the entry (positions, node list); slots with more occurrences stay occupied but unusable.  Should
+//           two DIFFERENT k-mers ever share a 64-bit hash, the second-hash sum of their slot differs from
+//           count x second hash: the flag is raised and the host builds the index instead (exact in every case).
+constexpr int PATH_KMAX_DEV = 64; // deepest stack of the device enumeration; longer k-mers use the host build
+constexpr uint64_t PATH_HASH_B2 = 0xD6E8FEB86659FD93ull;
+
+struct PathBuildArgs
+{
+    const SiteDev* sites;
+    const uint8_t* gbytes;
+    const int32_t* gints;
+    const PathSite* psites;
+    const int32_t* psucc;
+    const int32_t* col_base; // [n_sites + 1] first start position of each site in the flat thread index
+    int n_sites, k;
+    PathEntry* table;
+    uint32_t* cnt;           // per slot: occurrences
+    unsigned long long* sum2; // per slot: sum of the second hash
+    int32_t* lists;
+    int32_t* list_cursor;    // per site
+    const int32_t* list_cap; // per site
+    int* flag;               // 1 = hash collision between different k-mers, 2 = a capacity was exceeded
+};
+
+template <bool FILL> __global__ void __launch_bounds__(128) pg_path_index_kernel(const PathBuildArgs a)
+{
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= a.col_base[a.n_sites])
+        return;
+    int lo = 0, hi = a.n_sites - 1; // site of this start position
+    while (lo < hi)
+    {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.col_base[mid] <= gid)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const int site = lo;
+    const SiteDev sd = a.sites[site];
+    const PathSite ps = a.psites[site];
+    const int32_t* t = a.gints + sd.tab_off[0];
+    const int32_t *node_start = t, *node_len = t + sd.n_nodes;
+    const int32_t* succ_ptr = a.psucc + ps.succ_ptr_off;
+    const int32_t* succ_idx = succ_ptr + sd.n_nodes + 1;
+    const uint8_t* raw = a.gbytes + ps.raw_off;
+    PathEntry* tab = a.table + ps.table_off;
+    const uint32_t mask = (uint32_t)ps.table_mask;
+    const int k = a.k;
+    const int col = gid - a.col_base[site];
+    int v0 = 0;
+    while (v0 + 1 < sd.n_nodes && node_start[v0 + 1] <= col)
+        ++v0;
+    const int pos = col - node_start[v0];
+
+    int nodes[PATH_KMAX_DEV + 1], endp[PATH_KMAX_DEV + 2], ext[PATH_KMAX_DEV + 2], nxt[PATH_KMAX_DEV + 2];
+    int depth = 1;
+    nodes[0] = v0;
+    endp[1] = pos;
+    ext[1] = k - 1;
+    nxt[1] = 0;
+    while (depth > 0)
+    {
+        const int last = nodes[depth - 1];
+        const int room = node_len[last] - endp[depth] - 1;
+        if (ext[depth] > room)
+        {
+            if (nxt[depth] >= succ_ptr[last + 1] - succ_ptr[last])
+            {
+                --depth;
+                continue;
+            }
+            const int c = succ_idx[succ_ptr[last] + nxt[depth]++];
+            nodes[depth] = c;
+            endp[depth + 1] = 0;
+            ext[depth + 1] = ext[depth] - room - 1;
+            nxt[depth + 1] = 0;
+            ++depth;
+            continue;
+        }
+        // a complete k-mer path: nodes[0 .. depth), from pos in the first to end_pos in the last
+        const int end_pos = endp[depth] + ext[depth];
+        uint64_t h = 0, h2 = 0;
+        for (int x = 0; x < depth; ++x)
+        {
+            const int nd = nodes[x];
+            const int p0 = x == 0 ? pos : 0, p1 = x == depth - 1 ? end_pos : node_len[nd] - 1;
+            const uint8_t* sq = raw + node_start[nd];
+            for (int p = p0; p <= p1; ++p)
+            {
+                h = path_hash_step(h, sq[p]);
+                h2 = h2 * PATH_HASH_B2 + (uint64_t)sq[p] + 1u;
+            }
+        }
+        if (h == 0)
+            h = 1;
+        uint32_t slot = (uint32_t)(h ^ (h >> 29)) & mask;
+        for (uint32_t probes = 0;; slot = (slot + 1) & mask, ++probes)
+        {
+            unsigned long long* key = reinterpret_cast<unsigned long long*>(&tab[slot]); // key_lo | key_hi << 32
+            unsigned long long cur = FILL ? *key : atomicCAS(key, 0ull, (unsigned long long)h);
+            if (!FILL && cur == 0ull)
+                cur = h;
+            if (cur == h)
+                break;
+            if (probes > mask) // table full: cannot happen with the host's sizing
+            {
+                atomicExch(a.flag, 2);
+                return;
+            }
+        }
+        const size_t gslot = (size_t)ps.table_off + slot;
+        if (!FILL)
+        {
+            atomicAdd(a.cnt + gslot, 1u);
+            atomicAdd(a.sum2 + gslot, (unsigned long long)h2);
+        }
+        else
+        {
+            const uint32_t n = a.cnt[gslot];
+            if (n == 1)
+            {
+                const int off = atomicAdd(a.list_cursor + site, depth);
+                if (off + depth > a.list_cap[site])
+                    atomicExch(a.flag, 2);
+                else
+                {
+                    for (int x = 0; x < depth; ++x)
+                        a.lists[ps.lists_off + off + x] = nodes[x];
+                    tab[slot].start_pos = pos;
+                    tab[slot].end_pos = end_pos;
+                    tab[slot].nodes_off = off;
+                    tab[slot].n_nodes = depth;
+                }
+            }
+            else
+            {
+                tab[slot].n_nodes = -1; // occupied, not a unique k-mer (several paths write the same value)
+                if (a.sum2[gslot] != (unsigned long long)n * h2)
+                    atomicExch(a.flag, 1); // different k-mers under one 64-bit hash: let the host do it exactly
+            }
+        }
+        --depth;
     }
 }
 
@@ -1127,7 +1280,11 @@ struct pg_ctx
     bool path_dirty = true;
     DevBuf<PathSite> d_psites;
     DevBuf<PathEntry> d_ptable;
-    DevBuf<int32_t> d_plists, d_psucc, d_todo, d_ntodo;
+    DevBuf<int32_t> d_plists, d_psucc, d_todo, d_ntodo, d_pcolbase, d_plistcap, d_plistcur;
+    DevBuf<uint32_t> d_pcnt;
+    DevBuf<unsigned long long> d_psum2;
+    bool path_host_index = false;      // PG_PATH_HOST_INDEX=1: build the index on the host (A/B, fallback testing)
+    bool path_index_on_device = false; // how the current index was built
     DevBuf<unsigned long long> d_pcount;
     unsigned long long path_counters[3] = { 0, 0, 0 };
     unsigned long long path_index_us = 0; // host time of the last index build
@@ -1204,20 +1361,122 @@ int upload_graphs(pg_ctx* c)
 
 template <typename T> cudaError_t put(pg_ctx* c, DevBuf<T>& d, const std::vector<T>& h);
 
-// index of the exact-match stage (unique k-mer paths of every site), built on the host and uploaded once per graph set
-int upload_path_index(pg_ctx* c)
+// index of the exact-match stage on the host (pg_host.hpp), uploaded
+int upload_path_index_host(pg_ctx* c)
 {
-    if (!c->path_dirty)
-        return PG_OK;
     host::PathIndexHost ix;
-    const auto t0 = std::chrono::steady_clock::now();
     host::build_path_index(c->graphs, c->path_k, ix);
-    c->path_index_us = (unsigned long long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     PG_CUDA(c, put(c, c->d_psites, ix.sites));
     PG_CUDA(c, put(c, c->d_ptable, ix.table));
     PG_CUDA(c, put(c, c->d_plists, ix.lists));
     PG_CUDA(c, put(c, c->d_psucc, ix.succ));
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PG_OK;
+}
+
+// ... and on the device (pg_path_index_kernel): the host only sizes the tables.  Returns PG_OK with *done = false when
+// the device build has to be redone on the host (hash collision between different k-mers / k too long).
+int build_path_index_device(pg_ctx* c, bool* done)
+{
+    *done = false;
+    const host::GraphStore& gs = c->graphs;
+    const size_t ns = gs.sites.size();
+    const int k = c->path_k;
+    if (k > PATH_KMAX_DEV || c->path_host_index)
+        return PG_OK;
+    std::vector<PathSite> psites(ns);
+    std::vector<int32_t> succ, col_base(ns + 1, 0), list_cap(ns, 0);
+    size_t n_table = 0, n_lists = 0;
+    const auto dbg0 = std::chrono::steady_clock::now();
+    auto dbg = [&](const char* what) {
+        if (getenv("PG_DEBUG_TIMING"))
+            fprintf(stderr, "[pg] index build: %s at %.2f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - dbg0).count());
+    };
+    for (size_t si = 0; si < ns; ++si)
+    {
+        PathSite& ps = psites[si];
+        ps.k = k;
+        ps.raw_off = gs.sites[si].raw_off;
+        ps.succ_ptr_off = (int32_t)succ.size();
+        std::vector<std::vector<int32_t>> sv;
+        host::build_successors(gs, si, sv, succ);
+        int64_t n_paths = 0, list_ints = 0;
+        host::count_kmer_paths(gs, si, k, succ.data() + ps.succ_ptr_off, succ.data() + ps.succ_ptr_off + gs.sites[si].n_nodes + 1,
+                               n_paths, list_ints);
+        const size_t cap = host::path_table_cap((size_t)std::min<int64_t>(n_paths, (int64_t)1 << 40));
+        if (n_table + cap > ((size_t)1 << 28) || n_lists + (size_t)list_ints > ((size_t)1 << 30))
+            return fail(c, PG_E_GRAPH, "exact-match stage: the graphs have too many k-mer paths for the index ("
+                            + std::to_string(n_paths) + " in site " + std::to_string(si) + ")");
+        ps.table_off = (int32_t)n_table;
+        ps.table_mask = (int32_t)(cap - 1);
+        ps.lists_off = (int32_t)n_lists;
+        list_cap[si] = (int32_t)list_ints;
+        n_table += cap;
+        n_lists += (size_t)list_ints;
+        col_base[si + 1] = col_base[si] + gs.sites[si].G;
+    }
+    dbg("sized");
+    PG_CUDA(c, put(c, c->d_psites, psites));
+    PG_CUDA(c, put(c, c->d_psucc, succ));
+    PG_CUDA(c, put(c, c->d_pcolbase, col_base));
+    PG_CUDA(c, put(c, c->d_plistcap, list_cap));
+    PG_CUDA(c, c->d_ptable.reserve(n_table));
+    PG_CUDA(c, c->d_pcnt.reserve(n_table));
+    PG_CUDA(c, c->d_psum2.reserve(n_table));
+    PG_CUDA(c, c->d_plists.reserve(n_lists + 1));
+    PG_CUDA(c, c->d_plistcur.reserve(ns + 1)); // + the flag
+    dbg("allocated");
+    PG_CUDA(c, cudaMemsetAsync(c->d_ptable.p, 0, n_table * sizeof(PathEntry), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_pcnt.p, 0, n_table * sizeof(uint32_t), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_psum2.p, 0, n_table * sizeof(unsigned long long), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_plistcur.p, 0, (ns + 1) * sizeof(int32_t), c->stream));
+    PathBuildArgs ba;
+    ba.sites = c->d_sites.p;
+    ba.gbytes = c->d_gbytes.p;
+    ba.gints = c->d_gints.p;
+    ba.psites = c->d_psites.p;
+    ba.psucc = c->d_psucc.p;
+    ba.col_base = c->d_pcolbase.p;
+    ba.n_sites = (int)ns;
+    ba.k = k;
+    ba.table = c->d_ptable.p;
+    ba.cnt = c->d_pcnt.p;
+    ba.sum2 = c->d_psum2.p;
+    ba.lists = c->d_plists.p;
+    ba.list_cursor = c->d_plistcur.p;
+    ba.list_cap = c->d_plistcap.p;
+    ba.flag = c->d_plistcur.p + ns;
+    const int grid = (col_base[ns] + 127) / 128;
+    pg_path_index_kernel<false><<<grid, 128, 0, c->stream>>>(ba);
+    pg_path_index_kernel<true><<<grid, 128, 0, c->stream>>>(ba);
+    PG_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    int flag = 0;
+    PG_CUDA(c, cudaMemcpyAsync(&flag, ba.flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    dbg(flag ? "kernels done, FLAG raised" : "kernels done");
+    *done = flag == 0;
+    return PG_OK;
+}
+
+int upload_path_index(pg_ctx* c)
+{
+    if (!c->path_dirty)
+        return PG_OK;
+    const auto t0 = std::chrono::steady_clock::now();
+    bool done = false;
+    int rc = build_path_index_device(c, &done);
+    if (rc != PG_OK)
+        return rc;
+    c->path_index_on_device = done;
+    if (!done)
+    {
+        rc = upload_path_index_host(c);
+        if (rc != PG_OK)
+            return rc;
+    }
+    c->path_index_us = (unsigned long long)std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
     c->path_dirty = false;
     return PG_OK;
 }
@@ -1521,6 +1780,8 @@ int pg_create(int device, pg_ctx** out)
         c->split = std::max(1, atoi(e));
     if (const char* e = getenv("PG_NO_TMA"))
         c->use_tma = atoi(e) == 0;
+    if (const char* e = getenv("PG_PATH_HOST_INDEX"))
+        c->path_host_index = atoi(e) != 0;
     if (const char* e = getenv("PG_PATH_SCALAR"))
         c->path_scalar = atoi(e) != 0;
     if (const char* e = getenv("PG_GEOM_W"))
@@ -1560,6 +1821,11 @@ void pg_destroy(pg_ctx* c)
     c->d_ntodo.release();
     c->d_pcount.release();
     c->d_prerev.release();
+    c->d_pcolbase.release();
+    c->d_plistcap.release();
+    c->d_plistcur.release();
+    c->d_pcnt.release();
+    c->d_psum2.release();
     for (auto& ev : c->path_ev)
         if (ev)
             cudaEventDestroy(ev);

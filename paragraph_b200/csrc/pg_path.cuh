@@ -29,7 +29,8 @@ struct PathEntry // one unique k-mer of a site
     uint32_t key_lo, key_hi; // hash of the k characters; key_hi | key_lo == 0 never occurs (host adds 1 on zero)
     int32_t start_pos;       // position in the first node
     int32_t nodes_off;       // first entry of the node list in PathSite::node_lists
-    int32_t n_nodes;         // 0 = empty slot
+    int32_t n_nodes;         // > 0: nodes on the path; <= 0 with a key: a k-mer that is NOT unique (device-built tables
+                             // keep such slots occupied so that probing continues past them); key 0 = empty slot
     int32_t end_pos;         // position in the last node (inclusive)
 };
 
@@ -107,9 +108,9 @@ PG_HD const PathEntry* path_lookup(const PathView& v, uint64_t h, const uint8_t*
     for (uint32_t slot = (uint32_t)(h ^ (h >> 29)) & (uint32_t)v.mask;; slot = (slot + 1) & (uint32_t)v.mask)
     {
         const PathEntry& e = v.table[slot];
-        if (e.n_nodes == 0)
+        if ((e.key_lo | e.key_hi) == 0u)
             return nullptr;
-        if (e.key_lo == lo && e.key_hi == hi && path_entry_matches(v, e, bases, L, strand, pos))
+        if (e.n_nodes > 0 && e.key_lo == lo && e.key_hi == hi && path_entry_matches(v, e, bases, L, strand, pos))
             return &e;
     }
 }
@@ -299,12 +300,13 @@ PG_UNROLL
         for (int j = 0; j < PATH_BATCH; ++j) // first probe slot of every position of the batch
         {
             const uint64_t hj = h[j] ? h[j] : 1;
-            nn[j] = j < nb ? v.table[(uint32_t)(hj ^ (hj >> 29)) & (uint32_t)v.mask].n_nodes : 0;
+            const PathEntry& e0 = v.table[(uint32_t)(hj ^ (hj >> 29)) & (uint32_t)v.mask];
+            nn[j] = (j < nb && (e0.key_lo | e0.key_hi) != 0u) ? 1 : 0;
         }
         bool jumped = false;
         for (int j = 0; j < nb; ++j)
         {
-            if (nn[j] == 0) // empty slot: this k-mer is on no unique path
+            if (nn[j] == 0) // empty first slot: this k-mer is on no path at all
                 continue;
             const uint64_t hj = h[j] ? h[j] : 1;
             // occupied: the full lookup (key compare, collision check along the entry's nodes, further probing)

@@ -402,3 +402,27 @@ def test_path_stage_config2_mix(ctx):
         assert 0.3 < frac < 0.95
     finally:
         ctx.set_stages(0, True)
+
+
+def test_path_index_host_build_gives_the_same(built, monkeypatch):
+    """The k-mer index is built on the device by default (pg_path_index_kernel); PG_PATH_HOST_INDEX=1 selects the host
+    build (pg_host.hpp: build_path_index, also the fallback after a hash collision and for k > 64).  Both against the
+    oracle cascade, incl. a k-mer length the device build does not take."""
+    from test_path_oracle import path_cases
+    R.set_fill_variant(0)
+    for host_index, k_override in (("1", None), ("0", None), ("0", 70)):
+        monkeypatch.setenv("PG_PATH_HOST_INDEX", host_index)
+        c = capi.Context(0)
+        try:
+            rng = np.random.default_rng(51)
+            for nodes, edges, reads, k in path_cases(rng, 40):
+                k = k_override or k
+                c.clear_graphs()
+                c.add_graph(nodes, edges)
+                c.set_stages(k, True, True)
+                exp, cnt = _cascade_expected(nodes, edges, reads, k, None, True, True)
+                assert strip_status(c.align(reads)) == exp, (host_index, k, nodes, edges)
+                st = c.path_stats()
+                assert (st["attempted"], st["anchored"], st["mapped"]) == cnt
+        finally:
+            c.close()

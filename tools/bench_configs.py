@@ -44,7 +44,7 @@ def run(ctx, name, sites, check_sites=6):
     # the same batch through the cascade (exact-match stage in front, k = 32; second chance as the default filters cause)
     ctx.set_stages(32, True, True)
     t0 = time.perf_counter()
-    ctx.align_packed(blob, off, st)  # first call: builds + uploads the k-mer index of every site (host)
+    ctx.align_packed(blob, off, st)  # first call: builds the k-mer index of every site (on the device)
     torch.cuda.synchronize(); first = time.perf_counter() - t0
     t0 = time.perf_counter()
     for _ in range(3):
@@ -53,7 +53,7 @@ def run(ctx, name, sites, check_sites=6):
     ps, s2 = ctx.path_stats(), ctx.stats()
     ctx.set_stages(0, True, False)
     print("%-8s   cascade: e2e %.1f ms (%.2f Mreads/s), %d of %d reads by the exact-match stage (%.3f ms), fill+trace %.2f ms; "
-          "first call %.1f ms of which index build %.1f ms (host, %d sites)"
+          "first call %.1f ms of which index build %.1f ms (%d sites)"
           % ("", dt2 * 1e3, len(reads) / dt2 / 1e6, ps["mapped"], len(reads), ps["path_ms"], s2["fill_ms"] + s2["trace_ms"],
              first * 1e3, ps["index_build_ms"], len(sites)), flush=True)
     return bad
