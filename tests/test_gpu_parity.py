@@ -143,6 +143,30 @@ def test_many_nodes_graph(ctx, n_nodes):
     assert strip_status(ctx.align(reads)) == R.OracleGraph(nodes, edges).align_batch(reads)
 
 
+@pytest.mark.parametrize("n_nodes", [30, 120])
+def test_many_nodes_graph_long_reads(ctx, n_nodes):
+    """WIDE geometries (R = 10 / 16) with many-node graphs: the 4-word node tables in shared memory with fewer warps per
+    CTA (30 nodes) and in HBM (120 nodes), with the exact-match stage in front for half of the runs."""
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(77 + n_nodes)
+    nodes, edges = synth.bubble_graph(rng, n_nodes=n_nodes, max_len=60, p_edge=0.1 if n_nodes < 100 else 0.03)
+    reads = synth.fuzz_reads(rng, nodes, edges, 60, min_len=150, max_len=320) + \
+        synth.fuzz_reads(rng, nodes, edges, 40, min_len=321, max_len=512)
+    try:
+        for k in (0, 16):
+            for part in (reads[:60], reads):  # R = 10 batch, then an R = 16 batch
+                ctx.clear_graphs()
+                ctx.add_graph(nodes, edges)
+                ctx.set_stages(k, True, True)
+                if k:
+                    exp, _ = _cascade_expected(nodes, edges, part, k, None, True, True)
+                else:
+                    exp = R.OracleGraph(nodes, edges).align_batch(part)
+                assert strip_status(ctx.align(part)) == exp, (k, len(part))
+    finally:
+        ctx.set_stages(0, True, False)
+
+
 def test_empty_batch_is_legal(ctx):
     ctx.clear_graphs()
     ctx.add_graph(["ACGT"], [])
