@@ -144,6 +144,42 @@ int main()
                        (int)r->graph_mapping_status());
             printf("cascade %u %u %u %u %u\n", cascade.attempted(), cascade.mappedPath(), cascade.anchoredPath(),
                    cascade.mappedSw(), cascade.filtered());
+
+            // ... and the same cascade under alignAndCount: exact-match stage + second chance on the device, supports
+            // and counts from the device's counting stage (path-mapped reads keep PathAligner's strand convention)
+            Graph lg = graph;
+            lg.addLabelToEdge(0, 1, "P");
+            lg.addLabelToEdge(1, 3, "P");
+            lg.addLabelToEdge(0, 2, "Q");
+            lg.addLabelToEdge(2, 3, "Q");
+            lg.addLabelToEdge(0, 3, "D");
+            const char* names[] = { "LF", "P1", "Q1", "RF" };
+            for (uint32_t v = 0; v < 4; ++v)
+                lg.setNodeName(v, names[v]);
+            std::vector<std::unique_ptr<Read>> cd;
+            for (int i = 0; i < 10; ++i)
+                cd.emplace_back(new Read("c" + std::to_string(i + 1), cr[i], std::string(strlen(cr[i]), '#')));
+            grm::MultiSiteAligner<std::unique_ptr<Read>> counter;
+            counter.setPathMatching(8);
+            counter.addSite(&lg, &cd);
+            pgb::paragraph::CountOptions opt;
+            opt.use_support_filters = false;
+            auto counts = counter.alignAndCount(opt);
+            for (auto const& r : cd)
+            {
+                printf("k %s %s n", r->fragment_id().c_str(), r->graph_cigar().c_str());
+                for (auto const& x : r->graph_nodes_supported())
+                    printf(" %s", x.c_str());
+                printf(" q");
+                for (auto const& x : r->graph_sequences_supported())
+                    printf(" %s", x.c_str());
+                printf("\n");
+            }
+            for (auto const& kv : counts[0].read_counts_by_node)
+                printf("kn %s %llu %llu %llu %llu\n", kv.first.c_str(), (unsigned long long)kv.second.fragments,
+                       (unsigned long long)kv.second.reads, (unsigned long long)kv.second.fwd, (unsigned long long)kv.second.rev);
+            for (auto const& kv : counts[0].read_counts_by_edge)
+                printf("ke %s %llu\n", kv.first.c_str(), (unsigned long long)kv.second.fragments);
         }
     }
     catch (std::exception const& e)

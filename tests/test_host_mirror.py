@@ -40,6 +40,8 @@ def test_mirror_reproduces_reference_unit_test(built):
     ]
     # alignAndCount: supports as ParagraphTest.Aligns expects them (test_paragraph_parts.cpp:113-144), f7 filtered
     # (nonuniq); counts as the reference build gives them for these six single-read fragments
+    kl = [l for l in lines if l[:2] in ("k ", "kn", "ke")]
+    lines = [l for l in lines if l not in kl]
     cl = [l for l in lines if l[:2] in ("co", "s ", "cn", "ce", "cs")]
     assert cl == [
         "count-sites 1 reads 6",
@@ -70,3 +72,12 @@ def test_mirror_reproduces_reference_unit_test(built):
         "c9 8 0[3M]2[8M]3[3M] 14 60 1 AAAGGGGGGGGAAA 1",
         "c10 5 0[6M]1[6M] 12 60 0 AAAAAATTTTTT 1",
         "cascade 10 7 9 3 1"]
+    # alignAndCount behind the cascade: expectations = the oracle's counting over the cascade of the two alignment
+    # oracles (c6 is dropped as non-unique; c5 supports node Q1 only, no labelled edge)
+    assert kl == [
+        "k c1 0[8M]1[8M]3[8M] n LF P1 RF q P", "k c2 0[8M]1[8M]3[8M] n LF P1 RF q P",
+        "k c3 0[8M]1[4M1X3M]3[8M] n LF P1 RF q P", "k c4 0[11M]3[8M] n LF RF q D", "k c5 2[8M] n Q1 q",
+        "k c7 0[4M]1[8M]3[4M] n LF P1 RF q P", "k c8 0[3M]2[8M]3[3M] n LF Q1 RF q Q",
+        "k c9 0[3M]2[8M]3[3M] n LF Q1 RF q Q", "k c10 0[6M]1[6M] n LF P1 q P",
+        "kn LF 8 8 6 2", "kn P1 5 5 4 1", "kn Q1 3 3 2 1", "kn RF 7 7 5 2",
+        "ke LF_P1 5", "ke LF_Q1 2", "ke LF_RF 1", "ke P1_RF 4", "ke Q1_RF 2"]
