@@ -301,6 +301,61 @@ int pgemu_path_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq
     return 0;
 }
 
+// Sizing of the device-side index build (pg_host.hpp count_kmer_paths) against an actual enumeration of the site's k-mer
+// paths with the device kernel's own depth-first walk restated on the host.  out3 = {n_paths by the DP, list bound by
+// the DP, n_paths enumerated}; returns the number of node-list entries the enumeration needs.
+long long pgemu_count_kmer_paths(int n_nodes, const char* seq_blob, const int32_t* seq_off, int n_edges,
+                                 const int32_t* efrom, const int32_t* eto, int kmer_len, long long* out3)
+{
+    host::GraphStore gs;
+    std::string err;
+    if (gs.add(n_nodes, seq_blob, seq_off, n_edges, efrom, eto, err) < 0)
+        return -4;
+    std::vector<std::vector<int32_t>> sv;
+    std::vector<int32_t> csr;
+    host::build_successors(gs, 0, sv, csr);
+    int64_t n_paths = 0, list_ints = 0;
+    host::count_kmer_paths(gs, 0, kmer_len, csr.data(), csr.data() + n_nodes + 1, n_paths, list_ints);
+    const int32_t* node_len = gs.ints.data() + gs.sites[0].tab_off[0] + n_nodes;
+    long long enumerated = 0, lists = 0;
+    std::vector<int> nodes((size_t)kmer_len + 2), endp((size_t)kmer_len + 3), ext((size_t)kmer_len + 3), nxt((size_t)kmer_len + 3);
+    for (int v0 = 0; v0 < n_nodes; ++v0)
+        for (int pos = 0; pos < node_len[v0]; ++pos)
+        {
+            int depth = 1;
+            nodes[0] = v0;
+            endp[1] = pos;
+            ext[1] = kmer_len - 1;
+            nxt[1] = 0;
+            while (depth > 0)
+            {
+                const int last = nodes[(size_t)depth - 1];
+                const int room = node_len[last] - endp[(size_t)depth] - 1;
+                if (ext[(size_t)depth] > room)
+                {
+                    if (nxt[(size_t)depth] >= (int)sv[(size_t)last].size())
+                    {
+                        --depth;
+                        continue;
+                    }
+                    nodes[(size_t)depth] = sv[(size_t)last][(size_t)nxt[(size_t)depth]++];
+                    endp[(size_t)depth + 1] = 0;
+                    ext[(size_t)depth + 1] = ext[(size_t)depth] - room - 1;
+                    nxt[(size_t)depth + 1] = 0;
+                    ++depth;
+                    continue;
+                }
+                ++enumerated;
+                lists += depth;
+                --depth;
+            }
+        }
+    out3[0] = n_paths;
+    out3[1] = list_ints;
+    out3[2] = enumerated;
+    return lists;
+}
+
 // Align + count ONE site on the host with the device code of pg_core.cuh / pg_count.cuh.
 // support: n_reads x 16 bytes (pg_read_support); path_words / ops_out: capacity `cap` words each (the op arena is
 // returned too so that a test can look at the CIGARs); node_counts[n_nodes], edge_counts[n_edges] (4 x u32 each);

@@ -91,3 +91,26 @@ def test_device_code_on_host_golden(built):
         got, cnt = emubind.emu_path_align_batch(case["nodes"], [tuple(e) for e in case["edges"]], case["reads"], case["k"])
         assert got == case["expected"], case["name"]
         assert list(cnt) == case["counters"]
+
+
+def test_device_index_sizing_covers_every_kmer_path(built):
+    """The device-side index build sizes its tables from a DP count of the k-mer paths (pg_host.hpp count_kmer_paths);
+    the count must equal a real enumeration (the kernel's depth-first walk, restated on the host) and the node-list bound
+    must cover what the enumeration needs."""
+    import ctypes as C
+    import emubind
+    lib = emubind.lib()
+    lib.pgemu_count_kmer_paths.restype = C.c_longlong
+    lib.pgemu_count_kmer_paths.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32),
+                                           C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_longlong)]
+    rng = np.random.default_rng(61)
+    for gi in range(300):
+        nodes, edges = synth.bubble_graph(rng, n_nodes=int(rng.integers(1, 12)), max_len=int(rng.choice([2, 6, 20, 80])),
+                                          p_edge=float(rng.choice([0.2, 0.5, 0.9])))
+        k = int(rng.choice([3, 8, 16, 32, 64]))
+        blob, off, ef, et = R.pack_graph(nodes, edges)
+        out = (C.c_longlong * 3)()
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+        lists = lib.pgemu_count_kmer_paths(len(nodes), blob, p(off), len(edges), p(ef), p(et), k, out)
+        assert out[0] == out[2], (nodes, edges, k)
+        assert 0 <= lists <= out[1], (nodes, edges, k)
