@@ -345,8 +345,10 @@ def main():
                              path_mapped=pst["mapped"], path_anchored=pst["anchored"], reads=READS_PER_SITE,
                              path_ms=round(pst["path_ms"], 4), fill_ms=round(cascade_kernels["fill_ms"], 4),
                              trace_ms=round(cascade_kernels["trace_ms"], 4)),
-            roofline=dict(bound="alu (packed-int16 DPX issue; neither hbm nor tensor applies, see DESIGN.md)",
-                          kernel="pg_fill_kernel<5>", achieved=round(ach_cells / 1e9, 1), peak=round(peak_cells / 1e9, 1),
+            roofline=dict(bound="alu",
+                          note="packed-int16 DPX issue rate of the ALU pipe: the max-plus recurrence is neither HBM-bound "
+                               "(roofline_hbm) nor a tensor-core contraction (SURVEY.md 8d, DESIGN.md 4)",
+                          kernel="pg_fill_kernel<5,32>", achieved=round(ach_cells / 1e9, 1), peak=round(peak_cells / 1e9, 1),
                           unit="Gcell/s", frac=round(ach_cells / peak_cells, 4) if peak_cells else None,
                           traffic=ncu_traffic(),
                           peak_source="tools/ubench/dpx_ubench.cu on this pool: 63.2 DPX lane-ops/clk/SM x 148 SM x "
