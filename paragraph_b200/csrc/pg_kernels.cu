@@ -1603,7 +1603,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     while (fill_warps > 1 && (size_t)fill_warps * NT * fill_words * 4 > 200 * 1024)
         fill_warps >>= 1;
     bool tab_global = false;
-    if ((size_t)fill_warps * NT * fill_words * 4 > 200 * 1024)
+    if ((size_t)fill_warps * NT * fill_words * 4 > 200 * 1024 || getenv("PG_FORCE_TABG"))
     {
         tab_global = true;
         code_bytes = 0; // the HBM-table variant reads the codes through L1
