@@ -349,6 +349,30 @@ template <int R, int W = 32> PG_HD void build_profile(uint32_t* prof, const uint
     }
 }
 
+// The same with the two packed halves taken from two different reads of one site: half x is the string
+// (orientation ox, half hx) of read x, or absent (bases_x == nullptr: all NEG).  Used by the paired reversed-graph
+// tasks, where each half is the one reversed-graph fill some read still needs (rev_plan).
+template <int R, int W = 32>
+PG_HD void build_profile_pair(uint32_t* prof, const uint8_t* bases0, int L0, int o0, int h0, const uint8_t* bases1, int L1,
+                              int o1, int h1, int lane)
+{
+    for (int r = 0; r < R; ++r)
+    {
+        const int j = R * lane + r;
+        int c0 = -1, c1 = -1;
+        if (bases0 && j < L0)
+            c0 = nt_code(read_char(bases0, L0, o0, h0, j));
+        if (bases1 && j < L1)
+            c1 = nt_code(read_char(bases1, L1, o1, h1, j));
+        for (int c = 0; c < NCODE; ++c)
+        {
+            const int s0 = (c0 < 0 || c == 5) ? NEG : sub_score(c, c0);
+            const int s1 = (c1 < 0 || c == 5) ? NEG : sub_score(c, c1);
+            prof[(c * R + r) * W + lane] = pk(s0, s1);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-lane bookkeeping around the step: which node the lane is in, node maxima, node boundaries
 // ---------------------------------------------------------------------------------------------
@@ -753,6 +777,56 @@ PG_HD Decision decide_strand(const TaskOut& fw, const TaskOut& rv, unsigned flag
     d.unique = ret_rev ? rev_unique : fwd_unique;
     d.score = fw.score[d.half];
     return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Which reversed-graph fills does a read really need?  (pairing of reversed-graph tasks, pg_kernels.cu)
+// ---------------------------------------------------------------------------------------------
+// GraphAligner::alignRead fills the reversed graph twice per read only to learn rfwd_multi / rrev_multi, and the
+// strand rule above often does not look at both: a strand the forward-graph fill already found non-unique stays
+// non-unique whatever its reversed-graph fill says, and once the better-scoring strand turns out unique the other
+// strand's uniqueness cannot change the answer.  rv_known[h] = -1 while the reversed-graph result of half h is unknown,
+// else its n_top.  rev_plan returns the half to fill next, or -1 when the decision is settled: the decision is
+// evaluated for every completion of the unknowns and settled iff they all agree.
+PG_HD Decision decide_with(const TaskOut& fw, int n0, int n1, unsigned flags)
+{
+    TaskOut rv;
+    rv.n_top[0] = n0;
+    rv.n_top[1] = n1;
+    return decide_strand(fw, rv, flags);
+}
+PG_HD int rev_plan(const TaskOut& fw, const int* rv_known, unsigned flags)
+{
+    if (!(flags & AF_REVERSE_GRAPH))
+        return -1;
+    const bool both = (flags & AF_BOTH_STRANDS) != 0;
+    // completions: unknown -> {1 (not multi), 2 (multi)}
+    bool first = true, settled = true;
+    Decision ref;
+    ref.half = ref.unique = ref.score = 0;
+    for (int c0 = 0; c0 < 2; ++c0)
+        for (int c1 = 0; c1 < 2; ++c1)
+        {
+            if ((rv_known[0] >= 0 && c0) || ((rv_known[1] >= 0 || !both) && c1))
+                continue;
+            const Decision d = decide_with(fw, rv_known[0] >= 0 ? rv_known[0] : 1 + c0,
+                                           rv_known[1] >= 0 ? rv_known[1] : 1 + c1, flags);
+            if (first)
+            {
+                ref = d;
+                first = false;
+            }
+            else if (d.half != ref.half || d.unique != ref.unique)
+                settled = false;
+        }
+    if (settled)
+        return -1;
+    // unknown halves that can still matter: the forward-graph fill did not already call that strand non-unique
+    const bool want0 = rv_known[0] < 0 && fw.n_top[0] <= 1;
+    const bool want1 = both && rv_known[1] < 0 && fw.n_top[1] <= 1;
+    if (want0 && want1) // the better-scoring strand first: if it is unique the other one is never needed
+        return fw.score[0] >= fw.score[1] ? 0 : 1;
+    return want0 ? 0 : (want1 ? 1 : -1);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -77,7 +77,16 @@ struct FillArgs
     // exact-match stage in front (pg_path.cuh): the reads still to align, compacted; null = all reads of the chunk
     const int32_t* todo;
     const int32_t* n_todo;
+    // task list of the kernel: MODE_BOTH = (read, orientation) pairs, 2 per read (what GraphAligner::alignRead does);
+    // MODE_FWD = the forward-graph task of every read; MODE_PAIRS = reversed-graph tasks whose two packed halves are the
+    // still-needed reversed-graph fills (rev_plan, pg_core.cuh) of two reads of one site: rtasks[i] = {read << 1 | half,
+    // read << 1 | half or -1}; their only result is n_top -> rv_ntop[read * 2 + half]
+    int mode;
+    const int2* rtasks;
+    const int32_t* n_rtasks;
+    int32_t* rv_ntop;
 };
+enum { MODE_BOTH = 0, MODE_FWD = 1, MODE_PAIRS = 2 };
 
 // ---- TMA (bulk async copy) staging of a task's column codes into shared memory ---------------------------------
 // Canonical mbarrier protocol (CUDA programming guide, "Using TMA to transfer one-dimensional arrays"), at group
@@ -203,27 +212,46 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     const int wpc = blockDim.x >> 5; // warps per CTA: 4, fewer when the seed tables of a many-node graph need the room
     const int ltask = (blockIdx.x * wpc + wic) * NT + grp;
     int n_tasks = a.n_tasks;
-    if (a.todo) // tasks = the reads the exact-match stage left over, in the order it listed them
-        n_tasks = min(n_tasks, 2 * max(*a.n_todo - a.read0, 0));
+    if (a.mode == MODE_PAIRS)
+        n_tasks = min(n_tasks, *a.n_rtasks);
+    else if (a.todo) // tasks = the reads the exact-match stage left over, in the order it listed them
+        n_tasks = min(n_tasks, (a.mode == MODE_FWD ? 1 : 2) * max(*a.n_todo - a.read0, 0));
     if ((blockIdx.x * wpc + wic) * NT >= n_tasks)
         return; // whole warp beyond the work list
-    const int o = ltask & 1;
-    const int rd = (ltask < n_tasks) ? (a.todo ? a.todo[a.read0 + (ltask >> 1)] : a.read0 + (ltask >> 1)) : 0;
+    // the task: orientation o; packed half x = string (o, hx) of read rdx (MODE_PAIRS: possibly two different reads)
+    const int tcl = ltask < n_tasks ? ltask : ltask - grp; // inactive tail groups shadow the warp's first task (they only idle along)
+    int o, rd, rd1, h0 = 0, h1 = 1, slot;
+    if (a.mode == MODE_PAIRS)
+    {
+        const int2 pr = a.rtasks[tcl];
+        o = 1;
+        rd = pr.x >> 1;
+        h0 = pr.x & 1;
+        rd1 = pr.y >= 0 ? (pr.y >> 1) : -1;
+        h1 = pr.y >= 0 ? (pr.y & 1) : 1;
+        slot = 0;
+    }
+    else
+    {
+        const int per = a.mode == MODE_FWD ? 1 : 2;
+        o = a.mode == MODE_FWD ? 0 : (tcl & 1);
+        slot = tcl / per; // index of the read within the chunk: its scratch slot
+        rd = a.todo ? a.todo[a.read0 + slot] : a.read0 + slot;
+        rd1 = rd;
+    }
     const bool active = ltask < n_tasks && !(o == 1 && !(a.flags & AF_REVERSE_GRAPH));
     uint32_t* prof = smem + ((size_t)wic * NT + grp) * a.smem_words_per_task;
     // [n_nodes_cap][2R][W] seeds, [n_nodes_cap][IW][W] node maxima: warp-private shared memory, or (fallback) HBM
     uint32_t* seedS = TABG ? a.tabG + (size_t)(ltask < n_tasks ? ltask : 0) * a.stride_tab : prof + NCODE * R * W;
     uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * W;
     TaskOut* to = a.tout + (size_t)rd * 2 + o;
-    if (!active && ltask < n_tasks && gl == 0)
+    if (a.mode == MODE_BOTH && !active && ltask < n_tasks && gl == 0)
     {
         TaskOut z;
         memset(&z, 0, sizeof z);
         *to = z;
     }
-    // inactive tail groups shadow the warp's first read (they only idle along)
-    const int rdc = ltask < n_tasks ? rd : (a.todo ? a.todo[a.read0 + ((ltask - grp) >> 1)] : a.read0 + ((ltask - grp) >> 1));
-    const SiteDev sd = a.sites[a.read_site ? a.read_site[rdc] : 0];
+    const SiteDev sd = a.sites[a.read_site ? a.read_site[rd] : 0];
     // STAGED: the orientation's node tables (lengths, predecessor lists) are copied next to the seed tables, so that
     // the node-boundary code of the hot loop reads shared memory with 32-bit addresses instead of chasing HBM pointers
     int32_t* tabS = reinterpret_cast<int32_t*>(infoS + a.n_nodes_cap * IW * W);
@@ -231,8 +259,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         for (int x = gl; x < sd.tab_ints; x += W)
             tabS[x] = a.gints[sd.tab_off[o] + x];
     const GraphView g = STAGED ? make_view_at(sd, a.gbytes + sd.codes_off[o], tabS) : make_view(sd, a.gbytes, a.gints, o);
-    const uint8_t* bases = a.bases + a.read_off[rdc];
-    const int L = a.read_off[rdc + 1] - a.read_off[rdc];
+    const uint8_t* bases = a.bases + a.read_off[rd];
+    const int L = a.read_off[rd + 1] - a.read_off[rd];
     // node sequences (column codes) of this task's orientation: TMA-staged into shared memory when they fit
     uint8_t* code_s = reinterpret_cast<uint8_t*>(prof + a.smem_words_per_task) - a.code_smem_bytes;
     uint64_t* bar = reinterpret_cast<uint64_t*>(code_s) - 1;
@@ -244,7 +272,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     if (staged)
         tma_stage_codes(code_s, g.codes - SENT, span, bar, gl == 0); // in flight while the profile is built
     if (active)
-        build_profile<R, W>(prof, bases, L, o, gl);
+        build_profile_pair<R, W>(prof, bases, L, o, h0, rd1 >= 0 ? a.bases + a.read_off[rd1] : nullptr,
+                                 rd1 >= 0 ? a.read_off[rd1 + 1] - a.read_off[rd1] : 0, o, h1, gl);
     else
         for (int x = gl; x < NCODE * R * W; x += W)
             prof[x] = pk(NEG, NEG);
@@ -261,8 +290,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     if (!active)
         c.colsLeft = COLS_INF;
     const bool save = active && (o == 0);
-    uint32_t* last = a.last + (size_t)(ltask >> 1) * a.stride_last;
-    uint32_t* ckpt = a.ckpt + (size_t)(ltask >> 1) * a.stride_ckpt;
+    uint32_t* last = a.last + (size_t)slot * a.stride_last;
+    uint32_t* ckpt = a.ckpt + (size_t)slot * a.stride_ckpt;
     const uint8_t* codes = (STAGED ? code_s + SENT : g.codes) - gl;
     const int my_nck = active ? num_ckpt(g.G, W) : 0;
     int nck = my_nck;
@@ -342,7 +371,14 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     {
         if (WIDE) // long reads: the serial statement, with the 16-bit-mode uniqueness rule (n_top_rule)
             finalize_task(infoS, g.n_nodes, t, W, IW);
-        *to = t;
+        if (a.mode == MODE_PAIRS) // all a reversed-graph fill is for: does the top score sit in more than one node?
+        {
+            a.rv_ntop[rd * 2 + h0] = t.n_top[0];
+            if (rd1 >= 0)
+                a.rv_ntop[rd1 * 2 + h1] = t.n_top[1];
+        }
+        else
+            *to = t;
     }
 }
 
@@ -369,6 +405,7 @@ struct TraceArgs
     const int32_t* todo; // see FillArgs
     const int32_t* n_todo;
     const uint8_t* prerev; // see PathArgs; null without the exact-match stage
+    const int32_t* rv_ntop; // MODE_PAIRS: n_top of the reversed-graph fills that were needed (-1 = not needed); else null
 };
 
 template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_kernel(const TraceArgs a)
@@ -401,7 +438,15 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
     const uint32_t* ckpt = a.ckpt + (size_t)lrd * a.stride_ckpt;
     build_profile<R, W>(prof, bases, L, 0, gl);
 
-    const TaskOut fw = a.tout[(size_t)rd * 2], rv = a.tout[(size_t)rd * 2 + 1];
+    const TaskOut fw = a.tout[(size_t)rd * 2];
+    TaskOut rv;
+    if (a.rv_ntop) // an unknown half is one the strand rule provably does not look at (rev_plan): any value will do
+    {
+        rv.n_top[0] = max(a.rv_ntop[rd * 2], 0);
+        rv.n_top[1] = max(a.rv_ntop[rd * 2 + 1], 0);
+    }
+    else
+        rv = a.tout[(size_t)rd * 2 + 1];
     const Decision d = decide_strand(fw, rv, a.flags);
     const int half = d.half;
 
@@ -498,6 +543,67 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
                 rec.status = 2;
         }
         a.records[rd] = rec;
+    }
+}
+
+// ---- which reversed-graph fills are needed, and pairing them ----------------------------------------------------
+// pg_plan_kernel: one thread per read of the chunk: rev_plan (pg_core.cuh) on the forward-graph result and on what is
+// known of the reversed-graph halves; a needed half is appended to the request list, warp-aggregated so that requests
+// stay in read order within a warp (neighbouring reads mostly share their site).
+// pg_pair_kernel: one thread per two consecutive requests: same site -> one task carrying both halves, else two tasks.
+struct PlanArgs
+{
+    const TaskOut* tout;
+    const int32_t* rv_ntop;
+    const int32_t* read_site;
+    const int32_t* todo;
+    const int32_t* n_todo;
+    int read0, n_reads;
+    unsigned flags;
+    int32_t* req;
+    int32_t* n_req;
+    int2* rtasks;
+    int32_t* n_rtasks;
+};
+__global__ void __launch_bounds__(128) pg_plan_kernel(const PlanArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n = a.n_reads;
+    if (a.todo)
+        n = min(n, max(*a.n_todo - a.read0, 0));
+    int want = -1, rd = 0;
+    if (i < n)
+    {
+        rd = a.todo ? a.todo[a.read0 + i] : a.read0 + i;
+        const int known[2] = { a.rv_ntop[rd * 2], a.rv_ntop[rd * 2 + 1] };
+        want = rev_plan(a.tout[(size_t)rd * 2], known, a.flags);
+    }
+    const unsigned m = __ballot_sync(FULL, want >= 0);
+    if (!m)
+        return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs((int)m) - 1)
+        base = atomicAdd(a.n_req, __popc(m));
+    base = __shfl_sync(FULL, base, __ffs((int)m) - 1);
+    if (want >= 0)
+        a.req[base + __popc(m & ((1u << lane) - 1u))] = rd * 2 + want;
+}
+__global__ void __launch_bounds__(128) pg_pair_kernel(const PlanArgs a)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = *a.n_req;
+    if (2 * i >= n)
+        return;
+    const int x = a.req[2 * i], y = 2 * i + 1 < n ? a.req[2 * i + 1] : -1;
+    const bool same = y >= 0 && (!a.read_site || a.read_site[x >> 1] == a.read_site[y >> 1]);
+    if (same || y < 0)
+        a.rtasks[atomicAdd(a.n_rtasks, 1)] = make_int2(x, y);
+    else
+    {
+        const int at = atomicAdd(a.n_rtasks, 2);
+        a.rtasks[at] = make_int2(x, -1);
+        a.rtasks[at + 1] = make_int2(y, -1);
     }
 }
 
@@ -1271,6 +1377,11 @@ struct pg_ctx
     PinBuf<unsigned long long> h_cursor;
     unsigned long long arena_cap = 0;
 
+    // pairing of the reversed-graph fills (rev_plan): on by default for the byte-packed geometries, PG_PAIR_REV=0 = off
+    bool pair_rev = true;
+    DevBuf<int32_t> d_rvntop, d_req, d_nreq; // d_nreq: [0] requests, [1] tasks
+    DevBuf<int2> d_rtasks;
+
     // exact-match stage (pg_path.cuh)
     int path_k = 0; // k-mer length; 0 = the stage is off
     bool gssw_on = true; // graphMatching of the cascade
@@ -1659,6 +1770,27 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         c->evpool.push_back(e);
     }
     c->n_chunks_timed = (int)n_chunks;
+    // Reversed-graph fills: only the halves the strand rule needs (rev_plan), two reads per task.  Not for the WIDE
+    // geometries (their region maxima depend on the one read length of a task) and not together with the overlap mode.
+    const bool pairs = c->pair_rev && !Sizes<R, W>::WIDE && !overlap && (flags & AF_REVERSE_GRAPH);
+    if (pairs)
+    {
+        PG_CUDA(c, c->d_rvntop.reserve((size_t)c->n_reads * 2));
+        PG_CUDA(c, c->d_req.reserve((size_t)c->n_reads));
+        PG_CUDA(c, c->d_rtasks.reserve((size_t)c->n_reads));
+        PG_CUDA(c, c->d_nreq.reserve(2));
+        PG_CUDA(c, cudaMemsetAsync(c->d_rvntop.p, 0xFF, (size_t)c->n_reads * 2 * sizeof(int32_t), c->stream)); // -1 = unknown
+    }
+    auto launch_fill = [&](const FillArgs& fa, int n_tasks) {
+        const int fgrid = (n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
+        if (tab_global)
+            pg_fill_kernel<R, W, false, true><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+        else if (code_bytes)
+            pg_fill_kernel<R, W, true, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+        else
+            pg_fill_kernel<R, W, false, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+        ++c->launches;
+    };
     size_t ci = 0;
     for (size_t r0 = 0; r0 < (size_t)c->n_reads; r0 += chunk, ++ci)
     {
@@ -1675,7 +1807,11 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.read_off = c->d_off.p;
         fa.read_site = c->have_sites ? c->d_site.p : nullptr;
         fa.read0 = (int)r0;
-        fa.n_tasks = 2 * nr;
+        fa.n_tasks = pairs ? nr : 2 * nr;
+        fa.mode = pairs ? MODE_FWD : MODE_BOTH;
+        fa.rtasks = nullptr;
+        fa.n_rtasks = nullptr;
+        fa.rv_ntop = nullptr;
         fa.flags = flags;
         fa.last = c->d_last.p + slot * chunk * s_last;
         fa.ckpt = c->d_ckpt.p + slot * chunk * s_ckpt;
@@ -1690,15 +1826,44 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.smem_words_per_task = fill_words;
         fa.todo = after_path ? c->d_todo.p : nullptr;
         fa.n_todo = after_path ? c->d_ntodo.p : nullptr;
-        const int fgrid = (fa.n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
-        if (tab_global)
-            pg_fill_kernel<R, W, false, true><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
-        else if (code_bytes)
-            pg_fill_kernel<R, W, true, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
-        else
-            pg_fill_kernel<R, W, false, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+        launch_fill(fa, fa.n_tasks);
         PG_CUDA(c, cudaGetLastError());
-        ++c->launches;
+        if (pairs)
+        {
+            // two rounds: the half rev_plan asks for first, then -- for the few reads it did not settle -- the other one
+            PlanArgs pa;
+            pa.tout = c->d_tout.p;
+            pa.rv_ntop = c->d_rvntop.p;
+            pa.read_site = fa.read_site;
+            pa.todo = fa.todo;
+            pa.n_todo = fa.n_todo;
+            pa.read0 = (int)r0;
+            pa.n_reads = nr;
+            pa.flags = flags;
+            pa.req = c->d_req.p;
+            pa.n_req = c->d_nreq.p;
+            pa.rtasks = c->d_rtasks.p;
+            pa.n_rtasks = c->d_nreq.p + 1;
+            FillArgs fr = fa;
+            fr.mode = MODE_PAIRS;
+            fr.rtasks = c->d_rtasks.p;
+            fr.n_rtasks = c->d_nreq.p + 1;
+            fr.rv_ntop = c->d_rvntop.p;
+            fr.todo = nullptr;
+            fr.n_todo = nullptr;
+            for (int round = 0; round < 2; ++round)
+            {
+                PG_CUDA(c, cudaMemsetAsync(c->d_nreq.p, 0, 2 * sizeof(int32_t), c->stream));
+                pg_plan_kernel<<<(nr + 127) / 128, 128, 0, c->stream>>>(pa);
+                pg_pair_kernel<<<((nr + 1) / 2 + 127) / 128, 128, 0, c->stream>>>(pa);
+                c->launches += 2;
+                // at most one task per request: the grid covers the worst case (round 0 needs about nr / 2 tasks, round 1
+                // next to none) and the CTAs beyond *n_rtasks leave at once
+                fr.n_tasks = nr;
+                launch_fill(fr, nr);
+                PG_CUDA(c, cudaGetLastError());
+            }
+        }
         PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 1], c->stream));
         cudaStream_t ts = overlap ? c->aux_stream : c->stream;
         if (overlap)
@@ -1729,6 +1894,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         ta.todo = fa.todo;
         ta.n_todo = fa.n_todo;
         ta.prerev = after_path ? c->d_prerev.p : nullptr;
+        ta.rv_ntop = pairs ? c->d_rvntop.p : nullptr;
         const int tgrid = (nr + TRACE_WARPS * NT - 1) / (TRACE_WARPS * NT);
         pg_trace_kernel<R, W><<<tgrid, TRACE_WARPS * 32, trace_smem, ts>>>(ta);
         PG_CUDA(c, cudaGetLastError());
@@ -1780,6 +1946,8 @@ int pg_create(int device, pg_ctx** out)
         c->split = std::max(1, atoi(e));
     if (const char* e = getenv("PG_NO_TMA"))
         c->use_tma = atoi(e) == 0;
+    if (const char* e = getenv("PG_PAIR_REV"))
+        c->pair_rev = atoi(e) != 0;
     if (const char* e = getenv("PG_PATH_HOST_INDEX"))
         c->path_host_index = atoi(e) != 0;
     if (const char* e = getenv("PG_PATH_SCALAR"))
@@ -1821,6 +1989,10 @@ void pg_destroy(pg_ctx* c)
     c->d_ntodo.release();
     c->d_pcount.release();
     c->d_prerev.release();
+    c->d_rvntop.release();
+    c->d_req.release();
+    c->d_nreq.release();
+    c->d_rtasks.release();
     c->d_pcolbase.release();
     c->d_plistcap.release();
     c->d_plistcur.release();

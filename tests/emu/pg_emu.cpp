@@ -15,6 +15,13 @@
 
 using namespace pg;
 
+static long g_rev_rounds = 0, g_rev_reads = 0; // reversed-graph halves rev_plan asked for / reads (see emu_align_one)
+extern "C" void pgemu_rev_stats(long* o)
+{
+    o[0] = g_rev_rounds;
+    o[1] = g_rev_reads;
+}
+
 namespace
 {
 
@@ -118,7 +125,23 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     emu_fill<R, W>(g0, bases, L, 0, true, info0, last, ckpt, fw);
     if (flags & AF_REVERSE_GRAPH)
         emu_fill<R, W>(g1, bases, L, 1, false, info1, dummy1, dummy2, rv);
-    const Decision d = decide_strand(fw, rv, flags);
+    Decision d = decide_strand(fw, rv, flags);
+    {
+        // the kernels fill only the reversed-graph halves rev_plan asks for (paired with other reads' halves): replay
+        // that here -- reveal half by half -- and demand the same decision as with both halves known
+        int known[2] = { -1, -1 }, rounds = 0;
+        for (int h = rev_plan(fw, known, flags); h >= 0; h = rev_plan(fw, known, flags))
+        {
+            known[h] = rv.n_top[h];
+            if (++rounds > 2)
+                return -2;
+        }
+        const Decision dl = decide_with(fw, known[0] >= 0 ? known[0] : 0, known[1] >= 0 ? known[1] : 0, flags);
+        if (dl.half != d.half || dl.unique != d.unique || dl.score != d.score)
+            return -2;
+        g_rev_rounds += rounds;
+        ++g_rev_reads;
+    }
     std::vector<uint32_t> prof((size_t)NCODE * R * W);
     for (int t = 0; t < W; ++t)
         build_profile<R, W>(prof.data(), bases, L, 0, t);
@@ -193,6 +216,7 @@ int pgemu_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off,
         if (L <= 0 || L > MAX_READ_LEN)
             return -3;
         Record rec;
+        memset(&rec, 0, sizeof rec);
         std::vector<uint32_t> ops;
         int nt = 0;
         const SiteDev& sd0 = gs.sites[0];
