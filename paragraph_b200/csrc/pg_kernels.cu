@@ -1344,9 +1344,9 @@ struct pg_ctx
     std::string err;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::vector<cudaEvent_t> evpool; // 4 events per chunk: before / after fill (main stream), before / after trace (aux stream)
-    cudaStream_t aux_stream = nullptr; // the traceback of chunk i runs here, next to the fill of chunk i+1
-    int split = 1;                     // chunks a batch is cut into for that overlap (PG_SPLIT; 1 = off, the default:
-                                       // measured slower on the B200)
+    cudaStream_t aux_stream = nullptr; // odd chunks of a split batch run here, next to the even ones on the caller's stream
+    int split = 2;                     // chunks a batch is cut into for that overlap (PG_SPLIT; 1 = off; 2 measured best
+                                       // on the B200)
     int n_chunks_timed = 0;
     uint64_t launches = 0;
     float fill_ms = 0, trace_ms = 0;
@@ -1771,33 +1771,40 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     }
     c->n_chunks_timed = (int)n_chunks;
     // Reversed-graph fills: only the halves the strand rule needs (rev_plan), two reads per task.  Not for the WIDE
-    // geometries (their region maxima depend on the one read length of a task) and not together with the overlap mode.
-    const bool pairs = c->pair_rev && !Sizes<R, W>::WIDE && !overlap && (flags & AF_REVERSE_GRAPH);
+    // geometries (their region maxima depend on the one read length of a task).
+    const bool pairs = c->pair_rev && !Sizes<R, W>::WIDE && (flags & AF_REVERSE_GRAPH);
     if (pairs)
     {
         PG_CUDA(c, c->d_rvntop.reserve((size_t)c->n_reads * 2));
-        PG_CUDA(c, c->d_req.reserve((size_t)c->n_reads));
-        PG_CUDA(c, c->d_rtasks.reserve((size_t)c->n_reads));
-        PG_CUDA(c, c->d_nreq.reserve(2));
+        PG_CUDA(c, c->d_req.reserve(2 * (size_t)c->n_reads));
+        PG_CUDA(c, c->d_rtasks.reserve(2 * (size_t)c->n_reads));
+        PG_CUDA(c, c->d_nreq.reserve(4));
         PG_CUDA(c, cudaMemsetAsync(c->d_rvntop.p, 0xFF, (size_t)c->n_reads * 2 * sizeof(int32_t), c->stream)); // -1 = unknown
     }
-    auto launch_fill = [&](const FillArgs& fa, int n_tasks) {
+    auto launch_fill = [&](const FillArgs& fa, int n_tasks, cudaStream_t st) {
         const int fgrid = (n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
         if (tab_global)
-            pg_fill_kernel<R, W, false, true><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+            pg_fill_kernel<R, W, false, true><<<fgrid, fill_warps * 32, fill_smem, st>>>(fa);
         else if (code_bytes)
-            pg_fill_kernel<R, W, true, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+            pg_fill_kernel<R, W, true, false><<<fgrid, fill_warps * 32, fill_smem, st>>>(fa);
         else
-            pg_fill_kernel<R, W, false, false><<<fgrid, fill_warps * 32, fill_smem, c->stream>>>(fa);
+            pg_fill_kernel<R, W, false, false><<<fgrid, fill_warps * 32, fill_smem, st>>>(fa);
         ++c->launches;
     };
+    // overlap mode: chunk ci runs its whole sequence (fill, plan / pair / paired fills, traceback) on stream ci & 1, so
+    // that the tail of one chunk's launches is filled by the other chunk's kernels; the auxiliary stream starts after
+    // everything already queued on the caller's stream
+    if (overlap)
+    {
+        PG_CUDA(c, cudaEventRecord(c->evpool[0], c->stream));
+        PG_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->evpool[0], 0));
+    }
     size_t ci = 0;
     for (size_t r0 = 0; r0 < (size_t)c->n_reads; r0 += chunk, ++ci)
     {
         const size_t slot = overlap ? (ci & 1) : 0;
-        if (overlap && ci >= 2) // the scratch slot is free once the traceback of chunk ci-2 is through
-            PG_CUDA(c, cudaStreamWaitEvent(c->stream, c->evpool[4 * (ci - 2) + 3], 0));
-        PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci], c->stream));
+        cudaStream_t cs = (overlap && (ci & 1)) ? c->aux_stream : c->stream; // chunk ci-2 used the same slot on the same stream
+        PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci], cs));
         const int nr = (int)std::min(chunk, (size_t)c->n_reads - r0);
         FillArgs fa;
         fa.sites = c->d_sites.p;
@@ -1826,7 +1833,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.smem_words_per_task = fill_words;
         fa.todo = after_path ? c->d_todo.p : nullptr;
         fa.n_todo = after_path ? c->d_ntodo.p : nullptr;
-        launch_fill(fa, fa.n_tasks);
+        launch_fill(fa, fa.n_tasks, cs);
         PG_CUDA(c, cudaGetLastError());
         if (pairs)
         {
@@ -1840,34 +1847,32 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
             pa.read0 = (int)r0;
             pa.n_reads = nr;
             pa.flags = flags;
-            pa.req = c->d_req.p;
-            pa.n_req = c->d_nreq.p;
-            pa.rtasks = c->d_rtasks.p;
-            pa.n_rtasks = c->d_nreq.p + 1;
+            pa.req = c->d_req.p + slot * (size_t)c->n_reads;
+            pa.n_req = c->d_nreq.p + 2 * slot;
+            pa.rtasks = c->d_rtasks.p + slot * (size_t)c->n_reads;
+            pa.n_rtasks = pa.n_req + 1;
             FillArgs fr = fa;
             fr.mode = MODE_PAIRS;
-            fr.rtasks = c->d_rtasks.p;
-            fr.n_rtasks = c->d_nreq.p + 1;
+            fr.rtasks = pa.rtasks;
+            fr.n_rtasks = pa.n_rtasks;
             fr.rv_ntop = c->d_rvntop.p;
             fr.todo = nullptr;
             fr.n_todo = nullptr;
             for (int round = 0; round < 2; ++round)
             {
-                PG_CUDA(c, cudaMemsetAsync(c->d_nreq.p, 0, 2 * sizeof(int32_t), c->stream));
-                pg_plan_kernel<<<(nr + 127) / 128, 128, 0, c->stream>>>(pa);
-                pg_pair_kernel<<<((nr + 1) / 2 + 127) / 128, 128, 0, c->stream>>>(pa);
+                PG_CUDA(c, cudaMemsetAsync(pa.n_req, 0, 2 * sizeof(int32_t), cs));
+                pg_plan_kernel<<<(nr + 127) / 128, 128, 0, cs>>>(pa);
+                pg_pair_kernel<<<((nr + 1) / 2 + 127) / 128, 128, 0, cs>>>(pa);
                 c->launches += 2;
                 // at most one task per request: the grid covers the worst case (round 0 needs about nr / 2 tasks, round 1
                 // next to none) and the CTAs beyond *n_rtasks leave at once
                 fr.n_tasks = nr;
-                launch_fill(fr, nr);
+                launch_fill(fr, nr, cs);
                 PG_CUDA(c, cudaGetLastError());
             }
         }
-        PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 1], c->stream));
-        cudaStream_t ts = overlap ? c->aux_stream : c->stream;
-        if (overlap)
-            PG_CUDA(c, cudaStreamWaitEvent(ts, c->evpool[4 * ci + 1], 0));
+        PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 1], cs));
+        cudaStream_t ts = cs;
         PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 2], ts));
 
         TraceArgs ta;
@@ -1901,7 +1906,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         ++c->launches;
         PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 3], ts));
     }
-    if (overlap) // everything later on the caller's stream (download, counting stage) sees the tracebacks finished
+    if (overlap) // everything later on the caller's stream (download, counting stage) sees both streams finished
         for (size_t k = n_chunks >= 2 ? n_chunks - 2 : 0; k < n_chunks; ++k)
             PG_CUDA(c, cudaStreamWaitEvent(c->stream, c->evpool[4 * k + 3], 0));
     return PG_OK;
