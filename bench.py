@@ -229,8 +229,29 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in ev]
     launches = ctx.stats()["kernel_launches"] - l0
     rec, ops = ctx.download()
-    st = ctx.stats()  # per-kernel event times of the last run are resolved by download()
     total_ms = float(sum(step_ms))
+    # per-kernel times for the roofline: the default run cuts the batch in two chunk pipelines on two streams whose
+    # kernels overlap, so its per-launch event times are stretched; a context with PG_SPLIT=1 runs the same kernels one
+    # after the other on the launching stream -- fill phase (forward fill, plan / pair, paired reversed-graph fills) and
+    # traceback timed with the library's CUDA events around them, mean of 5 runs after 3 warm-ups
+    os.environ["PG_SPLIT"] = "1"
+    ctx1 = capi.Context(local_rank)
+    os.environ.pop("PG_SPLIT")
+    ctx1.set_stream(stream.cuda_stream)
+    ctx1.add_graph(nodes, edges)
+    ctx1.upload(blob, off)
+    for _ in range(3):
+        ctx1.run()
+    fills, traces = [], []
+    for _ in range(5):
+        flush.fill_(1)
+        ctx1.run()
+        ctx1.download()
+        s1 = ctx1.stats()
+        fills.append(s1["fill_ms"])
+        traces.append(s1["trace_ms"])
+    st = dict(fill_ms=float(np.mean(fills)), trace_ms=float(np.mean(traces)))
+    ctx1.close()
     # ---------------- e2e: host buffers in, host buffers out, through pg_align_batch
     for _ in range(2):
         ctx.align_packed(blob, off)
@@ -330,7 +351,9 @@ def main():
             e2e=dict(value=round(e2e_value, 1), unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
             gpu_launches=int(launches),
             kernels=dict(fill_ms=round(st["fill_ms"], 4), trace_ms=round(st["trace_ms"], 4),
-                         count_ms=round(cst["count_ms"], 4)),
+                         count_ms=round(cst["count_ms"], 4),
+                         note="fill / trace: run back to back on one stream (PG_SPLIT=1); the timed steps overlap two "
+                              "half-batch pipelines on two streams, which is why ms_per_step is below their sum"),
             e2e_counts=dict(value=round(n_reads_all * args.steps / (cnt_ms * 1e-3), 1), unit="reads/s",
                             what="host reads -> filters + disambiguation + node/edge/path-family fragment counts on "
                                  "the device (pg_batch_count); only the count tables are copied back",
@@ -348,7 +371,7 @@ def main():
             roofline=dict(bound="alu",
                           note="packed-int16 DPX issue rate of the ALU pipe: the max-plus recurrence is neither HBM-bound "
                                "(roofline_hbm) nor a tensor-core contraction (SURVEY.md 8d, DESIGN.md 4)",
-                          kernel="pg_fill_kernel<5,32>", achieved=round(ach_cells / 1e9, 1), peak=round(peak_cells / 1e9, 1),
+                          kernel="pg_fill_kernel<5,32> (fill phase of a step: forward-graph launch + paired reversed-graph launches)", achieved=round(ach_cells / 1e9, 1), peak=round(peak_cells / 1e9, 1),
                           unit="Gcell/s", frac=round(ach_cells / peak_cells, 4) if peak_cells else None,
                           traffic=ncu_traffic(),
                           peak_source="tools/ubench/dpx_ubench.cu on this pool: 63.2 DPX lane-ops/clk/SM x 148 SM x "
