@@ -325,6 +325,48 @@ int pgemu_path_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq
     return 0;
 }
 
+// rev_plan (pg_core.cuh) exhaustively: for every combination of forward-graph results (n_top 0..2 per half, score order),
+// reversed-graph results and flags, revealing only the halves the plan asks for must give the decision of the full
+// evaluation, in at most two rounds.  Returns the number of disagreements; *cases = combinations tried, *halves =
+// reversed-graph halves asked for in total.
+int pgemu_rev_plan_check(long* cases, long* halves)
+{
+    int bad = 0;
+    *cases = *halves = 0;
+    const unsigned flag_sets[] = { 0xFFFFFFFFu, 1u, 3u, 5u, 7u, 4u, 6u, 2u, 0u };
+    for (unsigned flags : flag_sets)
+        for (int f0 = 0; f0 <= 2; ++f0)
+            for (int f1 = 0; f1 <= 2; ++f1)
+                for (int sc = 0; sc < 3; ++sc) // S0 < S1, S0 == S1, S0 > S1
+                    for (int r0 = 0; r0 <= 2; ++r0)
+                        for (int r1 = 0; r1 <= 2; ++r1)
+                        {
+                            TaskOut fw, rv;
+                            memset(&fw, 0, sizeof fw);
+                            memset(&rv, 0, sizeof rv);
+                            fw.n_top[0] = f0;
+                            fw.n_top[1] = f1;
+                            fw.score[0] = 10 + (sc == 2);
+                            fw.score[1] = 10 + (sc == 0);
+                            rv.n_top[0] = r0;
+                            rv.n_top[1] = r1;
+                            if (!(flags & AF_REVERSE_GRAPH)) // the kernels do not fill the reversed graph at all then
+                                rv.n_top[0] = rv.n_top[1] = 0;
+                            const Decision full = decide_strand(fw, rv, flags);
+                            int known[2] = { -1, -1 }, rounds = 0;
+                            for (int h = rev_plan(fw, known, flags); h >= 0 && rounds < 3; h = rev_plan(fw, known, flags))
+                            {
+                                known[h] = rv.n_top[h];
+                                ++rounds;
+                            }
+                            const Decision lazy = decide_with(fw, known[0] >= 0 ? known[0] : 0, known[1] >= 0 ? known[1] : 0, flags);
+                            bad += rounds > 2 || lazy.half != full.half || lazy.unique != full.unique || lazy.score != full.score;
+                            ++*cases;
+                            *halves += rounds;
+                        }
+    return bad;
+}
+
 // Sizing of the device-side index build (pg_host.hpp count_kmer_paths) against an actual enumeration of the site's k-mer
 // paths with the device kernel's own depth-first walk restated on the host.  out3 = {n_paths by the DP, list bound by
 // the DP, n_paths enumerated}; returns the number of node-list entries the enumeration needs.

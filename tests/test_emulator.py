@@ -98,3 +98,15 @@ def test_emulator_16bit_uniqueness_rule(built):
         assert strip_status(got) == exp
         seen |= {(min(max(e["score"], 250), 256), e["unique"]) for e in exp}
     assert (256, True) in seen and (250, False) in seen and any(250 < s < 256 for s, _ in seen)
+
+
+def test_rev_plan_exhaustive(built):
+    """The kernels fill only the reversed-graph halves rev_plan (pg_core.cuh) asks for.  Every combination of forward /
+    reversed results, score order and flags: the lazily evaluated strand decision equals the full one, within two
+    rounds, and the plan saves work (fewer than two halves per case on average)."""
+    import ctypes as C
+    lib = emubind.lib()
+    lib.pgemu_rev_plan_check.restype = C.c_int
+    cases, halves = C.c_long(0), C.c_long(0)
+    assert lib.pgemu_rev_plan_check(C.byref(cases), C.byref(halves)) == 0
+    assert cases.value == 9 * 3 * 3 * 3 * 3 * 3 and halves.value < cases.value
