@@ -210,13 +210,17 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / W, gl = lane % W;
     const int wpc = blockDim.x >> 5; // warps per CTA: 4, fewer when the seed tables of a many-node graph need the room
-    const int ltask = (blockIdx.x * wpc + wic) * NT + grp;
     int n_tasks = a.n_tasks;
     if (a.mode == MODE_PAIRS)
         n_tasks = min(n_tasks, *a.n_rtasks);
     else if (a.todo) // tasks = the reads the exact-match stage left over, in the order it listed them
         n_tasks = min(n_tasks, (a.mode == MODE_FWD ? 1 : 2) * max(*a.n_todo - a.read0, 0));
-    if ((blockIdx.x * wpc + wic) * NT >= n_tasks)
+    // One task per group of W lanes.  A grid smaller than the task list (the second round of paired reversed-graph
+    // fills: mostly empty, launched with a few CTAs in the non-staged instantiation) strides over it.
+    for (int wbase = (blockIdx.x * wpc + wic) * NT;; wbase += gridDim.x * wpc * NT)
+    {
+    const int ltask = wbase + grp;
+    if (wbase >= n_tasks)
         return; // whole warp beyond the work list
     // the task: orientation o; packed half x = string (o, hx) of read rdx (MODE_PAIRS: possibly two different reads)
     const int tcl = ltask < n_tasks ? ltask : ltask - grp; // inactive tail groups shadow the warp's first task (they only idle along)
@@ -379,6 +383,10 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         }
         else
             *to = t;
+    }
+    if (STAGED || a.mode != MODE_PAIRS) // (the staged instantiation's mbarrier is single-use: full grids only)
+        return;
+    __syncwarp();
     }
 }
 
@@ -1781,8 +1789,15 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         PG_CUDA(c, c->d_nreq.reserve(4));
         PG_CUDA(c, cudaMemsetAsync(c->d_rvntop.p, 0xFF, (size_t)c->n_reads * 2 * sizeof(int32_t), c->stream)); // -1 = unknown
     }
-    auto launch_fill = [&](const FillArgs& fa, int n_tasks, cudaStream_t st) {
-        const int fgrid = (n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
+    auto launch_fill = [&](const FillArgs& fa, int n_tasks, cudaStream_t st, bool strided = false) {
+        int fgrid = (n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
+        if (strided && !tab_global) // few tasks expected: a small grid of the non-staged instantiation strides over them
+        {
+            fgrid = std::min(fgrid, 2 * 148);
+            pg_fill_kernel<R, W, false, false><<<fgrid, fill_warps * 32, fill_smem, st>>>(fa);
+            ++c->launches;
+            return;
+        }
         if (tab_global)
             pg_fill_kernel<R, W, false, true><<<fgrid, fill_warps * 32, fill_smem, st>>>(fa);
         else if (code_bytes)
@@ -1867,7 +1882,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
                 // at most one task per request: the grid covers the worst case (round 0 needs about nr / 2 tasks, round 1
                 // next to none) and the CTAs beyond *n_rtasks leave at once
                 fr.n_tasks = nr;
-                launch_fill(fr, nr, cs);
+                launch_fill(fr, nr, cs, round == 1);
                 PG_CUDA(c, cudaGetLastError());
             }
         }
