@@ -85,6 +85,7 @@ struct FillArgs
     const int2* rtasks;
     const int32_t* n_rtasks;
     int32_t* rv_ntop;
+    int strided; // the grid is smaller than the task list: every warp strides over it (persistent CTAs)
 };
 enum { MODE_BOTH = 0, MODE_FWD = 1, MODE_PAIRS = 2 };
 
@@ -92,7 +93,7 @@ enum { MODE_BOTH = 0, MODE_FWD = 1, MODE_PAIRS = 2 };
 // Canonical mbarrier protocol (CUDA programming guide, "Using TMA to transfer one-dimensional arrays"), at group
 // scope: the elected lane initialises the barrier for `nlanes` arrivals and fences the init towards the async
 // proxy; after a __syncwarp it posts the expected byte count (its own arrival) and issues cp.async.bulk
-// (SASS: UBLKCP.S.G); the other lanes arrive; everybody waits for phase 0.  Source and size are 16-byte aligned by
+// (SASS: UBLKCP.S.G); the other lanes arrive; everybody waits for the phase (a persistent warp re-uses its barrier: the phase parity alternates per task).  Source and size are 16-byte aligned by
 // construction (pg_host.hpp).
 __device__ __forceinline__ void tma_barrier_init(uint64_t* bar, int nlanes, bool elected)
 {
@@ -118,14 +119,14 @@ __device__ __forceinline__ void tma_stage_codes(void* dst_smem, const void* src_
     else
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
 }
-__device__ __forceinline__ void tma_wait(uint64_t* bar)
+__device__ __forceinline__ void tma_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(bar);
     uint32_t done = 0;
     while (!done)
-        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
                      : "=r"(done)
-                     : "r"(bar_s)
+                     : "r"(bar_s), "r"(parity)
                      : "memory");
 }
 
@@ -215,8 +216,9 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         n_tasks = min(n_tasks, *a.n_rtasks);
     else if (a.todo) // tasks = the reads the exact-match stage left over, in the order it listed them
         n_tasks = min(n_tasks, (a.mode == MODE_FWD ? 1 : 2) * max(*a.n_todo - a.read0, 0));
-    // One task per group of W lanes.  A grid smaller than the task list (the second round of paired reversed-graph
-    // fills: mostly empty, launched with a few CTAs in the non-staged instantiation) strides over it.
+    // One task per group of W lanes.  A grid smaller than the task list (a.strided: persistent CTAs, every warp on its
+    // own -- no warp waits for the slowest of its CTA before the next task starts) strides over it.
+    uint32_t tma_phase = 0;
     for (int wbase = (blockIdx.x * wpc + wic) * NT;; wbase += gridDim.x * wpc * NT)
     {
     const int ltask = wbase + grp;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     uint64_t* bar = reinterpret_cast<uint64_t*>(code_s) - 1;
     const uint32_t span = (uint32_t)code_span_bytes(g.G);
     const bool staged = STAGED && active; // the host only picks STAGED when every graph of the batch fits
-    if (staged)
+    if (staged && wbase < (int)gridDim.x * wpc * NT) // first task of this warp
         tma_barrier_init(bar, W, gl == 0);
     __syncwarp();
     if (staged)
@@ -283,7 +285,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
             prof[x] = pk(NEG, NEG);
     __syncwarp();
     if (staged)
-        tma_wait(bar);
+        tma_wait(bar, tma_phase);
+    tma_phase ^= 1u;
 
     Lane<R> s;
     lane_zero(s);
@@ -384,9 +387,11 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         else
             *to = t;
     }
-    if (STAGED || a.mode != MODE_PAIRS) // (the staged instantiation's mbarrier is single-use: full grids only)
+    if (!a.strided)
         return;
-    __syncwarp();
+    __syncwarp(); // the next task overwrites this one's profile, tables and staged codes
+    if (STAGED)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
 }
 
@@ -1387,6 +1392,9 @@ struct pg_ctx
 
     // pairing of the reversed-graph fills (rev_plan): on by default for the byte-packed geometries, PG_PAIR_REV=0 = off
     bool pair_rev = true;
+    int persist = 0; // PG_PERSIST: 1 = the paired reversed-graph launches, 2 = every fill launch runs as one wave of
+                     // persistent CTAs striding over the task list
+    int n_sms = 148;
     DevBuf<int32_t> d_rvntop, d_req, d_nreq; // d_nreq: [0] requests, [1] tasks
     DevBuf<int2> d_rtasks;
 
@@ -1789,14 +1797,32 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         PG_CUDA(c, c->d_nreq.reserve(4));
         PG_CUDA(c, cudaMemsetAsync(c->d_rvntop.p, 0xFF, (size_t)c->n_reads * 2 * sizeof(int32_t), c->stream)); // -1 = unknown
     }
-    auto launch_fill = [&](const FillArgs& fa, int n_tasks, cudaStream_t st, bool strided = false) {
+    // grid of one wave of resident CTAs (persistent launch), 0 = not wanted
+    int wave = 0;
+    if (c->persist > 0 && !tab_global)
+    {
+        int occ = 0;
+        if (code_bytes)
+            PG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pg_fill_kernel<R, W, true, false>, fill_warps * 32, fill_smem));
+        else
+            PG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pg_fill_kernel<R, W, false, false>, fill_warps * 32, fill_smem));
+        wave = occ * c->n_sms;
+    }
+    auto launch_fill = [&](FillArgs fa, int n_tasks, cudaStream_t st, bool few = false) {
         int fgrid = (n_tasks + fill_warps * NT - 1) / (fill_warps * NT);
-        if (strided && !tab_global) // few tasks expected: a small grid of the non-staged instantiation strides over them
+        fa.strided = 0;
+        if (few && !tab_global) // next to no tasks expected: a small grid of the non-staged instantiation strides over them
         {
-            fgrid = std::min(fgrid, 2 * 148);
+            fa.strided = 1;
+            fgrid = std::min(fgrid, 2 * c->n_sms);
             pg_fill_kernel<R, W, false, false><<<fgrid, fill_warps * 32, fill_smem, st>>>(fa);
             ++c->launches;
             return;
+        }
+        if (wave > 0 && fgrid > wave && (c->persist >= 2 || fa.mode == MODE_PAIRS))
+        {
+            fa.strided = 1;
+            fgrid = wave;
         }
         if (tab_global)
             pg_fill_kernel<R, W, false, true><<<fgrid, fill_warps * 32, fill_smem, st>>>(fa);
@@ -1968,6 +1994,9 @@ int pg_create(int device, pg_ctx** out)
         c->use_tma = atoi(e) == 0;
     if (const char* e = getenv("PG_PAIR_REV"))
         c->pair_rev = atoi(e) != 0;
+    if (const char* e = getenv("PG_PERSIST"))
+        c->persist = atoi(e);
+    cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device);
     if (const char* e = getenv("PG_PATH_HOST_INDEX"))
         c->path_host_index = atoi(e) != 0;
     if (const char* e = getenv("PG_PATH_SCALAR"))
