@@ -28,7 +28,30 @@ def test_mirror_reproduces_reference_unit_test(built):
     _compile()
     out = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
-    lines = out.stdout.strip().split("\n")
+    _check_output(out.stdout)
+
+
+def test_mirror_host_logic_over_the_emulated_abi(tmp_path):
+    """The same program and the same expectations without a GPU: the mirror is compiled against tests/emu/pg_abi_shim.cpp
+    (the lane emulator behind the C-ABI's signatures, entry points renamed pgshim_*), which checks the mirror's host
+    logic -- packing, record application, strand / quals handling, MAPPED-only semantics, filters, the cascade with its
+    second chance, MultiSiteAligner, alignAndCount -- in the CPU suite.  The GPU test above runs it over the real library."""
+    shim = os.path.join(str(tmp_path), "libpgshim.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", shim,
+                           os.path.join(ROOT, "tests", "emu", "pg_abi_shim.cpp")])
+    exe = os.path.join(str(tmp_path), "test_grm_shim")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-include", os.path.join(ROOT, "tests", "emu", "pg_shim_names.h"),
+                           "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_grm_mirror.cpp"), "-L" + str(tmp_path),
+                           "-lpgshim", "-Wl,-rpath," + str(tmp_path)])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    syms = subprocess.run(["nm", "-D", "--defined-only", shim], capture_output=True, text=True).stdout
+    assert " pgshim_align_batch" in syms and " pg_align_batch" not in syms  # cannot stand in for libpgalign.so
+    _check_output(out.stdout)
+
+
+def _check_output(stdout):
+    lines = stdout.strip().split("\n")
     assert lines[:7] == [
         "f1 3 0[8M]1[4M1X3M]3[8M] 19 60 0 AAAAAAAATTTTCTTTAAAAAAAA 1",
         "f2 4 0[7M]1[4M1X3M]3[6M] 16 60 1 AAAAAAATTTTCTTTAAAAAA 1",
