@@ -13,19 +13,24 @@
 //
 // The GPU engine is batch-first: alignReads() makes ONE pg_align_batch call for the whole read vector
 // (results are written back in input order, so the outcome is deterministic for any `threads`); the per-read
-// alignRead() facades are batches of one.  Only the gssw stage (graph_sequence_matching) runs on the GPU;
-// the path stage (grm::PathAligner) and the gssw stage run on the GPU; asking for the kmer / klib stages throws
-// (SURVEY.md 8f "next" rows, not silently skipped).
+// alignRead() facades are batches of one.  The path stage (grm::PathAligner) and the gssw stage run on the GPU; asking
+// for the kmer / klib stages throws (SURVEY.md 8f "next" rows, not silently skipped).  `threads` host threads gather
+// the batch into page-locked staging and write the records back into the reads.
 #pragma once
 #include <algorithm>
+#include <climits>
 #include <cstdint>
+#include <cstring>
+#include <exception>
 #include <functional>
 #include <list>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -177,6 +182,77 @@ struct CountOptions // paragraph::Parameters defaults (include/paragraph/Paramet
 namespace grm
 {
 
+namespace detail
+{
+// fn(begin, end) over [0, n) on up to `threads` host threads (the `threads` argument of grm::alignReads, Align.cpp:119:
+// the reference spends it on aligning, here it packs the batch and writes the results back -- at 5 M reads/s on the
+// device the ~0.7 us a single thread needs per read for that is what a caller would otherwise wait for).  Every index
+// belongs to exactly one thread, so the outcome does not depend on `threads`; the first exception is rethrown.
+template <typename F> void parallelFor(size_t n, unsigned threads, F&& fn)
+{
+    const size_t min_chunk = 1024;
+    const size_t nt = std::min<size_t>(threads ? threads : 1, (n + min_chunk - 1) / min_chunk);
+    if (nt <= 1)
+    {
+        fn((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    std::exception_ptr err;
+    std::mutex m;
+    for (size_t t = 0; t < nt; ++t)
+        pool.emplace_back([&, t] {
+            try
+            {
+                fn(n * t / nt, n * (t + 1) / nt);
+            }
+            catch (...)
+            {
+                std::lock_guard<std::mutex> lock(m);
+                if (!err)
+                    err = std::current_exception();
+            }
+        });
+    for (auto& th : pool)
+        th.join();
+    if (err)
+        std::rethrow_exception(err);
+}
+
+// page-locked staging (pg_host_alloc), grown geometrically and reused between batches: the library copies such
+// buffers to and from the device directly instead of staging pageable memory once more
+template <typename T> class PinnedBuf
+{
+public:
+    PinnedBuf() = default;
+    ~PinnedBuf() { pg_host_free(p_); }
+    PinnedBuf(PinnedBuf const&) = delete;
+    PinnedBuf& operator=(PinnedBuf const&) = delete;
+    T* reserve(size_t n) // contents are not kept
+    {
+        if (n > cap_)
+        {
+            const size_t want = std::max(n, cap_ * 2);
+            pg_host_free(p_);
+            p_ = nullptr;
+            cap_ = 0;
+            void* q = nullptr;
+            if (pg_host_alloc((uint64_t)(want * sizeof(T)), &q) != PG_OK || !q)
+                throw std::runtime_error("paragraph_b200: cannot allocate " + std::to_string(want * sizeof(T)) + " bytes of page-locked memory");
+            p_ = static_cast<T*>(q);
+            cap_ = want;
+        }
+        return p_;
+    }
+    T* data() const { return p_; }
+    size_t capacity() const { return cap_; }
+
+private:
+    T* p_ = nullptr;
+    size_t cap_ = 0;
+};
+} // namespace detail
+
 // RAII around pg_ctx; errors become std::runtime_error like the reference's error() (common/Error.hh:55-167)
 class Engine
 {
@@ -196,6 +272,33 @@ public:
             throw std::runtime_error(std::string("paragraph_b200: ") + pg_last_error(ctx_));
     }
 
+    // staging of the current batch (one batch at a time per engine, like one aligner per thread in the reference)
+    detail::PinnedBuf<char> blob;
+    detail::PinnedBuf<int32_t> off;
+    detail::PinnedBuf<pg_record> rec;
+    detail::PinnedBuf<uint32_t> ops;
+
+    // gather the bases of which[0..n) into blob / off (sizes serially, bytes on `threads` threads); returns the bytes
+    template <typename GetBases> size_t pack(size_t n, unsigned threads, GetBases&& bases_of)
+    {
+        int32_t* o = off.reserve(n + 1);
+        size_t total = 0;
+        o[0] = 0;
+        for (size_t i = 0; i < n; ++i)
+        {
+            total += bases_of(i).size();
+            if (total > (size_t)INT_MAX)
+                throw std::runtime_error("paragraph_b200: more than 2 GB of read bases in one batch");
+            o[i + 1] = (int32_t)total;
+        }
+        char* b = blob.reserve(total + 1);
+        detail::parallelFor(n, threads, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i)
+                std::memcpy(b + o[i], bases_of(i).data(), (size_t)(o[i + 1] - o[i]));
+        });
+        return total;
+    }
+
 private:
     pg_ctx* ctx_ = nullptr;
 };
@@ -207,6 +310,18 @@ inline std::string reverseComplement(std::string s)
         c = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
     std::reverse(s.begin(), s.end());
     return s;
+}
+
+// the same into a caller-owned string (applyRecord keeps one per thread: no allocation per read)
+inline void reverseComplementInto(std::string const& in, std::string& out)
+{
+    const size_t n = in.size();
+    out.resize(n);
+    for (size_t i = 0; i < n; ++i) // (a select chain: the compiler vectorises it, unlike a table lookup)
+    {
+        const char c = in[n - 1 - i];
+        out[i] = c == 'A' ? 'T' : c == 'C' ? 'G' : c == 'G' ? 'C' : c == 'T' ? 'A' : 'N';
+    }
 }
 
 class GraphAligner
@@ -246,61 +361,68 @@ public:
     void alignBatch(ReadIt begin, ReadIt end, unsigned flags = AF_ALL, std::vector<pg_record>* records_out = nullptr,
                     bool tolerate_unmapped = false) const
     {
-        std::string blob;
-        std::vector<int32_t> off{ 0 };
         std::vector<ReadIt> which;
         for (ReadIt it = begin; it != end; ++it)
-        {
-            if ((*it)->bases().empty())
-                continue;
-            blob += (*it)->bases();
-            off.push_back((int32_t)blob.size());
-            which.push_back(it);
-        }
+            if (!(*it)->bases().empty())
+                which.push_back(it);
         if (which.empty())
             return;
-        std::vector<pg_record> rec(which.size());
-        std::vector<uint32_t> ops(blob.size() + 16 * which.size() + 64);
+        Engine& e = *engine_;
+        const size_t n = which.size();
+        const size_t bytes = e.pack(n, threads_, [&](size_t i) -> std::string const& { return (*which[i])->bases(); });
+        pg_record* rec = e.rec.reserve(n);
+        const size_t ops_cap = bytes + 16 * n + 64;
+        uint32_t* ops = e.ops.reserve(ops_cap);
         uint64_t used = 0;
-        engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), blob.data(), off.data(), nullptr, flags,
-                                      rec.data(), ops.data(), ops.size(), &used));
+        e.check(pg_align_batch(e.get(), (int32_t)n, e.blob.data(), e.off.data(), nullptr, flags, rec, ops, ops_cap, &used));
         if (records_out) // e.g. for paragraph::DefaultReadFilter, which needs query_clipped
-            *records_out = rec;
-        for (size_t i = 0; i < which.size(); ++i)
-            if (!(tolerate_unmapped && rec[i].status == 3)) // 3: no enabled stage mapped the read -- it stays UNMAPPED
-                applyRecord(**which[i], rec[i], ops.data(), flags, i);
+            records_out->assign(rec, rec + n);
+        detail::parallelFor(n, threads_, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i)
+                if (!(tolerate_unmapped && rec[i].status == 3)) // 3: no enabled stage mapped the read -- it stays UNMAPPED
+                    applyRecord(**which[i], rec[i], ops, flags, i);
+        });
     }
+
+    // host threads for packing a batch and writing its results back (the `threads` of grm::alignReads); results are the
+    // same for any value
+    void setThreads(unsigned threads) { threads_ = threads ? threads : 1; }
 
     // write one record back into a read: the fields GraphAligner::alignRead sets (GraphAligner.cpp:358-401)
     template <typename ReadT>
     static void applyRecord(ReadT& read, pg_record const& r, const uint32_t* ops, unsigned flags, size_t index)
     {
+        static thread_local std::string tmp; // scratch for the rewritten bases / quals / CIGAR string
         if (r.status != 0)
             throw std::runtime_error("paragraph_b200: traceback failed for read " + std::to_string(index));
         if (r.mapped_by == PG_STAGE_PATH_ID) // what PathAligner::alignRead writes (PathAligner.cpp:124-161)
         {
             read.set_is_graph_reverse_strand(r.chose_reverse != 0);
-            if (r.chose_reverse)
-                read.set_bases(reverseComplement(read.bases())); // quals stay as they are
+            if (r.chose_reverse) // quals stay as they are
+            {
+                reverseComplementInto(read.bases(), tmp);
+                read.set_bases(tmp);
+            }
             read.set_graph_alignment_score(r.score);
             read.set_graph_pos(r.graph_pos);
-            std::string buf((size_t)12 * (r.cigar_len + 2), '\0');
-            const int n = pg_format_cigar(&r, ops, &buf[0], (int)buf.size());
-            buf.resize((size_t)std::min<int>(n, (int)buf.size() - 1));
-            read.set_graph_cigar(buf);
+            formatCigar(r, ops, tmp);
+            read.set_graph_cigar(tmp);
             read.set_is_graph_alignment_unique(r.unique != 0);
             read.set_graph_mapq(r.unique ? 60 : 0);
             return;
         }
         if (r.mapped_by == PG_STAGE_GSSW_REV_ID) // the exact-match stage had reverse-complemented the bases first
-            read.set_bases(reverseComplement(read.bases()));
+        {
+            reverseComplementInto(read.bases(), tmp);
+            read.set_bases(tmp);
+        }
         read.set_is_graph_reverse_strand(read.is_reverse_strand() != (r.chose_reverse != 0)); // :358-359
         if (r.chose_reverse) // :375-378
         {
-            read.set_bases(reverseComplement(read.bases()));
-            std::string q = read.quals();
-            std::reverse(q.begin(), q.end());
-            read.set_quals(q);
+            reverseComplementInto(read.bases(), tmp);
+            read.set_bases(tmp);
+            tmp.assign(read.quals().rbegin(), read.quals().rend());
+            read.set_quals(tmp);
         }
         read.set_graph_pos(r.graph_pos);
         read.set_graph_alignment_score(r.score);
@@ -308,11 +430,17 @@ public:
         read.set_graph_mapq(r.unique ? 60 : 0);
         if (flags & AF_CIGAR)
         {
-            std::string buf((size_t)12 * (r.cigar_len + 2), '\0');
-            const int n = pg_format_cigar(&r, ops, &buf[0], (int)buf.size());
-            buf.resize((size_t)std::min<int>(n, (int)buf.size() - 1));
-            read.set_graph_cigar(buf);
+            formatCigar(r, ops, tmp);
+            read.set_graph_cigar(tmp);
         }
+    }
+
+    // extractCigar (GraphAligner.cpp:88-108) of one record into `out`
+    static void formatCigar(pg_record const& r, const uint32_t* ops, std::string& out)
+    {
+        out.resize((size_t)12 * (r.cigar_len + 2));
+        const int n = pg_format_cigar(&r, ops, &out[0], (int)out.size());
+        out.resize((size_t)std::min<int>(n, (int)out.size() - 1));
     }
 
     pg_ctx* context() const { return engine_->get(); }
@@ -338,6 +466,7 @@ public:
 
 private:
     std::unique_ptr<Engine> engine_;
+    unsigned threads_ = 1;
 };
 
 // Many sites in ONE launch sequence.  grmpy hands (sample, graph) pairs to threads one at a time
@@ -353,6 +482,8 @@ public:
     // A non-unique exact match is what the default filter chain rejects right after that stage; it then gets its second
     // chance in gssw on the device (pg_set_stages: nonuniq_second_chance) iff remove_nonuniq_reads is set.
     void setPathMatching(int kmer_len) { path_kmer_ = kmer_len; }
+    // host threads for packing the batch and writing the results back (results do not depend on it)
+    void setThreads(unsigned threads) { threads_ = threads ? threads : 1; }
 
     // register a site: its graph and its reads (the vector is updated in place by run(), like grm::alignReads does)
     template <typename GraphT> void addSite(GraphT const* g, std::vector<ReadPtrT>* reads)
@@ -405,8 +536,7 @@ public:
     // in addSite order.
     std::vector<paragraph::SiteCounts> alignAndCount(paragraph::CountOptions const& opt = paragraph::CountOptions())
     {
-        std::string blob;
-        std::vector<int32_t> off{ 0 }, site, fragment;
+        std::vector<int32_t> site, fragment;
         std::vector<uint8_t> is_rev;
         std::vector<ReadPtrT*> which;
         int32_t next_fragment = 0;
@@ -418,8 +548,6 @@ public:
             {
                 if (r->bases().empty())
                     continue;
-                blob += r->bases();
-                off.push_back((int32_t)blob.size());
                 site.push_back(s.id);
                 is_rev.push_back(r->is_reverse_strand() ? 1 : 0);
                 auto it = frag_id.find(r->fragment_id());
@@ -438,12 +566,15 @@ public:
         uint64_t fam_used = 0;
         if (!which.empty())
         {
-            std::vector<pg_record> rec(which.size());
-            std::vector<uint32_t> ops(blob.size() + 16 * which.size() + 64);
+            Engine& e = *engine_;
+            const size_t bytes = e.pack(which.size(), threads_, [&](size_t i) -> std::string const& { return (**which[i]).bases(); });
+            pg_record* rec = e.rec.reserve(which.size());
+            const size_t ops_cap = bytes + 16 * which.size() + 64;
+            uint32_t* ops = e.ops.reserve(ops_cap);
             uint64_t used = 0, path_used = 0;
             engine_->check(pg_set_stages(engine_->get(), path_kmer_, 1, opt.remove_nonuniq_reads ? 1 : 0));
-            engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), blob.data(), off.data(), site.data(), flags_,
-                                          rec.data(), ops.data(), ops.size(), &used));
+            engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), e.blob.data(), e.off.data(), site.data(), flags_,
+                                          rec, ops, ops_cap, &used));
             path.resize(used + 1);
             pg_count_params prm{ opt.remove_nonuniq_reads ? 1 : 0, opt.use_support_filters ? 1 : 0, opt.bad_align_frac,
                                  opt.family_slots, 0 };
@@ -464,18 +595,20 @@ public:
             for (size_t k = 0; k < sites_.size(); ++k)
                 site_index[sites_[k].id] = k;
             for (size_t i = 0; i < which.size(); ++i)
+                out[site_index.at(site[i])].invalid_alignments += sup[i].verdict == PG_V_INVALID;
+            detail::parallelFor(which.size(), threads_, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i)
             {
                 auto& read = **which[i];
                 typedef typename std::remove_reference<decltype(read)>::type ReadT;
-                const Site& s = sites_[site_index[site[i]]];
-                GraphAligner::applyRecord(read, rec[i], ops.data(), flags_, i);
+                const Site& s = sites_[site_index.at(site[i])];
+                GraphAligner::applyRecord(read, rec[i], ops, flags_, i);
                 read.clear_graph_nodes_supported();
                 read.clear_graph_edges_supported();
                 read.clear_graph_sequences_supported();
                 if (sup[i].verdict != PG_V_MAPPED)
                 {
                     read.set_graph_mapping_status(ReadT::BAD_ALIGN); // Disambiguation.cpp:184 / CompositeAligner.cpp:165-169
-                    out[site_index[site[i]]].invalid_alignments += sup[i].verdict == PG_V_INVALID;
                     continue;
                 }
                 read.set_graph_mapping_status(ReadT::MAPPED);
@@ -498,6 +631,7 @@ public:
                 for (auto const& l : seqs)
                     read.add_graph_sequences_supported(l);
             }
+            });
         }
         // tables: rows are site-major in addSite order (this object registers nothing else on the context)
         size_t nb = 0, eb = 0;
@@ -548,32 +682,35 @@ public:
     // align every registered site in one batch, apply the filter, keep MAPPED reads per site (Align.cpp:72-84,155)
     template <typename FilterT> void run(FilterT filter)
     {
-        std::string blob;
-        std::vector<int32_t> off{ 0 }, site;
+        std::vector<int32_t> site;
         std::vector<ReadPtrT*> which;
         for (auto& s : sites_)
             for (auto& r : *s.reads)
             {
                 if (r->bases().empty())
                     continue;
-                blob += r->bases();
-                off.push_back((int32_t)blob.size());
                 site.push_back(s.id);
                 which.push_back(&r);
             }
         if (!which.empty())
         {
-            std::vector<pg_record> rec(which.size());
-            std::vector<uint32_t> ops(blob.size() + 16 * which.size() + 64);
+            Engine& e = *engine_;
+            const size_t bytes = e.pack(which.size(), threads_, [&](size_t i) -> std::string const& { return (**which[i]).bases(); });
+            pg_record* rec = e.rec.reserve(which.size());
+            const size_t ops_cap = bytes + 16 * which.size() + 64;
+            uint32_t* ops = e.ops.reserve(ops_cap);
             uint64_t used = 0;
             engine_->check(pg_set_stages(engine_->get(), 0, 1, 0)); // run(filter): gssw stage only
-            engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), blob.data(), off.data(), site.data(), flags_,
-                                          rec.data(), ops.data(), ops.size(), &used));
-            for (size_t i = 0; i < which.size(); ++i)
+            engine_->check(pg_align_batch(engine_->get(), (int32_t)which.size(), e.blob.data(), e.off.data(), site.data(), flags_,
+                                          rec, ops, ops_cap, &used));
+            detail::parallelFor(which.size(), threads_, [&](size_t lo, size_t hi) {
+                for (size_t i = lo; i < hi; ++i)
+                    GraphAligner::applyRecord(**which[i], rec[i], ops, flags_, i);
+            });
+            for (size_t i = 0; i < which.size(); ++i) // the filter callback: calling thread, input order
             {
                 auto& read = **which[i];
                 typedef typename std::remove_reference<decltype(read)>::type ReadT;
-                GraphAligner::applyRecord(read, rec[i], ops.data(), flags_, i);
                 read.set_graph_mapping_status(ReadT::MAPPED); // CompositeAligner.cpp:156
                 if (filter && filter(read))
                     read.set_graph_mapping_status(ReadT::BAD_ALIGN);
@@ -622,6 +759,7 @@ private:
     std::unique_ptr<Engine> engine_;
     unsigned flags_;
     int path_kmer_ = 0;
+    unsigned threads_ = 1;
     std::vector<Site> sites_;
 };
 
@@ -643,6 +781,7 @@ public:
     {
         graphAligner_.setGraph(graph);
     }
+    void setThreads(unsigned threads) { graphAligner_.setThreads(threads); }
 
     // CompositeAligner::alignRead for a whole range (CompositeAligner.cpp:78-176): exact-match stage (:82-95), the
     // filter right after it with a second chance for rejected reads (:97-103), gssw stage (:146-175: every read it
@@ -737,18 +876,19 @@ private:
 };
 
 // grm::alignReads (Align.hh:49-52; Align.cpp:114-156): aligns, then keeps only MAPPED reads (input order).
-// `threads` is accepted for signature compatibility: the batch is one GPU launch sequence.
+// The batch is one GPU launch sequence; `threads` host threads pack it and write the results back (detail::parallelFor),
+// the filter callback runs afterwards on the calling thread, in input order.
 template <typename GraphT, typename PathListT, typename ReadPtrT, typename FilterT>
 void alignReads(GraphT const* graph, PathListT const& paths, std::vector<ReadPtrT>& reads, FilterT const& filter,
                 bool path_sequence_matching, bool graph_sequence_matching, bool klib_sequence_matching,
                 bool kmer_sequence_matching, bool validate_alignments, uint32_t threads = 1, int device = 0)
 {
-    (void)threads;
     if (validate_alignments)
         throw std::runtime_error("paragraph_b200: ValidationAligner is diagnostics-only and not provided");
     CompositeAligner aligner(path_sequence_matching, graph_sequence_matching, klib_sequence_matching,
                              kmer_sequence_matching, GraphAligner::AF_ALL, device);
     aligner.setGraph(graph, paths);
+    aligner.setThreads(threads);
     for (auto& r : reads) // Align.cpp:72-78
         if (!r->bases().empty())
             r->set_graph_mapping_status(std::remove_reference<decltype(*r)>::type::UNMAPPED);

@@ -181,6 +181,69 @@ int main()
             for (auto const& kv : counts[0].read_counts_by_edge)
                 printf("ke %s %llu\n", kv.first.c_str(), (unsigned long long)kv.second.fragments);
         }
+        // `threads`: packing and writing back on several host threads gives the same reads in the same order
+        {
+            std::vector<std::unique_ptr<Read>> t1, t5;
+            for (int i = 0; i < 4200; ++i)
+            {
+                Read r(reads[(size_t)(i % 7)]);
+                r.set_is_reverse_strand((i / 7) % 2 == 1);
+                t1.emplace_back(new Read(r));
+                t5.emplace_back(new Read(r));
+            }
+            grm::alignReads(&graph, paths, t1, filter, true, true, false, false, false, 1);
+            grm::alignReads(&graph, paths, t5, filter, true, true, false, false, false, 5);
+            bool equal = t1.size() == t5.size();
+            for (size_t i = 0; equal && i < t1.size(); ++i)
+                equal = t1[i]->fragment_id() == t5[i]->fragment_id() && t1[i]->bases() == t5[i]->bases()
+                    && t1[i]->quals() == t5[i]->quals() && t1[i]->graph_cigar() == t5[i]->graph_cigar()
+                    && t1[i]->graph_pos() == t5[i]->graph_pos() && t1[i]->graph_mapq() == t5[i]->graph_mapq()
+                    && t1[i]->graph_alignment_score() == t5[i]->graph_alignment_score()
+                    && t1[i]->is_graph_reverse_strand() == t5[i]->is_graph_reverse_strand()
+                    && t1[i]->graph_mapping_status() == t5[i]->graph_mapping_status();
+            // the same for MultiSiteAligner::alignAndCount (two sites, exact-match stage in front)
+            Graph lg = graph;
+            lg.addLabelToEdge(0, 1, "P");
+            lg.addLabelToEdge(1, 3, "P");
+            lg.addLabelToEdge(0, 2, "Q");
+            lg.addLabelToEdge(2, 3, "Q");
+            lg.addLabelToEdge(0, 3, "D");
+            const char* names[] = { "LF", "P1", "Q1", "RF" };
+            for (uint32_t v = 0; v < 4; ++v)
+                lg.setNodeName(v, names[v]);
+            std::vector<std::unique_ptr<Read>> m[2][2];
+            std::vector<paragraph::SiteCounts> counts[2];
+            for (int variant = 0; variant < 2; ++variant)
+            {
+                for (int i = 0; i < 4200; ++i)
+                {
+                    Read r(reads[(size_t)(i % 7)]);
+                    r.setCoreInfo("frag" + std::to_string(i / 2), r.bases(), r.quals());
+                    r.set_is_reverse_strand(i % 2 == 1);
+                    m[variant][i % 2].emplace_back(new Read(r));
+                }
+                grm::MultiSiteAligner<std::unique_ptr<Read>> ms;
+                ms.setPathMatching(8);
+                ms.setThreads(variant ? 5 : 1);
+                ms.addSite(&lg, &m[variant][0]);
+                ms.addSite(&lg, &m[variant][1]);
+                counts[variant] = ms.alignAndCount();
+            }
+            for (int k = 0; k < 2; ++k)
+            {
+                equal = equal && m[0][k].size() == m[1][k].size()
+                    && counts[0][(size_t)k].read_counts_by_node.size() == counts[1][(size_t)k].read_counts_by_node.size();
+                for (size_t i = 0; equal && i < m[0][k].size(); ++i)
+                    equal = m[0][k][i]->bases() == m[1][k][i]->bases() && m[0][k][i]->graph_cigar() == m[1][k][i]->graph_cigar()
+                        && m[0][k][i]->graph_nodes_supported() == m[1][k][i]->graph_nodes_supported()
+                        && m[0][k][i]->graph_sequences_supported() == m[1][k][i]->graph_sequences_supported();
+                for (auto const& kv : counts[0][(size_t)k].read_counts_by_node)
+                    equal = equal && counts[1][(size_t)k].read_counts_by_node.count(kv.first)
+                        && counts[1][(size_t)k].read_counts_by_node.at(kv.first).reads == kv.second.reads;
+            }
+            printf("threads-equal %d kept %zu of 4200, multi-site kept %zu + %zu\n", (int)equal, t1.size(), m[1][0].size(),
+                   m[1][1].size());
+        }
     }
     catch (std::exception const& e)
     {

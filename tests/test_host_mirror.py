@@ -14,7 +14,7 @@ EXE = os.path.join(ROOT, "tests", "cpp", "test_grm_mirror")
 def _compile():
     src = os.path.join(ROOT, "tests", "cpp", "test_grm_mirror.cpp")
     lib = os.path.join(ROOT, "paragraph_b200")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-o", EXE, src, "-L" + lib, "-lpgalign",
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", "-o", EXE, src, "-L" + lib, "-lpgalign",
                            "-Wl,-rpath," + lib])
 
 
@@ -40,7 +40,7 @@ def test_mirror_host_logic_over_the_emulated_abi(tmp_path):
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", shim,
                            os.path.join(ROOT, "tests", "emu", "pg_abi_shim.cpp")])
     exe = os.path.join(str(tmp_path), "test_grm_shim")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-include", os.path.join(ROOT, "tests", "emu", "pg_shim_names.h"),
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-pthread", "-include", os.path.join(ROOT, "tests", "emu", "pg_shim_names.h"),
                            "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_grm_mirror.cpp"), "-L" + str(tmp_path),
                            "-lpgshim", "-Wl,-rpath," + str(tmp_path)])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
@@ -52,6 +52,10 @@ def test_mirror_host_logic_over_the_emulated_abi(tmp_path):
 
 def _check_output(stdout):
     lines = stdout.strip().split("\n")
+    # 4 200 reads (the seven above, cycled; f7 is filtered) through alignReads, and as two sites through
+    # MultiSiteAligner::alignAndCount, with 1 and with 5 host threads: same reads, fields, supports and counts
+    assert lines[-1] == "threads-equal 1 kept 3600 of 4200, multi-site kept 1800 + 1800"
+    lines = lines[:-1]
     assert lines[:7] == [
         "f1 3 0[8M]1[4M1X3M]3[8M] 19 60 0 AAAAAAAATTTTCTTTAAAAAAAA 1",
         "f2 4 0[7M]1[4M1X3M]3[6M] 16 60 1 AAAAAAATTTTCTTTAAAAAA 1",
