@@ -318,6 +318,68 @@ PG_UNROLL
     return mg;
 }
 
+// ---- steps with no gap alive ---------------------------------------------------------------------------------
+// While no E and no F of a lane group is positive, the recurrence collapses to t = H = max(diag + s, 0): E and F only
+// ever enter as max(., E) / max(., F) against values >= 0, a value <= 0 behaves like any other value <= 0 (the
+// checkpoints already rely on that, ck_pack), and they stay <= 0 as long as every t of the step is <= GAP_OPEN
+// (E' = max(E - ge, t - go), F' likewise).  Away from a real alignment that is the rule: t >= go + 1 takes seven
+// matching bases in a row.  So a block of steps may be run SPECULATIVELY with lane_step_dead -- one DPX operation
+// per packed cell pair instead of five, no F shuffle -- when gaps_alive() is false for every lane at its start; if
+// afterwards some t of the block turned out > GAP_OPEN (its maximum is tracked anyway), the block's start state is
+// restored and the block is redone with the full step.  Either way every H and every positive E / F is what the full
+// recurrence gives; E / F registers that are <= 0 keep a stale value <= 0.
+template <int R> PG_HD bool gaps_alive(const Lane<R>& s)
+{
+    uint32_t m = s.foutLast; // the F this lane hands to the next one
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+        m = max2(m, s.E[r]);
+    return max2(m, 0u) != 0u; // some half > 0
+}
+// one step of one lane under that premise; returns the maximum of t over the lane's rows (NOT offset by MBIAS).
+// zero = 0, on the device in a register the compiler cannot see through (a literal 0 as the third DPX operand makes
+// it materialise a zero register per operation).
+template <int R, class PF> PG_HD uint32_t lane_step_dead(Lane<R>& s, uint32_t recvH, const PF& pf, uint32_t zero = 0u)
+{
+    uint32_t d = s.hupPrev;
+    s.hupPrev = recvH;
+    uint32_t mt = zero;
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+    {
+        const uint32_t t = addmax_relu2(d, pf(r), zero);
+        d = s.Hp[r];
+        s.Hp[r] = t;
+        mt = max2(mt, t);
+    }
+    s.hbotLast = s.Hp[R - 1];
+    return mt;
+}
+// did a speculative block stay within the premise?  Mt = maximum of lane_step_dead's results over the block
+PG_HD bool dead_block_broken(uint32_t Mt) { return max2(add2(Mt, pk(-GAP_OPEN, -GAP_OPEN)), 0u) != 0u; }
+// what a speculative block changes and a redo has to put back (E, foutLast are not touched by lane_step_dead)
+template <int R> struct DeadSave
+{
+    uint32_t Hp[R], hupPrev, hbotLast;
+};
+template <int R> PG_HD void dead_save(const Lane<R>& s, DeadSave<R>& b)
+{
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+        b.Hp[r] = s.Hp[r];
+    b.hupPrev = s.hupPrev;
+    b.hbotLast = s.hbotLast;
+}
+template <int R> PG_HD void dead_restore(Lane<R>& s, const DeadSave<R>& b)
+{
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+        s.Hp[r] = b.Hp[r];
+    s.hupPrev = b.hupPrev;
+    s.hbotLast = b.hbotLast;
+}
+constexpr int SPEC_STEPS = 8; // steps per speculative block (CK is a multiple)
+
 // prof = this group's profile, word (c*R + r)*W + lane = packed score of column code c against this lane's row r.
 template <int R, bool KEEP, int W = 32>
 PG_HD uint32_t lane_step(Lane<R>& s, uint32_t recvH, uint32_t recvF, const uint32_t* prof, int code, int lane,

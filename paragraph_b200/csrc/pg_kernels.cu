@@ -39,6 +39,10 @@ namespace
 #ifndef PG_FILL_UNROLL
 #define PG_FILL_UNROLL 4
 #endif
+#ifndef PG_SPEC_DEAD
+#define PG_SPEC_DEAD 0 // 1: speculative "no gap alive" blocks in the fill kernel (emulator-verified,
+                       // to be switched on once measured and fuzzed on the B200)
+#endif
 #ifndef PG_FAST_UNROLL
 #define PG_FAST_UNROLL 8
 #endif
@@ -311,6 +315,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     asm("mov.u32 %0, %1;" : "=r"(lmask) : "r"(gl ? 1u : 0u));
     asm("mov.u32 %0, %1;" : "=r"(nof0) : "r"(gl ? 0u : NO_F));
     const ProfSmem<W> pf0 = { (uint32_t)__cvta_generic_to_shared(prof + gl) };
+    const uint32_t zero = (uint32_t)a.n_tasks >> 31; // 0, in a register neither compiler stage folds (see lane_step_dead)
     for (int cki = 0; cki < nck; ++cki)
     {
         const bool live = (NT == 1) || cki < my_nck;
@@ -324,20 +329,78 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         // straight-line.
         if (FAST_BLOCKS && __all_sync(FULL, c.colsLeft >= CK))
         {
-#pragma unroll FAST_UNROLL
-            for (int kk = 0; kk < CK; ++kk)
+            // Speculation on "no gap alive" (pg_core.cuh: lane_step_dead): sub-blocks of SPEC_STEPS steps run with the
+            // collapsed recurrence when no lane of the warp holds a positive E / F at their start, and are redone with
+            // the full step when a t > gap_open appeared in them.
+            if (PG_SPEC_DEAD && !WIDE)
             {
-                uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
-                uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
-                rh *= lmask; // lane 0 has no lane above it: H = 0, no insertion running in.  (Multiply-add by an opaque
-                rf = rf * lmask + nof0; // 0/1 instead of a select: runs on the FMA pipe, the ALU pipe is the busy one)
-                const int code = live ? cp[kk] : 5;
-                const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
-                uint32_t tg[R];
-                const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr, tg);
-                track_max(c, m, kbase + kk);
-                if (WIDE)
-                    track_region<R>(c, m, tg, g, L, gl);
+                PG_NOUNROLL
+                for (int sb = 0; sb < CK; sb += SPEC_STEPS)
+                {
+                    const uint8_t* cpb = cp + sb;
+                    bool full = __any_sync(FULL, gaps_alive(s));
+                    if (!full)
+                    {
+                        DeadSave<R> keep;
+                        dead_save(s, keep);
+                        const uint32_t keepM = c.Mnode;
+                        const int keepF0 = c.first[0], keepF1 = c.first[1];
+                        uint32_t Mt = zero;
+#pragma unroll
+                        for (int kk = 0; kk < SPEC_STEPS; ++kk)
+                        {
+                            uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
+                            rh *= lmask;
+                            const int code = live ? cpb[kk] : 5;
+                            const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
+                            const uint32_t mt = lane_step_dead<R>(s, rh, pf, zero);
+                            Mt = max2(Mt, mt);
+                            track_max(c, add2(mt, pk(-MBIAS, -MBIAS)), kbase + sb + kk);
+                        }
+                        full = __any_sync(FULL, dead_block_broken(Mt));
+                        if (full)
+                        {
+                            dead_restore(s, keep);
+                            c.Mnode = keepM;
+                            c.first[0] = keepF0;
+                            c.first[1] = keepF1;
+                        }
+                    }
+                    if (full)
+                    {
+#pragma unroll
+                        for (int kk = 0; kk < SPEC_STEPS; ++kk)
+                        {
+                            uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
+                            uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
+                            rh *= lmask;
+                            rf = rf * lmask + nof0;
+                            const int code = live ? cpb[kk] : 5;
+                            const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
+                            uint32_t tg[R];
+                            const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr, tg);
+                            track_max(c, m, kbase + sb + kk);
+                        }
+                    }
+                }
+            }
+            else
+            {
+#pragma unroll FAST_UNROLL
+                for (int kk = 0; kk < CK; ++kk)
+                {
+                    uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
+                    uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
+                    rh *= lmask; // lane 0 has no lane above it: H = 0, no insertion running in.  (Multiply-add by an opaque
+                    rf = rf * lmask + nof0; // 0/1 instead of a select: runs on the FMA pipe, the ALU pipe is the busy one)
+                    const int code = live ? cp[kk] : 5;
+                    const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
+                    uint32_t tg[R];
+                    const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr, tg);
+                    track_max(c, m, kbase + kk);
+                    if (WIDE)
+                        track_region<R>(c, m, tg, g, L, gl);
+                }
             }
             c.colsLeft -= CK;
             continue;

@@ -16,6 +16,16 @@
 using namespace pg;
 
 static long g_rev_rounds = 0, g_rev_reads = 0; // reversed-graph halves rev_plan asked for / reads (see emu_align_one)
+// Speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead) -- what pg_fill_kernel does when built with
+// PG_SPEC_DEAD=1.  Off by default, like in the kernels; pgemu_set_spec(1) switches it on.
+static int g_spec = 0;
+static long g_spec_blocks[4] = { 0, 0, 0, 0 }; // blocks of SPEC_STEPS steps: run dead, redone, gaps alive, node boundary inside
+extern "C" void pgemu_set_spec(int on) { g_spec = on; }
+extern "C" void pgemu_spec_stats(long* o)
+{
+    for (int i = 0; i < 4; ++i)
+        o[i] = g_spec_blocks[i];
+}
 extern "C" void pgemu_rev_stats(long* o)
 {
     o[0] = g_rev_rounds;
@@ -48,11 +58,62 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
     if (save_trace)
         ckpt.assign((size_t)num_ckpt(g.G, W) * CKW * W, 0);
     const int nck = num_ckpt(g.G, W);
+    int no_spec_before = 0;
     for (int k = 0; k < nck * CK; ++k)
     {
         if (save_trace && k % CK == 0)
             for (int t = 0; t < W; ++t)
                 ckpt_store<R, W>(s[t], ckpt.data() + (size_t)(k / CK) * CKW * W, t);
+        if (g_spec && !WIDE && k % SPEC_STEPS == 0 && k >= no_spec_before)
+        {
+            bool flat = true, dead = true;
+            for (int t = 0; t < W; ++t)
+            {
+                flat = flat && c[t].colsLeft >= SPEC_STEPS;
+                dead = dead && !gaps_alive(s[t]);
+            }
+            ++g_spec_blocks[!flat ? 3 : (!dead ? 2 : 0)];
+            if (flat && dead)
+            {
+                DeadSave<R> keep[W];
+                LaneCtl keepc[W];
+                for (int t = 0; t < W; ++t)
+                {
+                    dead_save(s[t], keep[t]);
+                    keepc[t] = c[t];
+                }
+                uint32_t Mt = 0u;
+                for (int kk = 0; kk < SPEC_STEPS; ++kk)
+                {
+                    uint32_t rh[W];
+                    for (int t = 0; t < W; ++t)
+                    {
+                        --c[t].colsLeft;
+                        rh[t] = t ? s[t - 1].hbotLast : 0;
+                    }
+                    for (int t = 0; t < W; ++t)
+                    {
+                        const ProfPtr<W> pf = { prof.data() + (g.codes[k + kk - t] * R) * W + t };
+                        const uint32_t mt = lane_step_dead<R>(s[t], rh[t], pf);
+                        Mt = max2(Mt, mt);
+                        track_max(c[t], add2(mt, pk(-MBIAS, -MBIAS)), k + kk);
+                    }
+                }
+                if (!dead_block_broken(Mt))
+                {
+                    k += SPEC_STEPS - 1;
+                    continue;
+                }
+                --g_spec_blocks[0];
+                ++g_spec_blocks[1];
+                for (int t = 0; t < W; ++t)
+                {
+                    dead_restore(s[t], keep[t]);
+                    c[t] = keepc[t];
+                }
+                no_spec_before = k + SPEC_STEPS;
+            }
+        }
         for (int t = 0; t < W; ++t) // events read what lane t-1 wrote at an EARLIER step only
             if (c[t].colsLeft == 0)
                 node_event<R, true, W>(s[t], c[t], g, t, seedS.data(), info.data(), L);

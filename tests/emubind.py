@@ -37,6 +37,18 @@ def lib():
     return _lib
 
 
+def set_spec(on):
+    """speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead), what the kernels do when built with PG_SPEC_DEAD=1"""
+    lib().pgemu_set_spec(int(bool(on)))
+
+
+def spec_stats():
+    """blocks of SPEC_STEPS steps so far: [run dead, redone, gaps alive at the start, node boundary inside]"""
+    o = (C.c_long * 4)()
+    lib().pgemu_spec_stats(o)
+    return list(o)
+
+
 def set_geometry(w):
     """lanes per task (32, 16 or 8) used by the emulated kernels"""
     lib().pgemu_set_geometry(int(w))

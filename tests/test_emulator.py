@@ -110,3 +110,44 @@ def test_rev_plan_exhaustive(built):
     cases, halves = C.c_long(0), C.c_long(0)
     assert lib.pgemu_rev_plan_check(C.byref(cases), C.byref(halves)) == 0
     assert cases.value == 9 * 3 * 3 * 3 * 3 * 3 and halves.value < cases.value
+
+
+def test_emulator_speculative_dead_blocks(built):
+    """pg_core.cuh: lane_step_dead -- blocks of 8 steps run with the collapsed recurrence (no E / F) while no gap is
+    alive, checked afterwards and redone in full when a t > gap_open showed up (what pg_fill_kernel does when built
+    with PG_SPEC_DEAD=1).  Results must not change: golden fixtures, a fuzz over bubble graphs / alphabets / flags
+    (2-letter alphabets keep gaps alive almost everywhere, 4-letter ones exercise the dead blocks and the redo), all three
+    geometries, and a config-2-shaped batch whose block statistics are the expected ones."""
+    emubind.set_spec(1)
+    try:
+        before = emubind.spec_stats()
+        for w in (32, 16, 8):
+            emubind.set_geometry(w)
+            for case in golden_cases():
+                got, _ = emubind.emu_align_batch(case["nodes"], case["edges"], case["reads"], is_rev=case["is_rev"],
+                                                 flags=case["flags"])
+                assert strip_status(got) == case["expected"], (w, case["name"])
+        emubind.set_geometry(32)
+        R.set_fill_variant(0)
+        rng = np.random.default_rng(4242)
+        for _ in range(80):
+            alpha = ["ACGT", "AC", "ACGTN", "ACGTRYN"][int(rng.integers(0, 4))]
+            nodes, edges = synth.bubble_graph(rng, max_len=int(rng.choice([5, 20, 60, 200, 600])), alphabet=alpha)
+            reads = [r[:250] for r in synth.fuzz_reads(rng, nodes, edges, 10, max_len=int(rng.choice([60, 160, 250])))]
+            flags = int(rng.choice([0xFFFFFFFF, 1, 3, 5, 7]))
+            isrev = [i & 1 for i in range(len(reads))]
+            exp = R.OracleGraph(nodes, edges).align_batch(reads, is_rev=isrev, flags=flags)
+            got, _ = emubind.emu_align_batch(nodes, edges, reads, is_rev=isrev, flags=flags)
+            assert strip_status(got) == exp
+        mid = emubind.spec_stats()
+        assert mid[0] > before[0] and mid[1] > before[1] and mid[2] > before[2]  # dead, redone and alive blocks all occurred
+        # config 2 (the bench workload): how many blocks run dead there
+        nodes, edges, reads = synth.config2(seed=42, n_reads=60)
+        exp = R.OracleGraph(nodes, edges).align_batch(reads)
+        got, _ = emubind.emu_align_batch(nodes, edges, reads)
+        assert strip_status(got) == exp
+        dead, redone, alive, boundary = [b - a for a, b in zip(mid, emubind.spec_stats())]
+        total = dead + redone + alive + boundary
+        assert dead > 0.5 * total and redone < 0.2 * total, (dead, redone, alive, boundary)
+    finally:
+        emubind.set_spec(0)

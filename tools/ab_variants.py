@@ -5,6 +5,7 @@ ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 OUT = os.path.join(ROOT, "ab_build")
 VARIANTS = {
     "base_u8": [],
+    "spec_dead": ["-DPG_SPEC_DEAD=1"],  # speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead)
     "u16": ["-DPG_FAST_UNROLL=16"],
     "u8_w2": ["-DPG_FILL_WARPS=2"],
     "u8_w8": ["-DPG_FILL_WARPS=8"],
