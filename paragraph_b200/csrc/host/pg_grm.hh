@@ -23,6 +23,7 @@
 #include <cstring>
 #include <exception>
 #include <functional>
+#include <future>
 #include <list>
 #include <map>
 #include <memory>
@@ -761,6 +762,99 @@ private:
     int path_kmer_ = 0;
     unsigned threads_ = 1;
     std::vector<Site> sites_;
+};
+
+// Site-level double buffering.  grmpy walks its targets one by one (Workflow.cpp:108-146):
+// extract the reads of a site, align, count, write JSON.  Here the caller keeps handing over (graph, reads) pairs; they
+// are collected into batches of about `batch_reads` reads, and a full batch runs MultiSiteAligner::alignAndCount on
+// one of TWO engines (contexts, streams, page-locked staging) in a worker thread while the caller fills the batch of
+// the other one -- read extraction, packing and result write-back of one batch overlap the device time of the other
+// (the overlap bench.py's e2e_two_contexts leg measures).  Results are those of one MultiSiteAligner over all sites.
+template <typename ReadPtrT> class SitePipeline
+{
+public:
+    explicit SitePipeline(int device = 0, unsigned flags = GraphAligner::AF_ALL, size_t batch_reads = 1 << 16,
+                          unsigned threads = 1, paragraph::CountOptions const& opt = paragraph::CountOptions())
+        : batch_reads_(batch_reads ? batch_reads : 1), opt_(opt)
+    {
+        for (auto& s : slots_)
+        {
+            s.aligner.reset(new MultiSiteAligner<ReadPtrT>(device, flags));
+            s.aligner->setThreads(threads);
+        }
+    }
+    ~SitePipeline()
+    {
+        for (auto& s : slots_) // never leave a worker behind that still writes into the caller's reads
+            if (s.done.valid())
+                s.done.wait();
+    }
+    void setPathMatching(int kmer_len)
+    {
+        for (auto& s : slots_)
+            s.aligner->setPathMatching(kmer_len);
+    }
+    // queue a site; `reads` must stay alive (and untouched) until finish() -- it is updated in place like
+    // MultiSiteAligner does.  May block while the other batch is still running.
+    template <typename GraphT> void addSite(GraphT const* g, std::vector<ReadPtrT>* reads)
+    {
+        Slot& s = slots_[cur_];
+        if (s.n_sites == 0)
+            s.first_site = n_sites_;
+        s.aligner->addSite(g, reads);
+        ++s.n_sites;
+        ++n_sites_;
+        s.n_reads += reads->size();
+        if (s.n_reads >= batch_reads_)
+            flush();
+    }
+    // run what is left and wait; one SiteCounts per site in addSite order
+    std::vector<paragraph::SiteCounts> finish()
+    {
+        flush();
+        collect(slots_[0]);
+        collect(slots_[1]);
+        std::vector<paragraph::SiteCounts> out;
+        out.swap(results_);
+        n_sites_ = 0;
+        return out;
+    }
+
+private:
+    struct Slot
+    {
+        std::unique_ptr<MultiSiteAligner<ReadPtrT>> aligner;
+        std::future<std::vector<paragraph::SiteCounts>> done;
+        size_t first_site = 0, n_sites = 0, n_reads = 0;
+    };
+    void flush()
+    {
+        Slot& s = slots_[cur_];
+        if (s.n_sites == 0)
+            return;
+        MultiSiteAligner<ReadPtrT>* a = s.aligner.get();
+        const paragraph::CountOptions opt = opt_;
+        s.done = std::async(std::launch::async, [a, opt] { return a->alignAndCount(opt); });
+        cur_ ^= 1;
+        collect(slots_[cur_]); // the engine the next sites go to must be idle
+    }
+    void collect(Slot& s)
+    {
+        if (!s.done.valid())
+            return;
+        std::vector<paragraph::SiteCounts> r = s.done.get(); // rethrows what the worker threw
+        if (results_.size() < s.first_site + r.size())
+            results_.resize(s.first_site + r.size());
+        for (size_t k = 0; k < r.size(); ++k)
+            results_[s.first_site + k] = std::move(r[k]);
+        s.n_sites = s.n_reads = 0;
+    }
+    Slot slots_[2];
+    int cur_ = 0;
+    size_t n_sites_ = 0;
+    const size_t batch_reads_;
+    const paragraph::CountOptions opt_;
+    std::vector<paragraph::SiteCounts> results_;
 };
 
 template <typename ReadT> using ReadFilterT = std::function<bool(ReadT&)>; // include/grm/Filter.hh:36

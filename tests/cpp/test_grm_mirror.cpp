@@ -241,8 +241,51 @@ int main()
                     equal = equal && counts[1][(size_t)k].read_counts_by_node.count(kv.first)
                         && counts[1][(size_t)k].read_counts_by_node.at(kv.first).reads == kv.second.reads;
             }
-            printf("threads-equal %d kept %zu of 4200, multi-site kept %zu + %zu\n", (int)equal, t1.size(), m[1][0].size(),
-                   m[1][1].size());
+            // SitePipeline: six sites in batches of ~1 000 reads on two engines = one MultiSiteAligner over all six
+            std::vector<std::unique_ptr<Read>> p[2][6];
+            std::vector<paragraph::SiteCounts> pc[2];
+            for (int variant = 0; variant < 2; ++variant)
+                for (int k = 0; k < 6; ++k)
+                    for (int i = 0; i < 700; ++i)
+                    {
+                        Read r(reads[(size_t)((i + k) % 7)]);
+                        r.setCoreInfo("frag" + std::to_string(i / 2), r.bases(), r.quals());
+                        r.set_is_reverse_strand((i + k) % 3 == 1);
+                        p[variant][k].emplace_back(new Read(r));
+                    }
+            {
+                grm::MultiSiteAligner<std::unique_ptr<Read>> ms;
+                ms.setPathMatching(8);
+                for (int k = 0; k < 6; ++k)
+                    ms.addSite(&lg, &p[0][k]);
+                pc[0] = ms.alignAndCount();
+                grm::SitePipeline<std::unique_ptr<Read>> pipe(0, grm::GraphAligner::AF_ALL, 1000, 3);
+                pipe.setPathMatching(8);
+                for (int k = 0; k < 6; ++k)
+                    pipe.addSite(&lg, &p[1][k]);
+                pc[1] = pipe.finish();
+            }
+            bool pipe_equal = pc[0].size() == 6 && pc[1].size() == 6;
+            size_t pipe_kept = 0;
+            for (int k = 0; pipe_equal && k < 6; ++k)
+            {
+                pipe_equal = p[0][k].size() == p[1][k].size()
+                    && pc[0][(size_t)k].read_counts_by_node.size() == pc[1][(size_t)k].read_counts_by_node.size()
+                    && pc[0][(size_t)k].read_counts_by_sequence.size() == pc[1][(size_t)k].read_counts_by_sequence.size();
+                for (size_t i = 0; pipe_equal && i < p[0][k].size(); ++i)
+                    pipe_equal = p[0][k][i]->bases() == p[1][k][i]->bases() && p[0][k][i]->graph_cigar() == p[1][k][i]->graph_cigar()
+                        && p[0][k][i]->graph_nodes_supported() == p[1][k][i]->graph_nodes_supported();
+                for (auto const& kv : pc[0][(size_t)k].read_counts_by_node)
+                    pipe_equal = pipe_equal && pc[1][(size_t)k].read_counts_by_node.count(kv.first)
+                        && pc[1][(size_t)k].read_counts_by_node.at(kv.first).fragments == kv.second.fragments
+                        && pc[1][(size_t)k].read_counts_by_node.at(kv.first).reads == kv.second.reads;
+                for (auto const& kv : pc[0][(size_t)k].read_counts_by_edge)
+                    pipe_equal = pipe_equal && pc[1][(size_t)k].read_counts_by_edge.count(kv.first)
+                        && pc[1][(size_t)k].read_counts_by_edge.at(kv.first).fragments == kv.second.fragments;
+                pipe_kept += p[1][k].size();
+            }
+            printf("threads-equal %d kept %zu of 4200, multi-site kept %zu + %zu, pipeline-equal %d kept %zu of 4200\n", (int)equal,
+                   t1.size(), m[1][0].size(), m[1][1].size(), (int)pipe_equal, pipe_kept);
         }
     }
     catch (std::exception const& e)

@@ -54,7 +54,10 @@ def _check_output(stdout):
     lines = stdout.strip().split("\n")
     # 4 200 reads (the seven above, cycled; f7 is filtered) through alignReads, and as two sites through
     # MultiSiteAligner::alignAndCount, with 1 and with 5 host threads: same reads, fields, supports and counts
-    assert lines[-1] == "threads-equal 1 kept 3600 of 4200, multi-site kept 1800 + 1800"
+    # ... and six sites through SitePipeline (batches of ~1 000 reads alternating between two engines, a worker thread
+    # per batch) = one MultiSiteAligner over all six
+    assert lines[-1] == ("threads-equal 1 kept 3600 of 4200, multi-site kept 1800 + 1800, "
+                         "pipeline-equal 1 kept 3600 of 4200")
     lines = lines[:-1]
     assert lines[:7] == [
         "f1 3 0[8M]1[4M1X3M]3[8M] 19 60 0 AAAAAAAATTTTCTTTAAAAAAAA 1",
