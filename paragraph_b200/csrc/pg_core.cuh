@@ -378,7 +378,12 @@ PG_UNROLL
     s.hupPrev = b.hupPrev;
     s.hbotLast = b.hbotLast;
 }
-constexpr int SPEC_STEPS = 8; // steps per speculative block (CK is a multiple)
+#ifndef PG_SPEC_STEPS
+#define PG_SPEC_STEPS 8
+#endif
+static_assert(CK % PG_SPEC_STEPS == 0, "PG_SPEC_STEPS must divide the checkpoint interval");
+constexpr int SPEC_STEPS = PG_SPEC_STEPS; // steps per speculative block; CK must be a multiple (4 / 8 / 16: shorter blocks
+                                          // are redone less often but pay the vote and the state copy more often)
 
 // prof = this group's profile, word (c*R + r)*W + lane = packed score of column code c against this lane's row r.
 template <int R, bool KEEP, int W = 32>

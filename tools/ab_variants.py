@@ -6,6 +6,8 @@ OUT = os.path.join(ROOT, "ab_build")
 VARIANTS = {
     "base_u8": [],
     "spec_dead": ["-DPG_SPEC_DEAD=1"],  # speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead)
+    "spec_dead_4": ["-DPG_SPEC_DEAD=1", "-DPG_SPEC_STEPS=4"],
+    "spec_dead_16": ["-DPG_SPEC_DEAD=1", "-DPG_SPEC_STEPS=16"],
     "u16": ["-DPG_FAST_UNROLL=16"],
     "u8_w2": ["-DPG_FILL_WARPS=2"],
     "u8_w8": ["-DPG_FILL_WARPS=8"],
