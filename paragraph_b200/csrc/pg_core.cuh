@@ -130,11 +130,15 @@ PG_HD int sub_score(int a, int b) { return (a == 4 || b == 4) ? 0 : (a == b ? 1 
 // packed half h), as the character the reference would see at row j after its toUpper():
 //   o=0,h=0: bases                      o=0,h=1: reverseComplement(bases)
 //   o=1,h=0: reverse(bases)             o=1,h=1: reverseComplement(reverse(bases)) = complement(bases)
-PG_HD uint8_t read_char(const uint8_t* bases, int L, int o, int h, int j)
+PG_HD int read_index(int L, int o, int h, int j) // where row j of that string sits in `bases`
 {
     const bool rev = (o == 0) ? (h == 1) : (h == 0);
-    const uint8_t c = bases[rev ? (L - 1 - j) : j];
-    return to_upper(h ? complement_base(c) : c);
+    return rev ? (L - 1 - j) : j;
+}
+PG_HD uint8_t read_char_of(uint8_t raw, int h) { return to_upper(h ? complement_base(raw) : raw); }
+PG_HD uint8_t read_char(const uint8_t* bases, int L, int o, int h, int j)
+{
+    return read_char_of(bases[read_index(L, o, h, j)], h);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -396,41 +400,40 @@ PG_HD uint32_t lane_step(Lane<R>& s, uint32_t recvH, uint32_t recvF, const uint3
 
 // Build this lane's part of the warp profile: rows [R*lane, R*lane+R) x 6 column codes, both halves.
 // Rows >= L and the sentinel code get NEG so that they can never reach a maximum (DESIGN.md "padding").
+template <int R, int W = 32>
+PG_HD void build_profile_pair(uint32_t* prof, const uint8_t* bases0, int L0, int o0, int h0, const uint8_t* bases1, int L1,
+                              int o1, int h1, int lane);
 template <int R, int W = 32> PG_HD void build_profile(uint32_t* prof, const uint8_t* bases, int L, int orient, int lane)
 {
-    for (int r = 0; r < R; ++r)
-    {
-        const int j = R * lane + r;
-        int c0 = -1, c1 = -1;
-        if (j < L)
-        {
-            c0 = nt_code(read_char(bases, L, orient, 0, j));
-            c1 = nt_code(read_char(bases, L, orient, 1, j));
-        }
-        for (int c = 0; c < NCODE; ++c)
-        {
-            const int s0 = (c0 < 0 || c == 5) ? NEG : sub_score(c, c0);
-            const int s1 = (c1 < 0 || c == 5) ? NEG : sub_score(c, c1);
-            prof[(c * R + r) * W + lane] = pk(s0, s1);
-        }
-    }
+    build_profile_pair<R, W>(prof, bases, L, orient, 0, bases, L, orient, 1, lane);
 }
 
 // The same with the two packed halves taken from two different reads of one site: half x is the string
 // (orientation ox, half hx) of read x, or absent (bases_x == nullptr: all NEG).  Used by the paired reversed-graph
 // tasks, where each half is the one reversed-graph fill some read still needs (rev_plan).
-template <int R, int W = 32>
+// All characters are fetched first and decoded afterwards: the 2R byte loads of a lane are independent and go out
+// back to back (one memory latency per task instead of 2R -- decoding between them had them serialised, 12 % of the
+// fill kernel's stall samples sat here).
+template <int R, int W>
 PG_HD void build_profile_pair(uint32_t* prof, const uint8_t* bases0, int L0, int o0, int h0, const uint8_t* bases1, int L1,
                               int o1, int h1, int lane)
 {
+    uint8_t raw0[R], raw1[R];
+    bool has0[R], has1[R];
+PG_UNROLL
     for (int r = 0; r < R; ++r)
     {
         const int j = R * lane + r;
-        int c0 = -1, c1 = -1;
-        if (bases0 && j < L0)
-            c0 = nt_code(read_char(bases0, L0, o0, h0, j));
-        if (bases1 && j < L1)
-            c1 = nt_code(read_char(bases1, L1, o1, h1, j));
+        has0[r] = bases0 && j < L0;
+        has1[r] = bases1 && j < L1;
+        raw0[r] = has0[r] ? bases0[read_index(L0, o0, h0, j)] : (uint8_t)0;
+        raw1[r] = has1[r] ? bases1[read_index(L1, o1, h1, j)] : (uint8_t)0;
+    }
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+    {
+        const int c0 = has0[r] ? nt_code(read_char_of(raw0[r], h0)) : -1;
+        const int c1 = has1[r] ? nt_code(read_char_of(raw1[r], h1)) : -1;
         for (int c = 0; c < NCODE; ++c)
         {
             const int s0 = (c0 < 0 || c == 5) ? NEG : sub_score(c, c0);
