@@ -559,6 +559,16 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         {
             ckpt_load<R, W>(s, ckpt + (size_t)T * Sizes<R, W>::CKW * W, gl);
             ctl_at_step(c, g, T * CK, gl);
+            // the walk moves towards smaller steps: the tile it misses next is almost always T - 1.  Its checkpoint is
+            // in HBM (the fill kernel wrote hundreds of MB since); start fetching it now, the load above was the stall
+            // of this kernel that the other warps hide least (long scoreboard at ck_unpack)
+            if (T > 0)
+            {
+                const uint32_t* nx = ckpt + (size_t)(T - 1) * Sizes<R, W>::CKW * W + gl;
+#pragma unroll
+                for (int x = 0; x < Sizes<R, W>::CKW; ++x)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + x * W));
+            }
         }
         else
         {
