@@ -181,6 +181,30 @@ int main()
             for (auto const& kv : counts[0].read_counts_by_edge)
                 printf("ke %s %llu\n", kv.first.c_str(), (unsigned long long)kv.second.fragments);
         }
+        // edges of the contract: a read without bases is skipped and dropped (Align.cpp:74-77), no reads at all is
+        // fine, a read beyond PG_MAX_READ_LEN is an error (thrown like the reference's error()), not a silent skip
+        {
+            std::vector<std::unique_ptr<Read>> e1;
+            e1.emplace_back(new Read(reads[0]));
+            e1.emplace_back(new Read("empty", "", ""));
+            e1.emplace_back(new Read(reads[5]));
+            grm::alignReads(&graph, paths, e1, filter, false, true, false, false, false, 2);
+            const bool dropped = e1.size() == 2 && e1[0]->fragment_id() == "f1" && e1[1]->fragment_id() == "f6";
+            std::vector<std::unique_ptr<Read>> e2;
+            grm::alignReads(&graph, paths, e2, filter, true, true, false, false, false, 2);
+            std::vector<std::unique_ptr<Read>> e3;
+            e3.emplace_back(new Read("long", std::string(600, 'A'), std::string(600, '#')));
+            bool long_throws = false;
+            try
+            {
+                grm::alignReads(&graph, paths, e3, filter, false, true, false, false, false, 1);
+            }
+            catch (std::runtime_error const&)
+            {
+                long_throws = true;
+            }
+            printf("edge empty-dropped %d none-ok %d long-throws %d\n", (int)dropped, (int)e2.empty(), (int)long_throws);
+        }
         // `threads`: packing and writing back on several host threads gives the same reads in the same order
         {
             std::vector<std::unique_ptr<Read>> t1, t5;
