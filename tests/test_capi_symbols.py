@@ -59,4 +59,4 @@ def test_product_does_not_import_oracle():
                 assert "oracle" not in src.replace("the oracle", "").replace("oracle/", "ORACLE_DIR_MENTION") \
                     or "import" not in src or "from oracle" not in src, f
                 assert "from oracle" not in src and "import oracle" not in src and "refbind" not in src, f
-                assert "pgemu" not in src, f
+                assert "pgemu" not in src and "pgshim" not in src and "pg_shim_names" not in src, f
