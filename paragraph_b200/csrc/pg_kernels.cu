@@ -327,17 +327,42 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         // branch with its reconvergence point, a warp barrier and the register shuffling of the merge.  So: when no
         // lane of the warp meets a boundary within this block of CK steps (warp-uniform test), run the block
         // straight-line.
-        if (FAST_BLOCKS && __all_sync(FULL, c.colsLeft >= CK))
+        // Speculation on "no gap alive" (pg_core.cuh: lane_step_dead; PG_SPEC_DEAD builds): the boundary test is made
+        // per sub-block of SPEC_STEPS steps; a boundary-free sub-block runs with the collapsed recurrence when no lane
+        // of the warp holds a positive E / F at its start, and is redone with the full step when a t > gap_open
+        // appeared in it.
+        if (PG_SPEC_DEAD && !WIDE && FAST_BLOCKS)
         {
-            // Speculation on "no gap alive" (pg_core.cuh: lane_step_dead): sub-blocks of SPEC_STEPS steps run with the
-            // collapsed recurrence when no lane of the warp holds a positive E / F at their start, and are redone with
-            // the full step when a t > gap_open appeared in them.
-            if (PG_SPEC_DEAD && !WIDE)
+            PG_NOUNROLL
+            for (int sb = 0; sb < CK; sb += SPEC_STEPS)
             {
-                PG_NOUNROLL
-                for (int sb = 0; sb < CK; sb += SPEC_STEPS)
+                const uint8_t* cpb = cp + sb;
+                if (!__all_sync(FULL, c.colsLeft >= SPEC_STEPS))
                 {
-                    const uint8_t* cpb = cp + sb;
+#pragma unroll FILL_UNROLL
+                    for (int kk = 0; kk < SPEC_STEPS; ++kk) // (the boundary-aware steps below)
+                    {
+                        __syncwarp();
+                        if (c.colsLeft == 0)
+                            node_event<R, true, W>(s, c, g, gl, seedS, infoS, L);
+                        else
+                            --c.colsLeft;
+                        uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
+                        uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
+                        if (gl == 0)
+                        {
+                            rh = 0;
+                            rf = NO_F;
+                        }
+                        const int code = live ? cpb[kk] : 5;
+                        const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
+                        uint32_t tg[R];
+                        const uint32_t m = lane_step_pf<R, false, FILL_LAZY_F>(s, rh, rf, pf, nullptr, nullptr, nullptr, tg);
+                        track_max(c, m, kbase + sb + kk);
+                    }
+                    continue;
+                }
+                {
                     bool full = __any_sync(FULL, gaps_alive(s));
                     if (!full)
                     {
@@ -382,9 +407,13 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                             track_max(c, m, kbase + sb + kk);
                         }
                     }
+                    c.colsLeft -= SPEC_STEPS;
                 }
             }
-            else
+            continue;
+        }
+        if (FAST_BLOCKS && __all_sync(FULL, c.colsLeft >= CK))
+        {
             {
 #pragma unroll FAST_UNROLL
                 for (int kk = 0; kk < CK; ++kk)
