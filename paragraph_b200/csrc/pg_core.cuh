@@ -690,21 +690,31 @@ template <int R> struct TileGeom
     static constexpr int SLOT_WORDS = CK * BAND_ROWS;
 };
 
+// PRMT: result byte i = byte (selector nibble i) of the eight bytes {a: 0-3, b: 4-7} (selector nibbles < 8 only)
+PG_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t v = (uint64_t)a | ((uint64_t)b << 32);
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i)
+        r |= (uint32_t)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
 template <bool WIDE> PG_HD uint32_t pack_cell(uint32_t h, uint32_t e, uint32_t f, int half)
 {
-    e = max2(e, 0u);
-    f = max2(f, 0u);
     if (WIDE) // 10-bit fields: scores <= MAX_READ_LEN = 512
+    {
+        e = max2(e, 0u);
+        f = max2(f, 0u);
         return (uint32_t)half16(h, half) | ((uint32_t)half16(e, half) << 10) | ((uint32_t)half16(f, half) << 20);
-#if defined(__CUDA_ARCH__)
-    // bytes: b0 = h.byte(2*half), b1 = e.byte(2*half), b2 = f.byte(2*half), b3 = f.byte(2*half+1) == 0
-    const uint32_t s1 = half ? 0x0062u : 0x0040u;
-    const uint32_t s2 = half ? 0x7610u : 0x5410u;
-    return __byte_perm(__byte_perm(h, e, s1), f, s2);
-#else
-    return (uint32_t)(half16(h, half) & 0xff) | ((uint32_t)(half16(e, half) & 0xff) << 8)
-        | ((uint32_t)(half16(f, half) & 0xff) << 16);
-#endif
+    }
+    // three operations: the chosen halves of E and F side by side as one int16 pair, one clamp for both, then
+    // bytes b0 = H.byte(2*half), b1 = E.byte0, b2 = F.byte0, b3 = F.byte1 (= 0: values <= 255 after the clamp)
+    const uint32_t ef = max2(bperm(e, f, half ? 0x7632u : 0x5410u), 0u);
+    return bperm(h, ef, half ? 0x7642u : 0x7640u);
 }
 template <bool WIDE> PG_HD int cellH(uint32_t w) { return (int)(WIDE ? (w & 0x3ffu) : (w & 0xffu)); }
 template <bool WIDE> PG_HD int cellE(uint32_t w) { return (int)(WIDE ? ((w >> 10) & 0x3ffu) : ((w >> 8) & 0xffu)); }
