@@ -514,6 +514,21 @@ PG_HD void track_max(LaneCtl& c, uint32_t m, int k)
         c.first[1] = k;
 }
 
+// The same for a run of steps whose maxima come in the t domain (lane_step_dead: max t, not max t - MBIAS): the node
+// maximum is moved to that domain once (track_t_begin), compared and updated there, and moved back at the end
+// (track_t_end) -- m - MBIAS > Mnode <=> m > Mnode + MBIAS -- which saves the subtraction per step.
+PG_HD uint32_t track_t_begin(const LaneCtl& c) { return add2(c.Mnode, pk(MBIAS, MBIAS)); }
+PG_HD void track_t(LaneCtl& c, uint32_t& Mn, uint32_t mt, int k)
+{
+    bool hi_ge, lo_ge;
+    Mn = max2_ge(Mn, mt, hi_ge, lo_ge);
+    if (!lo_ge)
+        c.first[0] = k;
+    if (!hi_ge)
+        c.first[1] = k;
+}
+PG_HD void track_t_end(LaneCtl& c, uint32_t Mn) { c.Mnode = add2(Mn, pk(-MBIAS, -MBIAS)); }
+
 // WIDE fill, once per step after lane_step: fold the step into the region-restricted maximum.  tg = the step's
 // per-row t - go (lane_step's optional output), mg their maximum.
 template <int R> PG_HD void track_region(LaneCtl& c, uint32_t mg, const uint32_t* tg, const GraphView& g, int L, int lane)

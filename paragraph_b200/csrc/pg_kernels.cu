@@ -368,9 +368,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                     {
                         DeadSave<R> keep;
                         dead_save(s, keep);
-                        const uint32_t keepM = c.Mnode;
                         const int keepF0 = c.first[0], keepF1 = c.first[1];
-                        uint32_t Mt = zero;
+                        uint32_t Mt = zero, Mn = track_t_begin(c);
 #pragma unroll
                         for (int kk = 0; kk < SPEC_STEPS; ++kk)
                         {
@@ -380,16 +379,17 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                             const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
                             const uint32_t mt = lane_step_dead<R>(s, rh, pf, zero);
                             Mt = max2(Mt, mt);
-                            track_max(c, add2(mt, pk(-MBIAS, -MBIAS)), kbase + sb + kk);
+                            track_t(c, Mn, mt, kbase + sb + kk);
                         }
                         full = __any_sync(FULL, dead_block_broken(Mt));
                         if (full)
                         {
                             dead_restore(s, keep);
-                            c.Mnode = keepM;
                             c.first[0] = keepF0;
                             c.first[1] = keepF1;
                         }
+                        else
+                            track_t_end(c, Mn);
                     }
                     if (full)
                     {

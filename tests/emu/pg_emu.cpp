@@ -82,7 +82,9 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
                     dead_save(s[t], keep[t]);
                     keepc[t] = c[t];
                 }
-                uint32_t Mt = 0u;
+                uint32_t Mt = 0u, Mn[W];
+                for (int t = 0; t < W; ++t)
+                    Mn[t] = track_t_begin(c[t]);
                 for (int kk = 0; kk < SPEC_STEPS; ++kk)
                 {
                     uint32_t rh[W];
@@ -96,11 +98,13 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
                         const ProfPtr<W> pf = { prof.data() + (g.codes[k + kk - t] * R) * W + t };
                         const uint32_t mt = lane_step_dead<R>(s[t], rh[t], pf);
                         Mt = max2(Mt, mt);
-                        track_max(c[t], add2(mt, pk(-MBIAS, -MBIAS)), k + kk);
+                        track_t(c[t], Mn[t], mt, k + kk);
                     }
                 }
                 if (!dead_block_broken(Mt))
                 {
+                    for (int t = 0; t < W; ++t)
+                        track_t_end(c[t], Mn[t]);
                     k += SPEC_STEPS - 1;
                     continue;
                 }
