@@ -43,9 +43,16 @@ for x in rec:
     h.update(ops[int(x["cigar_off"]):int(x["cigar_off"]) + int(x["cigar_len"])].tobytes())
 print("%%-9s W=%%s fill %%.3f trace %%.3f total %%.3f ms  digest %%s" %% (os.environ["PG_VARIANT"], os.environ.get("PG_GEOM_W","32"), f, t, f+t, h.hexdigest()[:12]), flush=True)
 ''' % ROOT
+    digests = set()
     for name in VARIANTS:
         for w in ["32"]:
             env = dict(os.environ, PG_LIB=os.path.join(OUT, "libpg_%s.so" % name), PG_VARIANT=name, PG_GEOM_W=w)
-            subprocess.run([sys.executable, "-c", code], env=env)
+            out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+            sys.stdout.write(out.stdout)
+            sys.stderr.write(out.stderr[-2000:])
+            for line in out.stdout.splitlines():
+                if "digest" in line:
+                    digests.add(line.split("digest")[1].strip())
+    print("RESULT DIGESTS %s (%d distinct over %d variants)" % ("AGREE" if len(digests) == 1 else "DIFFER", len(digests), len(VARIANTS)))
 if __name__ == "__main__":
     build() if sys.argv[1] == "build" else run()
