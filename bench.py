@@ -347,7 +347,8 @@ def main():
             higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int16 (packed x2, DPX)", data="synthetic",
             config=dict(workload=WORKLOAD, reads_per_gpu=READS_PER_SITE, read_len=READ_LEN, graph_cols=G_COLS,
                         cells_per_read=CELLS_PER_READ, parallelism="sites sharded, %d rank(s), no collective" % world,
-                        l2="256 MiB flush write between timed steps; per-step scratch (checkpoints) exceeds L2"),
+                        l2="256 MiB flush write between timed steps; per-step scratch (checkpoints) exceeds L2",
+                        library=capi.load().pg_version().decode()),
             e2e=dict(value=round(e2e_value, 1), unit="reads/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
             gpu_launches=int(launches),
             kernels=dict(fill_ms=round(st["fill_ms"], 4), trace_ms=round(st["trace_ms"], 4),

@@ -2059,7 +2059,14 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
 
 extern "C" {
 
-const char* pg_version(void) { return "paragraph_b200 0.3 sm_100a CK=16 int16x2-wavefront W=16/32/8 reads<=512"; }
+const char* pg_version(void)
+{
+#if PG_SPEC_DEAD
+    return "paragraph_b200 0.3 sm_100a CK=16 int16x2-wavefront W=16/32/8 reads<=512 spec-dead-blocks";
+#else
+    return "paragraph_b200 0.3 sm_100a CK=16 int16x2-wavefront W=16/32/8 reads<=512";
+#endif
+}
 
 int pg_create(int device, pg_ctx** out)
 {
