@@ -258,7 +258,7 @@ private:
 class Engine
 {
 public:
-    explicit Engine(int device = 0)
+    explicit Engine(int device = 0) : device_(device)
     {
         if (pg_create(device, &ctx_) != PG_OK || !ctx_)
             throw std::runtime_error("paragraph_b200: no usable sm_100 CUDA device (there is no CPU fallback)");
@@ -267,10 +267,36 @@ public:
     Engine(Engine const&) = delete;
     Engine& operator=(Engine const&) = delete;
     pg_ctx* get() const { return ctx_; }
+    int device() const { return device_; }
     void check(int rc) const
     {
         if (rc != PG_OK)
             throw std::runtime_error(std::string("paragraph_b200: ") + pg_last_error(ctx_));
+    }
+
+    // Engines of finished aligners are kept per host thread and handed to the next aligner on that thread: the
+    // reference builds its aligners per call (Align.cpp:96-110) and grmpy calls alignReads once per (sample, target)
+    // with a few hundred reads (Workflow.cpp:108-146) -- creating a context, its streams and its device buffers each
+    // time costs milliseconds, more than aligning those reads.  A pooled engine comes back without graphs and with
+    // the default stages.
+    static std::unique_ptr<Engine> take(int device)
+    {
+        auto& p = pool();
+        for (size_t i = 0; i < p.size(); ++i)
+            if (p[i]->device() == device)
+            {
+                std::unique_ptr<Engine> e = std::move(p[i]);
+                p.erase(p.begin() + (std::ptrdiff_t)i);
+                return e;
+            }
+        return std::unique_ptr<Engine>(new Engine(device));
+    }
+    static void give(std::unique_ptr<Engine> e)
+    {
+        if (!e || pool().size() >= 4)
+            return; // (destroyed)
+        if (pg_clear_graphs(e->get()) == PG_OK && pg_set_stages(e->get(), 0, 1, 0) == PG_OK)
+            pool().push_back(std::move(e));
     }
 
     // staging of the current batch (one batch at a time per engine, like one aligner per thread in the reference)
@@ -301,7 +327,13 @@ public:
     }
 
 private:
+    static std::vector<std::unique_ptr<Engine>>& pool()
+    {
+        static thread_local std::vector<std::unique_ptr<Engine>> p;
+        return p;
+    }
     pg_ctx* ctx_ = nullptr;
+    int device_ = 0;
 };
 
 // graphtools::reverseComplement (SequenceOperations.cpp:66-89): case-sensitive, non-ACGT -> 'N'
@@ -333,7 +365,10 @@ public:
     static const unsigned int AF_REVERSE_GRAPH = 0x04;
     static const unsigned int AF_ALL = (unsigned int)-1;
 
-    explicit GraphAligner(int device = 0) : engine_(new Engine(device)) {}
+    explicit GraphAligner(int device = 0) : engine_(Engine::take(device)) {}
+    ~GraphAligner() { Engine::give(std::move(engine_)); }
+    GraphAligner(GraphAligner const&) = delete;
+    GraphAligner& operator=(GraphAligner const&) = delete;
 
     // GraphAligner::setGraph (GraphAligner.cpp:277-285); the reversed graph is derived by the engine
     template <typename GraphT> void setGraph(GraphT const* g)
@@ -476,7 +511,10 @@ private:
 template <typename ReadPtrT> class MultiSiteAligner
 {
 public:
-    explicit MultiSiteAligner(int device = 0, unsigned flags = GraphAligner::AF_ALL) : engine_(new Engine(device)), flags_(flags) {}
+    explicit MultiSiteAligner(int device = 0, unsigned flags = GraphAligner::AF_ALL) : engine_(Engine::take(device)), flags_(flags) {}
+    ~MultiSiteAligner() { Engine::give(std::move(engine_)); }
+    MultiSiteAligner(MultiSiteAligner const&) = delete;
+    MultiSiteAligner& operator=(MultiSiteAligner const&) = delete;
 
     // path_sequence_matching of alignAndDisambiguate (`paragraph` switches it on by default, main/paragraph.cpp:60):
     // the exact-match stage (grm::PathAligner, k-mer size 32 in the reference) runs in front of gssw in alignAndCount().
