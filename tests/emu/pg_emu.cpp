@@ -5,6 +5,7 @@
 // fuzzed against the oracle on machines without a GPU; nothing in the product loads it.
 #include <cstdint>
 #include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,6 +20,8 @@ static long g_rev_rounds = 0, g_rev_reads = 0; // reversed-graph halves rev_plan
 // Speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead) -- what pg_fill_kernel does when built with
 // PG_SPEC_DEAD=1.  Off by default, like in the kernels; pgemu_set_spec(1) switches it on.
 static int g_spec = 0;
+static long g_spec_pruned = 0;
+extern "C" long pgemu_spec_pruned() { return g_spec_pruned; }
 static long g_spec_blocks[4] = { 0, 0, 0, 0 }; // blocks of SPEC_STEPS steps: run dead, redone, gaps alive, node boundary inside
 extern "C" void pgemu_set_spec(int on) { g_spec = on; }
 extern "C" void pgemu_spec_stats(long* o)
@@ -59,6 +62,7 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
         ckpt.assign((size_t)num_ckpt(g.G, W) * CKW * W, 0);
     const int nck = num_ckpt(g.G, W);
     int no_spec_before = 0;
+    int sbest[2] = { 0, 0 }, pending[2] = { 0, 0 }; // EXPERIMENT (g_spec == 2): best score so far, folded in at sub-block starts
     for (int k = 0; k < nck * CK; ++k)
     {
         if (save_trace && k % CK == 0)
@@ -67,10 +71,41 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
         if (g_spec && !WIDE && k % SPEC_STEPS == 0 && k >= no_spec_before)
         {
             bool flat = true, dead = true;
+            for (int h = 0; h < 2; ++h)
+                sbest[h] = std::max(sbest[h], pending[h]);
             for (int t = 0; t < W; ++t)
             {
                 flat = flat && c[t].colsLeft >= SPEC_STEPS;
                 dead = dead && !gaps_alive(s[t]);
+            }
+            if (g_spec == 2 && flat && !dead)
+            {
+                // upper-bound pruning: a gap value v in row j cannot end above v + (L - 1 - j)
+                bool relevant = false;
+                for (int t = 0; t < W && !relevant; ++t)
+                    for (int h = 0; h < 2 && !relevant; ++h)
+                    {
+                        for (int r = 0; r < R; ++r)
+                        {
+                            const int e = half16(s[t].E[r], h), j = R * t + r;
+                            if (e > 0 && j < L && e + (L - 1 - j) >= sbest[h])
+                                relevant = true;
+                        }
+                        const int f = half16(s[t].foutLast, h), jn = R * (t + 1);
+                        if (f > 0 && jn < L && f + (L - 1 - jn) >= sbest[h])
+                            relevant = true;
+                    }
+                if (!relevant)
+                {
+                    for (int t = 0; t < W; ++t)
+                    {
+                        for (int r = 0; r < R; ++r)
+                            s[t].E[r] = pk(std::min(lo16(s[t].E[r]), 0), std::min(hi16(s[t].E[r]), 0));
+                        s[t].foutLast = pk(std::min(lo16(s[t].foutLast), 0), std::min(hi16(s[t].foutLast), 0));
+                    }
+                    dead = true;
+                    ++g_spec_pruned;
+                }
             }
             ++g_spec_blocks[!flat ? 3 : (!dead ? 2 : 0)];
             if (flat && dead)
@@ -82,7 +117,9 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
                     dead_save(s[t], keep[t]);
                     keepc[t] = c[t];
                 }
-                uint32_t Mt = 0u, Mn[W];
+                uint32_t Mt = 0u, Mn[W], Mlane[W];
+                for (int t = 0; t < W; ++t)
+                    Mlane[t] = 0u;
                 for (int t = 0; t < W; ++t)
                     Mn[t] = track_t_begin(c[t]);
                 for (int kk = 0; kk < SPEC_STEPS; ++kk)
@@ -98,10 +135,26 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
                         const ProfPtr<W> pf = { prof.data() + (g.codes[k + kk - t] * R) * W + t };
                         const uint32_t mt = lane_step_dead<R>(s[t], rh[t], pf);
                         Mt = max2(Mt, mt);
+                        Mlane[t] = max2(Mlane[t], mt);
+                        pending[0] = std::max(pending[0], lo16(mt));
+                        pending[1] = std::max(pending[1], hi16(mt));
                         track_t(c[t], Mn[t], mt, k + kk);
                     }
                 }
-                if (!dead_block_broken(Mt))
+                bool broken = dead_block_broken(Mt);
+                if (g_spec == 2 && broken)
+                {
+                    // new gaps t - go opened in the block are tolerated when they are irrelevant by the same bound
+                    broken = false;
+                    for (int t = 0; t < W; ++t)
+                        for (int h = 0; h < 2; ++h)
+                        {
+                            const int g0 = half16(Mlane[t], h) - GAP_OPEN, j0 = R * t;
+                            if (g0 > 0 && j0 < L && g0 + (L - 1 - j0) >= sbest[h])
+                                broken = true;
+                        }
+                }
+                if (!broken)
                 {
                     for (int t = 0; t < W; ++t)
                         track_t_end(c[t], Mn[t]);
@@ -136,6 +189,8 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
             uint32_t tg[R];
             const uint32_t m = lane_step_pf<R, false, PG_LAZY_F != 0>(s[t], rh[t], rf[t], pf, nullptr, nullptr, nullptr, tg);
             track_max(c[t], m, k);
+            pending[0] = std::max(pending[0], lo16(m) + MBIAS);
+            pending[1] = std::max(pending[1], hi16(m) + MBIAS);
             if (WIDE)
                 track_region<R>(c[t], m, tg, g, L, t);
         }

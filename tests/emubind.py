@@ -39,7 +39,7 @@ def lib():
 
 def set_spec(on):
     """speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead), what the kernels do when built with PG_SPEC_DEAD=1"""
-    lib().pgemu_set_spec(int(bool(on)))
+    lib().pgemu_set_spec(int(on))  # 2 = EXPERIMENT: plus upper-bound pruning of gaps that cannot reach the best score so far
 
 
 def spec_stats():

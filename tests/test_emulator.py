@@ -149,5 +149,26 @@ def test_emulator_speculative_dead_blocks(built):
         dead, redone, alive, boundary = [b - a for a, b in zip(mid, emubind.spec_stats())]
         total = dead + redone + alive + boundary
         assert dead > 0.5 * total and redone < 0.2 * total, (dead, redone, alive, boundary)
+        # EXPERIMENT (mode 2, emulator only so far): live gaps that cannot reach the best score
+        # so far (value + remaining read rows < best) are dropped at a block start, and gaps opened inside a dead block
+        # are tolerated under the same bound -- results must still not change, and more blocks run dead
+        emubind.set_spec(2)
+        for case in golden_cases():
+            got, _ = emubind.emu_align_batch(case["nodes"], case["edges"], case["reads"], is_rev=case["is_rev"],
+                                             flags=case["flags"])
+            assert strip_status(got) == case["expected"], ("prune", case["name"])
+        rng = np.random.default_rng(99)
+        for _ in range(30):
+            nodes, edges = synth.bubble_graph(rng, max_len=int(rng.choice([20, 60, 200, 600])), alphabet="ACGT")
+            reads = [r[:250] for r in synth.fuzz_reads(rng, nodes, edges, 10, max_len=int(rng.choice([60, 160, 250])))]
+            exp = R.OracleGraph(nodes, edges).align_batch(reads)
+            got, _ = emubind.emu_align_batch(nodes, edges, reads)
+            assert strip_status(got) == exp
+        before2 = emubind.spec_stats()
+        nodes, edges, reads = synth.config2(seed=42, n_reads=60)
+        got, _ = emubind.emu_align_batch(nodes, edges, reads)
+        assert strip_status(got) == R.OracleGraph(nodes, edges).align_batch(reads)
+        dead2, redone2, alive2, boundary2 = [b - a for a, b in zip(before2, emubind.spec_stats())]
+        assert dead2 > dead and alive2 < alive, (dead, alive, dead2, alive2)
     finally:
         emubind.set_spec(0)

@@ -1,6 +1,6 @@
 """Differential fuzz of the speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead) in the CPU lane emulator against the
 compiled reference (oracle/_ref): config-2 batches, DEL/INS/DUP/INV sites, vcf2paragraph-shaped long deletions, random
-bubble graphs over several alphabets; all geometries and flag sets.  usage: emu_spec_fuzz.py <seed> <seconds>"""
+bubble graphs over several alphabets; all geometries and flag sets.  usage: emu_spec_fuzz.py <seed> <seconds> [mode: 1 = speculative blocks (default), 2 = plus the pruning experiment]"""
 import sys, time
 import os
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
@@ -10,7 +10,7 @@ import emubind
 from paragraph_b200 import synth
 from oracle import refbind as R
 from conftest import strip_status
-emubind.set_spec(1)
+emubind.set_spec(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
 R.set_fill_variant(0)
 rng = np.random.default_rng(int(sys.argv[1]))
 t0 = time.time(); n = 0; bad = 0; it = 0
