@@ -71,6 +71,8 @@ PG_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s
 PG_HD uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
 PG_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
 PG_HD uint32_t add2(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+PG_HD uint32_t sub2(uint32_t a, uint32_t b) { return __vsub2(a, b); }
+PG_HD uint32_t min2(uint32_t a, uint32_t b) { return __vmins2(a, b); }
 // max(a, b) per half plus "a >= b" per half (one VIMNMX.S16x2 with two predicate outputs)
 PG_HD uint32_t max2_ge(uint32_t a, uint32_t b, bool& hi_ge, bool& lo_ge) { return __vibmax_s16x2(a, b, &hi_ge, &lo_ge); }
 #else
@@ -86,6 +88,8 @@ PG_HD uint32_t addmax2(uint32_t a, uint32_t b, uint32_t c)
 PG_HD uint32_t max2(uint32_t a, uint32_t b) { return pk(imax_(lo16(a), lo16(b)), imax_(hi16(a), hi16(b))); }
 PG_HD uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return max2(max2(a, b), c); }
 PG_HD uint32_t add2(uint32_t a, uint32_t b) { return pk(lo16(a) + lo16(b), hi16(a) + hi16(b)); }
+PG_HD uint32_t sub2(uint32_t a, uint32_t b) { return pk(lo16(a) - lo16(b), hi16(a) - hi16(b)); }
+PG_HD uint32_t min2(uint32_t a, uint32_t b) { return pk(lo16(a) < lo16(b) ? lo16(a) : lo16(b), hi16(a) < hi16(b) ? hi16(a) : hi16(b)); }
 PG_HD uint32_t max2_ge(uint32_t a, uint32_t b, bool& hi_ge, bool& lo_ge)
 {
     hi_ge = hi16(a) >= hi16(b);
@@ -382,6 +386,40 @@ PG_UNROLL
     s.hupPrev = b.hupPrev;
     s.hbotLast = b.hbotLast;
 }
+// ---- upper-bound pruning of gaps (experiment) ---------------------------------------------
+// A gap value v reaching row j cannot end above v + rem, rem = L - 1 - j (one match per remaining read row).  With
+// Sb = a lower bound of the fill's final best score (the best seen so far), a gap with v + rem < Sb can change
+// neither score nor ties nor end cell nor traceback, and may be dropped.  All arguments are packed halves; rem may
+// be negative (padding rows: never relevant).
+// Some half: v > 0, rem >= 0 and v + rem >= Sb?
+PG_HD bool gap_relevant(uint32_t v, uint32_t rem, uint32_t Sb)
+{
+    const uint32_t neg = (sub2(add2(v, rem), Sb) | add2(v, pk(-1, -1)) | rem) & 0x80008000u; // per half: sign of any of the three
+    return neg != 0x80008000u;
+}
+// rem0 = rem of the lane's first row, remNext = rem of the next lane's first row (where foutLast arrives)
+template <int R> PG_HD bool lane_gaps_relevant(const Lane<R>& s, uint32_t rem0, uint32_t remNext, uint32_t Sb)
+{
+    bool rel = gap_relevant(s.foutLast, remNext, Sb);
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+        rel = rel || gap_relevant(s.E[r], sub2(rem0, pk(r, r)), Sb);
+    return rel;
+}
+template <int R> PG_HD void lane_gaps_drop(Lane<R>& s)
+{
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+        s.E[r] = min2(s.E[r], 0u);
+    s.foutLast = min2(s.foutLast, 0u);
+}
+// a dead block whose maximum Mt broke the premise: were the gaps it would have opened (at most Mt - go, in the
+// lane's first row at best) all droppable?
+PG_HD bool dead_block_broken_pruned(uint32_t Mt, uint32_t rem0, uint32_t Sb)
+{
+    return gap_relevant(add2(Mt, pk(-GAP_OPEN, -GAP_OPEN)), rem0, Sb);
+}
+
 #ifndef PG_SPEC_STEPS
 #define PG_SPEC_STEPS 8
 #endif

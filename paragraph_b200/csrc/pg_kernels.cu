@@ -43,6 +43,10 @@ namespace
 #define PG_SPEC_DEAD 0 // 1: speculative "no gap alive" blocks in the fill kernel (emulator-verified,
                        // to be switched on once measured and fuzzed on the B200)
 #endif
+#ifndef PG_SPEC_PRUNE
+#define PG_SPEC_PRUNE 0 // 1 (with PG_SPEC_DEAD): plus upper-bound pruning of gaps that cannot reach the best score so far
+                        // (pg_core.cuh: gap_relevant; emulator-verified experiment)
+#endif
 #ifndef PG_FAST_UNROLL
 #define PG_FAST_UNROLL 8
 #endif
@@ -150,6 +154,13 @@ template <int W> struct ProfSmem
 // finalize_task (pg_core.cuh, the serial statement used by the emulator) as W-lane group reductions: every lane scans
 // its own column of the [node][3][W] table, four min / max reductions per packed half give the global maximum, the
 // first node holding it, whether a second node holds it, and the earliest cell (column, then lane) in the first.
+template <int W> __device__ __forceinline__ uint32_t group_max2(uint32_t v) // packed maximum over the W lanes of a task
+{
+#pragma unroll
+    for (int d = W / 2; d >= 1; d >>= 1)
+        v = max2(v, __shfl_xor_sync(FULL, v, d));
+    return v;
+}
 template <int W> __device__ __forceinline__ int group_min(int v)
 {
 #pragma unroll
@@ -316,6 +327,11 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     asm("mov.u32 %0, %1;" : "=r"(nof0) : "r"(gl ? 0u : NO_F));
     const ProfSmem<W> pf0 = { (uint32_t)__cvta_generic_to_shared(prof + gl) };
     const uint32_t zero = (uint32_t)a.n_tasks >> 31; // 0, in a register neither compiler stage folds (see lane_step_dead)
+    // PG_SPEC_PRUNE: best t of this lane so far (a lower bound of it: folded in at sub-block starts), and the read rows
+    // left below this lane's first row, per half (an absent half never counts)
+    uint32_t Mall = zero;
+    const int L1p = (a.mode == MODE_PAIRS) ? (rd1 >= 0 ? a.read_off[rd1 + 1] - a.read_off[rd1] : 0) : L;
+    const uint32_t rem0 = pk(L - 1 - R * gl, L1p - 1 - R * gl);
     for (int cki = 0; cki < nck; ++cki)
     {
         const bool live = (NT == 1) || cki < my_nck;
@@ -364,6 +380,22 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                 }
                 {
                     bool full = __any_sync(FULL, gaps_alive(s));
+                    uint32_t Sb = 0u;
+                    bool haveSb = false;
+                    if (PG_SPEC_PRUNE)
+                    {
+                        Mall = max2(Mall, add2(c.Mnode, pk(MBIAS, MBIAS)));
+                        if (full) // live gaps: all of them unable to reach the best score so far?
+                        {
+                            Sb = group_max2<W>(Mall);
+                            haveSb = true;
+                            if (!__any_sync(FULL, lane_gaps_relevant<R>(s, rem0, sub2(rem0, pk(R, R)), Sb)))
+                            {
+                                lane_gaps_drop<R>(s);
+                                full = false;
+                            }
+                        }
+                    }
                     if (!full)
                     {
                         DeadSave<R> keep;
@@ -382,6 +414,12 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                             track_t(c, Mn, mt, kbase + sb + kk);
                         }
                         full = __any_sync(FULL, dead_block_broken(Mt));
+                        if (PG_SPEC_PRUNE && full) // the gaps it would have opened: all droppable?
+                        {
+                            if (!haveSb)
+                                Sb = group_max2<W>(Mall);
+                            full = __any_sync(FULL, dead_block_broken_pruned(Mt, rem0, Sb));
+                        }
                         if (full)
                         {
                             dead_restore(s, keep);

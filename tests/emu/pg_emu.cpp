@@ -80,29 +80,16 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
             }
             if (g_spec == 2 && flat && !dead)
             {
-                // upper-bound pruning: a gap value v in row j cannot end above v + (L - 1 - j)
+                // upper-bound pruning (pg_core.cuh: gap_relevant), with the packed helpers the kernel would use
+                const uint32_t Sb = pk(sbest[0], sbest[1]);
                 bool relevant = false;
-                for (int t = 0; t < W && !relevant; ++t)
-                    for (int h = 0; h < 2 && !relevant; ++h)
-                    {
-                        for (int r = 0; r < R; ++r)
-                        {
-                            const int e = half16(s[t].E[r], h), j = R * t + r;
-                            if (e > 0 && j < L && e + (L - 1 - j) >= sbest[h])
-                                relevant = true;
-                        }
-                        const int f = half16(s[t].foutLast, h), jn = R * (t + 1);
-                        if (f > 0 && jn < L && f + (L - 1 - jn) >= sbest[h])
-                            relevant = true;
-                    }
+                for (int t = 0; t < W; ++t)
+                    relevant = relevant
+                        || lane_gaps_relevant<R>(s[t], pk(L - 1 - R * t, L - 1 - R * t), pk(L - 1 - R * (t + 1), L - 1 - R * (t + 1)), Sb);
                 if (!relevant)
                 {
                     for (int t = 0; t < W; ++t)
-                    {
-                        for (int r = 0; r < R; ++r)
-                            s[t].E[r] = pk(std::min(lo16(s[t].E[r]), 0), std::min(hi16(s[t].E[r]), 0));
-                        s[t].foutLast = pk(std::min(lo16(s[t].foutLast), 0), std::min(hi16(s[t].foutLast), 0));
-                    }
+                        lane_gaps_drop<R>(s[t]);
                     dead = true;
                     ++g_spec_pruned;
                 }
@@ -147,12 +134,7 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
                     // new gaps t - go opened in the block are tolerated when they are irrelevant by the same bound
                     broken = false;
                     for (int t = 0; t < W; ++t)
-                        for (int h = 0; h < 2; ++h)
-                        {
-                            const int g0 = half16(Mlane[t], h) - GAP_OPEN, j0 = R * t;
-                            if (g0 > 0 && j0 < L && g0 + (L - 1 - j0) >= sbest[h])
-                                broken = true;
-                        }
+                        broken = broken || dead_block_broken_pruned(Mlane[t], pk(L - 1 - R * t, L - 1 - R * t), pk(sbest[0], sbest[1]));
                 }
                 if (!broken)
                 {

@@ -6,6 +6,7 @@ OUT = os.path.join(ROOT, "ab_build")
 VARIANTS = {
     "base_u8": [],
     "spec_dead": ["-DPG_SPEC_DEAD=1"],  # speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead)
+    "spec_prune": ["-DPG_SPEC_DEAD=1", "-DPG_SPEC_PRUNE=1"],  # plus upper-bound pruning of gaps (gap_relevant)
     "spec_dead_4": ["-DPG_SPEC_DEAD=1", "-DPG_SPEC_STEPS=4"],
     "spec_dead_16": ["-DPG_SPEC_DEAD=1", "-DPG_SPEC_STEPS=16"],
     "u16": ["-DPG_FAST_UNROLL=16"],

@@ -14,3 +14,8 @@ PG_LIB=ab_build/libpg_spec_dead.so timeout 300 python -m pytest tests -m gpu -x 
 tail -3 gpurun_out/spec_tests.txt
 PG_LIB=ab_build/libpg_spec_dead.so timeout 200 python tools/gpu_fuzz.py 60 300 11 > gpurun_out/spec_fuzz.txt 2>&1
 tail -2 gpurun_out/spec_fuzz.txt
+# the pruning experiment on top (-DPG_SPEC_PRUNE=1): same checks
+PG_LIB=ab_build/libpg_spec_prune.so timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/prune_tests.txt 2>&1
+tail -3 gpurun_out/prune_tests.txt
+PG_LIB=ab_build/libpg_spec_prune.so timeout 200 python tools/gpu_fuzz.py 60 300 12 > gpurun_out/prune_fuzz.txt 2>&1
+tail -2 gpurun_out/prune_fuzz.txt
