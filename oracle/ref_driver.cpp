@@ -10,6 +10,7 @@
 //                      de-striped mH/mE/mF matrices exposed, to pin oracle/pg_oracle.c
 //                      cell by cell.
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <math.h> // ::round for the reference BadAlign.hh (it relies on a transitive include)
@@ -144,6 +145,59 @@ int pgref_align_batch(
     for (auto& th : pool)
         th.join();
     return 0;
+}
+
+// Many sites in one call: `threads` host threads pull whole sites from a shared counter (largest first when the caller
+// sorted them so), one GraphAligner per (thread, site) -- the scheme of src/c++/lib/grmpy/Workflow.cpp:108-146, where
+// threads pull (sample, graph) pairs.  Graph s = nodes [node_ptr[s], node_ptr[s+1]) of seq_off (offsets into seq_blob,
+// n_nodes_total + 1 entries) and edges [edge_ptr[s], edge_ptr[s+1]) (node ids local to the site); its reads are
+// [read_ptr[s], read_ptr[s+1]).  Outputs as pgref_align_batch.  Returns the number of sites that threw.
+int pgref_align_sites(
+    int n_sites, const int32_t* node_ptr, const char* seq_blob, const int32_t* seq_off, const int32_t* edge_ptr,
+    const int32_t* efrom, const int32_t* eto, const int32_t* read_ptr, const char* bases_blob, const int32_t* read_off,
+    const uint8_t* is_rev, unsigned flags, int threads, int32_t* out6, char* out_bases_blob, char* cigars,
+    int cigar_stride)
+{
+    if (threads < 1)
+        threads = 1;
+    std::atomic<int> next(0), failed(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+    {
+        pool.emplace_back([&]() {
+            for (;;)
+            {
+                const int s = next.fetch_add(1);
+                if (s >= n_sites)
+                    return;
+                try
+                {
+                    const int n0 = node_ptr[s], nn = node_ptr[s + 1] - n0;
+                    std::vector<int32_t> off(static_cast<size_t>(nn) + 1);
+                    for (int i = 0; i <= nn; ++i)
+                        off[i] = seq_off[n0 + i] - seq_off[n0];
+                    const int e0 = edge_ptr[s], ne = edge_ptr[s + 1] - e0;
+                    Graph graph = makeGraph(nn, seq_blob + seq_off[n0], off.data(), ne, efrom + e0, eto + e0);
+                    grm::GraphAligner al;
+                    al.setGraph(&graph);
+                    for (int i = read_ptr[s]; i < read_ptr[s + 1]; ++i)
+                    {
+                        alignOne(
+                            al, bases_blob + read_off[i], read_off[i + 1] - read_off[i], is_rev ? is_rev[i] : 0, flags,
+                            out6 + 6 * i, out_bases_blob ? out_bases_blob + read_off[i] : nullptr,
+                            cigars ? cigars + static_cast<size_t>(i) * cigar_stride : nullptr, cigar_stride);
+                    }
+                }
+                catch (std::exception const&)
+                {
+                    failed.fetch_add(1);
+                }
+            }
+        });
+    }
+    for (auto& th : pool)
+        th.join();
+    return failed.load();
 }
 
 // ---------------------------------------------------------------- read filters (first piece)

@@ -65,6 +65,10 @@ def ref_lib():
                                           C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                           C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8),
                                           C.c_uint, C.c_int, C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int]
+        i32p = C.POINTER(C.c_int32)
+        lib.pgref_align_sites.restype = C.c_int
+        lib.pgref_align_sites.argtypes = [C.c_int, i32p, C.c_char_p, i32p, i32p, i32p, i32p, i32p, C.c_char_p, i32p,
+                                          C.POINTER(C.c_uint8), C.c_uint, C.c_int, i32p, C.c_char_p, C.c_char_p, C.c_int]
         lib.pgref_gssw_create.restype = C.c_void_p
         lib.pgref_gssw_create.argtypes = lib.pgref_aligner_create.argtypes
         lib.pgref_gssw_destroy.argtypes = [C.c_void_p]
@@ -101,6 +105,58 @@ def ref_align_batch(node_seqs, edges, reads, is_rev=None, flags=AF_ALL, threads=
     for i in range(n):
         c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
         res.append(_result_dict(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
+    return res
+
+
+def pack_sites(sites):
+    """sites = [(nodes, edges, reads), ...] -> the flat arrays pgref_align_sites takes (kept by the caller)."""
+    node_ptr, edge_ptr, read_ptr = [0], [0], [0]
+    seqs, ef, et, reads = [], [], [], []
+    for nodes, edges, rds in sites:
+        seqs += list(nodes)
+        ef += [e[0] for e in edges]
+        et += [e[1] for e in edges]
+        reads += list(rds)
+        node_ptr.append(len(seqs))
+        edge_ptr.append(len(ef))
+        read_ptr.append(len(reads))
+    blob = "".join(seqs).encode("latin-1")
+    off = np.zeros(len(seqs) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    rblob, roff = pack_reads(reads)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    return dict(n_sites=len(sites), node_ptr=i32(node_ptr), blob=blob, off=off, edge_ptr=i32(edge_ptr), ef=i32(ef),
+                et=i32(et), read_ptr=i32(read_ptr), rblob=rblob, roff=roff, n_reads=len(reads))
+
+
+def ref_align_sites_packed(pk, threads=1, flags=AF_ALL, cigar_stride=192, want_bases=False):
+    """The reference GraphAligner::alignRead over many sites: threads pull whole sites (Workflow.cpp:108-146).
+    Returns (out6 int32[n,6] = pos, score, unique, mapq, graph_reverse, cigar length; cigar bytes[n, stride])."""
+    lib = ref_lib()
+    n = pk["n_reads"]
+    out = np.zeros((n, 6), dtype=np.int32)
+    cg = np.zeros((max(1, n), cigar_stride), dtype=np.uint8)
+    ob = C.create_string_buffer(max(1, len(pk["rblob"]))) if want_bases else None
+    bad = lib.pgref_align_sites(pk["n_sites"], _p(pk["node_ptr"], C.c_int32), pk["blob"], _p(pk["off"], C.c_int32),
+                                _p(pk["edge_ptr"], C.c_int32), _p(pk["ef"], C.c_int32), _p(pk["et"], C.c_int32),
+                                _p(pk["read_ptr"], C.c_int32), pk["rblob"], _p(pk["roff"], C.c_int32), None,
+                                flags & 0xFFFFFFFF, threads, _p(out, C.c_int32), ob,
+                                cg.ctypes.data_as(C.c_char_p), cigar_stride)
+    if bad:
+        raise RuntimeError("reference threw on %d sites" % bad)
+    return out, cg
+
+
+def ref_align_sites(sites, threads=1, flags=AF_ALL):
+    """-> list of result dicts (pos, score, unique, mapq, graph_reverse, cigar) over all reads of all sites, in order."""
+    pk = pack_sites(sites)
+    out, cg = ref_align_sites_packed(pk, threads, flags, cigar_stride=1024)
+    res = []
+    for i in range(pk["n_reads"]):
+        c = cg[i].tobytes().split(b"\0", 1)[0].decode()
+        assert len(c) == out[i, 5], "cigar truncated"
+        res.append(dict(pos=int(out[i, 0]), score=int(out[i, 1]), unique=bool(out[i, 2]), mapq=int(out[i, 3]),
+                        graph_reverse=bool(out[i, 4]), cigar=c))
     return res
 
 

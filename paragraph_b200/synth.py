@@ -85,6 +85,130 @@ def site_graph(rng, kind, flank=None, sv_len=None):
     raise ValueError(kind)
 
 
+def _split(seq, max_len=300, pad=150):
+    """graphUtils.split_ref_nodes / split_alt_nodes (src/python/lib/grm/vcfgraph/graphUtils.py:54-101): a node longer
+    than max_len keeps its first and last `pad` bases as two nodes that are NOT connected to each other."""
+    return [seq] if len(seq) <= max_len else [seq[:pad], seq[-pad:]]
+
+
+def vcf_site_graph(rng, kind, sv_len, flank=150, max_len=300, pad=150):
+    """One SV site shaped as the reference's vcf2paragraph / multigrmpy.py make it (SURVEY.md 8d "shape fidelity"):
+    `flank` = read length bases of reference either side (multigrmpy.py:198), the padding base as its own 1-bp
+    reference node, nodes longer than 300 bp cut to their first / last 150 bp with the middle dropped
+    (graphUtils.py:54-101; the cut-off halves hang off source / sink), `source` / `sink` = the 1-base sequence "X"
+    (GraphInput.cpp:81-89).  DEL / INS / DUP / INV as vcfgraph.py:174-204 (DUP = inserted copy of the reference
+    segment, INV = swap bubble with the reverse complement).  cf. share/test-data/paragraph/long-del/*.json (7 nodes,
+    8 edges, two source branches).  Node ids are topologically ordered."""
+    lf, padb, rf = random_seq(rng, flank), random_seq(rng, 1), random_seq(rng, flank)
+    seg = random_seq(rng, sv_len)
+    if kind == "DEL":
+        ref_parts, alt_parts = _split(seg, max_len, pad), None
+    elif kind == "INS":
+        ref_parts, alt_parts = None, _split(seg, max_len, pad)
+    elif kind == "DUP":  # the reference segment follows the breakpoint; its copy is inserted in front of it
+        rf = (seg + rf)[:max(flank, min(len(seg) + flank, max_len))]
+        ref_parts, alt_parts = None, _split(seg, max_len, pad)
+    elif kind == "INV":
+        ref_parts, alt_parts = _split(seg, max_len, pad), _split(revcomp(seg), max_len, pad)
+    else:
+        raise ValueError(kind)
+    # layout (topological): source, [tails of cut nodes: fed by source], LF, padding base, [ref heads], [alt heads], RF, sink
+    nodes, edges = ["X"], []
+    SRC = 0
+    tails = []
+    for parts in (ref_parts, alt_parts):
+        if parts and len(parts) == 2:
+            nodes.append(parts[1])
+            tails.append(len(nodes) - 1)
+            edges.append((SRC, tails[-1]))
+        else:
+            tails.append(None)
+    nodes.append(lf)
+    LF = len(nodes) - 1
+    edges.append((SRC, LF))
+    nodes.append(padb)
+    PAD = len(nodes) - 1
+    edges.append((LF, PAD))
+    heads = []
+    for parts in (ref_parts, alt_parts):
+        if parts:
+            nodes.append(parts[0])
+            heads.append(len(nodes) - 1)
+            edges.append((PAD, heads[-1]))
+        else:
+            heads.append(None)
+    nodes.append(rf)
+    RF = len(nodes) - 1
+    nodes.append("X")
+    SNK = len(nodes) - 1
+    edges.append((RF, SNK))
+    if ref_parts is None or alt_parts is None:
+        edges.append((PAD, RF))  # the allele without sequence of its own: bypass edge
+    for parts, hd, tl in ((ref_parts, heads[0], tails[0]), (alt_parts, heads[1], tails[1])):
+        if not parts:
+            continue
+        if len(parts) == 1:
+            edges.append((hd, RF))
+        else:  # cut node: the head runs into the sink, the tail (fed by the source) continues into RF
+            edges.append((hd, SNK))
+            edges.append((tl, RF))
+    # tails sit before LF in id order but their successor RF after: ids ascend along every edge
+    assert all(f < t for f, t in edges)
+    return nodes, sorted(set(edges))
+
+
+def vcf_sites(seed, n_sites, kinds=("DEL", "INS", "DUP", "INV"), coverage=30, read_len=150, max_sv=1000, max_reads=None):
+    """configs[3] shape: SV sites as vcf2paragraph shapes them (vcf_site_graph), ~coverage x reads over each site."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_sites):
+        kind = kinds[i % len(kinds)]
+        nodes, edges = vcf_site_graph(rng, kind, int(rng.integers(50, max_sv + 1)), flank=read_len)
+        span = max(len(h) for h in haplotypes(nodes, edges))
+        nr = max(8, int(coverage * span / read_len))
+        if max_reads:
+            nr = min(nr, max_reads)
+        out.append((kind, nodes, edges, simulate_reads(rng, nodes, edges, nr, read_len, alternate=False)))
+    return out
+
+
+def long_node_sites(seed, n_sites=24, reads_per_site=1000, read_len=150, lo=1000, hi=10000):
+    """configs[4]: INV / DUP graphs whose variant nodes are 1-10 kb, 1k reads per site."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n_sites):
+        kind = "INV" if i % 2 else "DUP"
+        n = int(rng.integers(lo, hi + 1))
+        nodes, edges = (inv_graph(rng, 500, n) if kind == "INV" else dup_graph(rng, n + 500, n))
+        out.append((kind, nodes, edges, simulate_reads(rng, nodes, edges, reads_per_site, read_len, alternate=False)))
+    return out
+
+
+# The BASELINE.json workloads by name (shared by tests/ and bench.py so that both see the same batches).
+def workload(name, scale=1.0):
+    """-> list of (kind, nodes, edges, reads).  `scale` < 1 shrinks the number of sites (CPU-side tests)."""
+    if name == "config2":
+        nodes, edges, reads = config2(seed=42, n_reads=max(64, int(10000 * scale)))
+        return [("DEL", nodes, edges, reads)]
+    if name == "config3":  # 1k mixed DEL/INS sites <= 500 bp, 30x, idealised 3-node graphs (SURVEY.md 8d)
+        return sites(seed=3, n_sites=max(2, int(1000 * scale)), kinds=("DEL", "INS"))
+    if name == "config4_share":  # one GPU's eighth of the 10k-site DEL/INS/DUP/INV sweep, vcf2paragraph-shaped graphs
+        return vcf_sites(seed=4, n_sites=max(4, int(1250 * scale)))
+    if name == "config5":
+        return long_node_sites(seed=5, n_sites=max(2, int(24 * scale)))
+    raise ValueError(name)
+
+
+def flatten_sites(site_list):
+    """-> (reads, site id per read, cells = 4 L G summed) for a list of (kind, nodes, edges, reads) registered in order."""
+    reads, sids, cells = [], [], 0
+    for i, (_, nodes, _, rds) in enumerate(site_list):
+        reads += rds
+        sids += [i] * len(rds)
+        cells += 4 * sum(len(r) for r in rds) * sum(len(n) for n in nodes)
+    return reads, np.ascontiguousarray(sids, dtype=np.int32), cells
+
+
 # ----------------------------------------------------------------------------- reads
 
 def _successors(n, edges):

@@ -19,7 +19,7 @@ def pytest_configure(config):
 def golden_cases():
     out = []
     for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "*.json"))):
-        if os.path.basename(p).startswith(("counts_", "path_")):  # counting stage / PathAligner fixtures (own tests)
+        if os.path.basename(p).startswith(("counts_", "path_", "shapes_")):  # counting stage / PathAligner fixtures (own tests)
             continue
         with open(p) as f:
             out.append(json.load(f))
@@ -43,3 +43,9 @@ def built():
     import __graft_entry__ as g
     g.build()
     return True
+
+
+def ref_graph_shapes():
+    """The reference's own graph JSONs as committed shapes (tools/make_golden_graphs.py)."""
+    with open(os.path.join(GOLDEN_DIR, "shapes_ref_graphs.json")) as f:
+        return json.load(f)["graphs"]

@@ -19,3 +19,8 @@ PG_LIB=ab_build/libpg_spec_prune.so timeout 300 python -m pytest tests -m gpu -x
 tail -3 gpurun_out/prune_tests.txt
 PG_LIB=ab_build/libpg_spec_prune.so timeout 200 python tools/gpu_fuzz.py 60 300 12 > gpurun_out/prune_fuzz.txt 2>&1
 tail -2 gpurun_out/prune_fuzz.txt
+# the other workload shapes (configs 3 / 4 share / 5) on the default build and on the speculative one
+timeout 400 python tools/bench_configs.py > gpurun_out/configs_base.txt 2>&1
+tail -8 gpurun_out/configs_base.txt
+PG_LIB=ab_build/libpg_spec_dead.so timeout 400 python tools/bench_configs.py > gpurun_out/configs_spec.txt 2>&1
+tail -8 gpurun_out/configs_spec.txt
