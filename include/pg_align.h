@@ -101,6 +101,13 @@ int pg_set_scratch_limit(pg_ctx* ctx, uint64_t bytes);
  * non-empty; sequences are upper-cased; predecessor order is ascending id.  Returns the site id. */
 int pg_add_graph(pg_ctx* ctx, int32_t n_nodes, const char* seq_blob, const int32_t* seq_off, int32_t n_edges,
                  const int32_t* efrom, const int32_t* eto, int32_t* site_id);
+/* Many sites in one call -- what grmpy's workflow hands out one (sample, graph) pair at a time
+ * (src/c++/lib/grmpy/Workflow.cpp:108-146; every alignSingleSample loads its graph, AlignSamples.cpp:115-130).
+ * Graph s has the nodes [node_ptr[s], node_ptr[s+1]) of seq_off (n_nodes_total + 1 offsets into seq_blob) and the
+ * edges [edge_ptr[s], edge_ptr[s+1]) of efrom / eto (node ids local to the site).  Same rules and errors as
+ * pg_add_graph; the sites get consecutive ids starting at *first_site_id.  Nothing is registered if one fails. */
+int pg_add_graphs(pg_ctx* ctx, int32_t n_sites, const int32_t* node_ptr, const char* seq_blob, const int32_t* seq_off,
+                  const int32_t* edge_ptr, const int32_t* efrom, const int32_t* eto, int32_t* first_site_id);
 int pg_clear_graphs(pg_ctx* ctx);
 
 /* ---- alignment -------------------------------------------------------------------------------- */

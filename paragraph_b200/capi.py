@@ -23,7 +23,7 @@ RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i2"), ("query_clipped
 
 # every symbol include/pg_align.h declares
 SYMBOLS = ["pg_create", "pg_destroy", "pg_last_error", "pg_set_stream", "pg_set_scratch_limit", "pg_add_graph",
-           "pg_clear_graphs", "pg_align_batch", "pg_batch_upload", "pg_batch_run", "pg_batch_download",
+           "pg_add_graphs", "pg_clear_graphs", "pg_align_batch", "pg_batch_upload", "pg_batch_run", "pg_batch_download",
            "pg_format_cigar", "pg_stats", "pg_version", "pg_host_alloc", "pg_host_free", "pg_set_edge_labels",
            "pg_batch_import", "pg_batch_count", "pg_count_stats", "pg_set_stages", "pg_path_stats"]
 
@@ -69,6 +69,8 @@ def load():
     lib.pg_set_scratch_limit.argtypes = [vp, C.c_uint64]
     lib.pg_add_graph.restype = C.c_int
     lib.pg_add_graph.argtypes = [vp, C.c_int32, C.c_char_p, i32p, C.c_int32, i32p, i32p, i32p]
+    lib.pg_add_graphs.restype = C.c_int
+    lib.pg_add_graphs.argtypes = [vp, C.c_int32, i32p, C.c_char_p, i32p, i32p, i32p, i32p, i32p]
     lib.pg_clear_graphs.restype = C.c_int
     lib.pg_clear_graphs.argtypes = [vp]
     lib.pg_align_batch.restype = C.c_int
@@ -222,6 +224,30 @@ class Context:
                                           C.byref(sid)))
         self._shape.append((len(node_seqs), len(edges)))
         return sid.value
+
+    @staticmethod
+    def pack_graphs(graphs):
+        """[(node sequences, edges), ...] -> the flat arrays pg_add_graphs takes (node_ptr, blob, off, edge_ptr, ef, et)"""
+        node_ptr, edge_ptr, lens, ef, et, seqs = [0], [0], [], [], [], []
+        for nodes, edges in graphs:
+            seqs.extend(nodes)
+            lens.extend(len(x) for x in nodes)
+            ef.extend(e[0] for e in edges)
+            et.extend(e[1] for e in edges)
+            node_ptr.append(len(lens))
+            edge_ptr.append(len(ef))
+        off = np.zeros(len(lens) + 1, dtype=np.int32)
+        off[1:] = np.cumsum(lens)
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        return i32(node_ptr), "".join(seqs).encode("latin-1"), off, i32(edge_ptr), i32(ef), i32(et)
+
+    def add_graphs(self, graphs=None, packed=None):
+        """Register many sites with one call (pg_add_graphs); returns the id of the first one."""
+        node_ptr, blob, off, edge_ptr, ef, et = packed if packed is not None else self.pack_graphs(graphs)
+        first = C.c_int32(-1)
+        self._check(self.lib.pg_add_graphs(self.h, len(node_ptr) - 1, _i32(node_ptr), blob, _i32(off), _i32(edge_ptr),
+                                           _i32(ef), _i32(et), C.byref(first)))
+        return first.value
 
     def clear_graphs(self):
         self._check(self.lib.pg_clear_graphs(self.h))

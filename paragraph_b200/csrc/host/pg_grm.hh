@@ -895,6 +895,112 @@ private:
     std::vector<paragraph::SiteCounts> results_;
 };
 
+// Sites sharded over the GPUs of one box.  grmpy's workflow lets `threads` host threads pull (sample, graph) pairs off a
+// shared list until it is empty (src/c++/lib/grmpy/Workflow.cpp:108-146); sites are independent, so on a multi-GPU box
+// the same list is cut into one shard per device: longest-processing-time-first by cost = read bases x graph columns
+// (what a site costs the fill kernel), one host thread per device driving a SitePipeline (two engines, double
+// buffered) over its shard.  No device talks to another; results come back in addSite order and are those of one
+// MultiSiteAligner over all sites.  Naming a device twice gives it two shards (two more engines on it).
+template <typename ReadPtrT> class ShardedAligner
+{
+public:
+    explicit ShardedAligner(std::vector<int> devices, unsigned flags = GraphAligner::AF_ALL, size_t batch_reads = 1 << 16,
+                            unsigned threads_per_device = 1, paragraph::CountOptions const& opt = paragraph::CountOptions())
+        : devices_(std::move(devices)), flags_(flags), batch_reads_(batch_reads), threads_(threads_per_device), opt_(opt)
+    {
+        if (devices_.empty())
+            throw std::runtime_error("paragraph_b200: ShardedAligner needs at least one device");
+    }
+    void setPathMatching(int kmer_len) { path_kmer_ = kmer_len; }
+
+    // queue a site; graph and reads must stay alive until run() returns (reads are updated in place)
+    template <typename GraphT> void addSite(GraphT const* g, std::vector<ReadPtrT>* reads)
+    {
+        uint64_t cols = 0, bases = 0;
+        for (size_t i = 0; i < g->numNodes(); ++i)
+            cols += g->nodeSeq((uint32_t)i).size();
+        for (auto const& r : *reads)
+            bases += r->bases().size();
+        Item it;
+        it.cost = cols * bases;
+        it.feed = [g, reads](SitePipeline<ReadPtrT>& p) { p.addSite(g, reads); };
+        items_.push_back(std::move(it));
+    }
+
+    // shard index of every queued site (LPT: sites by falling cost, each to the least loaded shard so far)
+    std::vector<int> partition() const
+    {
+        std::vector<size_t> order(items_.size());
+        for (size_t i = 0; i < order.size(); ++i)
+            order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return items_[a].cost > items_[b].cost; });
+        std::vector<uint64_t> load(devices_.size(), 0);
+        std::vector<int> shard(items_.size(), 0);
+        for (size_t i : order)
+        {
+            const size_t d = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+            shard[i] = (int)d;
+            load[d] += items_[i].cost + 1;
+        }
+        return shard;
+    }
+
+    // align + count every queued site; one SiteCounts per site in addSite order
+    std::vector<paragraph::SiteCounts> run()
+    {
+        const std::vector<int> shard = partition();
+        std::vector<paragraph::SiteCounts> out(items_.size());
+        std::vector<std::thread> pool;
+        std::exception_ptr err;
+        std::mutex m;
+        for (size_t d = 0; d < devices_.size(); ++d)
+            pool.emplace_back([&, d] {
+                try
+                {
+                    std::vector<size_t> mine;
+                    for (size_t i = 0; i < items_.size(); ++i)
+                        if (shard[i] == (int)d)
+                            mine.push_back(i);
+                    if (mine.empty())
+                        return;
+                    SitePipeline<ReadPtrT> pipe(devices_[d], flags_, batch_reads_, threads_, opt_);
+                    pipe.setPathMatching(path_kmer_);
+                    for (size_t i : mine)
+                        items_[i].feed(pipe);
+                    std::vector<paragraph::SiteCounts> r = pipe.finish();
+                    for (size_t k = 0; k < mine.size(); ++k)
+                        out[mine[k]] = std::move(r[k]); // disjoint slots per shard
+                }
+                catch (...)
+                {
+                    std::lock_guard<std::mutex> lock(m);
+                    if (!err)
+                        err = std::current_exception();
+                }
+            });
+        for (auto& th : pool)
+            th.join();
+        items_.clear();
+        if (err)
+            std::rethrow_exception(err);
+        return out;
+    }
+
+private:
+    struct Item
+    {
+        uint64_t cost;
+        std::function<void(SitePipeline<ReadPtrT>&)> feed;
+    };
+    std::vector<int> devices_;
+    unsigned flags_;
+    size_t batch_reads_;
+    unsigned threads_;
+    paragraph::CountOptions opt_;
+    int path_kmer_ = 0;
+    std::vector<Item> items_;
+};
+
 template <typename ReadT> using ReadFilterT = std::function<bool(ReadT&)>; // include/grm/Filter.hh:36
 
 class CompositeAligner

@@ -49,6 +49,28 @@ struct GraphStore
         node_base.clear();
     }
 
+    // sizes of everything add() appends to: pg_add_graphs registers all of its sites or none
+    struct Mark
+    {
+        size_t sites, bytes, ints, in_edges, bases;
+        int max_nodes, max_G, max_tab_ints;
+    };
+    Mark mark() const { return Mark{ sites.size(), bytes.size(), ints.size(), in_from.size(), edge_base.size(), max_nodes, max_G, max_tab_ints }; }
+    void rollback(const Mark& m)
+    {
+        sites.resize(m.sites);
+        bytes.resize(m.bytes);
+        ints.resize(m.ints);
+        in_from.resize(m.in_edges);
+        in_to.resize(m.in_edges);
+        in_label.resize(m.in_edges);
+        edge_base.resize(m.bases);
+        node_base.resize(m.bases);
+        max_nodes = m.max_nodes;
+        max_G = m.max_G;
+        max_tab_ints = m.max_tab_ints;
+    }
+
     // returns site id >= 0, or -1 with err set
     int add(int n_nodes, const char* blob, const int32_t* off, int n_edges, const int32_t* ef, const int32_t* et,
             std::string& err)

@@ -1516,6 +1516,7 @@ struct pg_ctx
     // batch
     int n_reads = 0, max_len = 0;
     bool have_sites = false, uploaded = false, ran = false, staging_busy = false;
+    bool imported = false; // the batch came from pg_batch_import: records and op words only, no read bases on the device
     size_t bases_bytes = 0;
     PinBuf<uint8_t> h_bases;
     PinBuf<int32_t> h_off, h_site;
@@ -1544,6 +1545,10 @@ struct pg_ctx
     bool path_second_chance = false;
     bool path_scalar = false;
     DevBuf<uint8_t> d_prerev;
+    // second chance: the exact-match kernels leave reverse-complemented bases behind for the DP (as PathAligner does
+    // with the read); the uploaded bases are kept aside so that every pg_batch_run starts from what was uploaded
+    DevBuf<uint8_t> d_bases_orig;
+    bool have_bases_orig = false;
     bool path_dirty = true;
     DevBuf<PathSite> d_psites;
     DevBuf<PathEntry> d_ptable;
@@ -1748,6 +1753,15 @@ int upload_path_index(pg_ctx* c)
     return PG_OK;
 }
 
+// CIGAR arena of a batch, in op words: a read emits at most one op per base plus two per node of its path (exact-match
+// stage, DP), and never more than the traceback's op log holds (2 L + 16) -- the second bound keeps one many-node
+// site of a multi-site batch from multiplying the arena of every read.
+unsigned long long arena_words(const pg_ctx* c, int max_nodes)
+{
+    const unsigned long long per_read = (unsigned long long)std::min(c->max_len + 2 * max_nodes + 8, 2 * c->max_len + 16);
+    return (unsigned long long)c->n_reads * per_read;
+}
+
 // The stage itself: one launch over all reads of the batch.  Mapped reads get their record and op words here; the
 // others are listed in d_todo for the DP kernels.
 int run_path_stage(pg_ctx* c)
@@ -1762,7 +1776,15 @@ int run_path_stage(pg_ctx* c)
     PG_CUDA(c, c->d_ntodo.reserve(1));
     PG_CUDA(c, c->d_pcount.reserve(3));
     PG_CUDA(c, c->d_prerev.reserve((size_t)c->n_reads));
-    c->arena_cap = (unsigned long long)c->n_reads * (unsigned long long)(c->max_len + 2 * max_nodes + 8);
+    if (c->have_bases_orig) // an earlier run of this upload may have flipped reads: start from the uploaded bases again
+        PG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, c->d_bases_orig.p, c->bases_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    else if (c->path_second_chance && c->gssw_on)
+    {
+        PG_CUDA(c, c->d_bases_orig.reserve(c->bases_bytes + 16));
+        PG_CUDA(c, cudaMemcpyAsync(c->d_bases_orig.p, c->d_bases.p, c->bases_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        c->have_bases_orig = true;
+    }
+    c->arena_cap = arena_words(c, max_nodes);
     PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
     PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
     PG_CUDA(c, cudaMemsetAsync(c->d_ntodo.p, 0, sizeof(int32_t), c->stream));
@@ -1900,7 +1922,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     PG_CUDA(c, c->d_records.reserve((size_t)c->n_reads));
     PG_CUDA(c, c->d_cursor.reserve(1));
     const int oplog_cap = 2 * c->max_len + 16;
-    c->arena_cap = (unsigned long long)c->n_reads * (unsigned long long)(c->max_len + 2 * max_nodes + 8);
+    c->arena_cap = arena_words(c, max_nodes);
     PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
     const bool after_path = c->path_ran; // the exact-match stage already wrote records / op words
     if (!after_path)
@@ -2185,6 +2207,7 @@ void pg_destroy(pg_ctx* c)
     c->d_ntodo.release();
     c->d_pcount.release();
     c->d_prerev.release();
+    c->d_bases_orig.release();
     c->d_rvntop.release();
     c->d_req.release();
     c->d_nreq.release();
@@ -2250,6 +2273,32 @@ int pg_add_graph(pg_ctx* c, int32_t n_nodes, const char* blob, const int32_t* of
     return PG_OK;
 }
 
+int pg_add_graphs(pg_ctx* c, int32_t n_sites, const int32_t* node_ptr, const char* blob, const int32_t* off,
+                  const int32_t* edge_ptr, const int32_t* ef, const int32_t* et, int32_t* first_site_id)
+{
+    if (!c || n_sites < 0 || (n_sites > 0 && (!node_ptr || !blob || !off || !edge_ptr)))
+        return fail(c, PG_E_ARG, "pg_add_graphs: bad arguments");
+    const host::GraphStore::Mark mark = c->graphs.mark();
+    const int first = (int)c->graphs.sites.size();
+    std::string err;
+    for (int32_t s = 0; s < n_sites; ++s)
+    {
+        const int32_t n0 = node_ptr[s], e0 = edge_ptr[s];
+        const int id = c->graphs.add(node_ptr[s + 1] - n0, blob, off + n0, edge_ptr[s + 1] - e0, ef ? ef + e0 : nullptr,
+                                     et ? et + e0 : nullptr, err);
+        if (id < 0)
+        {
+            c->graphs.rollback(mark);
+            return fail(c, PG_E_GRAPH, "site " + std::to_string(s) + " of the batch: " + err);
+        }
+    }
+    if (n_sites > 0)
+        c->graphs_dirty = c->count_dirty = c->path_dirty = true;
+    if (first_site_id)
+        *first_site_id = first;
+    return PG_OK;
+}
+
 int pg_clear_graphs(pg_ctx* c)
 {
     if (!c)
@@ -2258,6 +2307,8 @@ int pg_clear_graphs(pg_ctx* c)
     c->graphs_dirty = true;
     c->count_dirty = true;
     c->path_dirty = true;
+    // the site ids of an uploaded / imported batch name graphs that are gone now: the batch goes with them
+    c->uploaded = c->ran = false;
     return PG_OK;
 }
 
@@ -2269,6 +2320,7 @@ int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t
     {
         c->n_reads = 0;
         c->uploaded = true;
+        c->imported = false;
         c->ran = false;
         return PG_OK;
     }
@@ -2328,6 +2380,8 @@ int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t
     c->n_reads = n_reads;
     c->max_len = maxl;
     c->bases_bytes = nb;
+    c->have_bases_orig = false;
+    c->imported = false;
     c->uploaded = true;
     c->ran = false;
     return PG_OK;
@@ -2339,6 +2393,8 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
         return PG_E_ARG;
     if (!c->uploaded)
         return fail(c, PG_E_STATE, "pg_batch_run before pg_batch_upload");
+    if (c->imported)
+        return fail(c, PG_E_STATE, "pg_batch_run on an imported batch: pg_batch_import brings alignments, not reads");
     if (c->n_reads == 0)
     {
         c->ran = true;
@@ -2496,6 +2552,8 @@ int pg_batch_import(pg_ctx* c, int32_t n_reads, const int32_t* read_len, const i
     c->uploaded = false;
     c->ran = false;
     c->n_reads = 0;
+    c->imported = true;
+    c->have_bases_orig = false;
     if (n_reads == 0)
     {
         c->uploaded = c->ran = true;

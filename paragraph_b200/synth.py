@@ -184,6 +184,97 @@ def long_node_sites(seed, n_sites=24, reads_per_site=1000, read_len=150, lo=1000
     return out
 
 
+# ----------------------------------------------------------------------------- packed (vectorised) batches for bench.py
+_COMP_LUT = np.full(256, ord("N"), dtype=np.uint8)
+for _a, _b in zip(b"ACGT", b"TGCA"):
+    _COMP_LUT[_a] = _b
+
+
+def site_reads_packed(rng, nodes, edges, n_reads, read_len=150, sub=0.01, indel_frac=0.01, rc_frac=0.5):
+    """simulate_reads(alternate=False) without the per-base Python loop: -> (uint8 bases of all reads back to back,
+    int32 length per read).  Same model: random haplotype and start, 1 % substitutions, 1 % of the reads with one
+    1-6 bp indel, half reverse-complemented."""
+    haps = [np.frombuffer(h.encode("latin-1"), dtype=np.uint8) for h in haplotypes(nodes, edges)]
+    pick = rng.integers(0, len(haps), size=n_reads)
+    rows, lens = [None] * n_reads, np.zeros(n_reads, dtype=np.int32)
+    for hi, H in enumerate(haps):
+        idx = np.flatnonzero(pick == hi)
+        if idx.size == 0:
+            continue
+        L = min(read_len, len(H))
+        span = len(H) - L
+        starts = rng.integers(0, max(1, span - 7), size=idx.size)
+        win = H[starts[:, None] + np.arange(L)[None, :]].copy()
+        m = rng.random(win.shape) < sub
+        win[m] = ACGT[rng.integers(0, 4, size=int(m.sum()))]
+        for k in np.flatnonzero(rng.random(idx.size) < indel_frac):  # the rare read with an indel: serial
+            frag = H[starts[k]:starts[k] + L + 8].tobytes().decode("latin-1")
+            r = mutate(rng, frag, sub=sub, indel=1.0)[:L]
+            if len(r) == L:
+                win[k] = np.frombuffer(r.encode("latin-1"), dtype=np.uint8)
+        rc = rng.random(idx.size) < rc_frac
+        win[rc] = _COMP_LUT[win[rc]][:, ::-1]
+        for j, i in enumerate(idx):
+            rows[i] = win[j]
+        lens[idx] = L
+    return np.concatenate(rows), lens
+
+
+def packed_sweep(seed, n_sites, kinds=("DEL", "INS", "DUP", "INV"), coverage=30, read_len=150, max_sv=1000, shaped=True):
+    """configs[3]: the SV-site sweep as flat arrays, generated fast enough for 10k sites inside bench.py.
+    -> dict(graphs=[(nodes, edges)], blob=uint8 bases, off=int32[n+1], site=int32[n], read_ptr=int32[n_sites+1],
+    cost=int64 per site (4 L G summed over its reads), kinds=[...]).  `shaped`: vcf2paragraph-shaped graphs
+    (vcf_site_graph), else the idealised 3- / 4-node ones (site_graph)."""
+    rng = np.random.default_rng(seed)
+    graphs, blobs, lens, read_ptr, cost, kd = [], [], [], [0], [], []
+    for i in range(n_sites):
+        kind = kinds[i % len(kinds)]
+        if shaped:
+            nodes, edges = vcf_site_graph(rng, kind, int(rng.integers(50, max_sv + 1)), flank=read_len)
+            span = max(len(h) for h in haplotypes(nodes, edges))
+        else:
+            nodes, edges = site_graph(rng, kind)
+            span = sum(len(x) for x in nodes)
+        nr = max(8, int(coverage * span / read_len))
+        b, l = site_reads_packed(rng, nodes, edges, nr, read_len)
+        graphs.append((nodes, edges))
+        blobs.append(b)
+        lens.append(l)
+        read_ptr.append(read_ptr[-1] + nr)
+        cost.append(4 * int(l.sum()) * sum(len(x) for x in nodes))
+        kd.append(kind)
+    lens = np.concatenate(lens)
+    off = np.zeros(len(lens) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(lens)
+    site = np.repeat(np.arange(n_sites, dtype=np.int32), np.diff(read_ptr))
+    return dict(graphs=graphs, blob=np.concatenate(blobs), off=off, site=site, read_ptr=np.asarray(read_ptr, dtype=np.int32),
+                cost=np.asarray(cost, dtype=np.int64), kinds=kd)
+
+
+def sweep_subset(sw, site_ids):
+    """The sites `site_ids` (ascending ids, e.g. one rank's LPT shard) of a packed sweep as a sweep of their own."""
+    site_ids = np.asarray(site_ids, dtype=np.int64)
+    rp = sw["read_ptr"]
+    sel = np.concatenate([np.arange(rp[s], rp[s + 1]) for s in site_ids]) if len(site_ids) else np.zeros(0, dtype=np.int64)
+    lens = np.diff(sw["off"])[sel]
+    off = np.zeros(len(sel) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(lens)
+    src = sw["off"][:-1][sel]
+    idx = np.repeat(src - off[:-1], lens) + np.arange(int(off[-1])) if len(sel) else np.zeros(0, dtype=np.int64)
+    counts = np.diff(rp)[site_ids]
+    return dict(graphs=[sw["graphs"][s] for s in site_ids], blob=sw["blob"][idx], off=off,
+                site=np.repeat(np.arange(len(site_ids), dtype=np.int32), counts),
+                read_ptr=np.concatenate([[0], np.cumsum(counts)]).astype(np.int32), cost=sw["cost"][site_ids],
+                kinds=[sw["kinds"][s] for s in site_ids])
+
+
+def sweep_reads(sw, site_index):
+    """python strings of one site's reads (tests, parity samples)"""
+    a, b = sw["read_ptr"][site_index], sw["read_ptr"][site_index + 1]
+    raw = sw["blob"].tobytes()
+    return [raw[sw["off"][i]:sw["off"][i + 1]].decode("latin-1") for i in range(a, b)]
+
+
 # The BASELINE.json workloads by name (shared by tests/ and bench.py so that both see the same batches).
 def workload(name, scale=1.0):
     """-> list of (kind, nodes, edges, reads).  `scale` < 1 shrinks the number of sites (CPU-side tests)."""

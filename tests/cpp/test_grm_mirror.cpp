@@ -308,6 +308,54 @@ int main()
                         && pc[1][(size_t)k].read_counts_by_edge.at(kv.first).fragments == kv.second.fragments;
                 pipe_kept += p[1][k].size();
             }
+            // ShardedAligner: the same six sites (different sizes) over three shards = one MultiSiteAligner over all six
+            {
+                std::vector<std::unique_ptr<Read>> q[6];
+                for (int k = 0; k < 6; ++k)
+                    for (int i = 0; i < 700 - 100 * k; ++i)
+                    {
+                        Read r(reads[(size_t)((i + k) % 7)]);
+                        r.setCoreInfo("frag" + std::to_string(i / 2), r.bases(), r.quals());
+                        r.set_is_reverse_strand((i + k) % 3 == 1);
+                        q[k].emplace_back(new Read(r));
+                    }
+                grm::ShardedAligner<std::unique_ptr<Read>> sh(std::vector<int>{ 0, 0, 0 }, grm::GraphAligner::AF_ALL, 500, 2);
+                sh.setPathMatching(8);
+                for (int k = 0; k < 6; ++k)
+                    sh.addSite(&lg, &q[k]);
+                const std::vector<int> part = sh.partition();
+                const std::vector<paragraph::SiteCounts> sc = sh.run();
+                bool sh_equal = sc.size() == 6 && part.size() == 6;
+                // LPT over costs 700, 600, ... 200 (x the same graph): shards {0, 5}, {1, 4}, {2, 3}
+                sh_equal = sh_equal && part[0] == 0 && part[1] == 1 && part[2] == 2 && part[3] == 2 && part[4] == 1 && part[5] == 0;
+                for (int k = 0; sh_equal && k < 6; ++k)
+                {
+                    // site k holds the first 700 - 100 k reads of pipeline site k: same reads survive, same fields
+                    size_t kept_ref = 0;
+                    std::vector<std::unique_ptr<Read>> again;
+                    for (int i = 0; i < 700 - 100 * k; ++i)
+                    {
+                        Read r(reads[(size_t)((i + k) % 7)]);
+                        r.setCoreInfo("frag" + std::to_string(i / 2), r.bases(), r.quals());
+                        r.set_is_reverse_strand((i + k) % 3 == 1);
+                        again.emplace_back(new Read(r));
+                    }
+                    grm::MultiSiteAligner<std::unique_ptr<Read>> one;
+                    one.setPathMatching(8);
+                    one.addSite(&lg, &again);
+                    const std::vector<paragraph::SiteCounts> oc = one.alignAndCount();
+                    kept_ref = again.size();
+                    sh_equal = q[k].size() == kept_ref && oc[0].read_counts_by_node.size() == sc[(size_t)k].read_counts_by_node.size()
+                        && oc[0].read_counts_by_edge.size() == sc[(size_t)k].read_counts_by_edge.size();
+                    for (size_t i = 0; sh_equal && i < kept_ref; ++i)
+                        sh_equal = q[k][i]->graph_cigar() == again[i]->graph_cigar() && q[k][i]->bases() == again[i]->bases()
+                            && q[k][i]->graph_nodes_supported() == again[i]->graph_nodes_supported();
+                    for (auto const& kv : oc[0].read_counts_by_node)
+                        sh_equal = sh_equal && sc[(size_t)k].read_counts_by_node.count(kv.first)
+                            && sc[(size_t)k].read_counts_by_node.at(kv.first).fragments == kv.second.fragments;
+                }
+                printf("sharded-equal %d\n", (int)sh_equal);
+            }
             printf("threads-equal %d kept %zu of 4200, multi-site kept %zu + %zu, pipeline-equal %d kept %zu of 4200\n", (int)equal,
                    t1.size(), m[1][0].size(), m[1][1].size(), (int)pipe_equal, pipe_kept);
         }

@@ -79,6 +79,25 @@ int pg_add_graph(pg_ctx* c, int32_t n_nodes, const char* blob, const int32_t* of
         *site_id = s;
     return PG_OK;
 }
+int pg_add_graphs(pg_ctx* c, int32_t n_sites, const int32_t* node_ptr, const char* blob, const int32_t* off,
+                  const int32_t* edge_ptr, const int32_t* ef, const int32_t* et, int32_t* first_site_id)
+{
+    if (!c || n_sites < 0 || (n_sites > 0 && (!node_ptr || !blob || !off || !edge_ptr)))
+        return PG_E_ARG;
+    const pg::host::GraphStore::Mark mark = c->graphs.mark();
+    const int first = (int)c->graphs.sites.size();
+    std::string err;
+    for (int32_t s = 0; s < n_sites; ++s)
+        if (c->graphs.add(node_ptr[s + 1] - node_ptr[s], blob, off + node_ptr[s], edge_ptr[s + 1] - edge_ptr[s],
+                          ef ? ef + edge_ptr[s] : nullptr, et ? et + edge_ptr[s] : nullptr, err) < 0)
+        {
+            c->graphs.rollback(mark);
+            return shim_fail(c, PG_E_GRAPH, "site " + std::to_string(s) + " of the batch: " + err);
+        }
+    if (first_site_id)
+        *first_site_id = first;
+    return PG_OK;
+}
 int pg_clear_graphs(pg_ctx* c)
 {
     if (!c)

@@ -10,6 +10,7 @@
 #define pg_set_stream pgshim_set_stream
 #define pg_set_scratch_limit pgshim_set_scratch_limit
 #define pg_add_graph pgshim_add_graph
+#define pg_add_graphs pgshim_add_graphs
 #define pg_clear_graphs pgshim_clear_graphs
 #define pg_align_batch pgshim_align_batch
 #define pg_batch_upload pgshim_batch_upload

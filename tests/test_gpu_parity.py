@@ -450,3 +450,52 @@ def test_path_index_host_build_gives_the_same(built, monkeypatch):
                 assert (st["attempted"], st["anchored"], st["mapped"]) == cnt
         finally:
             c.close()
+
+
+def test_staged_api_is_idempotent_with_second_chance(ctx):
+    """Upload once, run many times (the staged API's contract): with the second-chance rule the exact-match kernels
+    hand reverse-complemented bases to the DP; a later run over the same upload must see the uploaded bases again
+    (same records, same stage, same strand), as one pg_align_batch call gives."""
+    from test_path_oracle import path_cases
+    rng = np.random.default_rng(53)
+    flipped = 0
+    try:
+        for nodes, edges, reads, k in path_cases(rng, 60):
+            ctx.clear_graphs()
+            ctx.add_graph(nodes, edges)
+            ctx.set_stages(k, True, True)
+            blob, off = ctx.pack_reads(reads)
+            rec0, ops0 = ctx.align_packed(blob, off)
+            rec0, ops0 = rec0.copy(), ops0.copy()
+            ctx.upload(blob, off)
+            for _ in range(3):
+                ctx.run()
+            rec1, ops1 = ctx.download()
+            for f in ("graph_pos", "score", "unique", "chose_reverse", "status", "mapped_by", "cigar_len"):
+                assert (rec0[f] == rec1[f]).all(), (f, k)
+            assert [capi.format_cigar(r, ops0) for r in rec0] == [capi.format_cigar(r, ops1) for r in rec1]
+            flipped += int((rec0["mapped_by"] == 2).sum())
+        assert flipped > 0  # reads that went to the DP with the bases the exact-match stage had reverse-complemented
+    finally:
+        ctx.set_stages(0, True)
+
+
+def test_imported_batch_cannot_be_run_and_clear_graphs_drops_the_batch(ctx):
+    nodes, edges, reads = synth.config2(seed=14, n_reads=64)
+    ctx.clear_graphs()
+    ctx.add_graph(nodes, edges)
+    blob, off = ctx.pack_reads(reads)
+    rec, ops = ctx.align_packed(blob, off)
+    rec, ops = rec.copy(), ops.copy()
+    ctx.import_alignments([len(r) for r in reads], rec, ops)
+    with pytest.raises(capi.PgError):
+        ctx.run()  # alignments were imported, not reads: nothing to align
+    ctx.upload(blob, off)
+    ctx.clear_graphs()  # the uploaded site ids name graphs that are gone
+    ctx.add_graph(nodes[:1], [])
+    with pytest.raises(capi.PgError):
+        ctx.run()
+    ctx.clear_graphs()
+    ctx.add_graph(nodes, edges)
+    rec2, ops2 = ctx.align_packed(blob, off)
+    assert (rec2["score"] == rec["score"]).all()

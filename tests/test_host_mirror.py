@@ -58,8 +58,10 @@ def _check_output(stdout):
     # per batch) = one MultiSiteAligner over all six
     assert lines[-1] == ("threads-equal 1 kept 3600 of 4200, multi-site kept 1800 + 1800, "
                          "pipeline-equal 1 kept 3600 of 4200")
-    assert lines[-2] == "edge empty-dropped 1 none-ok 1 long-throws 1"
-    lines = lines[:-2]
+    # ... and over three shards of a ShardedAligner (LPT partition, a host thread and a SitePipeline per shard)
+    assert lines[-2] == "sharded-equal 1"
+    assert lines[-3] == "edge empty-dropped 1 none-ok 1 long-throws 1"
+    lines = lines[:-3]
     assert lines[:7] == [
         "f1 3 0[8M]1[4M1X3M]3[8M] 19 60 0 AAAAAAAATTTTCTTTAAAAAAAA 1",
         "f2 4 0[7M]1[4M1X3M]3[6M] 16 60 1 AAAAAAATTTTCTTTAAAAAA 1",
