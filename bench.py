@@ -14,12 +14,27 @@ across GPUs with no data-path collective -> weak scaling); value = reads of all 
   e2e    : the same batch through the one-call C-ABI pg_align_batch with HOST buffers: pinned staging, H2D,
            kernels, D2H of records + CIGAR ops, inside the timed region.
   roofline / cpu_baseline : see DESIGN.md "Measurement".
+
+Legs beside the headline (all in the one JSON line):
+  configs           the other BASELINE.json shapes at full size on one GPU (N = 1 runs): config3 (1 000 DEL/INS sites),
+                    config4_share (1 250 vcf2paragraph-shaped DEL/INS/DUP/INV sites = one GPU's eighth of config 4),
+                    config5 (24 sites with 1-10 kb nodes): host-to-host reads/s, kernel-phase times, Tcell/s, and a
+                    parity sample against the compiled reference (mismatches must be 0; every read is compared in
+                    tests/test_gpu_configs.py)
+  sweep_config4     every N: the FIXED 10 000-site config-4 sweep, LPT-sharded over the N ranks (strong scaling); the
+                    timed pass registers the rank's graphs (pg_add_graphs), uploads, aligns, downloads and gathers
+                    per-site summaries on rank 0
+  e2e_mirror        N = 1: the C++ drop-in surface itself (pgb::grm::alignReads over vector<unique_ptr<Read>>, bases /
+                    quals / CIGAR strings written back, MAPPED filter) and SitePipeline fed by a per-site producer
+                    (tools/cpp/bench_mirror.cpp)
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -31,25 +46,34 @@ import numpy as np  # noqa: E402
 
 from paragraph_b200 import synth  # noqa: E402
 
+METRIC = "reads/sec to graph (150bp, DEL/INS); bit-exact score+CIGAR"
 READS_PER_SITE = 10000
 READ_LEN = 150
 FLANK, DEL_LEN = 500, 300
 G_COLS = 2 * FLANK + DEL_LEN
 CELLS_PER_READ = 4 * READ_LEN * G_COLS  # 4 fills x L x G = 780 000
-DPX_SLOTS_PER_CELL_PAIR = 5.0           # 4 half-rate DPX ops + 2 full-rate VIMNMX per packed pair of cells
+DPX_SLOTS_PER_CELL_PAIR = 5.0           # full recurrence: 4 half-rate DPX ops + 2 full-rate VIMNMX per packed cell pair
 WORKLOAD = "config2: 3-node DEL graph (500 bp flanks, D=300), 10k synthetic 150 bp reads per GPU"
+SWEEP_SITES = 10000
 
 
-def ncu_traffic():
-    """dram bytes read + written per launch of the dominant kernel, from the committed ncu --set full capture."""
-    path = os.path.join(ROOT, "profiles", "r01j_fill_kernel_ncu.txt")
+def step_profile():
+    """Per-launch figures of ONE benchmark step from the newest committed ncu capture (profiles/r*_step_ncu.json, made
+    by tools/ncu_step_summary.py from `ncu --set full` of this workload): ALU-pipe instructions and DRAM bytes of the
+    step's fill launches.  The workload is fixed (seed 42), so the executed instruction counts are those of every step."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_ncu.json")))
+    if not files:
+        return None
     try:
-        tot, scale = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        for line in open(path):
-            f = line.split()
-            if f and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                tot += float(f[1]) * scale[f[2]]
-        return dict(dram_bytes_per_launch=int(tot), source="profiles/r01j_fill_kernel_ncu.txt (ncu --set full of the same workload, tools/profile_run.py)")
+        doc = json.load(open(files[-1]))
+        fills = [l for l in doc["launches"] if "pg_fill_kernel" in l["kernel"]]
+        return dict(source="profiles/" + os.path.basename(files[-1]), what=doc.get("what"),
+                    fill_launches=len(fills), fill_alu_inst=sum(l["alu_pipe_inst"] for l in fills),
+                    fill_inst=sum(l["inst_executed"] for l in fills),
+                    fill_dram_bytes=int(sum(l["dram_read_bytes"] + l["dram_write_bytes"] for l in fills)),
+                    fill_duration_us=sum(l["duration_us"] for l in fills),
+                    alu_peak_inst_per_sm_cycle=doc.get("alu_peak_inst_per_sm_cycle", 2.0),
+                    alu_inst_source=fills[0].get("alu_pipe_inst_source") if fills else None)
     except Exception:
         return None
 
@@ -91,78 +115,349 @@ class ClockSampler(threading.Thread):
                     reasons=reasons, samples=len(sm))
 
 
-def cpu_reference(nodes, edges, reads, budget_s=12.0):
-    """The reference's own CPU implementation (oracle/_ref = unmodified gssw.c + GraphAligner.cpp, -O3 -msse4.1)
-    on this box's host cores, one GraphAligner per thread over contiguous chunks like grm::alignReads
-    (Align.cpp:107-153), on a bounded sample.  Thread counts are swept and the best one reported (the reference's
-    per-fill allocations make it scale poorly past a few dozen threads)."""
-    from oracle import refbind
-    kind = "reference" if refbind.have_ref() else "port"
-    ncpu = os.cpu_count() or 1
-    best = None
+# ------------------------------------------------------------------------------------------------------------------
+# The reference's own CPU implementation on this box's host cores (oracle/_ref = unmodified gssw.c + GraphAligner.cpp,
+# -O3 -msse4.1), on the config-2 batch; the time is what is spent inside the compiled library (reads and graph are
+# packed before, results are not post-processed).  Two ways to use the cores, both timed, the best one reported:
+#   threads   : one GraphAligner per thread over contiguous chunks of the batch, inside one process -- exactly
+#               grm::alignReads (Align.cpp:107-153);
+#   processes : the same chunks, one single-threaded process each -- what the reference's README recommends for
+#               throughput (one multigrmpy.py per sample, README.md:111-117).  No reference source is touched.
+# (Round 1 reported 0.7-3 k reads/s that fell with the sample size: that was this harness, not the reference -- its
+# Python post-processing copied the whole CIGAR buffer once per read.)
+# ------------------------------------------------------------------------------------------------------------------
+_REF = {}
 
-    def run(sample, threads):
+
+def _ref_chunk(span):
+    lo, hi = span
+    if _REF["batch"] is not None:
+        _REF["batch"].run(lo, hi, 1)
+    else:
+        from oracle import refbind
+        refbind.OracleGraph(_REF["nodes"], _REF["edges"]).align_batch(_REF["reads"][lo:hi])
+    return hi - lo
+
+
+class CpuReference:
+    def __init__(self, nodes, edges, reads):
+        from oracle import refbind
+        self.refbind = refbind
+        self.kind = "reference" if refbind.have_ref() else "port"
+        self.nodes, self.edges, self.reads = nodes, edges, reads
+        self.ncpu = os.cpu_count() or 1
+        self.batch = refbind.RefBatch(nodes, edges, reads) if self.kind == "reference" else None  # packed once, outside every timed region
+        _REF.update(nodes=nodes, edges=edges, reads=reads, batch=self.batch)
+        self.pool = None
+
+    def run_threads(self, n, threads):
+        if self.batch is not None:
+            return n / self.batch.run(0, n, threads)  # seconds inside the library call only
         t0 = time.perf_counter()
-        if kind == "reference":
-            refbind.ref_align_batch(nodes, edges, sample, threads=threads)
-        else:
-            refbind.OracleGraph(nodes, edges).align_batch(sample)
-        return len(sample) / (time.perf_counter() - t0)
+        self.refbind.OracleGraph(self.nodes, self.edges).align_batch(self.reads[:n])
+        return n / (time.perf_counter() - t0)
 
-    run(reads[:64], min(8, ncpu))  # warm
-    cands = sorted({ncpu, max(1, ncpu // 2), max(1, ncpu // 4), min(ncpu, 32), min(ncpu, 16), min(ncpu, 8)}) \
-        if kind == "reference" else [1]
-    t_start = time.perf_counter()
-    for t in cands:
-        probe = run(reads[:min(len(reads), 64 * t)], t)
-        n = min(len(reads), max(64 * t, int(probe * 1.5)))  # ~1.5 s of wall time per candidate
-        rate = run(reads[:n], t)
-        if best is None or rate > best[0]:
-            best = (rate, t, n)
-        if time.perf_counter() - t_start > budget_s:
-            break
-    return dict(value=round(best[0], 1), unit="reads/s", cores=best[1], kind=kind,
-                sample="%d reads of the config-2 batch, best of thread counts %s (host has %d hardware threads)"
-                       % (best[2], cands, ncpu))
+    def run_processes(self, n, procs):
+        if self.pool is None or self.pool_size != procs:
+            import multiprocessing as mp
+            self.close()
+            self.pool = mp.get_context("fork").Pool(procs)
+            self.pool_size = procs
+            self.pool.map(_ref_chunk, [(i, i + 8) for i in range(0, 8 * procs, 8)], chunksize=1)  # warm: first touch in every worker
+        step = (n + procs - 1) // procs
+        spans = [(lo, min(n, lo + step)) for lo in range(0, n, step)]
+        t0 = time.perf_counter()
+        self.pool.map(_ref_chunk, spans, chunksize=1)
+        return n / (time.perf_counter() - t0)
+
+    def run(self, cfg, n):
+        return self.run_processes(n, cfg[1]) if cfg[0] == "processes" else self.run_threads(n, cfg[1])
+
+    def candidates(self):
+        n = self.ncpu
+        if self.kind != "reference":
+            return [("threads", 1)]
+        return [("threads", t) for t in sorted({1, max(1, n // 4), max(1, n // 2), n})] + [("processes", n)]
+
+    def table(self, reps=3, budget_s=60.0):
+        """-> (rows, best row).  Full batch for every multi-core row, warm, best of `reps`; a row whose warm-up rate says
+        the full batch would take more than its share of the time budget runs a bounded sample instead (and says so);
+        the single-core row runs a 2 000-read sample."""
+        rows = []
+        cands = self.candidates()
+        share = budget_s / len(cands)
+        for cfg in cands:
+            n = len(self.reads) if cfg[1] > 1 else min(len(self.reads), 2000)
+            probe = self.run(cfg, min(n, 64 * cfg[1]))  # warm-up, and a first estimate of the rate
+            n = int(max(min(n, 64 * cfg[1]), min(n, probe * share / reps)))
+            rates = [self.run(cfg, n) for _ in range(reps)]
+            rows.append(dict(how=cfg[0], cores=cfg[1], reads=n, runs=len(rates), reads_per_s=round(max(rates), 1),
+                             spread=round(max(rates) / min(rates), 3)))
+        best = max(rows, key=lambda r: r["reads_per_s"])
+        return rows, best
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
+
+
+def cpu_baseline(nodes, edges, reads):
+    ref = CpuReference(nodes, edges, reads)
+    try:
+        rows, best = ref.table()
+    finally:
+        ref.close()
+    return dict(value=best["reads_per_s"], unit="reads/s", cores=best["cores"], kind=ref.kind, how=best["how"],
+                sample="%d reads of the %d-read config-2 batch, warm, best of %d runs per row, time inside the library call; "
+                       "rows = grm::alignReads-style threads in one process, and one single-threaded process per core "
+                       "(host has %d hardware threads)" % (best["reads"], len(reads), best["runs"], ref.ncpu),
+                table=rows, same_config=best["reads"] == len(reads))
 
 
 def bench_reference(args):
-    """--impl reference: the reference CPU path on the host cores; rank 0 only."""
+    """--impl reference: the reference CPU path on the host cores, full config-2 batch per step, the best way of using
+    the cores found by one quick pass over the candidates; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     nodes, edges, reads = workload(0)
-    from oracle import refbind
-    kind = "reference" if refbind.have_ref() else "port"
-    ncpu = os.cpu_count() or 1
-    base = cpu_reference(nodes, edges, reads, budget_s=8.0)
-    threads, per_step = base["cores"], max(512, min(len(reads), int(base["value"] * 1.5)))
-    sample = reads[:per_step]
-
-    def step():
-        if kind == "reference":
-            refbind.ref_align_batch(nodes, edges, sample, threads=threads)
-        else:
-            refbind.OracleGraph(nodes, edges).align_batch(sample)
-
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    value = per_step * args.steps / dt
-    line = dict(metric="reads/sec to graph (150bp, DEL/INS); bit-exact score+CIGAR", value=round(value, 1),
-                unit="reads/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=round(dt / args.steps * 1e3, 3), higher_is_better=True, scaling="weak", vs_baseline=None,
-                dtype="u8", data="synthetic", impl="reference",
-                config=dict(workload=WORKLOAD, step_sample="%d reads per step" % per_step, threads=threads),
-                cpu_baseline=dict(value=round(value, 1), unit="reads/s", cores=threads, kind=kind,
-                                  sample="%d reads per step x %d steps (host has %d hardware threads)"
-                                         % (per_step, args.steps, ncpu)),
+    ref = CpuReference(nodes, edges, reads)
+    try:
+        rows, best = ref.table(reps=1, budget_s=30.0)
+        cfg = (best["how"], best["cores"])
+        n = len(reads)
+        if n / best["reads_per_s"] * (args.steps + args.warmup) > 240.0:  # keep the whole run within a few minutes
+            n = max(256, int(best["reads_per_s"] * 240.0 / (args.steps + args.warmup)))
+        for _ in range(args.warmup):
+            ref.run(cfg, n)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ref.run(cfg, n)
+        dt = time.perf_counter() - t0
+    finally:
+        ref.close()
+    value = n * args.steps / dt
+    line = dict(metric=METRIC, value=round(value, 1), unit="reads/s", n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=round(dt / args.steps * 1e3, 3), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="u8", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, step_sample="%d of the batch's %d reads per step" % (n, len(reads)), how=cfg[0],
+                            cores=cfg[1], same_config=n == len(reads)),
+                cpu_baseline=dict(value=round(value, 1), unit="reads/s", cores=cfg[1], kind=ref.kind, how=cfg[0],
+                                  sample="%d reads per step x %d steps (host has %d hardware threads)" % (n, args.steps, ref.ncpu),
+                                  selection=rows, same_config=n == len(reads)),
                 e2e=dict(value=round(value, 1), unit="reads/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
     return 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# legs on the other workload shapes
+# ------------------------------------------------------------------------------------------------------------------
+def config5_sweep(seed=5, n_sites=24, reads_per_site=1000):
+    """BASELINE.json configs[4] as a packed sweep: INV / DUP graphs whose variant nodes are 1-10 kb, 1k reads per site."""
+    rng = np.random.default_rng(seed)
+    graphs, blobs, lens, read_ptr, cost, kinds = [], [], [], [0], [], []
+    for i in range(n_sites):
+        kind = "INV" if i % 2 else "DUP"
+        n = int(rng.integers(1000, 10001))
+        nodes, edges = synth.inv_graph(rng, 500, n) if kind == "INV" else synth.dup_graph(rng, n + 500, n)
+        b, l = synth.site_reads_packed(rng, nodes, edges, reads_per_site, READ_LEN)
+        graphs.append((nodes, edges))
+        blobs.append(b)
+        lens.append(l)
+        read_ptr.append(read_ptr[-1] + reads_per_site)
+        cost.append(4 * int(l.sum()) * sum(len(x) for x in nodes))
+        kinds.append(kind)
+    lens = np.concatenate(lens)
+    off = np.zeros(len(lens) + 1, dtype=np.int32)
+    off[1:] = np.cumsum(lens)
+    return dict(graphs=graphs, blob=np.concatenate(blobs), off=off,
+                site=np.repeat(np.arange(n_sites, dtype=np.int32), reads_per_site),
+                read_ptr=np.asarray(read_ptr, dtype=np.int32), cost=np.asarray(cost, dtype=np.int64), kinds=kinds)
+
+
+def parity_sample(sw, rec, ops, want_reads=2000):
+    """Compare a sample of whole sites (spread over the sweep, about want_reads reads) with the compiled reference on all
+    host cores: graph_pos, score, uniqueness, strand, CIGAR string.  -> (reads checked, mismatches)"""
+    from oracle import refbind
+    from paragraph_b200 import capi
+    n_sites = len(sw["graphs"])
+    per = max(1, int(len(sw["site"]) / n_sites))
+    pick = sorted(set(np.linspace(0, n_sites - 1, max(1, min(n_sites, want_reads // per))).astype(int).tolist()))
+    sub = synth.sweep_subset(sw, pick)
+    pk = dict(n_sites=len(pick), blob=None)
+    node_ptr, blob, off, edge_ptr, ef, et = capi.Context.pack_graphs(sub["graphs"])
+    pk.update(node_ptr=node_ptr, blob=blob, off=off, edge_ptr=edge_ptr, ef=ef, et=et, read_ptr=sub["read_ptr"],
+              rblob=sub["blob"].tobytes(), roff=sub["off"], n_reads=len(sub["site"]))
+    if refbind.have_ref():
+        exp, ecg = refbind.ref_align_sites_packed(pk, threads=os.cpu_count() or 8, cigar_stride=512)
+    else:
+        return 0, 0
+    bad, at = 0, 0
+    for s in pick:
+        for i in range(sw["read_ptr"][s], sw["read_ptr"][s + 1]):
+            r, e = rec[i], exp[at]
+            c = capi.format_cigar(r, ops).encode()
+            if (r["graph_pos"], r["score"], r["unique"], r["chose_reverse"]) != (e[0], e[1], e[2], e[4]) \
+                    or r["status"] != 0 or len(c) != e[5] or c != ecg[at, :len(c)].tobytes():
+                bad += 1
+            at += 1
+    return at, bad
+
+
+def shape_leg(capi, torch, device, name, sw, reps=5):
+    """One BASELINE.json shape at full size on one GPU: graphs resident (registered once), then
+    e2e = pg_align_batch with host (page-locked) buffers per pass; kernel-phase times from a PG_SPLIT=1 context."""
+    n_reads, cells = len(sw["site"]), int(sw["cost"].sum())
+    packed = capi.Context.pack_graphs(sw["graphs"])
+    pb, po = capi.PinnedArray(sw["blob"].shape, np.uint8), capi.PinnedArray(sw["off"].shape, np.int32)
+    pb.array[:], po.array[:] = sw["blob"], sw["off"]
+    out = {}
+    ctx = capi.Context(device)
+    t0 = time.perf_counter()
+    ctx.add_graphs(packed=packed)
+    reg_ms = (time.perf_counter() - t0) * 1e3
+    for _ in range(2):
+        ctx.align_packed(pb.array, po.array, sw["site"])
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rec, ops = ctx.align_packed(pb.array, po.array, sw["site"])
+        ts.append(time.perf_counter() - t0)
+    e2e_s = float(np.median(ts))
+    checked, bad = parity_sample(sw, rec, ops)
+    ctx.close()
+    os.environ["PG_SPLIT"] = "1"
+    ctx1 = capi.Context(device)
+    os.environ.pop("PG_SPLIT")
+    ctx1.add_graphs(packed=packed)
+    ctx1.upload(pb.array, po.array, sw["site"])
+    for _ in range(2):
+        ctx1.run()
+    f, t = [], []
+    for _ in range(3):
+        ctx1.run()
+        ctx1.download()
+        s = ctx1.stats()
+        f.append(s["fill_ms"])
+        t.append(s["trace_ms"])
+    ctx1.close()
+    fill_ms, trace_ms = float(np.median(f)), float(np.median(t))
+    out.update(sites=len(sw["graphs"]), reads=n_reads, cells=cells,
+               e2e=dict(value=round(n_reads / e2e_s, 1), unit="reads/s", ms=round(e2e_s * 1e3, 3),
+                        h2d_bytes=int(sw["blob"].nbytes + sw["off"].nbytes + sw["site"].nbytes),
+                        d2h_bytes=int(rec.nbytes + ops.nbytes + 8)),
+               register_graphs_ms=round(reg_ms, 3), fill_ms=round(fill_ms, 3), trace_ms=round(trace_ms, 3),
+               fill_tcell_per_s=round(cells / fill_ms / 1e9, 3), kernels_tcell_per_s=round(cells / (fill_ms + trace_ms) / 1e9, 3),
+               parity=dict(reads_checked=checked, mismatches=bad, against="oracle/_ref on all host cores; every read of "
+                           "these shapes is compared in tests/test_gpu_configs.py"))
+    return out
+
+
+def sweep_leg(capi, torch, dist, multigpu, rank, world, device, reps=3):
+    """The fixed 10 000-site config-4 sweep (vcf2paragraph-shaped DEL / INS / DUP / INV graphs, 30x 150 bp), LPT-sharded
+    over the ranks: strong scaling.  A timed pass = register this rank's graphs (pg_add_graphs, incl. packing them),
+    upload the reads, align, download records + CIGARs, reduce them to per-site summaries and gather those on rank 0.
+    No data-path collective; time = max over ranks between two barriers."""
+    sw = synth.packed_sweep(seed=44, n_sites=SWEEP_SITES)
+    shards = multigpu.partition_sites([int(c) for c in sw["cost"]], world)
+    mine = shards[rank]
+    sub = synth.sweep_subset(sw, mine)
+    pb, po = capi.PinnedArray(sub["blob"].shape, np.uint8), capi.PinnedArray(sub["off"].shape, np.int32)
+    pb.array[:], po.array[:] = sub["blob"], sub["off"]
+    ctx = capi.Context(device)
+    counts = np.diff(sub["read_ptr"])
+
+    def one_pass():
+        ctx.clear_graphs()
+        ctx.add_graphs(sub["graphs"])
+        rec, ops = ctx.align_packed(pb.array, po.array, sub["site"])
+        uniq = np.add.reduceat(rec["unique"].astype(np.int64), sub["read_ptr"][:-1]) if len(rec) else np.zeros(0, np.int64)
+        score = np.add.reduceat(rec["score"].astype(np.int64), sub["read_ptr"][:-1]) if len(rec) else np.zeros(0, np.int64)
+        local = dict(sites=np.asarray(mine, dtype=np.int32), unique=uniq, score_sum=score, reads=counts, n_ops=len(ops))
+        if world > 1:
+            bucket = [None] * world if rank == 0 else None
+            dist.gather_object(local, bucket, dst=0)
+            return bucket
+        return [local]
+
+    one_pass()
+    times, phases = [], None
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        merged = one_pass()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        times.append(float(dt[0]))
+    # where a pass spends its time on this rank (untimed extra pass, phases measured one by one)
+    t0 = time.perf_counter()
+    ctx.clear_graphs()
+    packed = capi.Context.pack_graphs(sub["graphs"])
+    t1 = time.perf_counter()
+    ctx.add_graphs(packed=packed)
+    t2 = time.perf_counter()
+    ctx.align_packed(pb.array, po.array, sub["site"])
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    phases = dict(pack_graphs_ms=round((t1 - t0) * 1e3, 2), register_ms=round((t2 - t1) * 1e3, 2),
+                  upload_align_download_ms=round((t3 - t2) * 1e3, 2))
+    ctx.close()
+    if rank != 0:
+        return None
+    n_sites = sum(len(m["sites"]) for m in merged)
+    n_reads = int(sum(int(m["reads"].sum()) for m in merged))
+    best = min(times)
+    loads = [sum(int(sw["cost"][i]) for i in p) for p in shards]
+    return dict(what="fixed %d-site config-4 sweep (vcf2paragraph-shaped DEL/INS/DUP/INV), LPT shards over %d rank(s); a pass "
+                     "registers the rank's graphs, uploads, aligns, downloads and gathers per-site summaries" % (SWEEP_SITES, world),
+                scaling="strong", n_gpus=world, sites=n_sites, reads=n_reads, seconds=round(best, 5),
+                reads_per_s=round(n_reads / best, 1), sites_per_s=round(n_sites / best, 1),
+                cells=int(sw["cost"].sum()), tcell_per_s=round(float(sw["cost"].sum()) / best / 1e12, 3),
+                load_imbalance=round(max(loads) / (sum(loads) / world), 4), unique_reads=int(sum(int(m["unique"].sum()) for m in merged)),
+                rank0_phases=phases, passes=[round(t, 5) for t in times])
+
+
+def mirror_legs(device, steps):
+    """The C++ drop-in surface (tools/cpp/bench_mirror.cpp over paragraph_b200/csrc/host/pg_grm.hh): one process per leg on
+    this GPU.  alignReads: config 2 through pgb::grm::alignReads; pipeline: 200 config-4-shaped sites through SitePipeline
+    with a per-site read producer (align + filters + counts on the device)."""
+    exe = os.path.join(ROOT, "tools", "cpp", "bench_mirror")
+    if not os.path.exists(exe):
+        return dict(error="tools/cpp/bench_mirror is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    out = {}
+    ncpu = os.cpu_count() or 1
+    threads = max(1, min(16, ncpu))
+    with tempfile.TemporaryDirectory() as tmp:
+        nodes, edges, reads = workload(0)
+        f2 = os.path.join(tmp, "config2.txt")
+        synth.write_workload_file(f2, [("DEL", nodes, edges, reads)])
+        sw = synth.packed_sweep(seed=4, n_sites=1250)
+        f4 = os.path.join(tmp, "config4_share.txt")
+        synth.write_workload_file(f4, synth.sweep_as_site_list(sw))
+        for key, path, mode, st in (("alignReads_config2", f2, "alignReads", steps), ("pipeline_config4_share", f4, "pipeline", 5)):
+            for th in sorted({1, threads}):
+                r = subprocess.run([exe, path, mode, str(st), "2", str(th), str(device)], capture_output=True, text=True, timeout=600)
+                if r.returncode != 0:
+                    out["%s_t%d" % (key, th)] = dict(error=r.stderr.strip()[-300:])
+                    continue
+                d = json.loads(r.stdout)
+                out["%s_t%d" % (key, th)] = dict(value=d["reads_per_s"], unit="reads/s", host_threads=th, reads=d["reads"],
+                                                sites=d["sites"], kept=d["kept"], seconds=d["seconds"],
+                                                producer_seconds=d["producer_seconds"])
+    out["what"] = ("alignReads: pgb::grm::alignReads(graph, paths, vector<unique_ptr<Read>>, NonUniq filter, gssw stage) per "
+                   "step = pack + H2D + kernels + D2H + applyRecord (reverse complement, quals, CIGAR string) + filter + "
+                   "MAPPED-only swap; pipeline: SitePipeline::addSite per site with the site's Read objects built inside the "
+                   "timed region (stand-in for extractReads), alignAndCount on two engines; host threads = the `threads` "
+                   "argument of grm::alignReads")
+    return out
 
 
 def main():
@@ -172,18 +467,30 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-legs", action="store_true", help="headline only (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         return bench_reference(args)
 
-    import torch
-    import torch.distributed as dist
-    from paragraph_b200 import capi
-
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    nodes, edges, reads = workload(rank)
+    # the CPU baseline first: its process pool forks before this process holds a CUDA context
+    base = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            base = cpu_baseline(nodes, edges, reads)
+        except Exception as e:  # the baseline is reported, never required for the GPU number
+            base = dict(value=None, error=str(e))
+    elif not args.no_cpu_baseline:
+        base = dict(value=None, note="measured at N=1 only")
+
+    import torch
+    import torch.distributed as dist
+    from paragraph_b200 import capi, multigpu
+
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; paragraph_b200 has no CPU fallback (use --impl reference "
                          "for the CPU arm)")
@@ -192,7 +499,6 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    nodes, edges, reads = workload(rank)
     ctx = capi.Context(local_rank)
     # a dedicated (non-default) torch stream: the kernels are launched on it through the C-ABI and the CUDA events
     # below are recorded on the same stream
@@ -319,6 +625,28 @@ def main():
     clocks = sampler.stop()
     cnt_d2h = int(cnt["node_counts"].shape[0] * 16 + cnt["edge_counts"].shape[0] * 16
                   + sum(16 + 16 * v.shape[0] for v in cnt["families"].values()))
+    ctx.close()
+
+    # ---------------- the config-4 sweep, sharded over the ranks (every N), and the other shapes / the C++ surface (N = 1)
+    sweep = configs = mirror = None
+    if not args.no_extra_legs:
+        try:
+            sweep = sweep_leg(capi, torch, dist, multigpu, rank, world, local_rank)
+        except Exception as e:
+            sweep = dict(error=repr(e))
+        if world == 1:
+            configs = {}
+            for name, make in (("config3", lambda: synth.packed_sweep(seed=3, n_sites=1000, kinds=("DEL", "INS"), shaped=False)),
+                               ("config4_share", lambda: synth.packed_sweep(seed=4, n_sites=1250)),
+                               ("config5", config5_sweep)):
+                try:
+                    configs[name] = shape_leg(capi, torch, local_rank, name, make())
+                except Exception as e:
+                    configs[name] = dict(error=repr(e))
+            try:
+                mirror = mirror_legs(local_rank, args.steps)
+            except Exception as e:
+                mirror = dict(error=repr(e))
 
     t = torch.tensor([total_ms, e2e_s * 1e3, cnt_s * 1e3, casc_s * 1e3, two_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -334,15 +662,44 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        # dominant kernel = pg_fill_kernel: DPX-issue roofline.  Peak lane-op rate measured with
-        # tools/ubench/dpx_ubench.cu on this pool: 63.2 packed-int16 DPX lane-ops / clk / SM.
+        # Dominant kernel = pg_fill_kernel.  Roofline = the ALU pipe (packed-int16 DPX and the other integer instructions
+        # issue there): EXECUTED ALU-pipe warp instructions of the step's fill launches (counted by ncu on this fixed
+        # workload, profiles/) / the fill phase's live duration, against the pipe's issue rate.  Since the speculative
+        # dead blocks the kernel no longer executes a fixed number of operations per cell, so the algorithmic cell rate
+        # is reported beside it, not as the fraction.
         sm_max = (clocks.get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0)
-        dpx_peak = 63.2 * 148 * sm_max * 1e6                     # lane-ops/s
-        peak_cells = dpx_peak * 2.0 / DPX_SLOTS_PER_CELL_PAIR   # cell updates/s
         fill_ms = st["fill_ms"]
+        prof = step_profile()
         ach_cells = READS_PER_SITE * CELLS_PER_READ / (fill_ms * 1e-3) if fill_ms > 0 else 0.0
+        dpx_peak_cells = 63.2 * 148 * sm_max * 1e6 * 2.0 / DPX_SLOTS_PER_CELL_PAIR
+        roof = dict(bound="alu", kernel="pg_fill_kernel<5,32> (fill phase of a step: forward-graph launch + plan / pair + "
+                                        "paired reversed-graph launches, run back to back)",
+                    note="integer ALU pipe (packed-int16 DPX): the max-plus recurrence is neither HBM-bound (roofline_hbm) nor "
+                         "a tensor-core contraction (SURVEY.md 8d, DESIGN.md 4)",
+                    algorithmic_gcell_per_s=round(ach_cells / 1e9, 1),
+                    full_recurrence_peak_gcell_per_s=round(dpx_peak_cells / 1e9, 1),
+                    algorithmic_over_full_recurrence_peak=round(ach_cells / dpx_peak_cells, 4),
+                    algorithmic_note="4 L G cells per read / fill-phase time; the denominator is the issue-rate ceiling of the "
+                                     "FULL recurrence (5 issue slots per packed cell pair, tools/ubench/dpx_ubench.cu: 63.2 "
+                                     "lane-ops/clk/SM); rev_plan skips a quarter of the fills and dead blocks run a one-operation "
+                                     "step, so this ratio may pass 1 and is not the roofline fraction")
+        if prof and fill_ms > 0:
+            peak_inst = prof["alu_peak_inst_per_sm_cycle"] * 148 * sm_max * 1e6
+            ach_inst = prof["fill_alu_inst"] / (fill_ms * 1e-3)
+            roof.update(achieved=round(ach_inst / 1e9, 1), peak=round(peak_inst / 1e9, 1), unit="G ALU-pipe warp-inst/s",
+                        frac=round(ach_inst / peak_inst, 4),
+                        traffic=dict(dram_bytes_per_step=prof["fill_dram_bytes"], launches=prof["fill_launches"],
+                                     algorithmic_bytes_per_step=READS_PER_SITE * 200, source=prof["source"]),
+                        alu_inst_per_step=int(prof["fill_alu_inst"]), inst_per_step=int(prof["fill_inst"]),
+                        ncu_fill_duration_us=round(prof["fill_duration_us"], 1), profile=prof["source"],
+                        peak_source="ALU pipe issue rate: %.1f warp-inst/clk/SM (B300_MICROARCH.md pipe rates; ncu's own "
+                                    "pct_of_peak for this pipe uses the same ceiling) x 148 SMs x clocks.max.sm; instruction "
+                                    "count: %s" % (prof["alu_peak_inst_per_sm_cycle"], prof["alu_inst_source"]))
+        else:
+            roof.update(achieved=None, peak=None, unit="G ALU-pipe warp-inst/s", frac=None, traffic=None,
+                        note2="no profiles/r*_step_ncu.json found")
         line = dict(
-            metric="reads/sec to graph (150bp, DEL/INS); bit-exact score+CIGAR", value=round(value, 1), unit="reads/s",
+            metric=METRIC, value=round(value, 1), unit="reads/s",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=round(total_ms / args.steps, 4),
             higher_is_better=True, scaling="weak", vs_baseline=None, dtype="int16 (packed x2, DPX)", data="synthetic",
             config=dict(workload=WORKLOAD, reads_per_gpu=READS_PER_SITE, read_len=READ_LEN, graph_cols=G_COLS,
@@ -369,14 +726,7 @@ def main():
                              path_mapped=pst["mapped"], path_anchored=pst["anchored"], reads=READS_PER_SITE,
                              path_ms=round(pst["path_ms"], 4), fill_ms=round(cascade_kernels["fill_ms"], 4),
                              trace_ms=round(cascade_kernels["trace_ms"], 4)),
-            roofline=dict(bound="alu",
-                          note="packed-int16 DPX issue rate of the ALU pipe: the max-plus recurrence is neither HBM-bound "
-                               "(roofline_hbm) nor a tensor-core contraction (SURVEY.md 8d, DESIGN.md 4)",
-                          kernel="pg_fill_kernel<5,32> (fill phase of a step: forward-graph launch + paired reversed-graph launches)", achieved=round(ach_cells / 1e9, 1), peak=round(peak_cells / 1e9, 1),
-                          unit="Gcell/s", frac=round(ach_cells / peak_cells, 4) if peak_cells else None,
-                          traffic=ncu_traffic(),
-                          peak_source="tools/ubench/dpx_ubench.cu on this pool: 63.2 DPX lane-ops/clk/SM x 148 SM x "
-                                      "clocks.max.sm, 2 cells per lane-op, 5 issue slots per cell pair"),
+            roofline=roof,
             roofline_hbm=dict(bound="hbm", achieved=round(READS_PER_SITE * 200 / (fill_ms * 1e-3) / 1e9, 3) if fill_ms > 0 else None,
                               peak=peaks.get("hbm_gbs"), unit="GB/s",
                               frac=round(READS_PER_SITE * 200 / (fill_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 6)
@@ -384,15 +734,15 @@ def main():
                               note="algorithmic traffic ~200 B/read (reads in, records + CIGAR out, SURVEY.md 8d): the path "
                                    "is not HBM-bound; the checkpoint scratch actually written is roofline.traffic"),
             clocks=clocks)
-        if not args.no_cpu_baseline and world == 1:
-            try:
-                line["cpu_baseline"] = cpu_reference(nodes, edges, reads)
-            except Exception as e:  # the baseline is reported, never required for the GPU number
-                line["cpu_baseline"] = dict(value=None, error=str(e))
-        elif not args.no_cpu_baseline:
-            line["cpu_baseline"] = dict(value=None, note="measured at N=1 only")
+        if sweep is not None:
+            line["sweep_config4"] = sweep
+        if configs is not None:
+            line["configs"] = configs
+        if mirror is not None:
+            line["e2e_mirror"] = mirror
+        if base is not None:
+            line["cpu_baseline"] = base
         print(json.dumps(line))
-    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -102,10 +102,34 @@ def ref_align_batch(node_seqs, edges, reads, is_rev=None, flags=AF_ALL, threads=
                           flags & 0xFFFFFFFF, threads, _p(out, C.c_int32), ob, cg, CIGAR_STRIDE)
     res = []
     raw = ob.raw
+    craw = cg.raw  # ONE copy of the buffer (.raw copies: taking it per read made this loop quadratic in the batch size)
     for i in range(n):
-        c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
+        c = craw[i * CIGAR_STRIDE:i * CIGAR_STRIDE + int(out[i][5])].decode()
         res.append(_result_dict(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
     return res
+
+
+class RefBatch:
+    """A graph and a read batch packed once, for TIMING the compiled reference: run(lo, hi, threads) executes
+    pgref_align_batch (GraphAligner::alignRead over reads [lo, hi), `threads` GraphAligners over contiguous chunks like
+    grm::alignReads, Align.cpp:107-153) and returns the seconds spent inside the library call -- no Python per read."""
+
+    def __init__(self, node_seqs, edges, reads):
+        self.lib = ref_lib()
+        self.blob, self.off, self.ef, self.et = pack_graph(node_seqs, edges)
+        self.n_nodes, self.n_edges = len(node_seqs), len(edges)
+        self.rblob, self.roff = pack_reads(reads)
+        self.n = len(reads)
+        self.out = np.zeros((self.n, 6), dtype=np.int32)
+
+    def run(self, lo, hi, threads=1, flags=AF_ALL):
+        import time
+        off = np.ascontiguousarray(self.roff[lo:hi + 1])
+        t0 = time.perf_counter()
+        self.lib.pgref_align_batch(self.n_nodes, self.blob, _p(self.off, C.c_int32), self.n_edges, _p(self.ef, C.c_int32),
+                                   _p(self.et, C.c_int32), hi - lo, self.rblob, _p(off, C.c_int32), None,
+                                   flags & 0xFFFFFFFF, threads, _p(self.out[lo:hi], C.c_int32), None, None, 0)
+        return time.perf_counter() - t0
 
 
 def pack_sites(sites):
@@ -275,8 +299,9 @@ class OracleGraph:
         if rc != 0:
             raise RuntimeError("oracle: pgo_align_batch rc=%d" % rc)
         res, raw = [], ob.raw
+        craw = cg.raw  # one copy (see ref_align_batch)
         for i in range(n):
-            c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
+            c = craw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
             res.append(_result_dict(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
         return res
 
@@ -492,9 +517,10 @@ def ref_path_align_batch(node_seqs, edges, reads, kmer_len=32, is_rev=None):
     if rc != 0:
         raise RuntimeError("reference PathAligner threw")
     raw = ob.raw
+    craw = cg.raw
     res = []
     for i in range(n):
-        c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
+        c = craw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
         res.append(_path_result(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
     return res, tuple(int(x) for x in cnt)
 
@@ -528,9 +554,10 @@ class OraclePathIndex:
         self.lib.pgo_path_align_batch(self.h, n, rblob, _p(roff, C.c_int32), _p(out, C.c_int32), ob, cg, CIGAR_STRIDE,
                                       _p(cnt, C.c_int32))
         raw = ob.raw
+        craw = cg.raw
         res = []
         for i in range(n):
-            c = cg.raw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
+            c = craw[i * CIGAR_STRIDE:(i + 1) * CIGAR_STRIDE].split(b"\0", 1)[0].decode()
             res.append(_path_result(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
         return res, tuple(int(x) for x in cnt)
 

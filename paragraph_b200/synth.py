@@ -472,3 +472,20 @@ def fuzz_reads(rng, nodes, edges, n_reads, min_len=8, max_len=160, lower=0.02, i
 def revcomp_exact(s):
     """graphtools::reverseComplement (SequenceOperations.cpp:66-89): case-sensitive, non-ACGT -> 'N'."""
     return revcomp(s)
+
+
+def write_workload_file(path, site_list):
+    """The text format tools/cpp/bench_mirror.cpp reads: sites = [(kind, nodes, edges, reads)]."""
+    with open(path, "w") as f:
+        f.write("SITES %d\n" % len(site_list))
+        for _, nodes, edges, reads in site_list:
+            f.write("SITE %d %d %d\n" % (len(nodes), len(edges), len(reads)))
+            f.write("\n".join(nodes) + "\n")
+            if edges:
+                f.write("\n".join("%d %d" % (a, b) for a, b in edges) + "\n")
+            if reads:
+                f.write("\n".join(reads) + "\n")
+
+
+def sweep_as_site_list(sw):
+    return [(sw["kinds"][i], sw["graphs"][i][0], sw["graphs"][i][1], sweep_reads(sw, i)) for i in range(len(sw["graphs"]))]

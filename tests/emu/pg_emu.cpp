@@ -18,8 +18,8 @@ using namespace pg;
 
 static long g_rev_rounds = 0, g_rev_reads = 0; // reversed-graph halves rev_plan asked for / reads (see emu_align_one)
 // Speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead) -- what pg_fill_kernel does when built with
-// PG_SPEC_DEAD=1.  Off by default, like in the kernels; pgemu_set_spec(1) switches it on.
-static int g_spec = 0;
+// PG_SPEC_DEAD=1 (the default build).  On by default, like in the kernels; pgemu_set_spec(0) gives the plain fill.
+static int g_spec = 1;
 static long g_spec_pruned = 0;
 extern "C" long pgemu_spec_pruned() { return g_spec_pruned; }
 static long g_spec_blocks[4] = { 0, 0, 0, 0 }; // blocks of SPEC_STEPS steps: run dead, redone, gaps alive, node boundary inside

@@ -118,6 +118,11 @@ def test_emulator_speculative_dead_blocks(built):
     with PG_SPEC_DEAD=1).  Results must not change: golden fixtures, a fuzz over bubble graphs / alphabets / flags
     (2-letter alphabets keep gaps alive almost everywhere, 4-letter ones exercise the dead blocks and the redo), all three
     geometries, and a config-2-shaped batch whose block statistics are the expected ones."""
+    emubind.set_spec(0)  # the plain fill (kernels built with -DPG_SPEC_DEAD=0, kept for A/B)
+    for case in golden_cases():
+        got, _ = emubind.emu_align_batch(case["nodes"], case["edges"], case["reads"], is_rev=case["is_rev"],
+                                         flags=case["flags"])
+        assert strip_status(got) == case["expected"], ("plain", case["name"])
     emubind.set_spec(1)
     try:
         before = emubind.spec_stats()
@@ -171,4 +176,4 @@ def test_emulator_speculative_dead_blocks(built):
         dead2, redone2, alive2, boundary2 = [b - a for a, b in zip(before2, emubind.spec_stats())]
         assert dead2 > dead and alive2 < alive, (dead, alive, dead2, alive2)
     finally:
-        emubind.set_spec(0)
+        emubind.set_spec(1)  # the default, as in the kernels

@@ -4,7 +4,7 @@ import os, subprocess, sys
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 OUT = os.path.join(ROOT, "ab_build")
 VARIANTS = {
-    "base_u8": [],
+    "base_u8": ["-DPG_SPEC_DEAD=0"],
     "spec_dead": ["-DPG_SPEC_DEAD=1"],  # speculative "no gap alive" blocks (pg_core.cuh: lane_step_dead)
     "spec_prune": ["-DPG_SPEC_DEAD=1", "-DPG_SPEC_PRUNE=1"],  # plus upper-bound pruning of gaps (gap_relevant)
     "spec_dead_4": ["-DPG_SPEC_DEAD=1", "-DPG_SPEC_STEPS=4"],
