@@ -108,6 +108,18 @@ int pgo_path_align_read(const struct pgo_path_index* ix, const char* bases, int 
 int pgo_path_align_batch(const struct pgo_path_index* ix, int n_reads, const char* bases_blob, const int32_t* read_off,
                          int32_t* out8, char* out_bases_blob, char* cigars, int cigar_stride, int32_t* counters3);
 
+/* ---- grm::KmerAligner<K> (oracle/pg_oracle_kmer.c): gapless alignment to the graph's paths, seeded by k-mers ---- */
+struct pgo_kmer_index;
+struct pgo_kmer_index* pgo_kmer_index_create(int n_nodes, const char* blob, const int32_t* off, int n_paths,
+                                             const int32_t* path_ptr, const int32_t* path_nodes, int k);
+void pgo_kmer_index_destroy(struct pgo_kmer_index* ix);
+/* out8 = {status (0 UNMAPPED, 1 MAPPED, 2 BAD_ALIGN = not unique), graph_pos, score, unique, mapq,
+ *         is_graph_reverse_strand, cigar_strlen, 0} */
+int pgo_kmer_align_read(const struct pgo_kmer_index* ix, const char* bases, int L, int is_reverse_strand, int32_t* out8,
+                        char* out_bases, char* cigar, int cigar_cap);
+int pgo_kmer_align_batch(const struct pgo_kmer_index* ix, int n_reads, const char* blob, const int32_t* off,
+                         const uint8_t* is_rev, int32_t* out8, char* out_bases_blob, char* cigars, int cigar_stride);
+
 #ifdef __cplusplus
 }
 #endif

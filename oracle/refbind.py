@@ -69,6 +69,11 @@ def ref_lib():
         lib.pgref_align_sites.restype = C.c_int
         lib.pgref_align_sites.argtypes = [C.c_int, i32p, C.c_char_p, i32p, i32p, i32p, i32p, i32p, C.c_char_p, i32p,
                                           C.POINTER(C.c_uint8), C.c_uint, C.c_int, i32p, C.c_char_p, C.c_char_p, C.c_int]
+        if hasattr(lib, "pgref_kmer_align_batch"):
+            lib.pgref_kmer_align_batch.restype = C.c_int
+            lib.pgref_kmer_align_batch.argtypes = [C.c_int, C.c_char_p, i32p, C.c_int, i32p, i32p, C.c_int, i32p, i32p, C.c_int,
+                                                   C.c_int, C.c_char_p, i32p, C.POINTER(C.c_uint8), i32p, C.c_char_p,
+                                                   C.c_char_p, C.c_int, i32p]
         lib.pgref_gssw_create.restype = C.c_void_p
         lib.pgref_gssw_create.argtypes = lib.pgref_aligner_create.argtypes
         lib.pgref_gssw_destroy.argtypes = [C.c_void_p]
@@ -568,3 +573,99 @@ class OraclePathIndex:
 
     def __del__(self):
         self.close()
+
+
+# ---------------------------------------------------------------- grm::KmerAligner (second stage of the cascade)
+KMER_STATUS = ("unmapped", "mapped", "bad_align")
+
+
+def pack_paths(paths):
+    """[[node ids], ...] -> (path_ptr int32[n+1], path_nodes int32[])"""
+    ptr = np.zeros(len(paths) + 1, dtype=np.int32)
+    ptr[1:] = np.cumsum([len(p) for p in paths])
+    flat = np.ascontiguousarray([v for p in paths for v in p], dtype=np.int32)
+    if flat.size == 0:
+        flat = np.zeros(1, dtype=np.int32)
+    return ptr, flat
+
+
+def _kmer_result(o, bases, cigar):
+    st = KMER_STATUS[int(o[0])]
+    if st == "unmapped":  # nothing was written to the read
+        return dict(status=st)
+    return dict(status=st, pos=int(o[1]), score=int(o[2]), unique=bool(o[3]), mapq=int(o[4]), graph_reverse=bool(o[5]),
+                bases=bases, cigar=cigar)
+
+
+def _kmer_collect(out, ob, cg, roff, n):
+    raw, craw = ob.raw, cg.raw
+    res = []
+    for i in range(n):
+        c = craw[i * CIGAR_STRIDE:i * CIGAR_STRIDE + int(out[i][6])].decode()
+        res.append(_kmer_result(out[i], raw[roff[i]:roff[i + 1]].decode("latin-1"), c))
+    return res
+
+
+def ref_kmer_align_batch(node_seqs, edges, paths, reads, kmer_len=16, is_rev=None):
+    """The reference's KmerAligner<kmer_len> (kmer_len 16 or 10) over a batch -> (result dicts, (attempted, mapped))."""
+    lib = ref_lib()
+    blob, off, ef, et = pack_graph(node_seqs, edges)
+    pptr, pnodes = pack_paths(paths)
+    rblob, roff = pack_reads(reads)
+    n = len(reads)
+    out = np.zeros((max(n, 1), 8), dtype=np.int32)
+    ob = C.create_string_buffer(max(1, len(rblob)))
+    cg = C.create_string_buffer(max(1, n * CIGAR_STRIDE))
+    cnt = np.zeros(2, dtype=np.int32)
+    rv = None if is_rev is None else np.asarray(is_rev, dtype=np.uint8)
+    rc = lib.pgref_kmer_align_batch(len(node_seqs), blob, _p(off, C.c_int32), len(edges), _p(ef, C.c_int32), _p(et, C.c_int32),
+                                    len(paths), _p(pptr, C.c_int32), _p(pnodes, C.c_int32), int(kmer_len), n, rblob,
+                                    _p(roff, C.c_int32), None if rv is None else _p(rv, C.c_uint8), _p(out, C.c_int32), ob, cg,
+                                    CIGAR_STRIDE, _p(cnt, C.c_int32))
+    if rc != 0:
+        raise RuntimeError("reference KmerAligner: rc=%d" % rc)
+    return _kmer_collect(out, ob, cg, roff, n), tuple(int(x) for x in cnt)
+
+
+class OracleKmerIndex:
+    """oracle/pg_oracle_kmer.c: the restatement of grm::KmerAligner<K> (any 2 <= K <= 16)."""
+
+    def __init__(self, node_seqs, edges, paths, kmer_len=16):
+        self.lib = oracle_lib()
+        self.lib.pgo_kmer_index_create.restype = C.c_void_p
+        self.lib.pgo_kmer_index_create.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32),
+                                                   C.POINTER(C.c_int32), C.c_int]
+        self.lib.pgo_kmer_index_destroy.argtypes = [C.c_void_p]
+        self.lib.pgo_kmer_align_batch.restype = C.c_int
+        self.lib.pgo_kmer_align_batch.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8),
+                                                  C.POINTER(C.c_int32), C.c_char_p, C.c_char_p, C.c_int]
+        blob, off, _, _ = pack_graph(node_seqs, edges)
+        pptr, pnodes = pack_paths(paths)
+        self.h = self.lib.pgo_kmer_index_create(len(node_seqs), blob, _p(off, C.c_int32), len(paths), _p(pptr, C.c_int32),
+                                                _p(pnodes, C.c_int32), int(kmer_len))
+        if not self.h:
+            raise RuntimeError("oracle: pgo_kmer_index_create failed")
+
+    def align_batch(self, reads, is_rev=None):
+        rblob, roff = pack_reads(reads)
+        n = len(reads)
+        out = np.zeros((max(n, 1), 8), dtype=np.int32)
+        ob = C.create_string_buffer(max(1, len(rblob)))
+        cg = C.create_string_buffer(max(1, n * CIGAR_STRIDE))
+        rv = None if is_rev is None else np.asarray(is_rev, dtype=np.uint8)
+        rc = self.lib.pgo_kmer_align_batch(self.h, n, rblob, _p(roff, C.c_int32), None if rv is None else _p(rv, C.c_uint8),
+                                           _p(out, C.c_int32), ob, cg, CIGAR_STRIDE)
+        if rc != 0:
+            raise RuntimeError("oracle: pgo_kmer_align_batch rc=%d" % rc)
+        return _kmer_collect(out, ob, cg, roff, n)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pgo_kmer_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

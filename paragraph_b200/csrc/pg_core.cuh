@@ -227,8 +227,16 @@ template <int R, int W = 32> struct Sizes
     static constexpr bool WIDE = is_wide(R, W);
     // checkpoint words per lane: Hp[R], E[R], hupPrev, foutLast -- 4 byte values per word, or (WIDE) the 2R+2 packed registers as they are
     static constexpr int CKW = WIDE ? 2 * R + 2 : R + 1;
-    static constexpr int INFOW = WIDE ? 4 : 3; // words per (node, lane) of the node-maximum table
-    static constexpr int LASTW = 2 * R;    // node last column: H[R], E leaving it [R] (= the seed of its successors)
+    static constexpr int INFOW = WIDE ? 4 : 3; // node maximum, first step per half [, region maximum]
+    // The node table: ONE ROW per (node, lane) = that lane's part of the node's last column -- H and the E leaving it,
+    // i.e. the seed of the node's successors -- followed by the lane's node maximum and the steps it was first
+    // reached at.  Byte-packed like the checkpoints unless WIDE: word r = (H.lo, H.hi, E.lo, E.hi) of row r (H >= 0
+    // always, a negative E is as good as 0).  Rows are lane-major and a multiple of four words long, so that the lane
+    // that reaches a node boundary stores its row with two 128-bit stores (R = 5: 5 + 3 = 8 words; before: 13 scalar
+    // stores into [node][2R + 3][lane] tables that took 1.6 KB of shared memory per node instead of 1 KB -- graphs
+    // with many nodes keep more warps resident).
+    static constexpr int SEEDV = WIDE ? 2 * R : R;          // value words of a row
+    static constexpr int ROWW = (SEEDV + INFOW + 3) & ~3;   // row stride in words
     static constexpr int ROWS = W * R;
     static constexpr int NT = 32 / W;      // tasks per warp
 };
@@ -595,38 +603,111 @@ PG_HD void region_begin(LaneCtl& c, const GraphView& g, int L, int lane)
     c.Mreg = pk(-MBIAS, -MBIAS);
 }
 
+// row of (node n, lane) in a node table
+template <int R, int W> PG_HD uint32_t* node_row(uint32_t* tab, int n, int lane) { return tab + ((size_t)n * W + lane) * Sizes<R, W>::ROWW; }
+template <int R, int W> PG_HD const uint32_t* node_row(const uint32_t* tab, int n, int lane)
+{
+    return tab + ((size_t)n * W + lane) * Sizes<R, W>::ROWW;
+}
+PG_HD uint32_t ck_pack(uint32_t v0, uint32_t v1);
+PG_HD void ck_unpack(uint32_t w, uint32_t& v0, uint32_t& v1);
+// ck_pack of (H, E) when H is known to be >= 0 in both halves (H = max(t, F) with t >= 0): only E needs the clamp
+PG_HD uint32_t pack_he(uint32_t h, uint32_t e)
+{
+    e = max2(e, 0u);
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(h, e, 0x6420);
+#else
+    return (h & 0xffu) | (((h >> 16) & 0xffu) << 8) | ((e & 0xffu) << 16) | (((e >> 16) & 0xffu) << 24);
+#endif
+}
+
+// fold the last column saved in `row` into (H, E): element-wise maximum
+template <int R, int W> PG_HD void seed_max(const uint32_t* row, uint32_t* H, uint32_t* E)
+{
+    constexpr int V = Sizes<R, W>::SEEDV;
+    uint32_t v[V];
+#if defined(__CUDA_ARCH__)
+    static_assert(Sizes<R, W>::ROWW % 4 == 0, "rows are read with 128-bit loads");
+PG_UNROLL
+    for (int x = 0; x < (V + 3) / 4; ++x) // (the words after the values belong to the same row: reading them is harmless)
+    {
+        const uint4 q = reinterpret_cast<const uint4*>(row)[x];
+        if (4 * x + 0 < V) v[4 * x + 0] = q.x;
+        if (4 * x + 1 < V) v[4 * x + 1] = q.y;
+        if (4 * x + 2 < V) v[4 * x + 2] = q.z;
+        if (4 * x + 3 < V) v[4 * x + 3] = q.w;
+    }
+#else
+    for (int x = 0; x < V; ++x)
+        v[x] = row[x];
+#endif
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+    {
+        uint32_t h, e;
+        if (Sizes<R, W>::WIDE)
+        {
+            h = v[r];
+            e = v[R + r];
+        }
+        else
+            ck_unpack(v[r], h, e);
+        H[r] = max2(H[r], h);
+        E[r] = max2(E[r], e);
+    }
+}
+// H of the bottom row of `row`'s lane (the diagonal into the first row of the lane below)
+template <int R, int W> PG_HD uint32_t seed_bottom_h(const uint32_t* row)
+{
+    if (Sizes<R, W>::WIDE)
+        return row[R - 1];
+    uint32_t h, e;
+    ck_unpack(row[R - 1], h, e);
+    return h;
+}
+
 // Node boundary handling at the top of a step (rare, per lane: lanes reach a boundary at different steps).
-//   FILL = true  (fill kernel): save the finished node's last column (H, E leaving it) into the warp-private
-//                shared-memory seed table and the lane's node maximum / first step into infoS; then load the next
-//                node's seed from the seed table.  (The fill kernel copies the seed table to HBM once, at the end
-//                of a forward-graph task, for the traceback.)
+//   FILL = true  (fill kernel): save the finished node's row (last column H, E leaving it, the lane's node maximum /
+//                first steps) into the warp-private node table in shared memory; then load the next node's seed.
+//                (The fill kernel copies the table to HBM once, at the end of a forward-graph task, for the traceback.)
 //   FILL = false (tile recomputation in the traceback kernel): only load the next node's seed, from that copy.
 // Seed of a node = element-wise max over its predecessors' last columns (gssw_create_seed_byte,
 // gssw.c:3897-3931), zeros for a source; if the only predecessor is the node just finished the state
-// simply carries over.  The diagonal into this lane's first row comes from the seed row just above it,
-// i.e. lane-1's last word of each predecessor (written by lane-1 at least one step earlier).
+// simply carries over, and when it is one of several the registers stand for it (they ARE its last column).  The
+// diagonal into this lane's first row comes from the seed row just above it, i.e. the bottom row of lane-1's row of
+// each predecessor (written by lane-1 at least one step earlier).
 template <int R, bool FILL, int W = 32>
-PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* seeds, uint32_t* infoS,
-                           int L = 0)
+PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane, uint32_t* tab, int L = 0)
 {
-    constexpr int IW = Sizes<R, W>::INFOW;
+    constexpr int V = Sizes<R, W>::SEEDV, RW = Sizes<R, W>::ROWW;
     if (c.colsLeft == 0)
     {
         const int n = c.node;
         if (FILL)
         {
+            uint32_t v[RW];
+PG_UNROLL
+            for (int x = 0; x < RW; ++x)
+                v[x] = 0u;
+PG_UNROLL
             for (int r = 0; r < R; ++r)
             {
-                seeds[(n * 2 * R + r) * W + lane] = s.Hp[r];
-                seeds[(n * 2 * R + R + r) * W + lane] = s.E[r];
+                if (Sizes<R, W>::WIDE)
+                {
+                    v[r] = s.Hp[r];
+                    v[R + r] = s.E[r];
+                }
+                else
+                    v[r] = pack_he(s.Hp[r], s.E[r]);
             }
-            infoS[(n * IW + 0) * W + lane] = c.Mnode;
-            infoS[(n * IW + 1) * W + lane] = (uint32_t)c.first[0];
-            infoS[(n * IW + 2) * W + lane] = (uint32_t)c.first[1];
+            v[V + 0] = c.Mnode;
+            v[V + 1] = (uint32_t)c.first[0];
+            v[V + 2] = (uint32_t)c.first[1];
             c.Mnode = pk(-MBIAS, -MBIAS);
             if (Sizes<R, W>::WIDE)
             {
-                infoS[(n * IW + 3) * W + lane] = c.Mreg;
+                v[V + 3] = c.Mreg;
                 c.Mreg = pk(-MBIAS, -MBIAS);
                 c.regLeft = -1;
                 if (n + 1 < g.n_nodes)
@@ -635,6 +716,15 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
                     scan_region(g.node_len[n + 1], L, c.regLeft, part);
                 }
             }
+            uint32_t* row = node_row<R, W>(tab, n, lane);
+#if defined(__CUDA_ARCH__)
+PG_UNROLL
+            for (int x = 0; x < RW / 4; ++x)
+                reinterpret_cast<uint4*>(row)[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+#else
+            for (int x = 0; x < RW; ++x)
+                row[x] = v[x];
+#endif
         }
         c.node = n + 1;
         if (n + 1 < g.n_nodes)
@@ -649,14 +739,22 @@ PG_HD_COLD void node_event(Lane<R>& s, LaneCtl& c, const GraphView& g, int lane,
 PG_NOUNROLL
                 for (int e = p0; e < p1; ++e)
                 {
-                    const uint32_t* src = seeds + g.pred_idx[e] * (2 * R * W);
-                    for (int r = 0; r < R; ++r)
+                    const int p = g.pred_idx[e];
+                    if (p == n) // the node just finished: its last column is what the registers hold
                     {
-                        H[r] = max2(H[r], src[r * W + lane]);
-                        E[r] = max2(E[r], src[(R + r) * W + lane]);
+PG_UNROLL
+                        for (int r = 0; r < R; ++r)
+                        {
+                            H[r] = max2(H[r], s.Hp[r]);
+                            E[r] = max2(E[r], s.E[r]);
+                        }
+                        hup = max2(hup, s.hupPrev);
+                        continue;
                     }
+                    const uint32_t* src = node_row<R, W>(tab, p, lane);
+                    seed_max<R, W>(src, H, E);
                     if (lane > 0)
-                        hup = max2(hup, src[(R - 1) * W + lane - 1]);
+                        hup = max2(hup, seed_bottom_h<R, W>(src - RW));
                 }
                 for (int r = 0; r < R; ++r)
                 {
@@ -788,8 +886,9 @@ PG_HD void tile_store(uint32_t* tstep, int lane, int blo, const uint32_t* Hc, co
 // ---------------------------------------------------------------------------------------------
 // per-task scratch layout (32-bit words, [..][32 lanes] innermost so that a warp store is one 128 B line)
 // ---------------------------------------------------------------------------------------------
-//   info  [n_nodes][3][32]      : per node and lane: packed node maximum, first step reaching it (half 0, half 1)
-//   last  [n_nodes][2R][32]     : node last column: H, E leaving it (seed)            (forward-graph tasks only)
+//   node table [n_nodes][32][ROWW] : per node and lane one row (Sizes): the node's last column (H, E leaving it = seed),
+//                                  byte-packed, then the packed node maximum and the first step reaching it per half;
+//                                  copied to HBM as `last` by forward-graph tasks
 //   ckpt  [n_ck][R+1][32]       : byte-packed lane state before step c*CK           (forward-graph tasks only)
 PG_HD int num_steps(int G, int W) { return G + W; } // lane W-1 ends column G-1 at step G+W-2; its node event runs at step G+W-1
 PG_HD int num_ckpt(int G, int W) { return (num_steps(G, W) + CK - 1) / CK; }
@@ -815,15 +914,17 @@ PG_HD uint32_t ld_scratch(const uint32_t* p) { return *p; } // warp-private shar
 // the node's matrix only -> the count over the region-restricted maxima (LaneCtl::Mreg, info word 3).
 PG_HD int n_top_rule(int S, int plain, int region) { return S <= BYTE_MAX_SCORE ? plain : (S >= 256 ? 1 : region); }
 
-PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W, int IW = 3)
+template <int R, int W> PG_HD void finalize_task(const uint32_t* tab, int n_nodes, TaskOut& o)
 {
+    constexpr int IW = Sizes<R, W>::INFOW, V = Sizes<R, W>::SEEDV;
+    auto info = [&](int n, int x, int t) { return ld_scratch(node_row<R, W>(tab, n, t) + V + x); };
     for (int h = 0; h < 2; ++h)
     {
         int S = 0;
         for (int n = 0; n < n_nodes; ++n)
             for (int t = 0; t < W; ++t)
             {
-                const int v = half16(ld_scratch(info + (n * IW + 0) * W + t), h) + MBIAS;
+                const int v = half16(info(n, 0, t), h) + MBIAS;
                 if (v > S)
                     S = v;
             }
@@ -833,14 +934,14 @@ PG_HD void finalize_task(const uint32_t* info, int n_nodes, TaskOut& o, int W, i
             bool has = false, hasreg = false;
             for (int t = 0; t < W; ++t)
             {
-                if (IW > 3 && half16(ld_scratch(info + (n * IW + 3) * W + t), h) + MBIAS == S)
+                if (IW > 3 && half16(info(n, 3, t), h) + MBIAS == S)
                     hasreg = true;
-                if (half16(ld_scratch(info + (n * IW + 0) * W + t), h) + MBIAS != S)
+                if (half16(info(n, 0, t), h) + MBIAS != S)
                     continue;
                 has = true;
                 if (mnode == -1 || mnode == n)
                 {
-                    const int step = (int)ld_scratch(info + (n * IW + 1 + h) * W + t);
+                    const int step = (int)info(n, 1 + h, t);
                     if (step - t < bestq)
                     {
                         bestq = step - t;
@@ -1084,6 +1185,19 @@ template <int R> struct TileBuf
     }
 };
 
+// a cell of a node's saved last column (the traceback's cross-node moves): H, and the E leaving it clamped at 0
+template <int R, int W> PG_HD int last_h(const uint32_t* last, int node, int j, int half)
+{
+    const uint32_t w = node_row<R, W>(last, node, j / R)[j % R];
+    return is_wide(R, W) ? half16(w, half) : (int)((w >> (8 * half)) & 0xffu);
+}
+template <int R, int W> PG_HD int last_e(const uint32_t* last, int node, int j, int half)
+{
+    if (is_wide(R, W))
+        return imax0(half16(node_row<R, W>(last, node, j / R)[R + j % R], half));
+    return (int)((node_row<R, W>(last, node, j / R)[j % R] >> (16 + 8 * half)) & 0xffu);
+}
+
 struct Walker // traceback state of one read (lane 0 only)
 {
     int n, i, j;   // current node, column in node, read row
@@ -1220,7 +1334,7 @@ PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const ui
 // (w.need_step set).  Mirrors gssw_alignment_trace_back_byte (gssw.c:1112-1818, final_traceback = 1, no
 // deflections) and the cross-node part of gssw_graph_trace_back_internal (gssw.c:2836-3148, 3486-3528).
 //   g      forward graph view;  chars = upper-cased graph characters (column-indexed like codes)
-//   last   this read's saved node last columns [n_nodes][2R][32] (packed words)
+//   last   this read's node table (rows per (node, lane), Sizes<R, W>::ROWW words: the saved last columns)
 template <int R, int W>
 PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8_t* chars, const uint32_t* last,
                 const uint8_t* bases, int L, int half, const TaskOut& fo, uint32_t* oplog, int oplog_cap, int lane,
@@ -1422,11 +1536,10 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
         for (int e = g.pred_ptr[w.n]; e < g.pred_ptr[w.n + 1]; ++e)
         {
             const int c = g.pred_idx[e];
-            const uint32_t* lc = last + (size_t)c * (2 * R) * W;
             if (w.st == 0)
             {
                 // diagonal source = pred's last column at row j-1 (row -1 never matches: H(0,0) is start or E)
-                const int dsrc = w.j > 0 ? half16(lc[((w.j - 1) % R) * W + (w.j - 1) / R], half) : -1000;
+                const int dsrc = w.j > 0 ? last_h<R, W>(last, c, w.j - 1, half) : -1000;
                 if (w.v == dsrc + s) // gssw.c:2999-3040
                 {
                     best = c;
@@ -1438,7 +1551,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
             }
             else
             {
-                const int hsrc = half16(lc[(w.j % R) * W + w.j / R], half);
+                const int hsrc = last_h<R, W>(last, c, w.j, half);
                 if (w.v == hsrc - GAP_OPEN) // open, gssw.c:3089-3110
                 {
                     best = c;
@@ -1450,7 +1563,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                 // extend: the reference tests v == E_c(last, j) - ge with E *entering* pred's last column
                 // (gssw.c:3122-3136).  Saved is the seed E' = max(E - ge, t - go) >= E - ge, and v >= E' (v is the max
                 // of the seeds), so v == E' is necessary; only then is the exact E read from pred's last-column tile.
-                const int eseed = imax0(half16(lc[(R + w.j % R) * W + w.j / R], half));
+                const int eseed = last_e<R, W>(last, c, w.j, half);
                 if (w.v == eseed)
                 {
                     const int kc = g.node_start[c] + g.node_len[c] - 1 + w.j / R;

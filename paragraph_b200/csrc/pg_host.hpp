@@ -608,7 +608,11 @@ inline void build_path_index(const GraphStore& gs, int k, PathIndexHost& out, in
 }
 
 // per-read scratch sizes in 32-bit words (see pg_core.cuh "per-task scratch layout")
-inline size_t last_words(int max_nodes, int R, int W) { return (size_t)max_nodes * 2 * R * W; }
+inline size_t last_words(int max_nodes, int R, int W) // node table of one read: a row per (node, lane), pg_core.cuh Sizes
+{
+    const int v = is_wide(R, W) ? 2 * R : R, iw = is_wide(R, W) ? 4 : 3;
+    return (size_t)max_nodes * W * (size_t)((v + iw + 3) & ~3);
+}
 inline size_t ckpt_words(int max_G, int R, int W)
 {
     return (size_t)num_ckpt(max_G, W) * (is_wide(R, W) ? 2 * R + 2 : R + 1) * W;

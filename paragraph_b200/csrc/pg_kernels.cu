@@ -169,29 +169,61 @@ template <int W> __device__ __forceinline__ int group_min(int v)
         v = min(v, __shfl_xor_sync(FULL, v, d, W));
     return v;
 }
-template <int W> __device__ __forceinline__ void finalize_task_group(const uint32_t* info, int n_nodes, int gl, TaskOut& o)
+template <int R, int W> __device__ __forceinline__ void finalize_task_group(const uint32_t* tab, int n_nodes, int gl, TaskOut& o)
 {
-    constexpr int INF = 0x7fffffff;
+    constexpr int INF = 0x7fffffff, V = Sizes<R, W>::SEEDV, RW = Sizes<R, W>::ROWW;
+    // this lane's info words (node maximum, first step per half) of node n; rows are lane-major, so the three words of a
+    // lane come with one 128-bit load when they share an aligned quad (R = 5: words 5..7) instead of strided 32-bit ones
+    const uint32_t* row0 = tab + (size_t)gl * RW;
+    auto info3 = [&](int n, uint32_t& m, uint32_t& f0, uint32_t& f1) {
+        const uint32_t* r = row0 + (size_t)n * W * RW;
+        if ((V & 3) == 1) // the quad that starts at V - 1 holds all three
+        {
+            const uint4 q = *reinterpret_cast<const uint4*>(r + V - 1);
+            m = q.y;
+            f0 = q.z;
+            f1 = q.w;
+        }
+        else
+        {
+            m = r[V];
+            f0 = r[V + 1];
+            f1 = r[V + 2];
+        }
+    };
 #pragma unroll
     for (int h = 0; h < 2; ++h)
     {
         int S = 0;
         for (int n = 0; n < n_nodes; ++n)
-            S = max(S, half16(info[(n * 3 + 0) * W + gl], h) + MBIAS);
+        {
+            uint32_t m, f0, f1;
+            info3(n, m, f0, f1);
+            S = max(S, half16(m, h) + MBIAS);
+        }
         S = -group_min<W>(-S);
-        int first = INF;
+        int first = INF, second = INF, key = INF;
         for (int n = n_nodes - 1; n >= 0; --n)
-            if (half16(info[(n * 3 + 0) * W + gl], h) + MBIAS == S)
+        {
+            uint32_t m, f0, f1;
+            info3(n, m, f0, f1);
+            if (half16(m, h) + MBIAS == S)
                 first = n;
+        }
         const int mnode = group_min<W>(first);
-        int second = INF, key = INF;
         if (mnode != INF)
         {
-            for (int n = n_nodes - 1; n > mnode; --n)
-                if (half16(info[(n * 3 + 0) * W + gl], h) + MBIAS == S)
+            for (int n = n_nodes - 1; n >= mnode; --n)
+            {
+                uint32_t m, f0, f1;
+                info3(n, m, f0, f1);
+                if (half16(m, h) + MBIAS != S)
+                    continue;
+                if (n > mnode)
                     second = n;
-            if (half16(info[(mnode * 3 + 0) * W + gl], h) + MBIAS == S)
-                key = (((int)info[(mnode * 3 + 1 + h) * W + gl] - gl) << 5) | gl; // (column, lane): W <= 32
+                else
+                    key = (((int)(h ? f1 : f0) - gl) << 5) | gl; // (column, lane): W <= 32
+            }
         }
         second = group_min<W>(second);
         key = group_min<W>(key);
@@ -223,10 +255,10 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     extern __shared__ uint32_t smem[];
     constexpr int NT = 32 / W; // tasks per warp: a group of W lanes per task
     constexpr bool WIDE = Sizes<R, W>::WIDE; // reads that can score past a byte: wider checkpoints, region maxima
-    constexpr int CKW = Sizes<R, W>::CKW, IW = Sizes<R, W>::INFOW;
+    constexpr int CKW = Sizes<R, W>::CKW, ROWW = Sizes<R, W>::ROWW;
     const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / W, gl = lane % W;
-    const int wpc = blockDim.x >> 5; // warps per CTA: 4, fewer when the seed tables of a many-node graph need the room
+    const int wpc = blockDim.x >> 5; // warps per CTA: 4, fewer when the node tables of a many-node graph need the room
     int n_tasks = a.n_tasks;
     if (a.mode == MODE_PAIRS)
         n_tasks = min(n_tasks, *a.n_rtasks);
@@ -263,9 +295,8 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     }
     const bool active = ltask < n_tasks && !(o == 1 && !(a.flags & AF_REVERSE_GRAPH));
     uint32_t* prof = smem + ((size_t)wic * NT + grp) * a.smem_words_per_task;
-    // [n_nodes_cap][2R][W] seeds, [n_nodes_cap][IW][W] node maxima: warp-private shared memory, or (fallback) HBM
+    // node table [n_nodes_cap][W][ROWW] (pg_core.cuh: Sizes): warp-private shared memory, or (fallback) HBM
     uint32_t* seedS = TABG ? a.tabG + (size_t)(ltask < n_tasks ? ltask : 0) * a.stride_tab : prof + NCODE * R * W;
-    uint32_t* infoS = seedS + a.n_nodes_cap * 2 * R * W;
     TaskOut* to = a.tout + (size_t)rd * 2 + o;
     if (a.mode == MODE_BOTH && !active && ltask < n_tasks && gl == 0)
     {
@@ -276,7 +307,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     const SiteDev sd = a.sites[a.read_site ? a.read_site[rd] : 0];
     // STAGED: the orientation's node tables (lengths, predecessor lists) are copied next to the seed tables, so that
     // the node-boundary code of the hot loop reads shared memory with 32-bit addresses instead of chasing HBM pointers
-    int32_t* tabS = reinterpret_cast<int32_t*>(infoS + a.n_nodes_cap * IW * W);
+    int32_t* tabS = reinterpret_cast<int32_t*>(seedS + a.n_nodes_cap * ROWW * W);
     if (STAGED)
         for (int x = gl; x < sd.tab_ints; x += W)
             tabS[x] = a.gints[sd.tab_off[o] + x];
@@ -361,7 +392,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                     {
                         __syncwarp();
                         if (c.colsLeft == 0)
-                            node_event<R, true, W>(s, c, g, gl, seedS, infoS, L);
+                            node_event<R, true, W>(s, c, g, gl, seedS, L);
                         else
                             --c.colsLeft;
                         uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
@@ -479,7 +510,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
             const int k = kbase + kk;
             __syncwarp();
             if (c.colsLeft == 0) // rare, per lane: node boundary
-                node_event<R, true, W>(s, c, g, gl, seedS, infoS, L);
+                node_event<R, true, W>(s, c, g, gl, seedS, L);
             else
                 --c.colsLeft;
             uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
@@ -499,16 +530,16 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         }
     }
     __syncwarp();
-    if (save) // node last columns for the traceback kernel: one coalesced copy of the seed table
-        for (int x = gl; x < g.n_nodes * 2 * R * W; x += W)
+    if (save) // node last columns for the traceback kernel: one coalesced copy of the node table
+        for (int x = gl; x < g.n_nodes * ROWW * W; x += W)
             last[x] = seedS[x];
     TaskOut t;
     if (!WIDE)
-        finalize_task_group<W>(infoS, g.n_nodes, gl, t); // every lane of the warp takes part (group-wide reductions)
+        finalize_task_group<R, W>(seedS, g.n_nodes, gl, t); // every lane of the warp takes part (group-wide reductions)
     if (active && gl == 0)
     {
         if (WIDE) // long reads: the serial statement, with the 16-bit-mode uniqueness rule (n_top_rule)
-            finalize_task(infoS, g.n_nodes, t, W, IW);
+            finalize_task<R, W>(seedS, g.n_nodes, t);
         if (a.mode == MODE_PAIRS) // all a reversed-graph fill is for: does the top score sit in more than one node?
         {
             a.rv_ntop[rd * 2 + h0] = t.n_top[0];
@@ -652,7 +683,7 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         for (int kk = 0; kk < CK; ++kk)
         {
             if (c.colsLeft == 0)
-                node_event<R, false, W>(s, c, g, gl, const_cast<uint32_t*>(last), nullptr);
+                node_event<R, false, W>(s, c, g, gl, const_cast<uint32_t*>(last));
             else
                 --c.colsLeft;
             uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
@@ -1882,16 +1913,38 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     const size_t s_last = host::last_words(max_nodes, R, W), s_ckpt = host::ckpt_words(max_G, R, W);
     // fill kernel shared memory per task: profile + seed/info tables; fewer warps per CTA for many-node graphs, and
     // beyond that the tables move to HBM
-    const int tab_words = max_nodes * (2 * R + Sizes<R, W>::INFOW) * W;
+    const int tab_words = max_nodes * Sizes<R, W>::ROWW * W; // node table (pg_core.cuh: Sizes)
     // staged column codes (+ 8 bytes for the mbarrier in front, kept 16-byte aligned); graphs over 16 KB are read from L1/L2
     int code_bytes = (int)code_span_bytes(max_G) + 16;
     if (code_bytes > 16 * 1024 + 16 || !c->use_tma)
         code_bytes = 0;
     const int tab_ints_cap = code_bytes ? ((c->graphs.max_tab_ints + 3) & ~3) : 0; // staged with the codes (keeps 16-byte alignment)
     int fill_words = NCODE * R * W + tab_words + tab_ints_cap + code_bytes / 4;
+    // warps per CTA: the count that keeps most warps resident on an SM (shared memory is what limits residency here:
+    // per task the profile + the seed / node-maximum tables of max_nodes nodes + the staged codes).  4 warps per CTA
+    // for the usual 3-node graphs (41 KB per CTA, 5 CTAs); a batch with 9-node graphs (vcf2paragraph-shaped sites) needs
+    // 20 KB per warp -- 4-warp CTAs would leave 2 CTAs = 8 warps on an SM, 1-warp CTAs fit 11.
     int fill_warps = FILL_WARPS;
-    while (fill_warps > 1 && (size_t)fill_warps * NT * fill_words * 4 > 200 * 1024)
-        fill_warps >>= 1;
+    {
+        const size_t sm_bytes = 227 * 1024, per_cta_extra = 1024; // usable shared memory per SM, per-CTA reservation
+        size_t best = 0;
+        for (int w = FILL_WARPS; w >= 1; w >>= 1)
+        {
+            const size_t cta = (size_t)w * NT * fill_words * 4;
+            if (cta > 200 * 1024)
+                continue;
+            const size_t resident = std::min<size_t>(32, sm_bytes / (cta + per_cta_extra)) * (size_t)w;
+            if (resident > best)
+            {
+                best = resident;
+                fill_warps = w;
+            }
+        }
+        if (const char* e = getenv("PG_FILL_WARPS_RT")) // A/B
+            fill_warps = std::max(1, std::min(FILL_WARPS, atoi(e)));
+        while (fill_warps > 1 && (size_t)fill_warps * NT * fill_words * 4 > 200 * 1024)
+            fill_warps >>= 1;
+    }
     bool tab_global = false;
     if ((size_t)fill_warps * NT * fill_words * 4 > 200 * 1024 || getenv("PG_FORCE_TABG"))
     {

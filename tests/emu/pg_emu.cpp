@@ -43,11 +43,11 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
               std::vector<uint32_t>& last, std::vector<uint32_t>& ckpt, TaskOut& out)
 {
     std::vector<uint32_t> prof((size_t)NCODE * R * W);
-    std::vector<uint32_t> seedS((size_t)g.n_nodes * 2 * R * W, 0);
+    std::vector<uint32_t> seedS((size_t)g.n_nodes * Sizes<R, W>::ROWW * W, 0); // node table (pg_core.cuh: Sizes)
     for (int t = 0; t < W; ++t)
         build_profile<R, W>(prof.data(), bases, L, orient, t);
     constexpr bool WIDE = Sizes<R, W>::WIDE;
-    constexpr int CKW = Sizes<R, W>::CKW, IW = Sizes<R, W>::INFOW;
+    constexpr int CKW = Sizes<R, W>::CKW;
     Lane<R> s[W];
     LaneCtl c[W];
     for (int t = 0; t < W; ++t)
@@ -57,7 +57,6 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
         if (WIDE)
             region_begin(c[t], g, L, t);
     }
-    info.assign((size_t)g.n_nodes * IW * W, 0);
     if (save_trace)
         ckpt.assign((size_t)num_ckpt(g.G, W) * CKW * W, 0);
     const int nck = num_ckpt(g.G, W);
@@ -155,7 +154,7 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
         }
         for (int t = 0; t < W; ++t) // events read what lane t-1 wrote at an EARLIER step only
             if (c[t].colsLeft == 0)
-                node_event<R, true, W>(s[t], c[t], g, t, seedS.data(), info.data(), L);
+                node_event<R, true, W>(s[t], c[t], g, t, seedS.data(), L);
             else
                 --c[t].colsLeft;
         uint32_t rh[W], rf[W];
@@ -179,7 +178,7 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
     }
     if (save_trace)
         last = seedS; // the kernel copies its shared-memory seed table to HBM at the end of a forward-graph task
-    finalize_task(info.data(), g.n_nodes, out, W, IW);
+    finalize_task<R, W>(seedS.data(), g.n_nodes, out);
 }
 
 template <int R, int W>
@@ -198,7 +197,7 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
         const int k = T * CK + kk;
         for (int t = 0; t < W; ++t)
             if (c[t].colsLeft == 0)
-                node_event<R, false, W>(s[t], c[t], g, t, last.data(), nullptr);
+                node_event<R, false, W>(s[t], c[t], g, t, last.data());
             else
                 --c[t].colsLeft;
         uint32_t rh[W], rf[W];

@@ -459,8 +459,14 @@ def test_staged_api_is_idempotent_with_second_chance(ctx):
     from test_path_oracle import path_cases
     rng = np.random.default_rng(53)
     flipped = 0
+    # a bubble whose two branches carry the same sequence: a read across it matches two paths exactly (not unique), and
+    # given reverse-complemented it is the reverse strand that matches -> second chance with flipped bases
+    lf, mid, rf = synth.random_seq(rng, 60), synth.random_seq(rng, 40), synth.random_seq(rng, 60)
+    twin = ([lf, mid, mid, rf], [(0, 1), (0, 2), (1, 3), (2, 3)])
+    hap = lf + mid + rf
+    twin_reads = [synth.revcomp(hap[i:i + 100]) for i in range(0, 60, 7)] + [hap[i:i + 100] for i in range(0, 60, 11)]
     try:
-        for nodes, edges, reads, k in path_cases(rng, 60):
+        for nodes, edges, reads, k in [(twin[0], twin[1], twin_reads, 16)] + list(path_cases(rng, 60)):
             ctx.clear_graphs()
             ctx.add_graph(nodes, edges)
             ctx.set_stages(k, True, True)
