@@ -34,7 +34,10 @@ extern "C" {
 /* pg_record::mapped_by: the stage of grm::CompositeAligner that mapped the read */
 #define PG_STAGE_GSSW_ID 0
 #define PG_STAGE_PATH_ID 1
-#define PG_STAGE_GSSW_REV_ID 2 /* gssw, after the exact-match stage had reverse-complemented the bases (second chance) */
+#define PG_STAGE_GSSW_REV_ID 2 /* gssw, after ONE earlier stage had reverse-complemented the bases (second chance) */
+#define PG_STAGE_KMER_ID 3     /* grm::KmerAligner (pg_set_kmer_stage) */
+#define PG_STAGE_KMER_REV_ID 4 /* KmerAligner, after the exact-match stage had reverse-complemented the bases */
+#define PG_STAGE_GSSW_REV2_ID 5 /* gssw, after both earlier stages had reverse-complemented the bases */
 
 /* GraphAligner alignment flags (src/c++/include/grm/GraphAligner.hh:64-67) */
 #define PG_AF_CIGAR 0x01u
@@ -64,8 +67,10 @@ typedef struct pg_record
                           strand differently: gssw -> is_graph_reverse_strand = is_reverse_strand != chose_reverse,
                           bases reverse-complemented and quals reversed if chose_reverse (GraphAligner.cpp:358-378);
                           PathAligner -> is_graph_reverse_strand = chose_reverse, bases reverse-complemented, quals
-                          untouched (PathAligner.cpp:124-135); GSSW_REV -> as gssw, applied to bases that PathAligner
-                          had already reverse-complemented once */
+                          untouched (PathAligner.cpp:124-135); KmerAligner -> is_graph_reverse_strand =
+                          is_reverse_strand != chose_reverse, bases reverse-complemented, quals untouched
+                          (KmerAligner.cpp:452-466); the _REV / _REV2 ids -> the same, applied to bases that one / two
+                          earlier stages had already reverse-complemented (graphtools::reverseComplement each time) */
     uint32_t cigar_off;
     uint32_t cigar_len;
 } pg_record;
@@ -238,11 +243,26 @@ int pg_count_stats(const pg_ctx* ctx, uint64_t* kernel_launches, float* last_cou
  *                       match itself (what the cascade does with a null filter); a host adapter with an arbitrary
  *                       filter callback re-submits rejected reads itself (pg_grm.hh).
  * Default: path_kmer_len = 0, graph_matching = 1 (what grmpy runs: src/c++/main/grmpy.cpp:69-72).  The KmerAligner
- * and KlibAligner stages are not built. */
+ * stage is pg_set_kmer_stage below; the KlibAligner stage is not built. */
 int pg_set_stages(pg_ctx* ctx, int32_t path_kmer_len, int32_t graph_matching, int32_t nonuniq_second_chance);
 /* counters4 = {attempted, anchored, mapped} of the last batch (PathAligner::attempted/anchored/mapped,
  * PathAligner.hh:66-68) + the host time in microseconds of the last index build; path_ms = the stage's device time. */
 int pg_path_stats(pg_ctx* ctx, uint64_t* counters4, float* path_ms);
+
+/* ---- k-mer stage: grm::KmerAligner<K> (src/c++/lib/grm/KmerAligner.cpp; CompositeAligner.cpp:105-126, between the
+ * exact-match stage and gssw; off by default in both CLIs, main/grmpy.cpp:72) ------------------------------------------
+ * Gapless alignment of the read, on both strands, to the sequence of one of the site's PATHS: offsets proposed by shared
+ * k-mers, at most two mismatches; score = matching bases, soft clips where the path is 'N' (N-filled source / sink),
+ * unique unless an equally good candidate gives a different (position, CIGAR) -- then the read goes on to gssw with the
+ * bases KmerAligner left behind, like the reference's BAD_ALIGN (pickBest, KmerAligner.cpp:479-517).  Bit-exact incl.
+ * the order libstdc++'s heap keeps equal candidates in (oracle/pg_oracle_kmer.c). */
+/* The paths of a site's graph JSON (grm::pathsFromJson, GraphInput.cpp:168-197): path p = the nodes
+ * path_nodes[path_ptr[p] .. path_ptr[p+1]), whole nodes, consecutive ones joined by an edge.  At most 62 per site. */
+int pg_set_paths(pg_ctx* ctx, int32_t site, int32_t n_paths, const int32_t* path_ptr, const int32_t* path_nodes);
+/* kmer_len: 0 = off (default), else 2..16 (the reference instantiates 16; its unit test 10). */
+int pg_set_kmer_stage(pg_ctx* ctx, int32_t kmer_len);
+/* counters2 = {attempted, mapped} of the last batch (KmerAligner::attempted / mapped); kmer_ms = device time. */
+int pg_kmer_stats(pg_ctx* ctx, uint64_t* counters2, float* kmer_ms);
 
 /* Kernels launched by this context so far, and the last batch's per-kernel device time in ms
  * (fill, traceback) measured with CUDA events on the launching stream. */

@@ -25,13 +25,18 @@ RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i2"), ("query_clipped
 SYMBOLS = ["pg_create", "pg_destroy", "pg_last_error", "pg_set_stream", "pg_set_scratch_limit", "pg_add_graph",
            "pg_add_graphs", "pg_clear_graphs", "pg_align_batch", "pg_batch_upload", "pg_batch_run", "pg_batch_download",
            "pg_format_cigar", "pg_stats", "pg_version", "pg_host_alloc", "pg_host_free", "pg_set_edge_labels",
-           "pg_batch_import", "pg_batch_count", "pg_count_stats", "pg_set_stages", "pg_path_stats"]
+           "pg_batch_import", "pg_batch_count", "pg_count_stats", "pg_set_stages", "pg_path_stats", "pg_set_paths",
+           "pg_set_kmer_stage", "pg_kmer_stats"]
 
 # counting stage (include/pg_align.h, "Counting stage")
 V_MAPPED, V_NONUNIQ, V_BAD_ALIGN, V_INVALID = 0, 1, 2, 3
 SUP_NODE_MASK, SUP_NODE, SUP_EDGE = 0xFFFF, 0x40000000, 0x80000000
 SUPPORT_DTYPE = np.dtype([("sequences", "<u8"), ("path_off", "<u4"), ("path_len", "<u2"), ("verdict", "u1"),
                           ("graph_reverse", "u1")])
+
+
+# pg_record.mapped_by -> (stage of the cascade that mapped the read, reverse complements applied by the stages before it)
+STAGES = {0: ("gssw", 0), 1: ("path", 0), 2: ("gssw", 1), 3: ("kmer", 0), 4: ("kmer", 1), 5: ("gssw", 2)}
 
 
 class CountParams(C.Structure):
@@ -73,6 +78,12 @@ def load():
     lib.pg_add_graphs.argtypes = [vp, C.c_int32, i32p, C.c_char_p, i32p, i32p, i32p, i32p, i32p]
     lib.pg_clear_graphs.restype = C.c_int
     lib.pg_clear_graphs.argtypes = [vp]
+    lib.pg_set_paths.restype = C.c_int
+    lib.pg_set_paths.argtypes = [vp, C.c_int32, C.c_int32, i32p, i32p]
+    lib.pg_set_kmer_stage.restype = C.c_int
+    lib.pg_set_kmer_stage.argtypes = [vp, C.c_int32]
+    lib.pg_kmer_stats.restype = C.c_int
+    lib.pg_kmer_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_float)]
     lib.pg_align_batch.restype = C.c_int
     lib.pg_align_batch.argtypes = [vp, C.c_int32, vp, i32p, i32p, C.c_uint32, vp, u32p, C.c_uint64,
                                    C.POINTER(C.c_uint64)]
@@ -204,6 +215,24 @@ class Context:
         self._check(self.lib.pg_set_stages(self.h, int(path_kmer_len), 1 if graph_matching else 0,
                                            1 if nonuniq_second_chance else 0))
         self._path_k = int(path_kmer_len)
+
+    def set_paths(self, site, paths):
+        """The paths of the site's graph JSON ([[node ids], ...]): what the k-mer stage aligns to."""
+        ptr = np.zeros(len(paths) + 1, dtype=np.int32)
+        ptr[1:] = np.cumsum([len(p) for p in paths])
+        flat = np.ascontiguousarray([v for p in paths for v in p] or [0], dtype=np.int32)
+        self._check(self.lib.pg_set_paths(self.h, int(site), len(paths), _i32(ptr), _i32(flat)))
+
+    def set_kmer_stage(self, kmer_len=16):
+        """grm::KmerAligner<kmer_len> between the exact-match stage and gssw (0 = off)."""
+        self._check(self.lib.pg_set_kmer_stage(self.h, int(kmer_len)))
+        self._kmer_k = int(kmer_len)
+
+    def kmer_stats(self):
+        cnt = (C.c_uint64 * 2)()
+        ms = C.c_float(0)
+        self._check(self.lib.pg_kmer_stats(self.h, cnt, C.byref(ms)))
+        return dict(attempted=int(cnt[0]), mapped=int(cnt[1]), kmer_ms=float(ms.value))
 
     def path_stats(self):
         """-> dict(attempted, anchored, mapped, path_ms) of the last batch (PathAligner.hh:66-68)"""
@@ -394,17 +423,18 @@ class Context:
         for i, r in enumerate(reads):
             x = rec[i]
             rv = bool(x["chose_reverse"])
-            by_path = int(x["mapped_by"]) == 1  # PathAligner sets the strand itself and always writes a CIGAR
-            if int(x["mapped_by"]) == 2:  # second chance: gssw saw the bases PathAligner had reverse-complemented
+            stage, flips = STAGES[int(x["mapped_by"])]  # which aligner of the cascade, after how many reverse complements
+            by_path = stage == "path"  # PathAligner sets the strand itself and always writes a CIGAR
+            for _ in range(flips):  # second chance(s): the stage saw bases earlier stages had reverse-complemented
                 r = revcomp_exact(r)
             d = dict(pos=int(x["graph_pos"]), score=int(x["score"]), unique=bool(x["unique"]),
                      mapq=60 if x["unique"] else 0,
                      graph_reverse=rv if by_path else (bool(is_rev[i] if is_rev is not None else 0) != rv),
                      bases=revcomp_exact(r) if rv else r,
-                     cigar=format_cigar(x, ops) if (flags & AF_CIGAR or by_path) else "", status=int(x["status"]),
+                     cigar=format_cigar(x, ops) if (flags & AF_CIGAR or stage != "gssw") else "", status=int(x["status"]),
                      clipped=int(x["query_clipped"]))
-            if getattr(self, "_path_k", 0):
-                d["stage"] = ("gssw", "path", "gssw2")[int(x["mapped_by"])]
+            if getattr(self, "_path_k", 0) or getattr(self, "_kmer_k", 0):
+                d["stage"] = stage + ("2" if flips == 1 else "3" if flips == 2 else "")
             out.append(d)
         return out
 

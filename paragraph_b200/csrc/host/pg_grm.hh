@@ -78,9 +78,15 @@ private:
     std::map<std::pair<uint32_t, uint32_t>, std::set<std::string>> labels_;
 };
 
-struct Path
-{
-}; // placeholder for graphtools::Path (only used by the path-matching stage, which is not on the GPU path)
+struct Path // the part of graphtools::Path the k-mer stage needs: whole nodes from the first base of the first one to the
+{           // last base of the last one, as grm::pathsFromJson builds them (GraphInput.cpp:168-197)
+    Path() = default;
+    explicit Path(std::vector<uint32_t> nodes) : nodes_(std::move(nodes)) {}
+    std::vector<uint32_t> const& nodeIds() const { return nodes_; }
+
+private:
+    std::vector<uint32_t> nodes_;
+};
 
 class Read // the fields of common::Read the alignment path touches (src/c++/include/common/Read.hh:97-131)
 {
@@ -447,10 +453,29 @@ public:
             read.set_graph_mapq(r.unique ? 60 : 0);
             return;
         }
-        if (r.mapped_by == PG_STAGE_GSSW_REV_ID) // the exact-match stage had reverse-complemented the bases first
+        // the stages in front had reverse-complemented the bases (each one graphtools::reverseComplement, quals untouched)
+        const int flips = (r.mapped_by == PG_STAGE_GSSW_REV_ID || r.mapped_by == PG_STAGE_KMER_REV_ID) ? 1
+            : (r.mapped_by == PG_STAGE_GSSW_REV2_ID ? 2 : 0);
+        for (int f = 0; f < flips; ++f)
         {
             reverseComplementInto(read.bases(), tmp);
             read.set_bases(tmp);
+        }
+        if (r.mapped_by == PG_STAGE_KMER_ID || r.mapped_by == PG_STAGE_KMER_REV_ID) // KmerAligner.cpp:423-478
+        {
+            read.set_graph_pos(r.graph_pos);
+            read.set_is_graph_reverse_strand(read.is_reverse_strand() != (r.chose_reverse != 0));
+            if (r.chose_reverse) // quals stay as they are
+            {
+                reverseComplementInto(read.bases(), tmp);
+                read.set_bases(tmp);
+            }
+            formatCigar(r, ops, tmp);
+            read.set_graph_cigar(tmp);
+            read.set_graph_alignment_score(r.score);
+            read.set_graph_mapq(r.unique ? 60 : 0);
+            read.set_is_graph_alignment_unique(r.unique != 0);
+            return;
         }
         read.set_is_graph_reverse_strand(read.is_reverse_strand() != (r.chose_reverse != 0)); // :358-359
         if (r.chose_reverse) // :375-378
@@ -1007,89 +1032,148 @@ class CompositeAligner
 {
 public:
     CompositeAligner(bool pathMatching, bool graphMatching, bool klibMatching, bool kmerMatching,
-                     unsigned graphAlignmentFlags = GraphAligner::AF_ALL, int device = 0, int pathKmerSize = 32)
-        : pathMatching_(pathMatching), graphMatching_(graphMatching), flags_(graphAlignmentFlags),
-          pathKmerSize_(pathKmerSize), graphAligner_(device)
+                     unsigned graphAlignmentFlags = GraphAligner::AF_ALL, int device = 0, int pathKmerSize = 32,
+                     int kmerSize = 16)
+        : pathMatching_(pathMatching), graphMatching_(graphMatching), kmerMatching_(kmerMatching), flags_(graphAlignmentFlags),
+          pathKmerSize_(pathKmerSize), kmerSize_(kmerSize), graphAligner_(device)
     {
-        if (klibMatching || kmerMatching)
-            throw std::runtime_error("paragraph_b200: the path and gssw stages run on the GPU; "
-                                     "klib / kmer matching must stay on the reference's CPU aligners");
+        if (klibMatching)
+            throw std::runtime_error("paragraph_b200: the path, kmer and gssw stages run on the GPU; "
+                                     "klib matching must stay on the reference's CPU aligner");
     }
-    template <typename GraphT, typename PathListT> void setGraph(GraphT const* graph, PathListT const&)
+    // CompositeAligner::setGraph (CompositeAligner.cpp:52-76): the k-mer stage aligns to the graph's paths
+    template <typename GraphT, typename PathListT> void setGraph(GraphT const* graph, PathListT const& paths)
     {
         graphAligner_.setGraph(graph);
+        if (kmerMatching_)
+        {
+            std::vector<int32_t> ptr{ 0 }, nodes;
+            for (auto const& p : paths)
+            {
+                for (auto v : p.nodeIds())
+                    nodes.push_back((int32_t)v);
+                ptr.push_back((int32_t)nodes.size());
+            }
+            if (nodes.empty())
+                nodes.push_back(0);
+            graphAligner_.check(pg_set_paths(graphAligner_.context(), 0, (int32_t)ptr.size() - 1, ptr.data(), nodes.data()));
+        }
     }
     void setThreads(unsigned threads) { graphAligner_.setThreads(threads); }
 
-    // CompositeAligner::alignRead for a whole range (CompositeAligner.cpp:78-176): exact-match stage (:82-95), the
-    // filter right after it with a second chance for rejected reads (:97-103), gssw stage (:146-175: every read it
-    // sees becomes MAPPED, then the filter may turn it into BAD_ALIGN); counters as in the reference.
+    // CompositeAligner::alignRead for a whole range (CompositeAligner.cpp:78-176).  The reference runs, per read: the
+    // exact-match stage (:82-95), the filter on its result with a second chance in the later stages for a rejected
+    // read (:97-103), the k-mer stage (:105-126; a read it maps but not uniquely leaves it BAD_ALIGN and goes on), the
+    // gssw stage (:146-175: every read it sees becomes MAPPED, then the filter may turn it into BAD_ALIGN).  Here every
+    // stage is one launch over the batch, so the cascade runs in rounds: all enabled stages over all reads; then the
+    // later stages over the reads whose exact match the filter rejected; then gssw over the reads whose k-mer
+    // alignment it rejected.  Counters as in the reference.
     template <typename ReadIt, typename FilterT> void alignReads(ReadIt begin, ReadIt end, FilterT filter)
     {
         typedef typename std::remove_reference<decltype(**begin)>::type ReadT;
-        if (!pathMatching_ && !graphMatching_)
-        {
-            for (ReadIt it = begin; it != end; ++it)
-                attempted_ += !(*it)->bases().empty();
-            return;
-        }
-        graphAligner_.check(pg_set_stages(graphAligner_.context(), pathMatching_ ? pathKmerSize_ : 0, graphMatching_ ? 1 : 0, 0));
-        std::vector<pg_record> rec;
-        graphAligner_.alignBatch(begin, end, flags_, &rec, /*tolerate_unmapped=*/true);
-        std::vector<ReadT*> again; // rejected right after the exact-match stage: second chance in the gssw stage
-        size_t i = 0;
+        std::vector<ReadT*> todo;
         for (ReadIt it = begin; it != end; ++it)
-        {
-            ReadT& read = **it;
-            if (read.bases().empty())
-                continue;
-            ++attempted_;
-            const pg_record& r = rec[i++];
-            if (r.status == 3) // no stage mapped it (graphMatching off)
-                continue;
-            read.set_graph_mapping_status(ReadT::MAPPED);
-            const bool rejected = filter && filter(read);
-            if (r.mapped_by == PG_STAGE_PATH_ID)
+            if (!(*it)->bases().empty())
             {
-                ++mappedPath_;
-                if (rejected)
+                ++attempted_;
+                todo.push_back(&**it);
+            }
+        // stage sets of the rounds: {path?, kmer?, gssw?}
+        bool path_on = pathMatching_, kmer_on = kmerMatching_;
+        while (!todo.empty() && (path_on || kmer_on || graphMatching_))
+        {
+            graphAligner_.check(pg_set_kmer_stage(graphAligner_.context(), kmer_on ? kmerSize_ : 0));
+            graphAligner_.check(pg_set_stages(graphAligner_.context(), path_on ? pathKmerSize_ : 0, graphMatching_ ? 1 : 0, 0));
+            std::vector<pg_record> rec;
+            graphAligner_.alignBatch(todo.begin(), todo.end(), flags_, &rec, /*tolerate_unmapped=*/true);
+            std::vector<ReadT*> after_path, after_kmer; // rejected by the filter right after that stage
+            for (size_t i = 0; i < todo.size(); ++i)
+            {
+                ReadT& read = *todo[i];
+                const pg_record& r = rec[i];
+                if (r.status == 3) // no enabled stage mapped it
+                {
+                    if (kmer_on) // KmerAlignerImpl::alignRead starts by resetting the status (KmerAligner.cpp:521)
+                        read.set_graph_mapping_status(ReadT::UNMAPPED);
+                    continue;
+                }
+                const bool by_path = r.mapped_by == PG_STAGE_PATH_ID;
+                const bool by_kmer = r.mapped_by == PG_STAGE_KMER_ID || r.mapped_by == PG_STAGE_KMER_REV_ID;
+                if (by_kmer && !r.unique) // KmerAligner itself: an equally good second candidate -> BAD_ALIGN (gssw is off,
+                {                         // else the device had passed the read on)
+                    read.set_graph_mapping_status(ReadT::BAD_ALIGN);
+                    continue;
+                }
+                read.set_graph_mapping_status(ReadT::MAPPED);
+                const bool rejected = filter && filter(read);
+                if (by_path)
+                {
+                    ++mappedPath_;
+                    if (rejected)
+                    {
+                        read.set_graph_mapping_status(ReadT::BAD_ALIGN);
+                        filtered_ += !kmerMatching_ && !graphMatching_;
+                        if (kmerMatching_ || graphMatching_)
+                            after_path.push_back(&read);
+                    }
+                }
+                else if (by_kmer)
+                {
+                    if (rejected)
+                    {
+                        read.set_graph_mapping_status(ReadT::BAD_ALIGN);
+                        filtered_ += !graphMatching_;
+                        if (graphMatching_)
+                            after_kmer.push_back(&read);
+                    }
+                    else
+                        ++mappedKmers_;
+                }
+                else if (rejected)
                 {
                     read.set_graph_mapping_status(ReadT::BAD_ALIGN);
-                    filtered_ += !graphMatching_;
-                    if (graphMatching_)
-                        again.push_back(&read);
-                }
-            }
-            else if (rejected)
-            {
-                read.set_graph_mapping_status(ReadT::BAD_ALIGN);
-                ++filtered_;
-            }
-            else
-                ++mappedSw_;
-        }
-        if (pathMatching_)
-        {
-            uint64_t cnt[4] = { 0, 0, 0, 0 };
-            graphAligner_.check(pg_path_stats(graphAligner_.context(), cnt, nullptr));
-            anchoredPath_ += (unsigned)cnt[1];
-        }
-        if (!again.empty())
-        {
-            graphAligner_.check(pg_set_stages(graphAligner_.context(), 0, 1, 0));
-            graphAligner_.alignBatch(again.begin(), again.end(), flags_);
-            for (ReadT* p : again)
-            {
-                p->set_graph_mapping_status(ReadT::MAPPED);
-                if (filter && filter(*p))
-                {
-                    p->set_graph_mapping_status(ReadT::BAD_ALIGN);
                     ++filtered_;
                 }
                 else
                     ++mappedSw_;
             }
+            if (path_on)
+            {
+                uint64_t cnt[4] = { 0, 0, 0, 0 };
+                graphAligner_.check(pg_path_stats(graphAligner_.context(), cnt, nullptr));
+                anchoredPath_ += (unsigned)cnt[1];
+            }
+            // next round: what the filter sent on.  (After the exact-match stage: k-mer stage and gssw; the reads the
+            // k-mer stage of THIS round lost to the filter join the gssw-only round that follows.)
+            if (path_on)
+            {
+                path_on = false;
+                pending_gssw_.insert(pending_gssw_.end(), after_kmer.begin(), after_kmer.end());
+                todo.swap(after_path);
+                if (todo.empty())
+                {
+                    kmer_on = false;
+                    todo.clear();
+                    for (void* q : pending_gssw_)
+                        todo.push_back(static_cast<ReadT*>(q));
+                    pending_gssw_.clear();
+                }
+            }
+            else if (kmer_on)
+            {
+                kmer_on = false;
+                todo.clear();
+                for (void* q : pending_gssw_)
+                    todo.push_back(static_cast<ReadT*>(q));
+                pending_gssw_.clear();
+                todo.insert(todo.end(), after_kmer.begin(), after_kmer.end());
+            }
+            else
+                todo.clear();
+            if (!graphMatching_ && !kmer_on && !path_on)
+                break;
         }
+        pending_gssw_.clear();
     }
     template <typename ReadT, typename FilterT> void alignRead(ReadT& read, FilterT filter)
     {
@@ -1102,15 +1186,16 @@ public:
     unsigned mappedKlib() const { return 0; }
     unsigned mappedPath() const { return mappedPath_; }
     unsigned anchoredPath() const { return anchoredPath_; }
-    unsigned mappedKmers() const { return 0; }
+    unsigned mappedKmers() const { return mappedKmers_; }
     unsigned mappedSw() const { return mappedSw_; }
 
 private:
-    const bool pathMatching_, graphMatching_;
+    const bool pathMatching_, graphMatching_, kmerMatching_;
     const unsigned flags_;
-    const int pathKmerSize_;
+    const int pathKmerSize_, kmerSize_;
     GraphAligner graphAligner_;
-    unsigned attempted_ = 0, filtered_ = 0, mappedSw_ = 0, mappedPath_ = 0, anchoredPath_ = 0;
+    unsigned attempted_ = 0, filtered_ = 0, mappedSw_ = 0, mappedPath_ = 0, anchoredPath_ = 0, mappedKmers_ = 0;
+    std::vector<void*> pending_gssw_; // reads the filter rejected after the k-mer stage, waiting for the gssw-only round
 };
 
 // grm::alignReads (Align.hh:49-52; Align.cpp:114-156): aligns, then keeps only MAPPED reads (input order).

@@ -1066,7 +1066,7 @@ PG_HD int rev_plan(const TaskOut& fw, const int* rv_known, unsigned flags)
 // ---------------------------------------------------------------------------------------------
 // output records (these two structs ARE the C-ABI result layout, see include/pg_align.h)
 // ---------------------------------------------------------------------------------------------
-constexpr int STAGE_GSSW = 0, STAGE_PATH = 1, STAGE_GSSW_REV = 2; // Record::mapped_by (include/pg_align.h)
+constexpr int STAGE_GSSW = 0, STAGE_PATH = 1, STAGE_GSSW_REV = 2, STAGE_KMER = 3, STAGE_KMER_REV = 4, STAGE_GSSW_REV2 = 5; // Record::mapped_by (include/pg_align.h)
 constexpr int ST_UNMAPPED = 3;                // Record::status: no enabled stage mapped the read
 struct Record
 {

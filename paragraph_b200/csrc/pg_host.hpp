@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "pg_core.cuh"
+#include "pg_kmer.cuh"
 #include "pg_count.cuh"
 #include "pg_path.cuh"
 
@@ -35,6 +36,8 @@ struct GraphStore
     std::vector<int32_t> in_from, in_to;
     std::vector<uint64_t> in_label;
     std::vector<int64_t> edge_base, node_base; // [n_sites + 1]
+    // the paths of each site's graph JSON (GraphInput.cpp:168-197; pg_set_paths): what grm::KmerAligner aligns to
+    std::vector<std::vector<std::vector<int32_t>>> paths; // [site][path] = node ids
 
     void clear()
     {
@@ -47,6 +50,7 @@ struct GraphStore
         in_label.clear();
         edge_base.clear();
         node_base.clear();
+        paths.clear();
     }
 
     // sizes of everything add() appends to: pg_add_graphs registers all of its sites or none
@@ -66,6 +70,7 @@ struct GraphStore
         in_label.resize(m.in_edges);
         edge_base.resize(m.bases);
         node_base.resize(m.bases);
+        paths.resize(m.sites);
         max_nodes = m.max_nodes;
         max_G = m.max_G;
         max_tab_ints = m.max_tab_ints;
@@ -189,7 +194,49 @@ struct GraphStore
         node_base.push_back(node_base.back() + n_nodes);
         max_nodes = std::max(max_nodes, n_nodes);
         max_G = std::max(max_G, (int)G);
+        paths.emplace_back();
         return (int)sites.size() - 1;
+    }
+
+    // graphtools::Path(graph, 0, nodes, last node length - 1) for every path (GraphInput.cpp:168-197): node ids must
+    // exist and consecutive nodes must be joined by an edge (Path::assertValidity)
+    bool set_paths(int site, int n_paths, const int32_t* path_ptr, const int32_t* path_nodes, std::string& err)
+    {
+        if (site < 0 || (size_t)site >= sites.size() || n_paths < 0 || (n_paths > 0 && (!path_ptr || !path_nodes)))
+        {
+            err = "pg_set_paths: bad arguments";
+            return false;
+        }
+        const SiteDev& sd = sites[(size_t)site];
+        const int64_t eb = edge_base[(size_t)site];
+        std::vector<std::vector<int32_t>> out;
+        for (int p = 0; p < n_paths; ++p)
+        {
+            std::vector<int32_t> nodes(path_nodes + path_ptr[p], path_nodes + path_ptr[p + 1]);
+            if (nodes.empty())
+            {
+                err = "pg_set_paths: empty path";
+                return false;
+            }
+            for (size_t i = 0; i < nodes.size(); ++i)
+            {
+                bool ok = nodes[i] >= 0 && nodes[i] < sd.n_nodes;
+                if (ok && i > 0)
+                {
+                    ok = false;
+                    for (int e = 0; e < sd.n_edges && !ok; ++e)
+                        ok = in_from[(size_t)(eb + e)] == nodes[i - 1] && in_to[(size_t)(eb + e)] == nodes[i];
+                }
+                if (!ok)
+                {
+                    err = "pg_set_paths: path " + std::to_string(p) + " is not a path of the graph";
+                    return false;
+                }
+            }
+            out.push_back(std::move(nodes));
+        }
+        paths[(size_t)site] = std::move(out);
+        return true;
     }
 };
 
@@ -608,6 +655,74 @@ inline void build_path_index(const GraphStore& gs, int k, PathIndexHost& out, in
 }
 
 // per-read scratch sizes in 32-bit words (see pg_core.cuh "per-task scratch layout")
+// ---------------------------------------------------------------------------------------------
+// k-mer stage (pg_kmer.cuh), host side: per path its sequence, node offsets and sorted k-mers
+// (KmerAligner.cpp:135-160 BasicPath, :120-133 makeKmers)
+// ---------------------------------------------------------------------------------------------
+struct KmerIndexHost
+{
+    std::vector<KmerSiteDev> sites;
+    std::vector<KmerPathDev> paths;
+    std::vector<uint8_t> seqs;
+    std::vector<int32_t> nodes;
+    std::vector<KmerPos> kmers;
+    int max_path_nodes = 0, max_paths = 0;
+};
+inline void build_kmer_index(const GraphStore& gs, int k, KmerIndexHost& ix)
+{
+    const size_t ns = gs.sites.size();
+    ix.sites.resize(ns);
+    for (size_t si = 0; si < ns; ++si)
+    {
+        const SiteDev& sd = gs.sites[si];
+        const int32_t* node_start = gs.ints.data() + sd.tab_off[0];
+        const int32_t* node_len = node_start + sd.n_nodes;
+        const uint8_t* raw = gs.bytes.data() + sd.raw_off;
+        ix.sites[si].n_paths = (int32_t)gs.paths[si].size();
+        ix.sites[si].path0 = (int32_t)ix.paths.size();
+        ix.max_paths = std::max(ix.max_paths, ix.sites[si].n_paths);
+        for (auto const& nodes : gs.paths[si])
+        {
+            KmerPathDev kp;
+            kp.seq_off = (int32_t)ix.seqs.size();
+            kp.n_nodes = (int32_t)nodes.size();
+            kp.nodes_off = (int32_t)ix.nodes.size();
+            ix.max_path_nodes = std::max(ix.max_path_nodes, kp.n_nodes);
+            ix.nodes.insert(ix.nodes.end(), nodes.begin(), nodes.end());
+            int32_t len = 0;
+            for (int32_t v : nodes)
+            {
+                ix.nodes.push_back(len);
+                ix.seqs.insert(ix.seqs.end(), raw + node_start[v], raw + node_start[v] + node_len[v]);
+                len += node_len[v];
+            }
+            kp.len = len;
+            kp.kmers_off = (int32_t)ix.kmers.size();
+            const uint8_t* s = ix.seqs.data() + kp.seq_off;
+            uint32_t val = 0;
+            int have = 0;
+            const uint32_t mask = k >= 16 ? 0xFFFFFFFFu : ((1u << (2 * k)) - 1u);
+            for (int32_t i = 0; i < len; ++i)
+            {
+                const int b = kmer_base_value(s[i]);
+                if (b > 3)
+                {
+                    have = 0;
+                    continue;
+                }
+                val = (val << 2) | (uint32_t)b;
+                if (++have >= k)
+                    ix.kmers.push_back(KmerPos{ val & mask, i - k + 1 });
+            }
+            kp.n_kmers = (int32_t)ix.kmers.size() - kp.kmers_off;
+            std::sort(ix.kmers.begin() + kp.kmers_off, ix.kmers.end(), [](const KmerPos& a, const KmerPos& b) {
+                return a.kmer < b.kmer || (a.kmer == b.kmer && a.pos < b.pos);
+            });
+            ix.paths.push_back(kp);
+        }
+    }
+}
+
 inline size_t last_words(int max_nodes, int R, int W) // node table of one read: a row per (node, lane), pg_core.cuh Sizes
 {
     const int v = is_wide(R, W) ? 2 * R : R, iw = is_wide(R, W) ? 4 : 3;

@@ -21,6 +21,7 @@
 #include "../../include/pg_align.h"
 #include "pg_core.cuh"
 #include "pg_count.cuh"
+#include "pg_kmer.cuh"
 #include "pg_host.hpp"
 
 using namespace pg;
@@ -709,7 +710,8 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         rec.unique = (uint8_t)d.unique;
         rec.chose_reverse = (uint8_t)half;
         rec.status = (uint8_t)(w.phase == 2 ? w.status : 1);
-        rec.mapped_by = (uint8_t)((a.prerev && a.prerev[rd]) ? STAGE_GSSW_REV : STAGE_GSSW);
+        const int flips = a.prerev ? a.prerev[rd] : 0; // reverse complements the earlier stages applied to the bases
+        rec.mapped_by = (uint8_t)(flips == 0 ? STAGE_GSSW : (flips == 1 ? STAGE_GSSW_REV : STAGE_GSSW_REV2));
         rec.query_clipped = (uint16_t)w.clipped;
         rec.cigar_off = 0;
         rec.cigar_len = 0;
@@ -1237,6 +1239,124 @@ __global__ void __launch_bounds__(PATHW_WARPS * 32) pg_path_warp_kernel(const Pa
     }
 }
 
+// ---- the k-mer stage (grm::KmerAligner<K>, pg_kmer.cuh): one warp per read ------------------------------------------
+// Work list: the reads the exact-match stage left over (todo_in), or all reads.  A uniquely mapped read gets its record
+// and op words here; the others are listed in todo_out for the DP -- a read that mapped but not uniquely goes there
+// with the bases KmerAligner leaves behind (reverse-complemented when its best candidate was on the reverse strand,
+// KmerAligner.cpp:452-460) and one more flip counted in prerev.
+struct KmerArgs
+{
+    KmerView view;
+    uint8_t* bases;
+    const int32_t* read_off;
+    const int32_t* read_site;
+    int n_reads;
+    const int32_t* todo_in;
+    const int32_t* n_todo_in;
+    int32_t* todo_out;
+    int32_t* n_todo_out;
+    uint8_t* prerev;
+    Record* records;
+    uint32_t* arena;
+    unsigned long long* cursor;
+    unsigned long long arena_cap;
+    unsigned long long* counters; // attempted, mapped (KmerAligner::attempted / mapped)
+    int no_gssw;
+    int max_len, ops_cap, smem_bytes_per_warp;
+};
+constexpr int KMER_WARPS = 4;
+__global__ void __launch_bounds__(KMER_WARPS * 32) pg_kmer_kernel(const KmerArgs a)
+{
+    extern __shared__ uint32_t smem[];
+    const int wic = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * KMER_WARPS + wic;
+    const int n = a.todo_in ? min(a.n_reads, *a.n_todo_in) : a.n_reads;
+    if (w >= n)
+        return;
+    const int rd = a.todo_in ? a.todo_in[w] : w;
+    uint8_t* base = reinterpret_cast<uint8_t*>(smem) + (size_t)wic * a.smem_bytes_per_warp;
+    const int ml = (a.max_len + 3) & ~3;
+    KmerScratch sc;
+    sc.km[0] = reinterpret_cast<uint32_t*>(base);
+    sc.km[1] = sc.km[0] + ml;
+    sc.bitmap = sc.km[1] + ml;
+    sc.ops_best = sc.bitmap + KMER_WIN / 32;
+    sc.ops_tmp = sc.ops_best + a.ops_cap;
+    sc.heap = reinterpret_cast<KmerCand*>(sc.ops_tmp + a.ops_cap);
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(sc.heap + (KMER_MAX_PATHS + 2));
+    sc.seq[0] = bytes;
+    sc.seq[1] = bytes + ml;
+    sc.valid[0] = bytes + 2 * ml;
+    sc.valid[1] = bytes + 3 * ml;
+    sc.first[0] = bytes + 4 * ml;
+    sc.first[1] = bytes + 5 * ml;
+    sc.ops_cap = a.ops_cap;
+    uint8_t* bases = a.bases + a.read_off[rd];
+    const int L = a.read_off[rd + 1] - a.read_off[rd];
+    const int site = a.read_site ? a.read_site[rd] : 0;
+    if (!a.todo_in && lane == 0)
+        a.prerev[rd] = 0;
+    const KmerResult r = kmer_align_read(a.view, site, bases, L, lane, 32, sc);
+    if (lane == 0)
+        atomicAdd(a.counters + 0, 1ull);
+    const int flips = a.prerev[rd];
+    if (r.status == 1 || (r.status == 2 && a.no_gssw))
+    {
+        Record rec;
+        rec.graph_pos = r.pos;
+        rec.score = (int16_t)r.score;
+        rec.query_clipped = (uint16_t)r.clipped;
+        rec.unique = (uint8_t)(r.status == 1);
+        rec.chose_reverse = (uint8_t)r.rev;
+        rec.status = 0;
+        rec.mapped_by = (uint8_t)(flips ? STAGE_KMER_REV : STAGE_KMER);
+        rec.cigar_off = 0;
+        rec.cigar_len = (uint32_t)r.n_ops;
+        unsigned long long off = 0;
+        if (lane == 0)
+            off = atomicAdd(a.cursor, (unsigned long long)r.n_ops);
+        off = __shfl_sync(FULL, off, 0);
+        if (r.n_ops <= a.ops_cap && off + (unsigned long long)r.n_ops <= a.arena_cap)
+        {
+            for (int x = lane; x < r.n_ops; x += 32)
+                a.arena[off + x] = sc.ops_best[x];
+            rec.cigar_off = (uint32_t)off;
+        }
+        else
+        {
+            rec.status = 2;
+            rec.cigar_len = 0;
+        }
+        if (lane == 0)
+        {
+            a.records[rd] = rec;
+            if (r.status == 1)
+                atomicAdd(a.counters + 1, 1ull);
+        }
+        return;
+    }
+    if (a.no_gssw) // no later stage: the read stays UNMAPPED
+    {
+        if (lane == 0)
+        {
+            Record rec;
+            memset(&rec, 0, sizeof rec);
+            rec.status = (uint8_t)ST_UNMAPPED;
+            a.records[rd] = rec;
+        }
+        return;
+    }
+    if (r.status == 2 && r.rev) // BAD_ALIGN on the reverse strand: the later stages see the reverse complement
+    {
+        for (int x = lane; x < L; x += 32)
+            bases[x] = sc.seq[1][x];
+        if (lane == 0)
+            a.prerev[rd] = (uint8_t)(flips + 1);
+    }
+    if (lane == 0)
+        a.todo_out[atomicAdd(a.n_todo_out, 1)] = rd;
+}
+
 // ---- building the exact-match index on the device --------------------------------------------------------------
 // The host build (pg_host.hpp: build_path_index) costs ~25 us per site and thread; for a batch of 1 000 new sites that
 // is as long as aligning their reads.  Here: one thread per start position of every site enumerates its k-mer paths
@@ -1596,6 +1716,23 @@ struct pg_ctx
     float path_ms = 0;
     cudaEvent_t path_ev[2] = { nullptr, nullptr };
 
+    // k-mer stage (pg_kmer.cuh)
+    int kmer_k = 0; // 0 = the stage is off
+    bool kmer_dirty = true, kmer_ran = false;
+    int kmer_max_path_nodes = 0;
+    DevBuf<KmerSiteDev> d_ksites;
+    DevBuf<KmerPathDev> d_kpaths;
+    DevBuf<uint8_t> d_kseqs;
+    DevBuf<int32_t> d_knodes, d_todo2, d_ntodo2;
+    DevBuf<KmerPos> d_kkmers;
+    DevBuf<unsigned long long> d_kcount;
+    unsigned long long kmer_counters[2] = { 0, 0 };
+    float kmer_ms = 0;
+    cudaEvent_t kmer_ev[2] = { nullptr, nullptr };
+    // the reads the stages in front left for the DP: the list of the last stage that ran (null = all reads)
+    const int32_t* todo_final = nullptr;
+    const int32_t* ntodo_final = nullptr;
+
     // counting stage (pg_count.cuh)
     bool count_dirty = true;
     int count_slots = 0;
@@ -1801,24 +1938,9 @@ int run_path_stage(pg_ctx* c)
     int rc = upload_path_index(c);
     if (rc != PG_OK)
         return rc;
-    const int max_nodes = c->graphs.max_nodes;
-    PG_CUDA(c, c->d_records.reserve((size_t)c->n_reads));
-    PG_CUDA(c, c->d_cursor.reserve(1));
     PG_CUDA(c, c->d_todo.reserve((size_t)c->n_reads));
     PG_CUDA(c, c->d_ntodo.reserve(1));
     PG_CUDA(c, c->d_pcount.reserve(3));
-    PG_CUDA(c, c->d_prerev.reserve((size_t)c->n_reads));
-    if (c->have_bases_orig) // an earlier run of this upload may have flipped reads: start from the uploaded bases again
-        PG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, c->d_bases_orig.p, c->bases_bytes, cudaMemcpyDeviceToDevice, c->stream));
-    else if (c->path_second_chance && c->gssw_on)
-    {
-        PG_CUDA(c, c->d_bases_orig.reserve(c->bases_bytes + 16));
-        PG_CUDA(c, cudaMemcpyAsync(c->d_bases_orig.p, c->d_bases.p, c->bases_bytes, cudaMemcpyDeviceToDevice, c->stream));
-        c->have_bases_orig = true;
-    }
-    c->arena_cap = arena_words(c, max_nodes);
-    PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
-    PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
     PG_CUDA(c, cudaMemsetAsync(c->d_ntodo.p, 0, sizeof(int32_t), c->stream));
     PG_CUDA(c, cudaMemsetAsync(c->d_pcount.p, 0, 3 * sizeof(unsigned long long), c->stream));
     for (auto& ev : c->path_ev)
@@ -1836,7 +1958,7 @@ int run_path_stage(pg_ctx* c)
     pa.read_off = c->d_off.p;
     pa.read_site = c->have_sites ? c->d_site.p : nullptr;
     pa.n_reads = c->n_reads;
-    pa.no_gssw = c->gssw_on ? 0 : 1;
+    pa.no_gssw = (c->gssw_on || c->kmer_k > 0) ? 0 : 1; // a later stage takes the reads this one leaves
     pa.second_chance = c->path_second_chance ? 1 : 0;
     pa.prerev = c->d_prerev.p;
     pa.records = c->d_records.p;
@@ -1862,6 +1984,110 @@ int run_path_stage(pg_ctx* c)
     ++c->launches;
     PG_CUDA(c, cudaEventRecord(c->path_ev[1], c->stream));
     c->path_ran = true;
+    c->todo_final = c->d_todo.p;
+    c->ntodo_final = c->d_ntodo.p;
+    return PG_OK;
+}
+
+// what the stages in front of the DP share: records, the CIGAR arena with its cursor, the flip counts, and the
+// uploaded bases kept aside (the stages hand reverse-complemented bases to the later ones; every pg_batch_run starts
+// from what was uploaded)
+int prepare_front_stages(pg_ctx* c)
+{
+    PG_CUDA(c, c->d_records.reserve((size_t)c->n_reads));
+    PG_CUDA(c, c->d_cursor.reserve(1));
+    PG_CUDA(c, c->d_prerev.reserve((size_t)c->n_reads));
+    if (c->have_bases_orig) // an earlier run of this upload may have flipped reads
+        PG_CUDA(c, cudaMemcpyAsync(c->d_bases.p, c->d_bases_orig.p, c->bases_bytes, cudaMemcpyDeviceToDevice, c->stream));
+    else if (c->gssw_on && (c->kmer_k > 0 || c->path_second_chance))
+    {
+        PG_CUDA(c, c->d_bases_orig.reserve(c->bases_bytes + 16));
+        PG_CUDA(c, cudaMemcpyAsync(c->d_bases_orig.p, c->d_bases.p, c->bases_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        c->have_bases_orig = true;
+    }
+    int max_path_nodes = c->graphs.max_nodes;
+    for (auto const& sp : c->graphs.paths)
+        for (auto const& pth : sp)
+            max_path_nodes = std::max(max_path_nodes, (int)pth.size());
+    c->arena_cap = arena_words(c, max_path_nodes);
+    PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
+    PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
+    c->todo_final = nullptr;
+    c->ntodo_final = nullptr;
+    return PG_OK;
+}
+
+int upload_kmer_index(pg_ctx* c)
+{
+    if (!c->kmer_dirty)
+        return PG_OK;
+    host::KmerIndexHost ix;
+    host::build_kmer_index(c->graphs, c->kmer_k, ix);
+    if (ix.max_paths > KMER_MAX_PATHS)
+        return fail(c, PG_E_GRAPH, "k-mer stage: a site has " + std::to_string(ix.max_paths) + " paths (at most "
+                        + std::to_string(KMER_MAX_PATHS) + ")");
+    c->kmer_max_path_nodes = ix.max_path_nodes;
+    PG_CUDA(c, put(c, c->d_ksites, ix.sites));
+    PG_CUDA(c, put(c, c->d_kpaths, ix.paths));
+    PG_CUDA(c, put(c, c->d_kseqs, ix.seqs));
+    PG_CUDA(c, put(c, c->d_knodes, ix.nodes));
+    PG_CUDA(c, put(c, c->d_kkmers, ix.kmers));
+    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->kmer_dirty = false;
+    return PG_OK;
+}
+
+// grm::KmerAligner over the reads the exact-match stage left (or all reads): one launch
+int run_kmer_stage(pg_ctx* c)
+{
+    int rc = upload_kmer_index(c);
+    if (rc != PG_OK)
+        return rc;
+    PG_CUDA(c, c->d_todo2.reserve((size_t)c->n_reads));
+    PG_CUDA(c, c->d_ntodo2.reserve(1));
+    PG_CUDA(c, c->d_kcount.reserve(2));
+    PG_CUDA(c, cudaMemsetAsync(c->d_ntodo2.p, 0, sizeof(int32_t), c->stream));
+    PG_CUDA(c, cudaMemsetAsync(c->d_kcount.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    for (auto& ev : c->kmer_ev)
+        if (!ev)
+            PG_CUDA(c, cudaEventCreate(&ev));
+    KmerArgs ka;
+    ka.view.sites = c->d_ksites.p;
+    ka.view.paths = c->d_kpaths.p;
+    ka.view.seqs = c->d_kseqs.p;
+    ka.view.nodes = c->d_knodes.p;
+    ka.view.kmers = c->d_kkmers.p;
+    ka.view.k = c->kmer_k;
+    ka.bases = c->d_bases.p;
+    ka.read_off = c->d_off.p;
+    ka.read_site = c->have_sites ? c->d_site.p : nullptr;
+    ka.n_reads = c->n_reads;
+    ka.todo_in = c->todo_final;
+    ka.n_todo_in = c->ntodo_final;
+    ka.todo_out = c->d_todo2.p;
+    ka.n_todo_out = c->d_ntodo2.p;
+    ka.prerev = c->d_prerev.p;
+    ka.records = c->d_records.p;
+    ka.arena = c->d_arena.p;
+    ka.cursor = c->d_cursor.p;
+    ka.arena_cap = c->arena_cap;
+    ka.counters = c->d_kcount.p;
+    ka.no_gssw = c->gssw_on ? 0 : 1;
+    ka.max_len = c->max_len;
+    ka.ops_cap = c->max_len + 2 * c->kmer_max_path_nodes + 8;
+    const int ml = (c->max_len + 3) & ~3;
+    ka.smem_bytes_per_warp = (2 * ml + KMER_WIN / 32 + 2 * ka.ops_cap) * 4 + (KMER_MAX_PATHS + 2) * (int)sizeof(KmerCand) + 6 * ml;
+    ka.smem_bytes_per_warp = (ka.smem_bytes_per_warp + 15) & ~15;
+    const size_t smem = (size_t)KMER_WARPS * ka.smem_bytes_per_warp;
+    PG_CUDA(c, cudaFuncSetAttribute(pg_kmer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PG_CUDA(c, cudaEventRecord(c->kmer_ev[0], c->stream));
+    pg_kmer_kernel<<<(c->n_reads + KMER_WARPS - 1) / KMER_WARPS, KMER_WARPS * 32, smem, c->stream>>>(ka);
+    PG_CUDA(c, cudaGetLastError());
+    ++c->launches;
+    PG_CUDA(c, cudaEventRecord(c->kmer_ev[1], c->stream));
+    c->kmer_ran = true;
+    c->todo_final = c->d_todo2.p;
+    c->ntodo_final = c->d_ntodo2.p;
     return PG_OK;
 }
 
@@ -1976,9 +2202,12 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     PG_CUDA(c, c->d_records.reserve((size_t)c->n_reads));
     PG_CUDA(c, c->d_cursor.reserve(1));
     const int oplog_cap = 2 * c->max_len + 16;
-    c->arena_cap = arena_words(c, max_nodes);
-    PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
-    const bool after_path = c->path_ran; // the exact-match stage already wrote records / op words
+    if (!(c->path_ran || c->kmer_ran)) // (else sized by prepare_front_stages, and partly filled)
+    {
+        c->arena_cap = arena_words(c, max_nodes);
+        PG_CUDA(c, c->d_arena.reserve((size_t)c->arena_cap));
+    }
+    const bool after_path = c->path_ran || c->kmer_ran; // a stage in front already wrote records / op words
     if (!after_path)
         PG_CUDA(c, cudaMemsetAsync(c->d_cursor.p, 0, sizeof(unsigned long long), c->stream));
 
@@ -2088,8 +2317,8 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.stride_ckpt = s_ckpt;
         fa.tout = c->d_tout.p;
         fa.smem_words_per_task = fill_words;
-        fa.todo = after_path ? c->d_todo.p : nullptr;
-        fa.n_todo = after_path ? c->d_ntodo.p : nullptr;
+        fa.todo = after_path ? c->todo_final : nullptr;
+        fa.n_todo = after_path ? c->ntodo_final : nullptr;
         launch_fill(fa, fa.n_tasks, cs);
         PG_CUDA(c, cudaGetLastError());
         if (pairs)
@@ -2262,6 +2491,17 @@ void pg_destroy(pg_ctx* c)
     c->d_pcount.release();
     c->d_prerev.release();
     c->d_bases_orig.release();
+    c->d_ksites.release();
+    c->d_kpaths.release();
+    c->d_kseqs.release();
+    c->d_knodes.release();
+    c->d_kkmers.release();
+    c->d_todo2.release();
+    c->d_ntodo2.release();
+    c->d_kcount.release();
+    for (auto& ev : c->kmer_ev)
+        if (ev)
+            cudaEventDestroy(ev);
     c->d_rvntop.release();
     c->d_req.release();
     c->d_nreq.release();
@@ -2322,6 +2562,7 @@ int pg_add_graph(pg_ctx* c, int32_t n_nodes, const char* blob, const int32_t* of
     c->graphs_dirty = true;
     c->count_dirty = true;
     c->path_dirty = true;
+    c->kmer_dirty = true;
     if (site_id)
         *site_id = id;
     return PG_OK;
@@ -2347,7 +2588,7 @@ int pg_add_graphs(pg_ctx* c, int32_t n_sites, const int32_t* node_ptr, const cha
         }
     }
     if (n_sites > 0)
-        c->graphs_dirty = c->count_dirty = c->path_dirty = true;
+        c->graphs_dirty = c->count_dirty = c->path_dirty = c->kmer_dirty = true;
     if (first_site_id)
         *first_site_id = first;
     return PG_OK;
@@ -2361,6 +2602,7 @@ int pg_clear_graphs(pg_ctx* c)
     c->graphs_dirty = true;
     c->count_dirty = true;
     c->path_dirty = true;
+    c->kmer_dirty = true;
     // the site ids of an uploaded / imported batch name graphs that are gone now: the batch goes with them
     c->uploaded = c->ran = false;
     return PG_OK;
@@ -2459,12 +2701,24 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
     int rc = upload_graphs(c);
     if (rc != PG_OK)
         return rc;
-    c->path_ran = false;
-    if (c->path_k > 0) // grm::CompositeAligner with path matching on: exact matches first, the DP for the rest
+    c->path_ran = c->kmer_ran = false;
+    if (c->path_k > 0 || c->kmer_k > 0) // grm::CompositeAligner's stages in front of gssw (CompositeAligner.cpp:82-126)
     {
-        rc = run_path_stage(c);
+        rc = prepare_front_stages(c);
         if (rc != PG_OK)
             return rc;
+        if (c->path_k > 0) // exact matches first
+        {
+            rc = run_path_stage(c);
+            if (rc != PG_OK)
+                return rc;
+        }
+        if (c->kmer_k > 0) // then gapless alignment to the graph's paths for the rest
+        {
+            rc = run_kmer_stage(c);
+            if (rc != PG_OK)
+                return rc;
+        }
         if (!c->gssw_on)
         {
             c->n_chunks_timed = 0;
@@ -2850,7 +3104,7 @@ int pg_set_stages(pg_ctx* c, int32_t path_kmer_len, int32_t graph_matching, int3
 {
     if (!c || path_kmer_len < 0 || path_kmer_len > 4096)
         return fail(c, PG_E_ARG, "pg_set_stages: bad k-mer length");
-    if (path_kmer_len == 0 && !graph_matching)
+    if (path_kmer_len == 0 && !graph_matching && c->kmer_k == 0)
         return fail(c, PG_E_ARG, "pg_set_stages: no alignment stage enabled");
     if (path_kmer_len != c->path_k)
         c->path_dirty = true;
@@ -2886,6 +3140,54 @@ int pg_path_stats(pg_ctx* c, uint64_t* counters4, float* path_ms)
     }
     if (path_ms)
         *path_ms = c->path_ms;
+    return PG_OK;
+}
+
+int pg_set_paths(pg_ctx* c, int32_t site, int32_t n_paths, const int32_t* path_ptr, const int32_t* path_nodes)
+{
+    if (!c)
+        return PG_E_ARG;
+    std::string err;
+    if (!c->graphs.set_paths(site, n_paths, path_ptr, path_nodes, err))
+        return fail(c, PG_E_GRAPH, err);
+    c->kmer_dirty = true;
+    return PG_OK;
+}
+
+int pg_set_kmer_stage(pg_ctx* c, int32_t kmer_len)
+{
+    if (!c || kmer_len < 0 || kmer_len == 1 || kmer_len > 16)
+        return fail(c, PG_E_ARG, "pg_set_kmer_stage: k-mer length must be 0 (off) or 2..16");
+    if (kmer_len != c->kmer_k)
+        c->kmer_dirty = true;
+    c->kmer_k = kmer_len;
+    return PG_OK;
+}
+
+int pg_kmer_stats(pg_ctx* c, uint64_t* counters2, float* kmer_ms)
+{
+    if (!c)
+        return PG_E_ARG;
+    if (c->kmer_ran)
+    {
+        PG_CUDA(c, cudaSetDevice(c->device));
+        PG_CUDA(c, cudaMemcpyAsync(c->kmer_counters, c->d_kcount.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                   c->stream));
+        PG_CUDA(c, cudaStreamSynchronize(c->stream));
+        cudaEventElapsedTime(&c->kmer_ms, c->kmer_ev[0], c->kmer_ev[1]);
+    }
+    else
+    {
+        c->kmer_counters[0] = c->kmer_counters[1] = 0;
+        c->kmer_ms = 0;
+    }
+    if (counters2)
+    {
+        counters2[0] = c->kmer_counters[0];
+        counters2[1] = c->kmer_counters[1];
+    }
+    if (kmer_ms)
+        *kmer_ms = c->kmer_ms;
     return PG_OK;
 }
 

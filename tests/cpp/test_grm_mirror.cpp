@@ -55,6 +55,34 @@ int main()
         }
         printf("klib-stage-throws %d\n", (int)threw);
 
+        // the k-mer stage (grm::KmerAligner): the reference's own unit test (src/c++/test/test_kmeraligner.cpp:58-191:
+        // K = 10, paths P / Q / D), first the stage alone, then with gssw behind it and the NonUniq filter
+        {
+            const char* kb[6] = { "AAAAAAAATTTTTTTTAAAAAAAA", "TTTTTTAAAAAAAATTTTTTT", "AAAAAGGGGGGGGAAAAAA", "AAAAGGGGGGGGAAAAAA",
+                                  "TTTTTTCCCCCCCCTTTTT", "AAAAAAAAAAAAAAAAAAA" };
+            std::list<Path> kpaths;
+            kpaths.emplace_back(std::vector<uint32_t>{ 0, 1, 3 });
+            kpaths.emplace_back(std::vector<uint32_t>{ 0, 2, 3 });
+            kpaths.emplace_back(std::vector<uint32_t>{ 0, 3 });
+            for (int with_gssw = 0; with_gssw < 2; ++with_gssw)
+            {
+                std::vector<std::unique_ptr<Read>> kr;
+                for (int i = 0; i < 6; ++i)
+                {
+                    kr.emplace_back(new Read());
+                    kr.back()->setCoreInfo("q" + std::to_string(i + 1), kb[i], std::string(strlen(kb[i]), '#'));
+                }
+                grm::CompositeAligner ka(false, with_gssw != 0, false, true, grm::GraphAligner::AF_ALL, 0, 32, 10);
+                ka.setGraph(&graph, kpaths);
+                ka.alignReads(kr.begin(), kr.end(), filter);
+                for (auto const& r : kr)
+                    printf("%s %d %s %d %d %d %s %d\n", r->fragment_id().c_str(), r->graph_pos(), r->graph_cigar().c_str(),
+                           r->graph_alignment_score(), r->graph_mapq(), (int)r->is_graph_reverse_strand(), r->bases().c_str(),
+                           (int)r->graph_mapping_status());
+                printf("kmer-stage %u %u %u %u\n", ka.attempted(), ka.mappedKmers(), ka.mappedSw(), ka.filtered());
+            }
+        }
+
         // alignAndDisambiguate's core on the device: ParagraphTest.Aligns expects these supports
         // (test_paragraph_parts.cpp:113-144; the test calls disambiguateReads with null filters)
         {

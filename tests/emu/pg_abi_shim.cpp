@@ -17,8 +17,9 @@ struct pg_ctx
 {
     std::string err;
     host::GraphStore graphs;
-    int path_k = 0;
+    int path_k = 0, kmer_k = 0;
     bool gssw_on = true, second = false;
+    uint64_t kmer_counters[2] = { 0, 0 };
     // the last batch
     bool ran = false, have_sites = false;
     int n_reads = 0;
@@ -111,11 +112,40 @@ int pg_set_stages(pg_ctx* c, int32_t path_kmer_len, int32_t graph_matching, int3
 {
     if (!c || path_kmer_len < 0 || path_kmer_len > 4096)
         return shim_fail(c, PG_E_ARG, "pg_set_stages: bad k-mer length");
-    if (path_kmer_len == 0 && !graph_matching)
+    if (path_kmer_len == 0 && !graph_matching && c->kmer_k == 0)
         return shim_fail(c, PG_E_ARG, "pg_set_stages: no alignment stage enabled");
     c->path_k = path_kmer_len;
     c->gssw_on = graph_matching != 0;
     c->second = nonuniq_second_chance != 0;
+    return PG_OK;
+}
+int pg_set_paths(pg_ctx* c, int32_t site, int32_t n_paths, const int32_t* path_ptr, const int32_t* path_nodes)
+{
+    if (!c)
+        return PG_E_ARG;
+    std::string err;
+    if (!c->graphs.set_paths(site, n_paths, path_ptr, path_nodes, err))
+        return shim_fail(c, PG_E_GRAPH, err);
+    return PG_OK;
+}
+int pg_set_kmer_stage(pg_ctx* c, int32_t kmer_len)
+{
+    if (!c || kmer_len < 0 || kmer_len == 1 || kmer_len > 16)
+        return shim_fail(c, PG_E_ARG, "pg_set_kmer_stage: k-mer length must be 0 (off) or 2..16");
+    c->kmer_k = kmer_len;
+    return PG_OK;
+}
+int pg_kmer_stats(pg_ctx* c, uint64_t* counters2, float* kmer_ms)
+{
+    if (!c)
+        return PG_E_ARG;
+    if (counters2)
+    {
+        counters2[0] = c->kmer_counters[0];
+        counters2[1] = c->kmer_counters[1];
+    }
+    if (kmer_ms)
+        *kmer_ms = 0.f;
     return PG_OK;
 }
 int pg_path_stats(pg_ctx* c, uint64_t* counters4, float* path_ms)
@@ -155,6 +185,22 @@ int pg_align_batch(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t*
     host::PathIndexHost ix;
     if (c->path_k > 0)
         host::build_path_index(gs, c->path_k, ix);
+    host::KmerIndexHost kix;
+    KmerView kv;
+    memset(&kv, 0, sizeof kv);
+    if (c->kmer_k > 0)
+    {
+        host::build_kmer_index(gs, c->kmer_k, kix);
+        if (kix.max_paths > KMER_MAX_PATHS)
+            return shim_fail(c, PG_E_GRAPH, "k-mer stage: too many paths on a site");
+        kv.sites = kix.sites.data();
+        kv.paths = kix.paths.data();
+        kv.seqs = kix.seqs.data();
+        kv.nodes = kix.nodes.data();
+        kv.kmers = kix.kmers.data();
+        kv.k = c->kmer_k;
+    }
+    c->kmer_counters[0] = c->kmer_counters[1] = 0;
     c->n_reads = n_reads;
     c->have_sites = site != nullptr;
     c->read_off.assign(off, off + n_reads + 1);
@@ -175,7 +221,9 @@ int pg_align_batch(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t*
         memset(&rec, 0, sizeof rec);
         std::vector<uint32_t> ops;
         std::vector<uint8_t> q0((size_t)L + 1), q1((size_t)L + 1);
-        bool to_dp = true, prerev = false;
+        bool to_dp = true;
+        int flips = 0; // reverse complements the stages in front applied to the bases (the later stages see them)
+        std::vector<uint8_t> cur(b, b + L), tmp;
         if (c->path_k > 0)
         {
             const PathView v = make_path_view(ix.sites[(size_t)s], sd, ix.table.data(), ix.lists.data(), ix.succ.data(), gb, gi);
@@ -188,14 +236,46 @@ int pg_align_batch(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t*
             ++c->path_counters[0];
             c->path_counters[1] += r.n_matches > 0;
             c->path_counters[2] += r.n_full > 0;
-            if (r.n_full > 1 && c->second && c->gssw_on)
-                prerev = r.strand != 0; // the DP gets the bases PathAligner left behind
+            if (r.n_full > 1 && c->second && (c->gssw_on || c->kmer_k > 0))
+            {
+                if (r.strand != 0) // the later stages get the bases PathAligner left behind
+                {
+                    cur.assign(q1.begin(), q1.begin() + L);
+                    ++flips;
+                }
+            }
             else if (r.n_full > 0)
             {
                 path_record(r, L, rec);
                 ops.resize((size_t)r.first.n_nodes);
                 path_emit(v, r.strand ? q1.data() : q0.data(), L, r, ops.data());
                 to_dp = false;
+            }
+        }
+        if (to_dp && c->kmer_k > 0) // pg_kmer_kernel
+        {
+            const KmerResult kr = emu_kmer_one(kv, s, cur.data(), L, kix.max_path_nodes, ops, tmp);
+            ++c->kmer_counters[0];
+            if (kr.status == 1 || (kr.status == 2 && !c->gssw_on))
+            {
+                rec.graph_pos = kr.pos;
+                rec.score = (int16_t)kr.score;
+                rec.query_clipped = (uint16_t)kr.clipped;
+                rec.unique = (uint8_t)(kr.status == 1);
+                rec.chose_reverse = (uint8_t)kr.rev;
+                rec.mapped_by = (uint8_t)(flips ? STAGE_KMER_REV : STAGE_KMER);
+                rec.cigar_len = (uint32_t)ops.size();
+                c->kmer_counters[1] += kr.status == 1;
+                to_dp = false;
+            }
+            else
+            {
+                ops.clear();
+                if (kr.status == 2 && kr.rev)
+                {
+                    cur = tmp;
+                    ++flips;
+                }
             }
         }
         if (to_dp && !c->gssw_on)
@@ -205,10 +285,10 @@ int pg_align_batch(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t*
         }
         if (to_dp)
         {
-            const int rc = shim_dp(sd, gb, gi, prerev ? q1.data() : b, L, flags, rec, ops);
+            const int rc = shim_dp(sd, gb, gi, cur.data(), L, flags, rec, ops);
             if (rc)
                 return shim_fail(c, PG_E_ARG, "emulator failure " + std::to_string(rc));
-            rec.mapped_by = (uint8_t)(prerev ? STAGE_GSSW_REV : STAGE_GSSW);
+            rec.mapped_by = (uint8_t)(flips == 0 ? STAGE_GSSW : (flips == 1 ? STAGE_GSSW_REV : STAGE_GSSW_REV2));
         }
         rec.cigar_off = (uint32_t)c->arena.size();
         c->arena.insert(c->arena.end(), ops.begin(), ops.begin() + rec.cigar_len);

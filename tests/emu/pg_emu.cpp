@@ -287,6 +287,38 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
 
 namespace
 {
+// the k-mer stage (pg_kmer.cuh) for one read, the group being a single lane; ops = the op words of a mapped read
+KmerResult emu_kmer_one(const KmerView& v, int site, const uint8_t* bases, int L, int max_path_nodes, std::vector<uint32_t>& ops,
+                        std::vector<uint8_t>& rv_out)
+{
+    const int ops_cap = L + 2 * max_path_nodes + 8;
+    std::vector<uint32_t> km0((size_t)L + 1), km1((size_t)L + 1), bitmap(KMER_WIN / 32), ob((size_t)ops_cap), ot((size_t)ops_cap);
+    std::vector<uint8_t> bytes((size_t)6 * (L + 1));
+    std::vector<KmerCand> heap(KMER_MAX_PATHS + 2);
+    KmerScratch sc;
+    sc.km[0] = km0.data();
+    sc.km[1] = km1.data();
+    sc.bitmap = bitmap.data();
+    sc.ops_best = ob.data();
+    sc.ops_tmp = ot.data();
+    sc.heap = heap.data();
+    for (int x = 0; x < 2; ++x)
+    {
+        sc.seq[x] = bytes.data() + (size_t)x * (L + 1);
+        sc.valid[x] = bytes.data() + (size_t)(2 + x) * (L + 1);
+        sc.first[x] = bytes.data() + (size_t)(4 + x) * (L + 1);
+    }
+    sc.ops_cap = ops_cap;
+    const KmerResult r = kmer_align_read(v, site, bases, L, 0, 1, sc);
+    ops.assign(ob.begin(), ob.begin() + (r.status ? std::min(r.n_ops, ops_cap) : 0));
+    rv_out.assign(sc.seq[1], sc.seq[1] + L);
+    return r;
+}
+
+} // namespace
+
+namespace
+{
 int g_geom_w = 32; // lanes per task used by the emulator (the kernels' default), see pgemu_set_geometry
 }
 
@@ -613,6 +645,65 @@ int pgemu_count_site(int n_nodes, const char* seq_blob, const int32_t* seq_off, 
         w += 4 + 4 * n;
     }
     *family_used = w;
+    return 0;
+}
+
+// grm::KmerAligner<k> through the device source of pg_kmer.cuh.  out8 per read = {status (0 unmapped, 1 mapped, 2 not
+// unique), graph_pos, score, unique, mapq, is_graph_reverse_strand, cigar_strlen, 0}; out_bases = the read's bases after
+// the stage (reverse complement when the best candidate is on the reverse strand)
+int pgemu_kmer_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off, int n_edges, const int32_t* efrom,
+                           const int32_t* eto, int n_paths, const int32_t* path_ptr, const int32_t* path_nodes, int k,
+                           int n_reads, const char* bases_blob, const int32_t* read_off, const uint8_t* is_rev, int32_t* out8,
+                           char* out_bases_blob, char* cigars, int cigar_stride)
+{
+    host::GraphStore gs;
+    std::string err;
+    if (gs.add(n_nodes, seq_blob, seq_off, n_edges, efrom, eto, err) < 0 || !gs.set_paths(0, n_paths, path_ptr, path_nodes, err))
+        return -1;
+    if (n_paths > KMER_MAX_PATHS)
+        return -3;
+    host::KmerIndexHost ix;
+    host::build_kmer_index(gs, k, ix);
+    KmerView v;
+    v.sites = ix.sites.data();
+    v.paths = ix.paths.data();
+    v.seqs = ix.seqs.data();
+    v.nodes = ix.nodes.data();
+    v.kmers = ix.kmers.data();
+    v.k = k;
+    for (int i = 0; i < n_reads; ++i)
+    {
+        const uint8_t* b = (const uint8_t*)bases_blob + read_off[i];
+        const int L = read_off[i + 1] - read_off[i];
+        std::vector<uint32_t> ops;
+        std::vector<uint8_t> rv;
+        const KmerResult r = emu_kmer_one(v, 0, b, L, ix.max_path_nodes, ops, rv);
+        int32_t* o = out8 + 8 * i;
+        memset(o, 0, 8 * sizeof(int32_t));
+        o[0] = r.status;
+        if (out_bases_blob)
+            memcpy(out_bases_blob + read_off[i], (r.status && r.rev) ? rv.data() : b, (size_t)L);
+        if (cigars)
+            cigars[(size_t)i * cigar_stride] = 0;
+        if (!r.status)
+            continue;
+        Record rec;
+        memset(&rec, 0, sizeof rec);
+        rec.cigar_len = (uint32_t)ops.size();
+        const std::string cs = host::format_cigar(rec, ops.data());
+        o[1] = r.pos;
+        o[2] = r.score;
+        o[3] = r.status == 1;
+        o[4] = r.status == 1 ? 60 : 0;
+        o[5] = r.rev ? !(is_rev && is_rev[i]) : (is_rev && is_rev[i]);
+        o[6] = (int32_t)cs.size();
+        if (cigars && cigar_stride > 0)
+        {
+            const size_t m = std::min((size_t)cigar_stride - 1, cs.size());
+            memcpy(cigars + (size_t)i * cigar_stride, cs.data(), m);
+            cigars[(size_t)i * cigar_stride + m] = 0;
+        }
+    }
     return 0;
 }
 }

@@ -25,6 +25,9 @@
 #define pg_count_stats pgshim_count_stats
 #define pg_set_stages pgshim_set_stages
 #define pg_path_stats pgshim_path_stats
+#define pg_set_paths pgshim_set_paths
+#define pg_set_kmer_stage pgshim_set_kmer_stage
+#define pg_kmer_stats pgshim_kmer_stats
 #define pg_stats pgshim_stats
 #define pg_version pgshim_version
 #endif

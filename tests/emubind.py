@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "emu", "libpgemu.so")
 SRC = [os.path.join(HERE, "emu", "pg_emu.cpp"), os.path.join(ROOT, "paragraph_b200", "csrc", "pg_core.cuh"),
+       os.path.join(ROOT, "paragraph_b200", "csrc", "pg_kmer.cuh"), os.path.join(ROOT, "paragraph_b200", "csrc", "pg_path.cuh"),
        os.path.join(ROOT, "paragraph_b200", "csrc", "pg_host.hpp"),
        os.path.join(ROOT, "paragraph_b200", "csrc", "pg_count.cuh")]
 CIGAR_STRIDE = 4096
@@ -175,3 +176,25 @@ def emu_path_align_batch(node_seqs, edges, reads, kmer_len=32):
         res.append(dict(mapped=bool(o[0]), pos=int(o[1]), score=int(o[2]), unique=bool(o[3]), mapq=int(o[4]),
                         graph_reverse=bool(o[5]), bases=raw[roff[i]:roff[i + 1]].decode("latin-1"), cigar=c))
     return res, tuple(int(x) for x in cnt)
+
+
+def emu_kmer_align_batch(node_seqs, edges, paths, reads, kmer_len=16, is_rev=None):
+    """grm::KmerAligner<k> through the device source (pg_kmer.cuh) -> result dicts like refbind.ref_kmer_align_batch"""
+    from oracle import refbind as R
+    l = lib()
+    l.pgemu_kmer_align_batch.restype = C.c_int
+    blob, off, ef, et = R.pack_graph(node_seqs, edges)
+    pptr, pnodes = R.pack_paths(paths)
+    rblob, roff = R.pack_reads(reads)
+    n = len(reads)
+    out = np.zeros((max(n, 1), 8), dtype=np.int32)
+    ob = C.create_string_buffer(max(1, len(rblob)))
+    cg = C.create_string_buffer(max(1, n * CIGAR_STRIDE))
+    rv = None if is_rev is None else np.asarray(is_rev, dtype=np.uint8)
+    rc = l.pgemu_kmer_align_batch(C.c_int(len(node_seqs)), blob, _p(off, C.c_int32), C.c_int(len(edges)), _p(ef, C.c_int32),
+                                  _p(et, C.c_int32), C.c_int(len(paths)), _p(pptr, C.c_int32), _p(pnodes, C.c_int32),
+                                  C.c_int(int(kmer_len)), C.c_int(n), rblob, _p(roff, C.c_int32),
+                                  None if rv is None else _p(rv, C.c_uint8), _p(out, C.c_int32), ob, cg, C.c_int(CIGAR_STRIDE))
+    if rc != 0:
+        raise RuntimeError("emulator: pgemu_kmer_align_batch rc=%d" % rc)
+    return R._kmer_collect(out, ob, cg, roff, n)

@@ -459,12 +459,11 @@ def test_staged_api_is_idempotent_with_second_chance(ctx):
     from test_path_oracle import path_cases
     rng = np.random.default_rng(53)
     flipped = 0
-    # a bubble whose two branches carry the same sequence: a read across it matches two paths exactly (not unique), and
-    # given reverse-complemented it is the reverse strand that matches -> second chance with flipped bases
-    lf, mid, rf = synth.random_seq(rng, 60), synth.random_seq(rng, 40), synth.random_seq(rng, 60)
-    twin = ([lf, mid, mid, rf], [(0, 1), (0, 2), (1, 3), (2, 3)])
-    hap = lf + mid + rf
-    twin_reads = [synth.revcomp(hap[i:i + 100]) for i in range(0, 60, 7)] + [hap[i:i + 100] for i in range(0, 60, 11)]
+    # an inversion bubble: a read inside the inverted segment matches one branch as given and the other one reverse-
+    # complemented -- two full-length exact matches, not unique -> second chance in the DP
+    lf, mid, rf = synth.random_seq(rng, 60), synth.random_seq(rng, 90), synth.random_seq(rng, 60)
+    twin = ([lf, mid, synth.revcomp(mid), rf], [(0, 1), (0, 2), (1, 3), (2, 3)])
+    twin_reads = [mid[i:i + 60] for i in range(0, 30, 5)] + [synth.revcomp(mid[i:i + 60]) for i in range(0, 30, 7)]
     try:
         for nodes, edges, reads, k in [(twin[0], twin[1], twin_reads, 16)] + list(path_cases(rng, 60)):
             ctx.clear_graphs()

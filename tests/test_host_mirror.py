@@ -71,6 +71,25 @@ def _check_output(stdout):
         "f6 0 0[11M]3[8M] 19 60 0 AAAAAAAAAAAAAAAAAAA 1",
         "klib-stage-throws 1",
     ]
+    # the k-mer stage: the reference's unit test (test_kmeraligner.cpp:149-191) through CompositeAligner(kmer = true,
+    # K = 10): alone (q6, the repeat, is BAD_ALIGN with the fields KmerAligner leaves), then with gssw behind it
+    ql = [l for l in lines if l.startswith("q") or l.startswith("kmer-stage")]
+    lines = [l for l in lines if l not in ql]
+    assert ql == [
+        "q1 3 0[8M]1[8M]3[8M] 24 60 0 AAAAAAAATTTTTTTTAAAAAAAA 1",
+        "q2 4 0[7M]1[8M]3[6M] 21 60 1 AAAAAAATTTTTTTTAAAAAA 1",
+        "q3 6 0[5M]2[8M]3[6M] 19 60 0 AAAAAGGGGGGGGAAAAAA 1",
+        "q4 7 0[4M]2[8M]3[6M] 18 60 0 AAAAGGGGGGGGAAAAAA 1",
+        "q5 6 0[5M]2[8M]3[6M] 19 60 1 AAAAAGGGGGGGGAAAAAA 1",
+        "q6 0 0[11M]3[8M] 19 0 0 AAAAAAAAAAAAAAAAAAA 2",
+        "kmer-stage 6 5 0 0",
+        "q1 3 0[8M]1[8M]3[8M] 24 60 0 AAAAAAAATTTTTTTTAAAAAAAA 1",
+        "q2 4 0[7M]1[8M]3[6M] 21 60 1 AAAAAAATTTTTTTTAAAAAA 1",
+        "q3 6 0[5M]2[8M]3[6M] 19 60 0 AAAAAGGGGGGGGAAAAAA 1",
+        "q4 7 0[4M]2[8M]3[6M] 18 60 0 AAAAGGGGGGGGAAAAAA 1",
+        "q5 6 0[5M]2[8M]3[6M] 19 60 1 AAAAAGGGGGGGGAAAAAA 1",
+        "q6 0 0[11M]3[8M] 19 60 0 AAAAAAAAAAAAAAAAAAA 1",
+        "kmer-stage 6 5 1 0"]
     # alignAndCount: supports as ParagraphTest.Aligns expects them (test_paragraph_parts.cpp:113-144), f7 filtered
     # (nonuniq); counts as the reference build gives them for these six single-read fragments
     kl = [l for l in lines if l[:2] in ("k ", "kn", "ke")]

@@ -94,3 +94,23 @@ def test_oracle_vs_compiled_reference_fuzz(built, k):
         bad += sum(e["status"] == "bad_align" for e in exp)
         assert cnt == (len(reads), sum(e["status"] == "mapped" for e in exp))
     assert mapped > n // 5 and bad > 20 and mapped + bad < n
+
+
+def test_device_source_reproduces_the_reference_unit_test(built):
+    """pg_kmer.cuh (the kernel's source compiled for the host, one lane per group) on the same vectors"""
+    import emubind
+    assert emubind.emu_kmer_align_batch(UNIT_NODES, UNIT_EDGES, UNIT_PATHS, UNIT_READS, 10) == UNIT_EXPECTED
+
+
+@pytest.mark.parametrize("k", [10, 16, 5])
+def test_device_source_vs_oracle_fuzz(built, k):
+    import emubind
+    rng = np.random.default_rng(2000 + k)
+    n = 0
+    for nodes, edges, paths, reads in kmer_cases(rng, 250):
+        isrev = [int(x) for x in rng.integers(0, 2, size=len(reads))]
+        exp = R.OracleKmerIndex(nodes, edges, paths, k).align_batch(reads, is_rev=isrev)
+        got = emubind.emu_kmer_align_batch(nodes, edges, paths, reads, k, is_rev=isrev)
+        assert got == exp, (nodes, edges, paths, k, [(r, g, e) for r, g, e in zip(reads, got, exp) if g != e][:2])
+        n += len(reads)
+    assert n > 3000
