@@ -19,8 +19,10 @@
 #pragma once
 #include <algorithm>
 #include <climits>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <deque>
 #include <exception>
 #include <functional>
 #include <future>
@@ -191,39 +193,122 @@ namespace grm
 
 namespace detail
 {
+// Worker threads shared by every aligner of the process (created on first use, grown on demand, joined at exit):
+// grm::alignReads is called once per (sample, target) with a few hundred to a few thousand reads, and starting
+// `threads` std::threads twice per call (pack, write-back) costs more than the work they do.
+class WorkerPool
+{
+public:
+    static WorkerPool& instance()
+    {
+        static WorkerPool p;
+        return p;
+    }
+    // run job(0) .. job(n_jobs - 1); job 0 on the calling thread, the others on pool threads.  Rethrows the first exception.
+    template <typename F> void run(size_t n_jobs, F&& job)
+    {
+        if (n_jobs <= 1)
+        {
+            if (n_jobs == 1)
+                job((size_t)0);
+            return;
+        }
+        Batch batch;
+        batch.left = n_jobs - 1;
+        batch.fn = [&job](size_t k) { job(k); };
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            while (threads_.size() < std::min<size_t>(n_jobs - 1, 256))
+                threads_.emplace_back([this] { loop(); });
+            for (size_t k = 1; k < n_jobs; ++k)
+                queue_.emplace_back(&batch, k);
+        }
+        cv_.notify_all();
+        std::exception_ptr mine;
+        try
+        {
+            job((size_t)0);
+        }
+        catch (...)
+        {
+            mine = std::current_exception();
+        }
+        {
+            std::unique_lock<std::mutex> lock(m_);
+            batch.done.wait(lock, [&batch] { return batch.left == 0; });
+        }
+        if (mine)
+            std::rethrow_exception(mine);
+        if (batch.err)
+            std::rethrow_exception(batch.err);
+    }
+    ~WorkerPool()
+    {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_)
+            t.join();
+    }
+
+private:
+    struct Batch
+    {
+        std::function<void(size_t)> fn;
+        size_t left = 0;
+        std::exception_ptr err;
+        std::condition_variable done;
+    };
+    void loop()
+    {
+        std::unique_lock<std::mutex> lock(m_);
+        for (;;)
+        {
+            cv_.wait(lock, [this] { return stop_ || !queue_.empty(); });
+            if (queue_.empty())
+                return; // stop_
+            const std::pair<Batch*, size_t> item = queue_.front();
+            queue_.pop_front();
+            lock.unlock();
+            std::exception_ptr err;
+            try
+            {
+                item.first->fn(item.second);
+            }
+            catch (...)
+            {
+                err = std::current_exception();
+            }
+            lock.lock();
+            if (err && !item.first->err)
+                item.first->err = err;
+            if (--item.first->left == 0)
+                item.first->done.notify_all();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::pair<Batch*, size_t>> queue_;
+    std::vector<std::thread> threads_;
+    bool stop_ = false;
+};
+
 // fn(begin, end) over [0, n) on up to `threads` host threads (the `threads` argument of grm::alignReads, Align.cpp:119:
 // the reference spends it on aligning, here it packs the batch and writes the results back -- at 5 M reads/s on the
-// device the ~0.7 us a single thread needs per read for that is what a caller would otherwise wait for).  Every index
+// device the ~0.3 us a single thread needs per read for that is what a caller would otherwise wait for).  Every index
 // belongs to exactly one thread, so the outcome does not depend on `threads`; the first exception is rethrown.
 template <typename F> void parallelFor(size_t n, unsigned threads, F&& fn)
 {
-    const size_t min_chunk = 1024;
+    const size_t min_chunk = 512;
     const size_t nt = std::min<size_t>(threads ? threads : 1, (n + min_chunk - 1) / min_chunk);
     if (nt <= 1)
     {
         fn((size_t)0, n);
         return;
     }
-    std::vector<std::thread> pool;
-    std::exception_ptr err;
-    std::mutex m;
-    for (size_t t = 0; t < nt; ++t)
-        pool.emplace_back([&, t] {
-            try
-            {
-                fn(n * t / nt, n * (t + 1) / nt);
-            }
-            catch (...)
-            {
-                std::lock_guard<std::mutex> lock(m);
-                if (!err)
-                    err = std::current_exception();
-            }
-        });
-    for (auto& th : pool)
-        th.join();
-    if (err)
-        std::rethrow_exception(err);
+    WorkerPool::instance().run(nt, [&](size_t t) { fn(n * t / nt, n * (t + 1) / nt); });
 }
 
 // page-locked staging (pg_host_alloc), grown geometrically and reused between batches: the library copies such
@@ -496,12 +581,46 @@ public:
         }
     }
 
-    // extractCigar (GraphAligner.cpp:88-108) of one record into `out`
+    // extractCigar (GraphAligner.cpp:88-108) of one record into `out`: "<node>[<len><op>...]..." from the op words
+    // (the layout of include/pg_align.h; same text as pg_format_cigar, without a round trip through the C-ABI)
     static void formatCigar(pg_record const& r, const uint32_t* ops, std::string& out)
     {
-        out.resize((size_t)12 * (r.cigar_len + 2));
-        const int n = pg_format_cigar(&r, ops, &out[0], (int)out.size());
-        out.resize((size_t)std::min<int>(n, (int)out.size() - 1));
+        out.resize((size_t)12 * r.cigar_len + 16);
+        char* const base = &out[0];
+        char* p = base;
+        auto num = [&p](uint32_t v) {
+            char tmp[12];
+            int n = 0;
+            do
+            {
+                tmp[n++] = (char)('0' + v % 10);
+                v /= 10;
+            } while (v);
+            while (n)
+                *p++ = tmp[--n];
+        };
+        static const char OPS[8] = { 'M', 'X', 'N', 'I', 'D', 'S', '?', '?' };
+        uint32_t node = 0xFFFFFFFFu;
+        for (uint32_t i = 0; i < r.cigar_len; ++i)
+        {
+            const uint32_t w = ops[r.cigar_off + i];
+            if (PG_CIGAR_NODE(w) != node)
+            {
+                if (node != 0xFFFFFFFFu)
+                    *p++ = ']';
+                node = PG_CIGAR_NODE(w);
+                num(node);
+                *p++ = '[';
+            }
+            if (PG_CIGAR_OP(w) != PG_OP_NONE)
+            {
+                num(PG_CIGAR_LEN(w));
+                *p++ = OPS[PG_CIGAR_OP(w)];
+            }
+        }
+        if (node != 0xFFFFFFFFu)
+            *p++ = ']';
+        out.resize((size_t)(p - base));
     }
 
     pg_ctx* context() const { return engine_->get(); }
