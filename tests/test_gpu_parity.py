@@ -479,7 +479,7 @@ def test_staged_api_is_idempotent_with_second_chance(ctx):
             for f in ("graph_pos", "score", "unique", "chose_reverse", "status", "mapped_by", "cigar_len"):
                 assert (rec0[f] == rec1[f]).all(), (f, k)
             assert [capi.format_cigar(r, ops0) for r in rec0] == [capi.format_cigar(r, ops1) for r in rec1]
-                flipped += int((rec0["mapped_by"] != 1).sum())
+            flipped += int((rec0["mapped_by"] != 1).sum())
         assert flipped > 0  # reads that went on to the DP
     finally:
         ctx.set_stages(0, True)
