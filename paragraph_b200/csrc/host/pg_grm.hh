@@ -18,6 +18,7 @@
 // the batch into page-locked staging and write the records back into the reads.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <condition_variable>
 #include <cstdint>
@@ -234,8 +235,18 @@ public:
             mine = std::current_exception();
         }
         {
+            // wait for the others -- and work the queue meanwhile, so that jobs that themselves call run() (a pipelined
+            // batch: two halves, each with its own parallel pack / write-back) can never starve each other
             std::unique_lock<std::mutex> lock(m_);
-            batch.done.wait(lock, [&batch] { return batch.left == 0; });
+            while (batch.left != 0)
+            {
+                if (queue_.empty())
+                {
+                    batch.done.wait(lock);
+                    continue;
+                }
+                execute_front(lock);
+            }
         }
         if (mine)
             std::rethrow_exception(mine);
@@ -261,6 +272,26 @@ private:
         std::exception_ptr err;
         std::condition_variable done;
     };
+    void execute_front(std::unique_lock<std::mutex>& lock) // takes one queued job; called and returns with the lock held
+    {
+        const std::pair<Batch*, size_t> item = queue_.front();
+        queue_.pop_front();
+        lock.unlock();
+        std::exception_ptr err;
+        try
+        {
+            item.first->fn(item.second);
+        }
+        catch (...)
+        {
+            err = std::current_exception();
+        }
+        lock.lock();
+        if (err && !item.first->err)
+            item.first->err = err;
+        if (--item.first->left == 0)
+            item.first->done.notify_all();
+    }
     void loop()
     {
         std::unique_lock<std::mutex> lock(m_);
@@ -269,23 +300,7 @@ private:
             cv_.wait(lock, [this] { return stop_ || !queue_.empty(); });
             if (queue_.empty())
                 return; // stop_
-            const std::pair<Batch*, size_t> item = queue_.front();
-            queue_.pop_front();
-            lock.unlock();
-            std::exception_ptr err;
-            try
-            {
-                item.first->fn(item.second);
-            }
-            catch (...)
-            {
-                err = std::current_exception();
-            }
-            lock.lock();
-            if (err && !item.first->err)
-                item.first->err = err;
-            if (--item.first->left == 0)
-                item.first->done.notify_all();
+            execute_front(lock);
         }
     }
     std::mutex m_;
@@ -457,33 +472,58 @@ public:
     static const unsigned int AF_ALL = (unsigned int)-1;
 
     explicit GraphAligner(int device = 0) : engine_(Engine::take(device)) {}
-    ~GraphAligner() { Engine::give(std::move(engine_)); }
+    ~GraphAligner()
+    {
+        Engine::give(std::move(engine_));
+        Engine::give(std::move(engine2_));
+    }
     GraphAligner(GraphAligner const&) = delete;
     GraphAligner& operator=(GraphAligner const&) = delete;
 
     // GraphAligner::setGraph (GraphAligner.cpp:277-285); the reversed graph is derived by the engine
     template <typename GraphT> void setGraph(GraphT const* g)
     {
-        std::string blob;
-        std::vector<int32_t> off{ 0 }, ef, et;
+        blob_.clear();
+        off_.assign(1, 0);
+        ef_.clear();
+        et_.clear();
         const int32_t n = (int32_t)g->numNodes();
         for (int32_t i = 0; i < n; ++i)
         {
-            blob += g->nodeSeq((uint32_t)i);
-            off.push_back((int32_t)blob.size());
+            blob_ += g->nodeSeq((uint32_t)i);
+            off_.push_back((int32_t)blob_.size());
             for (auto p : g->predecessors((uint32_t)i))
             {
-                ef.push_back((int32_t)p);
-                et.push_back(i);
+                ef_.push_back((int32_t)p);
+                et_.push_back(i);
             }
         }
-        engine_->check(pg_clear_graphs(engine_->get()));
-        int32_t sid = -1;
-        engine_->check(pg_add_graph(engine_->get(), n, blob.data(), off.data(), (int32_t)ef.size(), ef.data(), et.data(), &sid));
+        path_ptr_.clear();
+        path_nodes_.clear();
+        registerGraph(*engine_);
+        engine2_fresh_ = false;
+    }
+    // the stages in front of gssw and the paths the k-mer stage aligns to (pg_set_stages / pg_set_kmer_stage / pg_set_paths):
+    // kept here so that a second engine can be brought to the same configuration
+    void setStages(int path_kmer_len, bool graph_matching, bool nonuniq_second_chance, int kmer_len)
+    {
+        path_k_ = path_kmer_len;
+        graph_on_ = graph_matching;
+        second_ = nonuniq_second_chance;
+        kmer_k_ = kmer_len;
+    }
+    void setPaths(std::vector<int32_t> ptr, std::vector<int32_t> nodes)
+    {
+        path_ptr_ = std::move(ptr);
+        path_nodes_ = std::move(nodes);
+        engine_->check(pg_set_paths(engine_->get(), 0, (int32_t)path_ptr_.size() - 1, path_ptr_.data(), path_nodes_.data()));
+        engine2_fresh_ = false;
     }
 
     // the loop `for read: alignRead(read, flags)` as one batch; writes the fields GraphAligner::alignRead writes
     // (GraphAligner.cpp:358-401).  ReadIt iterates over (smart) pointers to reads; empty reads are skipped.
+    // A batch of a few thousand reads or more is cut in two halves that run on two engines from two host threads: the
+    // packing and the write-back of one half (strings: reverse complements, CIGAR text) overlap the kernels of the other.
     template <typename ReadIt>
     void alignBatch(ReadIt begin, ReadIt end, unsigned flags = AF_ALL, std::vector<pg_record>* records_out = nullptr,
                     bool tolerate_unmapped = false) const
@@ -494,22 +534,53 @@ public:
                 which.push_back(it);
         if (which.empty())
             return;
-        Engine& e = *engine_;
         const size_t n = which.size();
-        const size_t bytes = e.pack(n, threads_, [&](size_t i) -> std::string const& { return (*which[i])->bases(); });
-        pg_record* rec = e.rec.reserve(n);
-        const size_t ops_cap = bytes + 16 * n + 64;
-        uint32_t* ops = e.ops.reserve(ops_cap);
-        uint64_t used = 0;
-        e.check(pg_align_batch(e.get(), (int32_t)n, e.blob.data(), e.off.data(), nullptr, flags, rec, ops, ops_cap, &used));
-        if (records_out) // e.g. for paragraph::DefaultReadFilter, which needs query_clipped
-            records_out->assign(rec, rec + n);
-        detail::parallelFor(n, threads_, [&](size_t lo, size_t hi) {
-            for (size_t i = lo; i < hi; ++i)
-                if (!(tolerate_unmapped && rec[i].status == 3)) // 3: no enabled stage mapped the read -- it stays UNMAPPED
-                    applyRecord(**which[i], rec[i], ops, flags, i);
-        });
+        if (records_out)
+            records_out->resize(n);
+        anchored_ = 0;
+        auto half = [&](Engine& e, size_t lo, size_t hi, unsigned threads) {
+            const size_t m = hi - lo;
+            e.check(pg_set_kmer_stage(e.get(), kmer_k_));
+            e.check(pg_set_stages(e.get(), path_k_, graph_on_ ? 1 : 0, second_ ? 1 : 0));
+            const size_t bytes = e.pack(m, threads, [&](size_t i) -> std::string const& { return (*which[lo + i])->bases(); });
+            pg_record* rec = e.rec.reserve(m);
+            const size_t ops_cap = bytes + 16 * m + 64;
+            uint32_t* ops = e.ops.reserve(ops_cap);
+            uint64_t used = 0;
+            e.check(pg_align_batch(e.get(), (int32_t)m, e.blob.data(), e.off.data(), nullptr, flags, rec, ops, ops_cap, &used));
+            if (path_k_ > 0) // PathAligner::anchored of this half
+            {
+                uint64_t cnt[4] = { 0, 0, 0, 0 };
+                e.check(pg_path_stats(e.get(), cnt, nullptr));
+                anchored_ += cnt[1];
+            }
+            if (records_out) // e.g. for paragraph::DefaultReadFilter, which needs query_clipped
+                std::copy(rec, rec + m, records_out->begin() + (std::ptrdiff_t)lo);
+            detail::parallelFor(m, threads, [&](size_t a, size_t b) {
+                for (size_t i = a; i < b; ++i)
+                    if (!(tolerate_unmapped && rec[i].status == 3)) // 3: no enabled stage mapped the read -- it stays UNMAPPED
+                        applyRecord(**which[lo + i], rec[i], ops, flags, lo + i);
+            });
+        };
+        if (n < pipeline_min_reads_ || threads_ < 2)
+        {
+            half(*engine_, 0, n, threads_);
+            return;
+        }
+        if (!engine2_)
+            engine2_ = Engine::take(engine_->device());
+        if (!engine2_fresh_)
+        {
+            registerGraph(*engine2_);
+            engine2_fresh_ = true;
+        }
+        const size_t mid = n / 2;
+        const unsigned th = (threads_ + 1) / 2;
+        detail::WorkerPool::instance().run(2, [&](size_t k) { k == 0 ? half(*engine_, 0, mid, th) : half(*engine2_, mid, n, th); });
     }
+    uint64_t lastAnchored() const { return anchored_; } // reads of the last batch the exact-match stage anchored
+    // reads from which a batch is cut in two pipelined halves (0 = never)
+    void setPipelineMinReads(size_t n) { pipeline_min_reads_ = n ? n : (size_t)-1; }
 
     // host threads for packing a batch and writing its results back (the `threads` of grm::alignReads); results are the
     // same for any value
@@ -645,8 +716,25 @@ public:
     }
 
 private:
+    void registerGraph(Engine& e) const
+    {
+        e.check(pg_clear_graphs(e.get()));
+        int32_t sid = -1;
+        e.check(pg_add_graph(e.get(), (int32_t)off_.size() - 1, blob_.data(), off_.data(), (int32_t)ef_.size(), ef_.data(), et_.data(),
+                             &sid));
+        if (!path_ptr_.empty())
+            e.check(pg_set_paths(e.get(), 0, (int32_t)path_ptr_.size() - 1, path_ptr_.data(), path_nodes_.data()));
+    }
     std::unique_ptr<Engine> engine_;
+    mutable std::unique_ptr<Engine> engine2_; // second half of a pipelined batch
+    mutable bool engine2_fresh_ = false;      // engine2_ holds the current graph and paths
+    mutable std::atomic<uint64_t> anchored_{ 0 };
     unsigned threads_ = 1;
+    size_t pipeline_min_reads_ = 4096;
+    std::string blob_;
+    std::vector<int32_t> off_{ 0 }, ef_, et_, path_ptr_, path_nodes_;
+    int path_k_ = 0, kmer_k_ = 0;
+    bool graph_on_ = true, second_ = false;
 };
 
 // Many sites in ONE launch sequence.  grmpy hands (sample, graph) pairs to threads one at a time
@@ -1175,7 +1263,7 @@ public:
             }
             if (nodes.empty())
                 nodes.push_back(0);
-            graphAligner_.check(pg_set_paths(graphAligner_.context(), 0, (int32_t)ptr.size() - 1, ptr.data(), nodes.data()));
+            graphAligner_.setPaths(std::move(ptr), std::move(nodes));
         }
     }
     void setThreads(unsigned threads) { graphAligner_.setThreads(threads); }
@@ -1201,8 +1289,7 @@ public:
         bool path_on = pathMatching_, kmer_on = kmerMatching_;
         while (!todo.empty() && (path_on || kmer_on || graphMatching_))
         {
-            graphAligner_.check(pg_set_kmer_stage(graphAligner_.context(), kmer_on ? kmerSize_ : 0));
-            graphAligner_.check(pg_set_stages(graphAligner_.context(), path_on ? pathKmerSize_ : 0, graphMatching_ ? 1 : 0, 0));
+            graphAligner_.setStages(path_on ? pathKmerSize_ : 0, graphMatching_, false, kmer_on ? kmerSize_ : 0);
             std::vector<pg_record> rec;
             graphAligner_.alignBatch(todo.begin(), todo.end(), flags_, &rec, /*tolerate_unmapped=*/true);
             std::vector<ReadT*> after_path, after_kmer; // rejected by the filter right after that stage
@@ -1257,11 +1344,7 @@ public:
                     ++mappedSw_;
             }
             if (path_on)
-            {
-                uint64_t cnt[4] = { 0, 0, 0, 0 };
-                graphAligner_.check(pg_path_stats(graphAligner_.context(), cnt, nullptr));
-                anchoredPath_ += (unsigned)cnt[1];
-            }
+                anchoredPath_ += (unsigned)graphAligner_.lastAnchored();
             // next round: what the filter sent on.  (After the exact-match stage: k-mer stage and gssw; the reads the
             // k-mer stage of THIS round lost to the filter join the gssw-only round that follows.)
             if (path_on)

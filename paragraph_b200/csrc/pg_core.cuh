@@ -1211,6 +1211,7 @@ struct Walker // traceback state of one read (lane 0 only)
     int need_row;  // ... with a row band ending at this row's lane
     int clipped;   // soft-clipped query bases (leading + trailing 'S'), for the BadAlign read filter
     int position;
+    int cert_off;  // certified stretches (cert_stretch) are not attempted while set: the last attempt failed here
 };
 
 // op log: one cigar_word per traceback move (length 1) or soft clip, in traceback order (back to front)
@@ -1330,6 +1331,266 @@ PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const ui
     return run;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Certified diagonal stretches: traceback moves without the DP matrices
+// ---------------------------------------------------------------------------------------------
+// Most alignments are one long diagonal (matches and a few mismatches); recomputing a tile of the matrices every 16
+// wavefront steps just to confirm "diagonal again" is most of the traceback kernel's work.  A stretch of diagonal
+// moves can be CERTIFIED from the sequences alone, given exact values at its two ends.  Let the walker stand in state
+// H at cell 0 = (i, j) of node n with the exact value v_0 = H(cell 0), let cell k = (i - k, j - k), s_k the
+// substitution score of cell k and v_{k+1} = v_k - s_k.  For interior cells (i - k > 0, j - k > 0) the recurrence gives
+// H(cell k) >= H(cell k+1) + s_k, hence by induction from cell 0:      H(cell k) <= v_k        (upper bounds).
+// If further along there is an ANCHOR cell a whose value is known to be at least v_a, the same inequality read the other
+// way gives H(cell k) >= H(cell k+1) + s_k >= v_k for all k < a        (lower bounds), so H(cell k) = v_k on the whole
+// stretch, every H(cell k) equals H(cell k+1) + s_k, and the reference's traceback -- which tests the diagonal first
+// in an interior cell (gssw.c:1591-1637) -- takes the diagonal at every one of them.  Anchors:
+//   * zero: v_{a} = 0 with all earlier v_k > 0 (H >= 0 always) -- the alignment starts behind cell a - 1; when cell
+//     a - 1 lies in the first row or column the move is the "alignment starts here" rule (v == s, gssw.c:1655-1690),
+//     which needs H(cell a-1) >= s only: true for any diagonal input >= 0;
+//   * first column: cell a = (0, j') reached with v_a > 0: H, E and F of the first column of a node follow from the
+//     saved last columns of its predecessors alone (col0_exact: the seed is their element-wise maximum), so the
+//     value is checked exactly, and the reference's first-column order -- start, F, E, then the predecessors in
+//     ascending order (gssw.c:1655-1768, 2966-3040) -- is evaluated on exact numbers; the walk continues in the
+//     predecessor that explains the score, where the argument starts over.
+// Anything else (a partial sum below zero: some gap lies on the true path; the first row reached with score left; F or
+// E explaining a first-column value; no predecessor explaining it) certifies nothing: the walker stays where it was
+// and the tile walk below takes over from that exact state.  Exact by construction; the emulator and the GPU tests
+// compare the result with the reference either way.
+#ifndef PG_TRACE_CERT
+#define PG_TRACE_CERT 1
+#endif
+
+// exact H, E (entering) and F (entering) of cell (0, jq) of node n for the chosen half, from the predecessors' saved
+// last columns: t(0, r) = max(seedH(r - 1) + s(0, r), seedE(r), 0), F(jq) = max_{r < jq} (t(0, r) - go - (jq - 1 - r))
+template <int R, int W>
+PG_HD void col0_exact(const GraphView& g, const uint8_t* chars, const uint32_t* last, const uint8_t* bases, int L, int half,
+                      int n, int jq, int lane, unsigned gmask, int& Hq, int& Eq, int& Fq)
+{
+    const int p0 = g.pred_ptr[n], p1 = g.pred_ptr[n + 1];
+    const int rc = nt_code(chars[g.node_start[n]]);
+    int best = -100000, tq = 0, eq = 0; // best = max over rows r < jq of t(0, r) + r
+#if defined(__CUDA_ARCH__)
+    const int r_lo = R * lane, r_hi = R * lane + R;
+#else
+    (void)lane;
+    (void)gmask;
+    const int r_lo = 0, r_hi = jq + 1;
+#endif
+    for (int r = r_lo; r < r_hi && r <= jq; ++r)
+    {
+        int sh = 0, se = 0;
+        for (int e = p0; e < p1; ++e)
+        {
+            const int c = g.pred_idx[e];
+            if (r > 0)
+            {
+                const int hv = last_h<R, W>(last, c, r - 1, half);
+                sh = sh > hv ? sh : hv;
+            }
+            const int ev = last_e<R, W>(last, c, r, half);
+            se = se > ev ? se : ev;
+        }
+        const int sc = sub_score(rc, nt_code(read_char(bases, L, 0, half, r)));
+        int t = sh + sc;
+        t = t > se ? t : se;
+        t = imax0(t);
+        if (r < jq)
+            best = best > t + r ? best : t + r;
+        else
+        {
+            tq = t;
+            eq = se;
+        }
+    }
+#if defined(__CUDA_ARCH__)
+    for (int d = W / 2; d >= 1; d >>= 1)
+    {
+        const int o = __shfl_xor_sync(gmask, best, d, W);
+        best = best > o ? best : o;
+    }
+    tq = __shfl_sync(gmask, tq, jq / R, W);
+    eq = __shfl_sync(gmask, eq, jq / R, W);
+#endif
+    Fq = jq > 0 ? best - (GAP_OPEN - GAP_EXT) - jq : -100000;
+    Eq = eq;
+    Hq = tq > Fq ? tq : Fq;
+}
+
+// Advance the walker (state H, exact w.v > 0) over certified stretches.  Returns true when it moved (w updated, ops
+// logged); false when nothing could be certified from here.  Group-uniform on the device like diag_run.
+template <int R, int W>
+PG_HD bool cert_stretch(Walker& w, const GraphView& g, const uint8_t* chars, const uint32_t* last, const uint8_t* bases, int L,
+                        int half, uint32_t* oplog, int oplog_cap, int lane, unsigned gmask)
+{
+    bool moved = false;
+    for (;;)
+    {
+        const int n = w.n, i = w.i, j = w.j, m = i < j ? i : j;
+        const int col0 = g.node_start[n];
+        int nops = w.nops;  // tentative until the stretch is certified
+        int vb = w.v;       // value entering the chunk's first cell
+        int k0 = -1;        // cell after which the value is 0 (zero anchor), -1 = none
+        int sm = 0, opm = OP_M, vm = 0; // cell m: its score, its diagonal op, its value
+        bool failed = false;
+#if defined(__CUDA_ARCH__)
+        constexpr unsigned WM = (W == 32) ? 0xffffffffu : ((1u << (W & 31)) - 1u);
+        const int gshift = __ffs((int)gmask) - 1;
+        for (int base = 0; base <= m && k0 < 0; base += W)
+        {
+            const int k = base + lane;
+            const bool valid = k <= m;
+            const uint8_t refc = valid ? chars[col0 + i - k] : (uint8_t)'A';
+            const uint8_t readc = valid ? read_char(bases, L, 0, half, j - k) : (uint8_t)'A';
+            const int sc = valid ? sub_score(nt_code(refc), nt_code(readc)) : 0;
+            int cs = sc; // inclusive prefix sum over the group
+            for (int d = 1; d < W; d <<= 1)
+            {
+                const int o = __shfl_up_sync(gmask, cs, d, W);
+                if (lane >= d)
+                    cs += o;
+            }
+            const int v1 = vb - cs; // value behind cell k
+            const unsigned neg = (__ballot_sync(gmask, valid && v1 < 0) >> gshift) & WM;
+            const unsigned zero = (__ballot_sync(gmask, valid && v1 == 0) >> gshift) & WM;
+            int cnt = m - base + 1 < W ? m - base + 1 : W; // cells of this chunk that are moves
+            if (neg | zero)
+            {
+                const int e = __ffs((int)(neg | zero)) - 1;
+                if ((neg >> e) & 1u)
+                {
+                    failed = true;
+                    break;
+                }
+                k0 = base + e;
+                cnt = e + 1;
+            }
+            if (base + cnt - 1 == m) // the chunk holds cell m: its numbers for the first-row / first-column rules
+            {
+                const int lm = m - base;
+                sm = __shfl_sync(gmask, sc, lm, W);
+                vm = __shfl_sync(gmask, v1 + sc, lm, W);
+                opm = __shfl_sync(gmask, match_op(refc, readc), lm, W);
+                if (k0 == m || k0 < 0)
+                    --cnt; // cell m is logged by the rule that applies to it
+            }
+            // run-length encode the diagonal ops of lanes [0, cnt)
+            const int op = match_op(refc, readc);
+            const int prev = __shfl_up_sync(gmask, op, 1, W);
+            const bool in = lane < cnt;
+            const unsigned starts = (__ballot_sync(gmask, in && (lane == 0 || op != prev)) >> gshift) & WM;
+            if (in && ((starts >> lane) & 1u))
+            {
+                const unsigned above = starts & ~((2u << lane) - 1u);
+                const int nxt = above ? (__ffs((int)above) - 1) : cnt;
+                const int idx = nops + __popc(starts & ((1u << lane) - 1u));
+                if (idx < oplog_cap)
+                    oplog[idx] = cigar_word(n, op, nxt - lane);
+            }
+            nops += __popc(starts);
+            vb = __shfl_sync(gmask, v1, W - 1, W);
+        }
+#else
+        (void)lane;
+        (void)gmask;
+        {
+            int v = vb, last_op = -1;
+            for (int k = 0; k <= m; ++k)
+            {
+                const uint8_t refc = chars[col0 + i - k];
+                const uint8_t readc = read_char(bases, L, 0, half, j - k);
+                const int sc = sub_score(nt_code(refc), nt_code(readc));
+                const int v1 = v - sc;
+                if (v1 < 0)
+                {
+                    failed = true;
+                    break;
+                }
+                if (k == m)
+                {
+                    sm = sc;
+                    vm = v;
+                    opm = match_op(refc, readc);
+                }
+                if (v1 == 0)
+                    k0 = k;
+                if (k < m) // a logged diagonal move (cell m is logged by the rule that applies to it)
+                {
+                    const int op = match_op(refc, readc);
+                    if (op == last_op)
+                    {
+                        if (nops - 1 < oplog_cap)
+                            oplog[nops - 1] += 1u << 3;
+                    }
+                    else
+                    {
+                        if (nops < oplog_cap)
+                            oplog[nops] = cigar_word(n, op, 1);
+                        ++nops;
+                        last_op = op;
+                    }
+                }
+                v = v1;
+                if (k0 >= 0)
+                    break;
+            }
+        }
+#endif
+        if (failed)
+            return moved;
+        if (nops > oplog_cap)
+            w.status = 2;
+        if (k0 >= 0) // zero anchor: the alignment starts at cell k0
+        {
+            if (k0 == m) // ... which lies in the first row or column: "alignment starts here" (gssw.c:1655-1690)
+            {
+                const uint8_t refc = chars[col0 + i - m];
+                const uint8_t readc = read_char(bases, L, 0, half, j - m);
+                w.nops = nops;
+                if (refc == 'N' || readc == 'N' || refc == readc)
+                    push_op(w, oplog, oplog_cap, n, (refc == 'N' || readc == 'N') ? OP_N : OP_M, 1);
+                else
+                    push_op(w, oplog, oplog_cap, n, OP_NONE, 0);
+            }
+            else
+                w.nops = nops;
+            w.i = i - (k0 + 1);
+            w.j = j - (k0 + 1);
+            w.v = 0;
+            return true;
+        }
+        // cell m reached with score left
+        if (i - m != 0)
+            return moved; // first row before first column: only E could explain it -- not certified
+        const int jq = j - m;
+        int Hq, Eq, Fq;
+        col0_exact<R, W>(g, chars, last, bases, L, half, n, jq, lane, gmask, Hq, Eq, Fq);
+        if (Hq != vm)
+            return moved; // the diagonal hypothesis does not hold
+        // the stretch (cells 0 .. m-1) is certified; the walker now stands at (0, jq) with the exact value vm
+        w.nops = nops;
+        w.i = 0;
+        w.j = jq;
+        w.v = vm;
+        moved = moved || m > 0;
+        if ((jq > 0 && vm == Fq) || vm == Eq || jq == 0)
+            return moved; // a gap (or a dead end) at the node's first column: the tile walk handles it from here
+        int best = -1;
+        for (int e = g.pred_ptr[n]; e < g.pred_ptr[n + 1] && best < 0; ++e) // gssw.c:2966-3040
+            if (vm == last_h<R, W>(last, g.pred_idx[e], jq - 1, half) + sm)
+                best = g.pred_idx[e];
+        if (best < 0)
+            return moved;
+        moved = true;
+        push_op(w, oplog, oplog_cap, n, opm, 1);
+        w.v = vm - sm;
+        w.j = jq - 1;
+        w.n = best;
+        w.i = g.node_len[best] - 1;
+        if (w.v <= 0)
+            return true;
+    }
+}
+
 // Walk as far as the resident tiles allow.  Returns true when finished (w.phase == 2), false on a tile miss
 // (w.need_step set).  Mirrors gssw_alignment_trace_back_byte (gssw.c:1112-1818, final_traceback = 1, no
 // deflections) and the cross-node part of gssw_graph_trace_back_internal (gssw.c:2836-3148, 3486-3528).
@@ -1389,6 +1650,12 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
         bool leave = false; // left the node through its first column
         while (w.v > 0 && w.i >= 0 && w.j >= 0)
         {
+            if (PG_TRACE_CERT && w.st == 0 && !w.cert_off)
+            {
+                if (cert_stretch<R, W>(w, g, chars, last, bases, L, half, oplog, oplog_cap, lane, gmask))
+                    continue;
+                w.cert_off = 1; // nothing certified from here: tiles, until the walk is past whatever is in the way
+            }
             const int k = g.node_start[w.n] + w.i + w.j / R; // step of the current cell
             // neighbours: (i-1,j-1) -> step k-1 or k-2; (i-1,j) -> k-1; (i,j-1) -> k or k-1
             const uint32_t* c0 = tb.find(k, w.j);
@@ -1419,6 +1686,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                     w.v += GAP_OPEN;
                     --w.i;
                     w.st = 0;
+                    w.cert_off = 0; // past the gap: the rest may be one certified diagonal again
                     continue;
                 }
                 if (w.v == cellE<WD>(*c1) - GAP_EXT) // gssw.c:1400-1423
@@ -1449,6 +1717,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                         w.v += GAP_OPEN;
                         --w.j;
                         w.st = 0;
+                        w.cert_off = 0;
                         continue;
                     }
                     if (w.v == cellF<WD>(*cl) - GAP_EXT) // gssw.c:1510-1532
@@ -1558,6 +1827,7 @@ PG_HD bool walk(Walker& w, const TileBuf<R>& tb, const GraphView& g, const uint8
                     push_op(w, oplog, oplog_cap, w.n, OP_D, 1);
                     w.v += GAP_OPEN;
                     w.st = 0;
+                    w.cert_off = 0;
                     break;
                 }
                 // extend: the reference tests v == E_c(last, j) - ge with E *entering* pred's last column
