@@ -9,6 +9,7 @@
 //
 // There is deliberately no CPU path in this file: without a CUDA device every entry point returns PG_E_CUDA.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <chrono>
 #include <cstdio>
@@ -2290,6 +2291,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     {
         const size_t slot = overlap ? (ci & 1) : 0;
         cudaStream_t cs = (overlap && (ci & 1)) ? c->aux_stream : c->stream; // chunk ci-2 used the same slot on the same stream
+        nvtxRangePushA(ci & 1 ? "pg chunk (aux stream): fill + plan/pair + traceback" : "pg chunk (main stream): fill + plan/pair + traceback");
         PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci], cs));
         const int nr = (int)std::min(chunk, (size_t)c->n_reads - r0);
         FillArgs fa;
@@ -2391,6 +2393,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
         PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 3], ts));
+        nvtxRangePop();
     }
     if (overlap) // everything later on the caller's stream (download, counting stage) sees both streams finished
         for (size_t k = n_chunks >= 2 ? n_chunks - 2 : 0; k < n_chunks; ++k)
@@ -2610,6 +2613,11 @@ int pg_clear_graphs(pg_ctx* c)
 
 int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t* off, const int32_t* site)
 {
+    struct Range
+    {
+        Range() { nvtxRangePushA("pg_batch_upload"); }
+        ~Range() { nvtxRangePop(); }
+    } range;
     if (!c || n_reads < 0 || (n_reads > 0 && (!bases || !off)))
         return fail(c, PG_E_ARG, "pg_batch_upload: bad arguments");
     if (n_reads == 0) // an empty batch is legal (grm::alignReads on an empty read vector does nothing)
@@ -2745,6 +2753,11 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
 
 int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap, uint64_t* used)
 {
+    struct Range
+    {
+        Range() { nvtxRangePushA("pg_batch_download"); }
+        ~Range() { nvtxRangePop(); }
+    } range;
     if (!c || (!records && c->n_reads > 0))
         return fail(c, PG_E_ARG, "pg_batch_download: bad arguments");
     if (!c->ran)
@@ -2770,6 +2783,17 @@ int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap
                                c->stream));
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
     c->staging_busy = false;
+    if (getenv("PG_DEBUG_TIMELINE") && c->n_chunks_timed > 0) // where each chunk's phases sat on the device clock (ms from
+    {                                                          // the first chunk's start): the two-stream overlap, in numbers
+        for (int ci = 0; ci < c->n_chunks_timed; ++ci)
+        {
+            float t[4] = { 0, 0, 0, 0 };
+            for (int x = 0; x < 4; ++x)
+                cudaEventElapsedTime(&t[x], c->evpool[0], c->evpool[4 * ci + x]);
+            fprintf(stderr, "[pg timeline] chunk %d on %s stream: fill %.3f .. %.3f ms, traceback %.3f .. %.3f ms\n", ci,
+                    (c->split > 1 && c->aux_stream && (ci & 1)) ? "aux " : "main", t[0], t[1], t[2], t[3]);
+        }
+    }
     c->fill_ms = c->trace_ms = 0;
     for (int ci = 0; ci < c->n_chunks_timed; ++ci) // summed over the chunks of the batch
     {

@@ -504,3 +504,39 @@ def test_imported_batch_cannot_be_run_and_clear_graphs_drops_the_batch(ctx):
     ctx.add_graph(nodes, edges)
     rec2, ops2 = ctx.align_packed(blob, off)
     assert (rec2["score"] == rec["score"]).all()
+
+
+def test_tma_staging_equals_the_l1_path(built, monkeypatch):
+    """The column codes of a task are staged into shared memory with a bulk async copy (cp.async.bulk + mbarrier) while
+    the profile is built; compute-sanitizer's racecheck cannot pair that warp-scoped barrier with its wait and reports
+    "potential hazards".  The same batches with the staging switched off (PG_NO_TMA=1: codes through L1, node tables
+    from HBM) must give bit-identical records and CIGARs -- repeatedly, on batches that keep every SM busy with
+    several waves of CTAs, so that a real race between the copy and the first loads would show."""
+    import hashlib
+    rng = np.random.default_rng(77)
+    sites = []
+    for k in range(40):
+        nodes, edges = synth.site_graph(rng, ["DEL", "INS", "DUP", "INV"][k % 4])
+        sites.append((nodes, edges, synth.simulate_reads(rng, nodes, edges, 400, alternate=False)))
+    reads = [r for _, _, rd in sites for r in rd]
+    sids = np.ascontiguousarray([i for i, s in enumerate(sites) for _ in s[2]], dtype=np.int32)
+    digests = {}
+    for no_tma in ("0", "1"):
+        monkeypatch.setenv("PG_NO_TMA", no_tma)
+        c = capi.Context(0)
+        try:
+            c.add_graphs([(n, e) for n, e, _ in sites])
+            blob, off = c.pack_reads(reads)
+            ds = set()
+            for _ in range(5):
+                rec, ops = c.align_packed(blob, off, sids)
+                h = hashlib.sha1()
+                for f in ("graph_pos", "score", "unique", "chose_reverse", "status", "cigar_len"):
+                    h.update(np.ascontiguousarray(rec[f]).tobytes())
+                h.update("".join(capi.format_cigar(r, ops) for r in rec[::7]).encode())
+                ds.add(h.hexdigest())
+            assert len(ds) == 1
+            digests[no_tma] = ds.pop()
+        finally:
+            c.close()
+    assert digests["0"] == digests["1"]

@@ -33,4 +33,13 @@ for second in (False, True):
 ctx.set_stages(32, False, False)
 ctx.align(synth.simulate_reads(rng, nodes, edges, 32, read_len=150, sub=0.003, indel_frac=0.0))
 ctx.set_stages(0, True, False)
+# the k-mer stage (grm::KmerAligner) in front of the DP, alone and behind the exact-match stage
+ctx.set_paths(0, [[0, 1, 2], [0, 2]])
+ctx.set_kmer_stage(16)
+got = ctx.align(synth.simulate_reads(rng, nodes, edges, 96, read_len=150, sub=0.01, indel_frac=0.05))
+print("k-mer stage:", ctx.kmer_stats(), sum(g["stage"].startswith("kmer") for g in got), "of", len(got))
+ctx.set_stages(32, True, True)
+ctx.align(synth.simulate_reads(rng, nodes, edges, 64, read_len=150, sub=0.005, indel_frac=0.02))
+ctx.set_stages(0, True, False)
+ctx.set_kmer_stage(0)
 print("sanitize extras ok")
