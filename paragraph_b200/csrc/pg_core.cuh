@@ -355,11 +355,11 @@ PG_UNROLL
 // one step of one lane under that premise; returns the maximum of t over the lane's rows (NOT offset by MBIAS).
 // zero = 0, on the device in a register the compiler cannot see through (a literal 0 as the third DPX operand makes
 // it materialise a zero register per operation).
-template <int R, class PF> PG_HD uint32_t lane_step_dead(Lane<R>& s, uint32_t recvH, const PF& pf, uint32_t zero = 0u)
+template <int R, class PF> PG_HD uint32_t lane_step_dead(Lane<R>& s, uint32_t recvH, const PF& pf, uint32_t zero = 0u, uint32_t acc = 0u)
 {
     uint32_t d = s.hupPrev;
     s.hupPrev = recvH;
-    uint32_t mt = zero;
+    uint32_t mt = acc; // a caller that only needs the maximum over a whole block passes the running one in (acc >= 0)
 PG_UNROLL
     for (int r = 0; r < R; ++r)
     {
@@ -371,6 +371,11 @@ PG_UNROLL
     s.hbotLast = s.Hp[R - 1];
     return mt;
 }
+// A speculative block need not track WHERE a lane's node maximum was first reached: everything it computes is <= GAP_OPEN
+// (else it is redone), and the first-reached steps only matter for the cells that hold the fill's top score.  So a
+// block just folds its maximum into the lane's node maximum; a fill whose top score ends up within 1 .. GAP_OPEN (a read
+// that matches nowhere) is done once more with exact bookkeeping (dead_range_score; fill kernel and emulator alike).
+PG_HD bool dead_range_score(int S) { return S > 0 && S <= GAP_OPEN; }
 // did a speculative block stay within the premise?  Mt = maximum of lane_step_dead's results over the block
 PG_HD bool dead_block_broken(uint32_t Mt) { return max2(add2(Mt, pk(-GAP_OPEN, -GAP_OPEN)), 0u) != 0u; }
 // what a speculative block changes and a redo has to put back (E, foutLast are not touched by lane_step_dead)

@@ -337,6 +337,13 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         tma_wait(bar, tma_phase);
     tma_phase ^= 1u;
 
+    const bool save = active && (o == 0);
+    TaskOut t;
+    // pass 0: speculative blocks with the cheap bookkeeping; pass 1 (rare): everything exact -- see dead_range_score
+    PG_NOUNROLL
+    for (int pass = 0; pass < 2; ++pass)
+    {
+    const bool precise = pass > 0;
     Lane<R> s;
     lane_zero(s);
     LaneCtl c;
@@ -345,7 +352,6 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         region_begin(c, g, L, gl);
     if (!active)
         c.colsLeft = COLS_INF;
-    const bool save = active && (o == 0);
     uint32_t* last = a.last + (size_t)slot * a.stride_last;
     uint32_t* ckpt = a.ckpt + (size_t)slot * a.stride_ckpt;
     const uint8_t* codes = (STAGED ? code_s + SENT : g.codes) - gl;
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                     continue;
                 }
                 {
-                    bool full = __any_sync(FULL, gaps_alive(s));
+                    bool full = precise || __any_sync(FULL, gaps_alive(s));
                     uint32_t Sb = 0u;
                     bool haveSb = false;
                     if (PG_SPEC_PRUNE)
@@ -434,8 +440,11 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                     {
                         DeadSave<R> keep;
                         dead_save(s, keep);
+                        uint32_t Mt = zero;
+#if PG_SPEC_PRUNE // the pruning experiment lets blocks with t > gap_open stay "dead": exact bookkeeping there
                         const int keepF0 = c.first[0], keepF1 = c.first[1];
-                        uint32_t Mt = zero, Mn = track_t_begin(c);
+                        uint32_t Mn = track_t_begin(c);
+#endif
 #pragma unroll
                         for (int kk = 0; kk < SPEC_STEPS; ++kk)
                         {
@@ -443,9 +452,13 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                             rh *= lmask;
                             const int code = live ? cpb[kk] : 5;
                             const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
+#if PG_SPEC_PRUNE
                             const uint32_t mt = lane_step_dead<R>(s, rh, pf, zero);
                             Mt = max2(Mt, mt);
                             track_t(c, Mn, mt, kbase + sb + kk);
+#else
+                            Mt = lane_step_dead<R>(s, rh, pf, zero, Mt); // the block's maximum, nothing else
+#endif
                         }
                         full = __any_sync(FULL, dead_block_broken(Mt));
                         if (PG_SPEC_PRUNE && full) // the gaps it would have opened: all droppable?
@@ -454,6 +467,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                                 Sb = group_max2<W>(Mall);
                             full = __any_sync(FULL, dead_block_broken_pruned(Mt, rem0, Sb));
                         }
+#if PG_SPEC_PRUNE
                         if (full)
                         {
                             dead_restore(s, keep);
@@ -462,6 +476,12 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                         }
                         else
                             track_t_end(c, Mn);
+#else
+                        if (full)
+                            dead_restore(s, keep);
+                        else // fold the block into the node maximum (kept with the offset MBIAS); no first-reached steps
+                            c.Mnode = max2(c.Mnode, add2(Mt, pk(-MBIAS, -MBIAS)));
+#endif
                     }
                     if (full)
                     {
@@ -535,9 +555,17 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     if (save) // node last columns for the traceback kernel: one coalesced copy of the node table
         for (int x = gl; x < g.n_nodes * ROWW * W; x += W)
             last[x] = seedS[x];
-    TaskOut t;
     if (!WIDE)
         finalize_task_group<R, W>(seedS, g.n_nodes, gl, t); // every lane of the warp takes part (group-wide reductions)
+    // a forward-graph fill whose top score lies in the range the speculative blocks do not keep first-reached steps
+    // for: once more, exactly (the traceback starts at that cell)
+    bool again = false;
+    if (PG_SPEC_DEAD && !PG_SPEC_PRUNE && !WIDE && FAST_BLOCKS && !precise)
+        again = __any_sync(FULL, save && (dead_range_score(t.score[0]) || dead_range_score(t.score[1])));
+    if (!again)
+        break;
+    __syncwarp();
+    } // pass
     if (active && gl == 0)
     {
         if (WIDE) // long reads: the serial statement, with the 16-bit-mode uniqueness rule (n_top_rule)

@@ -39,8 +39,28 @@ namespace
 {
 
 template <int R, int W>
+void emu_fill_pass(const GraphView& g, const uint8_t* bases, int L, int orient, bool save_trace, std::vector<uint32_t>& info,
+                   std::vector<uint32_t>& last, std::vector<uint32_t>& ckpt, TaskOut& out, bool precise);
+
+// pg_fill_kernel's two passes: speculative blocks with the cheap bookkeeping first; a forward-graph fill whose top score
+// lies in the range those blocks keep no first-reached steps for is done once more, exactly (pg_core.cuh: dead_range_score)
+static long g_second_pass = 0;
+extern "C" long pgemu_second_passes() { return g_second_pass; }
+template <int R, int W>
 void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool save_trace, std::vector<uint32_t>& info,
               std::vector<uint32_t>& last, std::vector<uint32_t>& ckpt, TaskOut& out)
+{
+    emu_fill_pass<R, W>(g, bases, L, orient, save_trace, info, last, ckpt, out, false);
+    if (g_spec == 1 && !Sizes<R, W>::WIDE && save_trace && (dead_range_score(out.score[0]) || dead_range_score(out.score[1])))
+    {
+        ++g_second_pass;
+        emu_fill_pass<R, W>(g, bases, L, orient, save_trace, info, last, ckpt, out, true);
+    }
+}
+
+template <int R, int W>
+void emu_fill_pass(const GraphView& g, const uint8_t* bases, int L, int orient, bool save_trace, std::vector<uint32_t>& info,
+                   std::vector<uint32_t>& last, std::vector<uint32_t>& ckpt, TaskOut& out, bool precise)
 {
     std::vector<uint32_t> prof((size_t)NCODE * R * W);
     std::vector<uint32_t> seedS((size_t)g.n_nodes * Sizes<R, W>::ROWW * W, 0); // node table (pg_core.cuh: Sizes)
@@ -67,7 +87,7 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
         if (save_trace && k % CK == 0)
             for (int t = 0; t < W; ++t)
                 ckpt_store<R, W>(s[t], ckpt.data() + (size_t)(k / CK) * CKW * W, t);
-        if (g_spec && !WIDE && k % SPEC_STEPS == 0 && k >= no_spec_before)
+        if (g_spec && !precise && !WIDE && k % SPEC_STEPS == 0 && k >= no_spec_before)
         {
             bool flat = true, dead = true;
             for (int h = 0; h < 2; ++h)
@@ -105,9 +125,9 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
                 }
                 uint32_t Mt = 0u, Mn[W], Mlane[W];
                 for (int t = 0; t < W; ++t)
-                    Mlane[t] = 0u;
-                for (int t = 0; t < W; ++t)
                     Mn[t] = track_t_begin(c[t]);
+                for (int t = 0; t < W; ++t)
+                    Mlane[t] = 0u;
                 for (int kk = 0; kk < SPEC_STEPS; ++kk)
                 {
                     uint32_t rh[W];
@@ -124,7 +144,8 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
                         Mlane[t] = max2(Mlane[t], mt);
                         pending[0] = std::max(pending[0], lo16(mt));
                         pending[1] = std::max(pending[1], hi16(mt));
-                        track_t(c[t], Mn[t], mt, k + kk);
+                        if (g_spec == 2) // the pruning experiment lets blocks with t > gap_open stay "dead": exact bookkeeping
+                            track_t(c[t], Mn[t], mt, k + kk);
                     }
                 }
                 bool broken = dead_block_broken(Mt);
@@ -138,7 +159,10 @@ void emu_fill(const GraphView& g, const uint8_t* bases, int L, int orient, bool 
                 if (!broken)
                 {
                     for (int t = 0; t < W; ++t)
-                        track_t_end(c[t], Mn[t]);
+                        if (g_spec == 2)
+                            track_t_end(c[t], Mn[t]);
+                        else // fold the block into the node maximum; no first-reached steps
+                            c[t].Mnode = max2(c[t].Mnode, add2(Mlane[t], pk(-MBIAS, -MBIAS)));
                     k += SPEC_STEPS - 1;
                     continue;
                 }
