@@ -53,6 +53,11 @@ namespace
 #ifndef PG_FAST_UNROLL
 #define PG_FAST_UNROLL 8
 #endif
+#ifndef PG_STATIC_BAR
+#define PG_STATIC_BAR 1 // the staging mbarriers live in a static shared array: compute-sanitizer's synccheck only follows
+                        // barriers it can see declared (in dynamic shared memory it reports "Missing init" on every wait
+                        // and aborts the kernel; profiles/r02e_synccheck_variants.txt)
+#endif
 #ifndef PG_FAST_BLOCKS
 #define PG_FAST_BLOCKS 1
 #endif
@@ -318,7 +323,12 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
     const int L = a.read_off[rd + 1] - a.read_off[rd];
     // node sequences (column codes) of this task's orientation: TMA-staged into shared memory when they fit
     uint8_t* code_s = reinterpret_cast<uint8_t*>(prof + a.smem_words_per_task) - a.code_smem_bytes;
+#if PG_STATIC_BAR
+    __shared__ __align__(8) uint64_t static_bars[FILL_WARPS * 4]; // one per task slot of the CTA
+    uint64_t* bar = static_bars + wic * NT + grp;
+#else
     uint64_t* bar = reinterpret_cast<uint64_t*>(code_s) - 1;
+#endif
     const uint32_t span = (uint32_t)code_span_bytes(g.G);
     const bool staged = STAGED && active; // the host only picks STAGED when every graph of the batch fits
     if (staged && wbase < (int)gridDim.x * wpc * NT) // first task of this warp
