@@ -1355,6 +1355,7 @@ __global__ void __launch_bounds__(KMER_WARPS * 32) pg_kmer_kernel(const KmerArgs
         if (lane == 0)
             off = atomicAdd(a.cursor, (unsigned long long)r.n_ops);
         off = __shfl_sync(FULL, off, 0);
+        __syncwarp(); // lane 0 wrote the op words (kmer_build_ops): make them visible to the lanes that copy them out
         if (r.n_ops <= a.ops_cap && off + (unsigned long long)r.n_ops <= a.arena_cap)
         {
             for (int x = lane; x < r.n_ops; x += 32)
