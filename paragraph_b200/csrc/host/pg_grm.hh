@@ -19,9 +19,11 @@
 #pragma once
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <condition_variable>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <exception>
@@ -310,6 +312,44 @@ private:
     bool stop_ = false;
 };
 
+// Where the host time of a batch goes (seconds, summed over calls; read and reset by a caller such as
+// tools/cpp/bench_mirror): a handful of clock reads per batch.
+struct Phases
+{
+    enum { SET_GRAPH, PACK, LAUNCH, WAIT, APPLY, FILTER, KEEP, N };
+    std::atomic<uint64_t> ns[N];
+    static Phases& instance()
+    {
+        static Phases p;
+        return p;
+    }
+    static const char* name(int i)
+    {
+        static const char* const names[N] = { "set_graph", "pack", "launch", "wait_download", "apply", "filter", "keep" };
+        return names[i];
+    }
+    void reset()
+    {
+        for (auto& x : ns)
+            x = 0;
+    }
+    struct Scope // adds the lifetime of the object to one phase
+    {
+        explicit Scope(int phase) : phase_(phase), t0_(std::chrono::steady_clock::now()) {}
+        ~Scope() { next(-1); }
+        void next(int phase) // closes the running phase and starts `phase` (-1: none)
+        {
+            const auto t1 = std::chrono::steady_clock::now();
+            if (phase_ >= 0)
+                instance().ns[phase_] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0_).count();
+            phase_ = phase;
+            t0_ = t1;
+        }
+        int phase_;
+        std::chrono::steady_clock::time_point t0_;
+    };
+};
+
 // fn(begin, end) over [0, n) on up to `threads` host threads (the `threads` argument of grm::alignReads, Align.cpp:119:
 // the reference spends it on aligning, here it packs the batch and writes the results back -- at 5 M reads/s on the
 // device the ~0.3 us a single thread needs per read for that is what a caller would otherwise wait for).  Every index
@@ -538,17 +578,31 @@ public:
         if (records_out)
             records_out->resize(n);
         anchored_ = 0;
-        auto half = [&](Engine& e, size_t lo, size_t hi, unsigned threads) {
+        // one part of the batch in two steps: submit = pack + H2D + kernels (returns with the kernels in flight),
+        // collect = D2H + write-back into the reads
+        auto submit = [&](Engine& e, size_t lo, size_t hi) -> size_t {
             const size_t m = hi - lo;
+            detail::Phases::Scope ph(detail::Phases::PACK);
             e.check(pg_set_kmer_stage(e.get(), kmer_k_));
             e.check(pg_set_stages(e.get(), path_k_, graph_on_ ? 1 : 0, second_ ? 1 : 0));
-            const size_t bytes = e.pack(m, threads, [&](size_t i) -> std::string const& { return (*which[lo + i])->bases(); });
-            pg_record* rec = e.rec.reserve(m);
+            const size_t bytes = e.pack(m, threads_, [&](size_t i) -> std::string const& { return (*which[lo + i])->bases(); });
+            e.rec.reserve(m);
             const size_t ops_cap = bytes + 16 * m + 64;
-            uint32_t* ops = e.ops.reserve(ops_cap);
+            e.ops.reserve(ops_cap);
+            ph.next(detail::Phases::LAUNCH);
+            e.check(pg_batch_upload(e.get(), (int32_t)m, e.blob.data(), e.off.data(), nullptr));
+            e.check(pg_batch_run(e.get(), flags));
+            return ops_cap;
+        };
+        auto collect = [&](Engine& e, size_t lo, size_t hi, size_t ops_cap) {
+            const size_t m = hi - lo;
+            pg_record* rec = e.rec.data();
+            uint32_t* ops = e.ops.data();
             uint64_t used = 0;
-            e.check(pg_align_batch(e.get(), (int32_t)m, e.blob.data(), e.off.data(), nullptr, flags, rec, ops, ops_cap, &used));
-            if (path_k_ > 0) // PathAligner::anchored of this half
+            detail::Phases::Scope ph(detail::Phases::WAIT);
+            e.check(pg_batch_download(e.get(), rec, ops, ops_cap, &used));
+            ph.next(detail::Phases::APPLY);
+            if (path_k_ > 0) // PathAligner::anchored of this part
             {
                 uint64_t cnt[4] = { 0, 0, 0, 0 };
                 e.check(pg_path_stats(e.get(), cnt, nullptr));
@@ -556,17 +610,22 @@ public:
             }
             if (records_out) // e.g. for paragraph::DefaultReadFilter, which needs query_clipped
                 std::copy(rec, rec + m, records_out->begin() + (std::ptrdiff_t)lo);
-            detail::parallelFor(m, threads, [&](size_t a, size_t b) {
+            detail::parallelFor(m, threads_, [&](size_t a, size_t b) {
                 for (size_t i = a; i < b; ++i)
                     if (!(tolerate_unmapped && rec[i].status == 3)) // 3: no enabled stage mapped the read -- it stays UNMAPPED
                         applyRecord(**which[lo + i], rec[i], ops, flags, lo + i);
             });
         };
-        if (n < pipeline_min_reads_ || threads_ < 2)
+        if (n < pipeline_min_reads_)
         {
-            half(*engine_, 0, n, threads_);
+            const size_t cap = submit(*engine_, 0, n);
+            collect(*engine_, 0, n, cap);
             return;
         }
+        // Software pipeline over two engines (two contexts, two streams): part k + 1 is packed and submitted before part
+        // k is collected, so the write-back of one part (strings: reverse complements, CIGAR text -- on all host
+        // threads) runs while the kernels of the next are in flight.  Parts of pipeline_min_reads_ / 2 reads or more,
+        // at most pipeline_max_parts_ of them.
         if (!engine2_)
             engine2_ = Engine::take(engine_->device());
         if (!engine2_fresh_)
@@ -574,13 +633,22 @@ public:
             registerGraph(*engine2_);
             engine2_fresh_ = true;
         }
-        const size_t mid = n / 2;
-        const unsigned th = (threads_ + 1) / 2;
-        detail::WorkerPool::instance().run(2, [&](size_t k) { k == 0 ? half(*engine_, 0, mid, th) : half(*engine2_, mid, n, th); });
+        const size_t parts = std::max<size_t>(2, std::min<size_t>(pipeline_max_parts_, n / std::max<size_t>(pipeline_min_reads_ / 2, 1)));
+        auto bound = [&](size_t k) { return n * k / parts; };
+        Engine* eng[2] = { engine_.get(), engine2_.get() };
+        size_t cap[2] = { 0, 0 };
+        cap[0] = submit(*eng[0], bound(0), bound(1));
+        for (size_t k = 0; k < parts; ++k)
+        {
+            if (k + 1 < parts) // (its engine's buffers are free: part k - 1 was collected in the last iteration)
+                cap[(k + 1) & 1] = submit(*eng[(k + 1) & 1], bound(k + 1), bound(k + 2));
+            collect(*eng[k & 1], bound(k), bound(k + 1), cap[k & 1]);
+        }
     }
     uint64_t lastAnchored() const { return anchored_; } // reads of the last batch the exact-match stage anchored
     // reads from which a batch is cut in two pipelined halves (0 = never)
     void setPipelineMinReads(size_t n) { pipeline_min_reads_ = n ? n : (size_t)-1; }
+    void setPipelineMaxParts(size_t n) { pipeline_max_parts_ = n < 2 ? 2 : n; }
 
     // host threads for packing a batch and writing its results back (the `threads` of grm::alignReads); results are the
     // same for any value
@@ -730,7 +798,14 @@ private:
     mutable bool engine2_fresh_ = false;      // engine2_ holds the current graph and paths
     mutable std::atomic<uint64_t> anchored_{ 0 };
     unsigned threads_ = 1;
-    size_t pipeline_min_reads_ = 4096;
+    // tuning knobs, PGB_PIPELINE_MIN_READS / PGB_PIPELINE_PARTS in the environment override the defaults
+    static size_t envKnob(const char* name, size_t dflt)
+    {
+        const char* e = std::getenv(name);
+        return e && *e ? (size_t)std::strtoull(e, nullptr, 10) : dflt;
+    }
+    size_t pipeline_min_reads_ = envKnob("PGB_PIPELINE_MIN_READS", 4096);
+    size_t pipeline_max_parts_ = std::max<size_t>(2, envKnob("PGB_PIPELINE_PARTS", 2));
     std::string blob_;
     std::vector<int32_t> off_{ 0 }, ef_, et_, path_ptr_, path_nodes_;
     int path_k_ = 0, kmer_k_ = 0;
@@ -1293,6 +1368,7 @@ public:
             std::vector<pg_record> rec;
             graphAligner_.alignBatch(todo.begin(), todo.end(), flags_, &rec, /*tolerate_unmapped=*/true);
             std::vector<ReadT*> after_path, after_kmer; // rejected by the filter right after that stage
+            detail::Phases::Scope ph(detail::Phases::FILTER);
             for (size_t i = 0; i < todo.size(); ++i)
             {
                 ReadT& read = *todo[i];
@@ -1410,14 +1486,18 @@ void alignReads(GraphT const* graph, PathListT const& paths, std::vector<ReadPtr
 {
     if (validate_alignments)
         throw std::runtime_error("paragraph_b200: ValidationAligner is diagnostics-only and not provided");
+    detail::Phases::Scope ph(detail::Phases::SET_GRAPH);
     CompositeAligner aligner(path_sequence_matching, graph_sequence_matching, klib_sequence_matching,
                              kmer_sequence_matching, GraphAligner::AF_ALL, device);
     aligner.setGraph(graph, paths);
     aligner.setThreads(threads);
+    ph.next(detail::Phases::KEEP);
     for (auto& r : reads) // Align.cpp:72-78
         if (!r->bases().empty())
             r->set_graph_mapping_status(std::remove_reference<decltype(*r)>::type::UNMAPPED);
+    ph.next(-1);
     aligner.alignReads(reads.begin(), reads.end(), filter);
+    ph.next(detail::Phases::KEEP);
     std::vector<ReadPtrT> kept;
     for (auto& r : reads)
         if (!r->bases().empty() && r->graph_mapping_status() == std::remove_reference<decltype(*r)>::type::MAPPED)

@@ -621,6 +621,10 @@ struct TraceArgs
     const int32_t* n_todo;
     const uint8_t* prerev; // see PathArgs; null without the exact-match stage
     const int32_t* rv_ntop; // MODE_PAIRS: n_top of the reversed-graph fills that were needed (-1 = not needed); else null
+    // the reads whose strand decision still waits for a second-round reversed-graph fill are traced by a second, tiny
+    // launch: pending_mode 1 = skip the reads flagged in `pending`, 2 = only those (0 / null: every read)
+    const uint8_t* pending;
+    int pending_mode;
 };
 
 template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_trace_kernel(const TraceArgs a)
@@ -636,9 +640,16 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         n_reads = min(n_reads, max(*a.n_todo - a.read0, 0));
     if (lrd0 >= n_reads)
         return;
-    const bool active = lrd0 + grp < n_reads;
+    bool active = lrd0 + grp < n_reads;
     const int lrd = active ? lrd0 + grp : lrd0; // idle tail groups shadow the warp's first read (no stores)
     const int rd = a.todo ? a.todo[a.read0 + lrd] : a.read0 + lrd;
+    if (a.pending_mode)
+    {
+        const bool mine = (a.pending[rd] != 0) == (a.pending_mode == 2);
+        if (!__any_sync(FULL, active && mine))
+            return; // nothing for this warp in this launch
+        active = active && mine;
+    }
     uint8_t* wmem = reinterpret_cast<uint8_t*>(smem) + ((size_t)wic * NT + grp) * a.smem_bytes_per_task;
     uint32_t* prof = reinterpret_cast<uint32_t*>(wmem);
     uint32_t* oplog = prof + NCODE * R * W;
@@ -790,6 +801,7 @@ struct PlanArgs
     int32_t* n_req;
     int2* rtasks;
     int32_t* n_rtasks;
+    uint8_t* pending; // may be null; [read] 1 = this round asks for another reversed-graph fill of the read
 };
 __global__ void __launch_bounds__(128) pg_plan_kernel(const PlanArgs a)
 {
@@ -803,6 +815,8 @@ __global__ void __launch_bounds__(128) pg_plan_kernel(const PlanArgs a)
         rd = a.todo ? a.todo[a.read0 + i] : a.read0 + i;
         const int known[2] = { a.rv_ntop[rd * 2], a.rv_ntop[rd * 2 + 1] };
         want = rev_plan(a.tout[(size_t)rd * 2], known, a.flags);
+        if (a.pending)
+            a.pending[rd] = want >= 0 ? 1 : 0;
     }
     const unsigned m = __ballot_sync(FULL, want >= 0);
     if (!m)
@@ -1729,6 +1743,10 @@ struct pg_ctx
                      // persistent CTAs striding over the task list
     int n_sms = 148;
     DevBuf<int32_t> d_rvntop, d_req, d_nreq; // d_nreq: [0] requests, [1] tasks
+    DevBuf<uint8_t> d_pending;               // [read] 1 = waits for a second-round reversed-graph fill (pg_plan_kernel)
+    cudaStream_t side_stream[2] = { nullptr, nullptr }; // second-round fills run here, next to the traceback of the settled reads
+    std::vector<cudaEvent_t> evside;                    // 2 per chunk: round-1 plan done / second-round fill done
+    int late_round = 1;                                 // PG_LATE_ROUND=0: second-round fills before the one traceback launch
     DevBuf<int2> d_rtasks;
 
     // exact-match stage (pg_path.cuh)
@@ -2270,6 +2288,12 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         PG_CUDA(c, cudaEventCreate(&e));
         c->evpool.push_back(e);
     }
+    while (c->evside.size() < 2 * n_chunks)
+    {
+        cudaEvent_t e;
+        PG_CUDA(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->evside.push_back(e);
+    }
     c->n_chunks_timed = (int)n_chunks;
     // Reversed-graph fills: only the halves the strand rule needs (rev_plan), two reads per task.  Not for the WIDE
     // geometries (their region maxima depend on the one read length of a task).
@@ -2280,6 +2304,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         PG_CUDA(c, c->d_req.reserve(2 * (size_t)c->n_reads));
         PG_CUDA(c, c->d_rtasks.reserve(2 * (size_t)c->n_reads));
         PG_CUDA(c, c->d_nreq.reserve(4));
+        PG_CUDA(c, c->d_pending.reserve((size_t)c->n_reads));
         PG_CUDA(c, cudaMemsetAsync(c->d_rvntop.p, 0xFF, (size_t)c->n_reads * 2 * sizeof(int32_t), c->stream)); // -1 = unknown
     }
     // grid of one wave of resident CTAs (persistent launch), 0 = not wanted
@@ -2362,6 +2387,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         fa.n_todo = after_path ? c->ntodo_final : nullptr;
         launch_fill(fa, fa.n_tasks, cs);
         PG_CUDA(c, cudaGetLastError());
+        bool late = false;
         if (pairs)
         {
             // two rounds: the half rev_plan asks for first, then -- for the few reads it did not settle -- the other one
@@ -2385,17 +2411,33 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
             fr.rv_ntop = c->d_rvntop.p;
             fr.todo = nullptr;
             fr.n_todo = nullptr;
+            // The second round is next to empty (a handful of reads in 10 000) but costs a whole fill latency; with
+            // `late` it runs on a side stream while the traceback of the settled reads is under way, and a second
+            // traceback launch picks up the reads that waited for it (TraceArgs::pending_mode).
+            // (worth it while that latency is a visible share of the chunk: measured -4 % on 2 x 5 000 reads, nothing on
+            // 2 x 12 000, +1 % on 2 x 48 000 where the second traceback launch costs more than the wait it hides)
+            late = c->late_round && c->side_stream[slot] != nullptr && (c->late_round > 1 || nr <= 32768);
             for (int round = 0; round < 2; ++round)
             {
                 PG_CUDA(c, cudaMemsetAsync(pa.n_req, 0, 2 * sizeof(int32_t), cs));
+                pa.pending = (late && round == 1) ? c->d_pending.p : nullptr;
                 pg_plan_kernel<<<(nr + 127) / 128, 128, 0, cs>>>(pa);
                 pg_pair_kernel<<<((nr + 1) / 2 + 127) / 128, 128, 0, cs>>>(pa);
                 c->launches += 2;
                 // at most one task per request: the grid covers the worst case (round 0 needs about nr / 2 tasks, round 1
                 // next to none) and the CTAs beyond *n_rtasks leave at once
                 fr.n_tasks = nr;
-                launch_fill(fr, nr, cs, round == 1);
+                cudaStream_t fs = cs;
+                if (late && round == 1)
+                {
+                    fs = c->side_stream[slot];
+                    PG_CUDA(c, cudaEventRecord(c->evside[2 * ci], cs));
+                    PG_CUDA(c, cudaStreamWaitEvent(fs, c->evside[2 * ci], 0));
+                }
+                launch_fill(fr, nr, fs, round == 1);
                 PG_CUDA(c, cudaGetLastError());
+                if (fs != cs)
+                    PG_CUDA(c, cudaEventRecord(c->evside[2 * ci + 1], fs));
             }
         }
         PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 1], cs));
@@ -2428,9 +2470,19 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         ta.prerev = after_path ? c->d_prerev.p : nullptr;
         ta.rv_ntop = pairs ? c->d_rvntop.p : nullptr;
         const int tgrid = (nr + TRACE_WARPS * NT - 1) / (TRACE_WARPS * NT);
+        ta.pending = late ? c->d_pending.p : nullptr;
+        ta.pending_mode = late ? 1 : 0;
         pg_trace_kernel<R, W><<<tgrid, TRACE_WARPS * 32, trace_smem, ts>>>(ta);
         PG_CUDA(c, cudaGetLastError());
         ++c->launches;
+        if (late)
+        {
+            PG_CUDA(c, cudaStreamWaitEvent(ts, c->evside[2 * ci + 1], 0));
+            ta.pending_mode = 2;
+            pg_trace_kernel<R, W><<<tgrid, TRACE_WARPS * 32, trace_smem, ts>>>(ta);
+            PG_CUDA(c, cudaGetLastError());
+            ++c->launches;
+        }
         PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci + 3], ts));
         nvtxRangePop();
     }
@@ -2482,6 +2534,11 @@ int pg_create(int device, pg_ctx** out)
     c->stream = c->own_stream;
     if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess)
         c->aux_stream = nullptr;
+    for (auto& st : c->side_stream)
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess)
+            st = nullptr;
+    if (const char* e = getenv("PG_LATE_ROUND"))
+        c->late_round = atoi(e);
     if (const char* e = getenv("PG_SPLIT"))
         c->split = std::max(1, atoi(e));
     if (const char* e = getenv("PG_NO_TMA"))
@@ -2547,6 +2604,7 @@ void pg_destroy(pg_ctx* c)
     c->d_rvntop.release();
     c->d_req.release();
     c->d_nreq.release();
+    c->d_pending.release();
     c->d_rtasks.release();
     c->d_pcolbase.release();
     c->d_plistcap.release();
@@ -2569,6 +2627,11 @@ void pg_destroy(pg_ctx* c)
             cudaEventDestroy(ev);
     if (c->aux_stream)
         cudaStreamDestroy(c->aux_stream);
+    for (auto st : c->side_stream)
+        if (st)
+            cudaStreamDestroy(st);
+    for (auto& ev : c->evside)
+        cudaEventDestroy(ev);
     if (c->own_stream)
         cudaStreamDestroy(c->own_stream);
     delete c;
@@ -2820,6 +2883,22 @@ int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap
                                c->stream));
     PG_CUDA(c, cudaMemcpyAsync(c->h_cursor.p, c->d_cursor.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                c->stream));
+    // the op words: how many there are is only known after the cursor has arrived, but a batch of short reads uses a few
+    // words per read -- copy a guess of 8 per read in the same trip and fetch the rest (rare) afterwards
+    const bool ops_direct = ops && is_pinned(ops);
+    unsigned long long guess = 0;
+    if (ops && cap > 0)
+    {
+        guess = std::min<unsigned long long>(std::min<unsigned long long>(cap, c->arena_cap), 8ull * (unsigned long long)c->n_reads);
+        uint32_t* dst = ops;
+        if (!ops_direct)
+        {
+            PG_CUDA(c, c->h_arena.reserve((size_t)std::max<unsigned long long>(guess, 1)));
+            dst = c->h_arena.p;
+        }
+        if (guess)
+            PG_CUDA(c, cudaMemcpyAsync(dst, c->d_arena.p, (size_t)guess * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
     PG_CUDA(c, cudaStreamSynchronize(c->stream));
     c->staging_busy = false;
     if (getenv("PG_DEBUG_TIMELINE") && c->n_chunks_timed > 0) // where each chunk's phases sat on the device clock (ms from
@@ -2856,18 +2935,27 @@ int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap
     {
         if (!ops || cap < n)
             return fail(c, PG_E_CAPACITY, "cigar arena too small: need " + std::to_string(n) + " ops");
-        if (is_pinned(ops))
+        if (ops_direct)
         {
-            PG_CUDA(c, cudaMemcpyAsync(ops, c->d_arena.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-            PG_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (n > guess) // the rest
+            {
+                PG_CUDA(c, cudaMemcpyAsync(ops + guess, c->d_arena.p + guess, (size_t)(n - guess) * sizeof(uint32_t),
+                                           cudaMemcpyDeviceToHost, c->stream));
+                PG_CUDA(c, cudaStreamSynchronize(c->stream));
+            }
         }
         else
         {
-            PG_CUDA(c, c->h_arena.reserve((size_t)n));
-            PG_CUDA(c, cudaMemcpyAsync(c->h_arena.p, c->d_arena.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                       c->stream));
-            PG_CUDA(c, cudaStreamSynchronize(c->stream));
-            memcpy(ops, c->h_arena.p, (size_t)n * sizeof(uint32_t));
+            const unsigned long long have = std::min(n, guess);
+            memcpy(ops, c->h_arena.p, (size_t)have * sizeof(uint32_t));
+            if (n > guess)
+            {
+                PG_CUDA(c, c->h_arena.reserve((size_t)(n - guess)));
+                PG_CUDA(c, cudaMemcpyAsync(c->h_arena.p, c->d_arena.p + guess, (size_t)(n - guess) * sizeof(uint32_t),
+                                           cudaMemcpyDeviceToHost, c->stream));
+                PG_CUDA(c, cudaStreamSynchronize(c->stream));
+                memcpy(ops + guess, c->h_arena.p, (size_t)(n - guess) * sizeof(uint32_t));
+            }
         }
     }
     return PG_OK;

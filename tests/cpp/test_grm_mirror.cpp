@@ -253,6 +253,31 @@ int main()
                     && t1[i]->graph_alignment_score() == t5[i]->graph_alignment_score()
                     && t1[i]->is_graph_reverse_strand() == t5[i]->is_graph_reverse_strand()
                     && t1[i]->graph_mapping_status() == t5[i]->graph_mapping_status();
+            // GraphAligner::alignBatch as one submit + collect and as a software pipeline of five parts over two engines
+            {
+                std::vector<std::unique_ptr<Read>> whole, parts;
+                for (int i = 0; i < 4200; ++i)
+                {
+                    Read r(reads[(size_t)(i % 7)]);
+                    r.set_is_reverse_strand((i / 7) % 2 == 1);
+                    whole.emplace_back(new Read(r));
+                    parts.emplace_back(new Read(r));
+                }
+                grm::GraphAligner a, b;
+                a.setGraph(&graph);
+                a.setPipelineMinReads(0);
+                a.alignBatch(whole.begin(), whole.end());
+                b.setGraph(&graph);
+                b.setThreads(3);
+                b.setPipelineMinReads(512);
+                b.setPipelineMaxParts(5);
+                b.alignBatch(parts.begin(), parts.end());
+                for (size_t i = 0; equal && i < whole.size(); ++i)
+                    equal = whole[i]->bases() == parts[i]->bases() && whole[i]->quals() == parts[i]->quals()
+                        && whole[i]->graph_cigar() == parts[i]->graph_cigar() && whole[i]->graph_pos() == parts[i]->graph_pos()
+                        && whole[i]->graph_mapq() == parts[i]->graph_mapq()
+                        && whole[i]->is_graph_reverse_strand() == parts[i]->is_graph_reverse_strand();
+            }
             // the same for MultiSiteAligner::alignAndCount (two sites, exact-match stage in front)
             Graph lg = graph;
             lg.addLabelToEdge(0, 1, "P");

@@ -27,6 +27,12 @@ struct pg_ctx
     std::vector<uint32_t> arena;
     std::vector<int32_t> read_off, site;
     uint64_t path_counters[3] = { 0, 0, 0 };
+    // pg_batch_upload / pg_batch_run: the staged input of the three-step form
+    std::vector<char> up_bases;
+    std::vector<int32_t> up_off, up_site;
+    int up_n = -1;
+    bool up_have_site = false, up_ran = false;
+    uint32_t up_flags = 0;
 };
 
 namespace
@@ -303,6 +309,38 @@ int pg_align_batch(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t*
     if (!c->arena.empty())
         memcpy(ops_out, c->arena.data(), c->arena.size() * sizeof(uint32_t));
     return PG_OK;
+}
+
+// the three-step form: upload keeps a copy of the input, run notes the flags, download does the work
+int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t* off, const int32_t* site)
+{
+    if (!c || n_reads < 0 || (n_reads > 0 && (!bases || !off)))
+        return shim_fail(c, PG_E_ARG, "pg_batch_upload: bad arguments");
+    c->up_n = n_reads;
+    c->up_off.assign(off, off + n_reads + 1);
+    c->up_bases.assign(bases, bases + (n_reads ? off[n_reads] : 0));
+    c->up_have_site = site != nullptr;
+    if (site)
+        c->up_site.assign(site, site + n_reads);
+    c->up_ran = false;
+    return PG_OK;
+}
+
+int pg_batch_run(pg_ctx* c, uint32_t flags)
+{
+    if (!c || c->up_n < 0)
+        return shim_fail(c, PG_E_STATE, "pg_batch_run: no batch uploaded");
+    c->up_flags = flags;
+    c->up_ran = true;
+    return PG_OK;
+}
+
+int pg_batch_download(pg_ctx* c, pg_record* records, uint32_t* ops, uint64_t cap, uint64_t* used)
+{
+    if (!c || !c->up_ran)
+        return shim_fail(c, PG_E_STATE, "pg_batch_download: no batch ran");
+    return pg_align_batch(c, c->up_n, c->up_bases.data(), c->up_off.data(), c->up_have_site ? c->up_site.data() : nullptr,
+                          c->up_flags, records, ops, cap, used);
 }
 
 int pg_format_cigar(const pg_record* rec, const uint32_t* ops, char* out, int cap)

@@ -183,6 +183,14 @@ int main(int argc, char** argv)
             else
                 throw std::runtime_error("unknown mode " + mode);
         }
+        {
+            // host phases of the mirror, per step (warm-up included in the sums; the printed figure is the mean)
+            auto& ph = pgb::grm::detail::Phases::instance();
+            fprintf(stderr, "phases (ms per step, %d steps incl. warm-up):", warmup + steps);
+            for (int i = 0; i < pgb::grm::detail::Phases::N; ++i)
+                fprintf(stderr, " %s %.3f", pgb::grm::detail::Phases::name(i), ph.ns[i] * 1e-6 / (warmup + steps));
+            fprintf(stderr, "\n");
+        }
         printf("{\"mode\": \"%s\", \"sites\": %zu, \"reads\": %zu, \"steps\": %d, \"threads\": %u, \"devices\": %zu, "
                "\"seconds\": %.6f, \"reads_per_s\": %.1f, \"producer_seconds\": %.6f, \"kept\": %zu, \"node_rows\": %zu}\n",
                mode.c_str(), sites.size(), n_reads, steps, threads, devices.size(), timed,
