@@ -423,9 +423,9 @@ public:
     // Engines of finished aligners are kept per host thread and handed to the next aligner on that thread: the
     // reference builds its aligners per call (Align.cpp:96-110) and grmpy calls alignReads once per (sample, target)
     // with a few hundred reads (Workflow.cpp:108-146) -- creating a context, its streams and its device buffers each
-    // time costs milliseconds, more than aligning those reads.  A pooled engine comes back without graphs and with
-    // the default stages.
-    static std::unique_ptr<Engine> take(int device)
+    // time costs milliseconds, more than aligning those reads.  A pooled engine comes back with the default stages
+    // and, unless the taker asks for it (keep_graph: GraphAligner, which compares graph_key), without graphs.
+    static std::unique_ptr<Engine> take(int device, bool keep_graph = false)
     {
         auto& p = pool();
         for (size_t i = 0; i < p.size(); ++i)
@@ -433,6 +433,11 @@ public:
             {
                 std::unique_ptr<Engine> e = std::move(p[i]);
                 p.erase(p.begin() + (std::ptrdiff_t)i);
+                if (!keep_graph && !e->graph_key.empty())
+                {
+                    e->graph_key.clear();
+                    e->check(pg_clear_graphs(e->get()));
+                }
                 return e;
             }
         return std::unique_ptr<Engine>(new Engine(device));
@@ -441,9 +446,14 @@ public:
     {
         if (!e || pool().size() >= 4)
             return; // (destroyed)
-        if (pg_clear_graphs(e->get()) == PG_OK && pg_set_stages(e->get(), 0, 1, 0) == PG_OK)
+        if ((!e->graph_key.empty() || pg_clear_graphs(e->get()) == PG_OK) && pg_set_stages(e->get(), 0, 1, 0) == PG_OK
+            && pg_set_kmer_stage(e->get(), 0) == PG_OK)
             pool().push_back(std::move(e));
     }
+    // Non-empty: the engine holds exactly the one graph (+ paths) this key spells out, registered by a GraphAligner.
+    // grmpy aligns every sample to the same graphs (Workflow.cpp:108-146): the next aligner on this thread that sets
+    // the same graph finds it on the device already.
+    std::string graph_key;
 
     // staging of the current batch (one batch at a time per engine, like one aligner per thread in the reference)
     detail::PinnedBuf<char> blob;
@@ -451,19 +461,33 @@ public:
     detail::PinnedBuf<pg_record> rec;
     detail::PinnedBuf<uint32_t> ops;
 
-    // gather the bases of which[0..n) into blob / off (sizes serially, bytes on `threads` threads); returns the bytes
+    // gather the bases of which[0..n) into blob / off; returns the bytes.  Both looks at the reads (lengths, then bytes)
+    // run on `threads` threads -- at this point the reads are cold in the caches and a serial pass over them costs more
+    // than the copy; the prefix sum between them runs over the offsets only.
     template <typename GetBases> size_t pack(size_t n, unsigned threads, GetBases&& bases_of)
     {
         int32_t* o = off.reserve(n + 1);
-        size_t total = 0;
         o[0] = 0;
-        for (size_t i = 0; i < n; ++i)
+        std::atomic<bool> too_long{ false };
+        detail::parallelFor(n, threads, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i)
+            {
+                const size_t len = bases_of(i).size();
+                if (len > (size_t)INT_MAX)
+                    too_long = true;
+                o[i + 1] = (int32_t)len;
+            }
+        });
+        size_t total = 0;
+        for (size_t i = 0; i < n && !too_long; ++i)
         {
-            total += bases_of(i).size();
+            total += (size_t)o[i + 1];
             if (total > (size_t)INT_MAX)
-                throw std::runtime_error("paragraph_b200: more than 2 GB of read bases in one batch");
+                too_long = true;
             o[i + 1] = (int32_t)total;
         }
+        if (too_long)
+            throw std::runtime_error("paragraph_b200: more than 2 GB of read bases in one batch");
         char* b = blob.reserve(total + 1);
         detail::parallelFor(n, threads, [&](size_t lo, size_t hi) {
             for (size_t i = lo; i < hi; ++i)
@@ -511,7 +535,7 @@ public:
     static const unsigned int AF_REVERSE_GRAPH = 0x04;
     static const unsigned int AF_ALL = (unsigned int)-1;
 
-    explicit GraphAligner(int device = 0) : engine_(Engine::take(device)) {}
+    explicit GraphAligner(int device = 0) : engine_(Engine::take(device, true)) {}
     ~GraphAligner()
     {
         Engine::give(std::move(engine_));
@@ -540,8 +564,8 @@ public:
         }
         path_ptr_.clear();
         path_nodes_.clear();
-        registerGraph(*engine_);
-        engine2_fresh_ = false;
+        key_.clear();
+        engine1_fresh_ = engine2_fresh_ = false; // registered when the next batch (or context()) needs it
     }
     // the stages in front of gssw and the paths the k-mer stage aligns to (pg_set_stages / pg_set_kmer_stage / pg_set_paths):
     // kept here so that a second engine can be brought to the same configuration
@@ -556,8 +580,8 @@ public:
     {
         path_ptr_ = std::move(ptr);
         path_nodes_ = std::move(nodes);
-        engine_->check(pg_set_paths(engine_->get(), 0, (int32_t)path_ptr_.size() - 1, path_ptr_.data(), path_nodes_.data()));
-        engine2_fresh_ = false;
+        key_.clear();
+        engine1_fresh_ = engine2_fresh_ = false;
     }
 
     // the loop `for read: alignRead(read, flags)` as one batch; writes the fields GraphAligner::alignRead writes
@@ -566,11 +590,15 @@ public:
     // packing and the write-back of one half (strings: reverse complements, CIGAR text) overlap the kernels of the other.
     template <typename ReadIt>
     void alignBatch(ReadIt begin, ReadIt end, unsigned flags = AF_ALL, std::vector<pg_record>* records_out = nullptr,
-                    bool tolerate_unmapped = false) const
+                    bool tolerate_unmapped = false, bool all_nonempty = false,
+                    std::function<void(size_t, size_t)> const* post = nullptr) const
     {
+        // post(lo, hi): called on the thread that just wrote reads [lo, hi) of the batch back (indices into the non-empty
+        // reads of [begin, end)), after records_out holds their records -- the caller's per-read work (filter, tallies)
+        // joins the pipeline instead of following it
         std::vector<ReadIt> which;
         for (ReadIt it = begin; it != end; ++it)
-            if (!(*it)->bases().empty())
+            if (all_nonempty || !(*it)->bases().empty())
                 which.push_back(it);
         if (which.empty())
             return;
@@ -578,6 +606,7 @@ public:
         if (records_out)
             records_out->resize(n);
         anchored_ = 0;
+        ensureRegistered();
         // one part of the batch in two steps: submit = pack + H2D + kernels (returns with the kernels in flight),
         // collect = D2H + write-back into the reads
         auto submit = [&](Engine& e, size_t lo, size_t hi) -> size_t {
@@ -614,6 +643,8 @@ public:
                 for (size_t i = a; i < b; ++i)
                     if (!(tolerate_unmapped && rec[i].status == 3)) // 3: no enabled stage mapped the read -- it stays UNMAPPED
                         applyRecord(**which[lo + i], rec[i], ops, flags, lo + i);
+                if (post)
+                    (*post)(lo + a, lo + b);
             });
         };
         if (n < pipeline_min_reads_)
@@ -627,14 +658,16 @@ public:
         // threads) runs while the kernels of the next are in flight.  Parts of pipeline_min_reads_ / 2 reads or more,
         // at most pipeline_max_parts_ of them.
         if (!engine2_)
-            engine2_ = Engine::take(engine_->device());
+            engine2_ = Engine::take(engine_->device(), true);
         if (!engine2_fresh_)
         {
             registerGraph(*engine2_);
             engine2_fresh_ = true;
         }
         const size_t parts = std::max<size_t>(2, std::min<size_t>(pipeline_max_parts_, n / std::max<size_t>(pipeline_min_reads_ / 2, 1)));
-        auto bound = [&](size_t k) { return n * k / parts; };
+        // (two parts: the first one may be the larger -- what follows the last download, the write-back of the last part,
+        // is not hidden behind any kernel)
+        auto bound = [&](size_t k) { return parts == 2 && k == 1 ? n * pipeline_first_pct_ / 100 : n * k / parts; };
         Engine* eng[2] = { engine_.get(), engine2_.get() };
         size_t cap[2] = { 0, 0 };
         cap[0] = submit(*eng[0], bound(0), bound(1));
@@ -762,7 +795,11 @@ public:
         out.resize((size_t)(p - base));
     }
 
-    pg_ctx* context() const { return engine_->get(); }
+    pg_ctx* context() const
+    {
+        ensureRegistered();
+        return engine_->get();
+    }
     void check(int rc) const { engine_->check(rc); }
 
     template <typename ReadT> void alignRead(ReadT& read, unsigned flags = AF_ALL) const
@@ -784,18 +821,48 @@ public:
     }
 
 private:
+    void ensureRegistered() const
+    {
+        if (!engine1_fresh_)
+        {
+            registerGraph(*engine_);
+            engine1_fresh_ = true;
+        }
+    }
+    // brings an engine to this aligner's graph and paths; nothing to do when it holds them already (Engine::graph_key)
     void registerGraph(Engine& e) const
     {
+        if (off_.size() < 2)
+            throw std::runtime_error("paragraph_b200: GraphAligner used before setGraph");
+        if (key_.empty())
+        {
+            auto put = [this](const void* p, size_t bytes) {
+                const uint64_t n = bytes;
+                key_.append(reinterpret_cast<const char*>(&n), sizeof n);
+                key_.append(static_cast<const char*>(p), bytes);
+            };
+            put(blob_.data(), blob_.size());
+            put(off_.data(), off_.size() * sizeof(int32_t));
+            put(ef_.data(), ef_.size() * sizeof(int32_t));
+            put(et_.data(), et_.size() * sizeof(int32_t));
+            put(path_ptr_.data(), path_ptr_.size() * sizeof(int32_t));
+            put(path_nodes_.data(), path_nodes_.size() * sizeof(int32_t));
+        }
+        if (e.graph_key == key_)
+            return;
+        e.graph_key.clear();
         e.check(pg_clear_graphs(e.get()));
         int32_t sid = -1;
         e.check(pg_add_graph(e.get(), (int32_t)off_.size() - 1, blob_.data(), off_.data(), (int32_t)ef_.size(), ef_.data(), et_.data(),
                              &sid));
         if (!path_ptr_.empty())
             e.check(pg_set_paths(e.get(), 0, (int32_t)path_ptr_.size() - 1, path_ptr_.data(), path_nodes_.data()));
+        e.graph_key = key_;
     }
     std::unique_ptr<Engine> engine_;
     mutable std::unique_ptr<Engine> engine2_; // second half of a pipelined batch
-    mutable bool engine2_fresh_ = false;      // engine2_ holds the current graph and paths
+    mutable bool engine1_fresh_ = false, engine2_fresh_ = false; // the engine holds the current graph and paths
+    mutable std::string key_;                                    // what Engine::graph_key is compared with
     mutable std::atomic<uint64_t> anchored_{ 0 };
     unsigned threads_ = 1;
     // tuning knobs, PGB_PIPELINE_MIN_READS / PGB_PIPELINE_PARTS in the environment override the defaults
@@ -806,6 +873,7 @@ private:
     }
     size_t pipeline_min_reads_ = envKnob("PGB_PIPELINE_MIN_READS", 4096);
     size_t pipeline_max_parts_ = std::max<size_t>(2, envKnob("PGB_PIPELINE_PARTS", 2));
+    size_t pipeline_first_pct_ = std::min<size_t>(90, std::max<size_t>(10, envKnob("PGB_PIPELINE_FIRST_PCT", 50)));
     std::string blob_;
     std::vector<int32_t> off_{ 0 }, ef_, et_, path_ptr_, path_nodes_;
     int path_k_ = 0, kmer_k_ = 0;
@@ -1341,7 +1409,11 @@ public:
             graphAligner_.setPaths(std::move(ptr), std::move(nodes));
         }
     }
-    void setThreads(unsigned threads) { graphAligner_.setThreads(threads); }
+    void setThreads(unsigned threads)
+    {
+        threads_ = threads ? threads : 1;
+        graphAligner_.setThreads(threads);
+    }
 
     // CompositeAligner::alignRead for a whole range (CompositeAligner.cpp:78-176).  The reference runs, per read: the
     // exact-match stage (:82-95), the filter on its result with a second chance in the later stages for a rejected
@@ -1350,26 +1422,51 @@ public:
     // stage is one launch over the batch, so the cascade runs in rounds: all enabled stages over all reads; then the
     // later stages over the reads whose exact match the filter rejected; then gssw over the reads whose k-mer
     // alignment it rejected.  Counters as in the reference.
-    template <typename ReadIt, typename FilterT> void alignReads(ReadIt begin, ReadIt end, FilterT filter)
+    // reset_status: every non-empty read starts UNMAPPED (what grm::alignReads does first, Align.cpp:72-78)
+    template <typename ReadIt, typename FilterT>
+    void alignReads(ReadIt begin, ReadIt end, FilterT filter, bool reset_status = false)
     {
         typedef typename std::remove_reference<decltype(**begin)>::type ReadT;
-        std::vector<ReadT*> todo;
+        // the reads that take part: the look at each read (cold in the caches at this point) on the host threads, then
+        // one pass over the flags
+        std::vector<ReadT*> all;
         for (ReadIt it = begin; it != end; ++it)
-            if (!(*it)->bases().empty())
-            {
-                ++attempted_;
-                todo.push_back(&**it);
-            }
+            all.push_back(&**it);
+        std::vector<uint8_t> takes_part(all.size());
+        detail::parallelFor(all.size(), threads_, [&](size_t lo, size_t hi) {
+            for (size_t i = lo; i < hi; ++i)
+                if ((takes_part[i] = !all[i]->bases().empty()) && reset_status)
+                    all[i]->set_graph_mapping_status(ReadT::UNMAPPED);
+        });
+        std::vector<ReadT*> todo;
+        todo.reserve(all.size());
+        for (size_t i = 0; i < all.size(); ++i)
+            if (takes_part[i])
+                todo.push_back(all[i]);
+        attempted_ += (unsigned)todo.size();
         // stage sets of the rounds: {path?, kmer?, gssw?}
         bool path_on = pathMatching_, kmer_on = kmerMatching_;
         while (!todo.empty() && (path_on || kmer_on || graphMatching_))
         {
             graphAligner_.setStages(path_on ? pathKmerSize_ : 0, graphMatching_, false, kmer_on ? kmerSize_ : 0);
             std::vector<pg_record> rec;
-            graphAligner_.alignBatch(todo.begin(), todo.end(), flags_, &rec, /*tolerate_unmapped=*/true);
             std::vector<ReadT*> after_path, after_kmer; // rejected by the filter right after that stage
-            detail::Phases::Scope ph(detail::Phases::FILTER);
-            for (size_t i = 0; i < todo.size(); ++i)
+            // statuses, filter and counters: on the `threads` host threads in contiguous chunks of the batch, right after a
+            // chunk's records were written into its reads (alignBatch's `post`), as the reference's alignReads runs its
+            // filter callback from its worker threads (Align.cpp:119-153); with one thread the callback sees the reads in
+            // input order.  The chunks' tallies are merged in chunk order.
+            struct Tally
+            {
+                size_t lo = 0;
+                unsigned mappedPath = 0, mappedKmers = 0, mappedSw = 0, filtered = 0;
+                std::vector<ReadT*> after_path, after_kmer;
+            };
+            std::vector<Tally> tallies;
+            std::mutex tallies_mutex;
+            const std::function<void(size_t, size_t)> post = [&](size_t lo, size_t hi) {
+            Tally t;
+            t.lo = lo;
+            for (size_t i = lo; i < hi; ++i)
             {
                 ReadT& read = *todo[i];
                 const pg_record& r = rec[i];
@@ -1390,13 +1487,13 @@ public:
                 const bool rejected = filter && filter(read);
                 if (by_path)
                 {
-                    ++mappedPath_;
+                    ++t.mappedPath;
                     if (rejected)
                     {
                         read.set_graph_mapping_status(ReadT::BAD_ALIGN);
-                        filtered_ += !kmerMatching_ && !graphMatching_;
+                        t.filtered += !kmerMatching_ && !graphMatching_;
                         if (kmerMatching_ || graphMatching_)
-                            after_path.push_back(&read);
+                            t.after_path.push_back(&read);
                     }
                 }
                 else if (by_kmer)
@@ -1404,21 +1501,37 @@ public:
                     if (rejected)
                     {
                         read.set_graph_mapping_status(ReadT::BAD_ALIGN);
-                        filtered_ += !graphMatching_;
+                        t.filtered += !graphMatching_;
                         if (graphMatching_)
-                            after_kmer.push_back(&read);
+                            t.after_kmer.push_back(&read);
                     }
                     else
-                        ++mappedKmers_;
+                        ++t.mappedKmers;
                 }
                 else if (rejected)
                 {
                     read.set_graph_mapping_status(ReadT::BAD_ALIGN);
-                    ++filtered_;
+                    ++t.filtered;
                 }
                 else
-                    ++mappedSw_;
+                    ++t.mappedSw;
             }
+            std::lock_guard<std::mutex> lock(tallies_mutex);
+            tallies.push_back(std::move(t));
+            };
+            graphAligner_.alignBatch(todo.begin(), todo.end(), flags_, &rec, /*tolerate_unmapped=*/true, /*all_nonempty=*/true, &post);
+            detail::Phases::Scope ph(detail::Phases::FILTER);
+            std::sort(tallies.begin(), tallies.end(), [](Tally const& a, Tally const& b) { return a.lo < b.lo; });
+            for (Tally const& t : tallies)
+            {
+                mappedPath_ += t.mappedPath;
+                mappedKmers_ += t.mappedKmers;
+                mappedSw_ += t.mappedSw;
+                filtered_ += t.filtered;
+                after_path.insert(after_path.end(), t.after_path.begin(), t.after_path.end());
+                after_kmer.insert(after_kmer.end(), t.after_kmer.begin(), t.after_kmer.end());
+            }
+            ph.next(-1);
             if (path_on)
                 anchoredPath_ += (unsigned)graphAligner_.lastAnchored();
             // next round: what the filter sent on.  (After the exact-match stage: k-mer stage and gssw; the reads the
@@ -1472,13 +1585,15 @@ private:
     const unsigned flags_;
     const int pathKmerSize_, kmerSize_;
     GraphAligner graphAligner_;
+    unsigned threads_ = 1;
     unsigned attempted_ = 0, filtered_ = 0, mappedSw_ = 0, mappedPath_ = 0, anchoredPath_ = 0, mappedKmers_ = 0;
     std::vector<void*> pending_gssw_; // reads the filter rejected after the k-mer stage, waiting for the gssw-only round
 };
 
 // grm::alignReads (Align.hh:49-52; Align.cpp:114-156): aligns, then keeps only MAPPED reads (input order).
-// The batch is one GPU launch sequence; `threads` host threads pack it and write the results back (detail::parallelFor),
-// the filter callback runs afterwards on the calling thread, in input order.
+// The batch is one GPU launch sequence; `threads` host threads pack it, write the results back and run the filter
+// callback (detail::parallelFor: contiguous chunks of the input, so one thread means input order) -- the reference calls
+// the filter from its `threads` worker threads too (Align.cpp:119-153), a filter that is safe there is safe here.
 template <typename GraphT, typename PathListT, typename ReadPtrT, typename FilterT>
 void alignReads(GraphT const* graph, PathListT const& paths, std::vector<ReadPtrT>& reads, FilterT const& filter,
                 bool path_sequence_matching, bool graph_sequence_matching, bool klib_sequence_matching,
@@ -1491,17 +1606,22 @@ void alignReads(GraphT const* graph, PathListT const& paths, std::vector<ReadPtr
                              kmer_sequence_matching, GraphAligner::AF_ALL, device);
     aligner.setGraph(graph, paths);
     aligner.setThreads(threads);
-    ph.next(detail::Phases::KEEP);
-    for (auto& r : reads) // Align.cpp:72-78
-        if (!r->bases().empty())
-            r->set_graph_mapping_status(std::remove_reference<decltype(*r)>::type::UNMAPPED);
+    typedef typename std::remove_reference<decltype(*reads.front())>::type ReadT;
     ph.next(-1);
-    aligner.alignReads(reads.begin(), reads.end(), filter);
+    aligner.alignReads(reads.begin(), reads.end(), filter, /*reset_status=*/true); // (Align.cpp:72-78 inside)
     ph.next(detail::Phases::KEEP);
+    // MAPPED reads only, in input order: the flags on the host threads (each touches the reads it wrote), then one pass
+    // over the pointers
+    std::vector<uint8_t> keep(reads.size());
+    detail::parallelFor(reads.size(), threads, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; ++i)
+            keep[i] = !reads[i]->bases().empty() && reads[i]->graph_mapping_status() == ReadT::MAPPED;
+    });
     std::vector<ReadPtrT> kept;
-    for (auto& r : reads)
-        if (!r->bases().empty() && r->graph_mapping_status() == std::remove_reference<decltype(*r)>::type::MAPPED)
-            kept.emplace_back(std::move(r));
+    kept.reserve(reads.size());
+    for (size_t i = 0; i < reads.size(); ++i)
+        if (keep[i])
+            kept.emplace_back(std::move(reads[i]));
     reads.swap(kept); // Align.cpp:155
 }
 

@@ -1715,6 +1715,9 @@ struct pg_ctx
 
     host::GraphStore graphs;
     bool graphs_dirty = true;
+    PinBuf<uint8_t> h_graph;        // page-locked staging of the graph store: its upload does not hold up the host
+    cudaEvent_t ev_graph = nullptr; // the last upload out of h_graph is through
+    bool graph_staging_busy = false;
     DevBuf<SiteDev> d_sites;
     DevBuf<uint8_t> d_gbytes;
     DevBuf<int32_t> d_gints;
@@ -1837,6 +1840,27 @@ bool is_pinned(const void* p)
     return a.type == cudaMemoryTypeHost;
 }
 
+// PG_DEBUG_HOST=1: where the host time of the entry points goes (microseconds between laps, on stderr)
+struct HostLaps
+{
+    const bool on;
+    const char* const who;
+    std::chrono::steady_clock::time_point t;
+    explicit HostLaps(const char* w) : on(getenv("PG_DEBUG_HOST") != nullptr), who(w)
+    {
+        if (on)
+            t = std::chrono::steady_clock::now();
+    }
+    void lap(const char* what)
+    {
+        if (!on)
+            return;
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pg host] %s: %s %.1f us\n", who, what, std::chrono::duration<double, std::micro>(n - t).count());
+        t = n;
+    }
+};
+
 int upload_graphs(pg_ctx* c)
 {
     if (!c->graphs_dirty)
@@ -1846,14 +1870,24 @@ int upload_graphs(pg_ctx* c)
     PG_CUDA(c, c->d_sites.reserve(c->graphs.sites.size()));
     PG_CUDA(c, c->d_gbytes.reserve(c->graphs.bytes.size()));
     PG_CUDA(c, c->d_gints.reserve(c->graphs.ints.size()));
-    PG_CUDA(c, cudaMemcpyAsync(c->d_sites.p, c->graphs.sites.data(), c->graphs.sites.size() * sizeof(SiteDev),
-                               cudaMemcpyHostToDevice, c->stream));
-    PG_CUDA(c, cudaMemcpyAsync(c->d_gbytes.p, c->graphs.bytes.data(), c->graphs.bytes.size(), cudaMemcpyHostToDevice,
-                               c->stream));
-    PG_CUDA(c, cudaMemcpyAsync(c->d_gints.p, c->graphs.ints.data(), c->graphs.ints.size() * sizeof(int32_t),
-                               cudaMemcpyHostToDevice, c->stream));
-    // the source vectors are pageable: the copies above are synchronous with respect to the host buffers
-    PG_CUDA(c, cudaStreamSynchronize(c->stream));
+    // through page-locked staging: the copies are asynchronous, the host goes on to launch the kernels behind them
+    const size_t b_sites = c->graphs.sites.size() * sizeof(SiteDev), b_bytes = c->graphs.bytes.size(),
+                 b_ints = c->graphs.ints.size() * sizeof(int32_t);
+    const size_t o_bytes = (b_sites + 15) & ~(size_t)15, o_ints = (o_bytes + b_bytes + 15) & ~(size_t)15;
+    if (!c->ev_graph)
+        PG_CUDA(c, cudaEventCreateWithFlags(&c->ev_graph, cudaEventDisableTiming));
+    if (c->graph_staging_busy) // (a graph registered while the previous one is still on its way: rare)
+        PG_CUDA(c, cudaEventSynchronize(c->ev_graph));
+    c->graph_staging_busy = false;
+    PG_CUDA(c, c->h_graph.reserve(o_ints + b_ints + 16));
+    memcpy(c->h_graph.p, c->graphs.sites.data(), b_sites);
+    memcpy(c->h_graph.p + o_bytes, c->graphs.bytes.data(), b_bytes);
+    memcpy(c->h_graph.p + o_ints, c->graphs.ints.data(), b_ints);
+    PG_CUDA(c, cudaMemcpyAsync(c->d_sites.p, c->h_graph.p, b_sites, cudaMemcpyHostToDevice, c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(c->d_gbytes.p, c->h_graph.p + o_bytes, b_bytes, cudaMemcpyHostToDevice, c->stream));
+    PG_CUDA(c, cudaMemcpyAsync(c->d_gints.p, c->h_graph.p + o_ints, b_ints, cudaMemcpyHostToDevice, c->stream));
+    PG_CUDA(c, cudaEventRecord(c->ev_graph, c->stream));
+    c->graph_staging_busy = true;
     c->graphs_dirty = false;
     return PG_OK;
 }
@@ -2193,6 +2227,7 @@ cudaError_t get(pg_ctx* c, void* dst, const void* src, size_t bytes)
 template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
 {
     constexpr int NT = 32 / W;
+    HostLaps laps("run_chunks");
     const int max_nodes = c->graphs.max_nodes, max_G = c->graphs.max_G;
     const size_t s_last = host::last_words(max_nodes, R, W), s_ckpt = host::ckpt_words(max_G, R, W);
     // fill kernel shared memory per task: profile + seed/info tables; fewer warps per CTA for many-node graphs, and
@@ -2281,6 +2316,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     PG_CUDA(c, cudaFuncSetAttribute(pg_fill_kernel<R, W, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
     PG_CUDA(c, cudaFuncSetAttribute(pg_trace_kernel<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
 
+    laps.lap("buffers + function attributes");
     const size_t n_chunks = ((size_t)c->n_reads + chunk - 1) / chunk;
     while (c->evpool.size() < 4 * n_chunks)
     {
@@ -2350,6 +2386,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
         PG_CUDA(c, cudaEventRecord(c->evpool[0], c->stream));
         PG_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->evpool[0], 0));
     }
+    laps.lap("events + occupancy");
     size_t ci = 0;
     for (size_t r0 = 0; r0 < (size_t)c->n_reads; r0 += chunk, ++ci)
     {
@@ -2489,6 +2526,7 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     if (overlap) // everything later on the caller's stream (download, counting stage) sees both streams finished
         for (size_t k = n_chunks >= 2 ? n_chunks - 2 : 0; k < n_chunks; ++k)
             PG_CUDA(c, cudaStreamWaitEvent(c->stream, c->evpool[4 * k + 3], 0));
+    laps.lap("launches");
     return PG_OK;
 }
 
@@ -2615,6 +2653,9 @@ void pg_destroy(pg_ctx* c)
         if (ev)
             cudaEventDestroy(ev);
     c->h_bases.release();
+    c->h_graph.release();
+    if (c->ev_graph)
+        cudaEventDestroy(c->ev_graph);
     c->h_off.release();
     c->h_site.release();
     c->h_records.release();
@@ -2643,7 +2684,13 @@ int pg_set_stream(pg_ctx* c, void* s)
 {
     if (!c)
         return PG_E_ARG;
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    cudaStream_t next = s ? (cudaStream_t)s : c->own_stream;
+    if (next != c->stream && c->graph_staging_busy) // work on the new stream must see the graphs copied on the old one
+    {
+        PG_CUDA(c, cudaSetDevice(c->device));
+        PG_CUDA(c, cudaStreamWaitEvent(next, c->ev_graph, 0));
+    }
+    c->stream = next;
     return PG_OK;
 }
 
@@ -2720,6 +2767,7 @@ int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t
         Range() { nvtxRangePushA("pg_batch_upload"); }
         ~Range() { nvtxRangePop(); }
     } range;
+    HostLaps laps("pg_batch_upload");
     if (!c || n_reads < 0 || (n_reads > 0 && (!bases || !off)))
         return fail(c, PG_E_ARG, "pg_batch_upload: bad arguments");
     if (n_reads == 0) // an empty batch is legal (grm::alignReads on an empty read vector does nothing)
@@ -2790,6 +2838,7 @@ int pg_batch_upload(pg_ctx* c, int32_t n_reads, const char* bases, const int32_t
     c->imported = false;
     c->uploaded = true;
     c->ran = false;
+    laps.lap("all");
     return PG_OK;
 }
 
@@ -2807,10 +2856,12 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
         c->n_chunks_timed = 0;
         return PG_OK;
     }
+    HostLaps laps("pg_batch_run");
     PG_CUDA(c, cudaSetDevice(c->device));
     int rc = upload_graphs(c);
     if (rc != PG_OK)
         return rc;
+    laps.lap("upload_graphs");
     c->path_ran = c->kmer_ran = false;
     if (c->path_k > 0 || c->kmer_k > 0) // grm::CompositeAligner's stages in front of gssw (CompositeAligner.cpp:82-126)
     {
@@ -2848,6 +2899,7 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
         rc = run_chunks<20, 8>(c, flags);
     else
         rc = c->max_len <= 160 ? run_chunks<10, 16>(c, flags) : run_chunks<16, 16>(c, flags);
+    laps.lap("stages in front + run_chunks");
     if (rc == PG_OK)
         c->ran = true;
     return rc;

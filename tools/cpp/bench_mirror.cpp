@@ -125,6 +125,8 @@ int main(int argc, char** argv)
         for (int it = 0; it < warmup + steps; ++it)
         {
             const bool on = it >= warmup;
+            if (it == warmup)
+                grm::detail::Phases::instance().reset();
             if (mode == "alignReads")
             {
                 std::vector<ReadVec> rv(sites.size());
@@ -184,11 +186,11 @@ int main(int argc, char** argv)
                 throw std::runtime_error("unknown mode " + mode);
         }
         {
-            // host phases of the mirror, per step (warm-up included in the sums; the printed figure is the mean)
+            // host phases of the mirror, mean per timed step
             auto& ph = pgb::grm::detail::Phases::instance();
-            fprintf(stderr, "phases (ms per step, %d steps incl. warm-up):", warmup + steps);
+            fprintf(stderr, "phases (ms per step, %d timed steps):", steps);
             for (int i = 0; i < pgb::grm::detail::Phases::N; ++i)
-                fprintf(stderr, " %s %.3f", pgb::grm::detail::Phases::name(i), ph.ns[i] * 1e-6 / (warmup + steps));
+                fprintf(stderr, " %s %.3f", pgb::grm::detail::Phases::name(i), ph.ns[i] * 1e-6 / (steps > 0 ? steps : 1));
             fprintf(stderr, "\n");
         }
         printf("{\"mode\": \"%s\", \"sites\": %zu, \"reads\": %zu, \"steps\": %d, \"threads\": %u, \"devices\": %zu, "

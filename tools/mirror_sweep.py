@@ -19,9 +19,9 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         f2 = os.path.join(tmp, "config2.txt")
         synth.write_workload_file(f2, [("DEL", nodes, edges, reads)])
-        for minr, parts in ((0, 2), (4096, 2), (4096, 3), (4096, 4), (2048, 6)):
-            for th in (1, 4, 8, 16):
-                env = dict(os.environ, PGB_PIPELINE_PARTS=str(parts),
+        for minr, parts, first in ((0, 2, 50), (4096, 2, 50), (4096, 2, 60), (4096, 3, 50)):
+            for th in (1, 8, 16):
+                env = dict(os.environ, PGB_PIPELINE_PARTS=str(parts), PGB_PIPELINE_FIRST_PCT=str(first),
                            PGB_PIPELINE_MIN_READS=str(minr if minr else 1 << 30))
                 r = subprocess.run([exe, f2, "alignReads", str(steps), "3", str(th), "0"], capture_output=True, text=True,
                                    timeout=600, env=env)
@@ -29,8 +29,8 @@ def main():
                     print("FAILED", minr, parts, th, r.stderr[-300:])
                     continue
                 d = json.loads(r.stdout)
-                print("min_reads %5d parts %d threads %2d: %.2f Mreads/s (%.3f ms/step) | %s" % (
-                    minr, parts, th, d["reads_per_s"] / 1e6, 1e3 * d["seconds"] / d["steps"], r.stderr.strip().split("\n")[-1]))
+                print("min_reads %5d parts %d first %d%% threads %2d: %.2f Mreads/s (%.3f ms/step) | %s" % (
+                    minr, parts, first, th, d["reads_per_s"] / 1e6, 1e3 * d["seconds"] / d["steps"], r.stderr.strip().split("\n")[-1]))
                 sys.stdout.flush()
 
 
