@@ -775,6 +775,162 @@ PG_UNROLL
     --c.colsLeft;
 }
 
+// ---- node boundaries inside the fill's boundary sub-blocks: entry words + prefetched seeds -----------------------
+// A boundary reaches the lanes of a group on consecutive steps, so node_event runs with ONE active lane and costs the
+// warp its whole instruction count every time: 60 (chain) to 130 (merge of two predecessors) issue slots per lane and
+// boundary -- 11 % of the fill's instructions on 3-node graphs, nearly half on 6-9-node vcf2paragraph-shaped ones
+// (profiles/r02d_fill_fwd_source.csv.gz: the rows executed with one thread).  Two things make it lean:
+//   * entry_word(m): what a lane needs to know when it enters node m from node m - 1, precomputed once per task into
+//     shared memory -- the node's length, whether m - 1 is among its predecessors (EV_PREV) and whether anything has
+//     to be merged at all (EV_MERGE; clear for a chain link, where the state just carries over);
+//   * seed_prefetch: at the start of a boundary sub-block, ALL lanes that will enter a merging node within it fold
+//     the last columns of that node's OLDER predecessors (ids < m - 1) at once -- rows they wrote themselves at
+//     earlier boundaries, so they are complete -- which leaves the lane-at-a-time event with the row store and
+//     a register-only maximum (node_event_pre).  A lane that crosses a second boundary within the same sub-block
+//     (nodes shorter than it) takes the general path for that one.
+constexpr uint32_t EV_LEN = 0x3fffffffu, EV_PREV = 0x40000000u, EV_MERGE = 0x80000000u;
+PG_HD uint32_t entry_word(const GraphView& g, int m) // m >= 1
+{
+    const int p0 = g.pred_ptr[m], p1 = g.pred_ptr[m + 1];
+    const bool prev = p1 > p0 && g.pred_idx[p1 - 1] == m - 1; // ids ascending and < m: m - 1 can only be the last one
+    uint32_t w = (uint32_t)g.node_len[m] & EV_LEN;
+    if (prev)
+        w |= EV_PREV;
+    if (!(prev && p1 - p0 == 1))
+        w |= EV_MERGE;
+    return w;
+}
+template <int R> struct SeedPre
+{
+    uint32_t H[R], E[R], hup; // element-wise maximum over the older predecessors' last columns (>= 0)
+    int node;                 // the node they are the seed part of; -1: nothing prefetched
+};
+template <int R, int W>
+PG_HD void seed_prefetch(SeedPre<R>& p, const LaneCtl& c, const GraphView& g, const uint32_t* entry, int lane,
+                         const uint32_t* tab, int horizon)
+{
+    constexpr int RW = Sizes<R, W>::ROWW;
+    p.node = -1;
+    const int m = c.node + 1;
+    if (c.colsLeft >= horizon || m >= g.n_nodes)
+        return;
+    const uint32_t w = entry[m];
+    if (!(w & EV_MERGE))
+        return;
+    p.node = m;
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+        p.H[r] = p.E[r] = 0;
+    p.hup = 0;
+    const int p0 = g.pred_ptr[m], p1 = g.pred_ptr[m + 1] - ((w & EV_PREV) ? 1 : 0);
+PG_NOUNROLL
+    for (int e = p0; e < p1; ++e)
+    {
+        const uint32_t* src = node_row<R, W>(tab, g.pred_idx[e], lane);
+        seed_max<R, W>(src, p.H, p.E);
+        if (lane > 0)
+            p.hup = max2(p.hup, seed_bottom_h<R, W>(src - RW));
+    }
+}
+// node_event<R, true, W> of a non-WIDE geometry with the entry words and (where it applies) the prefetched seed part
+template <int R, int W>
+PG_HD_COLD void node_event_pre(Lane<R>& s, LaneCtl& c, const GraphView& g, const uint32_t* entry, const SeedPre<R>& pre,
+                               int lane, uint32_t* tab)
+{
+    // (byte-packed rows: non-WIDE geometries only)
+    constexpr int V = Sizes<R, W>::SEEDV, RW = Sizes<R, W>::ROWW;
+    const int n = c.node;
+    {
+        uint32_t v[RW];
+PG_UNROLL
+        for (int x = 0; x < RW; ++x)
+            v[x] = 0u;
+PG_UNROLL
+        for (int r = 0; r < R; ++r)
+            v[r] = pack_he(s.Hp[r], s.E[r]);
+        v[V + 0] = c.Mnode;
+        v[V + 1] = (uint32_t)c.first[0];
+        v[V + 2] = (uint32_t)c.first[1];
+        c.Mnode = pk(-MBIAS, -MBIAS);
+        uint32_t* row = node_row<R, W>(tab, n, lane);
+#if defined(__CUDA_ARCH__)
+PG_UNROLL
+        for (int x = 0; x < RW / 4; ++x)
+            reinterpret_cast<uint4*>(row)[x] = make_uint4(v[4 * x], v[4 * x + 1], v[4 * x + 2], v[4 * x + 3]);
+#else
+        for (int x = 0; x < RW; ++x)
+            row[x] = v[x];
+#endif
+    }
+    c.node = n + 1;
+    if (n + 1 < g.n_nodes)
+    {
+        const uint32_t w = entry[n + 1];
+        c.colsLeft = (int)(w & EV_LEN) - 1;
+        if (w & EV_MERGE)
+        {
+            if (pre.node == n + 1)
+            {
+                if (w & EV_PREV) // the node just finished is a predecessor too: the registers are its last column
+                {
+PG_UNROLL
+                    for (int r = 0; r < R; ++r)
+                    {
+                        s.Hp[r] = max2(s.Hp[r], pre.H[r]);
+                        s.E[r] = max2(s.E[r], pre.E[r]);
+                    }
+                    s.hupPrev = max2(s.hupPrev, pre.hup);
+                }
+                else
+                {
+PG_UNROLL
+                    for (int r = 0; r < R; ++r)
+                    {
+                        s.Hp[r] = pre.H[r];
+                        s.E[r] = pre.E[r];
+                    }
+                    s.hupPrev = pre.hup;
+                }
+            }
+            else // second boundary of this lane within one sub-block: the general statement
+            {
+                uint32_t H[R], E[R], hup = 0;
+                for (int r = 0; r < R; ++r)
+                    H[r] = E[r] = 0;
+                const int p0 = g.pred_ptr[n + 1], p1 = g.pred_ptr[n + 2];
+PG_NOUNROLL
+                for (int e = p0; e < p1; ++e)
+                {
+                    const int p = g.pred_idx[e];
+                    if (p == n)
+                    {
+PG_UNROLL
+                        for (int r = 0; r < R; ++r)
+                        {
+                            H[r] = max2(H[r], s.Hp[r]);
+                            E[r] = max2(E[r], s.E[r]);
+                        }
+                        hup = max2(hup, s.hupPrev);
+                        continue;
+                    }
+                    const uint32_t* src = node_row<R, W>(tab, p, lane);
+                    seed_max<R, W>(src, H, E);
+                    if (lane > 0)
+                        hup = max2(hup, seed_bottom_h<R, W>(src - RW));
+                }
+                for (int r = 0; r < R; ++r)
+                {
+                    s.Hp[r] = H[r];
+                    s.E[r] = E[r];
+                }
+                s.hupPrev = hup;
+            }
+        }
+    }
+    else
+        c.colsLeft = COLS_INF - 1;
+}
+
 // Checkpoint = lane state at the top of a step, byte-packed: every value is two halves in [0, 255] once clamped at
 // 0 (scores <= MAX_READ_LEN; negative E / F are equivalent to 0), so two packed registers fit
 // one 32-bit word: (lo0, hi0, lo1, hi1).  R + 1 words per lane instead of 2R + 2.
@@ -1141,6 +1297,12 @@ PG_HD int emit_cigar(const uint32_t* oplog, int n, uint32_t* out, int cap)
 // ---------------------------------------------------------------------------------------------
 // A tile holds H/E/F (bytes, the chosen half, clamped at 0 like gssw's unsigned saturation) of all rows for
 // CK consecutive wavefront steps; cell (node n, column i in node, row j) lives at step node_start[n]+i+j/R.
+// steps of tile T the walk can still look at after a miss at need_step (see the trace kernel's recompute phase)
+PG_HD int tile_steps_needed(int need_step, int T)
+{
+    const int n = need_step - T * CK + 3;
+    return n < CK ? n : CK;
+}
 template <int R> struct TileBuf
 {
     uint32_t* mem;    // [2 slots][CK][BAND_ROWS] cell words

@@ -58,6 +58,9 @@ namespace
                         // barriers it can see declared (in dynamic shared memory it reports "Missing init" on every wait
                         // and aborts the kernel; profiles/r02e_synccheck_variants.txt)
 #endif
+#ifndef PG_LEAN_EVENTS
+#define PG_LEAN_EVENTS 1 // entry words + prefetched seeds at node boundaries (pg_core.cuh: node_event_pre); 0 = A/B
+#endif
 #ifndef PG_FAST_BLOCKS
 #define PG_FAST_BLOCKS 1
 #endif
@@ -319,6 +322,15 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
         for (int x = gl; x < sd.tab_ints; x += W)
             tabS[x] = a.gints[sd.tab_off[o] + x];
     const GraphView g = STAGED ? make_view_at(sd, a.gbytes + sd.codes_off[o], tabS) : make_view(sd, a.gbytes, a.gints, o);
+    // ... followed by the entry word of every node (pg_core.cuh: entry_word), what a lane reads when it crosses into it
+    uint32_t* evS = reinterpret_cast<uint32_t*>(tabS + sd.tab_ints);
+    constexpr bool LEAN_EVENTS = STAGED && !TABG && !WIDE && PG_LEAN_EVENTS;
+    if (LEAN_EVENTS)
+    {
+        __syncwarp();
+        for (int m = 1 + gl; m < sd.n_nodes; m += W)
+            evS[m] = entry_word(g, m);
+    }
     const uint8_t* bases = a.bases + a.read_off[rd];
     const int L = a.read_off[rd + 1] - a.read_off[rd];
     // node sequences (column codes) of this task's orientation: TMA-staged into shared memory when they fit
@@ -405,21 +417,31 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                 const uint8_t* cpb = cp + sb;
                 if (!__all_sync(FULL, c.colsLeft >= SPEC_STEPS))
                 {
+                    // the lanes that enter a merging node within this sub-block fold its older predecessors' last
+                    // columns now, together (pg_core.cuh: seed_prefetch) -- their events, one lane at a time, stay short
+                    SeedPre<R> pre;
+                    if (LEAN_EVENTS)
+                    {
+                        __syncwarp();
+                        seed_prefetch<R, W>(pre, c, g, evS, gl, seedS, SPEC_STEPS);
+                    }
 #pragma unroll FILL_UNROLL
                     for (int kk = 0; kk < SPEC_STEPS; ++kk) // (the boundary-aware steps below)
                     {
                         __syncwarp();
                         if (c.colsLeft == 0)
-                            node_event<R, true, W>(s, c, g, gl, seedS, L);
+                        {
+                            if (LEAN_EVENTS)
+                                node_event_pre<R, W>(s, c, g, evS, pre, gl, seedS);
+                            else
+                                node_event<R, true, W>(s, c, g, gl, seedS, L);
+                        }
                         else
                             --c.colsLeft;
                         uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
                         uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
-                        if (gl == 0)
-                        {
-                            rh = 0;
-                            rf = NO_F;
-                        }
+                        rh *= lmask;
+                        rf = rf * lmask + nof0;
                         const int code = live ? cpb[kk] : 5;
                         const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
                         uint32_t tg[R];
@@ -730,8 +752,16 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         }
         uint32_t* dst = tiles + (size_t)slot * TileGeom<R>::SLOT_WORDS;
         const uint8_t* cp = codes + T * CK;
+        // The walk only ever moves to smaller steps (left, up and diagonal moves all do; so does the jump into a
+        // predecessor's last column), and what it asks for is its current cell or a neighbour of it, at most two steps
+        // before the current cell (pg_core.cuh: walk): of the tile it missed it can touch the steps up to need_step + 2,
+        // no later one (tile_steps_needed; the emulator poisons the rest).  That saves 40 % of the recomputation.
+        int kend = done ? 0 : tile_steps_needed(w.need_step, T);
+        if (NT > 1)
+            for (int dd = W; dd < 32; dd <<= 1)
+                kend = max(kend, __shfl_xor_sync(FULL, kend, dd));
 #pragma unroll 2
-        for (int kk = 0; kk < CK; ++kk)
+        for (int kk = 0; kk < kend; ++kk)
         {
             if (c.colsLeft == 0)
                 node_event<R, false, W>(s, c, g, gl, const_cast<uint32_t*>(last));
@@ -2237,7 +2267,8 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     int code_bytes = (int)code_span_bytes(max_G) + 16;
     if (code_bytes > 16 * 1024 + 16 || !c->use_tma)
         code_bytes = 0;
-    const int tab_ints_cap = code_bytes ? ((c->graphs.max_tab_ints + 3) & ~3) : 0; // staged with the codes (keeps 16-byte alignment)
+    // staged with the codes (keeps 16-byte alignment), plus one entry word per node (pg_core.cuh: entry_word)
+    const int tab_ints_cap = code_bytes ? ((c->graphs.max_tab_ints + max_nodes + 3) & ~3) : 0;
     int fill_words = NCODE * R * W + tab_words + tab_ints_cap + code_bytes / 4;
     // warps per CTA: the count that keeps most warps resident on an SM (shared memory is what limits residency here:
     // per task the profile + the seed / node-maximum tables of max_nodes nodes + the staged codes).  4 warps per CTA
@@ -2534,12 +2565,14 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
 
 extern "C" {
 
+#define PG_STR_(x) #x
+#define PG_STR(x) PG_STR_(x)
 const char* pg_version(void)
 {
 #if PG_SPEC_DEAD
-    return "paragraph_b200 0.3 sm_100a CK=16 int16x2-wavefront W=16/32/8 reads<=512 spec-dead-blocks";
+    return "paragraph_b200 0.4 sm_100a CK=" PG_STR(PG_CK) " int16x2-wavefront W=16/32/8 reads<=512 spec-dead-blocks lean-node-events";
 #else
-    return "paragraph_b200 0.3 sm_100a CK=16 int16x2-wavefront W=16/32/8 reads<=512";
+    return "paragraph_b200 0.4 sm_100a CK=" PG_STR(PG_CK) " int16x2-wavefront W=16/32/8 reads<=512";
 #endif
 }
 

@@ -81,6 +81,15 @@ void emu_fill_pass(const GraphView& g, const uint8_t* bases, int L, int orient, 
         ckpt.assign((size_t)num_ckpt(g.G, W) * CKW * W, 0);
     const int nck = num_ckpt(g.G, W);
     int no_spec_before = 0;
+    // node boundaries inside boundary sub-blocks as the kernel handles them (pg_core.cuh: entry_word, seed_prefetch,
+    // node_event_pre): entry words per node, the older predecessors' part of a seed folded at the sub-block's start
+    std::vector<uint32_t> entry((size_t)g.n_nodes + 1, 0);
+    for (int m = 1; m < g.n_nodes; ++m)
+        entry[m] = entry_word(g, m);
+    SeedPre<R> pre[W];
+    for (int t = 0; t < W; ++t)
+        pre[t].node = -1;
+    const bool lean = g_spec && !WIDE;
     int sbest[2] = { 0, 0 }, pending[2] = { 0, 0 }; // EXPERIMENT (g_spec == 2): best score so far, folded in at sub-block starts
     for (int k = 0; k < nck * CK; ++k)
     {
@@ -114,6 +123,11 @@ void emu_fill_pass(const GraphView& g, const uint8_t* bases, int L, int orient, 
                 }
             }
             ++g_spec_blocks[!flat ? 3 : (!dead ? 2 : 0)];
+            for (int t = 0; t < W; ++t)
+                pre[t].node = -1;
+            if (!flat)
+                for (int t = 0; t < W; ++t)
+                    seed_prefetch<R, W>(pre[t], c[t], g, entry.data(), t, seedS.data(), SPEC_STEPS);
             if (flat && dead)
             {
                 DeadSave<R> keep[W];
@@ -176,9 +190,26 @@ void emu_fill_pass(const GraphView& g, const uint8_t* bases, int L, int orient, 
                 no_spec_before = k + SPEC_STEPS;
             }
         }
+        if (lean && precise && k % SPEC_STEPS == 0) // (the exact second pass takes the same boundary path in the kernel)
+        {
+            bool flat = true;
+            for (int t = 0; t < W; ++t)
+            {
+                flat = flat && c[t].colsLeft >= SPEC_STEPS;
+                pre[t].node = -1;
+            }
+            if (!flat)
+                for (int t = 0; t < W; ++t)
+                    seed_prefetch<R, W>(pre[t], c[t], g, entry.data(), t, seedS.data(), SPEC_STEPS);
+        }
         for (int t = 0; t < W; ++t) // events read what lane t-1 wrote at an EARLIER step only
             if (c[t].colsLeft == 0)
-                node_event<R, true, W>(s[t], c[t], g, t, seedS.data(), L);
+            {
+                if (lean)
+                    node_event_pre<R, W>(s[t], c[t], g, entry.data(), pre[t], t, seedS.data());
+                else
+                    node_event<R, true, W>(s[t], c[t], g, t, seedS.data(), L);
+            }
             else
                 --c[t].colsLeft;
         uint32_t rh[W], rf[W];
@@ -207,8 +238,12 @@ void emu_fill_pass(const GraphView& g, const uint8_t* bases, int L, int orient, 
 
 template <int R, int W>
 void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::vector<uint32_t>& ckpt,
-              std::vector<uint32_t>& last, int T, int blo, uint32_t* dst, int half)
+              std::vector<uint32_t>& last, int T, int blo, uint32_t* dst, int half, int kend)
 {
+    // the trace kernel recomputes a tile only up to the step the walk asked for (it never moves to a later one): the
+    // rest of the slot is poisoned here, so that a walk that did look there would not go unnoticed
+    for (int x = kend * TileGeom<R>::BAND_ROWS; x < TileGeom<R>::SLOT_WORDS; ++x)
+        dst[x] = 0xffffffffu;
     Lane<R> s[W];
     LaneCtl c[W];
     for (int t = 0; t < W; ++t)
@@ -216,7 +251,7 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
         ckpt_load<R, W>(s[t], ckpt.data() + (size_t)T * Sizes<R, W>::CKW * W, t);
         ctl_at_step(c[t], g, T * CK, t);
     }
-    for (int kk = 0; kk < CK; ++kk)
+    for (int kk = 0; kk < kend; ++kk)
     {
         const int k = T * CK + kk;
         for (int t = 0; t < W; ++t)
@@ -286,7 +321,8 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
         const int T = w.need_step / CK;
         int blo;
         const int slot = tb.admit(T, w.need_row, blo);
-        emu_tile<R, W>(g0, prof, ckpt, last, T, blo, tiles.data() + (size_t)slot * TileGeom<R>::SLOT_WORDS, d.half);
+        emu_tile<R, W>(g0, prof, ckpt, last, T, blo, tiles.data() + (size_t)slot * TileGeom<R>::SLOT_WORDS, d.half,
+                       tile_steps_needed(w.need_step, T));
         if (n_tiles)
             ++*n_tiles;
         if (++guard > 100000)
