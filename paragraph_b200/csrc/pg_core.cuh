@@ -44,7 +44,13 @@ constexpr int NEG = -16384; // substitution score of sentinel columns / padded r
 #ifndef PG_CK
 #define PG_CK 16
 #endif
-constexpr int CK = PG_CK;   // checkpoint interval = traceback tile size, in wavefront steps
+constexpr int CK = PG_CK;   // checkpoint interval of the fill, in wavefront steps
+#ifndef PG_TS
+#define PG_TS 16
+#endif
+constexpr int TS = PG_TS;   // traceback tile size in steps: a tile is recomputed from the checkpoint at or before its first
+                            // step (CK a multiple of TS: the steps in between are run without keeping their cells)
+static_assert(CK % TS == 0, "the checkpoint interval must be a multiple of the tile size");
 constexpr int SENT = 32;    // sentinel columns (code 5) before and after every column sequence
 constexpr int NCODE = 6;    // A C G T other sentinel
 constexpr int MAX_READ_LEN = 512;  // R = 16 rows per lane x 32 lanes
@@ -997,9 +1003,9 @@ template <int R, int W = 32> PG_HD void ckpt_load(Lane<R>& s, const uint32_t* ck
 template <int R> struct TileGeom
 {
     // rows the walk can climb within one tile (<= 1 per step on a diagonal, + insertions) + lane alignment slack
-    static constexpr int BAND_LANES = (CK + 19 + R - 1) / R + 1;
+    static constexpr int BAND_LANES = (TS + 19 + R - 1) / R + 1;
     static constexpr int BAND_ROWS = BAND_LANES * R;
-    static constexpr int SLOT_WORDS = CK * BAND_ROWS;
+    static constexpr int SLOT_WORDS = TS * BAND_ROWS;
 };
 
 // PRMT: result byte i = byte (selector nibble i) of the eight bytes {a: 0-3, b: 4-7} (selector nibbles < 8 only)
@@ -1300,12 +1306,12 @@ PG_HD int emit_cigar(const uint32_t* oplog, int n, uint32_t* out, int cap)
 // steps of tile T the walk can still look at after a miss at need_step (see the trace kernel's recompute phase)
 PG_HD int tile_steps_needed(int need_step, int T)
 {
-    const int n = need_step - T * CK + 3;
-    return n < CK ? n : CK;
+    const int n = need_step - T * TS + 3;
+    return n < TS ? n : TS;
 }
 template <int R> struct TileBuf
 {
-    uint32_t* mem;    // [2 slots][CK][BAND_ROWS] cell words
+    uint32_t* mem;    // [2 slots][TS][BAND_ROWS] cell words
     int tile0, tile1; // tile index resident in each slot, -1 = empty
     int blo0, blo1;   // first lane of each slot's row band
     int lru;          // slot to evict next
@@ -1313,7 +1319,7 @@ template <int R> struct TileBuf
     {
         if (step < 0)
             return nullptr;
-        const int T = step / CK, ln = row / R;
+        const int T = step / TS, ln = row / R;
         int sl = -1, blo = 0;
         constexpr int BAND_LANES = TileGeom<R>::BAND_LANES;
         if (tile0 == T && ln >= blo0 && ln < blo0 + BAND_LANES)
@@ -1328,7 +1334,7 @@ template <int R> struct TileBuf
         }
         if (sl < 0)
             return nullptr;
-        return mem + (size_t)(sl * CK + (step - T * CK)) * TileGeom<R>::BAND_ROWS + (row - R * blo);
+        return mem + (size_t)(sl * TS + (step - T * TS)) * TileGeom<R>::BAND_ROWS + (row - R * blo);
     }
     // slot that will receive tile T with a band ending at `row`'s lane (round-robin eviction)
     PG_HD int admit(int T, int row, int& blo)

@@ -23,6 +23,19 @@ namespace pg
 namespace host
 {
 
+struct CodeTable // per input character: gssw column code and the upper-cased character (pg_core.cuh: nt_code, to_upper)
+{
+    uint8_t code[256], upper[256];
+    CodeTable()
+    {
+        for (int ch = 0; ch < 256; ++ch)
+        {
+            upper[ch] = to_upper((uint8_t)ch);
+            code[ch] = (uint8_t)nt_code(upper[ch]);
+        }
+    }
+};
+
 struct GraphStore
 {
     std::vector<SiteDev> sites;
@@ -31,6 +44,7 @@ struct GraphStore
     int max_nodes = 0;
     int max_G = 0;
     int max_tab_ints = 0; // largest per-orientation int table (SiteDev::tab_ints)
+    std::vector<int32_t> scratch_deg, scratch_idx, scratch_fill; // add(): reused between sites
     // for the counting stage (pg_count.cuh): the edges as given (input order is the order of the edge count rows),
     // their path-family label masks (pg_set_edge_labels; 0 = unlabelled) and each site's first row
     std::vector<int32_t> in_from, in_to;
@@ -121,63 +135,86 @@ struct GraphStore
         sd.G = (int32_t)G;
         sd.n_edges = n_edges;
         const int32_t base0 = off[0];
-        // forward characters (upper-cased), concatenated in node order
-        std::vector<uint8_t> chars((size_t)G);
-        for (int64_t x = 0; x < G; ++x)
-            chars[(size_t)x] = to_upper((uint8_t)blob[base0 + x]);
+        // forward characters (upper-cased), concatenated in node order.  (Everything below is written through pointers
+        // into space reserved once per site: a 10 000-site sweep registers its graphs inside the timed pass.)
+        static const CodeTable lut;
+        const uint8_t* raw = (const uint8_t*)blob + base0;
+        const size_t tail = (size_t)SENT + CK + 4 + 16; // + slack so the span can be rounded up to 16 bytes
+        size_t pos = (bytes.size() + 15) & ~(size_t)15; // the staged span [codes - SENT, ...) must be 16-byte aligned (TMA)
+        size_t need = pos;
+        for (int o = 0; o < 2; ++o)
+            need = ((need + 15) & ~(size_t)15) + SENT + (size_t)G + tail;
+        need += 2 * (size_t)G;
+        bytes.resize(need, 0);
+        uint8_t* B = bytes.data();
         for (int o = 0; o < 2; ++o)
         {
-            while (bytes.size() % 16) // the staged span [codes - SENT, ...) must be 16-byte aligned for the bulk copy (TMA)
-                bytes.push_back(0);
-            bytes.insert(bytes.end(), SENT, (uint8_t)5);
-            sd.codes_off[o] = (int32_t)bytes.size();
-            for (int64_t x = 0; x < G; ++x)
-                bytes.push_back((uint8_t)nt_code(chars[(size_t)(o == 0 ? x : G - 1 - x)]));
-            bytes.insert(bytes.end(), SENT + CK + 4 + 16, (uint8_t)5); // + slack so the span can be rounded up to 16 bytes
+            pos = (pos + 15) & ~(size_t)15;
+            memset(B + pos, 5, SENT);
+            pos += SENT;
+            sd.codes_off[o] = (int32_t)pos;
+            if (o == 0)
+                for (int64_t x = 0; x < G; ++x)
+                    B[pos + (size_t)x] = lut.code[raw[x]];
+            else
+                for (int64_t x = 0; x < G; ++x)
+                    B[pos + (size_t)x] = lut.code[raw[G - 1 - x]];
+            pos += (size_t)G;
+            memset(B + pos, 5, tail);
+            pos += tail;
         }
-        sd.chars_off = (int32_t)bytes.size();
-        bytes.insert(bytes.end(), chars.begin(), chars.end());
-        sd.raw_off = (int32_t)bytes.size(); // as given: the exact-match stage compares characters case-sensitively
-        bytes.insert(bytes.end(), (const uint8_t*)blob + base0, (const uint8_t*)blob + base0 + G);
+        sd.chars_off = (int32_t)pos;
+        for (int64_t x = 0; x < G; ++x)
+            B[pos + (size_t)x] = lut.upper[raw[x]];
+        pos += (size_t)G;
+        sd.raw_off = (int32_t)pos; // as given: the exact-match stage compares characters case-sensitively
+        memcpy(B + pos, raw, (size_t)G);
+        const int tab_ints = 3 * n_nodes + 1 + n_edges;
+        const size_t ints0 = ints.size();
+        ints.resize(ints0 + 2 * (size_t)tab_ints, 0);
+        scratch_deg.assign((size_t)n_nodes + 1, 0);
         for (int o = 0; o < 2; ++o)
         {
-            sd.tab_off[o] = (int32_t)ints.size();
-            std::vector<int32_t> len((size_t)n_nodes), start((size_t)n_nodes);
-            for (int i = 0; i < n_nodes; ++i)
-            {
-                const int src = o == 0 ? i : n_nodes - 1 - i;
-                len[(size_t)i] = off[src + 1] - off[src];
-            }
+            sd.tab_off[o] = (int32_t)(ints0 + (size_t)o * tab_ints);
+            int32_t* start = ints.data() + sd.tab_off[o];
+            int32_t* len = start + n_nodes;
+            int32_t* ptr = len + n_nodes;
+            int32_t* idx = ptr + n_nodes + 1;
             int32_t acc = 0;
             for (int i = 0; i < n_nodes; ++i)
             {
-                start[(size_t)i] = acc;
-                acc += len[(size_t)i];
+                const int src = o == 0 ? i : n_nodes - 1 - i;
+                len[i] = off[src + 1] - off[src];
+                start[i] = acc;
+                acc += len[i];
             }
-            std::vector<std::vector<int32_t>> preds((size_t)n_nodes);
+            // predecessor lists: counting sort of the edges by target, each list ascending and without duplicates
+            // (Graph::addEdge rejects duplicates anyway)
+            std::fill(scratch_deg.begin(), scratch_deg.end(), 0);
+            for (int e = 0; e < n_edges; ++e)
+                ++scratch_deg[(size_t)(o == 0 ? et[e] : n_nodes - 1 - ef[e]) + 1];
+            for (int i = 0; i < n_nodes; ++i)
+                scratch_deg[(size_t)i + 1] += scratch_deg[(size_t)i];
+            scratch_idx.assign((size_t)n_edges, 0);
+            scratch_fill.assign(scratch_deg.begin(), scratch_deg.end() - 1);
             for (int e = 0; e < n_edges; ++e)
             {
                 const int f = o == 0 ? ef[e] : n_nodes - 1 - et[e];
                 const int t = o == 0 ? et[e] : n_nodes - 1 - ef[e];
-                preds[(size_t)t].push_back(f);
+                scratch_idx[(size_t)scratch_fill[(size_t)t]++] = f;
             }
-            ints.insert(ints.end(), start.begin(), start.end());
-            ints.insert(ints.end(), len.begin(), len.end());
-            int32_t ptr = 0;
+            int32_t out = 0;
             for (int i = 0; i < n_nodes; ++i)
             {
-                ints.push_back(ptr);
-                auto& p = preds[(size_t)i];
-                std::sort(p.begin(), p.end());
-                p.erase(std::unique(p.begin(), p.end()), p.end()); // Graph::addEdge rejects duplicates anyway
-                ptr += (int32_t)p.size();
+                ptr[i] = out;
+                int32_t* b = scratch_idx.data() + scratch_deg[(size_t)i];
+                int32_t* e = scratch_idx.data() + scratch_deg[(size_t)i + 1];
+                std::sort(b, e);
+                e = std::unique(b, e);
+                for (; b < e; ++b)
+                    idx[out++] = *b;
             }
-            ints.push_back(ptr);
-            for (int i = 0; i < n_nodes; ++i)
-                ints.insert(ints.end(), preds[(size_t)i].begin(), preds[(size_t)i].end());
-            // pad pred_idx to n_edges entries so both orientations occupy the same space
-            for (int32_t x = ptr; x < n_edges; ++x)
-                ints.push_back(0);
+            ptr[n_nodes] = out; // (pred_idx is padded with zeros to n_edges entries: both orientations occupy the same space)
         }
         sd.tab_ints = 3 * n_nodes + 1 + n_edges;
         max_tab_ints = std::max(max_tab_ints, sd.tab_ints);

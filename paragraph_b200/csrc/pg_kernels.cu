@@ -721,22 +721,23 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
         int T = 0, slot = 0, blo = 0;
         if (!done)
         {
-            T = w.need_step / CK;
+            T = w.need_step / TS;
             slot = tb.admit(T, w.need_row, blo);
         }
         __syncwarp();
         Lane<R> s;
         LaneCtl c;
+        const int ck = T * TS / CK; // the checkpoint at or before the tile's first step
         if (!done)
         {
-            ckpt_load<R, W>(s, ckpt + (size_t)T * Sizes<R, W>::CKW * W, gl);
-            ctl_at_step(c, g, T * CK, gl);
+            ckpt_load<R, W>(s, ckpt + (size_t)ck * Sizes<R, W>::CKW * W, gl);
+            ctl_at_step(c, g, ck * CK, gl);
             // the walk moves towards smaller steps: the tile it misses next is almost always T - 1.  Its checkpoint is
             // in HBM (the fill kernel wrote hundreds of MB since); start fetching it now, the load above was the stall
             // of this kernel that the other warps hide least (long scoreboard at ck_unpack)
-            if (T > 0)
+            if (T > 0 && (T - 1) * TS / CK != ck)
             {
-                const uint32_t* nx = ckpt + (size_t)(T - 1) * Sizes<R, W>::CKW * W + gl;
+                const uint32_t* nx = ckpt + (size_t)((T - 1) * TS / CK) * Sizes<R, W>::CKW * W + gl;
 #pragma unroll
                 for (int x = 0; x < Sizes<R, W>::CKW; ++x)
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + x * W));
@@ -751,7 +752,37 @@ template <int R, int W> __global__ void __launch_bounds__(TRACE_WARPS * 32) pg_t
             c.first[0] = c.first[1] = 0;
         }
         uint32_t* dst = tiles + (size_t)slot * TileGeom<R>::SLOT_WORDS;
-        const uint8_t* cp = codes + T * CK;
+        const uint8_t* cp = codes + T * TS;
+        // the steps between the checkpoint and the tile (CK > TS): the same recurrence, cells not kept
+        int pre = done ? 0 : T * TS - ck * CK;
+        if (NT > 1)
+            for (int dd = W; dd < 32; dd <<= 1)
+                pre = max(pre, __shfl_xor_sync(FULL, pre, dd));
+        if (CK > TS)
+        {
+            const int mine = done ? 0 : T * TS - ck * CK; // groups with a shorter run-up idle on sentinel columns first
+#pragma unroll 2
+            for (int kk = -pre; kk < 0; ++kk)
+            {
+                const bool on = kk >= -mine;
+                if (on)
+                {
+                    if (c.colsLeft == 0)
+                        node_event<R, false, W>(s, c, g, gl, const_cast<uint32_t*>(last));
+                    else
+                        --c.colsLeft;
+                }
+                uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
+                uint32_t rf = __shfl_up_sync(FULL, s.foutLast, 1, W);
+                if (gl == 0)
+                {
+                    rh = 0;
+                    rf = 0;
+                }
+                if (on)
+                    lane_step<R, false, W>(s, rh, rf, prof, cp[kk], gl, nullptr, nullptr, nullptr);
+            }
+        }
         // The walk only ever moves to smaller steps (left, up and diagonal moves all do; so does the jump into a
         // predecessor's last column), and what it asks for is its current cell or a neighbour of it, at most two steps
         // before the current cell (pg_core.cuh: walk): of the tile it missed it can touch the steps up to need_step + 2,
@@ -2623,6 +2654,8 @@ int pg_create(int device, pg_ctx** out)
         c->path_host_index = atoi(e) != 0;
     if (const char* e = getenv("PG_PATH_SCALAR"))
         c->path_scalar = atoi(e) != 0;
+    if (const char* e = getenv("PG_SCRATCH_GB")) // A/B: the default of pg_set_scratch_limit
+        c->scratch_limit = (uint64_t)std::max(1, atoi(e)) << 30;
     if (const char* e = getenv("PG_GEOM_W"))
     {
         const int w = atoi(e);

@@ -246,14 +246,15 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
         dst[x] = 0xffffffffu;
     Lane<R> s[W];
     LaneCtl c[W];
+    const int ck = T * TS / CK; // the checkpoint at or before the tile's first step; the steps in between are not kept
     for (int t = 0; t < W; ++t)
     {
-        ckpt_load<R, W>(s[t], ckpt.data() + (size_t)T * Sizes<R, W>::CKW * W, t);
-        ctl_at_step(c[t], g, T * CK, t);
+        ckpt_load<R, W>(s[t], ckpt.data() + (size_t)ck * Sizes<R, W>::CKW * W, t);
+        ctl_at_step(c[t], g, ck * CK, t);
     }
-    for (int kk = 0; kk < kend; ++kk)
+    for (int kk = ck * CK - T * TS; kk < kend; ++kk)
     {
-        const int k = T * CK + kk;
+        const int k = T * TS + kk;
         for (int t = 0; t < W; ++t)
             if (c[t].colsLeft == 0)
                 node_event<R, false, W>(s[t], c[t], g, t, last.data());
@@ -268,6 +269,11 @@ void emu_tile(const GraphView& g, const std::vector<uint32_t>& prof, const std::
         for (int t = 0; t < W; ++t)
         {
             uint32_t Hc[R], Ec[R], Fc[R];
+            if (kk < 0)
+            {
+                lane_step<R, false, W>(s[t], rh[t], rf[t], prof.data(), g.codes[k - t], t, nullptr, nullptr, nullptr);
+                continue;
+            }
             lane_step<R, true, W>(s[t], rh[t], rf[t], prof.data(), g.codes[k - t], t, Hc, Ec, Fc);
             tile_store<R, Sizes<R, W>::WIDE>(dst + (size_t)kk * TileGeom<R>::BAND_ROWS, t, blo, Hc, Ec, Fc, half);
         }
@@ -318,7 +324,7 @@ int emu_align_one(const SiteDev& sd, const uint8_t* bytes, const int32_t* ints, 
     int guard = 0;
     while (!walk<R, W>(w, tb, g0, chars, last.data(), bases, L, d.half, fw, oplog.data(), (int)oplog.size(), 0, 0u))
     {
-        const int T = w.need_step / CK;
+        const int T = w.need_step / TS;
         int blo;
         const int slot = tb.admit(T, w.need_row, blo);
         emu_tile<R, W>(g0, prof, ckpt, last, T, blo, tiles.data() + (size_t)slot * TileGeom<R>::SLOT_WORDS, d.half,

@@ -18,6 +18,8 @@ _lib = None
 
 
 def build():
+    if os.environ.get("PG_EMU_SO"):  # a prebuilt variant (e.g. another -DPG_CK): tools / A-B only
+        return
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in SRC):
         return
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++", "-o", SO, SRC[0]])
@@ -27,7 +29,7 @@ def lib():
     global _lib
     if _lib is None:
         build()
-        l = C.CDLL(SO)
+        l = C.CDLL(os.environ.get("PG_EMU_SO") or SO)
         l.pgemu_align_batch.restype = C.c_int
         l.pgemu_align_batch.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int32), C.c_int, C.c_char_p, C.POINTER(C.c_int32),
