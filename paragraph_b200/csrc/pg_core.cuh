@@ -42,7 +42,7 @@ constexpr int GAP_OPEN = 6; // GraphAligner.cpp:231
 constexpr int GAP_EXT = 1;  // GraphAligner.cpp:232
 constexpr int NEG = -16384; // substitution score of sentinel columns / padded rows
 #ifndef PG_CK
-#define PG_CK 16
+#define PG_CK 32 // 16 / 32 / 64 measured on the B200: 32 halves the scratch written by the fill for 16 steps of run-up in half of the tracebacks
 #endif
 constexpr int CK = PG_CK;   // checkpoint interval of the fill, in wavefront steps
 #ifndef PG_TS

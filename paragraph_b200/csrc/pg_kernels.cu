@@ -1770,7 +1770,7 @@ struct pg_ctx
     int n_chunks_timed = 0;
     uint64_t launches = 0;
     float fill_ms = 0, trace_ms = 0;
-    uint64_t scratch_limit = 24ull << 30;
+    uint64_t scratch_limit = 64ull << 30; // pg_create lowers it to 40 % of the device's memory if that is less
     bool use_tma = true; // PG_NO_TMA=1 disables the shared-memory staging of column codes (A/B only)
     int geom_w = 32; // lanes per task; PG_GEOM_W=32|16|8 overrides (tuning / A-B measurements only)
 
@@ -2654,6 +2654,11 @@ int pg_create(int device, pg_ctx** out)
         c->path_host_index = atoi(e) != 0;
     if (const char* e = getenv("PG_PATH_SCALAR"))
         c->path_scalar = atoi(e) != 0;
+    {
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0)
+            c->scratch_limit = std::min<uint64_t>(c->scratch_limit, (uint64_t)(total_b / 10 * 4));
+    }
     if (const char* e = getenv("PG_SCRATCH_GB")) // A/B: the default of pg_set_scratch_limit
         c->scratch_limit = (uint64_t)std::max(1, atoi(e)) << 30;
     if (const char* e = getenv("PG_GEOM_W"))

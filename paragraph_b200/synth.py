@@ -71,6 +71,39 @@ def bubble_graph(rng, n_nodes=None, max_len=60, p_edge=0.5, alphabet="ACGT"):
     return nodes, sorted(edges)
 
 
+def short_node_graphs(rng, n_graphs=6):
+    """Graphs that exercise every branch of the fill's node events (pg_core.cuh: entry_word / seed_prefetch / node_event_pre):
+    runs of 1-3 bp nodes (a lane crosses two boundaries within one 8-step sub-block), chain links, merges that include the
+    node just finished, merges that do not, several sources, fan-in of up to five predecessors, between longer flanks."""
+    a = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seq = lambda n: a[rng.integers(0, 4, size=int(n))].tobytes().decode()
+    out = []
+    for gi in range(n_graphs):
+        lens = [int(rng.integers(40, 160))]
+        for _ in range(int(rng.integers(6, 14))):
+            lens.append(int(rng.choice([1, 1, 2, 3, 5, 9, 30])))
+        lens.append(int(rng.integers(40, 160)))
+        n = len(lens)
+        edges = set()
+        for t in range(1, n):
+            mode = int(rng.integers(0, 5)) if t < n - 1 else 1
+            if mode == 0:    # chain link
+                edges.add((t - 1, t))
+            elif mode == 1:  # merge including the node just finished
+                edges.add((t - 1, t))
+                for f in rng.choice(t, size=min(t, int(rng.integers(1, 5))), replace=False):
+                    edges.add((int(f), t))
+            elif mode == 2 and t >= 2:  # merge of older nodes only
+                for f in rng.choice(t - 1, size=min(t - 1, int(rng.integers(1, 4))), replace=False):
+                    edges.add((int(f), t))
+            elif mode == 3 and gi % 2:  # another source
+                pass
+            else:
+                edges.add((int(rng.integers(0, t)), t))
+        out.append(([seq(l) for l in lens], sorted(edges)))
+    return out
+
+
 def site_graph(rng, kind, flank=None, sv_len=None):
     flank = int(flank if flank is not None else rng.integers(150, 501))
     sv_len = int(sv_len if sv_len is not None else rng.integers(20, 501))

@@ -177,3 +177,17 @@ def test_emulator_speculative_dead_blocks(built):
         assert dead2 > dead and alive2 < alive, (dead, alive, dead2, alive2)
     finally:
         emubind.set_spec(1)  # the default, as in the kernels
+
+
+def test_emulator_short_node_events(built):
+    """every branch of the lean node events (entry words, prefetched seeds, second boundary inside a sub-block) vs the oracle"""
+    rng = np.random.default_rng(2024)
+    for w in (32, 16):
+        emubind.set_geometry(w)
+        try:
+            for nodes, edges in synth.short_node_graphs(rng, 8):
+                reads = [r[:150] for r in synth.fuzz_reads(rng, nodes, edges, 10, max_len=150)]
+                got, _ = emubind.emu_align_batch(nodes, edges, reads)
+                assert strip_status(got) == R.OracleGraph(nodes, edges).align_batch(reads), (w, nodes, edges)
+        finally:
+            emubind.set_geometry(32)

@@ -126,7 +126,7 @@ def test_long_nodes_many_checkpoints(ctx):
     try:
         got = strip_status(ctx.align(reads))
     finally:
-        ctx.set_scratch_limit(24 << 30)
+        ctx.set_scratch_limit(64 << 30)
     assert got == R.OracleGraph(nodes, edges).align_batch(reads)
 
 
@@ -141,6 +141,23 @@ def test_many_nodes_graph(ctx, n_nodes):
     ctx.clear_graphs()
     ctx.add_graph(nodes, edges)
     assert strip_status(ctx.align(reads)) == R.OracleGraph(nodes, edges).align_batch(reads)
+
+
+def test_short_node_events(ctx):
+    """Runs of 1-3 bp nodes, chain links, merges with and without the node just finished, several sources: every branch of
+    the fill's lean node events (pg_core.cuh: entry_word / seed_prefetch / node_event_pre), many sites in one batch."""
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(2025)
+    graphs = synth.short_node_graphs(rng, 40)
+    ctx.clear_graphs()
+    reads, sites, exp = [], [], []
+    for nodes, edges in graphs:
+        sid = ctx.add_graph(nodes, edges)
+        rd = [r[:150] for r in synth.fuzz_reads(rng, nodes, edges, 24, max_len=150)]
+        reads += rd
+        sites += [sid] * len(rd)
+        exp += R.OracleGraph(nodes, edges).align_batch(rd)
+    assert strip_status(ctx.align(reads, sites=sites)) == exp
 
 
 @pytest.mark.parametrize("n_nodes", [30, 120])
