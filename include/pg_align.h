@@ -26,10 +26,10 @@ extern "C" {
 #define PG_E_CAPACITY (-5) /* caller's cigar arena too small */
 #define PG_E_STATE (-6)    /* call order (e.g. run before upload) */
 
-/* Longest read (16 rows per lane x 32 lanes).  Reads whose score reaches 251 take gssw's 16-bit mode in the
+/* Longest read (32 rows per lane x 32 lanes).  Reads whose score reaches 251 take gssw's 16-bit mode in the
  * reference (external/gssw/gssw.c:380, 527-786, 4001-4013); results stay bit-identical, including what
  * GraphAligner's uniqueness scan makes of a 16-bit matrix (src/c++/lib/grm/GraphAligner.cpp:177-186). */
-#define PG_MAX_READ_LEN 512
+#define PG_MAX_READ_LEN 1024
 
 /* pg_record::mapped_by: the stage of grm::CompositeAligner that mapped the read */
 #define PG_STAGE_GSSW_ID 0

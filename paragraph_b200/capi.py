@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libpgalign.so")
 
 PG_OK = 0
 AF_CIGAR, AF_BOTH_STRANDS, AF_REVERSE_GRAPH, AF_ALL = 1, 2, 4, 0xFFFFFFFF
-MAX_READ_LEN = 512
+MAX_READ_LEN = 1024
 OPS = "MXNIDS??"
 
 RECORD_DTYPE = np.dtype([("graph_pos", "<i4"), ("score", "<i2"), ("query_clipped", "<u2"), ("unique", "u1"),

@@ -53,7 +53,7 @@ constexpr int TS = PG_TS;   // traceback tile size in steps: a tile is recompute
 static_assert(CK % TS == 0, "the checkpoint interval must be a multiple of the tile size");
 constexpr int SENT = 32;    // sentinel columns (code 5) before and after every column sequence
 constexpr int NCODE = 6;    // A C G T other sentinel
-constexpr int MAX_READ_LEN = 512;  // R = 16 rows per lane x 32 lanes
+constexpr int MAX_READ_LEN = 1024; // R = 32 rows per lane x 32 lanes
 // gssw fills in 8-bit mode until a score reaches 251 (score + bias(4) >= 255, gssw.c:380, 467) and then redoes the
 // whole graph in 16-bit mode (gssw.c:4001-4013).  Scores are the same in both modes (this path computes in int16
 // throughout); what changes is GraphAligner's uniqueness scan (finalize_task) and what fits a byte in the scratch
@@ -1023,20 +1023,21 @@ PG_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel)
 }
 template <bool WIDE> PG_HD uint32_t pack_cell(uint32_t h, uint32_t e, uint32_t f, int half)
 {
-    if (WIDE) // 10-bit fields: scores <= MAX_READ_LEN = 512
+    if (WIDE) // H in 11 bits (scores <= MAX_READ_LEN = 1024), E and F in 10 bits each (a gap value is <= score - GAP_OPEN)
     {
         e = max2(e, 0u);
         f = max2(f, 0u);
-        return (uint32_t)half16(h, half) | ((uint32_t)half16(e, half) << 10) | ((uint32_t)half16(f, half) << 20);
+        return (uint32_t)half16(h, half) | ((uint32_t)half16(e, half) << 11) | ((uint32_t)half16(f, half) << 21);
     }
     // three operations: the chosen halves of E and F side by side as one int16 pair, one clamp for both, then
     // bytes b0 = H.byte(2*half), b1 = E.byte0, b2 = F.byte0, b3 = F.byte1 (= 0: values <= 255 after the clamp)
     const uint32_t ef = max2(bperm(e, f, half ? 0x7632u : 0x5410u), 0u);
     return bperm(h, ef, half ? 0x7642u : 0x7640u);
 }
-template <bool WIDE> PG_HD int cellH(uint32_t w) { return (int)(WIDE ? (w & 0x3ffu) : (w & 0xffu)); }
-template <bool WIDE> PG_HD int cellE(uint32_t w) { return (int)(WIDE ? ((w >> 10) & 0x3ffu) : ((w >> 8) & 0xffu)); }
-template <bool WIDE> PG_HD int cellF(uint32_t w) { return (int)(WIDE ? ((w >> 20) & 0x3ffu) : ((w >> 16) & 0xffu)); }
+template <bool WIDE> PG_HD int cellH(uint32_t w) { return (int)(WIDE ? (w & 0x7ffu) : (w & 0xffu)); }
+template <bool WIDE> PG_HD int cellE(uint32_t w) { return (int)(WIDE ? ((w >> 11) & 0x3ffu) : ((w >> 8) & 0xffu)); }
+template <bool WIDE> PG_HD int cellF(uint32_t w) { return (int)(WIDE ? ((w >> 21) & 0x3ffu) : ((w >> 16) & 0xffu)); }
+static_assert(MAX_READ_LEN <= 1024 && MAX_READ_LEN - GAP_OPEN < 1024, "WIDE tile cells: 11 + 10 + 10 bits");
 
 // one step of a traceback tile: lanes [blo, blo + BAND_LANES) store their R cells
 template <int R, bool WIDE = false>

@@ -2601,9 +2601,9 @@ extern "C" {
 const char* pg_version(void)
 {
 #if PG_SPEC_DEAD
-    return "paragraph_b200 0.4 sm_100a CK=" PG_STR(PG_CK) " int16x2-wavefront W=16/32/8 reads<=512 spec-dead-blocks lean-node-events";
+    return "paragraph_b200 0.4 sm_100a CK=" PG_STR(PG_CK) " int16x2-wavefront W=16/32/8 reads<=1024 spec-dead-blocks lean-node-events";
 #else
-    return "paragraph_b200 0.4 sm_100a CK=" PG_STR(PG_CK) " int16x2-wavefront W=16/32/8 reads<=512";
+    return "paragraph_b200 0.4 sm_100a CK=" PG_STR(PG_CK) " int16x2-wavefront W=16/32/8 reads<=1024";
 #endif
 }
 
@@ -2963,7 +2963,8 @@ int pg_batch_run(pg_ctx* c, uint32_t flags)
     // geometry: W lanes per task, R rows per lane (W * R >= read length); see DESIGN.md "geometry"
     // reads over BYTE_MAX_READ_LEN can score past a byte (gssw's 16-bit mode): WIDE geometries, W = 32 only
     if (c->max_len > BYTE_MAX_READ_LEN)
-        rc = c->max_len <= 320 ? run_chunks<10, 32>(c, flags) : run_chunks<16, 32>(c, flags);
+        rc = c->max_len <= 320 ? run_chunks<10, 32>(c, flags)
+            : (c->max_len <= 512 ? run_chunks<16, 32>(c, flags) : run_chunks<32, 32>(c, flags));
     else if (c->geom_w == 32)
         rc = c->max_len <= 160 ? run_chunks<5, 32>(c, flags) : run_chunks<8, 32>(c, flags);
     else if (c->geom_w == 8 && c->max_len <= 160)

@@ -221,7 +221,7 @@ int main()
             std::vector<std::unique_ptr<Read>> e2;
             grm::alignReads(&graph, paths, e2, filter, true, true, false, false, false, 2);
             std::vector<std::unique_ptr<Read>> e3;
-            e3.emplace_back(new Read("long", std::string(600, 'A'), std::string(600, '#')));
+            e3.emplace_back(new Read("long", std::string(1100, 'A'), std::string(1100, '#')));
             bool long_throws = false;
             try
             {

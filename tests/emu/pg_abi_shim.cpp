@@ -51,7 +51,8 @@ int shim_dp(const SiteDev& sd, const uint8_t* gb, const int32_t* gi, const uint8
     int nt = 0;
     if (L > BYTE_MAX_READ_LEN)
         return L <= 320 ? emu_align_one<10, 32>(sd, gb, gi, b, L, flags, rec, ops, &nt)
-                        : emu_align_one<16, 32>(sd, gb, gi, b, L, flags, rec, ops, &nt);
+            : (L <= 512 ? emu_align_one<16, 32>(sd, gb, gi, b, L, flags, rec, ops, &nt)
+                        : emu_align_one<32, 32>(sd, gb, gi, b, L, flags, rec, ops, &nt));
     return L <= 160 ? emu_align_one<5, 32>(sd, gb, gi, b, L, flags, rec, ops, &nt)
                     : emu_align_one<8, 32>(sd, gb, gi, b, L, flags, rec, ops, &nt);
 }

@@ -425,7 +425,8 @@ int pgemu_align_batch(int n_nodes, const char* seq_blob, const int32_t* seq_off,
         // reads that can leave gssw's 8-bit mode take a WIDE geometry (W = 32 only), like the kernels' dispatch
         if (L > BYTE_MAX_READ_LEN)
             rc = L <= 320 ? emu_align_one<10, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt)
-                          : emu_align_one<16, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt);
+                : (L <= 512 ? emu_align_one<16, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt)
+                            : emu_align_one<32, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt));
         else if (g_geom_w == 32)
             rc = L <= 160 ? emu_align_one<5, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt)
                           : emu_align_one<8, 32>(sd0, gb, gi, b, L, flags, rec, ops, &nt);

@@ -54,7 +54,7 @@ def test_emulator_fuzz_vs_oracle(built):
 
 def test_emulator_rejects_long_reads(built):
     with pytest.raises(RuntimeError):
-        emubind.emu_align_batch(["ACGT" * 200], [], ["ACGT" * 129])  # 516 > 512
+        emubind.emu_align_batch(["ACGT" * 300], [], ["ACGT" * 257])  # 1028 > 1024
 
 
 def test_emulator_long_reads_16bit_mode(built):
@@ -75,6 +75,26 @@ def test_emulator_long_reads_16bit_mode(built):
         n += len(reads)
         hi += sum(e["score"] >= 251 for e in exp)
     assert hi > 30
+
+
+def test_emulator_reads_up_to_1024(built):
+    """513..1024 bp reads: the R = 32 geometry (32 rows per lane; tile cells H 11 bits, E / F 10 bits)."""
+    R.set_fill_variant(0)
+    rng = np.random.default_rng(33)
+    top = 0
+    for it in range(10):
+        if it % 2 == 0:
+            nodes, edges = synth.del_graph(rng, 900, 300)
+            reads = synth.simulate_reads(rng, nodes, edges, 3, read_len=[513, 640, 777, 1000, 1024][it // 2], sub=0.01, indel_frac=0.3)
+        else:
+            nodes, edges = synth.bubble_graph(rng, n_nodes=int(rng.integers(2, 7)), max_len=600, alphabet=["ACGT", "ACGTN"][it % 4 == 1])
+            reads = synth.fuzz_reads(rng, nodes, edges, 4, min_len=513, max_len=1024)
+        isrev = [i & 1 for i in range(len(reads))]
+        exp = R.OracleGraph(nodes, edges).align_batch(reads, is_rev=isrev)
+        got, _ = emubind.emu_align_batch(nodes, edges, reads, is_rev=isrev)
+        assert strip_status(got) == exp
+        top = max([top] + [e["score"] for e in exp])
+    assert top > 900
 
 
 def long_read_uniqueness_cases(rng):

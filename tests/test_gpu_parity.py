@@ -73,12 +73,12 @@ def test_long_reads_up_to_8bit_limit(ctx):
 
 
 def test_reads_past_the_8bit_limit(ctx):
-    """251..512 bp reads: WIDE geometries (R = 10 / 16), scores >= 251 = gssw's 16-bit mode in the reference."""
+    """251..1024 bp reads: WIDE geometries (R = 10 / 16 / 32), scores >= 251 = gssw's 16-bit mode in the reference."""
     R.set_fill_variant(0)
     rng = np.random.default_rng(19)
-    nodes, edges = synth.del_graph(rng, 600, 300)
-    for rl in (251, 300, 320, 321, 450, 512):
-        reads = synth.simulate_reads(rng, nodes, edges, 60, read_len=rl, sub=0.02, indel_frac=0.3)
+    nodes, edges = synth.del_graph(rng, 1100, 300)
+    for rl in (251, 300, 320, 321, 450, 512, 513, 700, 1024):
+        reads = synth.simulate_reads(rng, nodes, edges, 60 if rl <= 512 else 24, read_len=rl, sub=0.02, indel_frac=0.3)
         ctx.clear_graphs()
         ctx.add_graph(nodes, edges)
         exp = R.OracleGraph(nodes, edges).align_batch(reads)
@@ -89,7 +89,7 @@ def test_reads_past_the_8bit_limit(ctx):
         alpha = ["ACGT", "ACGT", "AC", "ACGTN"][int(rng.integers(0, 4))]
         nodes, edges = synth.bubble_graph(rng, n_nodes=int(rng.integers(1, 6)), max_len=int(rng.choice([300, 500, 700])),
                                           alphabet=alpha)
-        reads = synth.fuzz_reads(rng, nodes, edges, 8, min_len=100, max_len=512)
+        reads = synth.fuzz_reads(rng, nodes, edges, 8, min_len=100, max_len=512 if _ % 4 else 1024)
         isrev = [i & 1 for i in range(len(reads))]
         ctx.clear_graphs()
         ctx.add_graph(nodes, edges)
@@ -168,10 +168,11 @@ def test_many_nodes_graph_long_reads(ctx, n_nodes):
     rng = np.random.default_rng(77 + n_nodes)
     nodes, edges = synth.bubble_graph(rng, n_nodes=n_nodes, max_len=60, p_edge=0.1 if n_nodes < 100 else 0.03)
     reads = synth.fuzz_reads(rng, nodes, edges, 60, min_len=150, max_len=320) + \
-        synth.fuzz_reads(rng, nodes, edges, 40, min_len=321, max_len=512)
+        synth.fuzz_reads(rng, nodes, edges, 40, min_len=321, max_len=512) + \
+        synth.fuzz_reads(rng, nodes, edges, 16, min_len=513, max_len=1024)
     try:
         for k in (0, 16):
-            for part in (reads[:60], reads):  # R = 10 batch, then an R = 16 batch
+            for part in (reads[:60], reads[:100], reads):  # R = 10 batch, then an R = 16 batch, then an R = 32 batch
                 ctx.clear_graphs()
                 ctx.add_graph(nodes, edges)
                 ctx.set_stages(k, True, True)
@@ -203,7 +204,7 @@ def test_errors_are_loud(ctx):
         ctx.add_graph(["ACGT", ""], [(0, 1)])  # empty node
     ctx.add_graph(["ACGT" * 100], [])
     with pytest.raises(capi.PgError):
-        ctx.align(["ACGT" * 129])  # 516 bp > PG_MAX_READ_LEN
+        ctx.align(["ACGT" * 257])  # 1028 bp > PG_MAX_READ_LEN
     with pytest.raises(capi.PgError):
         ctx.align(["ACGT"], sites=[5])  # unknown site
 
