@@ -28,11 +28,20 @@
 #define PG_HD_COLD __host__ __device__ __forceinline__
 #define PG_UNROLL _Pragma("unroll")
 #define PG_NOUNROLL _Pragma("unroll 1")
+#ifndef PG_OUTLINE_GENERAL
+#define PG_OUTLINE_GENERAL 0 // 1: seed_general as a real call -- measured: 135 registers, a stack frame, fill + 14 %
+#endif
+#if PG_OUTLINE_GENERAL
+#define PG_COLD_CALL __host__ __device__ __noinline__
+#else
+#define PG_COLD_CALL __host__ __device__ __forceinline__
+#endif
 #else
 #define PG_HD inline
 #define PG_HD_COLD inline
 #define PG_UNROLL
 #define PG_NOUNROLL
+#define PG_COLD_CALL inline
 #endif
 
 namespace pg
@@ -357,6 +366,14 @@ PG_UNROLL
     for (int r = 0; r < R; ++r)
         m = max2(m, s.E[r]);
     return max2(m, 0u) != 0u; // some half > 0
+}
+template <int R> PG_HD bool e_alive(const Lane<R>& s) // the E half of gaps_alive
+{
+    uint32_t m = 0u;
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+        m = max2(m, s.E[r]);
+    return m != 0u;
 }
 // one step of one lane under that premise; returns the maximum of t over the lane's rows (NOT offset by MBIAS).
 // zero = 0, on the device in a register the compiler cannot see through (a literal 0 as the third DPX operand makes
@@ -810,17 +827,31 @@ template <int R> struct SeedPre
 {
     uint32_t H[R], E[R], hup; // element-wise maximum over the older predecessors' last columns (>= 0)
     int node;                 // the node they are the seed part of; -1: nothing prefetched
+    bool twice;               // the lane crosses a second boundary within the horizon (nodes shorter than it)
 };
+// does the prefetched seed part bring a live gap (an E > 0) into the node?
+template <int R> PG_HD bool seed_live(const SeedPre<R>& p)
+{
+    if (p.node < 0)
+        return false;
+    uint32_t m = 0u;
+PG_UNROLL
+    for (int r = 0; r < R; ++r)
+        m = max2(m, p.E[r]);
+    return m != 0u; // (all E here are >= 0)
+}
 template <int R, int W>
 PG_HD void seed_prefetch(SeedPre<R>& p, const LaneCtl& c, const GraphView& g, const uint32_t* entry, int lane,
                          const uint32_t* tab, int horizon)
 {
     constexpr int RW = Sizes<R, W>::ROWW;
     p.node = -1;
+    p.twice = false;
     const int m = c.node + 1;
     if (c.colsLeft >= horizon || m >= g.n_nodes)
         return;
     const uint32_t w = entry[m];
+    p.twice = c.colsLeft + (int)(w & EV_LEN) < horizon;
     if (!(w & EV_MERGE))
         return;
     p.node = m;
@@ -837,6 +868,43 @@ PG_NOUNROLL
         if (lane > 0)
             p.hup = max2(p.hup, seed_bottom_h<R, W>(src - RW));
     }
+}
+// The general statement of a merge (what node_event does): every predecessor of node n + 1 from the table, the registers
+// standing for the node just finished.  Rare here (see above).
+template <int R, int W>
+PG_COLD_CALL void seed_general(Lane<R>& s, const GraphView& g, int n, int lane, const uint32_t* tab)
+{
+    constexpr int RW = Sizes<R, W>::ROWW;
+    uint32_t H[R], E[R], hup = 0;
+    for (int r = 0; r < R; ++r)
+        H[r] = E[r] = 0;
+    const int p0 = g.pred_ptr[n + 1], p1 = g.pred_ptr[n + 2];
+PG_NOUNROLL
+    for (int e = p0; e < p1; ++e)
+    {
+        const int p = g.pred_idx[e];
+        if (p == n)
+        {
+PG_UNROLL
+            for (int r = 0; r < R; ++r)
+            {
+                H[r] = max2(H[r], s.Hp[r]);
+                E[r] = max2(E[r], s.E[r]);
+            }
+            hup = max2(hup, s.hupPrev);
+            continue;
+        }
+        const uint32_t* src = node_row<R, W>(tab, p, lane);
+        seed_max<R, W>(src, H, E);
+        if (lane > 0)
+            hup = max2(hup, seed_bottom_h<R, W>(src - RW));
+    }
+    for (int r = 0; r < R; ++r)
+    {
+        s.Hp[r] = H[r];
+        s.E[r] = E[r];
+    }
+    s.hupPrev = hup;
 }
 // node_event<R, true, W> of a non-WIDE geometry with the entry words and (where it applies) the prefetched seed part
 template <int R, int W>
@@ -899,38 +967,7 @@ PG_UNROLL
                 }
             }
             else // second boundary of this lane within one sub-block: the general statement
-            {
-                uint32_t H[R], E[R], hup = 0;
-                for (int r = 0; r < R; ++r)
-                    H[r] = E[r] = 0;
-                const int p0 = g.pred_ptr[n + 1], p1 = g.pred_ptr[n + 2];
-PG_NOUNROLL
-                for (int e = p0; e < p1; ++e)
-                {
-                    const int p = g.pred_idx[e];
-                    if (p == n)
-                    {
-PG_UNROLL
-                        for (int r = 0; r < R; ++r)
-                        {
-                            H[r] = max2(H[r], s.Hp[r]);
-                            E[r] = max2(E[r], s.E[r]);
-                        }
-                        hup = max2(hup, s.hupPrev);
-                        continue;
-                    }
-                    const uint32_t* src = node_row<R, W>(tab, p, lane);
-                    seed_max<R, W>(src, H, E);
-                    if (lane > 0)
-                        hup = max2(hup, seed_bottom_h<R, W>(src - RW));
-                }
-                for (int r = 0; r < R; ++r)
-                {
-                    s.Hp[r] = H[r];
-                    s.E[r] = E[r];
-                }
-                s.hupPrev = hup;
-            }
+                seed_general<R, W>(s, g, n, lane, tab);
         }
     }
     else

@@ -58,6 +58,13 @@ namespace
                         // barriers it can see declared (in dynamic shared memory it reports "Missing init" on every wait
                         // and aborts the kernel; profiles/r02e_synccheck_variants.txt)
 #endif
+#ifndef PG_DEAD_BOUNDARY
+#define PG_DEAD_BOUNDARY 0 // 1: node-boundary sub-blocks may run with the collapsed recurrence too (needs PG_LEAN_EVENTS).  Exact
+                           // (GPU suite, fuzz) and measured slower on every shape, twice: off
+#endif
+#ifndef PG_DEADB_UNROLL
+#define PG_DEADB_UNROLL 2
+#endif
 #ifndef PG_LEAN_EVENTS
 #define PG_LEAN_EVENTS 1 // entry words + prefetched seeds at node boundaries (pg_core.cuh: node_event_pre); 0 = A/B
 #endif
@@ -65,6 +72,7 @@ namespace
 #define PG_FAST_BLOCKS 1
 #endif
 constexpr int FILL_UNROLL = PG_FILL_UNROLL;
+constexpr int DEADB_UNROLL = PG_DEADB_UNROLL; // unroll of the collapsed steps of a boundary sub-block
 constexpr int FAST_UNROLL = PG_FAST_UNROLL;   // unroll of the boundary-free block of the fill kernel
 constexpr bool FAST_BLOCKS = PG_FAST_BLOCKS != 0;
 constexpr bool FILL_LAZY_F = PG_LAZY_F != 0;
@@ -424,6 +432,59 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs
                     {
                         __syncwarp();
                         seed_prefetch<R, W>(pre, c, g, evS, gl, seedS, SPEC_STEPS);
+                    }
+                    // A boundary sub-block may run with the collapsed recurrence as well (PG_DEAD_BOUNDARY): no lane holds a
+                    // live gap and no prefetched seed brings one.  The lane's events run between the collapsed steps; each
+                    // folds the maximum of the steps since the last one into the node it closes, and an event that left
+                    // the lane with a live E (a second crossing inside the sub-block merges through the general path,
+                    // whose seeds were not looked at beforehand) fails the attempt like a t > gap_open does.  What a
+                    // failed attempt has to put back: Hp, the two shuffle values and the node bookkeeping -- the E of a
+                    // valid attempt stay <= 0 whatever an event did to them, a failed attempt's E are set to 0 (they were
+                    // <= 0 when it began), the rows it stored are stored again by the full steps.
+                    if (PG_DEAD_BOUNDARY && LEAN_EVENTS && !PG_SPEC_PRUNE && !precise
+                        && !__any_sync(FULL, gaps_alive(s) || seed_live(pre)))
+                    {
+                        bool brk = false;
+                        DeadSave<R> keep;
+                        dead_save(s, keep);
+                        const int keepNode = c.node, keepLeft = c.colsLeft, keepF0 = c.first[0], keepF1 = c.first[1];
+                        const uint32_t keepM = c.Mnode;
+                        uint32_t Mt = zero, Mall = zero;
+#pragma unroll DEADB_UNROLL
+                        for (int kk = 0; kk < SPEC_STEPS; ++kk)
+                        {
+                            __syncwarp();
+                            if (c.colsLeft == 0)
+                            {
+                                c.Mnode = max2(c.Mnode, add2(Mt, pk(-MBIAS, -MBIAS)));
+                                Mall = max2(Mall, Mt);
+                                Mt = zero;
+                                node_event_pre<R, W>(s, c, g, evS, pre, gl, seedS);
+                                brk = brk || e_alive(s);
+                            }
+                            else
+                                --c.colsLeft;
+                            uint32_t rh = __shfl_up_sync(FULL, s.hbotLast, 1, W);
+                            rh *= lmask;
+                            const int code = live ? cpb[kk] : 5;
+                            const ProfSmem<W> pf = { pf0.a + (uint32_t)code * (uint32_t)(R * W * 4) };
+                            Mt = lane_step_dead<R>(s, rh, pf, zero, Mt);
+                        }
+                        Mall = max2(Mall, Mt);
+                        if (!__any_sync(FULL, brk || dead_block_broken(Mall)))
+                        {
+                            c.Mnode = max2(c.Mnode, add2(Mt, pk(-MBIAS, -MBIAS)));
+                            continue;
+                        }
+                        dead_restore(s, keep);
+#pragma unroll
+                        for (int r = 0; r < R; ++r) // (they were <= 0 when the attempt began: 0 is as good as what they were)
+                            s.E[r] = zero;
+                        c.node = keepNode;
+                        c.colsLeft = keepLeft;
+                        c.first[0] = keepF0;
+                        c.first[1] = keepF1;
+                        c.Mnode = keepM;
                     }
 #pragma unroll FILL_UNROLL
                     for (int kk = 0; kk < SPEC_STEPS; ++kk) // (the boundary-aware steps below)

@@ -22,6 +22,10 @@ static long g_rev_rounds = 0, g_rev_reads = 0; // reversed-graph halves rev_plan
 static int g_spec = 1;
 static long g_spec_pruned = 0;
 extern "C" long pgemu_spec_pruned() { return g_spec_pruned; }
+static int g_dead_boundary = 0;                  // boundary sub-blocks may run dead as well (pg_fill_kernel: PG_DEAD_BOUNDARY builds)
+static long g_dead_boundary_blocks[2] = { 0, 0 }; // run dead, redone
+extern "C" void pgemu_set_dead_boundary(int on) { g_dead_boundary = on; }
+extern "C" void pgemu_dead_boundary_stats(long* out) { out[0] = g_dead_boundary_blocks[0]; out[1] = g_dead_boundary_blocks[1]; }
 static long g_spec_blocks[4] = { 0, 0, 0, 0 }; // blocks of SPEC_STEPS steps: run dead, redone, gaps alive, node boundary inside
 extern "C" void pgemu_set_spec(int on) { g_spec = on; }
 extern "C" void pgemu_spec_stats(long* o)
@@ -124,10 +128,76 @@ void emu_fill_pass(const GraphView& g, const uint8_t* bases, int L, int orient, 
             }
             ++g_spec_blocks[!flat ? 3 : (!dead ? 2 : 0)];
             for (int t = 0; t < W; ++t)
+            {
                 pre[t].node = -1;
+                pre[t].twice = false;
+            }
             if (!flat)
                 for (int t = 0; t < W; ++t)
                     seed_prefetch<R, W>(pre[t], c[t], g, entry.data(), t, seedS.data(), SPEC_STEPS);
+            // a boundary sub-block with the collapsed recurrence (pg_fill_kernel, PG_DEAD_BOUNDARY): no live gap in any lane,
+            // none brought by a merged seed, no lane crossing twice; the events run between the collapsed steps
+            if (!flat && g_spec == 1 && g_dead_boundary)
+            {
+                bool bad = false;
+                for (int t = 0; t < W; ++t)
+                    bad = bad || gaps_alive(s[t]) || seed_live(pre[t]);
+                if (!bad)
+                {
+                    DeadSave<R> keep[W];
+                    LaneCtl keepc[W];
+                    uint32_t Mt[W], Mall = 0u;
+                    bool brk = false;
+                    for (int t = 0; t < W; ++t)
+                    {
+                        dead_save(s[t], keep[t]);
+                        keepc[t] = c[t];
+                        Mt[t] = 0u;
+                    }
+                    for (int kk = 0; kk < SPEC_STEPS; ++kk)
+                    {
+                        for (int t = 0; t < W; ++t)
+                            if (c[t].colsLeft == 0)
+                            {
+                                c[t].Mnode = max2(c[t].Mnode, add2(Mt[t], pk(-MBIAS, -MBIAS)));
+                                Mall = max2(Mall, Mt[t]);
+                                Mt[t] = 0u;
+                                node_event_pre<R, W>(s[t], c[t], g, entry.data(), pre[t], t, seedS.data());
+                                brk = brk || e_alive(s[t]);
+                            }
+                            else
+                                --c[t].colsLeft;
+                        uint32_t rh[W];
+                        for (int t = 0; t < W; ++t)
+                            rh[t] = t ? s[t - 1].hbotLast : 0;
+                        for (int t = 0; t < W; ++t)
+                        {
+                            const ProfPtr<W> pf = { prof.data() + (g.codes[k + kk - t] * R) * W + t };
+                            Mt[t] = lane_step_dead<R>(s[t], rh[t], pf, 0u, Mt[t]);
+                            pending[0] = std::max(pending[0], lo16(Mt[t]));
+                            pending[1] = std::max(pending[1], hi16(Mt[t]));
+                        }
+                    }
+                    for (int t = 0; t < W; ++t)
+                        Mall = max2(Mall, Mt[t]);
+                    if (!brk && !dead_block_broken(Mall))
+                    {
+                        for (int t = 0; t < W; ++t)
+                            c[t].Mnode = max2(c[t].Mnode, add2(Mt[t], pk(-MBIAS, -MBIAS)));
+                        ++g_dead_boundary_blocks[0];
+                        k += SPEC_STEPS - 1;
+                        continue;
+                    }
+                    ++g_dead_boundary_blocks[1];
+                    for (int t = 0; t < W; ++t)
+                    {
+                        dead_restore(s[t], keep[t]);
+                        for (int r = 0; r < R; ++r)
+                            s[t].E[r] = 0u;
+                        c[t] = keepc[t];
+                    }
+                }
+            }
             if (flat && dead)
             {
                 DeadSave<R> keep[W];

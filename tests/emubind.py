@@ -45,6 +45,18 @@ def set_spec(on):
     lib().pgemu_set_spec(int(on))  # 2 = EXPERIMENT: plus upper-bound pruning of gaps that cannot reach the best score so far
 
 
+def set_dead_boundary(on):
+    """node-boundary sub-blocks may run with the collapsed recurrence as well (the kernels' PG_DEAD_BOUNDARY)"""
+    lib().pgemu_set_dead_boundary(int(on))
+
+
+def dead_boundary_stats():
+    """boundary sub-blocks so far: [run dead, attempted and redone]"""
+    o = (C.c_long * 2)()
+    lib().pgemu_dead_boundary_stats(o)
+    return list(o)
+
+
 def spec_stats():
     """blocks of SPEC_STEPS steps so far: [run dead, redone, gaps alive at the start, node boundary inside]"""
     o = (C.c_long * 4)()

@@ -211,3 +211,29 @@ def test_emulator_short_node_events(built):
                 assert strip_status(got) == R.OracleGraph(nodes, edges).align_batch(reads), (w, nodes, edges)
         finally:
             emubind.set_geometry(32)
+
+
+def test_emulator_dead_boundary_blocks(built):
+    """Node-boundary sub-blocks with the collapsed recurrence (the kernels' PG_DEAD_BOUNDARY): events between collapsed
+    steps, attempts that fail on a t > gap_open or on a live E merged in by an event; with and without, against the oracle."""
+    rng = np.random.default_rng(4242)
+    cases = [(n, e, [r[:150] for r in synth.fuzz_reads(rng, n, e, 8, max_len=150)]) for n, e in synth.short_node_graphs(rng, 6)]
+    nodes, edges, reads = synth.config2(seed=5, n_reads=16)
+    cases.append((nodes, edges, reads))
+    for s in synth.sites(77, 4, kinds=("DEL", "INS", "DUP", "INV"), max_reads=8):
+        cases.append((s[1], s[2], s[3]))
+    exp = [R.OracleGraph(n, e).align_batch(r) for n, e, r in cases]
+    try:
+        for on in (1, 0):
+            emubind.set_dead_boundary(on)
+            before = emubind.dead_boundary_stats()
+            for (n, e, r), x in zip(cases, exp):
+                got, _ = emubind.emu_align_batch(n, e, r)
+                assert strip_status(got) == x, (on, n, e)
+            after = emubind.dead_boundary_stats()
+            if on:
+                assert after[0] - before[0] > 100 and after[1] - before[1] > 5  # both outcomes were exercised
+            else:
+                assert after == before
+    finally:
+        emubind.set_dead_boundary(0)  # the default, as in the kernels

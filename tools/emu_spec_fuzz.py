@@ -42,5 +42,7 @@ while time.time() - t0 < float(sys.argv[2]):
         bad += 1
         print("MISMATCH iteration", it, "kind", kind, "w", w, "flags", flags, flush=True)
     n += len(reads)
+db = emubind.dead_boundary_stats()
+print("boundary sub-blocks run dead %d, attempted and redone %d" % tuple(db), flush=True)
 st = emubind.spec_stats(); tot = sum(st)
 print("SPEC FUZZ seed %s: %d reads in %d batches, %d mismatching batches; blocks dead %.1f%% redone %.1f%% alive %.1f%% boundary %.1f%%" % ((sys.argv[1], n, it, bad) + tuple(100.0 * x / tot for x in st)), flush=True)
