@@ -372,6 +372,7 @@ def sweep_leg(capi, torch, dist, multigpu, rank, world, device, reps=3):
     pb.array[:], po.array[:] = sub["blob"], sub["off"]
     ctx = capi.Context(device)
     counts = np.diff(sub["read_ptr"])
+    cap = max(len(p) for p in shards)  # sites of the largest shard: the gathered tensors have one shape
     # the graphs in the C-ABI's input format (flat arrays, pg_add_graphs); flattening the Python lists of strings is the
     # harness's own cost (23 ms for 10 000 sites) and is reported in rank0_phases, not timed -- registering them is
     packed = capi.Context.pack_graphs(sub["graphs"])
@@ -383,11 +384,13 @@ def sweep_leg(capi, torch, dist, multigpu, rank, world, device, reps=3):
         uniq = np.add.reduceat(rec["unique"].astype(np.int64), sub["read_ptr"][:-1]) if len(rec) else np.zeros(0, np.int64)
         score = np.add.reduceat(rec["score"].astype(np.int64), sub["read_ptr"][:-1]) if len(rec) else np.zeros(0, np.int64)
         local = dict(sites=np.asarray(mine, dtype=np.int32), unique=uniq, score_sum=score, reads=counts, n_ops=len(ops))
-        if world > 1:
-            bucket = [None] * world if rank == 0 else None
-            dist.gather_object(local, bucket, dst=0)
-            return bucket
-        return [local]
+        # per-site summaries to rank 0 as ONE fixed-size tensor gather (multigpu.gather_site_summaries)
+        parts = multigpu.gather_site_summaries(local["sites"], [uniq, score, counts, np.full(len(mine), len(ops))], cap,
+                                               dist if world > 1 else None, device="cuda")
+        if parts is None:
+            return None
+        return [dict(sites=s_, unique=c_[0], score_sum=c_[1], reads=c_[2], n_ops=int(c_[3][0]) if len(s_) else 0)
+                for s_, c_ in parts]
 
     one_pass()
     times, phases = [], None

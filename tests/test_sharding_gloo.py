@@ -28,9 +28,22 @@ for i in mine:
     res, _ = emubind.emu_align_batch(nodes, edges, reads)
     local[i] = res
 merged = multigpu.gather_site_results(local, dist, dst=0)
+# the per-site integer summaries of bench.py's sweep leg: one fixed-size tensor gather
+import numpy as np
+shards = multigpu.partition_sites(costs, world)
+cap = max(len(p) for p in shards)
+uniq = [sum(int(x["unique"]) for x in local[i]) for i in mine]
+score = [sum(int(x["score"]) for x in local[i]) for i in mine]
+parts = multigpu.gather_site_summaries(np.asarray(mine, dtype=np.int32), [uniq, score], cap, dist, device="cpu", dst=0)
 dist.barrier()
 if rank == 0:
-    json.dump({str(k): v for k, v in merged.items()}, open(sys.argv[2], "w"))
+    summ = {}
+    for ids, cols in parts:
+        for j, i in enumerate(ids):
+            summ[str(int(i))] = [int(cols[0][j]), int(cols[1][j])]
+    json.dump({"results": {str(k): v for k, v in merged.items()}, "summaries": summ}, open(sys.argv[2], "w"))
+else:
+    assert parts is None
 dist.destroy_process_group()
 '''
 
@@ -57,9 +70,18 @@ def test_two_rank_gloo_gather_matches_single_process(built, tmp_path):
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                     "--master-addr", "127.0.0.1", "--master-port", "29531", str(script), ROOT, str(out)],
                    check=True, env=env, timeout=600)
-    merged = json.load(open(out))
+    doc = json.load(open(out))
+    merged, summ = doc["results"], doc["summaries"]
     sites = synth.sites(seed=5, n_sites=6, max_reads=6)
-    assert sorted(map(int, merged)) == list(range(6))
+    assert sorted(map(int, merged)) == list(range(6)) and sorted(map(int, summ)) == list(range(6))
     for i, (_, nodes, edges, reads) in enumerate(sites):
         exp, _ = emubind.emu_align_batch(nodes, edges, reads)
         assert merged[str(i)] == exp
+        # the tensor gather of the per-site summaries (multigpu.gather_site_summaries) agrees with the per-read results
+        assert summ[str(i)] == [sum(int(x["unique"]) for x in exp), sum(int(x["score"]) for x in exp)]
+
+
+def test_site_summaries_single_process():
+    parts = multigpu.gather_site_summaries(np.array([4, 7, 9], dtype=np.int32), [[1, 2, 3], [10, 20, 30]], cap=5)
+    assert len(parts) == 1 and parts[0][0].tolist() == [4, 7, 9]
+    assert [c.tolist() for c in parts[0][1]] == [[1, 2, 3], [10, 20, 30]]
