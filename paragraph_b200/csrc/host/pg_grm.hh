@@ -664,10 +664,28 @@ public:
             registerGraph(*engine2_);
             engine2_fresh_ = true;
         }
-        const size_t parts = std::max<size_t>(2, std::min<size_t>(pipeline_max_parts_, n / std::max<size_t>(pipeline_min_reads_ / 2, 1)));
+        size_t parts = std::max<size_t>(2, std::min<size_t>(pipeline_max_parts_, n / std::max<size_t>(pipeline_min_reads_ / 2, 1)));
         // (two parts: the first one may be the larger -- what follows the last download, the write-back of the last part,
-        // is not hidden behind any kernel)
-        auto bound = [&](size_t k) { return parts == 2 && k == 1 ? n * pipeline_first_pct_ / 100 : n * k / parts; };
+        // is not hidden behind any kernel.  PGB_PIPELINE_SPLIT = "15,70,15": explicit part sizes in per cent -- a small
+        // first part gets the device going early, a small last one leaves little write-back uncovered)
+        std::vector<size_t> cut;
+        if (!pipeline_split_.empty())
+        {
+            size_t acc = 0;
+            cut.push_back(0);
+            for (size_t pct : pipeline_split_)
+            {
+                acc += pct;
+                cut.push_back(std::min(n, n * acc / 100));
+            }
+            cut.back() = n;
+            parts = cut.size() - 1;
+        }
+        auto bound = [&](size_t k) {
+            if (!cut.empty())
+                return cut[std::min(k, cut.size() - 1)];
+            return parts == 2 && k == 1 ? n * pipeline_first_pct_ / 100 : n * k / parts;
+        };
         Engine* eng[2] = { engine_.get(), engine2_.get() };
         size_t cap[2] = { 0, 0 };
         cap[0] = submit(*eng[0], bound(0), bound(1));
@@ -874,6 +892,28 @@ private:
     size_t pipeline_min_reads_ = envKnob("PGB_PIPELINE_MIN_READS", 4096);
     size_t pipeline_max_parts_ = std::max<size_t>(2, envKnob("PGB_PIPELINE_PARTS", 2));
     size_t pipeline_first_pct_ = std::min<size_t>(90, std::max<size_t>(10, envKnob("PGB_PIPELINE_FIRST_PCT", 50)));
+    static std::vector<size_t> envSplit(const char* name)
+    {
+        std::vector<size_t> v;
+        const char* e = std::getenv(name);
+        if (!e || !*e)
+            return v;
+        size_t sum = 0;
+        for (const char* p = e; *p;)
+        {
+            char* end = nullptr;
+            const unsigned long x = std::strtoul(p, &end, 10);
+            if (end == p)
+                break;
+            v.push_back((size_t)x);
+            sum += x;
+            p = *end ? end + 1 : end;
+        }
+        if (v.size() < 2 || sum != 100)
+            v.clear();
+        return v;
+    }
+    std::vector<size_t> pipeline_split_ = envSplit("PGB_PIPELINE_SPLIT");
     std::string blob_;
     std::vector<int32_t> off_{ 0 }, ef_, et_, path_ptr_, path_nodes_;
     int path_k_ = 0, kmer_k_ = 0;
