@@ -1502,6 +1502,7 @@ PG_HD int diag_run(Walker& w, const TileBuf<R>& tb, const GraphView& g, const ui
         if (idx < oplog_cap)
             oplog[idx] = cigar_word(w.n, op, nxt - lane);
     }
+    __syncwarp(gmask);
     nent = __popc(starts);
 #else
     (void)lane;
@@ -1697,6 +1698,7 @@ PG_HD bool cert_stretch(Walker& w, const GraphView& g, const uint8_t* chars, con
                 if (idx < oplog_cap)
                     oplog[idx] = cigar_word(n, op, nxt - lane);
             }
+            __syncwarp(gmask); // these slots are written again (same words, or by a later push_op when nothing was certified)
             nops += __popc(starts);
             vb = __shfl_sync(gmask, v1, W - 1, W);
         }

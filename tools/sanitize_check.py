@@ -43,3 +43,17 @@ ctx.align(synth.simulate_reads(rng, nodes, edges, 64, read_len=150, sub=0.005, i
 ctx.set_stages(0, True, False)
 ctx.set_kmer_stage(0)
 print("sanitize extras ok")
+# round 2, second session: every branch of the lean node events (runs of 1-3 bp nodes, merges with and without the node just
+# finished, several sources), many sites in one batch; and the R = 32 geometry (reads of 513 .. 1024 bp)
+ctx.clear_graphs()
+reads, sites = [], []
+for nodes, edges in synth.short_node_graphs(rng, 10):
+    sid = ctx.add_graph(nodes, edges)
+    rd = [r[:150] for r in synth.fuzz_reads(rng, nodes, edges, 8, max_len=150)]
+    reads += rd
+    sites += [sid] * len(rd)
+ctx.align(reads, sites=sites)
+nodes, edges = synth.del_graph(rng, 700, 200)
+ctx.clear_graphs(); ctx.add_graph(nodes, edges)
+ctx.align(synth.simulate_reads(rng, nodes, edges, 6, read_len=700, sub=0.01) + synth.simulate_reads(rng, nodes, edges, 4, read_len=1024, sub=0.01))
+print("sanitize lean events + 1024 bp ok")
