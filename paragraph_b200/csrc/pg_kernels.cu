@@ -1864,6 +1864,7 @@ struct pg_ctx
 
     // pairing of the reversed-graph fills (rev_plan): on by default for the byte-packed geometries, PG_PAIR_REV=0 = off
     bool pair_rev = true;
+    int stagger = 0; // PG_STAGGER: size of a batch's first chunk in per cent of the others (0 = all equal)
     int persist = 0; // PG_PERSIST: 1 = the paired reversed-graph launches, 2 = every fill launch runs as one wave of
                      // persistent CTAs striding over the task list
     int n_sms = 148;
@@ -2440,7 +2441,21 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     PG_CUDA(c, cudaFuncSetAttribute(pg_trace_kernel<R, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trace_smem));
 
     laps.lap("buffers + function attributes");
-    const size_t n_chunks = ((size_t)c->n_reads + chunk - 1) / chunk;
+    // chunk boundaries.  PG_STAGGER: a first chunk of half the size puts the two streams' sequences out of phase, so that the
+    // (latency-bound) traceback of one chunk runs beside the (ALU-bound) fill of the next instead of beside the other traceback
+    std::vector<size_t> bounds{ 0 };
+    {
+        size_t first = chunk;
+        if (overlap && c->stagger && chunk >= 256)
+            first = (chunk * (size_t)c->stagger / 100 + 63) & ~(size_t)63;
+        for (size_t r = std::min(first, (size_t)c->n_reads); ; r = std::min(r + chunk, (size_t)c->n_reads))
+        {
+            bounds.push_back(r);
+            if (r >= (size_t)c->n_reads)
+                break;
+        }
+    }
+    const size_t n_chunks = bounds.size() - 1;
     while (c->evpool.size() < 4 * n_chunks)
     {
         cudaEvent_t e;
@@ -2511,13 +2526,14 @@ template <int R, int W> int run_chunks(pg_ctx* c, unsigned flags)
     }
     laps.lap("events + occupancy");
     size_t ci = 0;
-    for (size_t r0 = 0; r0 < (size_t)c->n_reads; r0 += chunk, ++ci)
+    for (; ci < n_chunks; ++ci)
     {
+        const size_t r0 = bounds[ci];
         const size_t slot = overlap ? (ci & 1) : 0;
         cudaStream_t cs = (overlap && (ci & 1)) ? c->aux_stream : c->stream; // chunk ci-2 used the same slot on the same stream
         nvtxRangePushA(ci & 1 ? "pg chunk (aux stream): fill + plan/pair + traceback" : "pg chunk (main stream): fill + plan/pair + traceback");
         PG_CUDA(c, cudaEventRecord(c->evpool[4 * ci], cs));
-        const int nr = (int)std::min(chunk, (size_t)c->n_reads - r0);
+        const int nr = (int)(bounds[ci + 1] - r0);
         FillArgs fa;
         fa.sites = c->d_sites.p;
         fa.gbytes = c->d_gbytes.p;
@@ -2695,8 +2711,19 @@ int pg_create(int device, pg_ctx** out)
         return PG_E_CUDA;
     }
     c->stream = c->own_stream;
-    if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess)
-        c->aux_stream = nullptr;
+    {
+        // PG_PRIO=1: the auxiliary stream (odd chunks) at the lowest priority, 2: at the highest (A/B)
+        int least = 0, greatest = 0;
+        const char* e = getenv("PG_PRIO");
+        const int prio = e ? atoi(e) : 0;
+        cudaError_t rc;
+        if (prio && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess)
+            rc = cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, prio == 1 ? least : greatest);
+        else
+            rc = cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking);
+        if (rc != cudaSuccess)
+            c->aux_stream = nullptr;
+    }
     for (auto& st : c->side_stream)
         if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess)
             st = nullptr;
@@ -2704,6 +2731,8 @@ int pg_create(int device, pg_ctx** out)
         c->late_round = atoi(e);
     if (const char* e = getenv("PG_SPLIT"))
         c->split = std::max(1, atoi(e));
+    if (const char* e = getenv("PG_STAGGER"))
+        c->stagger = std::max(0, std::min(100, atoi(e)));
     if (const char* e = getenv("PG_NO_TMA"))
         c->use_tma = atoi(e) == 0;
     if (const char* e = getenv("PG_PAIR_REV"))
