@@ -268,7 +268,11 @@ template <int R, int W> __device__ __forceinline__ void finalize_task_group(cons
 // through L1 from global memory.  A template parameter so that the hot loop's loads have a static address space.
 // TABG: the seed / node-maximum tables live in HBM (graphs with so many nodes that they do not fit shared memory).
 template <int R, int W, bool STAGED, bool TABG>
+#if defined(PG_FILL_MINB) // A/B: promise the compiler this many CTAs per SM for the short-read instantiations (register cap)
+__global__ void __launch_bounds__(FILL_WARPS * 32, (R <= 8 && W == 32) ? PG_FILL_MINB : 1) pg_fill_kernel(const FillArgs a)
+#else
 __global__ void __launch_bounds__(FILL_WARPS * 32) pg_fill_kernel(const FillArgs a)
+#endif
 {
     extern __shared__ uint32_t smem[];
     constexpr int NT = 32 / W; // tasks per warp: a group of W lanes per task
