@@ -60,3 +60,14 @@ def test_product_does_not_import_oracle():
                     or "import" not in src or "from oracle" not in src, f
                 assert "from oracle" not in src and "import oracle" not in src and "refbind" not in src, f
                 assert "pgemu" not in src and "pgshim" not in src and "pg_shim_names" not in src, f
+
+
+def test_read_length_limit_is_the_same_everywhere(built):
+    """PG_MAX_READ_LEN of the header, of the Python binding, of the device source and of the version string agree."""
+    from paragraph_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "pg_align.h")).read()
+    core = open(os.path.join(ROOT, "paragraph_b200", "csrc", "pg_core.cuh")).read()
+    h = int(re.search(r"#define\s+PG_MAX_READ_LEN\s+(\d+)", hdr).group(1))
+    c = int(re.search(r"constexpr int MAX_READ_LEN = (\d+);", core).group(1))
+    assert h == c == capi.MAX_READ_LEN
+    assert ("reads<=%d" % h).encode() in capi.load().pg_version()
