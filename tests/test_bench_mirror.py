@@ -31,3 +31,13 @@ def test_bench_mirror_modes_over_the_emulated_abi(tmp_path):
     assert out["sharded"]["kept"] == out["pipeline"]["kept"]
     assert out["sharded"]["node_rows"] == out["pipeline"]["node_rows"] > 0
     assert out["sharded"]["devices"] == 2
+
+
+def test_bench_reads_the_config2_step_profile():
+    """bench.py's roofline takes its instruction counts from the newest committed ncu capture of the BENCHMARK workload
+    (profiles/r<round><state>_step_ncu.json), never from a capture of another shape (r..._config4_step_ncu.json)."""
+    import bench
+    prof = bench.step_profile()
+    assert prof is not None and "config4" not in prof["source"]
+    assert "config 2" in (prof["what"] or "")
+    assert prof["fill_launches"] == 3 and prof["fill_alu_inst"] > 1e8 and prof["fill_dram_bytes"] > 1e8
